@@ -1,0 +1,163 @@
+"""ctypes view of oracle/libsvo_oracle.so — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module (see oracle/svo_oracle.c).
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+MAX_LEVELS = 16
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4")])
+
+
+class Pyramid(C.Structure):
+    _fields_ = [("nlevels", C.c_int), ("w", C.c_int * MAX_LEVELS), ("h", C.c_int * MAX_LEVELS),
+                ("scale", C.c_float * MAX_LEVELS),
+                ("img", C.POINTER(C.c_uint8) * MAX_LEVELS), ("blur", C.POINTER(C.c_uint8) * MAX_LEVELS)]
+
+    def level(self, l, blurred=False):
+        p = (self.blur if blurred else self.img)[l]
+        return np.ctypeslib.as_array(p, shape=(self.h[l], self.w[l])).copy()
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libsvo_oracle.so")
+    if force or not os.path.exists(so):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.svo_o_fast_atan2.restype = C.c_float
+        _LIB.svo_o_fast_atan2.argtypes = [C.c_float, C.c_float]
+    return _LIB
+
+
+def _p(a, t=C.c_void_p):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+def geometry(W, H, nlevels=8, scale=1.2, nfeatures=500):
+    lw = np.zeros(nlevels, np.int32); lh = np.zeros(nlevels, np.int32)
+    ls = np.zeros(nlevels, np.float32); q = np.zeros(nlevels, np.int32)
+    lib().svo_o_geometry(W, H, nlevels, C.c_float(scale), nfeatures, _p(lw), _p(lh), _p(ls), _p(q))
+    return lw, lh, ls, q
+
+
+def resize(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().svo_o_resize(_p(src), src.shape[1], src.shape[0], src.shape[1], _p(dst), dw, dh, dw)
+    return dst
+
+
+def fast_nms(img, threshold=20, border=31):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = ((w + 1) // 2) * ((h + 1) // 2)
+    xs = np.empty(cap, np.int32); ys = np.empty(cap, np.int32); sc = np.empty(cap, np.int32)
+    n = lib().svo_o_fast_nms(_p(img), w, h, w, threshold, border, _p(xs), _p(ys), _p(sc), cap)
+    return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+
+def retain_best(resp, n_points):
+    resp = np.array(resp, np.float32)
+    idx = np.arange(resp.size, dtype=np.int32)
+    k = lib().svo_o_retain_best(_p(resp), _p(idx), resp.size, n_points)
+    return idx[:k].copy(), resp[:k].copy()
+
+
+def harris(img, xs, ys):
+    img = np.ascontiguousarray(img, np.uint8)
+    xs = np.ascontiguousarray(xs, np.int32); ys = np.ascontiguousarray(ys, np.int32)
+    r = np.empty(xs.size, np.float32)
+    lib().svo_o_harris(_p(img), img.shape[1], _p(xs), _p(ys), xs.size, _p(r))
+    return r
+
+
+def ic_angle(img, xs, ys):
+    img = np.ascontiguousarray(img, np.uint8)
+    xs = np.ascontiguousarray(xs, np.int32); ys = np.ascontiguousarray(ys, np.int32)
+    r = np.empty(xs.size, np.float32)
+    lib().svo_o_ic_angle(_p(img), img.shape[1], _p(xs), _p(ys), xs.size, _p(r))
+    return r
+
+
+def blur7(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty_like(img)
+    lib().svo_o_blur7(_p(img), img.shape[1], img.shape[0], img.shape[1], _p(out), img.shape[1])
+    return out
+
+
+def orb(gray, nfeatures=500, scale=1.2, nlevels=8, fast_threshold=20, with_pyramid=False):
+    """cv::ORB::detectAndCompute restatement -> (keypoints[KP_DTYPE], descriptors[n,32], Pyramid|None)."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    H, W = gray.shape
+    cap = 4 * nfeatures + 4096
+    kps = np.zeros(cap, KP_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    pyr = Pyramid() if with_pyramid else None
+    n = lib().svo_o_orb(_p(gray), W, H, W, nfeatures, C.c_float(scale), nlevels, fast_threshold,
+                        _p(kps), _p(desc), cap, C.byref(pyr) if pyr is not None else None)
+    assert 0 <= n <= cap, n
+    return kps[:n].copy(), desc[:n].copy(), pyr
+
+
+def pyramid_free(pyr):
+    lib().svo_o_pyramid_free(C.byref(pyr))
+
+
+def hamming(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return lib().svo_o_hamming(_p(a), _p(b))
+
+
+def match_bf(q, t):
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+    idx = np.empty(len(q), np.int32); dist = np.empty(len(q), np.int32); keep = np.empty(len(q), np.uint8)
+    lib().svo_o_match_bf(_p(q), len(q), _p(t), len(t), _p(idx), _p(dist), _p(keep))
+    return idx, dist, keep
+
+
+def match_greedy(rows, cur, mode, claimed=None, row_live=None, row_base=0, claim_row=None,
+                 win_uvr=None, cur_xy=None):
+    rows = np.ascontiguousarray(rows, np.uint8).reshape(-1, 32); cur = np.ascontiguousarray(cur, np.uint8).reshape(-1, 32)
+    M, N = len(rows), len(cur)
+    claimed = np.zeros(N, np.uint8) if claimed is None else np.ascontiguousarray(claimed, np.uint8).copy()
+    claim_row = np.full(N, -1, np.int32) if claim_row is None else np.ascontiguousarray(claim_row, np.int32).copy()
+    if row_live is not None:
+        row_live = np.ascontiguousarray(row_live, np.uint8)
+    if win_uvr is not None:
+        win_uvr = np.ascontiguousarray(win_uvr, np.float32); cur_xy = np.ascontiguousarray(cur_xy, np.float32)
+    bi = np.empty(M, np.int32); b = np.empty(M, np.int32); s = np.empty(M, np.int32); rc = np.empty(M, np.uint8)
+    lib().svo_o_match_greedy(_p(rows), M, _p(cur), N, mode, _p(row_live), _p(claimed), _p(claim_row), row_base,
+                             _p(bi), _p(b), _p(s), _p(rc), _p(win_uvr), _p(cur_xy))
+    return dict(best_idx=bi, best=b, second=s, row_claimed=rc, claimed=claimed, claim_row=claim_row)
+
+
+def disp2depth(disp, bf):
+    disp = np.ascontiguousarray(disp, np.float32)
+    out = np.empty_like(disp)
+    lib().svo_o_disp2depth(_p(disp), _p(out), C.c_size_t(disp.size), C.c_float(bf))
+    return out
+
+
+def stereo_sparse(kl, dl, pl, kr, dr, pr, bf, b):
+    kl = np.ascontiguousarray(kl); kr = np.ascontiguousarray(kr)
+    dl = np.ascontiguousarray(dl, np.uint8); dr = np.ascontiguousarray(dr, np.uint8)
+    n = len(kl)
+    ur = np.empty(n, np.float32); dep = np.empty(n, np.float32)
+    mr = np.empty(n, np.int32); sad = np.empty(n, np.int32)
+    lib().svo_o_stereo_sparse(_p(kl), _p(dl), n, _p(kr), _p(dr), len(kr), C.byref(pl), C.byref(pr),
+                              C.c_float(bf), C.c_float(b), _p(ur), _p(dep), _p(mr), _p(sad))
+    return ur, dep, mr, sad

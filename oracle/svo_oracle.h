@@ -1,0 +1,60 @@
+/* svo_oracle.h — C interface of the CPU oracle (test infrastructure only;
+ * see the header of svo_oracle.c for scope and reference citations). */
+#ifndef SVO_ORACLE_H
+#define SVO_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVO_O_MAX_LEVELS 16
+
+/* cv::KeyPoint minus class_id (always -1): src/frame.cc:78 fills vector<cv::KeyPoint> */
+typedef struct {
+    float x, y, size, angle, response;
+    int32_t octave;
+} svo_o_keypoint;
+
+typedef struct {
+    int nlevels;
+    int w[SVO_O_MAX_LEVELS], h[SVO_O_MAX_LEVELS];
+    float scale[SVO_O_MAX_LEVELS];
+    uint8_t *img[SVO_O_MAX_LEVELS];  /* un-blurred levels, stride == w */
+    uint8_t *blur[SVO_O_MAX_LEVELS]; /* 7x7 sigma-2 blurred levels      */
+} svo_o_pyramid;
+
+void svo_o_geometry(int W, int H, int nlevels, float scale_factor, int nfeatures,
+                    int *lw, int *lh, float *lscale, int *quota);
+void svo_o_resize_coeffs(int src, int dst, int *ofs, int *w1);
+void svo_o_resize(const uint8_t *src, int sw, int sh, int sstride, uint8_t *dst, int dw, int dh, int dstride);
+int svo_o_fast_score(const uint8_t *p, int stride);
+int svo_o_fast_nms(const uint8_t *img, int w, int h, int stride, int threshold, int border,
+                   int32_t *xs, int32_t *ys, int32_t *scores, int cap);
+/* KeyPointsFilter::retainBest replay (retain_best.cpp): permutes resp/idx in place, returns kept count */
+int svo_o_retain_best(float *resp, int32_t *idx, int n, int n_points);
+void svo_o_harris(const uint8_t *img, int stride, const int32_t *xs, const int32_t *ys, int n, float *resp);
+float svo_o_fast_atan2(float y, float x);
+void svo_o_ic_angle(const uint8_t *img, int stride, const int32_t *xs, const int32_t *ys, int n, float *angle);
+void svo_o_blur7(const uint8_t *src, int w, int h, int sstride, uint8_t *dst, int dstride);
+void svo_o_brief(const uint8_t *blur, int stride, int cx, int cy, float angle_deg, uint8_t *desc);
+int svo_o_orb(const uint8_t *gray, int W, int H, int stride, int nfeatures, float scale_factor,
+              int nlevels, int fast_threshold, svo_o_keypoint *kps, uint8_t *desc, int cap,
+              svo_o_pyramid *pyr_out);
+void svo_o_pyramid_free(svo_o_pyramid *p);
+
+int svo_o_hamming(const uint8_t *a, const uint8_t *b);
+void svo_o_match_bf(const uint8_t *q, int nq, const uint8_t *t, int nt, int32_t *idx, int32_t *dist, uint8_t *keep);
+void svo_o_match_greedy(const uint8_t *rows, int M, const uint8_t *cur, int N, int mode,
+                        const uint8_t *row_live, uint8_t *claimed, int32_t *claim_row, int row_base,
+                        int32_t *best_idx, int32_t *best, int32_t *second, uint8_t *row_claimed,
+                        const float *win_uvr, const float *cur_xy);
+void svo_o_disp2depth(const float *disp, float *depth, size_t n, float bf);
+int svo_o_stereo_sparse(const svo_o_keypoint *kl, const uint8_t *dl, int nl,
+                        const svo_o_keypoint *kr, const uint8_t *dr, int nr,
+                        const svo_o_pyramid *pl, const svo_o_pyramid *pr,
+                        float bf, float b, float *u_right, float *depth, int32_t *match_r, int32_t *sad);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,87 @@
+"""Oracle matchers vs literal pure-Python transcriptions of the reference loops
+(src/pnpmatch.cc:14-30, :75-95/:99-153 pass 1, :173-197 pass 2) on small cases."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+
+def ham(a, b):
+    return int(np.unpackbits(a ^ b).sum())
+
+
+def ref_greedy(rows, cur, mode, claimed):
+    """Transcription of the inner/outer loops; returns per-row (idx, best, second, took)."""
+    claimed = claimed.copy()
+    out = []
+    for i in range(len(rows)):
+        best, second, idx = 256, 256, -1
+        for j in range(len(cur)):
+            if claimed[j]:
+                continue
+            d = ham(rows[i], cur[j])
+            if d < best:
+                second, best, idx = best, d, j
+        if mode == 0:
+            take = best < 15
+        else:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                take = best < 30 and np.float32(second) / np.float32(best) > 2
+        take = bool(take) and idx >= 0
+        if take:
+            claimed[idx] = 1
+        out.append((idx, best, second, take))
+    return out, claimed
+
+
+def make_case(rng, M, N, flip_ps=(0.0, 0.01, 0.03, 0.08, 0.2)):
+    cur = rng.integers(0, 256, (N, 32), dtype=np.uint8)
+    rows = np.empty((M, 32), np.uint8)
+    for i in range(M):
+        src = cur[rng.integers(0, N)]
+        p = flip_ps[rng.integers(0, len(flip_ps))]
+        flips = np.packbits(rng.random(256) < p, bitorder="little")
+        rows[i] = src ^ flips
+    return rows, cur
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_greedy_matches_transcription(mode, seed):
+    rng = np.random.default_rng(seed)
+    rows, cur = make_case(rng, 70, 50)
+    cur[10] = cur[11]                      # exact duplicate columns: first-min tie-break
+    claimed0 = (rng.random(50) < 0.1).astype(np.uint8)
+    ref, claimed_ref = ref_greedy(rows, cur, mode, claimed0)
+    got = O.match_greedy(rows, cur, mode, claimed=claimed0)
+    assert [r[0] for r in ref] == list(got["best_idx"])
+    assert [r[1] for r in ref] == list(got["best"])
+    assert [r[2] for r in ref] == list(got["second"])
+    assert [int(r[3]) for r in ref] == list(got["row_claimed"])
+    assert (claimed_ref == got["claimed"]).all()
+
+
+def test_hamming_swar_equals_popcount():
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 256, (200, 32), dtype=np.uint8)
+    b = rng.integers(0, 256, (200, 32), dtype=np.uint8)
+    for x, y in zip(a, b):
+        assert O.hamming(x, y) == ham(x, y)
+    assert O.hamming(a[0], a[0]) == 0
+    assert O.hamming(np.zeros(32, np.uint8), np.full(32, 255, np.uint8)) == 256
+
+
+def test_greedy_empty_and_all_claimed():
+    rng = np.random.default_rng(4)
+    rows, cur = make_case(rng, 5, 8)
+    got = O.match_greedy(rows, cur, 1, claimed=np.ones(8, np.uint8))
+    assert (got["best_idx"] == -1).all() and (got["best"] == 256).all() and not got["row_claimed"].any()
+    got = O.match_greedy(rows[:0], cur, 0)
+    assert len(got["best_idx"]) == 0
+
+
+def test_disp2depth():
+    d = np.array([0.0, -1.0, 2.0, 0.5], np.float32)
+    z = O.disp2depth(d, 379.8145)
+    assert z[0] == -1.0 and z[1] == np.float32(379.8145) / np.float32(-1.0)
+    assert z[2] == np.float32(379.8145) / np.float32(2.0)

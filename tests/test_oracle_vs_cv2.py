@@ -1,0 +1,47 @@
+"""Pin the oracle against the live OpenCV in this container (skipped where cv2 is absent)."""
+import numpy as np
+import pytest
+
+cv2 = pytest.importorskip("cv2")
+import synth  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+
+def cv_orb(img, nf):
+    cv2.setUseOptimized(False)
+    kp, desc = cv2.ORB_create(nfeatures=nf, scaleFactor=1.2, nlevels=8).detectAndCompute(img, None)
+    return np.array([(p.pt[0], p.pt[1], p.size, p.angle, p.response, p.octave) for p in kp], dtype=O.KP_DTYPE), desc
+
+
+@pytest.mark.parametrize("shape,seed,nf", [(synth.K_SHAPE, 2, 2000), (synth.K_SHAPE, 3, 500), (synth.K_SHAPE, 4, 4000),
+                                           ((203, 317), 5, 300), (synth.H_SHAPE, 6, 8000)])
+def test_orb_equals_cv2(shape, seed, nf):
+    img = synth.texture(shape, seed)
+    ref, rdesc = cv_orb(img, nf)
+    kp, desc, _ = O.orb(img, nf)
+    assert len(kp) == len(ref)
+    for f in ("x", "y", "size", "angle", "response"):
+        assert (kp[f].view(np.uint32) == ref[f].view(np.uint32)).all(), f
+    assert (kp["octave"] == ref["octave"]).all()
+    assert (desc == rdesc).all()
+
+
+def test_pyramid_chain_equals_cv2_resize():
+    img = synth.texture(synth.K_SHAPE, 9)
+    lw, lh, _, _ = O.geometry(img.shape[1], img.shape[0], 8, 1.2, 2000)
+    a = b = img
+    for l in range(1, 8):
+        a = cv2.resize(a, (int(lw[l]), int(lh[l])), interpolation=cv2.INTER_LINEAR_EXACT)
+        b = O.resize(b, int(lw[l]), int(lh[l]))
+        assert (a == b).all(), l
+
+
+def test_sequence_frames_equal_cv2():
+    seq = synth.Sequence(seed=0)
+    for t in (0, 17):
+        L, R = seq.frame(t)
+        for img in (L, R):
+            ref, rdesc = cv_orb(img, 2000)
+            kp, desc, _ = O.orb(img, 2000)
+            assert len(kp) == len(ref) and (desc == rdesc).all()
+            assert (kp["x"] == ref["x"]).all() and (kp["angle"].view(np.uint32) == ref["angle"].view(np.uint32)).all()
