@@ -1,0 +1,218 @@
+/*
+ * svo_b200.h — C ABI of libsvo_b200.so: the per-frame stereo front-end of
+ * zssjh/stereo-semantic-vo as hand-written sm_100a CUDA.
+ *
+ * Plain pointers and sizes only; no cv:: / torch types.  The style follows the
+ * reference's own precedent for a dlopen'ed C-ABI GPU plugin
+ * (include/YOLOv3SE.h:61-64,208-232): opaque handle, caller-allocated result
+ * arrays with a capacity, functions return a count or a negative status.
+ *
+ * Every entry point cites the reference interface it replaces (paths relative
+ * to the reference root).  There is NO CPU fallback: every call fails with
+ * SVO_E_CUDA when no sm_100 device / kernel image is available.
+ *
+ * Threading: one svo_ctx per host thread (not thread-safe), no process globals
+ * (contrast src/Tracking.cc:19-20, src/pnpmatch.cc:13).
+ */
+#ifndef SVO_B200_H
+#define SVO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVO_OK 0
+#define SVO_E_INVALID (-1)   /* bad argument                                   */
+#define SVO_E_CUDA (-2)      /* CUDA error (see svo_last_error)                */
+#define SVO_E_CAPACITY (-3)  /* an internal or caller capacity was exceeded    */
+#define SVO_E_NOMEM (-4)
+
+#define SVO_MAX_LEVELS 8
+#define SVO_CAM_LEFT 0
+#define SVO_CAM_RIGHT 1
+
+/* greedy matcher modes (src/pnpmatch.cc) */
+#define SVO_GREEDY_PASS1 0 /* :61-156  claim iff best < 15 (and not vetoed)                       */
+#define SVO_GREEDY_PASS2 1 /* :160-199 claim iff best < 30 && (float)second/(float)best > 2       */
+
+typedef struct svo_ctx svo_ctx;
+
+/* cv::KeyPoint as filled by cv::ORB (src/frame.cc:78) minus class_id (always -1). */
+typedef struct svo_keypoint {
+    float x, y;     /* pt, level-0 pixel units                     */
+    float size;     /* 31 * scale[octave]                          */
+    float angle;    /* degrees, [0,360)                            */
+    float response; /* Harris response                             */
+    int32_t octave;
+} svo_keypoint;
+
+typedef struct svo_config {
+    int device;          /* CUDA device ordinal                                                   */
+    int width, height;   /* image size this context is built for                                  */
+    int nfeatures;       /* ORBextractor.nFeatures (Stereo/KITTI00-02.yaml:38; frame.cc:77 uses 500) */
+    int nlevels;         /* <= SVO_MAX_LEVELS                                                     */
+    float scale_factor;  /* 1.2f                                                                  */
+    int fast_threshold;  /* 20                                                                    */
+    int max_batch;       /* stereo frames per svo_batch_submit (>= 1)                             */
+    int lanes;           /* independent pipeline lanes (stream + buffers each), >= 1              */
+    int max_rows;        /* capacity of one greedy row set / BF train set (e.g. 5000-row local map)*/
+    void *stream;        /* optional cudaStream_t for lane 0 (NULL: the context creates its own)  */
+} svo_config;
+
+void svo_default_config(svo_config *cfg);
+const char *svo_version(void);
+
+/* Replaces `new frame(...)`'s per-frame allocations (src/frame.cc:36-64) with one
+ * up-front allocation of every device buffer, stream and graph. */
+int svo_create(const svo_config *cfg, svo_ctx **out);
+void svo_destroy(svo_ctx *ctx);
+const char *svo_last_error(const svo_ctx *ctx);
+
+/* Level geometry and per-level feature quotas (cv::ORB internals). */
+int svo_get_geometry(const svo_ctx *ctx, int *lw, int *lh, float *lscale, int *quota);
+
+/* ---------------------------------------------------------------------------
+ * Synchronous single-call drop-ins (host buffers in, host buffers out).
+ * ------------------------------------------------------------------------- */
+
+/* frame::featuredetect (src/frame.cc:75-79) == cv::ORB::detectAndCompute.
+ * gray: w x h 8-bit, `stride` bytes per row.  Writes up to `cap` keypoints (cv2's
+ * exact output order) and cap x 32 descriptor bytes; returns the number of
+ * keypoints found (may exceed nfeatures on response ties) or a negative status.
+ * The pyramid/keypoints of `cam` stay resident for svo_stereo_sparse. */
+int svo_extract(svo_ctx *ctx, int cam, const uint8_t *gray, int stride, int w, int h,
+                svo_keypoint *kp_out, uint8_t *desc_out, int cap);
+
+/* north_star's ComputeStereoMatches stage: fills what frame::computekeypoint_r and
+ * frame::disp2Depth deliver at keypoint pixels (src/frame.cc:122-164): u_right[i]
+ * (keypoints_r[i].x) and depth[i] (depthimg at the keypoint), -1 where unmatched.
+ * Row-band Hamming + 11x11 SAD + parabola, on the LEFT and
+ * RIGHT images last given to svo_extract.  match_r / sad may be NULL.
+ * Returns the number of left keypoints. */
+int svo_stereo_sparse(svo_ctx *ctx, float bf, float baseline, float *u_right, float *depth,
+                      int32_t *match_r, int32_t *sad, int cap);
+
+/* cv::BFMatcher(NORM_HAMMING).match + the distance filter of find_feature_matches
+ * (src/pnpmatch.cc:266,278,281-299).  q: nq x 32, t: nt x 32.  Per query: first
+ * minimum train index, integer distance, keep = dist <= max(2*min_dist, 30). */
+int svo_match_bf(svo_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt,
+                 int32_t *idx, int32_t *dist, uint8_t *keep);
+
+/* The "dynamic" veto of pass 1 (src/pnpmatch.cc:103-137): a would-be match whose current
+ * keypoint lies inside an offline YOLO box (+-10 px) and whose f64 epipolar distance under
+ * F exceeds 0.1 marks the map point bad instead of claiming. */
+typedef struct svo_veto {
+    const int32_t *boxes; /* n_boxes x 4: left, right, top, bottom (main.cpp:59-97)        */
+    int n_boxes;
+    const double *F;      /* 3x3 row-major fundamental matrix (src/pnpmatch.cc:336)        */
+    const float *row_xy;  /* 2 x M: LastFrame.keypoints_l[i].pt                            */
+    const float *cur_xy;  /* 2 x N: CurrentFrame->keypoints_l[j].pt                        */
+} svo_veto;
+
+/* The sequential greedy scans of pnpmatch::poseEstimationPnP
+ * (src/pnpmatch.cc:75-95 pass 1, :173-190 pass 2) with their accept rules.
+ *   rows: M x 32 map-point descriptors in scan order; cur: N x 32 (f_descriptor)
+ *   row_live[M] (NULL = all): 0 skips a row (no live map point, :66 / :165-172)
+ *   claimed[N]  in/out: CurrentFrame->MapPoints[j] != NULL
+ *   claim_row[N] in/out (may be NULL): row_base + i for the row that claimed j
+ *   best_idx/best/second[M] (may be NULL): exact (bestIdx2, bestDist, secondBestDist)
+ *   row_claimed[M] (may be NULL): 1 where the row claimed its best column
+ *   win_uvr (3 x M) + cur_xy (2 x N): optional projection window |du|,|dv| <= r;
+ *   NULL reproduces the reference (brute force over all columns).
+ *   veto (pass 1 only, may be NULL) + row_bad[M] out: rows whose map point turns bad. */
+int svo_match_greedy(svo_ctx *ctx, const uint8_t *rows, int M, const uint8_t *cur, int N, int mode,
+                     const uint8_t *row_live, uint8_t *claimed, int32_t *claim_row, int row_base,
+                     int32_t *best_idx, int32_t *best, int32_t *second, uint8_t *row_claimed,
+                     const float *win_uvr, const float *cur_xy,
+                     const svo_veto *veto, uint8_t *row_bad);
+
+/* frame::disp2Depth (src/frame.cc:140-164): depth = bf/disp where disp != 0 else -1. */
+int svo_disp2depth(svo_ctx *ctx, const float *disp, float *depth, size_t n, float bf);
+
+/* ---------------------------------------------------------------------------
+ * Batched, pipelined front-end: what Tracking::Track runs per stereo pair
+ * (src/Tracking.cc:225-231): extract L+R, sparse stereo, BF match against the
+ * previous frame, greedy pass 1 (previous frame's map points) and pass 2
+ * (local map).  Inputs may be host (ideally pinned) or device pointers.
+ * Results land in a context-owned pinned arena: one D2H copy per batch.
+ * ------------------------------------------------------------------------- */
+typedef struct svo_frame_in {
+    const uint8_t *left, *right; /* width x height gray                                   */
+    int stride;                  /* bytes per row                                         */
+    float bf, baseline;          /* Camera.bf and bf/fx (Stereo/KITTI04-12.yaml:25)       */
+    const uint8_t *prev_desc;    /* n_prev x 32: last frame's f_descriptor (BF train set  */
+    int n_prev;                  /*   and pass-1 rows); NULL/0 skips both                 */
+    const uint8_t *prev_live;    /* n_prev: 1 where LastFrame.MapPoints[i] is live; NULL=all */
+    const uint8_t *map_desc;     /* n_map x 32 local-map descriptors in scan order        */
+    int n_map;                   /*   NULL/0 skips pass 2                                 */
+    const int32_t *map_prev_row; /* n_map (may be NULL): index of the pass-1 row holding the
+                                    same map point, -1 if none; such rows are skipped in pass 2
+                                    when pass 1 claimed them (observations.count, :167)   */
+} svo_frame_in;
+
+typedef struct svo_frame_out {
+    int32_t status;              /* SVO_OK or a negative status for this frame            */
+    int32_t n_left, n_right;     /* keypoints found                                       */
+    int32_t n_stereo;            /* left keypoints with depth > 0                         */
+    const svo_keypoint *kp_left, *kp_right;
+    const uint8_t *desc_left, *desc_right;       /* n x 32                                */
+    const float *u_right, *depth;                /* n_left                                */
+    const int32_t *bf_idx, *bf_dist;             /* n_left (query = current frame)        */
+    const uint8_t *bf_keep;                      /* n_left                                */
+    const int32_t *p1_best_idx, *p1_best, *p1_second; /* n_prev; match_score = second/best */
+    const uint8_t *p1_row_claimed;               /* n_prev                                */
+    const uint8_t *p2_row_claimed;               /* n_map                                 */
+    const int32_t *claim_row;                    /* n_left: row that claimed column j     */
+                                                 /* (0..n_prev-1 pass 1, n_prev+i pass 2), -1 = free */
+} svo_frame_out;
+
+/* Enqueue H2D + all kernels + one D2H for `n` frames on `lane`; returns at once. */
+int svo_batch_submit(svo_ctx *ctx, int lane, const svo_frame_in *frames, int n);
+/* Block until the lane's batch is complete. */
+int svo_batch_wait(svo_ctx *ctx, int lane);
+/* View of frame `i` of the lane's last batch (valid until the lane's next submit). */
+int svo_batch_result(svo_ctx *ctx, int lane, int i, svo_frame_out *out);
+
+/* Pinned host / device memory helpers for callers that want zero staging. */
+void *svo_alloc_pinned(svo_ctx *ctx, size_t bytes);
+void svo_free_pinned(svo_ctx *ctx, void *p);
+void *svo_alloc_device(svo_ctx *ctx, size_t bytes);
+void svo_free_device(svo_ctx *ctx, void *p);
+int svo_copy_to_device(svo_ctx *ctx, void *dst, const void *src, size_t bytes);
+
+/* Kernel launches issued by this context so far (bench.py's gpu_launches). */
+long long svo_launch_count(const svo_ctx *ctx);
+/* Device times (ms) of the lane's last batch, measured with CUDA events on the lane's own
+ * stream (profiling must be on): ms[0] whole batch (H2D..D2H), [1] H2D, [2] pyramid,
+ * [3] FAST, [4] first cull, [5] Harris, [6] second cull, [7] blur, [8] orient+BRIEF,
+ * [9] stereo, [10] matching, [11] D2H.  Writes min(n, 12) values. */
+int svo_batch_stage_ms(svo_ctx *ctx, int lane, float *ms, int n);
+/* Turn per-stage event recording on (1) or off (0, default). */
+int svo_set_profiling(svo_ctx *ctx, int on);
+void *svo_lane_stream(svo_ctx *ctx, int lane);
+
+/* ---------------------------------------------------------------------------
+ * Stage taps for the parity tests (device -> host copies of intermediate state
+ * of the image last extracted on `cam`).
+ * ------------------------------------------------------------------------- */
+#define SVO_TAP_LEVEL 0      /* u8 level image, w*h bytes (tight)              */
+#define SVO_TAP_BLUR 1       /* u8 blurred level                               */
+#define SVO_TAP_FAST 2       /* int32 triples (x, y, score), raster order      */
+#define SVO_TAP_SELECT1 3    /* int32 triples after the first retainBest       */
+#define SVO_TAP_SELECT2 4    /* int32 triples (x, y, response bits) after the second retainBest */
+/* Returns the number of elements written (bytes for images) or a negative status. */
+long long svo_debug_tap(svo_ctx *ctx, int cam, int what, int level, void *out, size_t cap_bytes);
+
+/* Runs the on-device retainBest replay (std::nth_element + std::partition order) on a
+ * bare response array: idx_out receives the kept original indices in order; returns the
+ * kept count.  depth_limit < 0 uses 2*floor(log2(n)) like libstdc++. */
+int svo_debug_retain_best(svo_ctx *ctx, const float *resp, int n, int n_points, int depth_limit,
+                          int32_t *idx_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVO_B200_H */

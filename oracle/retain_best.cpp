@@ -27,3 +27,17 @@ extern "C" int svo_o_retain_best(float* resp, int32_t* idx, int n, int n_points)
     for (int i = 0; i < n; ++i) { resp[i] = v[i].response; idx[i] = v[i].idx; }
     return kept;
 }
+
+// Test shims: call libstdc++'s own internals so the GPU replay can be checked
+// on forced depth limits (heap-select fallback) and on bare key arrays.
+extern "C" void svo_o_introselect(float* resp, int32_t* idx, int n, int nth, int depth_limit)
+{
+    std::vector<Item> v(n);
+    for (int i = 0; i < n; ++i) v[i] = Item{resp[i], idx[i]};
+    if (n > 0 && nth < n) {
+        if (depth_limit < 0) depth_limit = std::__lg(n) * 2;
+        std::__introselect(v.begin(), v.begin() + nth, v.end(), depth_limit,
+                           __gnu_cxx::__ops::__iter_comp_iter(Greater()));
+    }
+    for (int i = 0; i < n; ++i) { resp[i] = v[i].response; idx[i] = v[i].idx; }
+}

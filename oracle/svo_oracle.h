@@ -33,6 +33,7 @@ int svo_o_fast_nms(const uint8_t *img, int w, int h, int stride, int threshold, 
                    int32_t *xs, int32_t *ys, int32_t *scores, int cap);
 /* KeyPointsFilter::retainBest replay (retain_best.cpp): permutes resp/idx in place, returns kept count */
 int svo_o_retain_best(float *resp, int32_t *idx, int n, int n_points);
+void svo_o_introselect(float *resp, int32_t *idx, int n, int nth, int depth_limit);
 void svo_o_harris(const uint8_t *img, int stride, const int32_t *xs, const int32_t *ys, int n, float *resp);
 float svo_o_fast_atan2(float y, float x);
 void svo_o_ic_angle(const uint8_t *img, int stride, const int32_t *xs, const int32_t *ys, int n, float *angle);

@@ -1,0 +1,470 @@
+// match.cu — 256-bit Hamming matching: BFMatcher 1-NN (src/pnpmatch.cc:266,278-299), the two
+// sequential greedy scans of pnpmatch::poseEstimationPnP (src/pnpmatch.cc:75-95 + :99-153,
+// :173-197) and frame::disp2Depth (src/frame.cc:140-164).  SURVEY.md Appendix B.
+//
+// Distance = popc(xor) over two uint4 halves of a 32-byte descriptor row (pnpmatch.cc:14-30).
+// Column descriptors are staged in shared memory in tiles of 992 rows, 16-byte units swizzled
+// so that both lane-strided and lane-blocked 128-bit reads are bank-conflict free; the row
+// descriptor lives in registers.  Minima are reduced with redux.sync on (dist << 16 | col)
+// keys, which yields "first minimum wins" for free.
+//
+// The greedy scans are sequentially dependent (a claim hides a column from every later
+// row).  Exact parallel form:
+//   1. k_shortlist : all row x column distances; per row the ascending-column list of
+//                    columns with d < T (T = 15 pass 1, 60 pass 2 — beyond T a column can
+//                    neither be claimed nor break the ratio test).
+//   2. k_resolve   : one warp per frame walks the non-empty rows in order and applies the
+//                    reference's accept rule against the live claim set (rows whose list
+//                    overflowed are re-scanned exhaustively), recording claim times.
+//   3. k_scores    : exact (bestIdx, bestDist, secondBestDist) per row, in parallel, by
+//                    replaying each row against the columns not claimed before it.
+#include "svo_internal.cuh"
+#include <limits.h>
+
+#define COL_TILE 992          // 31 columns per lane
+#define COLS_PER_LANE 31
+#define M_THREADS 256
+#define M_WARPS (M_THREADS / 32)
+
+__device__ __forceinline__ int unit_of(int j, int h) { return 2 * j + (h ^ ((j >> 2) & 1)); }
+
+__device__ __forceinline__ int set_count(const MatchSet &s, int f) { return s.count ? min(s.count[(size_t)f * s.count_stride], s.stride_rows) : s.fixed_count; }
+__device__ __forceinline__ const uint8_t *set_desc(const MatchSet &s, int f) { return s.desc + (size_t)f * s.desc_stride * 32; }
+
+// stage columns [c0, c0+nc) of a descriptor set into the swizzled shared tile
+__device__ __forceinline__ void load_tile(uint4 *tile, const uint8_t *desc, int c0, int nc)
+{
+    const uint4 *src = reinterpret_cast<const uint4 *>(desc) + (size_t)c0 * 2;
+    for (int i = threadIdx.x; i < nc * 2; i += blockDim.x) {
+        const int j = i >> 1, h = i & 1;
+        tile[unit_of(j, h)] = src[i];
+    }
+}
+
+struct Row { uint4 a, b; };
+__device__ __forceinline__ Row load_row(const uint8_t *desc, int r)
+{
+    const uint4 *p = reinterpret_cast<const uint4 *>(desc) + (size_t)r * 2;
+    Row R; R.a = p[0]; R.b = p[1];
+    return R;
+}
+__device__ __forceinline__ int ham(const Row &R, const uint4 *tile, int j)
+{
+    const uint4 x = tile[unit_of(j, 0)], y = tile[unit_of(j, 1)];
+    return __popc(R.a.x ^ x.x) + __popc(R.a.y ^ x.y) + __popc(R.a.z ^ x.z) + __popc(R.a.w ^ x.w) +
+           __popc(R.b.x ^ y.x) + __popc(R.b.y ^ y.y) + __popc(R.b.z ^ y.z) + __popc(R.b.w ^ y.w);
+}
+__device__ __forceinline__ int ham_global(const Row &R, const uint8_t *desc, int j)
+{
+    const uint4 *p = reinterpret_cast<const uint4 *>(desc) + (size_t)j * 2;
+    const uint4 x = p[0], y = p[1];
+    return __popc(R.a.x ^ x.x) + __popc(R.a.y ^ x.y) + __popc(R.a.z ^ x.z) + __popc(R.a.w ^ x.w) +
+           __popc(R.b.x ^ y.x) + __popc(R.b.y ^ y.y) + __popc(R.b.z ^ y.z) + __popc(R.b.w ^ y.w);
+}
+
+__device__ __forceinline__ bool in_window(const float *win, const float *cxy, int j)
+{
+    if (!win) return true;
+    const float du = cxy[2 * j] - win[0], dv = cxy[2 * j + 1] - win[1], r = win[2];
+    return !(du < -r || du > r || dv < -r || dv > r);
+}
+
+// ---------------------------------------------------------------------------------------
+// BFMatcher: per query the first minimum over the train set
+// ---------------------------------------------------------------------------------------
+#define BF_ROWS_PER_WARP 4
+
+__global__ void __launch_bounds__(M_THREADS) k_bf(BfArgs a)
+{
+    __shared__ uint4 tile[COL_TILE * 2];
+    const int f = blockIdx.y;
+    const int nq = set_count(a.q, f), nt = set_count(a.t, f);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = (blockIdx.x * M_WARPS + warp) * BF_ROWS_PER_WARP;
+    if (blockIdx.x * M_WARPS * BF_ROWS_PER_WARP >= nq) return;
+    const uint8_t *qd = set_desc(a.q, f), *td = set_desc(a.t, f);
+    Row R[BF_ROWS_PER_WARP];
+    uint32_t best[BF_ROWS_PER_WARP];
+#pragma unroll
+    for (int k = 0; k < BF_ROWS_PER_WARP; ++k) {
+        best[k] = 0xffffffffu;
+        R[k] = load_row(qd, min(r0 + k, nq - 1));
+    }
+    for (int c0 = 0; c0 < nt; c0 += COL_TILE) {
+        const int nc = min(COL_TILE, nt - c0);
+        __syncthreads();
+        load_tile(tile, td, c0, nc);
+        __syncthreads();
+        for (int j = lane; j < nc; j += 32) {
+#pragma unroll
+            for (int k = 0; k < BF_ROWS_PER_WARP; ++k) {
+                const uint32_t key = ((uint32_t)ham(R[k], tile, j) << 16) | (uint32_t)(c0 + j);
+                best[k] = min(best[k], key);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < BF_ROWS_PER_WARP; ++k) {
+        const uint32_t m = __reduce_min_sync(0xffffffffu, best[k]);
+        const int r = r0 + k;
+        if (lane == 0 && r < nq) {
+            const size_t o = (size_t)f * a.q.stride_rows + r;
+            if (nt > 0) {
+                a.idx[o] = (int)(m & 0xffffu); a.dist[o] = (int)(m >> 16);
+                atomicMin(a.min_dist + f, (int)(m >> 16));
+            } else { a.idx[o] = -1; a.dist[o] = -1; }
+        }
+    }
+}
+
+// keep = dist <= max(2*min_dist, 30)   (src/pnpmatch.cc:281-299)
+__global__ void k_bf_keep(BfArgs a)
+{
+    const int f = blockIdx.y;
+    const int nq = set_count(a.q, f), nt = set_count(a.t, f);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const size_t o = (size_t)f * a.q.stride_rows + i;
+    const double thr = fmax(2.0 * (double)a.min_dist[f], 30.0);
+    a.keep[o] = (nt > 0 && (double)a.dist[o] <= thr) ? 1 : 0;
+}
+
+__global__ void k_fill_int(int *p, int n, int v)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+void launch_bf(const BfArgs &a, int nframes, cudaStream_t st, long long *launches)
+{
+    k_fill_int<<<(nframes + 255) / 256, 256, 0, st>>>(a.min_dist, nframes, 10000);
+    const int maxq = a.q.count ? a.q.stride_rows : a.q.fixed_count;
+    if (maxq > 0) {
+        dim3 grid((maxq + M_WARPS * BF_ROWS_PER_WARP - 1) / (M_WARPS * BF_ROWS_PER_WARP), nframes);
+        k_bf<<<grid, M_THREADS, 0, st>>>(a);
+        dim3 g2((maxq + 255) / 256, nframes);
+        k_bf_keep<<<g2, 256, 0, st>>>(a);
+        *launches += 2;
+    }
+    ++*launches;
+}
+
+// ---------------------------------------------------------------------------------------
+// greedy step 0: claim_time from the incoming claim mask; per-row outputs cleared
+// ---------------------------------------------------------------------------------------
+__global__ void k_greedy_init(GreedyArgs a, int reset_time)
+{
+    const int f = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = set_count(a.cols, f), M = set_count(a.rows, f);
+    if (reset_time && i < N) {
+        const size_t o = (size_t)f * a.cols.stride_rows + i;
+        a.claim_time[o] = a.claimed[o] ? INT_MIN : INT_MAX;
+    }
+    if (i < M) {
+        const size_t o = (size_t)f * a.rows.stride_rows + i;
+        a.row_claimed[o] = 0;
+        if (a.row_bad) a.row_bad[o] = 0;
+        a.short_cnt[o] = 0;
+        if (a.best_idx) { a.best_idx[o] = -1; a.best[o] = 256; a.second[o] = 256; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// greedy step 1: short lists (ascending column) of columns with d < T
+// ---------------------------------------------------------------------------------------
+#define SL_ROWS_PER_WARP 4
+
+__global__ void __launch_bounds__(M_THREADS) k_shortlist(GreedyArgs a, int T)
+{
+    __shared__ uint4 tile[COL_TILE * 2];
+    const int f = blockIdx.y;
+    const int M = set_count(a.rows, f), N = set_count(a.cols, f);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (blockIdx.x * M_WARPS * SL_ROWS_PER_WARP >= M) return;
+    const int r0 = (blockIdx.x * M_WARPS + warp) * SL_ROWS_PER_WARP;
+    const uint8_t *rd = set_desc(a.rows, f), *cd = set_desc(a.cols, f);
+    const float *cxy = a.cur_xy ? a.cur_xy + (size_t)f * a.cols.stride_rows * 2 : nullptr;
+    Row R[SL_ROWS_PER_WARP];
+    int cnt[SL_ROWS_PER_WARP];
+    bool live[SL_ROWS_PER_WARP];
+#pragma unroll
+    for (int k = 0; k < SL_ROWS_PER_WARP; ++k) {
+        const int r = r0 + k;
+        cnt[k] = 0;
+        live[k] = r < M && (!a.row_live || a.row_live[(size_t)f * a.rows.stride_rows + r]);
+        R[k] = load_row(rd, min(r, M - 1));
+    }
+    for (int c0 = 0; c0 < N; c0 += COL_TILE) {
+        const int nc = min(COL_TILE, N - c0);
+        __syncthreads();
+        load_tile(tile, cd, c0, nc);
+        __syncthreads();
+        for (int jb = 0; jb < nc; jb += 32) {
+            const int j = jb + lane;
+#pragma unroll
+            for (int k = 0; k < SL_ROWS_PER_WARP; ++k) {
+                if (!live[k]) continue;   // warp-uniform
+                const int r = r0 + k;
+                int d = 256;
+                if (j < nc) {
+                    const float *win = a.win_uvr ? a.win_uvr + ((size_t)f * a.rows.stride_rows + r) * 3 : nullptr;
+                    if (in_window(win, cxy, c0 + j)) d = ham(R[k], tile, j);
+                }
+                const bool hit = d < T;
+                const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                if (hit) {
+                    const int pos = cnt[k] + __popc(m & ((1u << lane) - 1u));
+                    if (pos < SVO_SHORT_CAP)
+                        a.shortlist[((size_t)f * a.rows.stride_rows + r) * SVO_SHORT_CAP + pos] = ((uint32_t)d << 16) | (uint32_t)(c0 + j);
+                }
+                cnt[k] += __popc(m);
+            }
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < SL_ROWS_PER_WARP; ++k)
+            if (r0 + k < M) a.short_cnt[(size_t)f * a.rows.stride_rows + r0 + k] = live[k] ? cnt[k] : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// greedy step 2: sequential resolution, one CTA per frame (warp 0 walks the rows)
+// ---------------------------------------------------------------------------------------
+extern __shared__ __align__(16) uint8_t resolve_smem[];
+
+__device__ bool veto_dynamic(const GreedyArgs &a, int f, int row, int col)
+{
+    // src/pnpmatch.cc:103-122
+    const float *cxy = a.cur_xy + ((size_t)f * a.cols.stride_rows + col) * 2;
+    const float *lxy = a.row_xy + ((size_t)f * a.rows.stride_rows + row) * 2;
+    const float cx = cxy[0], cy = cxy[1], lx = lxy[0], ly = lxy[1];
+    const double *F = a.F + (size_t)f * 9;
+    for (int k = 0; k < a.n_boxes; ++k) {
+        const int *bx = a.boxes + ((size_t)f * a.n_boxes + k) * 4;
+        const int left = bx[0], right = bx[1], top = bx[2], bottom = bx[3];
+        if (cx > left - 10 && cx < right + 10 && cy > top - 10 && cy < bottom + 10) {
+            const double A = __dadd_rn(__dadd_rn(__dmul_rn(F[0], lx), __dmul_rn(F[1], ly)), F[2]);
+            const double B = __dadd_rn(__dadd_rn(__dmul_rn(F[3], lx), __dmul_rn(F[4], ly)), F[5]);
+            const double C = __dadd_rn(__dadd_rn(__dmul_rn(F[6], lx), __dmul_rn(F[7], ly)), F[8]);
+            const double num = fabs(__dadd_rn(__dadd_rn(__dmul_rn(A, cx), __dmul_rn(B, cy)), C));
+            const double den = __dsqrt_rn(__dadd_rn(__dmul_rn(A, A), __dmul_rn(B, B)));
+            if (__ddiv_rn(num, den) > 0.1) return true;
+        }
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(M_THREADS) k_resolve(GreedyArgs a, int max_rows)
+{
+    const int f = blockIdx.x;
+    const int M = set_count(a.rows, f), N = set_count(a.cols, f);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int *rows_ne = reinterpret_cast<int *>(resolve_smem);              // non-empty live rows, ascending
+    uint8_t *claimed = resolve_smem + (size_t)max_rows * sizeof(int);  // N bytes
+    __shared__ int wcnt[M_WARPS];
+    __shared__ int n_ne;
+    const size_t ro = (size_t)f * a.rows.stride_rows, co = (size_t)f * a.cols.stride_rows;
+    for (int j = tid; j < N; j += M_THREADS) claimed[j] = a.claimed[co + j];
+
+    auto alive = [&](int r) -> bool {
+        if (r >= M) return false;
+        if (a.short_cnt[ro + r] == 0) return false;
+        if (a.map_prev_row) {
+            const int pr = a.map_prev_row[ro + r];
+            if (pr >= 0 && a.prev_row_claimed[(size_t)f * a.prev_stride + pr]) return false;
+        }
+        return true;
+    };
+    // ordered compaction of the rows that can possibly claim
+    const int seg = (((M + M_WARPS - 1) / M_WARPS) + 31) & ~31;
+    const int beg = warp * seg, end = min(beg + seg, M);
+    int c = 0;
+    for (int base = beg; base < end; base += 32) c += __popc(__ballot_sync(0xffffffffu, base + lane < end && alive(base + lane)));
+    if (lane == 0) wcnt[warp] = c;
+    __syncthreads();
+    int off = 0, tot = 0;
+    for (int w = 0; w < M_WARPS; ++w) { if (w < warp) off += wcnt[w]; tot += wcnt[w]; }
+    for (int base = beg; base < end; base += 32) {
+        const bool k = base + lane < end && alive(base + lane);
+        const uint32_t m = __ballot_sync(0xffffffffu, k);
+        if (k) rows_ne[off + __popc(m & ((1u << lane) - 1u))] = base + lane;
+        off += __popc(m);
+    }
+    if (tid == 0) n_ne = tot;
+    __syncthreads();
+    if (warp != 0) return;
+
+    const uint8_t *rd = set_desc(a.rows, f), *cd = set_desc(a.cols, f);
+    const float *cxy = a.cur_xy ? a.cur_xy + co * 2 : nullptr;
+    const int total = n_ne;
+    const int rbase = a.row_base + (a.row_base_arr ? a.row_base_arr[f] : 0);
+    uint32_t e_next = 0xffffffffu;
+    int cnt_next = 0;
+    if (total > 0) {
+        const int r = rows_ne[0];
+        cnt_next = a.short_cnt[ro + r];
+        e_next = (lane < cnt_next && lane < SVO_SHORT_CAP) ? a.shortlist[(ro + r) * SVO_SHORT_CAP + lane] : 0xffffffffu;
+    }
+    for (int it = 0; it < total; ++it) {
+        const int r = rows_ne[it];
+        const uint32_t e = e_next;
+        const int cnt = cnt_next;
+        if (it + 1 < total) {  // prefetch the next row's list while this one is resolved
+            const int rn = rows_ne[it + 1];
+            cnt_next = a.short_cnt[ro + rn];
+            e_next = (lane < cnt_next && lane < SVO_SHORT_CAP) ? a.shortlist[(ro + rn) * SVO_SHORT_CAP + lane] : 0xffffffffu;
+        }
+        int bd = 256, bi = -1, sd = 256;
+        if (cnt <= SVO_SHORT_CAP) {
+            const int col = (int)(e & 0xffffu);
+            const bool valid = lane < cnt && !claimed[col];
+            const uint32_t kmin = __reduce_min_sync(0xffffffffu, valid ? e : 0xffffffffu);
+            if (kmin != 0xffffffffu) {
+                bd = (int)(kmin >> 16); bi = (int)(kmin & 0xffffu);
+                sd = (int)__reduce_min_sync(0xffffffffu, (valid && col < bi) ? (e >> 16) : 256u);
+            }
+        } else {
+            // list overflow: exhaustive scan of this row against the live claim set
+            const Row R = load_row(rd, r);
+            const float *win = a.win_uvr ? a.win_uvr + (ro + r) * 3 : nullptr;
+            uint32_t key = 0xffffffffu;
+            for (int j = lane; j < N; j += 32)
+                if (!claimed[j] && in_window(win, cxy, j)) key = min(key, ((uint32_t)ham_global(R, cd, j) << 16) | (uint32_t)j);
+            const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
+            if (kmin != 0xffffffffu) {
+                bd = (int)(kmin >> 16); bi = (int)(kmin & 0xffffu);
+                uint32_t s = 256u;
+                for (int j = lane; j < bi; j += 32)
+                    if (!claimed[j] && in_window(win, cxy, j)) s = min(s, (uint32_t)ham_global(R, cd, j));
+                sd = (int)__reduce_min_sync(0xffffffffu, s);
+            }
+        }
+        bool take = bi >= 0 && (a.mode == SVO_GREEDY_PASS1 ? bd < 15 : (bd < 30 && sd > 2 * bd));
+        if (take && a.mode == SVO_GREEDY_PASS1 && a.n_boxes > 0 && a.F) {
+            int v = 0;
+            if (lane == 0) v = veto_dynamic(a, f, r, bi);
+            v = __shfl_sync(0xffffffffu, v, 0);
+            if (v) {
+                take = false;
+                if (lane == 0 && a.row_bad) a.row_bad[ro + r] = 1;
+            }
+        }
+        if (take) {
+            if (lane == 0) {
+                claimed[bi] = 1;
+                a.claimed[co + bi] = 1;
+                if (a.claim_row) a.claim_row[co + bi] = rbase + r;
+                a.claim_time[co + bi] = rbase + r;
+                a.row_claimed[ro + r] = 1;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// greedy step 3: exact (bestIdx, bestDist, secondBestDist) per row.  Lane l owns the
+// contiguous columns [31 l, 31 l + 31) of each tile so "second = running best before the
+// final update" composes across lanes and tiles.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(M_THREADS) k_scores(GreedyArgs a)
+{
+    __shared__ uint4 tile[COL_TILE * 2];
+    __shared__ int s_time[COL_TILE];
+    const int f = blockIdx.y;
+    const int M = set_count(a.rows, f), N = set_count(a.cols, f);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (blockIdx.x * M_WARPS >= M) return;
+    const int r = blockIdx.x * M_WARPS + warp;
+    const size_t ro = (size_t)f * a.rows.stride_rows, co = (size_t)f * a.cols.stride_rows;
+    const uint8_t *rd = set_desc(a.rows, f), *cd = set_desc(a.cols, f);
+    const float *cxy = a.cur_xy ? a.cur_xy + co * 2 : nullptr;
+    bool live = r < M && (!a.row_live || a.row_live[ro + r]);
+    if (live && a.map_prev_row) {
+        const int pr = a.map_prev_row[ro + r];
+        if (pr >= 0 && a.prev_row_claimed[(size_t)f * a.prev_stride + pr]) live = false;
+    }
+    const Row R = load_row(rd, min(r, M - 1));
+    const float *win = (a.win_uvr && r < M) ? a.win_uvr + (ro + r) * 3 : nullptr;
+    const int g = a.row_base + (a.row_base_arr ? a.row_base_arr[f] : 0) + r;
+    int bd = 256, sd = 256, bi = -1;
+    for (int c0 = 0; c0 < N; c0 += COL_TILE) {
+        const int nc = min(COL_TILE, N - c0);
+        __syncthreads();
+        load_tile(tile, cd, c0, nc);
+        for (int j = threadIdx.x; j < nc; j += M_THREADS) s_time[j] = a.claim_time[co + c0 + j];
+        __syncthreads();
+        if (!live) continue;
+        int lb = 256, ls = 256, li = -1;
+        const int jb = lane * COLS_PER_LANE;
+#pragma unroll 1
+        for (int k = 0; k < COLS_PER_LANE; ++k) {
+            const int j = jb + k;
+            if (j < nc && s_time[j] >= g && in_window(win, cxy, c0 + j)) {
+                const int d = ham(R, tile, j);
+                if (d < lb) { ls = lb; lb = d; li = c0 + j; }
+            }
+        }
+        const uint32_t key = li >= 0 ? (((uint32_t)lb << 16) | (uint32_t)(li - c0)) : 0xffffffffu;
+        const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
+        if (kmin == 0xffffffffu) continue;
+        const int tb = (int)(kmin >> 16), ti = c0 + (int)(kmin & 0xffffu);
+        const int lstar = (ti - c0) / COLS_PER_LANE;
+        const uint32_t before = __reduce_min_sync(0xffffffffu, lane < lstar ? (uint32_t)lb : 256u);
+        const int ls_star = __shfl_sync(0xffffffffu, ls, lstar);
+        const int tsec = min((int)before, ls_star);
+        if (tb < bd) { sd = min(bd, tsec); bd = tb; bi = ti; }
+    }
+    if (live && lane == 0) { a.best_idx[ro + r] = bi; a.best[ro + r] = bd; a.second[ro + r] = sd; }
+}
+
+static int g_resolve_smem_limit = 48 * 1024;
+
+int setup_match_attributes()
+{
+    g_resolve_smem_limit = 200 * 1024;
+    return (int)cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, g_resolve_smem_limit);
+}
+
+void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStream_t st, long long *launches)
+{
+    const int maxM = a.rows.count ? a.rows.stride_rows : a.rows.fixed_count;
+    const int maxN = a.cols.count ? a.cols.stride_rows : a.cols.fixed_count;
+    if (maxM <= 0 || nframes <= 0) return;
+    const int mx = maxM > maxN ? maxM : maxN;
+    dim3 gi((mx + 255) / 256, nframes);
+    k_greedy_init<<<gi, 256, 0, st>>>(a, 1);
+    const int T = a.mode == SVO_GREEDY_PASS1 ? 15 : 60;
+    dim3 gs((maxM + M_WARPS * SL_ROWS_PER_WARP - 1) / (M_WARPS * SL_ROWS_PER_WARP), nframes);
+    k_shortlist<<<gs, M_THREADS, 0, st>>>(a, T);
+    const size_t smem = (size_t)maxM * sizeof(int) + (size_t)maxN + 16;
+    k_resolve<<<nframes, M_THREADS, smem, st>>>(a, maxM);
+    *launches += 3;
+    if (want_scores && a.best_idx) {
+        dim3 gf((maxM + M_WARPS - 1) / M_WARPS, nframes);
+        k_scores<<<gf, M_THREADS, 0, st>>>(a);
+        ++*launches;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// frame::disp2Depth (src/frame.cc:140-164)
+// ---------------------------------------------------------------------------------------
+__global__ void k_disp2depth(const float *__restrict__ disp, float *__restrict__ depth, size_t n, float bf)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float d = disp[i];
+        depth[i] = d != 0.f ? __fdiv_rn(bf, d) : -1.f;
+    }
+}
+
+void launch_disp2depth(const float *disp, float *depth, size_t n, float bf, cudaStream_t st, long long *launches)
+{
+    if (!n) return;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_disp2depth<<<(unsigned)blocks, 256, 0, st>>>(disp, depth, n, bf);
+    ++*launches;
+}

@@ -1,0 +1,307 @@
+// select.cu — cv::KeyPointsFilter::retainBest on the device, ORDER included.
+//
+// cv::ORB culls each level twice (2*quota by FAST score, quota by Harris response) with
+//   std::nth_element(begin, begin+n-1, end, response-greater);
+//   amb = v[n-1].response;  std::partition(begin+n, end, response >= amb);
+// and never sorts, so the output order is whatever libstdc++'s introselect and partition
+// leave — and the reference's matchers are order-sensitive
+// (src/pnpmatch.cc:75-95 first-minimum tie-break, greedy claims).  This file replays both
+// algorithms exactly, as a data-parallel program in one thread block per (image, level):
+//
+//   Hoare's unguarded partition is deterministic: the k-th element (from the left) at which
+//   the left scan stops is swapped with the k-th element (from the right) at which the
+//   right scan stops, for as long as the former lies left of the latter.  So one round is:
+//   flag stoppers -> block-wide prefix sums -> positions of the k-th stoppers -> count the
+//   crossing point m -> m independent swaps.  std::partition has the same two-pointer shape.
+//   The median-of-3 pivot move, the <=3-element insertion sort and the (never observed)
+//   depth-limit heap-select fallback are run by one thread, instruction for instruction.
+//
+// tools/model_retain_best.py is the executable design model of this file; the oracle
+// (oracle/retain_best.cpp) calls the real std:: algorithms.
+#include "svo_internal.cuh"
+
+#define SEL_THREADS 1024
+#define SEL_WARPS (SEL_THREADS / 32)
+
+struct SelSmem {
+    int wl[SEL_WARPS], wr[SEL_WARPS];
+    int m;
+};
+
+struct Greater {
+    __device__ __forceinline__ bool operator()(float a, float b) const { return a > b; }
+};
+
+__device__ __forceinline__ void sel_swap(float *key, uint32_t *val, int i, int j)
+{
+    const float k = key[i]; key[i] = key[j]; key[j] = k;
+    const uint32_t v = val[i]; val[i] = val[j]; val[j] = v;
+}
+
+// Two-pointer swap round over [lo, hi).  MODE 0: Hoare step against `pivot` (left scan stops
+// on !(x > pivot), right scan on !(pivot > x)).  MODE 1: std::partition with x >= pivot (left
+// stops on false, right on true).  Returns through nl/nr the stopper totals and `cut`.
+template <int MODE>
+__device__ void two_pointer_round(float *key, uint32_t *val, int lo, int hi, float pivot,
+                                  uint32_t *lpos, uint32_t *rasc, SelSmem &sh, int &nl, int &nr, int &cut)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int len = hi - lo;
+    const int seg = (((len + SEL_WARPS - 1) / SEL_WARPS) + 31) & ~31;
+    const int beg = lo + warp * seg, end = min(beg + seg, hi);
+    auto flags = [&](int i, bool &fl, bool &fr) {
+        if (i < end) {
+            const float x = key[i];
+            if (MODE == 0) { fl = !(x > pivot); fr = !(pivot > x); }
+            else { fr = x >= pivot; fl = !fr; }
+        } else { fl = false; fr = false; }
+    };
+    int cl = 0, cr = 0;
+    for (int base = beg; base < end; base += 32) {
+        bool fl, fr;
+        flags(base + lane, fl, fr);
+        cl += __popc(__ballot_sync(0xffffffffu, fl));
+        cr += __popc(__ballot_sync(0xffffffffu, fr));
+    }
+    if (lane == 0) { sh.wl[warp] = cl; sh.wr[warp] = cr; }
+    if (tid == 0) sh.m = 0;
+    __syncthreads();
+    int ol = 0, orr = 0; nl = 0; nr = 0;
+    {   // every warp scans the 32 per-warp counts itself
+        int a = sh.wl[lane], c = sh.wr[lane];
+        int ia = a, ic = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int ta = __shfl_up_sync(0xffffffffu, ia, d), tc = __shfl_up_sync(0xffffffffu, ic, d);
+            if (lane >= d) { ia += ta; ic += tc; }
+        }
+        nl = __shfl_sync(0xffffffffu, ia, 31); nr = __shfl_sync(0xffffffffu, ic, 31);
+        ol = __shfl_sync(0xffffffffu, ia - a, warp); orr = __shfl_sync(0xffffffffu, ic - c, warp);
+    }
+    for (int base = beg; base < end; base += 32) {
+        bool fl, fr;
+        flags(base + lane, fl, fr);
+        const uint32_t ml = __ballot_sync(0xffffffffu, fl), mr = __ballot_sync(0xffffffffu, fr);
+        const uint32_t lt = (1u << lane) - 1u;
+        if (fl) lpos[ol + __popc(ml & lt)] = base + lane;
+        if (fr) rasc[orr + __popc(mr & lt)] = base + lane;
+        ol += __popc(ml); orr += __popc(mr);
+    }
+    __syncthreads();
+    // m = #{k : lpos[k] < rpos[k]},  rpos[k] = rasc[nr-1-k]
+    const int kmax = min(nl, nr);
+    int c = 0;
+    for (int k = tid; k < kmax; k += SEL_THREADS) c += lpos[k] < rasc[nr - 1 - k];
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0 && c) atomicAdd(&sh.m, c);
+    __syncthreads();
+    const int m = sh.m;
+    const int c1 = m < nl ? (int)lpos[m] : 0x7fffffff;
+    const int c2 = m >= 1 ? (int)rasc[nr - m] : 0x7fffffff;
+    cut = min(c1, c2);
+    for (int k = tid; k < m; k += SEL_THREADS) sel_swap(key, val, lpos[k], rasc[nr - 1 - k]);
+    __syncthreads();
+}
+
+// libstdc++ __adjust_heap + __push_heap with comp = greater (min-heap on response)
+__device__ void adjust_heap(float *key, uint32_t *val, int first, int hole, int len, float vk, uint32_t vv)
+{
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (key[first + child] > key[first + child - 1]) --child;
+        key[first + hole] = key[first + child]; val[first + hole] = val[first + child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        key[first + hole] = key[first + child - 1]; val[first + hole] = val[first + child - 1];
+        hole = child - 1;
+    }
+    int parent = (hole - 1) / 2;
+    while (hole > top && key[first + parent] > vk) {
+        key[first + hole] = key[first + parent]; val[first + hole] = val[first + parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    key[first + hole] = vk; val[first + hole] = vv;
+}
+
+__device__ void heap_select(float *key, uint32_t *val, int first, int middle, int last)
+{
+    const int len = middle - first;
+    if (len >= 2) {
+        int parent = (len - 2) / 2;
+        while (true) {
+            adjust_heap(key, val, first, parent, len, key[first + parent], val[first + parent]);
+            if (parent == 0) break;
+            --parent;
+        }
+    }
+    for (int i = middle; i < last; ++i)
+        if (key[i] > key[first]) {
+            const float vk = key[i]; const uint32_t vv = val[i];
+            key[i] = key[first]; val[i] = val[first];
+            adjust_heap(key, val, first, 0, len, vk, vv);
+        }
+}
+
+__device__ void move_median_to_first(float *key, uint32_t *val, int r, int a, int b, int c)
+{
+    const float ka = key[a], kb = key[b], kc = key[c];
+    if (ka > kb) {
+        if (kb > kc) sel_swap(key, val, r, b);
+        else if (ka > kc) sel_swap(key, val, r, c);
+        else sel_swap(key, val, r, a);
+    } else if (ka > kc) sel_swap(key, val, r, a);
+    else if (kb > kc) sel_swap(key, val, r, c);
+    else sel_swap(key, val, r, b);
+}
+
+// Whole retainBest; every thread of the block must call it; returns the kept count.
+__device__ int block_retain_best(float *key, uint32_t *val, int n, int n_points, int depth_limit,
+                                 uint32_t *lpos, uint32_t *rasc, SelSmem &sh, int *status)
+{
+    if (n_points < 0 || n <= n_points) return n;
+    if (n_points == 0) return 0;
+    const int nth = n_points - 1;
+    int first = 0, last = n;
+    if (depth_limit < 0) depth_limit = 2 * (31 - __clz(n));
+    bool done = false;
+    while (last - first > 3) {
+        if (depth_limit == 0) {
+            if (threadIdx.x == 0) {
+                heap_select(key, val, first, nth + 1, last);
+                sel_swap(key, val, first, nth);
+                if (status) atomicOr(status, SVO_STATUS_DEPTH);
+            }
+            __syncthreads();
+            done = true;
+            break;
+        }
+        --depth_limit;
+        if (threadIdx.x == 0) move_median_to_first(key, val, first, first + 1, first + (last - first) / 2, last - 1);
+        __syncthreads();
+        const float pivot = key[first];
+        int nl, nr, cut;
+        two_pointer_round<0>(key, val, first + 1, last, pivot, lpos, rasc, sh, nl, nr, cut);
+        if (cut <= nth) first = cut; else last = cut;
+    }
+    if (!done) {
+        if (threadIdx.x == 0) {  // __insertion_sort on <= 3 elements
+            for (int i = first + 1; i < last; ++i) {
+                const float k = key[i]; const uint32_t v = val[i];
+                int j = i;
+                if (k > key[first]) {
+                    while (j > first) { key[j] = key[j - 1]; val[j] = val[j - 1]; --j; }
+                } else {
+                    while (k > key[j - 1]) { key[j] = key[j - 1]; val[j] = val[j - 1]; --j; }
+                }
+                key[j] = k; val[j] = v;
+            }
+        }
+        __syncthreads();
+    }
+    const float amb = key[n_points - 1];
+    int nl, nr, cut;
+    two_pointer_round<1>(key, val, n_points, n, amb, lpos, rasc, sh, nl, nr, cut);
+    return n_points + nr;
+}
+
+// ---- first cull: gather the level's band lists (raster order) and keep 2*quota by FAST score
+__global__ void __launch_bounds__(SEL_THREADS) k_select1(Bufs b, Geom g, int slot0)
+{
+    __shared__ SelSmem sh;
+    __shared__ int band_base[512];
+    const int l = blockIdx.x, slot = slot0 + blockIdx.y;
+    const LevelGeom &L = g.lv[l];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int *cnt1 = b.cnt1 + (size_t)slot * SVO_MAX_LEVELS;
+    int *kept1 = b.kept1 + (size_t)slot * SVO_MAX_LEVELS;
+    if (L.nbands == 0) {
+        if (tid == 0) { cnt1[l] = 0; kept1[l] = 0; }
+        return;
+    }
+    const int *bc = b.bandcnt + (size_t)slot * g.bandcnt_total + L.bandcnt_off;
+    if (warp == 0) {  // exclusive scan of the band counts
+        int run = 0;
+        for (int base = 0; base < L.nbands; base += 32) {
+            const int i = base + lane;
+            const int c = i < L.nbands ? bc[i] : 0;
+            int inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            if (i < L.nbands) band_base[i] = run + inc - c;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) band_base[L.nbands] = run;
+    }
+    __syncthreads();
+    const int n = band_base[L.nbands];
+    float *key = b.ckey + (size_t)slot * g.cand_total + L.cand_off;
+    uint32_t *val = b.cval + (size_t)slot * g.cand_total + L.cand_off;
+    uint32_t *lpos = b.lpos + (size_t)slot * g.cand_total + L.cand_off;
+    uint32_t *rasc = b.rpos + (size_t)slot * g.cand_total + L.cand_off;
+    const uint32_t *bands = b.bands + (size_t)slot * g.band_total + L.band_off;
+    for (int bi = warp; bi < L.nbands; bi += SEL_WARPS) {
+        const int c = bc[bi], o = band_base[bi];
+        const uint32_t *src = bands + (size_t)bi * L.band_cap;
+        for (int i = lane; i < c; i += 32) {
+            const uint32_t e = src[i];
+            val[o + i] = e;
+            key[o + i] = (float)unpack_s(e);
+        }
+    }
+    __syncthreads();
+    const int kept = block_retain_best(key, val, n, 2 * L.quota, -1, lpos, rasc, sh, b.status + slot);
+    if (tid == 0) { cnt1[l] = n; kept1[l] = kept; }
+}
+
+// ---- second cull: keep quota by Harris response
+__global__ void __launch_bounds__(SEL_THREADS) k_select2(Bufs b, Geom g, int slot0)
+{
+    __shared__ SelSmem sh;
+    const int l = blockIdx.x, slot = slot0 + blockIdx.y;
+    const LevelGeom &L = g.lv[l];
+    const int n = min(b.kept1[(size_t)slot * SVO_MAX_LEVELS + l], L.cap2);
+    float *key = b.key2 + (size_t)slot * g.total2 + L.off2;
+    uint32_t *val = b.val2 + (size_t)slot * g.total2 + L.off2;
+    uint32_t *lpos = b.lpos + (size_t)slot * g.cand_total + L.cand_off;
+    uint32_t *rasc = b.rpos + (size_t)slot * g.cand_total + L.cand_off;
+    const int kept = block_retain_best(key, val, n, L.quota, -1, lpos, rasc, sh, b.status + slot);
+    if (threadIdx.x == 0) b.kept2[(size_t)slot * SVO_MAX_LEVELS + l] = kept;
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) k_retain_best_raw(float *key, uint32_t *val, int n, int n_points,
+                                                                 int depth_limit, uint32_t *lpos, uint32_t *rasc,
+                                                                 int *kept_out, int *status)
+{
+    __shared__ SelSmem sh;
+    const int kept = block_retain_best(key, val, n, n_points, depth_limit, lpos, rasc, sh, status);
+    if (threadIdx.x == 0) *kept_out = kept;
+}
+
+void launch_select1(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches)
+{
+    dim3 grid(g.nlevels, nimg);
+    k_select1<<<grid, SEL_THREADS, 0, st>>>(b, g, slot0);
+    ++*launches;
+}
+
+void launch_select2(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches)
+{
+    dim3 grid(g.nlevels, nimg);
+    k_select2<<<grid, SEL_THREADS, 0, st>>>(b, g, slot0);
+    ++*launches;
+}
+
+void launch_retain_best_raw(float *key, uint32_t *val, int n, int n_points, int depth_limit, uint32_t *lpos,
+                            uint32_t *rpos, int *kept_out, int *status, cudaStream_t st, long long *launches)
+{
+    k_retain_best_raw<<<1, SEL_THREADS, 0, st>>>(key, val, n, n_points, depth_limit, lpos, rpos, kept_out, status);
+    ++*launches;
+}

@@ -1,0 +1,828 @@
+// svo_api.cu — context, HBM layout, streams and the C ABI of libsvo_b200.so
+// (include/svo_b200.h).  Host-side orchestration only; every computation is a kernel in
+// pyramid.cu / fast.cu / select.cu / describe.cu / stereo.cu / match.cu.  No CPU fallback.
+#include "svo_internal.cuh"
+
+#include <limits.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#define N_EVENTS 12
+
+namespace {
+
+struct FrameBufs {           // per-frame (stereo pair) device arrays
+    int nframes, col_stride, row_stride;
+    uint8_t *prev, *map;     // [f][row_stride][32]
+    uint8_t *prev_live;      // [f][row_stride]
+    int *map_prev;           // [f][row_stride]
+    uint8_t *claimed;        // [f][col_stride]
+    int *claim_row, *claim_time;
+    int *bf_idx, *bf_dist; uint8_t *bf_keep; int *min_dist;
+    int *p1_best_idx, *p1_best, *p1_second; uint8_t *p1_row_claimed, *p1_row_bad;
+    int *p2_best_idx, *p2_best, *p2_second; uint8_t *p2_row_claimed;
+    uint32_t *shortlist; int *short_cnt;
+    float *u_right, *depth; int *match_r, *sad, *n_stereo;
+    int *params;             // [4][nframes]: n_prev, n_map, bf bits, baseline bits
+    // sync-only extras
+    uint8_t *cols;           // [col_stride][32] caller-provided column descriptors
+    float *win, *cur_xy, *row_xy; int *boxes; double *F;
+};
+
+struct HostArena {           // pinned mirror of one lane's outputs
+    svo_keypoint *kp; uint8_t *desc; int *nkp, *status;
+    float *u_right, *depth; int *n_stereo;
+    int *bf_idx, *bf_dist; uint8_t *bf_keep;
+    int *p1_best_idx, *p1_best, *p1_second; uint8_t *p1_row_claimed, *p2_row_claimed;
+    int *claim_row;
+    int *params;             // staging for the per-batch parameter upload
+};
+
+struct Lane {
+    cudaStream_t st;
+    bool own_stream;
+    cudaEvent_t done;
+    cudaEvent_t ev[N_EVENTS];
+    int slot0, frame0, nframes;
+    bool busy;
+    HostArena h;
+    std::vector<svo_frame_in> in;
+};
+
+}  // namespace
+
+struct svo_ctx {
+    svo_config cfg;
+    Geom g;
+    Bufs b;
+    FrameBufs fb;            // batch frames
+    FrameBufs sb;            // the single synchronous frame
+    std::vector<Lane> lanes;
+    cudaStream_t sync_st;
+    int sync_slot0;          // two slots: cam 0 / cam 1
+    int nslots;
+    std::vector<void *> dev_allocs, pinned_allocs;
+    std::vector<uint32_t> rtab_host;
+    long long launches;
+    bool profiling;
+    bool sync_have[2];
+    char err[512];
+};
+
+namespace {
+
+int fail(svo_ctx *c, int code, const char *fmt, ...)
+{
+    if (c) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(c->err, sizeof(c->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(ctx, SVO_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+template <typename T>
+int dalloc(svo_ctx *ctx, T **p, size_t n)
+{
+    void *q = nullptr;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+    if (e != cudaSuccess) return fail(ctx, SVO_E_NOMEM, "cudaMalloc(%zu) -> %s", n * sizeof(T), cudaGetErrorString(e));
+    ctx->dev_allocs.push_back(q);
+    *p = (T *)q;
+    return SVO_OK;
+}
+template <typename T>
+int halloc(svo_ctx *ctx, T **p, size_t n)
+{
+    void *q = nullptr;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMallocHost(&q, n * sizeof(T));
+    if (e != cudaSuccess) return fail(ctx, SVO_E_NOMEM, "cudaMallocHost(%zu) -> %s", n * sizeof(T), cudaGetErrorString(e));
+    ctx->pinned_allocs.push_back(q);
+    memset(q, 0, n * sizeof(T));
+    *p = (T *)q;
+    return SVO_OK;
+}
+#define TRY(x) do { int r_ = (x); if (r_ != SVO_OK) return r_; } while (0)
+
+inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// cv::ORB geometry: float scale = (float)pow((double)scaleFactor, l), sizes by
+// cvRound(cols/scale), quotas by the geometric series in float.
+void orb_geometry(int W, int H, int nlevels, float scale_factor_f, int nfeatures, int *lw, int *lh, float *ls, int *quota)
+{
+    const double sf = (double)scale_factor_f;
+    for (int l = 0; l < nlevels; ++l) {
+        const float s = (float)pow(sf, (double)l);
+        ls[l] = s;
+        lw[l] = (int)lrintf((float)W / s);
+        lh[l] = (int)lrintf((float)H / s);
+    }
+    const float factor = (float)(1.0 / sf);
+    float ndes = (float)nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; ++l) {
+        quota[l] = (int)lrintf(ndes);
+        sum += quota[l];
+        ndes *= factor;
+    }
+    quota[nlevels - 1] = nfeatures - sum > 0 ? nfeatures - sum : 0;
+}
+
+// INTER_LINEAR_EXACT coefficients: packed (ofs << 9) | w1, w1 in Q8
+void resize_table(int src, int dst, uint32_t *tab)
+{
+    const double scale = (double)src / (double)dst;
+    for (int d = 0; d < dst; ++d) {
+        const double fv = scale * ((double)d + 0.5) - 0.5;
+        int iv = (int)floor(fv);
+        int w1 = 0;
+        if (iv >= 0 && src > 1) {
+            if (iv < src - 1) w1 = (int)lrint((fv - (double)iv) * 256.0);
+            else iv = src - 1;
+        } else iv = 0;
+        tab[d] = ((uint32_t)iv << 9) | (uint32_t)w1;
+    }
+}
+
+int build_geometry(svo_ctx *ctx)
+{
+    const svo_config &c = ctx->cfg;
+    Geom &g = ctx->g;
+    memset(&g, 0, sizeof(g));
+    g.nlevels = c.nlevels; g.W = c.width; g.H = c.height; g.fast_threshold = c.fast_threshold;
+    int lw[SVO_MAX_LEVELS], lh[SVO_MAX_LEVELS], quota[SVO_MAX_LEVELS];
+    float ls[SVO_MAX_LEVELS];
+    orb_geometry(c.width, c.height, c.nlevels, c.scale_factor, c.nfeatures, lw, lh, ls, quota);
+    int off = 0, band_off = 0, bandcnt_off = 0, cand_off = 0, off2 = 0, tab_off = 0, tiles = 0;
+    for (int l = 0; l < g.nlevels; ++l) {
+        LevelGeom &L = g.lv[l];
+        L.w = lw[l]; L.h = lh[l]; L.pitch = align_up(lw[l], 16);
+        if (L.w < 8 || L.h < 8) return fail(ctx, SVO_E_INVALID, "level %d is %dx%d: image too small for %d levels", l, L.w, L.h, g.nlevels);
+        L.off = off; off += align_up(L.pitch * (L.h + 1), 256);
+        L.scale = ls[l]; L.inv_scale = 1.f / ls[l]; L.quota = quota[l];
+        L.x0 = SVO_EDGE; L.x1 = L.w - SVO_EDGE; L.y0 = SVO_EDGE; L.y1 = L.h - SVO_EDGE;
+        if (L.x1 <= L.x0 || L.y1 <= L.y0) { L.x1 = L.x0; L.y1 = L.y0; L.nbands = 0; }
+        else L.nbands = (L.y1 - L.y0 + SVO_FAST_BAND - 1) / SVO_FAST_BAND;
+        if (L.nbands > 500) return fail(ctx, SVO_E_INVALID, "image too tall");
+        L.band_cap = ((SVO_FAST_BAND + 1) / 2) * ((L.x1 - L.x0 + 1) / 2) + 1;
+        L.band_off = band_off; band_off += L.nbands * L.band_cap;
+        L.bandcnt_off = bandcnt_off; bandcnt_off += L.nbands;
+        L.cand_cap = L.nbands * L.band_cap + 4;
+        L.cand_off = cand_off; cand_off += align_up(L.cand_cap, 4);
+        L.cap2 = 4 * L.quota + 1024 < L.cand_cap ? 4 * L.quota + 1024 : L.cand_cap;
+        L.off2 = off2; off2 += align_up(L.cap2, 4);
+        L.tab_off = tab_off; if (l) tab_off += L.w + L.h;
+        L.blur_tiles_x = (L.w + 127) / 128;
+        L.blur_tile_off = tiles; tiles += L.blur_tiles_x * ((L.h + 15) / 16);
+        g.fast_bands += L.nbands;
+    }
+    if (lw[0] >= 4096 || lh[0] >= 4096) return fail(ctx, SVO_E_INVALID, "images up to 4095x4095 are supported");
+    g.pyr_bytes = off; g.band_total = band_off; g.bandcnt_total = bandcnt_off;
+    g.cand_total = cand_off; g.total2 = off2; g.blur_tiles = tiles;
+    g.kp_cap = align_up(c.nfeatures + c.nfeatures / 8 + 64, 64);
+    ctx->rtab_host.assign((size_t)tab_off + 1, 0);
+    for (int l = 1; l < g.nlevels; ++l) {
+        resize_table(lw[l - 1], lw[l], ctx->rtab_host.data() + g.lv[l].tab_off);
+        resize_table(lh[l - 1], lh[l], ctx->rtab_host.data() + g.lv[l].tab_off + lw[l]);
+    }
+    return SVO_OK;
+}
+
+int alloc_frames(svo_ctx *ctx, FrameBufs &f, int nframes, int col_stride, int row_stride, bool sync_extras)
+{
+    f.nframes = nframes; f.col_stride = col_stride; f.row_stride = row_stride;
+    const size_t F = nframes, C = (size_t)col_stride * F, R = (size_t)row_stride * F;
+    TRY(dalloc(ctx, &f.prev, R * 32)); TRY(dalloc(ctx, &f.map, R * 32));
+    TRY(dalloc(ctx, &f.prev_live, R)); TRY(dalloc(ctx, &f.map_prev, R));
+    TRY(dalloc(ctx, &f.claimed, C)); TRY(dalloc(ctx, &f.claim_row, C)); TRY(dalloc(ctx, &f.claim_time, C));
+    TRY(dalloc(ctx, &f.bf_idx, C)); TRY(dalloc(ctx, &f.bf_dist, C)); TRY(dalloc(ctx, &f.bf_keep, C));
+    TRY(dalloc(ctx, &f.min_dist, F));
+    TRY(dalloc(ctx, &f.p1_best_idx, R)); TRY(dalloc(ctx, &f.p1_best, R)); TRY(dalloc(ctx, &f.p1_second, R));
+    TRY(dalloc(ctx, &f.p1_row_claimed, R)); TRY(dalloc(ctx, &f.p1_row_bad, R));
+    TRY(dalloc(ctx, &f.p2_best_idx, R)); TRY(dalloc(ctx, &f.p2_best, R)); TRY(dalloc(ctx, &f.p2_second, R));
+    TRY(dalloc(ctx, &f.p2_row_claimed, R));
+    TRY(dalloc(ctx, &f.shortlist, R * SVO_SHORT_CAP)); TRY(dalloc(ctx, &f.short_cnt, R));
+    TRY(dalloc(ctx, &f.u_right, C)); TRY(dalloc(ctx, &f.depth, C)); TRY(dalloc(ctx, &f.match_r, C));
+    TRY(dalloc(ctx, &f.sad, C)); TRY(dalloc(ctx, &f.n_stereo, F));
+    TRY(dalloc(ctx, &f.params, 4 * F));
+    f.cols = nullptr; f.win = f.cur_xy = f.row_xy = nullptr; f.boxes = nullptr; f.F = nullptr;
+    if (sync_extras) {
+        TRY(dalloc(ctx, &f.cols, C * 32));
+        TRY(dalloc(ctx, &f.win, R * 3)); TRY(dalloc(ctx, &f.cur_xy, C * 2)); TRY(dalloc(ctx, &f.row_xy, R * 2));
+        TRY(dalloc(ctx, &f.boxes, 4 * 256)); TRY(dalloc(ctx, &f.F, 9));
+    }
+    return SVO_OK;
+}
+
+// enqueue the extraction kernels for images [slot0, slot0+nimg) on `st`
+void enqueue_extract(svo_ctx *ctx, int slot0, int nimg, cudaStream_t st, cudaEvent_t *ev)
+{
+    const Bufs &b = ctx->b; const Geom &g = ctx->g;
+    long long *n = &ctx->launches;
+    cudaMemsetAsync(b.status + slot0, 0, sizeof(int) * nimg, st);
+    if (ev) cudaEventRecord(ev[1], st);
+    launch_pyramid(b, g, slot0, nimg, st, n);
+    if (ev) cudaEventRecord(ev[2], st);
+    launch_fast(b, g, slot0, nimg, st, n);
+    if (ev) cudaEventRecord(ev[3], st);
+    launch_select1(b, g, slot0, nimg, st, n);
+    if (ev) cudaEventRecord(ev[4], st);
+    launch_harris(b, g, slot0, nimg, st, n);
+    if (ev) cudaEventRecord(ev[5], st);
+    launch_select2(b, g, slot0, nimg, st, n);
+    if (ev) cudaEventRecord(ev[6], st);
+    launch_blur(b, g, slot0, nimg, st, n);
+    if (ev) cudaEventRecord(ev[7], st);
+    launch_describe(b, g, slot0, nimg, st, n);
+    if (ev) cudaEventRecord(ev[8], st);
+}
+
+int upload_image(svo_ctx *ctx, int slot, const uint8_t *img, int stride, cudaStream_t st)
+{
+    const Geom &g = ctx->g;
+    uint8_t *dst = ctx->b.pyr + (size_t)slot * g.pyr_bytes + g.lv[0].off;
+    CU(cudaMemcpy2DAsync(dst, g.lv[0].pitch, img, stride, g.W, g.H, cudaMemcpyDefault, st));
+    return SVO_OK;
+}
+
+MatchSet make_set(const uint8_t *desc, const int *count, int count_stride, int stride_rows, int fixed, int desc_stride = -1)
+{
+    MatchSet s; s.desc = desc; s.count = count; s.count_stride = count_stride; s.stride_rows = stride_rows; s.fixed_count = fixed;
+    s.desc_stride = desc_stride < 0 ? stride_rows : desc_stride;
+    return s;
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" {
+
+void svo_default_config(svo_config *c)
+{
+    memset(c, 0, sizeof(*c));
+    c->device = 0; c->width = 1241; c->height = 376;
+    c->nfeatures = 2000; c->nlevels = 8; c->scale_factor = 1.2f; c->fast_threshold = 20;
+    c->max_batch = 1; c->lanes = 1; c->max_rows = 5000; c->stream = nullptr;
+}
+
+const char *svo_version(void) { return "svo_b200 0.1 (sm_100a)"; }
+
+const char *svo_last_error(const svo_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+
+void svo_destroy(svo_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    cudaDeviceSynchronize();
+    for (Lane &l : ctx->lanes) {
+        if (l.done) cudaEventDestroy(l.done);
+        for (int i = 0; i < N_EVENTS; ++i) if (l.ev[i]) cudaEventDestroy(l.ev[i]);
+        if (l.own_stream && l.st) cudaStreamDestroy(l.st);
+    }
+    if (ctx->sync_st) cudaStreamDestroy(ctx->sync_st);
+    for (void *p : ctx->dev_allocs) cudaFree(p);
+    for (void *p : ctx->pinned_allocs) cudaFreeHost(p);
+    delete ctx;
+}
+
+int svo_create(const svo_config *cfg, svo_ctx **out)
+{
+    if (!cfg || !out) return SVO_E_INVALID;
+    *out = nullptr;
+    svo_ctx *ctx = new svo_ctx();
+    ctx->cfg = *cfg; ctx->launches = 0; ctx->profiling = false; ctx->err[0] = 0;
+    ctx->sync_st = nullptr; ctx->sync_have[0] = ctx->sync_have[1] = false;
+    *out = ctx;  // returned even on failure so the caller can read svo_last_error, then svo_destroy
+    const svo_config &c = ctx->cfg;
+    if (c.nlevels < 1 || c.nlevels > SVO_MAX_LEVELS || c.nfeatures < 1 || c.nfeatures > 60000 || c.max_batch < 1 ||
+        c.lanes < 1 || c.max_rows < 1 || c.max_rows > 40000 || c.width < 64 || c.height < 64 || !(c.scale_factor > 1.f))
+        return fail(ctx, SVO_E_INVALID, "invalid configuration");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(ctx, SVO_E_CUDA, "no CUDA device: %s (libsvo_b200 has no CPU fallback)", cudaGetErrorString(e));
+    CU(cudaSetDevice(c.device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, c.device));
+    if (prop.major != 10)
+        return fail(ctx, SVO_E_CUDA, "device %s is sm_%d%d; this library carries sm_100a code only", prop.name, prop.major, prop.minor);
+    TRY(build_geometry(ctx));
+    const Geom &g = ctx->g;
+    const int nbatch_frames = c.lanes * c.max_batch;
+    ctx->nslots = 2 * nbatch_frames + 2;
+    ctx->sync_slot0 = 2 * nbatch_frames;
+    const size_t S = ctx->nslots;
+    Bufs &b = ctx->b;
+    TRY(dalloc(ctx, &b.pyr, S * g.pyr_bytes)); TRY(dalloc(ctx, &b.blur, S * g.pyr_bytes));
+    TRY(dalloc(ctx, &b.bands, S * g.band_total)); TRY(dalloc(ctx, &b.bandcnt, S * g.bandcnt_total));
+    TRY(dalloc(ctx, &b.ckey, S * g.cand_total)); TRY(dalloc(ctx, &b.cval, S * g.cand_total));
+    TRY(dalloc(ctx, &b.lpos, S * g.cand_total)); TRY(dalloc(ctx, &b.rpos, S * g.cand_total));
+    TRY(dalloc(ctx, &b.key2, S * g.total2)); TRY(dalloc(ctx, &b.val2, S * g.total2));
+    TRY(dalloc(ctx, &b.cnt1, S * SVO_MAX_LEVELS)); TRY(dalloc(ctx, &b.kept1, S * SVO_MAX_LEVELS)); TRY(dalloc(ctx, &b.kept2, S * SVO_MAX_LEVELS));
+    TRY(dalloc(ctx, &b.kp, S * g.kp_cap)); TRY(dalloc(ctx, &b.desc, S * g.kp_cap * 32));
+    TRY(dalloc(ctx, &b.nkp, S)); TRY(dalloc(ctx, &b.status, S));
+    uint32_t *rtab = nullptr;
+    TRY(dalloc(ctx, &rtab, ctx->rtab_host.size()));
+    CU(cudaMemcpy(rtab, ctx->rtab_host.data(), ctx->rtab_host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    b.rtab = rtab;
+    CU(cudaMemset(b.pyr, 0, S * g.pyr_bytes)); CU(cudaMemset(b.blur, 0, S * g.pyr_bytes));
+    CU(cudaMemset(b.nkp, 0, S * sizeof(int))); CU(cudaMemset(b.status, 0, S * sizeof(int)));
+    CU(cudaMemset(b.kept1, 0, S * SVO_MAX_LEVELS * sizeof(int))); CU(cudaMemset(b.kept2, 0, S * SVO_MAX_LEVELS * sizeof(int)));
+    TRY(alloc_frames(ctx, ctx->fb, nbatch_frames, g.kp_cap, c.max_rows, false));
+    const int sync_stride = g.kp_cap > c.max_rows ? g.kp_cap : c.max_rows;
+    TRY(alloc_frames(ctx, ctx->sb, 1, sync_stride, sync_stride, true));
+    if (setup_fast_attributes(g) != 0 || setup_match_attributes() != 0)
+        return fail(ctx, SVO_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+    CU(cudaStreamCreateWithFlags(&ctx->sync_st, cudaStreamNonBlocking));
+    ctx->lanes.resize(c.lanes);
+    for (int i = 0; i < c.lanes; ++i) {
+        Lane &l = ctx->lanes[i];
+        l.st = nullptr; l.own_stream = true; l.done = nullptr; l.busy = false; l.nframes = 0;
+        for (int k = 0; k < N_EVENTS; ++k) l.ev[k] = nullptr;
+        l.slot0 = 2 * i * c.max_batch; l.frame0 = i * c.max_batch;
+        if (i == 0 && c.stream) { l.st = (cudaStream_t)c.stream; l.own_stream = false; }
+        else CU(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+        for (int k = 0; k < N_EVENTS; ++k) CU(cudaEventCreate(&l.ev[k]));
+        const size_t B = c.max_batch, I = 2 * B, K = g.kp_cap, R = c.max_rows;
+        HostArena &h = l.h;
+        TRY(halloc(ctx, &h.kp, I * K)); TRY(halloc(ctx, &h.desc, I * K * 32));
+        TRY(halloc(ctx, &h.nkp, I)); TRY(halloc(ctx, &h.status, I));
+        TRY(halloc(ctx, &h.u_right, B * K)); TRY(halloc(ctx, &h.depth, B * K)); TRY(halloc(ctx, &h.n_stereo, B));
+        TRY(halloc(ctx, &h.bf_idx, B * K)); TRY(halloc(ctx, &h.bf_dist, B * K)); TRY(halloc(ctx, &h.bf_keep, B * K));
+        TRY(halloc(ctx, &h.p1_best_idx, B * R)); TRY(halloc(ctx, &h.p1_best, B * R)); TRY(halloc(ctx, &h.p1_second, B * R));
+        TRY(halloc(ctx, &h.p1_row_claimed, B * R)); TRY(halloc(ctx, &h.p2_row_claimed, B * R));
+        TRY(halloc(ctx, &h.claim_row, B * K));
+        TRY(halloc(ctx, &h.params, 4 * B));
+    }
+    CU(cudaDeviceSynchronize());
+    return SVO_OK;
+}
+
+int svo_get_geometry(const svo_ctx *ctx, int *lw, int *lh, float *lscale, int *quota)
+{
+    if (!ctx) return SVO_E_INVALID;
+    for (int l = 0; l < ctx->g.nlevels; ++l) {
+        if (lw) lw[l] = ctx->g.lv[l].w;
+        if (lh) lh[l] = ctx->g.lv[l].h;
+        if (lscale) lscale[l] = ctx->g.lv[l].scale;
+        if (quota) quota[l] = ctx->g.lv[l].quota;
+    }
+    return ctx->g.nlevels;
+}
+
+long long svo_launch_count(const svo_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int svo_set_profiling(svo_ctx *ctx, int on) { if (!ctx) return SVO_E_INVALID; ctx->profiling = on != 0; return SVO_OK; }
+void *svo_lane_stream(svo_ctx *ctx, int lane) { return (ctx && lane >= 0 && lane < (int)ctx->lanes.size()) ? (void *)ctx->lanes[lane].st : nullptr; }
+
+void *svo_alloc_pinned(svo_ctx *ctx, size_t bytes)
+{
+    void *p = nullptr;
+    if (!ctx || cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void svo_free_pinned(svo_ctx *ctx, void *p) { (void)ctx; if (p) cudaFreeHost(p); }
+void *svo_alloc_device(svo_ctx *ctx, size_t bytes)
+{
+    void *p = nullptr;
+    if (!ctx || cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void svo_free_device(svo_ctx *ctx, void *p) { (void)ctx; if (p) cudaFree(p); }
+int svo_copy_to_device(svo_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (!ctx) return SVO_E_INVALID;
+    CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
+    return SVO_OK;
+}
+
+// ------------------------------------------------------------------------------ sync API
+int svo_extract(svo_ctx *ctx, int cam, const uint8_t *gray, int stride, int w, int h,
+                svo_keypoint *kp_out, uint8_t *desc_out, int cap)
+{
+    if (!ctx || !gray || cam < 0 || cam > 1 || cap < 0) return fail(ctx, SVO_E_INVALID, "svo_extract: bad argument");
+    const Geom &g = ctx->g;
+    if (w != g.W || h != g.H || stride < w) return fail(ctx, SVO_E_INVALID, "svo_extract: image is %dx%d, context is %dx%d", w, h, g.W, g.H);
+    CU(cudaSetDevice(ctx->cfg.device));
+    const int slot = ctx->sync_slot0 + cam;
+    cudaStream_t st = ctx->sync_st;
+    TRY(upload_image(ctx, slot, gray, stride, st));
+    enqueue_extract(ctx, slot, 1, st, nullptr);
+    int hdr[2] = {0, 0};
+    CU(cudaMemcpyAsync(&hdr[0], ctx->b.nkp + slot, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&hdr[1], ctx->b.status + slot, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    if (hdr[1] & SVO_STATUS_OVERFLOW) return fail(ctx, SVO_E_CAPACITY, "svo_extract: internal capacity exceeded (status %d, n %d)", hdr[1], hdr[0]);
+    const int n = hdr[0];
+    const int m = n < cap ? n : cap;
+    if (m > 0 && kp_out) CU(cudaMemcpy(kp_out, ctx->b.kp + (size_t)slot * g.kp_cap, sizeof(svo_keypoint) * m, cudaMemcpyDeviceToHost));
+    if (m > 0 && desc_out) CU(cudaMemcpy(desc_out, ctx->b.desc + (size_t)slot * g.kp_cap * 32, 32 * (size_t)m, cudaMemcpyDeviceToHost));
+    ctx->sync_have[cam] = true;
+    return n;
+}
+
+int svo_stereo_sparse(svo_ctx *ctx, float bf, float baseline, float *u_right, float *depth,
+                      int32_t *match_r, int32_t *sad, int cap)
+{
+    if (!ctx || !u_right || !depth || cap < 0) return fail(ctx, SVO_E_INVALID, "svo_stereo_sparse: bad argument");
+    if (!ctx->sync_have[0] || !ctx->sync_have[1]) return fail(ctx, SVO_E_INVALID, "svo_stereo_sparse: extract both cameras first");
+    CU(cudaSetDevice(ctx->cfg.device));
+    const Geom &g = ctx->g;
+    FrameBufs &s = ctx->sb;
+    cudaStream_t st = ctx->sync_st;
+    float prm[2] = {bf, baseline};
+    CU(cudaMemcpyAsync(s.params + 2, &prm[0], sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s.params + 3, &prm[1], sizeof(float), cudaMemcpyHostToDevice, st));
+    StereoArgs a;
+    a.u_right = s.u_right; a.depth = s.depth; a.match_r = s.match_r; a.sad = s.sad; a.n_stereo = s.n_stereo;
+    a.stride = s.col_stride;
+    a.bf = reinterpret_cast<const float *>(s.params + 2); a.baseline = reinterpret_cast<const float *>(s.params + 3);
+    launch_stereo(ctx->b, g, ctx->sync_slot0, 1, a, st, &ctx->launches);
+    int n = 0;
+    CU(cudaMemcpyAsync(&n, ctx->b.nkp + ctx->sync_slot0, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    if (n > g.kp_cap) n = g.kp_cap;
+    const int m = n < cap ? n : cap;
+    if (m > 0) {
+        CU(cudaMemcpy(u_right, s.u_right, sizeof(float) * m, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(depth, s.depth, sizeof(float) * m, cudaMemcpyDeviceToHost));
+        if (match_r) CU(cudaMemcpy(match_r, s.match_r, sizeof(int) * m, cudaMemcpyDeviceToHost));
+        if (sad) CU(cudaMemcpy(sad, s.sad, sizeof(int) * m, cudaMemcpyDeviceToHost));
+    }
+    return n;
+}
+
+int svo_match_bf(svo_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt,
+                 int32_t *idx, int32_t *dist, uint8_t *keep)
+{
+    if (!ctx || nq < 0 || nt < 0 || (nq && !q) || (nt && !t)) return fail(ctx, SVO_E_INVALID, "svo_match_bf: bad argument");
+    FrameBufs &s = ctx->sb;
+    if (nq > s.col_stride || nt > s.row_stride) return fail(ctx, SVO_E_CAPACITY, "svo_match_bf: %d x %d exceeds capacity %d", nq, nt, s.col_stride);
+    if (nq == 0) return 0;
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = ctx->sync_st;
+    CU(cudaMemcpyAsync(s.cols, q, (size_t)nq * 32, cudaMemcpyDefault, st));
+    if (nt) CU(cudaMemcpyAsync(s.prev, t, (size_t)nt * 32, cudaMemcpyDefault, st));
+    BfArgs a;
+    a.q = make_set(s.cols, nullptr, 0, s.col_stride, nq);
+    a.t = make_set(s.prev, nullptr, 0, s.row_stride, nt);
+    a.idx = s.bf_idx; a.dist = s.bf_dist; a.keep = s.bf_keep; a.min_dist = s.min_dist;
+    launch_bf(a, 1, st, &ctx->launches);
+    if (idx) CU(cudaMemcpyAsync(idx, s.bf_idx, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
+    if (dist) CU(cudaMemcpyAsync(dist, s.bf_dist, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
+    if (keep) CU(cudaMemcpyAsync(keep, s.bf_keep, (size_t)nq, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    return nq;
+}
+
+int svo_match_greedy(svo_ctx *ctx, const uint8_t *rows, int M, const uint8_t *cur, int N, int mode,
+                     const uint8_t *row_live, uint8_t *claimed, int32_t *claim_row, int row_base,
+                     int32_t *best_idx, int32_t *best, int32_t *second, uint8_t *row_claimed,
+                     const float *win_uvr, const float *cur_xy, const svo_veto *veto, uint8_t *row_bad)
+{
+    if (!ctx || M < 0 || N < 0 || (M && !rows) || (N && !cur) || !claimed || (mode != 0 && mode != 1) || (win_uvr && !cur_xy))
+        return fail(ctx, SVO_E_INVALID, "svo_match_greedy: bad argument");
+    FrameBufs &s = ctx->sb;
+    if (M > s.row_stride || N > s.col_stride) return fail(ctx, SVO_E_CAPACITY, "svo_match_greedy: %d x %d exceeds capacity %d", M, N, s.col_stride);
+    if (veto && (veto->n_boxes > 256 || veto->n_boxes < 0)) return fail(ctx, SVO_E_CAPACITY, "svo_match_greedy: at most 256 boxes");
+    if (M == 0) return 0;
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = ctx->sync_st;
+    CU(cudaMemcpyAsync(s.map, rows, (size_t)M * 32, cudaMemcpyDefault, st));
+    if (N) CU(cudaMemcpyAsync(s.cols, cur, (size_t)N * 32, cudaMemcpyDefault, st));
+    if (N) CU(cudaMemcpyAsync(s.claimed, claimed, (size_t)N, cudaMemcpyDefault, st));
+    if (N && claim_row) CU(cudaMemcpyAsync(s.claim_row, claim_row, sizeof(int) * N, cudaMemcpyDefault, st));
+    if (row_live) CU(cudaMemcpyAsync(s.prev_live, row_live, (size_t)M, cudaMemcpyDefault, st));
+    if (win_uvr) {
+        CU(cudaMemcpyAsync(s.win, win_uvr, sizeof(float) * 3 * M, cudaMemcpyDefault, st));
+    }
+    if (cur_xy && N) CU(cudaMemcpyAsync(s.cur_xy, cur_xy, sizeof(float) * 2 * N, cudaMemcpyDefault, st));
+    const bool use_veto = veto && veto->n_boxes > 0 && veto->F && veto->boxes && veto->row_xy && veto->cur_xy && mode == SVO_GREEDY_PASS1;
+    if (use_veto) {
+        CU(cudaMemcpyAsync(s.boxes, veto->boxes, sizeof(int) * 4 * veto->n_boxes, cudaMemcpyDefault, st));
+        CU(cudaMemcpyAsync(s.F, veto->F, sizeof(double) * 9, cudaMemcpyDefault, st));
+        CU(cudaMemcpyAsync(s.row_xy, veto->row_xy, sizeof(float) * 2 * M, cudaMemcpyDefault, st));
+        if (N) CU(cudaMemcpyAsync(s.cur_xy, veto->cur_xy, sizeof(float) * 2 * N, cudaMemcpyDefault, st));
+    }
+    GreedyArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rows = make_set(s.map, nullptr, 0, s.row_stride, M);
+    a.cols = make_set(s.cols, nullptr, 0, s.col_stride, N);
+    a.mode = mode; a.row_base = row_base; a.row_base_arr = nullptr;
+    a.row_live = row_live ? s.prev_live : nullptr;
+    a.claimed = s.claimed; a.claim_row = s.claim_row; a.claim_time = s.claim_time;
+    a.best_idx = s.p2_best_idx; a.best = s.p2_best; a.second = s.p2_second;
+    a.row_claimed = s.p2_row_claimed; a.row_bad = s.p1_row_bad;
+    a.shortlist = s.shortlist; a.short_cnt = s.short_cnt;
+    a.win_uvr = win_uvr ? s.win : nullptr;
+    a.cur_xy = (win_uvr || use_veto) ? s.cur_xy : nullptr;
+    if (use_veto) { a.boxes = s.boxes; a.n_boxes = veto->n_boxes; a.F = s.F; a.row_xy = s.row_xy; }
+    const bool want_scores = best_idx || best || second;
+    launch_greedy(a, 1, want_scores, st, &ctx->launches);
+    if (N) CU(cudaMemcpyAsync(claimed, s.claimed, (size_t)N, cudaMemcpyDeviceToHost, st));
+    if (N && claim_row) CU(cudaMemcpyAsync(claim_row, s.claim_row, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
+    if (best_idx) CU(cudaMemcpyAsync(best_idx, s.p2_best_idx, sizeof(int) * M, cudaMemcpyDeviceToHost, st));
+    if (best) CU(cudaMemcpyAsync(best, s.p2_best, sizeof(int) * M, cudaMemcpyDeviceToHost, st));
+    if (second) CU(cudaMemcpyAsync(second, s.p2_second, sizeof(int) * M, cudaMemcpyDeviceToHost, st));
+    if (row_claimed) CU(cudaMemcpyAsync(row_claimed, s.p2_row_claimed, (size_t)M, cudaMemcpyDeviceToHost, st));
+    if (row_bad) CU(cudaMemcpyAsync(row_bad, s.p1_row_bad, (size_t)M, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    return M;
+}
+
+int svo_disp2depth(svo_ctx *ctx, const float *disp, float *depth, size_t n, float bf)
+{
+    if (!ctx || (n && (!disp || !depth))) return fail(ctx, SVO_E_INVALID, "svo_disp2depth: bad argument");
+    if (!n) return SVO_OK;
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = ctx->sync_st;
+    float *d_in = nullptr, *d_out = nullptr;
+    CU(cudaMallocAsync((void **)&d_in, n * sizeof(float), st));
+    CU(cudaMallocAsync((void **)&d_out, n * sizeof(float), st));
+    CU(cudaMemcpyAsync(d_in, disp, n * sizeof(float), cudaMemcpyDefault, st));
+    launch_disp2depth(d_in, d_out, n, bf, st, &ctx->launches);
+    CU(cudaMemcpyAsync(depth, d_out, n * sizeof(float), cudaMemcpyDefault, st));
+    CU(cudaFreeAsync(d_in, st));
+    CU(cudaFreeAsync(d_out, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    return SVO_OK;
+}
+
+// ----------------------------------------------------------------------------- batch API
+int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n)
+{
+    if (!ctx || lane_i < 0 || lane_i >= (int)ctx->lanes.size() || !frames || n < 1 || n > ctx->cfg.max_batch)
+        return fail(ctx, SVO_E_INVALID, "svo_batch_submit: bad argument");
+    Lane &L = ctx->lanes[lane_i];
+    if (L.busy) return fail(ctx, SVO_E_INVALID, "svo_batch_submit: lane %d still has a batch in flight", lane_i);
+    CU(cudaSetDevice(ctx->cfg.device));
+    const Geom &g = ctx->g;
+    const Bufs &b = ctx->b;
+    FrameBufs &fb = ctx->fb;
+    cudaStream_t st = L.st;
+    const int R = fb.row_stride, K = fb.col_stride, B = ctx->cfg.max_batch;
+    cudaEvent_t *ev = ctx->profiling ? L.ev : nullptr;
+    bool any_prev = false, any_map = false;
+    for (int i = 0; i < n; ++i) {
+        const svo_frame_in &f = frames[i];
+        if (!f.left || !f.right || f.stride < g.W || f.n_prev < 0 || f.n_map < 0 || f.n_prev > R || f.n_map > R ||
+            (f.n_prev && !f.prev_desc) || (f.n_map && !f.map_desc) || !(f.baseline > 0.f))
+            return fail(ctx, SVO_E_INVALID, "svo_batch_submit: frame %d has bad inputs", i);
+        any_prev |= f.n_prev > 0; any_map |= f.n_map > 0;
+    }
+    L.in.assign(frames, frames + n);
+    L.nframes = n;
+    if (ev) cudaEventRecord(ev[0], st);
+    // ---- H2D
+    int *hp = L.h.params;
+    for (int i = 0; i < n; ++i) {
+        const svo_frame_in &f = frames[i];
+        const int fi = L.frame0 + i;
+        TRY(upload_image(ctx, L.slot0 + 2 * i, f.left, f.stride, st));
+        TRY(upload_image(ctx, L.slot0 + 2 * i + 1, f.right, f.stride, st));
+        if (f.n_prev) {
+            CU(cudaMemcpyAsync(fb.prev + (size_t)fi * R * 32, f.prev_desc, (size_t)f.n_prev * 32, cudaMemcpyDefault, st));
+            if (f.prev_live) CU(cudaMemcpyAsync(fb.prev_live + (size_t)fi * R, f.prev_live, (size_t)f.n_prev, cudaMemcpyDefault, st));
+            else CU(cudaMemsetAsync(fb.prev_live + (size_t)fi * R, 1, (size_t)f.n_prev, st));
+        }
+        if (f.n_map) {
+            CU(cudaMemcpyAsync(fb.map + (size_t)fi * R * 32, f.map_desc, (size_t)f.n_map * 32, cudaMemcpyDefault, st));
+            if (f.map_prev_row && f.n_prev) CU(cudaMemcpyAsync(fb.map_prev + (size_t)fi * R, f.map_prev_row, sizeof(int) * f.n_map, cudaMemcpyDefault, st));
+            else CU(cudaMemsetAsync(fb.map_prev + (size_t)fi * R, 0xff, sizeof(int) * f.n_map, st));
+        }
+        hp[i] = f.n_prev; hp[B + i] = f.n_map;
+        memcpy(&hp[2 * B + i], &f.bf, 4); memcpy(&hp[3 * B + i], &f.baseline, 4);
+    }
+    // params live as [4][nframes_total] on the device; this lane owns columns frame0..frame0+B
+    const int FT = fb.nframes;
+    for (int k = 0; k < 4; ++k)
+        CU(cudaMemcpyAsync(fb.params + (size_t)k * FT + L.frame0, hp + (size_t)k * B, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(fb.claimed + (size_t)L.frame0 * K, 0, (size_t)n * K, st));
+    CU(cudaMemsetAsync(fb.claim_row + (size_t)L.frame0 * K, 0xff, sizeof(int) * (size_t)n * K, st));
+    // ---- extraction of 2n images
+    enqueue_extract(ctx, L.slot0, 2 * n, st, ev);
+    // ---- sparse stereo
+    const int *d_nprev = fb.params + L.frame0, *d_nmap = fb.params + FT + L.frame0;
+    StereoArgs sa;
+    sa.u_right = fb.u_right + (size_t)L.frame0 * K; sa.depth = fb.depth + (size_t)L.frame0 * K;
+    sa.match_r = fb.match_r + (size_t)L.frame0 * K; sa.sad = fb.sad + (size_t)L.frame0 * K;
+    sa.n_stereo = fb.n_stereo + L.frame0; sa.stride = K;
+    sa.bf = reinterpret_cast<const float *>(fb.params + 2 * (size_t)FT + L.frame0);
+    sa.baseline = reinterpret_cast<const float *>(fb.params + 3 * (size_t)FT + L.frame0);
+    launch_stereo(b, g, L.slot0, n, sa, st, &ctx->launches);
+    if (ev) cudaEventRecord(ev[9], st);
+    // ---- matching: BF (cur -> prev), greedy pass 1 (prev rows), greedy pass 2 (map rows)
+    // left images sit in even slots: consecutive frames' descriptor blocks are 2*kp_cap rows apart
+    const MatchSet cur = make_set(b.desc + (size_t)L.slot0 * g.kp_cap * 32, b.nkp + L.slot0, 2, g.kp_cap, 0, 2 * g.kp_cap);
+    if (any_prev) {
+        BfArgs ba;
+        ba.q = cur; ba.t = make_set(fb.prev + (size_t)L.frame0 * R * 32, d_nprev, 1, R, 0);
+        ba.idx = fb.bf_idx + (size_t)L.frame0 * K; ba.dist = fb.bf_dist + (size_t)L.frame0 * K;
+        ba.keep = fb.bf_keep + (size_t)L.frame0 * K; ba.min_dist = fb.min_dist + L.frame0;
+        launch_bf(ba, n, st, &ctx->launches);
+    }
+    GreedyArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.cols = cur;
+    ga.claimed = fb.claimed + (size_t)L.frame0 * K; ga.claim_row = fb.claim_row + (size_t)L.frame0 * K;
+    ga.claim_time = fb.claim_time + (size_t)L.frame0 * K;
+    ga.shortlist = fb.shortlist + (size_t)L.frame0 * R * SVO_SHORT_CAP; ga.short_cnt = fb.short_cnt + (size_t)L.frame0 * R;
+    if (any_prev) {
+        ga.rows = make_set(fb.prev + (size_t)L.frame0 * R * 32, d_nprev, 1, R, 0);
+        ga.mode = SVO_GREEDY_PASS1; ga.row_base = 0; ga.row_base_arr = nullptr;
+        ga.row_live = fb.prev_live + (size_t)L.frame0 * R;
+        ga.best_idx = fb.p1_best_idx + (size_t)L.frame0 * R; ga.best = fb.p1_best + (size_t)L.frame0 * R;
+        ga.second = fb.p1_second + (size_t)L.frame0 * R;
+        ga.row_claimed = fb.p1_row_claimed + (size_t)L.frame0 * R; ga.row_bad = nullptr;
+        launch_greedy(ga, n, true, st, &ctx->launches);
+    }
+    if (any_map) {
+        ga.rows = make_set(fb.map + (size_t)L.frame0 * R * 32, d_nmap, 1, R, 0);
+        ga.mode = SVO_GREEDY_PASS2; ga.row_base = 0; ga.row_base_arr = d_nprev;
+        ga.row_live = nullptr;
+        ga.map_prev_row = any_prev ? fb.map_prev + (size_t)L.frame0 * R : nullptr;
+        ga.prev_row_claimed = fb.p1_row_claimed + (size_t)L.frame0 * R; ga.prev_stride = R;
+        ga.best_idx = nullptr; ga.best = nullptr; ga.second = nullptr;
+        ga.row_claimed = fb.p2_row_claimed + (size_t)L.frame0 * R; ga.row_bad = nullptr;
+        launch_greedy(ga, n, false, st, &ctx->launches);
+    }
+    if (ev) cudaEventRecord(ev[10], st);
+    // ---- D2H: one copy per output array for the whole batch
+    HostArena &h = L.h;
+    const size_t I = 2 * (size_t)n, KC = g.kp_cap;
+    CU(cudaMemcpyAsync(h.nkp, b.nkp + L.slot0, sizeof(int) * I, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h.status, b.status + L.slot0, sizeof(int) * I, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h.kp, b.kp + (size_t)L.slot0 * KC, sizeof(svo_keypoint) * I * KC, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h.desc, b.desc + (size_t)L.slot0 * KC * 32, I * KC * 32, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h.u_right, sa.u_right, sizeof(float) * n * KC, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h.depth, sa.depth, sizeof(float) * n * KC, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h.n_stereo, sa.n_stereo, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    if (any_prev) {
+        CU(cudaMemcpyAsync(h.bf_idx, fb.bf_idx + (size_t)L.frame0 * K, sizeof(int) * n * KC, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h.bf_dist, fb.bf_dist + (size_t)L.frame0 * K, sizeof(int) * n * KC, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h.bf_keep, fb.bf_keep + (size_t)L.frame0 * K, (size_t)n * KC, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h.p1_best_idx, fb.p1_best_idx + (size_t)L.frame0 * R, sizeof(int) * n * R, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h.p1_best, fb.p1_best + (size_t)L.frame0 * R, sizeof(int) * n * R, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h.p1_second, fb.p1_second + (size_t)L.frame0 * R, sizeof(int) * n * R, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h.p1_row_claimed, fb.p1_row_claimed + (size_t)L.frame0 * R, (size_t)n * R, cudaMemcpyDeviceToHost, st));
+    }
+    if (any_map) CU(cudaMemcpyAsync(h.p2_row_claimed, fb.p2_row_claimed + (size_t)L.frame0 * R, (size_t)n * R, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h.claim_row, fb.claim_row + (size_t)L.frame0 * K, sizeof(int) * n * KC, cudaMemcpyDeviceToHost, st));
+    if (ev) cudaEventRecord(ev[11], st);
+    CU(cudaEventRecord(L.done, st));
+    CU(cudaGetLastError());
+    L.busy = true;
+    return SVO_OK;
+}
+
+int svo_batch_wait(svo_ctx *ctx, int lane_i)
+{
+    if (!ctx || lane_i < 0 || lane_i >= (int)ctx->lanes.size()) return fail(ctx, SVO_E_INVALID, "svo_batch_wait: bad lane");
+    Lane &L = ctx->lanes[lane_i];
+    if (!L.busy) return SVO_OK;
+    CU(cudaEventSynchronize(L.done));
+    L.busy = false;
+    CU(cudaGetLastError());
+    return SVO_OK;
+}
+
+int svo_batch_result(svo_ctx *ctx, int lane_i, int i, svo_frame_out *o)
+{
+    if (!ctx || !o || lane_i < 0 || lane_i >= (int)ctx->lanes.size()) return fail(ctx, SVO_E_INVALID, "svo_batch_result: bad argument");
+    Lane &L = ctx->lanes[lane_i];
+    if (L.busy) return fail(ctx, SVO_E_INVALID, "svo_batch_result: call svo_batch_wait first");
+    if (i < 0 || i >= L.nframes) return fail(ctx, SVO_E_INVALID, "svo_batch_result: frame %d of %d", i, L.nframes);
+    const size_t K = ctx->g.kp_cap, R = ctx->cfg.max_rows;
+    const HostArena &h = L.h;
+    const svo_frame_in &in = L.in[i];
+    memset(o, 0, sizeof(*o));
+    const int st = h.status[2 * i] | h.status[2 * i + 1];
+    o->n_left = h.nkp[2 * i]; o->n_right = h.nkp[2 * i + 1];
+    o->status = (st & SVO_STATUS_OVERFLOW) ? SVO_E_CAPACITY : SVO_OK;
+    if (o->n_left > (int)K) { o->n_left = (int)K; o->status = SVO_E_CAPACITY; }
+    if (o->n_right > (int)K) { o->n_right = (int)K; o->status = SVO_E_CAPACITY; }
+    o->n_stereo = h.n_stereo[i];
+    o->kp_left = h.kp + (2 * (size_t)i) * K; o->kp_right = h.kp + (2 * (size_t)i + 1) * K;
+    o->desc_left = h.desc + (2 * (size_t)i) * K * 32; o->desc_right = h.desc + (2 * (size_t)i + 1) * K * 32;
+    o->u_right = h.u_right + (size_t)i * K; o->depth = h.depth + (size_t)i * K;
+    if (in.n_prev) {
+        o->bf_idx = h.bf_idx + (size_t)i * K; o->bf_dist = h.bf_dist + (size_t)i * K; o->bf_keep = h.bf_keep + (size_t)i * K;
+        o->p1_best_idx = h.p1_best_idx + (size_t)i * R; o->p1_best = h.p1_best + (size_t)i * R;
+        o->p1_second = h.p1_second + (size_t)i * R; o->p1_row_claimed = h.p1_row_claimed + (size_t)i * R;
+    }
+    if (in.n_map) o->p2_row_claimed = h.p2_row_claimed + (size_t)i * R;
+    o->claim_row = h.claim_row + (size_t)i * K;
+    return SVO_OK;
+}
+
+int svo_batch_stage_ms(svo_ctx *ctx, int lane_i, float *ms, int n)
+{
+    if (!ctx || !ms || lane_i < 0 || lane_i >= (int)ctx->lanes.size()) return fail(ctx, SVO_E_INVALID, "svo_batch_stage_ms: bad argument");
+    if (!ctx->profiling) return fail(ctx, SVO_E_INVALID, "svo_batch_stage_ms: profiling is off");
+    Lane &L = ctx->lanes[lane_i];
+    if (L.busy) return fail(ctx, SVO_E_INVALID, "svo_batch_stage_ms: call svo_batch_wait first");
+    float v[12];
+    CU(cudaEventElapsedTime(&v[0], L.ev[0], L.ev[11]));
+    for (int k = 1; k < 12; ++k) CU(cudaEventElapsedTime(&v[k], L.ev[k - 1], L.ev[k]));
+    for (int k = 0; k < n && k < 12; ++k) ms[k] = v[k];
+    return n < 12 ? n : 12;
+}
+
+// ----------------------------------------------------------------------------- debug taps
+long long svo_debug_tap(svo_ctx *ctx, int cam, int what, int level, void *out, size_t cap_bytes)
+{
+    if (!ctx || cam < 0 || cam > 1 || level < 0 || level >= ctx->g.nlevels || !out)
+        return fail(ctx, SVO_E_INVALID, "svo_debug_tap: bad argument");
+    if (!ctx->sync_have[cam]) return fail(ctx, SVO_E_INVALID, "svo_debug_tap: nothing extracted on cam %d", cam);
+    CU(cudaSetDevice(ctx->cfg.device));
+    const Geom &g = ctx->g; const LevelGeom &L = g.lv[level]; const Bufs &b = ctx->b;
+    const int slot = ctx->sync_slot0 + cam;
+    CU(cudaDeviceSynchronize());
+    if (what == SVO_TAP_LEVEL || what == SVO_TAP_BLUR) {
+        const size_t need = (size_t)L.w * L.h;
+        if (cap_bytes < need) return fail(ctx, SVO_E_CAPACITY, "svo_debug_tap: need %zu bytes", need);
+        const uint8_t *src = (what == SVO_TAP_LEVEL ? b.pyr : b.blur) + (size_t)slot * g.pyr_bytes + L.off;
+        CU(cudaMemcpy2D(out, L.w, src, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+        return (long long)need;
+    }
+    int32_t *o = (int32_t *)out;
+    const size_t cap = cap_bytes / (3 * sizeof(int32_t));
+    if (what == SVO_TAP_FAST) {
+        if (L.nbands == 0) return 0;
+        std::vector<int> cnt(L.nbands);
+        CU(cudaMemcpy(cnt.data(), b.bandcnt + (size_t)slot * g.bandcnt_total + L.bandcnt_off, sizeof(int) * L.nbands, cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> band(L.band_cap);
+        size_t n = 0;
+        for (int bi = 0; bi < L.nbands; ++bi) {
+            if (cnt[bi] > L.band_cap) return fail(ctx, SVO_E_CAPACITY, "band overflow");
+            CU(cudaMemcpy(band.data(), b.bands + (size_t)slot * g.band_total + L.band_off + (size_t)bi * L.band_cap, sizeof(uint32_t) * cnt[bi], cudaMemcpyDeviceToHost));
+            for (int i = 0; i < cnt[bi]; ++i, ++n)
+                if (n < cap) { o[3 * n] = unpack_x(band[i]); o[3 * n + 1] = unpack_y(band[i]); o[3 * n + 2] = unpack_s(band[i]); }
+        }
+        return (long long)n;
+    }
+    if (what == SVO_TAP_SELECT1) {
+        int n = 0;
+        CU(cudaMemcpy(&n, b.kept1 + (size_t)slot * SVO_MAX_LEVELS + level, sizeof(int), cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> v(n > 0 ? n : 1);
+        CU(cudaMemcpy(v.data(), b.cval + (size_t)slot * g.cand_total + L.cand_off, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n && (size_t)i < cap; ++i) { o[3 * i] = unpack_x(v[i]); o[3 * i + 1] = unpack_y(v[i]); o[3 * i + 2] = unpack_s(v[i]); }
+        return n;
+    }
+    if (what == SVO_TAP_SELECT2) {
+        int n = 0;
+        CU(cudaMemcpy(&n, b.kept2 + (size_t)slot * SVO_MAX_LEVELS + level, sizeof(int), cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> v(n > 0 ? n : 1), k(n > 0 ? n : 1);
+        CU(cudaMemcpy(v.data(), b.val2 + (size_t)slot * g.total2 + L.off2, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(k.data(), b.key2 + (size_t)slot * g.total2 + L.off2, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n && (size_t)i < cap; ++i) { o[3 * i] = unpack_x(v[i]); o[3 * i + 1] = unpack_y(v[i]); o[3 * i + 2] = (int32_t)k[i]; }
+        return n;
+    }
+    return fail(ctx, SVO_E_INVALID, "svo_debug_tap: unknown tap %d", what);
+}
+
+int svo_debug_retain_best(svo_ctx *ctx, const float *resp, int n, int n_points, int depth_limit, int32_t *idx_out)
+{
+    if (!ctx || n < 0 || (n && (!resp || !idx_out))) return fail(ctx, SVO_E_INVALID, "svo_debug_retain_best: bad argument");
+    if (n == 0) return 0;
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = ctx->sync_st;
+    float *key; uint32_t *val, *lp, *rp; int *kept;
+    CU(cudaMalloc((void **)&key, sizeof(float) * n)); CU(cudaMalloc((void **)&val, sizeof(uint32_t) * n));
+    CU(cudaMalloc((void **)&lp, sizeof(uint32_t) * n)); CU(cudaMalloc((void **)&rp, sizeof(uint32_t) * n));
+    CU(cudaMalloc((void **)&kept, 2 * sizeof(int)));
+    std::vector<uint32_t> iota(n);
+    for (int i = 0; i < n; ++i) iota[i] = (uint32_t)i;
+    CU(cudaMemcpyAsync(key, resp, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(val, iota.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(kept, 0, 2 * sizeof(int), st));
+    launch_retain_best_raw(key, val, n, n_points, depth_limit, lp, rp, kept, kept + 1, st, &ctx->launches);
+    int k = 0;
+    CU(cudaMemcpyAsync(&k, kept, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    if (k > 0) CU(cudaMemcpy(idx_out, val, sizeof(uint32_t) * k, cudaMemcpyDeviceToHost));
+    cudaFree(key); cudaFree(val); cudaFree(lp); cudaFree(rp); cudaFree(kept);
+    return k;
+}
+
+}  // extern "C"

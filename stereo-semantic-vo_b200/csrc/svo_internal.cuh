@@ -1,0 +1,149 @@
+// svo_internal.cuh — shared layout of the device-resident front-end state.
+//
+// HBM layout (all sized once in svo_create, nothing allocated per frame):
+//   one "image slot" per image in flight (2 per stereo frame), each holding
+//     pyr   : the 8 un-blurred pyramid levels, rows padded to 16 B (level offsets 256-B aligned)
+//     blur  : the 7x7 sigma-2 blurred levels, same layout
+//     bands : per level, per 8-row band, the raster-ordered FAST corners (packed u32)
+//     ckey/cval/lpos/rpos : per level candidate arrays the retainBest replay permutes
+//     key2/val2           : Harris-rescored survivors of the first cull
+//     kp/desc             : final keypoints (cv2 order) and 32-byte descriptors
+// Everything a frame touches (~10 MB at 1241x376) stays L2-resident on B200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/svo_b200.h"
+
+#define SVO_EDGE 31            // cv::ORB edgeThreshold
+#define SVO_FAST_BAND 8        // output rows per FAST band (one CTA each)
+#define SVO_SHORT_CAP 32       // short-list entries per greedy row before the full-scan path
+#define SVO_STATUS_OVERFLOW 1  // bit set in the per-image status word on a capacity overflow
+#define SVO_STATUS_DEPTH 2     // introselect reached its depth limit (heap-select path ran)
+
+struct LevelGeom {
+    int w, h, pitch;   // pitch: bytes per row, multiple of 16
+    int off;           // byte offset of the level inside a slot's pyramid buffer
+    float scale;       // (float)pow(1.2, l)
+    float inv_scale;   // 1.f / scale
+    int quota;         // nfeaturesPerLevel[l]
+    int x0, x1, y0, y1;  // keypoints live in [x0,x1) x [y0,y1) = [31, w-31) x [31, h-31)
+    int nbands;        // ceil((y1-y0)/SVO_FAST_BAND), 0 when the level is too small
+    int band_cap;      // entries per band list
+    int band_off;      // entry offset of this level's band lists inside a slot
+    int bandcnt_off;   // offset of this level's band counters
+    int cand_cap;      // candidate capacity (sum of band caps)
+    int cand_off;      // entry offset of the candidate arrays
+    int cap2;          // capacity after the first cull
+    int off2;          // entry offset of key2/val2
+    int tab_off;       // offset of this level's resize tables (x table then y table), level >= 1
+    int blur_tile_off; // first blur tile index of this level
+    int blur_tiles_x;  // blur tiles per row of tiles
+};
+
+struct Geom {
+    int nlevels, W, H;
+    int fast_threshold;
+    int pyr_bytes;       // per slot
+    int band_total;      // entries per slot
+    int bandcnt_total;   // counters per slot
+    int cand_total;      // entries per slot
+    int total2;          // entries per slot
+    int kp_cap;          // final keypoints per image
+    int blur_tiles;      // blur tiles per image
+    int fast_bands;      // FAST bands per image (sum of nbands)
+    LevelGeom lv[SVO_MAX_LEVELS];
+};
+
+// Base pointers of the slot arrays (index = slot * per-slot size + offset).
+struct Bufs {
+    uint8_t *pyr, *blur;
+    uint32_t *bands;
+    int *bandcnt;
+    float *ckey;
+    uint32_t *cval, *lpos, *rpos;
+    float *key2;
+    uint32_t *val2;
+    int *cnt1;    // [slot][8] candidates per level
+    int *kept1;   // [slot][8] survivors of the first cull
+    int *kept2;   // [slot][8] survivors of the second cull
+    svo_keypoint *kp;
+    uint8_t *desc;
+    int *nkp;     // [slot]
+    int *status;  // [slot]
+    const uint32_t *rtab;  // resize tables: (ofs << 9) | w1
+};
+
+// packed candidate: x | y << 12 | score << 24
+__host__ __device__ inline uint32_t pack_xy(int x, int y, int s) { return (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24); }
+__host__ __device__ inline int unpack_x(uint32_t v) { return (int)(v & 0xfffu); }
+__host__ __device__ inline int unpack_y(uint32_t v) { return (int)((v >> 12) & 0xfffu); }
+__host__ __device__ inline int unpack_s(uint32_t v) { return (int)(v >> 24); }
+
+// ---- stage launchers (each enqueues on `st` for images [slot0, slot0 + nimg)) ----
+void launch_pyramid(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches);
+void launch_fast(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches);
+void launch_select1(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches);
+void launch_harris(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches);
+void launch_select2(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches);
+void launch_blur(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches);
+void launch_describe(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches);
+int fast_smem_bytes(const Geom &g);
+int setup_fast_attributes(const Geom &g);
+
+// bare retainBest replay (debug/test entry)
+void launch_retain_best_raw(float *key, uint32_t *val, int n, int n_points, int depth_limit,
+                            uint32_t *lpos, uint32_t *rpos, int *kept_out, int *status, cudaStream_t st,
+                            long long *launches);
+
+// ---- stereo ----
+struct StereoArgs {
+    float *u_right, *depth;   // [frame][kp_cap]
+    int *match_r, *sad;       // [frame][kp_cap]
+    int *n_stereo;            // [frame]
+    int stride;               // entries per frame in the arrays above
+    const float *bf, *baseline;  // [frame]
+};
+void launch_stereo(const Bufs &b, const Geom &g, int slot0, int nframes, const StereoArgs &a, cudaStream_t st,
+                   long long *launches);
+
+// ---- matching ----
+struct MatchSet {            // one descriptor set per frame, fixed stride
+    const uint8_t *desc;     // [frame][stride_rows][32]
+    const int *count;        // [frame * count_stride] (device) or NULL -> use fixed_count
+    int count_stride;
+    int stride_rows;         // rows per frame in the per-row/per-column side arrays
+    int desc_stride;         // descriptor rows between consecutive frames' blocks
+    int fixed_count;
+};
+struct GreedyArgs {
+    MatchSet rows, cols;
+    int mode, row_base;
+    const int *row_base_arr;      // [frame] or NULL: per-frame row base added to row_base
+    const uint8_t *row_live;      // [frame][rows.stride_rows] or NULL
+    const int *map_prev_row;      // [frame][rows.stride_rows] or NULL (pass 2)
+    const uint8_t *prev_row_claimed;  // [frame][prev stride] (pass 2, with map_prev_row)
+    int prev_stride;
+    uint8_t *claimed;             // [frame][cols.stride_rows] in/out
+    int *claim_row;               // [frame][cols.stride_rows] in/out
+    int *claim_time;              // [frame][cols.stride_rows] scratch (global row that claimed, INT_MAX = free, -1 = pre-claimed)
+    int *best_idx, *best, *second;   // [frame][rows.stride_rows] or NULL
+    uint8_t *row_claimed;         // [frame][rows.stride_rows]
+    uint8_t *row_bad;             // [frame][rows.stride_rows] or NULL
+    uint32_t *shortlist;          // [frame][rows.stride_rows][SVO_SHORT_CAP]
+    int *short_cnt;               // [frame][rows.stride_rows]
+    const float *win_uvr;         // [frame][rows.stride_rows][3] or NULL
+    const float *cur_xy;          // [frame][cols.stride_rows][2] or NULL
+    // veto (pass 1)
+    const int *boxes; int n_boxes; const double *F; const float *row_xy;
+};
+void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStream_t st, long long *launches);
+
+struct BfArgs {
+    MatchSet q, t;
+    int *idx, *dist;      // [frame][q.stride_rows]
+    uint8_t *keep;        // [frame][q.stride_rows]
+    int *min_dist;        // [frame] scratch
+};
+void launch_bf(const BfArgs &a, int nframes, cudaStream_t st, long long *launches);
+void launch_disp2depth(const float *disp, float *depth, size_t n, float bf, cudaStream_t st, long long *launches);
+int setup_match_attributes();

@@ -1,0 +1,290 @@
+"""GPU parity: every stage of libsvo_b200.so (through the C ABI) against the CPU oracle and the
+committed OpenCV golden vectors.  Integer/byte/index work must be bit-exact; floats (angle,
+response, keypoint coordinates) are compared by bit pattern too; sparse-stereo sub-pixel
+disparity/depth within 1e-3 (north_star's tolerance)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def svo():
+    import svo as S
+    return S
+
+
+@pytest.fixture(scope="module")
+def ctxK(svo):
+    c = svo.Context(1241, 376, nfeatures=2000, max_batch=4, lanes=2, max_rows=5000)
+    yield c
+    c.close()
+
+
+def assert_kp_equal(kp, ref):
+    assert len(kp) == len(ref)
+    for f in ("x", "y", "size", "angle", "response"):
+        bad = np.nonzero(bits(kp[f]) != bits(ref[f]))[0]
+        assert len(bad) == 0, "%s differs at %s (%d of %d)" % (f, bad[:5], len(bad), len(ref))
+    assert (kp["octave"] == ref["octave"]).all()
+
+
+def test_geometry(ctxK):
+    lw, lh, ls, q = ctxK.geometry()
+    olw, olh, ols, oq = O.geometry(1241, 376, 8, 1.2, 2000)
+    assert (lw == olw).all() and (lh == olh).all() and (q == oq).all()
+    assert (bits(ls) == bits(ols)).all()
+
+
+def test_stages_vs_oracle(ctxK, svo):
+    """pyramid, blur, FAST list, first and second cull per level (order included)."""
+    img = synth.texture(synth.K_SHAPE, 31)
+    ctxK.extract(img, cam=0)
+    kp, desc, pyr = O.orb(img, 2000, with_pyramid=True)
+    lw, lh, ls, quota = O.geometry(1241, 376, 8, 1.2, 2000)
+    for l in range(8):
+        lev = pyr.level(l)
+        assert (ctxK.tap_image(0, l) == lev).all(), "pyramid level %d" % l
+        assert (ctxK.tap_image(0, l, blurred=True) == pyr.level(l, True)).all(), "blur level %d" % l
+        xs, ys, sc = O.fast_nms(lev, 20, 31)
+        f = ctxK.tap_list(0, svo.TAP_FAST, l)
+        assert len(f) == len(xs), "FAST count level %d: %d vs %d" % (l, len(f), len(xs))
+        assert (f[:, 0] == xs).all() and (f[:, 1] == ys).all() and (f[:, 2] == sc).all(), "FAST list level %d" % l
+        idx, _ = O.retain_best(sc.astype(np.float32), 2 * int(quota[l]))
+        s1 = ctxK.tap_list(0, svo.TAP_SELECT1, l)
+        assert len(s1) == len(idx), "first cull count level %d" % l
+        assert (s1[:, 0] == xs[idx]).all() and (s1[:, 1] == ys[idx]).all(), "first cull order level %d" % l
+        hr = O.harris(lev, xs[idx], ys[idx])
+        idx2, r2 = O.retain_best(hr, int(quota[l]))
+        s2 = ctxK.tap_list(0, svo.TAP_SELECT2, l)
+        assert len(s2) == len(idx2), "second cull count level %d" % l
+        assert (s2[:, 0] == xs[idx][idx2]).all() and (s2[:, 1] == ys[idx][idx2]).all(), "second cull order level %d" % l
+        assert (s2[:, 2].view(np.uint32) == bits(r2)).all(), "harris bits level %d" % l
+    O.pyramid_free(pyr)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(G, "k2000*.npz"))), ids=lambda p: os.path.basename(p)[:-4])
+def test_extract_vs_cv2_golden(ctxK, path):
+    g = np.load(path)
+    kp, desc = ctxK.extract(g["image"], cam=0)
+    assert_kp_equal(kp, g["kp"])
+    assert (desc == g["desc"]).all()
+
+
+@pytest.mark.parametrize("seed", [41, 42])
+def test_extract_vs_oracle(ctxK, seed):
+    img = synth.texture(synth.K_SHAPE, seed)
+    kp, desc = ctxK.extract(img, cam=1)
+    okp, odesc, _ = O.orb(img, 2000)
+    assert_kp_equal(kp, okp)
+    assert (desc == odesc).all()
+
+
+def test_extract_small_golden_and_other_sizes(svo):
+    g = np.load(os.path.join(G, "s500_seed21.npz"))
+    c = svo.Context(400, 240, nfeatures=500, max_rows=1000)
+    kp, desc = c.extract(g["image"])
+    assert_kp_equal(kp, g["kp"])
+    assert (desc == g["desc"]).all()
+    c.close()
+    # odd size, few features wanted, strided input
+    img = synth.texture((203, 330), 5)
+    c = svo.Context(317, 203, nfeatures=300, max_rows=1000)
+    kp, desc = c.extract(img[:, :317])
+    okp, odesc, _ = O.orb(np.ascontiguousarray(img[:, :317]), 300)
+    assert_kp_equal(kp, okp)
+    assert (desc == odesc).all()
+    # featureless image: zero keypoints, no error
+    kp, desc = c.extract(np.full((203, 317), 90, np.uint8))
+    assert len(kp) == 0
+    c.close()
+
+
+def test_extract_highres_8000(svo):
+    img = synth.texture(synth.H_SHAPE, 51)
+    c = svo.Context(2560, 720, nfeatures=8000, max_rows=8000)
+    kp, desc = c.extract(img)
+    okp, odesc, _ = O.orb(img, 8000)
+    assert_kp_equal(kp, okp)
+    assert (desc == odesc).all()
+    c.close()
+
+
+def test_retain_best_replay_vs_libstdcxx(ctxK):
+    """The on-device introselect/partition replay against std::nth_element/std::partition."""
+    rng = np.random.default_rng(0)
+    for trial in range(60):
+        n = int(rng.integers(1, 600)) if trial % 3 else int(rng.integers(600, 40000))
+        kind = trial % 4
+        if kind == 0:
+            resp = rng.integers(20, 60, n).astype(np.float32)
+        elif kind == 1:
+            resp = rng.normal(0, 1e-5, n).astype(np.float32)
+        elif kind == 2:
+            resp = np.sort(rng.integers(0, 1000, n)).astype(np.float32)
+        else:
+            resp = rng.integers(0, 3, n).astype(np.float32)
+        npts = int(rng.integers(0, n + 2))
+        ref, _ = O.retain_best(resp, npts)
+        got = ctxK.retain_best(resp, npts)
+        assert len(got) == len(ref) and (got == ref).all(), (trial, n, npts)
+
+
+def test_retain_best_forced_heap_select(ctxK):
+    import ctypes as C
+    rng = np.random.default_rng(1)
+    for trial in range(12):
+        n = int(rng.integers(5, 3000))
+        resp = rng.integers(0, 50, n).astype(np.float32)
+        npts = int(rng.integers(1, n))
+        for dl in (0, 1, 3):
+            k = resp.copy(); v = np.arange(n, dtype=np.int32)
+            O.lib().svo_o_introselect(k.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), n, npts - 1, dl)
+            amb = k[npts - 1]
+            got = ctxK.retain_best(resp, npts, depth_limit=dl)
+            assert (got[:npts] == v[:npts]).all(), (trial, n, npts, dl)
+            assert (resp[got[npts:]] >= amb).all()
+
+
+def test_match_bf_golden_and_oracle(ctxK):
+    g = np.load(os.path.join(G, "bfmatch.npz"))
+    idx, dist, keep = ctxK.match_bf(g["q"], g["t"])
+    assert (idx == g["train"]).all() and (dist.astype(np.float32) == g["dist"]).all()
+    rng = np.random.default_rng(2)
+    q = rng.integers(0, 256, (2100, 32), dtype=np.uint8); t = rng.integers(0, 256, (3001, 32), dtype=np.uint8)
+    t[5:900] = q[100:995]; t[1500] = t[7]
+    oi, od, ok = O.match_bf(q, t)
+    idx, dist, keep = ctxK.match_bf(q, t)
+    assert (idx == oi).all() and (dist == od).all() and (keep == ok).all()
+
+
+def noisy_copies(rng, base, n, ps=(0.0, 0.01, 0.03, 0.08, 0.2, 0.5)):
+    src = base[rng.integers(0, len(base), n)]
+    p = np.asarray(ps)[rng.integers(0, len(ps), n)]
+    flips = np.packbits(rng.random((n, 256)) < p[:, None], axis=1, bitorder="little")
+    return src ^ flips
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("seed", [0, 1])
+def test_match_greedy_vs_oracle(ctxK, mode, seed):
+    rng = np.random.default_rng(seed)
+    cur = rng.integers(0, 256, (1999, 32), dtype=np.uint8)
+    cur[300:340] = cur[100]                      # 41 identical columns: short-list overflow path
+    rows = noisy_copies(rng, cur, 3000)
+    rows[10:60] = cur[100]
+    claimed0 = (rng.random(len(cur)) < 0.05).astype(np.uint8)
+    live = (rng.random(len(rows)) < 0.9).astype(np.uint8)
+    ref = O.match_greedy(rows, cur, mode, claimed=claimed0, row_live=live, row_base=7)
+    got = ctxK.match_greedy(rows, cur, mode, claimed=claimed0, row_live=live, row_base=7)
+    for k in ("row_claimed", "claimed", "claim_row"):
+        assert (ref[k] == got[k]).all(), k
+    lv = live.astype(bool)
+    for k in ("best_idx", "best", "second"):
+        assert (ref[k][lv] == got[k][lv]).all(), k
+
+
+def test_match_greedy_window_and_edge_cases(ctxK):
+    rng = np.random.default_rng(3)
+    cur = rng.integers(0, 256, (500, 32), dtype=np.uint8)
+    rows = noisy_copies(rng, cur, 700)
+    cur_xy = rng.uniform(0, 1000, (500, 2)).astype(np.float32)
+    win = np.concatenate([rng.uniform(0, 1000, (700, 2)), rng.uniform(50, 400, (700, 1))], 1).astype(np.float32)
+    ref = O.match_greedy(rows, cur, 1, win_uvr=win, cur_xy=cur_xy)
+    got = ctxK.match_greedy(rows, cur, 1, win_uvr=win, cur_xy=cur_xy)
+    for k in ("row_claimed", "claimed", "claim_row", "best_idx", "best", "second"):
+        assert (ref[k] == got[k]).all(), k
+    # everything already claimed
+    got = ctxK.match_greedy(rows, cur, 0, claimed=np.ones(500, np.uint8))
+    assert not got["row_claimed"].any() and (got["best_idx"] == -1).all() and (got["best"] == 256).all()
+
+
+def test_disp2depth(ctxK):
+    rng = np.random.default_rng(4)
+    d = rng.uniform(-1, 60, 376 * 1241).astype(np.float32)
+    d[::7] = 0
+    assert (bits(ctxK.disp2depth(d, 379.8145)) == bits(O.disp2depth(d, 379.8145))).all()
+
+
+def stereo_oracle(L, R, nf, bf, b):
+    kl, dl, pl = O.orb(L, nf, with_pyramid=True)
+    kr, dr, pr = O.orb(R, nf, with_pyramid=True)
+    ur, dep, mr, sad = O.stereo_sparse(kl, dl, pl, kr, dr, pr, bf, b)
+    O.pyramid_free(pl); O.pyramid_free(pr)
+    return kl, dl, kr, dr, ur, dep, mr, sad
+
+
+def test_stereo_sparse_vs_oracle(ctxK):
+    cal = synth.KITTI_04_12
+    bf, b = cal["bf"], cal["bf"] / cal["fx"]
+    L, R, _ = synth.stereo_pair(synth.K_SHAPE, seed=61)
+    kl, dl, kr, dr, ur, dep, mr, sad = stereo_oracle(L, R, 2000, bf, b)
+    ctxK.extract(L, cam=0); ctxK.extract(R, cam=1)
+    gur, gdep, gmr, gsad = ctxK.stereo_sparse(bf, b)
+    assert len(gur) == len(ur)
+    valid = dep > 0
+    assert valid.sum() > 300, "synthetic pair should yield stereo matches (%d)" % valid.sum()
+    assert ((gdep > 0) == valid).all()
+    assert (gmr[valid] == mr[valid]).all() and (gsad[valid] == sad[valid]).all()
+    assert np.abs(gur[valid] - ur[valid]).max() <= 1e-3
+    assert (np.abs(gdep[valid] - dep[valid]) <= 1e-3 * np.abs(dep[valid])).all()
+    assert (gur[~valid] == -1).all() and (gdep[~valid] == -1).all()
+
+
+def test_batch_pipeline_vs_oracle(ctxK):
+    """Full per-frame front-end through svo_batch_submit on two lanes, checked against the oracle."""
+    cal = synth.KITTI_04_12
+    bf, b = np.float32(cal["bf"]), np.float32(cal["bf"] / cal["fx"])
+    seq = synth.Sequence(seed=2)
+    frames = [seq.frame(t) for t in range(4)]
+    ora = [stereo_oracle(L, R, 2000, bf, b) for L, R in frames]
+    rng = np.random.default_rng(9)
+    jobs = []
+    for t in range(1, 4):
+        prev_desc = ora[t - 1][1]
+        live = (ora[t - 1][5] > 0).astype(np.uint8)          # map points exist where stereo depth > 0
+        mp = synth.local_map([o[1] for o in ora[:t]], rows=5000, seed=t)
+        mpr = np.full(5000, -1, np.int32)
+        take = rng.permutation(5000)[:600]
+        src = rng.integers(0, len(prev_desc), 600)
+        mp[take] = prev_desc[src]; mpr[take] = src            # map rows that are the last frame's own points
+        jobs.append(dict(left=frames[t][0], right=frames[t][1], bf=float(bf), baseline=float(b),
+                         prev_desc=prev_desc, prev_live=live, map_desc=mp, map_prev_row=mpr))
+    ctxK.batch_submit(0, jobs[:2])
+    ctxK.batch_submit(1, jobs[2:])
+    ctxK.batch_wait(0); ctxK.batch_wait(1)
+    res = [ctxK.batch_result(0, 0), ctxK.batch_result(0, 1), ctxK.batch_result(1, 0)]
+    for t, (job, r) in enumerate(zip(jobs, res), start=1):
+        kl, dl, kr, dr, ur, dep, mr, sad = ora[t]
+        assert r["status"] == 0
+        assert_kp_equal(r["kp_left"], kl); assert_kp_equal(r["kp_right"], kr)
+        assert (r["desc_left"] == dl).all() and (r["desc_right"] == dr).all()
+        valid = dep > 0
+        assert ((r["depth"] > 0) == valid).all() and r["n_stereo"] == valid.sum()
+        assert np.abs(r["u_right"][valid] - ur[valid]).max() <= 1e-3
+        oi, od, ok = O.match_bf(dl, job["prev_desc"])
+        assert (r["bf_idx"] == oi).all() and (r["bf_dist"] == od).all() and (r["bf_keep"] == ok).all()
+        p1 = O.match_greedy(job["prev_desc"], dl, 0, row_live=job["prev_live"])
+        lv = job["prev_live"].astype(bool)
+        assert (r["p1_row_claimed"] == p1["row_claimed"]).all()
+        for k in ("best_idx", "best", "second"):
+            assert (r["p1_" + k][lv] == p1[k][lv]).all(), k
+        live2 = np.ones(5000, np.uint8)
+        m = job["map_prev_row"] >= 0
+        live2[m] = 1 - p1["row_claimed"][job["map_prev_row"][m]]
+        p2 = O.match_greedy(job["map_desc"], dl, 1, claimed=p1["claimed"], claim_row=p1["claim_row"],
+                            row_live=live2, row_base=len(job["prev_desc"]))
+        assert (r["p2_row_claimed"] == p2["row_claimed"]).all()
+        assert (r["claim_row"] == p2["claim_row"]).all()
+        assert p1["row_claimed"].sum() > 50 and p2["row_claimed"].sum() > 50
