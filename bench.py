@@ -1,0 +1,447 @@
+#!/usr/bin/env python3
+"""bench.py — per-frame stereo front-end throughput on B200 (BASELINE.json metric).
+
+One "step" = one batch of `--batch` stereo frames through the whole hot path: extract(L) +
+extract(R) + sparse stereo/SAD + BFMatcher(cur->prev) + greedy pass 1 (previous frame's map
+points) + greedy pass 2 (5k-row local map).  Workload = BASELINE.json configs[1]: a synthetic
+KITTI-shape (1241x376) stereo sequence with KITTI04-12 intrinsics, 2000 ORB features, 8 levels.
+
+  value : frames/s with every input already resident in HBM (device pointers into the C ABI)
+  e2e   : frames/s through the same C-ABI call with pinned HOST buffers — H2D of both images,
+          the previous-frame descriptors and the 5k-row map, and D2H of every result, all inside
+          the timed region.
+
+Multi-GPU (`torchrun ... bench.py --gpus N`): independent sequences, one per rank, no data-path
+collective ("replicas only"); torch.distributed is used for the barrier and the max-over-ranks.
+
+`--impl reference` times the reference's CPU implementation of the same path on all host cores
+(cv2.ORB, which is what frame.cc:77 calls, + the C port of the pnpmatch.cc loops and of the
+sparse-stereo stage from oracle/).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "stereo-semantic-vo_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import synth  # noqa: E402
+
+W_IMG, H_IMG, NFEAT, NLEVELS, MAP_ROWS = 1241, 376, 2000, 8, 5000
+CAL = synth.KITTI_04_12
+BF = float(np.float32(CAL["bf"]))
+BASELINE = float(np.float32(CAL["bf"] / CAL["fx"]))
+METRIC = "stereo_frames_per_sec"
+UNIT = "frames/s"
+
+
+def kp_cap(nf):
+    return (nf + nf // 8 + 64 + 63) // 64 * 64
+
+
+def level_sizes():
+    # cv::ORB geometry for 1241x376, scale 1.2, 8 levels
+    return [(1241, 376), (1034, 313), (862, 261), (718, 218), (598, 181), (499, 151), (416, 126), (346, 105)]
+
+
+def algorithmic_bytes_per_image():
+    """algorithmic bytes of each extraction kernel per image."""
+    px = [w * h for w, h in level_sizes()]
+    return {
+        "pyramid": sum(px[l - 1] + px[l] for l in range(1, 8)),
+        "fast": sum(px),
+        "blur": 2 * sum(px),
+        "harris": 2 * NFEAT * 81,
+        "describe": NFEAT * (512 + 32) + NFEAT * 749,
+    }
+
+
+def build_map(descs, live_prev, rng):
+    """5k-row local map for a frame from the 4 previous frames' left descriptors, padded with
+    bit-flipped copies; rows taken from the immediately previous frame carry map_prev_row."""
+    rows, prow = [], []
+    per = MAP_ROWS // 4
+    for age, d in enumerate(descs):            # descs[0] = frame t-1, descs[1] = t-2, ...
+        take = rng.permutation(len(d))[:per]
+        rows.append(d[take])
+        prow.append(take.astype(np.int32) if age == 0 else np.full(len(take), -1, np.int32))
+    rows = np.concatenate(rows, 0); prow = np.concatenate(prow, 0)
+    k = 0
+    while len(rows) < MAP_ROWS:
+        need = MAP_ROWS - len(rows)
+        src = rows[rng.permutation(len(rows))[:need]]
+        flips = np.packbits(rng.random((len(src), 256)) < (0.02, 0.1, 0.5)[k % 3], axis=1, bitorder="little")
+        rows = np.concatenate([rows, src ^ flips], 0); prow = np.concatenate([prow, np.full(len(src), -1, np.int32)], 0)
+        k += 1
+    order = rng.permutation(MAP_ROWS)          # explicit, fixed scan order
+    return np.ascontiguousarray(rows[order]), np.ascontiguousarray(prow[order])
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.sm_max = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {getattr(nv, n): n[len("nvmlClocksEventReason"):] for n in dir(nv) if n.startswith("nvmlClocksEventReason")
+                 and isinstance(getattr(nv, n), int)}
+        if not names:
+            names = {getattr(nv, n): n[len("nvmlClocksThrottleReason"):] for n in dir(nv)
+                     if n.startswith("nvmlClocksThrottleReason") and isinstance(getattr(nv, n), int)}
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, n in names.items():
+                    if bit and (r & bit) and n not in ("None", "GpuIdle", "All"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def result(self):
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import svo
+    dev = local_rank
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    B, P = args.batch, args.pool
+    ctx = svo.Context(W_IMG, H_IMG, nfeatures=NFEAT, nlevels=NLEVELS, max_batch=B, lanes=args.lanes,
+                      max_rows=MAP_ROWS, device=dev)
+    # ---- synthetic sequence (one per rank): pool of P distinct stereo frames in pinned memory
+    seq = synth.Sequence((H_IMG, W_IMG), seed=rank)
+    rng = np.random.default_rng(1000 + rank)
+    pitch = W_IMG
+    hl = ctx.pinned_array((P, H_IMG, pitch)); hr = ctx.pinned_array((P, H_IMG, pitch))
+    for t in range(P):
+        L, R = seq.frame(t)
+        hl[t] = L; hr[t] = R
+    # ---- untimed setup pass: extract the pool once to obtain the previous-frame descriptors and maps
+    K = kp_cap(NFEAT)
+    descs, lives = [], []
+    for t0 in range(0, P, B):
+        n = min(B, P - t0)
+        ctx.batch_submit(0, [dict(left=hl[t0 + i], right=hr[t0 + i], bf=BF, baseline=BASELINE) for i in range(n)])
+        ctx.batch_wait(0)
+        for i in range(n):
+            r = ctx.batch_result(0, i)
+            assert r["status"] == 0
+            descs.append(r["desc_left"]); lives.append((r["depth"] > 0).astype(np.uint8))
+    h_prev = ctx.pinned_array((P, K, 32)); h_live = ctx.pinned_array((P, K))
+    h_map = ctx.pinned_array((P, MAP_ROWS, 32)); h_mpr = ctx.pinned_array((P, MAP_ROWS), np.int32)
+    n_prev = np.zeros(P, np.int32)
+    for t in range(P):
+        prev = [descs[(t - a) % P] for a in range(1, 5)]
+        n_prev[t] = len(prev[0])
+        h_prev[t, :n_prev[t]] = prev[0]; h_live[t, :n_prev[t]] = lives[(t - 1) % P]
+        h_map[t], h_mpr[t] = build_map(prev, lives[(t - 1) % P], rng)
+    # device-resident copies for the `value` measurement
+    d_l, d_r = ctx.to_device(hl), ctx.to_device(hr)
+    d_prev, d_live, d_map, d_mpr = ctx.to_device(h_prev), ctx.to_device(h_live), ctx.to_device(h_map), ctx.to_device(h_mpr)
+    img_b = H_IMG * pitch
+
+    def frame_host(t):
+        return dict(left=hl[t], right=hr[t], bf=BF, baseline=BASELINE, prev_desc=h_prev[t, :n_prev[t]],
+                    prev_live=h_live[t, :n_prev[t]], map_desc=h_map[t], map_prev_row=h_mpr[t])
+
+    class Raw:  # minimal stand-in so svo.batch_submit takes raw device addresses
+        def __init__(self, addr):
+            self.ctypes = type("c", (), {"data": addr})()
+
+    def frame_dev(t):
+        return dict(left=d_l + t * img_b, right=d_r + t * img_b, stride=pitch, bf=BF, baseline=BASELINE,
+                    prev_desc=d_prev + t * K * 32, n_prev=int(n_prev[t]), prev_live=Raw(d_live + t * K),
+                    map_desc=d_map + t * MAP_ROWS * 32, n_map=MAP_ROWS, map_prev_row=Raw(d_mpr + t * MAP_ROWS * 4))
+
+    streams = [torch.cuda.ExternalStream(ctx.lane_stream(l), device=dev) for l in range(args.lanes)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(make_frame, steps, warmup, profile):
+        cursor = [0]
+
+        def submit(lane):
+            ts = [(cursor[0] + i) % P for i in range(B)]
+            cursor[0] = (cursor[0] + B) % P
+            ctx.batch_submit(lane, [make_frame(t) for t in ts])
+
+        for s in range(warmup):
+            lane = s % args.lanes
+            ctx.batch_wait(lane)
+            submit(lane)
+        for lane in range(args.lanes):
+            ctx.batch_wait(lane)
+        ctx.set_profiling(profile)
+        stage = {}
+        barrier()
+        launches0 = ctx.launch_count()
+        start = torch.cuda.Event(enable_timing=True)
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.lanes)]
+        start.record(streams[0])
+        for l in range(1, args.lanes):
+            streams[l].wait_event(start)
+        t0 = time.perf_counter()
+        for s in range(steps):
+            lane = s % args.lanes
+            if s >= args.lanes:
+                ctx.batch_wait(lane)
+                if profile:
+                    for k, v in ctx.stage_ms(lane).items():
+                        stage[k] = stage.get(k, 0.0) + v
+            submit(lane)
+        for lane in range(args.lanes):
+            ends[lane].record(streams[lane])
+        for lane in range(args.lanes):
+            ctx.batch_wait(lane)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        barrier()
+        ms = max(start.elapsed_time(e) for e in ends)
+        launches = ctx.launch_count() - launches0
+        ctx.set_profiling(0)
+        if profile:
+            nprof = max(steps - args.lanes, 1)
+            stage = {k: v / nprof for k, v in stage.items()}
+        return ms, wall * 1e3, launches, stage
+
+    sampler = ClockSampler(dev)
+    sampler.start()
+    ms_dev, wall_dev, launches, stage = timed(frame_dev, args.steps, args.warmup, 1)
+    ms_e2e, wall_e2e, _, _ = timed(frame_host, args.steps, args.warmup, 0)
+    sampler.stop_flag = True
+    sampler.join(timeout=1)
+
+    # single-frame latency through the synchronous drop-in calls (p50 of 30 frames)
+    lat = []
+    for t in range(min(30, P)):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx.batch_submit(0, [frame_host(t)])
+        ctx.batch_wait(0)
+        lat.append((time.perf_counter() - t0) * 1e3)
+    p50 = float(np.median(lat))
+
+    tms = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = tms.tolist()
+    frames_total = args.steps * B * world
+    out = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        ab = algorithmic_bytes_per_image()
+        kernels = {k: stage.get(k, 0.0) for k in ("pyramid", "fast", "select1", "harris", "select2", "blur", "describe", "stereo", "match")}
+        dom = max(kernels, key=kernels.get)
+        nimg = 2 * B
+        alg = {"pyramid": ab["pyramid"] * nimg, "fast": ab["fast"] * nimg, "blur": ab["blur"] * nimg,
+               "harris": ab["harris"] * nimg, "describe": ab["describe"] * nimg,
+               "select1": 30000 * 8 * nimg, "select2": 2 * NFEAT * 8 * nimg,
+               "stereo": B * (2 * NFEAT * 56 + NFEAT * 2 * 11 * 21),
+               "match": B * ((NFEAT + NFEAT) * 32 + (NFEAT + NFEAT) * 32 + (MAP_ROWS + NFEAT) * 32)}
+        # the FAST launch is one kernel; pyramid is 7 launches (report per-launch averages)
+        nlaunch = {"pyramid": 7}.get(dom, 1)
+        dur_ms = kernels[dom] / nlaunch if kernels[dom] > 0 else float("nan")
+        achieved = alg[dom] / nlaunch / (dur_ms * 1e-3) / 1e9 if dur_ms == dur_ms and dur_ms > 0 else None
+        h2d = B * (2 * W_IMG * H_IMG + int(n_prev.mean()) * 33 + MAP_ROWS * 36 + 16)
+        d2h = 2 * B * (K * 56 + 8) + B * (K * 21 + 4) + B * MAP_ROWS * 14
+        out = {
+            "metric": METRIC, "value": frames_total / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (f32 for response, angle, sub-pixel)",
+            "data": "synthetic",
+            "config": {"workload": "configs[1]: synthetic KITTI-shape 1241x376 stereo sequence, KITTI04-12 intrinsics, "
+                                   "2000 ORB features / 8 levels / 1.2, full front-end: extract L+R, sparse stereo + SAD, "
+                                   "BF match vs previous frame, greedy pass 1 + pass 2 vs 5000-row local map",
+                       "frames_per_step": B, "lanes": args.lanes, "pool_frames": P,
+                       "l2": "inputs larger than L2: %d-frame pool = %.0f MB of images + %.0f MB of descriptors cycled"
+                             % (P, 2 * P * img_b / 1e6, P * (K * 33 + MAP_ROWS * 36) / 1e6),
+                       "parallelism": "replicas only: one independent sequence per GPU, no collective"},
+            "e2e": {"value": frames_total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": sampler.result(),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                         "launch_ms": dur_ms, "algorithmic_bytes_per_launch": alg[dom] / nlaunch,
+                         "note": "working set is L2-resident; the path is latency/issue bound, not HBM bound (DESIGN.md)"},
+            "stage_ms_per_step": kernels, "p50_ms_per_frame_single": p50, "wall_ms_per_step": wall_dev / args.steps,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(seq, cores=1, budget_s=args.cpu_seconds)
+    ctx.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+def _cpu_worker_init():
+    global _O, _cv2
+    from oracle import oracle as _O  # noqa: F401  (bench's cpu legs may execute oracle/)
+    try:
+        import cv2 as _cv2
+        _cv2.setNumThreads(1)
+    except Exception:
+        _cv2 = None
+
+
+def _cpu_extract(img):
+    if _cv2 is not None:
+        kp, desc = _cv2.ORB_create(nfeatures=NFEAT, scaleFactor=1.2, nlevels=NLEVELS).detectAndCompute(img, None)
+        k = np.array([(p.pt[0], p.pt[1], p.size, p.angle, p.response, p.octave) for p in kp], dtype=_O.KP_DTYPE)
+        return k, desc
+    k, d, _ = _O.orb(img, NFEAT)
+    return k, d
+
+
+def _cpu_frame(job):
+    """The reference's per-frame CPU front-end on one core (GUI, drawing, sleeps and per-row vector copies of
+    pnpmatch.cc removed): ORB on L and R, sparse stereo, BF match + greedy pass 1 + pass 2."""
+    L, R, prev_desc, prev_live, map_desc = job
+    t0 = time.perf_counter()
+    kl, dl = _cpu_extract(L)
+    kr, dr = _cpu_extract(R)
+    # the stereo stage needs the un-blurred pyramids; the oracle rebuilds them (cv2 does not expose them)
+    _, _, pl = _O.orb(L, 1, with_pyramid=True)
+    _, _, pr = _O.orb(R, 1, with_pyramid=True)
+    _O.stereo_sparse(kl, dl, pl, kr, dr, pr, BF, BASELINE)
+    _O.pyramid_free(pl); _O.pyramid_free(pr)
+    _O.match_bf(dl, prev_desc)
+    p1 = _O.match_greedy(prev_desc, dl, 0, row_live=prev_live)
+    _O.match_greedy(map_desc, dl, 1, claimed=p1["claimed"], claim_row=p1["claim_row"], row_base=len(prev_desc))
+    return time.perf_counter() - t0
+
+
+def _cpu_jobs(seq, n):
+    _cpu_worker_init()
+    rng = np.random.default_rng(77)
+    frames = [seq.frame(t) for t in range(n + 1)]
+    descs = [_cpu_extract(f[0])[1] for f in frames]
+    jobs = []
+    for t in range(1, n + 1):
+        prev = [descs[max(t - a, 0)] for a in range(1, 5)]
+        mp, _ = build_map(prev, None, rng)
+        jobs.append((frames[t][0], frames[t][1], prev[0], np.ones(len(prev[0]), np.uint8), mp))
+    return jobs
+
+
+def cpu_baseline(seq, cores, budget_s):
+    """Bounded sample of the same workload on the host (reported beside the GPU number; not the target)."""
+    jobs = _cpu_jobs(seq, 4)
+    t1 = _cpu_frame(jobs[0])                                 # warm-up + per-frame cost estimate
+    n = int(max(2, min(len(jobs) * 8, budget_s / max(t1, 1e-3))))
+    t0 = time.perf_counter()
+    for i in range(n):
+        _cpu_frame(jobs[i % len(jobs)])
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d frames of the same synthetic sequence on 1 core: %s ORB x2 + C port of pnpmatch.cc loops "
+                      "(-O2, popcnt) + sparse stereo (oracle/)" % (n, "cv2 %s" % _cv2.__version__ if _cv2 else "oracle C"),
+            "ms_per_frame": dt / n * 1e3}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU front-end on all host cores of the box (rank 0 only)."""
+    if rank != 0:
+        return None
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    seq = synth.Sequence((H_IMG, W_IMG), seed=0)
+    jobs = _cpu_jobs(seq, 4)
+    per_step = cores                                           # one frame per core per step
+    pool = mp.get_context("fork").Pool(cores, initializer=_cpu_worker_init)
+    work = [jobs[i % len(jobs)] for i in range(per_step)]
+    steps = max(1, min(args.steps, 12)); warm = max(1, min(args.warmup, 2))
+    for _ in range(warm):
+        pool.map(_cpu_frame, work)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        pool.map(_cpu_frame, work)
+    dt = time.perf_counter() - t0
+    pool.close()
+    v = steps * per_step / dt
+    sample = ("%d steps x %d frames (one per host core) of the same synthetic sequence; %s ORB x2 (what frame.cc:77 calls) + "
+              "C port of the pnpmatch.cc matching loops + sparse stereo" % (steps, per_step, "cv2 %s" % _cv2.__version__ if _cv2 else "oracle C"))
+    return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/int32 (f32 for response, angle, sub-pixel)", "data": "synthetic",
+            "config": {"workload": "configs[1]: synthetic KITTI-shape 1241x376 stereo sequence, 2000 ORB features, full front-end "
+                                   "(extract L+R, sparse stereo, BF + greedy pass 1 + pass 2 vs 5000-row map) on host cores",
+                       "frames_per_step": per_step},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="stereo frames per step")
+    ap.add_argument("--lanes", type=int, default=2)
+    ap.add_argument("--pool", type=int, default=160, help="distinct synthetic frames cycled (must exceed L2)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        _cpu_worker_init()
+        out = run_reference(args, rank, world)
+    else:
+        out = run_gpu(args, rank, world, local_rank)
+    if rank == 0 and out is not None:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -456,6 +456,19 @@ int svo_o_hamming(const uint8_t *a, const uint8_t *b)
     return dist;
 }
 
+/* Same distance with the popcnt instruction: what -O3 -march=native makes of the loops that
+ * call DescriptorDistance; used by the bulk matchers below so the CPU baseline is not
+ * handicapped by the SWAR form (tests check both agree). */
+static inline int ham256(const uint8_t *a, const uint8_t *b)
+{
+    uint64_t x[4], y[4];
+    memcpy(x, a, 32);
+    memcpy(y, b, 32);
+    return __builtin_popcountll(x[0] ^ y[0]) + __builtin_popcountll(x[1] ^ y[1]) +
+           __builtin_popcountll(x[2] ^ y[2]) + __builtin_popcountll(x[3] ^ y[3]);
+}
+int svo_o_hamming_popcnt(const uint8_t *a, const uint8_t *b) { return ham256(a, b); }
+
 /* B.2 BFMatcher(NORM_HAMMING).match: per query, first minimum over train
  * (src/pnpmatch.cc:266,278); then the keep filter of :281-299. */
 void svo_o_match_bf(const uint8_t *q, int nq, const uint8_t *t, int nt,
@@ -465,7 +478,7 @@ void svo_o_match_bf(const uint8_t *q, int nq, const uint8_t *t, int nt,
     for (int i = 0; i < nq; ++i) {
         int best = 1 << 30, bi = -1;
         for (int j = 0; j < nt; ++j) {
-            int d = svo_o_hamming(q + 32 * (size_t)i, t + 32 * (size_t)j);
+            int d = ham256(q + 32 * (size_t)i, t + 32 * (size_t)j);
             if (d < best) { best = d; bi = j; }
         }
         idx[i] = bi;
@@ -506,7 +519,7 @@ void svo_o_match_greedy(const uint8_t *rows, int M, const uint8_t *cur, int N, i
                 float r = win_uvr[3 * i + 2];
                 if (du < -r || du > r || dv < -r || dv > r) continue;
             }
-            int d = svo_o_hamming(rows + 32 * (size_t)i, cur + 32 * (size_t)j);
+            int d = ham256(rows + 32 * (size_t)i, cur + 32 * (size_t)j);
             if (d < bd) { sd = bd; bd = d; bi = j; }
         }
         best_idx[i] = bi; best[i] = bd; second[i] = sd;
@@ -569,7 +582,7 @@ int svo_o_stereo_sparse(const svo_o_keypoint *kl, const uint8_t *dl, int nl,
             if (kpR->octave < levelL - 1 || kpR->octave > levelL + 1) continue;
             float uR = kpR->x;
             if (uR >= minU && uR <= maxU) {
-                int d = svo_o_hamming(dl + 32 * (size_t)iL, dr + 32 * (size_t)iR);
+                int d = ham256(dl + 32 * (size_t)iL, dr + 32 * (size_t)iR);
                 if (d < bestDist) { bestDist = d; bestIdxR = iR; }
             }
         }

@@ -45,6 +45,7 @@ int svo_o_orb(const uint8_t *gray, int W, int H, int stride, int nfeatures, floa
 void svo_o_pyramid_free(svo_o_pyramid *p);
 
 int svo_o_hamming(const uint8_t *a, const uint8_t *b);
+int svo_o_hamming_popcnt(const uint8_t *a, const uint8_t *b);
 void svo_o_match_bf(const uint8_t *q, int nq, const uint8_t *t, int nt, int32_t *idx, int32_t *dist, uint8_t *keep);
 void svo_o_match_greedy(const uint8_t *rows, int M, const uint8_t *cur, int N, int mode,
                         const uint8_t *row_live, uint8_t *claimed, int32_t *claim_row, int row_base,

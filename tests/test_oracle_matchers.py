@@ -1,5 +1,7 @@
 """Oracle matchers vs literal pure-Python transcriptions of the reference loops
 (src/pnpmatch.cc:14-30, :75-95/:99-153 pass 1, :173-197 pass 2) on small cases."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -67,6 +69,7 @@ def test_hamming_swar_equals_popcount():
     b = rng.integers(0, 256, (200, 32), dtype=np.uint8)
     for x, y in zip(a, b):
         assert O.hamming(x, y) == ham(x, y)
+        assert O.lib().svo_o_hamming_popcnt(x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p)) == ham(x, y)
     assert O.hamming(a[0], a[0]) == 0
     assert O.hamming(np.zeros(32, np.uint8), np.full(32, 255, np.uint8)) == 256
 
