@@ -256,74 +256,103 @@ __device__ bool veto_dynamic(const GreedyArgs &a, int f, int row, int col)
     return false;
 }
 
-__global__ void __launch_bounds__(M_THREADS) k_resolve(GreedyArgs a, int max_rows)
+__global__ void __launch_bounds__(M_THREADS) k_resolve(GreedyArgs a, int max_rows, int pool_cap)
 {
     const int f = blockIdx.x;
     const int M = set_count(a.rows, f), N = set_count(a.cols, f);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int *rows_ne = reinterpret_cast<int *>(resolve_smem);              // non-empty live rows, ascending
-    uint8_t *claimed = resolve_smem + (size_t)max_rows * sizeof(int);  // N bytes
-    __shared__ int wcnt[M_WARPS];
-    __shared__ int n_ne;
+    // shared: [rows_ne: max_rows ints][row_off: max_rows ints][pool: pool_cap u32][claimed: N bytes]
+    int *rows_ne = reinterpret_cast<int *>(resolve_smem);   // (row | min(cnt, CAP+1) << 16) of rows that can claim, ascending
+    int *row_off = rows_ne + max_rows;                      // offset of the row's entries in `pool`
+    uint32_t *pool = reinterpret_cast<uint32_t *>(row_off + max_rows);
+    uint8_t *claimed = reinterpret_cast<uint8_t *>(pool + pool_cap);
+    __shared__ int wcnt[M_WARPS], wsz[M_WARPS];
+    __shared__ int n_ne, n_sz;
     const size_t ro = (size_t)f * a.rows.stride_rows, co = (size_t)f * a.cols.stride_rows;
     for (int j = tid; j < N; j += M_THREADS) claimed[j] = a.claimed[co + j];
 
-    auto alive = [&](int r) -> bool {
-        if (r >= M) return false;
-        if (a.short_cnt[ro + r] == 0) return false;
+    auto row_size = [&](int r) -> int {   // 0 = cannot claim, else min(cnt, CAP+1)
+        if (r >= M) return 0;
+        const int c = a.short_cnt[ro + r];
+        if (c == 0) return 0;
         if (a.map_prev_row) {
             const int pr = a.map_prev_row[ro + r];
-            if (pr >= 0 && a.prev_row_claimed[(size_t)f * a.prev_stride + pr]) return false;
+            if (pr >= 0 && a.prev_row_claimed[(size_t)f * a.prev_stride + pr]) return 0;
         }
-        return true;
+        return min(c, SVO_SHORT_CAP + 1);
     };
-    // ordered compaction of the rows that can possibly claim
+    // ordered compaction of the rows that can possibly claim, and of their short lists
     const int seg = (((M + M_WARPS - 1) / M_WARPS) + 31) & ~31;
     const int beg = warp * seg, end = min(beg + seg, M);
-    int c = 0;
-    for (int base = beg; base < end; base += 32) c += __popc(__ballot_sync(0xffffffffu, base + lane < end && alive(base + lane)));
-    if (lane == 0) wcnt[warp] = c;
-    __syncthreads();
-    int off = 0, tot = 0;
-    for (int w = 0; w < M_WARPS; ++w) { if (w < warp) off += wcnt[w]; tot += wcnt[w]; }
+    int c = 0, z = 0;
     for (int base = beg; base < end; base += 32) {
-        const bool k = base + lane < end && alive(base + lane);
-        const uint32_t m = __ballot_sync(0xffffffffu, k);
-        if (k) rows_ne[off + __popc(m & ((1u << lane) - 1u))] = base + lane;
+        const int s = base + lane < end ? row_size(base + lane) : 0;
+        c += __popc(__ballot_sync(0xffffffffu, s > 0));
+        z += __reduce_add_sync(0xffffffffu, s <= SVO_SHORT_CAP ? s : 0);
+    }
+    if (lane == 0) { wcnt[warp] = c; wsz[warp] = z; }
+    __syncthreads();
+    int off = 0, tot = 0, zoff = 0;
+    for (int w = 0; w < M_WARPS; ++w) { if (w < warp) { off += wcnt[w]; zoff += wsz[w]; } tot += wcnt[w]; }
+    for (int base = beg; base < end; base += 32) {
+        const int s = base + lane < end ? row_size(base + lane) : 0;
+        const int sz = s <= SVO_SHORT_CAP ? s : 0;
+        const uint32_t m = __ballot_sync(0xffffffffu, s > 0);
+        int inc = sz;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (s > 0) {
+            const int pos = off + __popc(m & ((1u << lane) - 1u));
+            rows_ne[pos] = (base + lane) | (s << 16);
+            row_off[pos] = zoff + inc - sz;
+        }
         off += __popc(m);
+        zoff += __shfl_sync(0xffffffffu, inc, 31);
     }
     if (tid == 0) n_ne = tot;
+    if (tid == M_THREADS - 1) n_sz = zoff;   // last lane of the last warp holds the grand total
     __syncthreads();
-    if (warp != 0) return;
-
+    const int total = n_ne, total_sz = n_sz;
     const uint8_t *rd = set_desc(a.rows, f), *cd = set_desc(a.cols, f);
     const float *cxy = a.cur_xy ? a.cur_xy + co * 2 : nullptr;
-    const int total = n_ne;
     const int rbase = a.row_base + (a.row_base_arr ? a.row_base_arr[f] : 0);
-    uint32_t e_next = 0xffffffffu;
-    int cnt_next = 0;
-    if (total > 0) {
-        const int r = rows_ne[0];
-        cnt_next = a.short_cnt[ro + r];
-        e_next = (lane < cnt_next && lane < SVO_SHORT_CAP) ? a.shortlist[(ro + r) * SVO_SHORT_CAP + lane] : 0xffffffffu;
-    }
-    for (int it = 0; it < total; ++it) {
-        const int r = rows_ne[it];
-        const uint32_t e = e_next;
-        const int cnt = cnt_next;
-        if (it + 1 < total) {  // prefetch the next row's list while this one is resolved
-            const int rn = rows_ne[it + 1];
-            cnt_next = a.short_cnt[ro + rn];
-            e_next = (lane < cnt_next && lane < SVO_SHORT_CAP) ? a.shortlist[(ro + rn) * SVO_SHORT_CAP + lane] : 0xffffffffu;
+    // chunks of consecutive rows whose short lists fit the shared pool: all warps stage a chunk,
+    // warp 0 resolves it sequentially out of shared memory
+    for (int cs = 0; cs < total;) {
+        const int base_off = row_off[cs];
+        int lo = cs + 1, hi = total;            // largest ce in (cs, total] with size(cs..ce) <= pool_cap
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            const int endoff = mid == total ? total_sz : row_off[mid];
+            if (endoff - base_off <= pool_cap) lo = mid; else hi = mid - 1;
         }
+        const int ce = lo;
+        for (int it = cs + warp; it < ce; it += M_WARPS) {
+            const int pk = rows_ne[it], r = pk & 0xffff, cnt = pk >> 16, o = row_off[it] - base_off;
+            if (cnt <= SVO_SHORT_CAP) {
+                const uint32_t *src = a.shortlist + (ro + r) * SVO_SHORT_CAP;
+                if (lane < cnt) pool[o + lane] = src[lane];
+                if (lane + 32 < cnt) pool[o + lane + 32] = src[lane + 32];
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            for (int it = cs; it < ce; ++it) {
+        const int pk = rows_ne[it], r = pk & 0xffff, cnt = pk >> 16, o = row_off[it] - base_off;
         int bd = 256, bi = -1, sd = 256;
         if (cnt <= SVO_SHORT_CAP) {
-            const int col = (int)(e & 0xffffu);
-            const bool valid = lane < cnt && !claimed[col];
-            const uint32_t kmin = __reduce_min_sync(0xffffffffu, valid ? e : 0xffffffffu);
+            const uint32_t e0 = lane < cnt ? pool[o + lane] : 0xffffffffu;
+            const uint32_t e1 = lane + 32 < cnt ? pool[o + lane + 32] : 0xffffffffu;
+            const int c0 = (int)(e0 & 0xffffu), c1 = (int)(e1 & 0xffffu);
+            const bool v0 = lane < cnt && !claimed[c0], v1 = lane + 32 < cnt && !claimed[c1];
+            const uint32_t kmin = __reduce_min_sync(0xffffffffu, min(v0 ? e0 : 0xffffffffu, v1 ? e1 : 0xffffffffu));
             if (kmin != 0xffffffffu) {
                 bd = (int)(kmin >> 16); bi = (int)(kmin & 0xffffu);
-                sd = (int)__reduce_min_sync(0xffffffffu, (valid && col < bi) ? (e >> 16) : 256u);
+                const uint32_t s0 = (v0 && c0 < bi) ? (e0 >> 16) : 256u, s1 = (v1 && c1 < bi) ? (e1 >> 16) : 256u;
+                sd = (int)__reduce_min_sync(0xffffffffu, min(s0, s1));
             }
         } else {
             // list overflow: exhaustive scan of this row against the live claim set
@@ -361,6 +390,10 @@ __global__ void __launch_bounds__(M_THREADS) k_resolve(GreedyArgs a, int max_row
             }
             __syncwarp();
         }
+            }   // rows of the chunk
+        }       // warp 0
+        __syncthreads();
+        cs = ce;
     }
 }
 
@@ -439,8 +472,13 @@ void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStrea
     const int T = a.mode == SVO_GREEDY_PASS1 ? 15 : 60;
     dim3 gs((maxM + M_WARPS * SL_ROWS_PER_WARP - 1) / (M_WARPS * SL_ROWS_PER_WARP), nframes);
     k_shortlist<<<gs, M_THREADS, 0, st>>>(a, T);
-    const size_t smem = (size_t)maxM * sizeof(int) + (size_t)maxN + 16;
-    k_resolve<<<nframes, M_THREADS, smem, st>>>(a, maxM);
+    // shared memory: row list + offsets + staged short lists + claim bytes
+    int pool_cap = (g_resolve_smem_limit - 2 * maxM * (int)sizeof(int) - maxN - 64) / (int)sizeof(uint32_t);
+    if (pool_cap > 8 * maxM + 64) pool_cap = 8 * maxM + 64;
+    if (pool_cap < SVO_SHORT_CAP) pool_cap = SVO_SHORT_CAP;
+    if (pool_cap < 0) pool_cap = 0;
+    const size_t smem = (size_t)2 * maxM * sizeof(int) + (size_t)pool_cap * sizeof(uint32_t) + (size_t)maxN + 16;
+    k_resolve<<<nframes, M_THREADS, smem, st>>>(a, maxM, pool_cap);
     *launches += 3;
     if (want_scores && a.best_idx) {
         dim3 gf((maxM + M_WARPS - 1) / M_WARPS, nframes);
