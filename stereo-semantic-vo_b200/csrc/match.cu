@@ -334,25 +334,42 @@ __global__ void __launch_bounds__(M_THREADS) k_resolve(GreedyArgs a, int max_row
             const int pk = rows_ne[it], r = pk & 0xffff, cnt = pk >> 16, o = row_off[it] - base_off;
             if (cnt <= SVO_SHORT_CAP) {
                 const uint32_t *src = a.shortlist + (ro + r) * SVO_SHORT_CAP;
-                if (lane < cnt) pool[o + lane] = src[lane];
-                if (lane + 32 < cnt) pool[o + lane + 32] = src[lane + 32];
+                for (int k = lane; k < cnt; k += 32) pool[o + k] = src[k];
             }
         }
         __syncthreads();
         if (warp == 0) {
+            // software pipeline: the next row's entries are fetched while this row is decided
+            int pk_n = rows_ne[cs], o_n = row_off[cs] - base_off;
+            uint32_t en[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) en[k] = (lane + 32 * k < (pk_n >> 16) && (pk_n >> 16) <= SVO_SHORT_CAP) ? pool[o_n + lane + 32 * k] : 0xffffffffu;
             for (int it = cs; it < ce; ++it) {
-        const int pk = rows_ne[it], r = pk & 0xffff, cnt = pk >> 16, o = row_off[it] - base_off;
+        const int pk = pk_n, r = pk & 0xffff, cnt = pk >> 16;
+        uint32_t e[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) e[k] = en[k];
+        if (it + 1 < ce) {
+            pk_n = rows_ne[it + 1]; o_n = row_off[it + 1] - base_off;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) en[k] = (lane + 32 * k < (pk_n >> 16) && (pk_n >> 16) <= SVO_SHORT_CAP) ? pool[o_n + lane + 32 * k] : 0xffffffffu;
+        }
         int bd = 256, bi = -1, sd = 256;
         if (cnt <= SVO_SHORT_CAP) {
-            const uint32_t e0 = lane < cnt ? pool[o + lane] : 0xffffffffu;
-            const uint32_t e1 = lane + 32 < cnt ? pool[o + lane + 32] : 0xffffffffu;
-            const int c0 = (int)(e0 & 0xffffu), c1 = (int)(e1 & 0xffffu);
-            const bool v0 = lane < cnt && !claimed[c0], v1 = lane + 32 < cnt && !claimed[c1];
-            const uint32_t kmin = __reduce_min_sync(0xffffffffu, min(v0 ? e0 : 0xffffffffu, v1 ? e1 : 0xffffffffu));
+            uint32_t key = 0xffffffffu;
+            bool v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v[k] = e[k] != 0xffffffffu && !claimed[e[k] & 0xffffu];
+                if (v[k]) key = min(key, e[k]);
+            }
+            const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
             if (kmin != 0xffffffffu) {
                 bd = (int)(kmin >> 16); bi = (int)(kmin & 0xffffu);
-                const uint32_t s0 = (v0 && c0 < bi) ? (e0 >> 16) : 256u, s1 = (v1 && c1 < bi) ? (e1 >> 16) : 256u;
-                sd = (int)__reduce_min_sync(0xffffffffu, min(s0, s1));
+                uint32_t s = 256u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (v[k] && (int)(e[k] & 0xffffu) < bi) s = min(s, e[k] >> 16);
+                sd = (int)__reduce_min_sync(0xffffffffu, s);
             }
         } else {
             // list overflow: exhaustive scan of this row against the live claim set
