@@ -256,7 +256,15 @@ __device__ bool veto_dynamic(const GreedyArgs &a, int f, int row, int col)
     return false;
 }
 
-__global__ void __launch_bounds__(M_THREADS) k_resolve(GreedyArgs a, int max_rows, int pool_cap)
+#define RES_THREADS 512
+#define RES_WARPS (RES_THREADS / 32)
+
+// Sequential semantics, parallel execution: the rows that can claim are taken in groups of
+// RES_WARPS consecutive rows.  Every warp decides one row against the claim set as of the start
+// of the group (speculation); a row's decision is exact unless an earlier row of the same group
+// claims a column that appears in its short list.  The maximal prefix of rows without such a
+// conflict is committed, and the next group starts at the first conflicting row.
+__global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_rows, int pool_cap)
 {
     const int f = blockIdx.x;
     const int M = set_count(a.rows, f), N = set_count(a.cols, f);
@@ -266,10 +274,12 @@ __global__ void __launch_bounds__(M_THREADS) k_resolve(GreedyArgs a, int max_row
     int *row_off = rows_ne + max_rows;                      // offset of the row's entries in `pool`
     uint32_t *pool = reinterpret_cast<uint32_t *>(row_off + max_rows);
     uint8_t *claimed = reinterpret_cast<uint8_t *>(pool + pool_cap);
-    __shared__ int wcnt[M_WARPS], wsz[M_WARPS];
+    __shared__ int wcnt[RES_WARPS], wsz[RES_WARPS];
     __shared__ int n_ne, n_sz;
+    __shared__ int g_col[RES_WARPS];     // column the row wants to claim, -1 none
+    __shared__ int g_flag[RES_WARPS];    // bit 0 = list conflict with an earlier row of the group, bit 1 = vetoed ("dynamic")
     const size_t ro = (size_t)f * a.rows.stride_rows, co = (size_t)f * a.cols.stride_rows;
-    for (int j = tid; j < N; j += M_THREADS) claimed[j] = a.claimed[co + j];
+    for (int j = tid; j < N; j += RES_THREADS) claimed[j] = a.claimed[co + j];
 
     auto row_size = [&](int r) -> int {   // 0 = cannot claim, else min(cnt, CAP+1)
         if (r >= M) return 0;
@@ -282,7 +292,7 @@ __global__ void __launch_bounds__(M_THREADS) k_resolve(GreedyArgs a, int max_row
         return min(c, SVO_SHORT_CAP + 1);
     };
     // ordered compaction of the rows that can possibly claim, and of their short lists
-    const int seg = (((M + M_WARPS - 1) / M_WARPS) + 31) & ~31;
+    const int seg = (((M + RES_WARPS - 1) / RES_WARPS) + 31) & ~31;
     const int beg = warp * seg, end = min(beg + seg, M);
     int c = 0, z = 0;
     for (int base = beg; base < end; base += 32) {
@@ -293,7 +303,7 @@ __global__ void __launch_bounds__(M_THREADS) k_resolve(GreedyArgs a, int max_row
     if (lane == 0) { wcnt[warp] = c; wsz[warp] = z; }
     __syncthreads();
     int off = 0, tot = 0, zoff = 0;
-    for (int w = 0; w < M_WARPS; ++w) { if (w < warp) { off += wcnt[w]; zoff += wsz[w]; } tot += wcnt[w]; }
+    for (int w = 0; w < RES_WARPS; ++w) { if (w < warp) { off += wcnt[w]; zoff += wsz[w]; } tot += wcnt[w]; }
     for (int base = beg; base < end; base += 32) {
         const int s = base + lane < end ? row_size(base + lane) : 0;
         const int sz = s <= SVO_SHORT_CAP ? s : 0;
@@ -313,14 +323,13 @@ __global__ void __launch_bounds__(M_THREADS) k_resolve(GreedyArgs a, int max_row
         zoff += __shfl_sync(0xffffffffu, inc, 31);
     }
     if (tid == 0) n_ne = tot;
-    if (tid == M_THREADS - 1) n_sz = zoff;   // last lane of the last warp holds the grand total
+    if (tid == RES_THREADS - 1) n_sz = zoff;   // the last warp ends at the grand total
     __syncthreads();
     const int total = n_ne, total_sz = n_sz;
     const uint8_t *rd = set_desc(a.rows, f), *cd = set_desc(a.cols, f);
     const float *cxy = a.cur_xy ? a.cur_xy + co * 2 : nullptr;
     const int rbase = a.row_base + (a.row_base_arr ? a.row_base_arr[f] : 0);
-    // chunks of consecutive rows whose short lists fit the shared pool: all warps stage a chunk,
-    // warp 0 resolves it sequentially out of shared memory
+    // chunks of consecutive rows whose short lists fit the shared pool
     for (int cs = 0; cs < total;) {
         const int base_off = row_off[cs];
         int lo = cs + 1, hi = total;            // largest ce in (cs, total] with size(cs..ce) <= pool_cap
@@ -330,7 +339,7 @@ __global__ void __launch_bounds__(M_THREADS) k_resolve(GreedyArgs a, int max_row
             if (endoff - base_off <= pool_cap) lo = mid; else hi = mid - 1;
         }
         const int ce = lo;
-        for (int it = cs + warp; it < ce; it += M_WARPS) {
+        for (int it = cs + warp; it < ce; it += RES_WARPS) {
             const int pk = rows_ne[it], r = pk & 0xffff, cnt = pk >> 16, o = row_off[it] - base_off;
             if (cnt <= SVO_SHORT_CAP) {
                 const uint32_t *src = a.shortlist + (ro + r) * SVO_SHORT_CAP;
@@ -338,78 +347,89 @@ __global__ void __launch_bounds__(M_THREADS) k_resolve(GreedyArgs a, int max_row
             }
         }
         __syncthreads();
-        if (warp == 0) {
-            // software pipeline: the next row's entries are fetched while this row is decided
-            int pk_n = rows_ne[cs], o_n = row_off[cs] - base_off;
-            uint32_t en[4];
+        for (int it0 = cs; it0 < ce;) {
+            const int ng = min(RES_WARPS, ce - it0);
+            // ---- 1. speculative decision of row it0 + warp against the claims as of the group start
+            uint32_t e[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+            int r = 0, cnt = 0, want = -1, flag = 0;
+            if (warp < ng) {
+                const int pk = rows_ne[it0 + warp], o = row_off[it0 + warp] - base_off;
+                r = pk & 0xffff; cnt = pk >> 16;
+                int bd = 256, bi = -1, sd = 256;
+                if (cnt <= SVO_SHORT_CAP) {
+                    uint32_t key = 0xffffffffu;
+                    bool v[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) en[k] = (lane + 32 * k < (pk_n >> 16) && (pk_n >> 16) <= SVO_SHORT_CAP) ? pool[o_n + lane + 32 * k] : 0xffffffffu;
-            for (int it = cs; it < ce; ++it) {
-        const int pk = pk_n, r = pk & 0xffff, cnt = pk >> 16;
-        uint32_t e[4];
+                    for (int k = 0; k < 4; ++k) {
+                        if (lane + 32 * k < cnt) e[k] = pool[o + lane + 32 * k];
+                        v[k] = e[k] != 0xffffffffu && !claimed[e[k] & 0xffffu];
+                        if (v[k]) key = min(key, e[k]);
+                    }
+                    const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
+                    if (kmin != 0xffffffffu) {
+                        bd = (int)(kmin >> 16); bi = (int)(kmin & 0xffffu);
+                        uint32_t s = 256u;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) e[k] = en[k];
-        if (it + 1 < ce) {
-            pk_n = rows_ne[it + 1]; o_n = row_off[it + 1] - base_off;
+                        for (int k = 0; k < 4; ++k) if (v[k] && (int)(e[k] & 0xffffu) < bi) s = min(s, e[k] >> 16);
+                        sd = (int)__reduce_min_sync(0xffffffffu, s);
+                    }
+                } else {
+                    // list overflow: exhaustive scan of this row against the claim set
+                    const Row R = load_row(rd, r);
+                    const float *win = a.win_uvr ? a.win_uvr + (ro + r) * 3 : nullptr;
+                    uint32_t key = 0xffffffffu;
+                    for (int j = lane; j < N; j += 32)
+                        if (!claimed[j] && in_window(win, cxy, j)) key = min(key, ((uint32_t)ham_global(R, cd, j) << 16) | (uint32_t)j);
+                    const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
+                    if (kmin != 0xffffffffu) {
+                        bd = (int)(kmin >> 16); bi = (int)(kmin & 0xffffu);
+                        uint32_t s = 256u;
+                        for (int j = lane; j < bi; j += 32)
+                            if (!claimed[j] && in_window(win, cxy, j)) s = min(s, (uint32_t)ham_global(R, cd, j));
+                        sd = (int)__reduce_min_sync(0xffffffffu, s);
+                    }
+                }
+                bool take = bi >= 0 && (a.mode == SVO_GREEDY_PASS1 ? bd < 15 : (bd < 30 && sd > 2 * bd));
+                if (take && a.mode == SVO_GREEDY_PASS1 && a.n_boxes > 0 && a.F) {
+                    int v = 0;
+                    if (lane == 0) v = veto_dynamic(a, f, r, bi);
+                    v = __shfl_sync(0xffffffffu, v, 0);
+                    if (v) { take = false; flag = 2; }
+                }
+                want = take ? bi : -1;
+                if (lane == 0) g_col[warp] = want;
+            }
+            __syncthreads();
+            // ---- 2. does an earlier row of the group claim a column of this row's list?
+            if (warp < ng) {
+                bool hit = false;
+                for (int j = 0; j < warp; ++j) {
+                    const int cj = g_col[j];
+                    if (cj < 0) continue;
+                    if (cnt > SVO_SHORT_CAP) hit = true;   // list unknown: be conservative
 #pragma unroll
-            for (int k = 0; k < 4; ++k) en[k] = (lane + 32 * k < (pk_n >> 16) && (pk_n >> 16) <= SVO_SHORT_CAP) ? pool[o_n + lane + 32 * k] : 0xffffffffu;
+                    for (int k = 0; k < 4; ++k) hit = hit || (int)(e[k] & 0xffffu) == cj && e[k] != 0xffffffffu;
+                }
+                if (__any_sync(0xffffffffu, hit)) flag |= 1;
+                if (lane == 0) g_flag[warp] = flag;
+            }
+            __syncthreads();
+            // ---- 3. commit the conflict-free prefix
+            int fd = ng;
+            for (int j = ng - 1; j >= 1; --j) if (g_flag[j] & 1) fd = j;
+            if (warp < fd && lane == 0) {
+                if (flag & 2) { if (a.row_bad) a.row_bad[ro + r] = 1; }
+                else if (want >= 0) {
+                    claimed[want] = 1;
+                    a.claimed[co + want] = 1;
+                    if (a.claim_row) a.claim_row[co + want] = rbase + r;
+                    a.claim_time[co + want] = rbase + r;
+                    a.row_claimed[ro + r] = 1;
+                }
+            }
+            __syncthreads();
+            it0 += fd;
         }
-        int bd = 256, bi = -1, sd = 256;
-        if (cnt <= SVO_SHORT_CAP) {
-            uint32_t key = 0xffffffffu;
-            bool v[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                v[k] = e[k] != 0xffffffffu && !claimed[e[k] & 0xffffu];
-                if (v[k]) key = min(key, e[k]);
-            }
-            const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
-            if (kmin != 0xffffffffu) {
-                bd = (int)(kmin >> 16); bi = (int)(kmin & 0xffffu);
-                uint32_t s = 256u;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) if (v[k] && (int)(e[k] & 0xffffu) < bi) s = min(s, e[k] >> 16);
-                sd = (int)__reduce_min_sync(0xffffffffu, s);
-            }
-        } else {
-            // list overflow: exhaustive scan of this row against the live claim set
-            const Row R = load_row(rd, r);
-            const float *win = a.win_uvr ? a.win_uvr + (ro + r) * 3 : nullptr;
-            uint32_t key = 0xffffffffu;
-            for (int j = lane; j < N; j += 32)
-                if (!claimed[j] && in_window(win, cxy, j)) key = min(key, ((uint32_t)ham_global(R, cd, j) << 16) | (uint32_t)j);
-            const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
-            if (kmin != 0xffffffffu) {
-                bd = (int)(kmin >> 16); bi = (int)(kmin & 0xffffu);
-                uint32_t s = 256u;
-                for (int j = lane; j < bi; j += 32)
-                    if (!claimed[j] && in_window(win, cxy, j)) s = min(s, (uint32_t)ham_global(R, cd, j));
-                sd = (int)__reduce_min_sync(0xffffffffu, s);
-            }
-        }
-        bool take = bi >= 0 && (a.mode == SVO_GREEDY_PASS1 ? bd < 15 : (bd < 30 && sd > 2 * bd));
-        if (take && a.mode == SVO_GREEDY_PASS1 && a.n_boxes > 0 && a.F) {
-            int v = 0;
-            if (lane == 0) v = veto_dynamic(a, f, r, bi);
-            v = __shfl_sync(0xffffffffu, v, 0);
-            if (v) {
-                take = false;
-                if (lane == 0 && a.row_bad) a.row_bad[ro + r] = 1;
-            }
-        }
-        if (take) {
-            if (lane == 0) {
-                claimed[bi] = 1;
-                a.claimed[co + bi] = 1;
-                if (a.claim_row) a.claim_row[co + bi] = rbase + r;
-                a.claim_time[co + bi] = rbase + r;
-                a.row_claimed[ro + r] = 1;
-            }
-            __syncwarp();
-        }
-            }   // rows of the chunk
-        }       // warp 0
-        __syncthreads();
         cs = ce;
     }
 }
@@ -495,7 +515,7 @@ void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStrea
     if (pool_cap < SVO_SHORT_CAP) pool_cap = SVO_SHORT_CAP;
     if (pool_cap < 0) pool_cap = 0;
     const size_t smem = (size_t)2 * maxM * sizeof(int) + (size_t)pool_cap * sizeof(uint32_t) + (size_t)maxN + 16;
-    k_resolve<<<nframes, M_THREADS, smem, st>>>(a, maxM, pool_cap);
+    k_resolve<<<nframes, RES_THREADS, smem, st>>>(a, maxM, pool_cap);
     *launches += 3;
     if (want_scores && a.best_idx) {
         dim3 gf((maxM + M_WARPS - 1) / M_WARPS, nframes);
