@@ -263,23 +263,23 @@ __device__ bool veto_dynamic(const GreedyArgs &a, int f, int row, int col)
 // RES_WARPS consecutive rows.  Every warp decides one row against the claim set as of the start
 // of the group (speculation); a row's decision is exact unless an earlier row of the same group
 // claims a column that appears in its short list.  The maximal prefix of rows without such a
-// conflict is committed, and the next group starts at the first conflicting row.
-__global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_rows, int pool_cap)
+// conflict is committed, and the next group starts at the first conflicting row.  Short lists are
+// read straight from global memory, prefetched one group ahead.
+__global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_rows)
 {
     const int f = blockIdx.x;
     const int M = set_count(a.rows, f), N = set_count(a.cols, f);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // shared: [rows_ne: max_rows ints][row_off: max_rows ints][pool: pool_cap u32][claimed: N bytes]
+    // shared: [rows_ne: max_rows ints][first_want: N ints][claimed: N bytes]
     int *rows_ne = reinterpret_cast<int *>(resolve_smem);   // (row | min(cnt, CAP+1) << 16) of rows that can claim, ascending
-    int *row_off = rows_ne + max_rows;                      // offset of the row's entries in `pool`
-    uint32_t *pool = reinterpret_cast<uint32_t *>(row_off + max_rows);
-    uint8_t *claimed = reinterpret_cast<uint8_t *>(pool + pool_cap);
-    __shared__ int wcnt[RES_WARPS], wsz[RES_WARPS];
-    __shared__ int n_ne, n_sz;
-    __shared__ int g_col[RES_WARPS];     // column the row wants to claim, -1 none
-    __shared__ int g_flag[RES_WARPS];    // bit 0 = list conflict with an earlier row of the group, bit 1 = vetoed ("dynamic")
+    int *first_want = rows_ne + max_rows;                   // lowest warp of the group that wants the column
+    uint8_t *claimed = reinterpret_cast<uint8_t *>(first_want + N);
+    __shared__ int wcnt[RES_WARPS];
+    __shared__ int n_ne;
+    __shared__ unsigned g_dirty[2], g_want[2];   // per-group bit sets (double buffered across groups)
     const size_t ro = (size_t)f * a.rows.stride_rows, co = (size_t)f * a.cols.stride_rows;
-    for (int j = tid; j < N; j += RES_THREADS) claimed[j] = a.claimed[co + j];
+    for (int j = tid; j < N; j += RES_THREADS) { claimed[j] = a.claimed[co + j]; first_want[j] = 0x7fffffff; }
+    if (tid < 2) { g_dirty[tid] = 0; g_want[tid] = 0; }
 
     auto row_size = [&](int r) -> int {   // 0 = cannot claim, else min(cnt, CAP+1)
         if (r >= M) return 0;
@@ -291,133 +291,114 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_r
         }
         return min(c, SVO_SHORT_CAP + 1);
     };
-    // ordered compaction of the rows that can possibly claim, and of their short lists
+    // ordered compaction of the rows that can possibly claim
     const int seg = (((M + RES_WARPS - 1) / RES_WARPS) + 31) & ~31;
     const int beg = warp * seg, end = min(beg + seg, M);
-    int c = 0, z = 0;
-    for (int base = beg; base < end; base += 32) {
-        const int s = base + lane < end ? row_size(base + lane) : 0;
-        c += __popc(__ballot_sync(0xffffffffu, s > 0));
-        z += __reduce_add_sync(0xffffffffu, s <= SVO_SHORT_CAP ? s : 0);
-    }
-    if (lane == 0) { wcnt[warp] = c; wsz[warp] = z; }
+    int c = 0;
+    for (int base = beg; base < end; base += 32) c += __popc(__ballot_sync(0xffffffffu, base + lane < end && row_size(base + lane) > 0));
+    if (lane == 0) wcnt[warp] = c;
     __syncthreads();
-    int off = 0, tot = 0, zoff = 0;
-    for (int w = 0; w < RES_WARPS; ++w) { if (w < warp) { off += wcnt[w]; zoff += wsz[w]; } tot += wcnt[w]; }
+    int off = 0, tot = 0;
+    for (int w = 0; w < RES_WARPS; ++w) { if (w < warp) off += wcnt[w]; tot += wcnt[w]; }
     for (int base = beg; base < end; base += 32) {
         const int s = base + lane < end ? row_size(base + lane) : 0;
-        const int sz = s <= SVO_SHORT_CAP ? s : 0;
         const uint32_t m = __ballot_sync(0xffffffffu, s > 0);
-        int inc = sz;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += t;
-        }
-        if (s > 0) {
-            const int pos = off + __popc(m & ((1u << lane) - 1u));
-            rows_ne[pos] = (base + lane) | (s << 16);
-            row_off[pos] = zoff + inc - sz;
-        }
+        if (s > 0) rows_ne[off + __popc(m & ((1u << lane) - 1u))] = (base + lane) | (s << 16);
         off += __popc(m);
-        zoff += __shfl_sync(0xffffffffu, inc, 31);
     }
     if (tid == 0) n_ne = tot;
-    if (tid == RES_THREADS - 1) n_sz = zoff;   // the last warp ends at the grand total
     __syncthreads();
-    const int total = n_ne, total_sz = n_sz;
+    const int total = n_ne;
     const uint8_t *rd = set_desc(a.rows, f), *cd = set_desc(a.cols, f);
     const float *cxy = a.cur_xy ? a.cur_xy + co * 2 : nullptr;
     const int rbase = a.row_base + (a.row_base_arr ? a.row_base_arr[f] : 0);
-    // chunks of consecutive rows whose short lists fit the shared pool
-    for (int cs = 0; cs < total;) {
-        const int base_off = row_off[cs];
-        int lo = cs + 1, hi = total;            // largest ce in (cs, total] with size(cs..ce) <= pool_cap
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            const int endoff = mid == total ? total_sz : row_off[mid];
-            if (endoff - base_off <= pool_cap) lo = mid; else hi = mid - 1;
-        }
-        const int ce = lo;
-        for (int it = cs + warp; it < ce; it += RES_WARPS) {
-            const int pk = rows_ne[it], r = pk & 0xffff, cnt = pk >> 16, o = row_off[it] - base_off;
+    const uint32_t *lists = a.shortlist + ro * SVO_SHORT_CAP;
+
+    auto fetch = [&](int it, uint32_t (&e)[4], int &pk) {
+        pk = it < total ? rows_ne[it] : 0;
+        const int r = pk & 0xffff, cnt = pk >> 16;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            e[k] = (cnt <= SVO_SHORT_CAP && lane + 32 * k < cnt) ? lists[(size_t)r * SVO_SHORT_CAP + lane + 32 * k] : 0xffffffffu;
+    };
+    uint32_t en[4];
+    int pk_n, it_n = warp;
+    fetch(it_n, en, pk_n);
+    unsigned par = 0;
+    for (int it0 = 0; it0 < total; par ^= 1u) {
+        const int ng = min(RES_WARPS, total - it0);
+        // ---- 1. speculative decision of row it0 + warp against the claims as of the group start
+        uint32_t e[4];
+        int pk;
+        if (it_n == it0 + warp) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) e[k] = en[k];
+            pk = pk_n;
+        } else fetch(it0 + warp, e, pk);          // the previous group committed only a prefix
+        it_n = it0 + ng + warp;                       // prefetch for the (likely) next group
+        fetch(it_n, en, pk_n);
+        const int r = pk & 0xffff, cnt = pk >> 16;
+        int want = -1, flag = 0;
+        if (warp < ng) {
+            int bd = 256, bi = -1, sd = 256;
             if (cnt <= SVO_SHORT_CAP) {
-                const uint32_t *src = a.shortlist + (ro + r) * SVO_SHORT_CAP;
-                for (int k = lane; k < cnt; k += 32) pool[o + k] = src[k];
+                uint32_t key = 0xffffffffu;
+                bool v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    v[k] = e[k] != 0xffffffffu && !claimed[e[k] & 0xffffu];
+                    if (v[k]) key = min(key, e[k]);
+                }
+                const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
+                if (kmin != 0xffffffffu) {
+                    bd = (int)(kmin >> 16); bi = (int)(kmin & 0xffffu);
+                    uint32_t s = 256u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) if (v[k] && (int)(e[k] & 0xffffu) < bi) s = min(s, e[k] >> 16);
+                    sd = (int)__reduce_min_sync(0xffffffffu, s);
+                }
+            } else {
+                // list overflow: exhaustive scan of this row against the claim set
+                const Row R = load_row(rd, r);
+                const float *win = a.win_uvr ? a.win_uvr + (ro + r) * 3 : nullptr;
+                uint32_t key = 0xffffffffu;
+                for (int j = lane; j < N; j += 32)
+                    if (!claimed[j] && in_window(win, cxy, j)) key = min(key, ((uint32_t)ham_global(R, cd, j) << 16) | (uint32_t)j);
+                const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
+                if (kmin != 0xffffffffu) {
+                    bd = (int)(kmin >> 16); bi = (int)(kmin & 0xffffu);
+                    uint32_t s = 256u;
+                    for (int j = lane; j < bi; j += 32)
+                        if (!claimed[j] && in_window(win, cxy, j)) s = min(s, (uint32_t)ham_global(R, cd, j));
+                    sd = (int)__reduce_min_sync(0xffffffffu, s);
+                }
             }
+            bool take = bi >= 0 && (a.mode == SVO_GREEDY_PASS1 ? bd < 15 : (bd < 30 && sd > 2 * bd));
+            if (take && a.mode == SVO_GREEDY_PASS1 && a.n_boxes > 0 && a.F) {
+                int v = 0;
+                if (lane == 0) v = veto_dynamic(a, f, r, bi);
+                v = __shfl_sync(0xffffffffu, v, 0);
+                if (v) { take = false; flag = 2; }
+            }
+            want = take ? bi : -1;
+            if (lane == 0 && want >= 0) { atomicMin(&first_want[want], warp); atomicOr(&g_want[par], 1u << warp); }
         }
         __syncthreads();
-        for (int it0 = cs; it0 < ce;) {
-            const int ng = min(RES_WARPS, ce - it0);
-            // ---- 1. speculative decision of row it0 + warp against the claims as of the group start
-            uint32_t e[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-            int r = 0, cnt = 0, want = -1, flag = 0;
-            if (warp < ng) {
-                const int pk = rows_ne[it0 + warp], o = row_off[it0 + warp] - base_off;
-                r = pk & 0xffff; cnt = pk >> 16;
-                int bd = 256, bi = -1, sd = 256;
-                if (cnt <= SVO_SHORT_CAP) {
-                    uint32_t key = 0xffffffffu;
-                    bool v[4];
+        // ---- 2. does an earlier row of the group claim a column of this row's list?
+        if (warp < ng) {
+            bool hit = false;
+            if (cnt > SVO_SHORT_CAP) hit = (g_want[par] & ((1u << warp) - 1u)) != 0;   // list unknown: be conservative
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (lane + 32 * k < cnt) e[k] = pool[o + lane + 32 * k];
-                        v[k] = e[k] != 0xffffffffu && !claimed[e[k] & 0xffffu];
-                        if (v[k]) key = min(key, e[k]);
-                    }
-                    const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
-                    if (kmin != 0xffffffffu) {
-                        bd = (int)(kmin >> 16); bi = (int)(kmin & 0xffffu);
-                        uint32_t s = 256u;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) if (v[k] && (int)(e[k] & 0xffffu) < bi) s = min(s, e[k] >> 16);
-                        sd = (int)__reduce_min_sync(0xffffffffu, s);
-                    }
-                } else {
-                    // list overflow: exhaustive scan of this row against the claim set
-                    const Row R = load_row(rd, r);
-                    const float *win = a.win_uvr ? a.win_uvr + (ro + r) * 3 : nullptr;
-                    uint32_t key = 0xffffffffu;
-                    for (int j = lane; j < N; j += 32)
-                        if (!claimed[j] && in_window(win, cxy, j)) key = min(key, ((uint32_t)ham_global(R, cd, j) << 16) | (uint32_t)j);
-                    const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
-                    if (kmin != 0xffffffffu) {
-                        bd = (int)(kmin >> 16); bi = (int)(kmin & 0xffffu);
-                        uint32_t s = 256u;
-                        for (int j = lane; j < bi; j += 32)
-                            if (!claimed[j] && in_window(win, cxy, j)) s = min(s, (uint32_t)ham_global(R, cd, j));
-                        sd = (int)__reduce_min_sync(0xffffffffu, s);
-                    }
-                }
-                bool take = bi >= 0 && (a.mode == SVO_GREEDY_PASS1 ? bd < 15 : (bd < 30 && sd > 2 * bd));
-                if (take && a.mode == SVO_GREEDY_PASS1 && a.n_boxes > 0 && a.F) {
-                    int v = 0;
-                    if (lane == 0) v = veto_dynamic(a, f, r, bi);
-                    v = __shfl_sync(0xffffffffu, v, 0);
-                    if (v) { take = false; flag = 2; }
-                }
-                want = take ? bi : -1;
-                if (lane == 0) g_col[warp] = want;
-            }
-            __syncthreads();
-            // ---- 2. does an earlier row of the group claim a column of this row's list?
-            if (warp < ng) {
-                bool hit = false;
-                for (int j = 0; j < warp; ++j) {
-                    const int cj = g_col[j];
-                    if (cj < 0) continue;
-                    if (cnt > SVO_SHORT_CAP) hit = true;   // list unknown: be conservative
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) hit = hit || (int)(e[k] & 0xffffu) == cj && e[k] != 0xffffffffu;
-                }
-                if (__any_sync(0xffffffffu, hit)) flag |= 1;
-                if (lane == 0) g_flag[warp] = flag;
-            }
-            __syncthreads();
-            // ---- 3. commit the conflict-free prefix
-            int fd = ng;
-            for (int j = ng - 1; j >= 1; --j) if (g_flag[j] & 1) fd = j;
-            if (warp < fd && lane == 0) {
+            for (int k = 0; k < 4; ++k) hit = hit || (e[k] != 0xffffffffu && first_want[e[k] & 0xffffu] < warp);
+            if (__any_sync(0xffffffffu, hit) && lane == 0) atomicOr(&g_dirty[par], 1u << warp);
+        }
+        __syncthreads();
+        // ---- 3. commit the conflict-free prefix; reset the per-group state
+        const unsigned dirty = g_dirty[par];
+        const int fd = dirty ? __ffs(dirty) - 1 : ng;
+        if (warp < ng && lane == 0) {
+            if (want >= 0) first_want[want] = 0x7fffffff;
+            if (warp < fd) {
                 if (flag & 2) { if (a.row_bad) a.row_bad[ro + r] = 1; }
                 else if (want >= 0) {
                     claimed[want] = 1;
@@ -427,10 +408,10 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_r
                     a.row_claimed[ro + r] = 1;
                 }
             }
-            __syncthreads();
-            it0 += fd;
         }
-        cs = ce;
+        if (tid == 0) { g_dirty[par ^ 1u] = 0; g_want[par ^ 1u] = 0; }
+        __syncthreads();
+        it0 += fd;
     }
 }
 
@@ -509,13 +490,9 @@ void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStrea
     const int T = a.mode == SVO_GREEDY_PASS1 ? 15 : 60;
     dim3 gs((maxM + M_WARPS * SL_ROWS_PER_WARP - 1) / (M_WARPS * SL_ROWS_PER_WARP), nframes);
     k_shortlist<<<gs, M_THREADS, 0, st>>>(a, T);
-    // shared memory: row list + offsets + staged short lists + claim bytes
-    int pool_cap = (g_resolve_smem_limit - 2 * maxM * (int)sizeof(int) - maxN - 64) / (int)sizeof(uint32_t);
-    if (pool_cap > 8 * maxM + 64) pool_cap = 8 * maxM + 64;
-    if (pool_cap < SVO_SHORT_CAP) pool_cap = SVO_SHORT_CAP;
-    if (pool_cap < 0) pool_cap = 0;
-    const size_t smem = (size_t)2 * maxM * sizeof(int) + (size_t)pool_cap * sizeof(uint32_t) + (size_t)maxN + 16;
-    k_resolve<<<nframes, RES_THREADS, smem, st>>>(a, maxM, pool_cap);
+    // shared memory: row list + per-column first-wanting-warp + claim bytes
+    const size_t smem = (size_t)maxM * sizeof(int) + (size_t)maxN * (sizeof(int) + 1) + 16;
+    k_resolve<<<nframes, RES_THREADS, smem, st>>>(a, maxM);
     *launches += 3;
     if (want_scores && a.best_idx) {
         dim3 gf((maxM + M_WARPS - 1) / M_WARPS, nframes);
