@@ -1,0 +1,32 @@
+// pnpmatch.h — drop-in for the reference's include/pnpmatch.h.  The Hamming work of
+// poseEstimationPnP (src/pnpmatch.cc:61-199) and find_feature_matches (:253-300) runs on the
+// device; findFundamentalMat / solvePnPRansac stay with whatever OpenCV the integrator links and
+// are reached through the two hooks below (they are outside the hot path).
+#pragma once
+#include <functional>
+#include <set>
+#include <vector>
+#include "frame.h"
+
+class pnpmatch {
+public:
+    static cv::Mat Cur_Tcw;
+
+    static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b);                      // :14-30
+    static int poseEstimationPnP(frame *cframe, frame &lastframe, std::set<mappoint *> &localmappoints,
+                                 cv::Mat &mVelocity, cv::Mat &K);                           // :33-251
+    static void find_feature_matches(const cv::Mat &img_1, const cv::Mat &img_2,
+                                     std::vector<cv::KeyPoint> &keypoints_1, std::vector<cv::KeyPoint> &keypoints_2,
+                                     std::vector<cv::DMatch> &matches);                     // :253-300
+    static int poseEstimation2D_2D(frame *CurrentFrame, frame &LastFrame, cv::Mat &K, cv::Mat &fundamental_matrix);  // :302-337
+
+    // The two matching passes on their own (what poseEstimationPnP runs before the PnP solve).
+    static int match_last_frame(frame *cur, frame &last, const cv::Mat &fundamental_matrix);        // pass 1
+    static int match_local_map(frame *cur, std::set<mappoint *> &localmappoints);                   // pass 2
+
+    // Host hooks (unset: the step is skipped).  F from matched points (cv::findFundamentalMat, :336);
+    // pose from 3D-2D pairs (cv::solvePnPRansac + Rodrigues, :227-247) returning a 4x4 CV_32F Tcl.
+    static std::function<cv::Mat(const std::vector<cv::Point2f> &, const std::vector<cv::Point2f> &)> fundamental_solver;
+    static std::function<bool(const std::vector<cv::Mat> &pts3d, const std::vector<cv::Point2f> &pts2d, const cv::Mat &K,
+                              cv::Mat &Tcl, int &inliers)> pnp_solver;
+};
