@@ -25,6 +25,21 @@ def lookup_depth(kp, ur, dep, bf, H, W):
         return np.where(d != 0, np.float32(bf) / d, np.float32(-1)).astype(np.float32)
 
 
+def expected_keypoints_r(kp, ur, dep, H, W):
+    """frame::computekeypoint_r over the scattered disparity image (rx sticks when disp == -1)."""
+    disp = np.full((H, W), -1, np.float32)
+    for i in np.nonzero(dep > 0)[0]:
+        disp[int(kp["y"][i]), int(kp["x"][i])] = kp["x"][i] - ur[i]
+    out = np.empty(len(kp), np.float32)
+    rx = np.float32(-1)
+    for i in range(len(kp)):
+        d = disp[int(kp["y"][i]), int(kp["x"][i])]
+        if d != -1:
+            rx = kp["x"][i] - d
+        out[i] = rx
+    return out
+
+
 def test_adapter_two_frames(tmp_path):
     exe = os.path.join(ADAPTER, "adapter_test")
     if not os.path.exists(exe):
@@ -74,8 +89,9 @@ def test_adapter_two_frames(tmp_path):
     valid = z1 > 0
     assert ((z > 0) == valid).all()
     assert (np.abs(z[valid] - z1[valid]) <= 2e-3 * z1[valid]).all()
-    own = dep1 > 0
-    assert np.abs(xr[own] - ur1[own]).max() <= 2e-3
+    exp_xr = expected_keypoints_r(k1, ur1, dep1, H, W)
+    assert np.abs(xr - exp_xr).max() <= 2e-3
+    assert (dep1 > 0).sum() > 200
     # pass 1: rows = last frame's keypoints that own a map point (depthimg > 0 at their pixel)
     live = (lookup_depth(k0, ur0, dep0, bf, H, W) > 0).astype(np.uint8)
     g1 = O.match_greedy(d0, d1, 0, row_live=live)
