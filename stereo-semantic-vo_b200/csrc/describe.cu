@@ -10,9 +10,6 @@
 
 #define DESC_WARPS 8
 
-__constant__ int8_t c_pattern[256 * 4] = {
-#include "../../include/svo_orb_pattern.inc"
-};
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 // cv::getGaussianKernel(7, 2, CV_32F), exact bits
 __constant__ uint32_t c_gauss[7] = {0x3d8fafb1u, 0x3e06387eu, 0x3e434a39u, 0x3e5d4ae0u,
@@ -76,10 +73,15 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_harris(Bufs b, Geom g, int 
 
 // ---------------------------------------------------------------------------------------
 // Blur: u8 -> f32 row pass (taps left to right) -> f32 column pass (centre, then symmetric
-// pairs) -> rint -> u8, reflect-101 borders.  One CTA per 128x16 tile, staged in shared memory.
+// pairs) -> rint -> u8, reflect-101 borders; every float op separately rounded.
+// One thread owns a 4-pixel-wide, BLUR_ROWS-tall strip: per row it reads the 12 bytes around
+// its quad as three aligned words (neighbouring lanes overlap, so these are L1 hits), turns
+// them into floats with a PRMT + FADD magic-number trick (keeps the XU pipe free), forms the 4
+// horizontal sums and pushes them into a 7-row register window from which the vertical pass
+// is taken.  No shared memory, no barriers; stores are one aligned word per row.
 // ---------------------------------------------------------------------------------------
-#define BLUR_TW 128
-#define BLUR_TH 16
+#define BLUR_ROWS 32
+#define BLUR_THREADS 128
 
 __device__ __forceinline__ int reflect101(int i, int n)
 {
@@ -88,48 +90,78 @@ __device__ __forceinline__ int reflect101(int i, int n)
     return i;
 }
 
-__global__ void __launch_bounds__(256) k_blur(Bufs b, Geom g, int slot0)
+__device__ __forceinline__ float byte_to_float(uint32_t word, int sel)
 {
-    __shared__ uint8_t s_in[BLUR_TH + 6][BLUR_TW + 8];
-    __shared__ float s_row[BLUR_TH + 6][BLUR_TW];
-    int tile = blockIdx.x, l = 0;
-    while (l + 1 < g.nlevels && tile >= g.lv[l + 1].blur_tile_off) ++l;
+    // bytes {b, 00, 00, 4B} = 2^23 + b as a float; subtracting 2^23 is exact
+    return __fsub_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440 | sel)), 8388608.f);
+}
+
+__global__ void __launch_bounds__(BLUR_THREADS) k_blur(Bufs b, Geom g, int slot0)
+{
+    int blk = blockIdx.x, l = 0;
+    while (l + 1 < g.nlevels && blk >= g.lv[l + 1].blur_tile_off) ++l;
     const LevelGeom &L = g.lv[l];
-    tile -= L.blur_tile_off;
-    const int ty = tile / L.blur_tiles_x, tx = tile - ty * L.blur_tiles_x;
-    const int x0 = tx * BLUR_TW, y0 = ty * BLUR_TH;
+    blk -= L.blur_tile_off;
+    const int quads = (L.w + 3) >> 2;                 // blur_tiles_x holds this too
+    const int item = blk * BLUR_THREADS + threadIdx.x;
+    const int strip = item / quads, cg = item - strip * quads;
+    const int y0 = strip * BLUR_ROWS, x0 = cg << 2;
+    if (y0 >= L.h) return;
     const int slot = slot0 + blockIdx.y;
     const uint8_t *img = b.pyr + (size_t)slot * g.pyr_bytes + L.off;
     uint8_t *out = b.blur + (size_t)slot * g.pyr_bytes + L.off;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
-        const int r = i / (BLUR_TW + 6), c = i - r * (BLUR_TW + 6);
-        const int yy = reflect101(y0 - 3 + r, L.h), xx = reflect101(x0 - 3 + c, L.w);
-        s_in[r][c] = img[(size_t)yy * L.pitch + xx];
-    }
-    __syncthreads();
+    const int sp = L.pitch;
     float gk[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) gk[k] = __uint_as_float(c_gauss[k]);
-    for (int i = tid; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
-        const int r = i / BLUR_TW, c = i - r * BLUR_TW;
-        float acc = __fmul_rn(gk[0], (float)s_in[r][c]);
+    const bool interior = x0 >= 4 && x0 + 6 < L.w;   // bytes x0-3 .. x0+6 all inside the row
+    float win[7][4];
 #pragma unroll
-        for (int k = 1; k < 7; ++k) acc = __fadd_rn(acc, __fmul_rn(gk[k], (float)s_in[r][c + k]));
-        s_row[r][c] = acc;
-    }
-    __syncthreads();
-    for (int i = tid; i < BLUR_TH * BLUR_TW; i += 256) {
-        const int r = i / BLUR_TW, c = i - r * BLUR_TW;
-        const int x = x0 + c, y = y0 + r;
-        if (x >= L.w || y >= L.h) continue;
-        float acc = __fmul_rn(gk[3], s_row[r + 3][c]);
+    for (int k = 0; k < 7; ++k)
 #pragma unroll
-        for (int k = 1; k <= 3; ++k)
-            acc = __fadd_rn(acc, __fmul_rn(gk[3 + k], __fadd_rn(s_row[r + 3 + k][c], s_row[r + 3 - k][c])));
-        int v = __float2int_rn(acc);
-        v = v < 0 ? 0 : (v > 255 ? 255 : v);
-        out[(size_t)y * L.pitch + x] = (uint8_t)v;
+        for (int j = 0; j < 4; ++j) win[k][j] = 0.f;
+    const int rows = min(BLUR_ROWS, L.h - y0);
+    for (int r0 = 0; r0 < rows + 6; r0 += 7) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const int r = r0 + k;                       // window row r <-> image row y0 + r - 3
+            if (r < rows + 6) {
+                const int yy = reflect101(y0 + r - 3, L.h);
+                const uint8_t *row = img + (size_t)yy * sp;
+                float f[10];
+                if (interior) {
+                    const uint32_t *w = reinterpret_cast<const uint32_t *>(row + x0 - 4);
+                    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+                    f[0] = byte_to_float(w0, 1); f[1] = byte_to_float(w0, 2); f[2] = byte_to_float(w0, 3);
+                    f[3] = byte_to_float(w1, 0); f[4] = byte_to_float(w1, 1); f[5] = byte_to_float(w1, 2); f[6] = byte_to_float(w1, 3);
+                    f[7] = byte_to_float(w2, 0); f[8] = byte_to_float(w2, 1); f[9] = byte_to_float(w2, 2);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) f[j] = (float)row[reflect101(x0 - 3 + j, L.w)];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float acc = __fmul_rn(gk[0], f[j]);
+#pragma unroll
+                    for (int t = 1; t < 7; ++t) acc = __fadd_rn(acc, __fmul_rn(gk[t], f[j + t]));
+                    win[k][j] = acc;
+                }
+                if (r >= 6) {                           // rows r-6 .. r are in the window: emit image row y0 + r - 6
+                    uint32_t packed = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float acc = __fmul_rn(gk[3], win[(k + 4) % 7][j]);
+                        acc = __fadd_rn(acc, __fmul_rn(gk[4], __fadd_rn(win[(k + 5) % 7][j], win[(k + 3) % 7][j])));
+                        acc = __fadd_rn(acc, __fmul_rn(gk[5], __fadd_rn(win[(k + 6) % 7][j], win[(k + 2) % 7][j])));
+                        acc = __fadd_rn(acc, __fmul_rn(gk[6], __fadd_rn(win[k][j], win[(k + 1) % 7][j])));
+                        int v = __float2int_rn(acc);
+                        v = max(0, min(255, v));
+                        packed |= (uint32_t)v << (8 * j);
+                    }
+                    *reinterpret_cast<uint32_t *>(out + (size_t)(y0 + r - 6) * sp + x0) = packed;
+                }
+            }
+        }
     }
 }
 
@@ -158,89 +190,84 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
     return a;
 }
 
-__global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(Bufs b, Geom g, int slot0)
+__global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(Bufs b, Geom g, int slot0, const int *__restrict__ pattern)
 {
-    __shared__ int8_t s_pat[4][8][32];  // [coord][bit j][lane]: conflict-free per-lane reads
-    const int l = blockIdx.y, slot = slot0 + blockIdx.z;
-    const LevelGeom &L = g.lv[l];
+    const int slot = slot0 + blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 1024; i += DESC_WARPS * 32) {
-        const int test = i >> 2, cidx = i & 3;       // test = 8*byte + bit
-        s_pat[cidx][test & 7][test >> 3] = c_pattern[i];
-    }
-    __syncthreads();
     const int *kept2 = b.kept2 + (size_t)slot * SVO_MAX_LEVELS;
-    int base = 0, total = 0;
+    // output index -> (level, index within level): levels are concatenated in order
+    const int oi = blockIdx.x * DESC_WARPS + warp;
+    int l = 0, base = 0, total = 0;
     for (int i = 0; i < g.nlevels; ++i) {
         const int k = kept2[i];
-        if (i < l) base += k;
+        if (oi >= total + k) { l = i + 1; base = total + k; }
         total += k;
     }
-    if (blockIdx.x == 0 && l == 0 && threadIdx.x == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         b.nkp[slot] = total;
         if (total > g.kp_cap) atomicOr(b.status + slot, SVO_STATUS_OVERFLOW);
     }
-    const int n = kept2[l];
+    if (oi >= total || oi >= g.kp_cap) return;
+    const LevelGeom &L = g.lv[l];
+    const int c = oi - base;
     const uint8_t *img = b.pyr + (size_t)slot * g.pyr_bytes + L.off;
     const uint8_t *blr = b.blur + (size_t)slot * g.pyr_bytes + L.off;
-    const float *key2 = b.key2 + (size_t)slot * g.total2 + L.off2;
-    const uint32_t *val2 = b.val2 + (size_t)slot * g.total2 + L.off2;
-    svo_keypoint *kp = b.kp + (size_t)slot * g.kp_cap;
-    uint8_t *desc = b.desc + (size_t)slot * g.kp_cap * 32;
     const int sp = L.pitch;
-    for (int c = blockIdx.x * DESC_WARPS + warp; c < n; c += gridDim.x * DESC_WARPS) {
-        const int oi = base + c;
-        if (oi >= g.kp_cap) continue;
-        const uint32_t e = val2[c];
-        const int x = unpack_x(e), y = unpack_y(e);
-        // intensity centroid over the radius-15 disc
-        const uint8_t *ctr = img + (size_t)y * sp + x;
-        int m10 = 0, m01 = 0;
-        const int u = lane - 15;
-        if (lane < 31) {
-#pragma unroll 1
-            for (int v = -15; v <= 15; ++v) {
-                const int av = v < 0 ? -v : v;
-                if (u >= -c_umax[av] && u <= c_umax[av]) {
-                    const int val = ctr[v * sp + u];
-                    m10 += u * val;
-                    m01 += v * val;
-                }
-            }
-        }
-        m10 = __reduce_add_sync(0xffffffffu, m10);
-        m01 = __reduce_add_sync(0xffffffffu, m01);
-        const float angle = fast_atan2_deg((float)m01, (float)m10);
-        // keypoint record
-        const float px = l ? __fmul_rn((float)x, L.scale) : (float)x;
-        const float py = l ? __fmul_rn((float)y, L.scale) : (float)y;
-        if (lane == 0) {
-            svo_keypoint k;
-            k.x = px; k.y = py; k.size = __fmul_rn(31.f, L.scale); k.angle = angle;
-            k.response = key2[c]; k.octave = l;
-            kp[oi] = k;
-        }
-        // rBRIEF on the blurred level around (cvRound(pt.x/scale), cvRound(pt.y/scale))
-        const int cx = __float2int_rn(__fmul_rn(px, L.inv_scale)), cy = __float2int_rn(__fmul_rn(py, L.inv_scale));
-        const float ang = __fmul_rn(angle, (float)(3.1415926535897932384626433832795 / 180.f));
-        float ca = 0.f, sa = 0.f;
-        if (lane == 0) { ca = (float)cos((double)ang); sa = (float)sin((double)ang); }
-        ca = __shfl_sync(0xffffffffu, ca, 0); sa = __shfl_sync(0xffffffffu, sa, 0);
-        const uint8_t *bc = blr + (size_t)cy * sp + cx;
-        int byte = 0;
+    const uint32_t e = b.val2[(size_t)slot * g.total2 + L.off2 + c];
+    const int x = unpack_x(e), y = unpack_y(e);
+    // lane i owns descriptor byte i: its 8 tests (x0,y0,x1,y1 as int8) are loop-invariant
+    int pat[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float x0 = (float)s_pat[0][j][lane], y0 = (float)s_pat[1][j][lane];
-            const float x1 = (float)s_pat[2][j][lane], y1 = (float)s_pat[3][j][lane];
-            const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sa)));
-            const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sa), __fmul_rn(y0, ca)));
-            const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sa)));
-            const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sa), __fmul_rn(y1, ca)));
-            const int v0 = bc[iy0 * sp + ix0], v1 = bc[iy1 * sp + ix1];
-            byte |= (v0 < v1) << j;
+    for (int j = 0; j < 8; ++j) pat[j] = pattern[8 * lane + j];
+    // intensity centroid over the radius-15 disc: lane <-> column u, rows |v| <= umax[|u|]
+    // (the disc is symmetric, so the row limit of column u is the column limit of row |u|)
+    const uint8_t *ctr = img + (size_t)y * sp + x;
+    const int u = lane - 15;
+    const int vm = lane < 31 ? c_umax[u < 0 ? -u : u] : -1;
+    int sum = 0, m01 = 0;
+#pragma unroll
+    for (int v = -15; v <= 15; ++v) {
+        if ((v < 0 ? -v : v) <= vm) {
+            const int val = ctr[v * sp + u];
+            sum += val;
+            m01 += v * val;
         }
-        desc[(size_t)oi * 32 + lane] = (uint8_t)byte;
     }
+    const int m10 = __reduce_add_sync(0xffffffffu, u * sum);
+    m01 = __reduce_add_sync(0xffffffffu, m01);
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+    const float px = l ? __fmul_rn((float)x, L.scale) : (float)x;
+    const float py = l ? __fmul_rn((float)y, L.scale) : (float)y;
+    if (lane == 0) {
+        svo_keypoint k;
+        k.x = px; k.y = py; k.size = __fmul_rn(31.f, L.scale); k.angle = angle;
+        k.response = b.key2[(size_t)slot * g.total2 + L.off2 + c]; k.octave = l;
+        b.kp[(size_t)slot * g.kp_cap + oi] = k;
+    }
+    // rBRIEF on the blurred level around (cvRound(pt.x/scale), cvRound(pt.y/scale))
+    const int cx = __float2int_rn(__fmul_rn(px, L.inv_scale)), cy = __float2int_rn(__fmul_rn(py, L.inv_scale));
+    const float ang = __fmul_rn(angle, (float)(3.1415926535897932384626433832795 / 180.f));
+    float ca = 0.f, sa = 0.f;
+    if (lane == 0) {
+        double ds, dc;
+        sincos((double)ang, &ds, &dc);
+        ca = (float)dc; sa = (float)ds;
+    }
+    ca = __shfl_sync(0xffffffffu, ca, 0); sa = __shfl_sync(0xffffffffu, sa, 0);
+    const uint8_t *bc = blr + (size_t)cy * sp + cx;
+    int byte = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float x0 = (float)(int8_t)(pat[j] & 0xff), y0 = (float)(int8_t)((pat[j] >> 8) & 0xff);
+        const float x1 = (float)(int8_t)((pat[j] >> 16) & 0xff), y1 = (float)(int8_t)((pat[j] >> 24) & 0xff);
+        const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sa)));
+        const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sa), __fmul_rn(y0, ca)));
+        const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sa)));
+        const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sa), __fmul_rn(y1, ca)));
+        const int v0 = bc[iy0 * sp + ix0], v1 = bc[iy1 * sp + ix1];
+        byte |= (v0 < v1) << j;
+    }
+    b.desc[((size_t)slot * g.kp_cap + oi) * 32 + lane] = (uint8_t)byte;
 }
 
 void launch_harris(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches)
@@ -255,15 +282,39 @@ void launch_harris(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream
 void launch_blur(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches)
 {
     dim3 grid(g.blur_tiles, nimg);
-    k_blur<<<grid, 256, 0, st>>>(b, g, slot0);
+    k_blur<<<grid, BLUR_THREADS, 0, st>>>(b, g, slot0);
     ++*launches;
 }
 
+static int *g_pattern_dev[64] = {nullptr};
+
+// The rBRIEF pattern as 256 packed int32 (x0 | y0<<8 | x1<<16 | y1<<24) in global memory of the current device.
+static const int *pattern_on_device()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return nullptr;
+    if (!g_pattern_dev[dev]) {
+        static const int8_t host_pat[1024] = {
+#include "../../include/svo_orb_pattern.inc"
+        };
+        int packed[256];
+        for (int t = 0; t < 256; ++t)
+            packed[t] = (int)((uint32_t)(uint8_t)host_pat[4 * t] | ((uint32_t)(uint8_t)host_pat[4 * t + 1] << 8) |
+                              ((uint32_t)(uint8_t)host_pat[4 * t + 2] << 16) | ((uint32_t)(uint8_t)host_pat[4 * t + 3] << 24));
+        int *p = nullptr;
+        if (cudaMalloc((void **)&p, sizeof(packed)) != cudaSuccess) return nullptr;
+        cudaMemcpy(p, packed, sizeof(packed), cudaMemcpyHostToDevice);
+        g_pattern_dev[dev] = p;
+    }
+    return g_pattern_dev[dev];
+}
+
+int setup_describe() { return pattern_on_device() ? 0 : 1; }
+
 void launch_describe(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches)
 {
-    int mx = 1;
-    for (int l = 0; l < g.nlevels; ++l) mx = g.lv[l].quota + 32 > mx ? g.lv[l].quota + 32 : mx;
-    dim3 grid((mx + DESC_WARPS - 1) / DESC_WARPS, g.nlevels, nimg);
-    k_describe<<<grid, DESC_WARPS * 32, 0, st>>>(b, g, slot0);
+    dim3 grid((g.kp_cap + DESC_WARPS - 1) / DESC_WARPS, nimg);
+    k_describe<<<grid, DESC_WARPS * 32, 0, st>>>(b, g, slot0, pattern_on_device());
     ++*launches;
 }

@@ -186,8 +186,9 @@ int build_geometry(svo_ctx *ctx)
         L.cap2 = 4 * L.quota + 1024 < L.cand_cap ? 4 * L.quota + 1024 : L.cand_cap;
         L.off2 = off2; off2 += align_up(L.cap2, 4);
         L.tab_off = tab_off; if (l) tab_off += L.w + L.h;
-        L.blur_tiles_x = (L.w + 127) / 128;
-        L.blur_tile_off = tiles; tiles += L.blur_tiles_x * ((L.h + 15) / 16);
+        L.blur_tiles_x = (L.w + 3) / 4;                      // quads per row
+        L.blur_tile_off = tiles;                             // first blur CTA of the level (128 strips of 4 x 32 px each)
+        tiles += (L.blur_tiles_x * ((L.h + 31) / 32) + 127) / 128;
         g.fast_bands += L.nbands;
     }
     if (lw[0] >= 4096 || lh[0] >= 4096) return fail(ctx, SVO_E_INVALID, "images up to 4095x4095 are supported");
@@ -345,7 +346,7 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
     TRY(alloc_frames(ctx, ctx->fb, nbatch_frames, g.kp_cap, c.max_rows, false));
     const int sync_stride = g.kp_cap > c.max_rows ? g.kp_cap : c.max_rows;
     TRY(alloc_frames(ctx, ctx->sb, 1, sync_stride, sync_stride, true));
-    if (setup_fast_attributes(g) != 0 || setup_match_attributes() != 0)
+    if (setup_fast_attributes(g) != 0 || setup_match_attributes() != 0 || setup_describe() != 0)
         return fail(ctx, SVO_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
     CU(cudaStreamCreateWithFlags(&ctx->sync_st, cudaStreamNonBlocking));
     ctx->lanes.resize(c.lanes);
