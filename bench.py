@@ -245,7 +245,7 @@ def run_gpu(args, rank, world, local_rank):
     sampler = ClockSampler(dev)
     sampler.start()
     ms_dev, wall_dev, launches, stage = timed(frame_dev, args.steps, args.warmup, 1)
-    ms_e2e, wall_e2e, _, _ = timed(frame_host, args.steps, args.warmup, 0)
+    ms_e2e, wall_e2e, _, stage_e2e = timed(frame_host, args.steps, args.warmup, 1)
     sampler.stop_flag = True
     sampler.join(timeout=1)
 
@@ -302,7 +302,9 @@ def run_gpu(args, rank, world, local_rank):
                              % (P, 2 * P * img_b / 1e6, P * (K * 33 + MAP_ROWS * 36) / 1e6),
                        "parallelism": "replicas only: one independent sequence per GPU, no collective"},
             "e2e": {"value": frames_total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_e2e / args.steps,
+                    "h2d_ms_per_step": stage_e2e.get("h2d"), "d2h_ms_per_step": stage_e2e.get("d2h"),
+                    "lane_total_ms_per_step": stage_e2e.get("total")},
             "gpu_launches": launches,
             "clocks": sampler.result(),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -51,6 +51,8 @@ struct Lane {
     bool busy;
     HostArena h;
     std::vector<svo_frame_in> in;
+    uint8_t *d_stage;          // contiguous landing zone for the images of a batch (2 per frame)
+    int *d_strides, *h_strides; // per image: row stride in the landing zone, 0 = uploaded with a 2-D copy
 };
 
 }  // namespace
@@ -68,6 +70,7 @@ struct svo_ctx {
     std::vector<void *> dev_allocs, pinned_allocs;
     std::vector<uint32_t> rtab_host;
     long long launches;
+    size_t stage_img_bytes;
     bool profiling;
     bool sync_have[2];
     char err[512];
@@ -349,6 +352,7 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
     if (setup_fast_attributes(g) != 0 || setup_match_attributes() != 0 || setup_describe() != 0)
         return fail(ctx, SVO_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
     CU(cudaStreamCreateWithFlags(&ctx->sync_st, cudaStreamNonBlocking));
+    ctx->stage_img_bytes = (size_t)g.H * (g.W + 256);
     ctx->lanes.resize(c.lanes);
     for (int i = 0; i < c.lanes; ++i) {
         Lane &l = ctx->lanes[i];
@@ -369,6 +373,8 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
         TRY(halloc(ctx, &h.p1_row_claimed, B * R)); TRY(halloc(ctx, &h.p2_row_claimed, B * R));
         TRY(halloc(ctx, &h.claim_row, B * K));
         TRY(halloc(ctx, &h.params, 4 * B));
+        TRY(dalloc(ctx, &l.d_stage, I * ctx->stage_img_bytes));
+        TRY(dalloc(ctx, &l.d_strides, I)); TRY(halloc(ctx, &l.h_strides, I));
     }
     CU(cudaDeviceSynchronize());
     return SVO_OK;
@@ -598,8 +604,19 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
     for (int i = 0; i < n; ++i) {
         const svo_frame_in &f = frames[i];
         const int fi = L.frame0 + i;
-        TRY(upload_image(ctx, L.slot0 + 2 * i, f.left, f.stride, st));
-        TRY(upload_image(ctx, L.slot0 + 2 * i + 1, f.right, f.stride, st));
+        // one contiguous copy per image (a strided 2-D H2D copy of 1241-byte rows runs at a fraction of
+        // PCIe speed); k_unpack re-pitches on the device.  Oversized strides fall back to the 2-D copy.
+        const size_t img_bytes = (size_t)f.stride * (g.H - 1) + g.W;
+        const uint8_t *srcs[2] = {f.left, f.right};
+        for (int s = 0; s < 2; ++s) {
+            if (img_bytes <= ctx->stage_img_bytes) {
+                CU(cudaMemcpyAsync(L.d_stage + (size_t)(2 * i + s) * ctx->stage_img_bytes, srcs[s], img_bytes, cudaMemcpyDefault, st));
+                L.h_strides[2 * i + s] = f.stride;
+            } else {
+                TRY(upload_image(ctx, L.slot0 + 2 * i + s, srcs[s], f.stride, st));
+                L.h_strides[2 * i + s] = 0;
+            }
+        }
         if (f.n_prev) {
             CU(cudaMemcpyAsync(fb.prev + (size_t)fi * R * 32, f.prev_desc, (size_t)f.n_prev * 32, cudaMemcpyDefault, st));
             if (f.prev_live) CU(cudaMemcpyAsync(fb.prev_live + (size_t)fi * R, f.prev_live, (size_t)f.n_prev, cudaMemcpyDefault, st));
@@ -617,6 +634,8 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
     const int FT = fb.nframes;
     for (int k = 0; k < 4; ++k)
         CU(cudaMemcpyAsync(fb.params + (size_t)k * FT + L.frame0, hp + (size_t)k * B, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(L.d_strides, L.h_strides, sizeof(int) * 2 * n, cudaMemcpyHostToDevice, st));
+    launch_unpack(b, g, L.slot0, 2 * n, L.d_stage, ctx->stage_img_bytes, L.d_strides, st, &ctx->launches);
     CU(cudaMemsetAsync(fb.claimed + (size_t)L.frame0 * K, 0, (size_t)n * K, st));
     CU(cudaMemsetAsync(fb.claim_row + (size_t)L.frame0 * K, 0xff, sizeof(int) * (size_t)n * K, st));
     // ---- extraction of 2n images

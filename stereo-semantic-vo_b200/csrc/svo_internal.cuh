@@ -80,6 +80,8 @@ __host__ __device__ inline int unpack_y(uint32_t v) { return (int)((v >> 12) & 0
 __host__ __device__ inline int unpack_s(uint32_t v) { return (int)(v >> 24); }
 
 // ---- stage launchers (each enqueues on `st` for images [slot0, slot0 + nimg)) ----
+void launch_unpack(const Bufs &b, const Geom &g, int slot0, int nimg, const uint8_t *stage, size_t stage_img_bytes,
+                   const int *strides, cudaStream_t st, long long *launches);
 void launch_pyramid(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches);
 void launch_fast(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches);
 void launch_select1(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches);
