@@ -48,18 +48,27 @@ __device__ __forceinline__ Row load_row(const uint8_t *desc, int r)
     Row R; R.a = p[0]; R.b = p[1];
     return R;
 }
+// popcount of 8 words with one level of carry-save adders: 6 POPC (XU pipe) + 4 extra LOP3 (ALU)
+// instead of 8 POPC.  The XU pipe is the bottleneck of these kernels (84 % busy with the plain
+// form); the full 4-POPC adder tree moves the bottleneck to the ALU pipe and is no faster.
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a | b)); }
+__device__ __forceinline__ int popc8(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t x4, uint32_t x5,
+                                     uint32_t x6, uint32_t x7)
+{
+    const uint32_t s1 = x0 ^ x1 ^ x2, c1 = maj3(x0, x1, x2);
+    const uint32_t s2 = x3 ^ x4 ^ x5, c2 = maj3(x3, x4, x5);
+    return __popc(s1) + __popc(s2) + __popc(x6) + __popc(x7) + 2 * (__popc(c1) + __popc(c2));
+}
 __device__ __forceinline__ int ham(const Row &R, const uint4 *tile, int j)
 {
     const uint4 x = tile[unit_of(j, 0)], y = tile[unit_of(j, 1)];
-    return __popc(R.a.x ^ x.x) + __popc(R.a.y ^ x.y) + __popc(R.a.z ^ x.z) + __popc(R.a.w ^ x.w) +
-           __popc(R.b.x ^ y.x) + __popc(R.b.y ^ y.y) + __popc(R.b.z ^ y.z) + __popc(R.b.w ^ y.w);
+    return popc8(R.a.x ^ x.x, R.a.y ^ x.y, R.a.z ^ x.z, R.a.w ^ x.w, R.b.x ^ y.x, R.b.y ^ y.y, R.b.z ^ y.z, R.b.w ^ y.w);
 }
 __device__ __forceinline__ int ham_global(const Row &R, const uint8_t *desc, int j)
 {
     const uint4 *p = reinterpret_cast<const uint4 *>(desc) + (size_t)j * 2;
     const uint4 x = p[0], y = p[1];
-    return __popc(R.a.x ^ x.x) + __popc(R.a.y ^ x.y) + __popc(R.a.z ^ x.z) + __popc(R.a.w ^ x.w) +
-           __popc(R.b.x ^ y.x) + __popc(R.b.y ^ y.y) + __popc(R.b.z ^ y.z) + __popc(R.b.w ^ y.w);
+    return popc8(R.a.x ^ x.x, R.a.y ^ x.y, R.a.z ^ x.z, R.a.w ^ x.w, R.b.x ^ y.x, R.b.y ^ y.y, R.b.z ^ y.z, R.b.w ^ y.w);
 }
 
 __device__ __forceinline__ bool in_window(const float *win, const float *cxy, int j)
@@ -175,6 +184,14 @@ __global__ void k_greedy_init(GreedyArgs a, int reset_time)
 // ---------------------------------------------------------------------------------------
 #define SL_ROWS_PER_WARP 4
 
+// Short lists live in two arrays so the common case (<= 32 entries) touches one 128-byte line per
+// row: entries 0..31 in shortlist[row][32], entries 32..CAP-1 in shortlist_hi[row][CAP-32].
+__device__ __forceinline__ uint32_t *short_slot(const GreedyArgs &a, size_t row, int pos)
+{
+    return pos < 32 ? a.shortlist + row * 32 + pos : a.shortlist_hi + row * (SVO_SHORT_CAP - 32) + (pos - 32);
+}
+
+template <bool WIN>
 __global__ void __launch_bounds__(M_THREADS) k_shortlist(GreedyArgs a, int T)
 {
     __shared__ uint4 tile[COL_TILE * 2];
@@ -184,16 +201,20 @@ __global__ void __launch_bounds__(M_THREADS) k_shortlist(GreedyArgs a, int T)
     if (blockIdx.x * M_WARPS * SL_ROWS_PER_WARP >= M) return;
     const int r0 = (blockIdx.x * M_WARPS + warp) * SL_ROWS_PER_WARP;
     const uint8_t *rd = set_desc(a.rows, f), *cd = set_desc(a.cols, f);
-    const float *cxy = a.cur_xy ? a.cur_xy + (size_t)f * a.cols.stride_rows * 2 : nullptr;
+    const float *cxy = WIN ? a.cur_xy + (size_t)f * a.cols.stride_rows * 2 : nullptr;
+    const size_t ro = (size_t)f * a.rows.stride_rows;
     Row R[SL_ROWS_PER_WARP];
     int cnt[SL_ROWS_PER_WARP];
     bool live[SL_ROWS_PER_WARP];
+    float wu[SL_ROWS_PER_WARP], wv[SL_ROWS_PER_WARP], wr[SL_ROWS_PER_WARP];
 #pragma unroll
     for (int k = 0; k < SL_ROWS_PER_WARP; ++k) {
         const int r = r0 + k;
         cnt[k] = 0;
-        live[k] = r < M && (!a.row_live || a.row_live[(size_t)f * a.rows.stride_rows + r]);
+        live[k] = r < M && (!a.row_live || a.row_live[ro + r]);
         R[k] = load_row(rd, min(r, M - 1));
+        wu[k] = wv[k] = wr[k] = 0.f;
+        if (WIN && r < M) { wu[k] = a.win_uvr[(ro + r) * 3]; wv[k] = a.win_uvr[(ro + r) * 3 + 1]; wr[k] = a.win_uvr[(ro + r) * 3 + 2]; }
     }
     for (int c0 = 0; c0 < N; c0 += COL_TILE) {
         const int nc = min(COL_TILE, N - c0);
@@ -202,30 +223,36 @@ __global__ void __launch_bounds__(M_THREADS) k_shortlist(GreedyArgs a, int T)
         __syncthreads();
         for (int jb = 0; jb < nc; jb += 32) {
             const int j = jb + lane;
+            const bool inb = j < nc;
+            const int jj = inb ? j : 0;
+            const uint4 x = tile[unit_of(jj, 0)], y = tile[unit_of(jj, 1)];
+            float cu = 0.f, cv = 0.f;
+            if (WIN && inb) { cu = cxy[2 * (c0 + j)]; cv = cxy[2 * (c0 + j) + 1]; }
 #pragma unroll
             for (int k = 0; k < SL_ROWS_PER_WARP; ++k) {
                 if (!live[k]) continue;   // warp-uniform
-                const int r = r0 + k;
-                int d = 256;
-                if (j < nc) {
-                    const float *win = a.win_uvr ? a.win_uvr + ((size_t)f * a.rows.stride_rows + r) * 3 : nullptr;
-                    if (in_window(win, cxy, c0 + j)) d = ham(R[k], tile, j);
+                int d = popc8(R[k].a.x ^ x.x, R[k].a.y ^ x.y, R[k].a.z ^ x.z, R[k].a.w ^ x.w,
+                              R[k].b.x ^ y.x, R[k].b.y ^ y.y, R[k].b.z ^ y.z, R[k].b.w ^ y.w);
+                bool hit = inb && d < T;
+                if (WIN) {
+                    const float du = cu - wu[k], dv = cv - wv[k];
+                    hit = hit && !(du < -wr[k] || du > wr[k] || dv < -wr[k] || dv > wr[k]);
                 }
-                const bool hit = d < T;
                 const uint32_t m = __ballot_sync(0xffffffffu, hit);
-                if (hit) {
-                    const int pos = cnt[k] + __popc(m & ((1u << lane) - 1u));
-                    if (pos < SVO_SHORT_CAP)
-                        a.shortlist[((size_t)f * a.rows.stride_rows + r) * SVO_SHORT_CAP + pos] = ((uint32_t)d << 16) | (uint32_t)(c0 + j);
+                if (m) {
+                    if (hit) {
+                        const int pos = cnt[k] + __popc(m & ((1u << lane) - 1u));
+                        if (pos < SVO_SHORT_CAP) *short_slot(a, ro + r0 + k, pos) = ((uint32_t)d << 16) | (uint32_t)(c0 + j);
+                    }
+                    cnt[k] += __popc(m);
                 }
-                cnt[k] += __popc(m);
             }
         }
     }
     if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < SL_ROWS_PER_WARP; ++k)
-            if (r0 + k < M) a.short_cnt[(size_t)f * a.rows.stride_rows + r0 + k] = live[k] ? cnt[k] : 0;
+            if (r0 + k < M) a.short_cnt[ro + r0 + k] = live[k] ? cnt[k] : 0;
     }
 }
 
@@ -312,14 +339,13 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_r
     const uint8_t *rd = set_desc(a.rows, f), *cd = set_desc(a.cols, f);
     const float *cxy = a.cur_xy ? a.cur_xy + co * 2 : nullptr;
     const int rbase = a.row_base + (a.row_base_arr ? a.row_base_arr[f] : 0);
-    const uint32_t *lists = a.shortlist + ro * SVO_SHORT_CAP;
 
     auto fetch = [&](int it, uint32_t (&e)[4], int &pk) {
         pk = it < total ? rows_ne[it] : 0;
         const int r = pk & 0xffff, cnt = pk >> 16;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            e[k] = (cnt <= SVO_SHORT_CAP && lane + 32 * k < cnt) ? lists[(size_t)r * SVO_SHORT_CAP + lane + 32 * k] : 0xffffffffu;
+            e[k] = (cnt <= SVO_SHORT_CAP && lane + 32 * k < cnt) ? *short_slot(a, ro + r, lane + 32 * k) : 0xffffffffu;
     };
     uint32_t en[4];
     int pk_n, it_n = warp;
@@ -420,6 +446,7 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_r
 // contiguous columns [31 l, 31 l + 31) of each tile so "second = running best before the
 // final update" composes across lanes and tiles.
 // ---------------------------------------------------------------------------------------
+template <bool WIN>
 __global__ void __launch_bounds__(M_THREADS) k_scores(GreedyArgs a)
 {
     __shared__ uint4 tile[COL_TILE * 2];
@@ -453,7 +480,7 @@ __global__ void __launch_bounds__(M_THREADS) k_scores(GreedyArgs a)
 #pragma unroll 1
         for (int k = 0; k < COLS_PER_LANE; ++k) {
             const int j = jb + k;
-            if (j < nc && s_time[j] >= g && in_window(win, cxy, c0 + j)) {
+            if (j < nc && s_time[j] >= g && (!WIN || in_window(win, cxy, c0 + j))) {
                 const int d = ham(R, tile, j);
                 if (d < lb) { ls = lb; lb = d; li = c0 + j; }
             }
@@ -489,14 +516,16 @@ void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStrea
     k_greedy_init<<<gi, 256, 0, st>>>(a, 1);
     const int T = a.mode == SVO_GREEDY_PASS1 ? 15 : 60;
     dim3 gs((maxM + M_WARPS * SL_ROWS_PER_WARP - 1) / (M_WARPS * SL_ROWS_PER_WARP), nframes);
-    k_shortlist<<<gs, M_THREADS, 0, st>>>(a, T);
+    if (a.win_uvr) k_shortlist<true><<<gs, M_THREADS, 0, st>>>(a, T);
+    else k_shortlist<false><<<gs, M_THREADS, 0, st>>>(a, T);
     // shared memory: row list + per-column first-wanting-warp + claim bytes
     const size_t smem = (size_t)maxM * sizeof(int) + (size_t)maxN * (sizeof(int) + 1) + 16;
     k_resolve<<<nframes, RES_THREADS, smem, st>>>(a, maxM);
     *launches += 3;
     if (want_scores && a.best_idx) {
         dim3 gf((maxM + M_WARPS - 1) / M_WARPS, nframes);
-        k_scores<<<gf, M_THREADS, 0, st>>>(a);
+        if (a.win_uvr) k_scores<true><<<gf, M_THREADS, 0, st>>>(a);
+        else k_scores<false><<<gf, M_THREADS, 0, st>>>(a);
         ++*launches;
     }
 }

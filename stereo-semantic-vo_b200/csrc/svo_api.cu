@@ -25,7 +25,7 @@ struct FrameBufs {           // per-frame (stereo pair) device arrays
     int *bf_idx, *bf_dist; uint8_t *bf_keep; int *min_dist;
     int *p1_best_idx, *p1_best, *p1_second; uint8_t *p1_row_claimed, *p1_row_bad;
     int *p2_best_idx, *p2_best, *p2_second; uint8_t *p2_row_claimed;
-    uint32_t *shortlist; int *short_cnt;
+    uint32_t *shortlist, *shortlist_hi; int *short_cnt;
     float *u_right, *depth; int *match_r, *sad, *n_stereo;
     int *params;             // [4][nframes]: n_prev, n_map, bf bits, baseline bits
     // sync-only extras
@@ -219,7 +219,7 @@ int alloc_frames(svo_ctx *ctx, FrameBufs &f, int nframes, int col_stride, int ro
     TRY(dalloc(ctx, &f.p1_row_claimed, R)); TRY(dalloc(ctx, &f.p1_row_bad, R));
     TRY(dalloc(ctx, &f.p2_best_idx, R)); TRY(dalloc(ctx, &f.p2_best, R)); TRY(dalloc(ctx, &f.p2_second, R));
     TRY(dalloc(ctx, &f.p2_row_claimed, R));
-    TRY(dalloc(ctx, &f.shortlist, R * SVO_SHORT_CAP)); TRY(dalloc(ctx, &f.short_cnt, R));
+    TRY(dalloc(ctx, &f.shortlist, R * 32)); TRY(dalloc(ctx, &f.shortlist_hi, R * (SVO_SHORT_CAP - 32))); TRY(dalloc(ctx, &f.short_cnt, R));
     TRY(dalloc(ctx, &f.u_right, C)); TRY(dalloc(ctx, &f.depth, C)); TRY(dalloc(ctx, &f.match_r, C));
     TRY(dalloc(ctx, &f.sad, C)); TRY(dalloc(ctx, &f.n_stereo, F));
     TRY(dalloc(ctx, &f.params, 4 * F));
@@ -537,7 +537,7 @@ int svo_match_greedy(svo_ctx *ctx, const uint8_t *rows, int M, const uint8_t *cu
     a.claimed = s.claimed; a.claim_row = s.claim_row; a.claim_time = s.claim_time;
     a.best_idx = s.p2_best_idx; a.best = s.p2_best; a.second = s.p2_second;
     a.row_claimed = s.p2_row_claimed; a.row_bad = s.p1_row_bad;
-    a.shortlist = s.shortlist; a.short_cnt = s.short_cnt;
+    a.shortlist = s.shortlist; a.shortlist_hi = s.shortlist_hi; a.short_cnt = s.short_cnt;
     a.win_uvr = win_uvr ? s.win : nullptr;
     a.cur_xy = (win_uvr || use_veto) ? s.cur_xy : nullptr;
     if (use_veto) { a.boxes = s.boxes; a.n_boxes = veto->n_boxes; a.F = s.F; a.row_xy = s.row_xy; }
@@ -665,7 +665,8 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
     ga.cols = cur;
     ga.claimed = fb.claimed + (size_t)L.frame0 * K; ga.claim_row = fb.claim_row + (size_t)L.frame0 * K;
     ga.claim_time = fb.claim_time + (size_t)L.frame0 * K;
-    ga.shortlist = fb.shortlist + (size_t)L.frame0 * R * SVO_SHORT_CAP; ga.short_cnt = fb.short_cnt + (size_t)L.frame0 * R;
+    ga.shortlist = fb.shortlist + (size_t)L.frame0 * R * 32; ga.shortlist_hi = fb.shortlist_hi + (size_t)L.frame0 * R * (SVO_SHORT_CAP - 32);
+    ga.short_cnt = fb.short_cnt + (size_t)L.frame0 * R;
     if (any_prev) {
         ga.rows = make_set(fb.prev + (size_t)L.frame0 * R * 32, d_nprev, 1, R, 0);
         ga.mode = SVO_GREEDY_PASS1; ga.row_base = 0; ga.row_base_arr = nullptr;

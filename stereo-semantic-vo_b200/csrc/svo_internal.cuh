@@ -132,7 +132,8 @@ struct GreedyArgs {
     int *best_idx, *best, *second;   // [frame][rows.stride_rows] or NULL
     uint8_t *row_claimed;         // [frame][rows.stride_rows]
     uint8_t *row_bad;             // [frame][rows.stride_rows] or NULL
-    uint32_t *shortlist;          // [frame][rows.stride_rows][SVO_SHORT_CAP]
+    uint32_t *shortlist;          // [frame][rows.stride_rows][32]: entries 0..31
+    uint32_t *shortlist_hi;       // [frame][rows.stride_rows][SVO_SHORT_CAP - 32]: the rest
     int *short_cnt;               // [frame][rows.stride_rows]
     const float *win_uvr;         // [frame][rows.stride_rows][3] or NULL
     const float *cur_xy;          // [frame][cols.stride_rows][2] or NULL
