@@ -20,6 +20,7 @@
 //                    replaying each row against the columns not claimed before it.
 #include "svo_internal.cuh"
 #include <limits.h>
+#include <cuda_pipeline.h>
 
 #define COL_TILE 992          // 31 columns per lane
 #define COLS_PER_LANE 31
@@ -285,6 +286,7 @@ __device__ bool veto_dynamic(const GreedyArgs &a, int f, int row, int col)
 
 #define RES_THREADS 512
 #define RES_WARPS (RES_THREADS / 32)
+#define RES_RING 128
 
 // Sequential semantics, parallel execution: the rows that can claim are taken in groups of
 // RES_WARPS consecutive rows.  Every warp decides one row against the claim set as of the start
@@ -292,15 +294,16 @@ __device__ bool veto_dynamic(const GreedyArgs &a, int f, int row, int col)
 // claims a column that appears in its short list.  The maximal prefix of rows without such a
 // conflict is committed, and the next group starts at the first conflicting row.  Short lists are
 // read straight from global memory, prefetched one group ahead.
-__global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_rows)
+__global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_rows, int max_cols)
 {
     const int f = blockIdx.x;
     const int M = set_count(a.rows, f), N = set_count(a.cols, f);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // shared: [rows_ne: max_rows ints][first_want: N ints][claimed: N bytes]
+    // shared: [rows_ne: max_rows ints][first_want: max_cols ints][ring: RES_RING x CAP u32][claimed: N bytes]
     int *rows_ne = reinterpret_cast<int *>(resolve_smem);   // (row | min(cnt, CAP+1) << 16) of rows that can claim, ascending
     int *first_want = rows_ne + max_rows;                   // lowest warp of the group that wants the column
-    uint8_t *claimed = reinterpret_cast<uint8_t *>(first_want + N);
+    uint32_t *ring = reinterpret_cast<uint32_t *>(first_want + max_cols);   // look-ahead short lists
+    uint8_t *claimed = reinterpret_cast<uint8_t *>(ring + RES_RING * SVO_SHORT_CAP);
     __shared__ int wcnt[RES_WARPS];
     __shared__ int n_ne;
     __shared__ unsigned g_dirty[2], g_want[2];   // per-group bit sets (double buffered across groups)
@@ -340,34 +343,39 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_r
     const float *cxy = a.cur_xy ? a.cur_xy + co * 2 : nullptr;
     const int rbase = a.row_base + (a.row_base_arr ? a.row_base_arr[f] : 0);
 
-    auto fetch = [&](int it, uint32_t (&e)[4], int &pk) {
-        pk = it < total ? rows_ne[it] : 0;
-        const int r = pk & 0xffff, cnt = pk >> 16;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            e[k] = (cnt <= SVO_SHORT_CAP && lane + 32 * k < cnt) ? *short_slot(a, ro + r, lane + 32 * k) : 0xffffffffu;
+    // Look-ahead ring: the first 32 entries of the next RING rows are copied global -> shared with
+    // cp.async at least (RING-16)/16 = 7 groups before they are consumed, so the sequential part never
+    // waits on a global load.  Entries 32.. (rare) are read directly.
+    auto stage = [&](int it) {
+        if (it < total) {
+            const int pk = rows_ne[it], r = pk & 0xffff, cnt = pk >> 16;
+            if (cnt <= SVO_SHORT_CAP) {
+                uint32_t *dst = ring + (size_t)(it % RES_RING) * SVO_SHORT_CAP;
+                if (lane < cnt) __pipeline_memcpy_async(dst + lane, a.shortlist + (ro + r) * 32 + lane, 4);
+                for (int k = lane + 32; k < cnt; k += 32)
+                    __pipeline_memcpy_async(dst + k, a.shortlist_hi + (ro + r) * (SVO_SHORT_CAP - 32) + (k - 32), 4);
+            }
+        }
     };
-    uint32_t en[4];
-    int pk_n, it_n = warp;
-    fetch(it_n, en, pk_n);
+    for (int it = warp; it < RES_RING; it += RES_WARPS) stage(it);
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+    __syncthreads();
     unsigned par = 0;
     for (int it0 = 0; it0 < total; par ^= 1u) {
         const int ng = min(RES_WARPS, total - it0);
         // ---- 1. speculative decision of row it0 + warp against the claims as of the group start
-        uint32_t e[4];
-        int pk;
-        if (it_n == it0 + warp) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) e[k] = en[k];
-            pk = pk_n;
-        } else fetch(it0 + warp, e, pk);          // the previous group committed only a prefix
-        it_n = it0 + ng + warp;                       // prefetch for the (likely) next group
-        fetch(it_n, en, pk_n);
+        uint32_t e[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        const int pk = warp < ng ? rows_ne[it0 + warp] : 0;
         const int r = pk & 0xffff, cnt = pk >> 16;
         int want = -1, flag = 0;
         if (warp < ng) {
             int bd = 256, bi = -1, sd = 256;
             if (cnt <= SVO_SHORT_CAP) {
+                const uint32_t *src = ring + (size_t)((it0 + warp) % RES_RING) * SVO_SHORT_CAP;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (lane + 32 * k < cnt) e[k] = src[lane + 32 * k];
                 uint32_t key = 0xffffffffu;
                 bool v[4];
 #pragma unroll
@@ -436,6 +444,9 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_r
             }
         }
         if (tid == 0) { g_dirty[par ^ 1u] = 0; g_want[par ^ 1u] = 0; }
+        if (warp < fd) stage(it0 + RES_RING + warp);     // the slot of a committed row takes the next entrant
+        __pipeline_commit();
+        __pipeline_wait_prior(5);
         __syncthreads();
         it0 += fd;
     }
@@ -519,8 +530,8 @@ void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStrea
     if (a.win_uvr) k_shortlist<true><<<gs, M_THREADS, 0, st>>>(a, T);
     else k_shortlist<false><<<gs, M_THREADS, 0, st>>>(a, T);
     // shared memory: row list + per-column first-wanting-warp + claim bytes
-    const size_t smem = (size_t)maxM * sizeof(int) + (size_t)maxN * (sizeof(int) + 1) + 16;
-    k_resolve<<<nframes, RES_THREADS, smem, st>>>(a, maxM);
+    const size_t smem = (size_t)maxM * sizeof(int) + (size_t)maxN * (sizeof(int) + 1) + (size_t)RES_RING * SVO_SHORT_CAP * 4 + 16;
+    k_resolve<<<nframes, RES_THREADS, smem, st>>>(a, maxM, maxN);
     *launches += 3;
     if (want_scores && a.best_idx) {
         dim3 gf((maxM + M_WARPS - 1) / M_WARPS, nframes);
