@@ -288,6 +288,30 @@ __device__ bool veto_dynamic(const GreedyArgs &a, int f, int row, int col)
 #define RES_WARPS (RES_THREADS / 32)
 #define RES_RING 128
 
+// One row's decision from its short list (K entries per lane) against the claim bytes:
+// (bestDist, bestIdx) = first minimum over unclaimed entries, second = minimum before bestIdx.
+template <int K>
+__device__ __forceinline__ void decide(const uint32_t *src, int cnt, int lane, const uint8_t *claimed, uint32_t (&e)[4],
+                                       int &bd, int &bi, int &sd)
+{
+    uint32_t key = 0xffffffffu;
+    bool v[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        if (lane + 32 * k < cnt) e[k] = src[lane + 32 * k];
+        v[k] = e[k] != 0xffffffffu && !claimed[e[k] & 0xffffu];
+        if (v[k]) key = min(key, e[k]);
+    }
+    const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
+    if (kmin != 0xffffffffu) {
+        bd = (int)(kmin >> 16); bi = (int)(kmin & 0xffffu);
+        uint32_t s = 256u;
+#pragma unroll
+        for (int k = 0; k < K; ++k) if (v[k] && (int)(e[k] & 0xffffu) < bi) s = min(s, e[k] >> 16);
+        sd = (int)__reduce_min_sync(0xffffffffu, s);
+    }
+}
+
 // Sequential semantics, parallel execution: the rows that can claim are taken in groups of
 // RES_WARPS consecutive rows.  Every warp decides one row against the claim set as of the start
 // of the group (speculation); a row's decision is exact unless an earlier row of the same group
@@ -373,24 +397,8 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_r
             int bd = 256, bi = -1, sd = 256;
             if (cnt <= SVO_SHORT_CAP) {
                 const uint32_t *src = ring + (size_t)((it0 + warp) % RES_RING) * SVO_SHORT_CAP;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (lane + 32 * k < cnt) e[k] = src[lane + 32 * k];
-                uint32_t key = 0xffffffffu;
-                bool v[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    v[k] = e[k] != 0xffffffffu && !claimed[e[k] & 0xffffu];
-                    if (v[k]) key = min(key, e[k]);
-                }
-                const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
-                if (kmin != 0xffffffffu) {
-                    bd = (int)(kmin >> 16); bi = (int)(kmin & 0xffffu);
-                    uint32_t s = 256u;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) if (v[k] && (int)(e[k] & 0xffffu) < bi) s = min(s, e[k] >> 16);
-                    sd = (int)__reduce_min_sync(0xffffffffu, s);
-                }
+                if (cnt <= 32) decide<1>(src, cnt, lane, claimed, e, bd, bi, sd);   // the common case: one entry per lane
+                else decide<4>(src, cnt, lane, claimed, e, bd, bi, sd);
             } else {
                 // list overflow: exhaustive scan of this row against the claim set
                 const Row R = load_row(rd, r);
@@ -422,8 +430,11 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_r
         if (warp < ng) {
             bool hit = false;
             if (cnt > SVO_SHORT_CAP) hit = (g_want[par] & ((1u << warp) - 1u)) != 0;   // list unknown: be conservative
+            if (cnt <= 32) hit = hit || (e[0] != 0xffffffffu && first_want[e[0] & 0xffffu] < warp);
+            else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) hit = hit || (e[k] != 0xffffffffu && first_want[e[k] & 0xffffu] < warp);
+                for (int k = 0; k < 4; ++k) hit = hit || (e[k] != 0xffffffffu && first_want[e[k] & 0xffffu] < warp);
+            }
             if (__any_sync(0xffffffffu, hit) && lane == 0) atomicOr(&g_dirty[par], 1u << warp);
         }
         __syncthreads();
