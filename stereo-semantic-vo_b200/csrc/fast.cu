@@ -75,7 +75,7 @@ extern __shared__ __align__(16) uint8_t fast_smem[];
 // shared-memory carve-up for a level of pitch sp (bytes)
 __host__ __device__ inline int fast_off_sc(int sp) { return (SVO_FAST_BAND + 8) * sp; }
 __host__ __device__ inline int fast_off_cand(int sp) { return fast_off_sc(sp) + (SVO_FAST_BAND + 2) * sp; }
-__host__ __device__ inline int fast_off_mask(int sp) { return fast_off_cand(sp) + 2 * (SVO_FAST_BAND + 2) * sp; }
+__host__ __device__ inline int fast_off_mask(int sp) { return fast_off_cand(sp) + 2 * (SVO_FAST_BAND + 2) * sp + 512; }
 __host__ __device__ inline int fast_mask_words(int sp) { return SVO_FAST_BAND * ((sp + 31) / 32); }
 
 __global__ void __launch_bounds__(FAST_THREADS) k_fast(Bufs b, Geom g, int slot0)
@@ -97,7 +97,6 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(Bufs b, Geom g, int slot0
     uint32_t *mask = reinterpret_cast<uint32_t *>(fast_smem + fast_off_mask(sp)); // kept-corner bitmap, row major
     const int wv = L.x1 - L.x0;
     const int wpr = (wv + 31) >> 5;   // bitmap words per row
-    __shared__ int n_cand;
     __shared__ int wsum[FAST_THREADS / 32];
 
     {   // stage pixel rows with 128-bit loads; clear the score tile and the bitmap
@@ -109,40 +108,38 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(Bufs b, Geom g, int slot0
         const int z16 = ((nrow + 2) * sp) >> 4;
         for (int i = tid; i < z16; i += FAST_THREADS) z[i] = make_uint4(0, 0, 0, 0);
         for (int i = tid; i < nrow * wpr; i += FAST_THREADS) mask[i] = 0;
-        if (tid == 0) n_cand = 0;
     }
     __syncthreads();
-    // A. cheap necessary test on every pixel of rows yb-1..ye, columns x0-1..x1; survivors are
-    //    appended (warp-aggregated) to the shared candidate list
-    for (int r = warp; r < nrow + 2; r += nwarps) {
-        const uint8_t *prow = pix + (r + 3) * sp;
-        for (int xb = L.x0 - 1; xb < L.x1 + 1; xb += 32) {
-            const int x = xb + lane;
-            const bool c = x < L.x1 + 1 && fast_quick(prow + x, sp, t);
-            const uint32_t m = __ballot_sync(0xffffffffu, c);
-            if (m) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&n_cand, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (c) cand[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(r * sp + x);
-            }
-        }
+    // A. cheap necessary test on every pixel of rows yb-1..ye, columns x0-1..x1, in 32-pixel chunks
+    //    dealt round-robin to the warps; each warp appends survivors to its OWN candidate list (no
+    //    atomics, no block barrier) and then
+    // B. exact-scores its own candidates, densely packed over the lanes.
+    const int sw = L.x1 - L.x0 + 2;
+    const int cpr = (sw + 31) >> 5;
+    const int nchunks = (nrow + 2) * cpr;
+    const int wcap = ((nchunks + nwarps - 1) / nwarps) << 5;
+    uint16_t *mine = cand + warp * wcap;
+    int nmine = 0;
+    for (int c = warp; c < nchunks; c += nwarps) {
+        const int r = c / cpr, x = L.x0 - 1 + ((c - r * cpr) << 5) + lane;
+        const bool ok = x < L.x1 + 1 && fast_quick(pix + (r + 3) * sp + x, sp, t);
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        if (ok) mine[nmine + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(r * sp + x);
+        nmine += __popc(m);
     }
-    __syncthreads();
-    // B. exact score, densely packed over the candidates
-    const int nc = n_cand;
-    for (int i = tid; i < nc; i += FAST_THREADS) {
-        const int pos = cand[i];
+    __syncwarp();
+    for (int i = lane; i < nmine; i += 32) {
+        const int pos = mine[i];
         const int s = fast_score(pix + pos + 3 * sp, sp, t);
         sc[pos] = (uint8_t)s;
-        if (s == 0) cand[i] = 0xffffu;   // not a corner
+        if (s == 0) mine[i] = 0xffffu;   // not a corner
     }
     __syncthreads();
     // C. 3x3 strict non-max suppression of the corners in the output rows -> bitmap
-    for (int i = tid; i < nc; i += FAST_THREADS) {
-        const int pos = cand[i];
+    for (int i = lane; i < nmine; i += 32) {
+        const int pos = mine[i];
         if (pos == 0xffff) continue;
-        const int r = pos / sp, x = pos - r * sp;
+        const int r = __umulhi((uint32_t)pos, L.pitch_magic), x = pos - r * sp;
         if (r < 1 || r > nrow || x < L.x0 || x >= L.x1) continue;
         const uint8_t *q = sc + pos;
         const int s = q[0];

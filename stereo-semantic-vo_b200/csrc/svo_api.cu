@@ -174,6 +174,7 @@ int build_geometry(svo_ctx *ctx)
     for (int l = 0; l < g.nlevels; ++l) {
         LevelGeom &L = g.lv[l];
         L.w = lw[l]; L.h = lh[l]; L.pitch = align_up(lw[l], 16);
+        L.pitch_magic = (unsigned)((0x100000000ull + L.pitch - 1) / L.pitch);
         if (L.w < 8 || L.h < 8) return fail(ctx, SVO_E_INVALID, "level %d is %dx%d: image too small for %d levels", l, L.w, L.h, g.nlevels);
         L.off = off; off += align_up(L.pitch * (L.h + 1), 256);
         L.scale = ls[l]; L.inv_scale = 1.f / ls[l]; L.quota = quota[l];

@@ -22,6 +22,7 @@
 
 struct LevelGeom {
     int w, h, pitch;   // pitch: bytes per row, multiple of 16
+    unsigned pitch_magic;  // ceil(2^32 / pitch): __umulhi(v, pitch_magic) == v / pitch for v < 2^16
     int off;           // byte offset of the level inside a slot's pyramid buffer
     float scale;       // (float)pow(1.2, l)
     float inv_scale;   // 1.f / scale
