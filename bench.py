@@ -33,6 +33,7 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+import replicas  # noqa: E402
 import synth  # noqa: E402
 
 W_IMG, H_IMG, NFEAT, NLEVELS, MAP_ROWS = 1241, 376, 2000, 8, 5000
@@ -135,14 +136,13 @@ def run_gpu(args, rank, world, local_rank):
     import svo
     dev = local_rank
     torch.cuda.set_device(dev)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    grp = replicas.Group(backend="nccl", device=dev)   # barrier + max-over-ranks only; no data-path collective
     B, P = args.batch, args.pool
     ctx = svo.Context(W_IMG, H_IMG, nfeatures=NFEAT, nlevels=NLEVELS, max_batch=B, lanes=args.lanes,
                       max_rows=MAP_ROWS, device=dev)
     # ---- synthetic sequence (one per rank): pool of P distinct stereo frames in pinned memory
-    seq = synth.Sequence((H_IMG, W_IMG), seed=rank)
+    seq_id = replicas.assign_sequences(world, world, rank)[0]
+    seq = synth.Sequence((H_IMG, W_IMG), seed=seq_id)
     rng = np.random.default_rng(1000 + rank)
     pitch = W_IMG
     hl = ctx.pinned_array((P, H_IMG, pitch)); hr = ctx.pinned_array((P, H_IMG, pitch))
@@ -188,12 +188,7 @@ def run_gpu(args, rank, world, local_rank):
 
     streams = [torch.cuda.ExternalStream(ctx.lane_stream(l), device=dev) for l in range(args.lanes)]
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-            torch.cuda.synchronize()
+    barrier = grp.barrier
 
     def timed(make_frame, steps, warmup, profile):
         cursor = [0]
@@ -259,12 +254,8 @@ def run_gpu(args, rank, world, local_rank):
         lat.append((time.perf_counter() - t0) * 1e3)
     p50 = float(np.median(lat))
 
-    tms = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = tms.tolist()
-    frames_total = args.steps * B * world
+    ms_dev, ms_e2e = grp.max_over_ranks([ms_dev, ms_e2e])
+    frames_total = int(grp.sum_over_ranks([args.steps * B])[0])
     out = None
     if rank == 0:
         peaks = {}
@@ -316,10 +307,7 @@ def run_gpu(args, rank, world, local_rank):
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(seq, cores=1, budget_s=args.cpu_seconds)
     ctx.close()
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        dist.destroy_process_group()
+    grp.close()
     return out
 
 
@@ -397,7 +385,8 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     seq = synth.Sequence((H_IMG, W_IMG), seed=0)
     jobs = _cpu_jobs(seq, 4)
-    per_step = cores                                           # one frame per core per step
+    per_step = args.ref_frames or cores                        # one frame per core per step
+    cores = min(cores, per_step)
     pool = mp.get_context("fork").Pool(cores, initializer=_cpu_worker_init)
     work = [jobs[i % len(jobs)] for i in range(per_step)]
     steps = max(1, min(args.steps, 12)); warm = max(1, min(args.warmup, 2))
@@ -432,6 +421,7 @@ def main():
     ap.add_argument("--pool", type=int, default=160, help="distinct synthetic frames cycled (must exceed L2)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-frames", type=int, default=0, help="--impl reference: frames per step (default: one per host core)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
