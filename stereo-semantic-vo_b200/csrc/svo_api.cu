@@ -26,6 +26,7 @@ struct FrameBufs {           // per-frame (stereo pair) device arrays
     int *p1_best_idx, *p1_best, *p1_second; uint8_t *p1_row_claimed, *p1_row_bad;
     int *p2_best_idx, *p2_best, *p2_second; uint8_t *p2_row_claimed;
     uint32_t *shortlist, *shortlist_hi; int *short_cnt;
+    int *res_rows, *res_off, *res_want;
     float *u_right, *depth; int *match_r, *sad, *n_stereo;
     int *params;             // [4][nframes]: n_prev, n_map, bf bits, baseline bits
     // sync-only extras
@@ -221,6 +222,7 @@ int alloc_frames(svo_ctx *ctx, FrameBufs &f, int nframes, int col_stride, int ro
     TRY(dalloc(ctx, &f.p2_best_idx, R)); TRY(dalloc(ctx, &f.p2_best, R)); TRY(dalloc(ctx, &f.p2_second, R));
     TRY(dalloc(ctx, &f.p2_row_claimed, R));
     TRY(dalloc(ctx, &f.shortlist, R * 32)); TRY(dalloc(ctx, &f.shortlist_hi, R * (SVO_SHORT_CAP - 32))); TRY(dalloc(ctx, &f.short_cnt, R));
+    TRY(dalloc(ctx, &f.res_rows, R)); TRY(dalloc(ctx, &f.res_off, R)); TRY(dalloc(ctx, &f.res_want, R));
     TRY(dalloc(ctx, &f.u_right, C)); TRY(dalloc(ctx, &f.depth, C)); TRY(dalloc(ctx, &f.match_r, C));
     TRY(dalloc(ctx, &f.sad, C)); TRY(dalloc(ctx, &f.n_stereo, F));
     TRY(dalloc(ctx, &f.params, 4 * F));
@@ -347,6 +349,8 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
     CU(cudaMemset(b.pyr, 0, S * g.pyr_bytes)); CU(cudaMemset(b.blur, 0, S * g.pyr_bytes));
     CU(cudaMemset(b.nkp, 0, S * sizeof(int))); CU(cudaMemset(b.status, 0, S * sizeof(int)));
     CU(cudaMemset(b.kept1, 0, S * SVO_MAX_LEVELS * sizeof(int))); CU(cudaMemset(b.kept2, 0, S * SVO_MAX_LEVELS * sizeof(int)));
+    if (g.kp_cap > greedy_max_cols())
+        return fail(ctx, SVO_E_INVALID, "nfeatures %d exceeds the matcher's limit of %d keypoints per frame", c.nfeatures, greedy_max_cols());
     TRY(alloc_frames(ctx, ctx->fb, nbatch_frames, g.kp_cap, c.max_rows, false));
     const int sync_stride = g.kp_cap > c.max_rows ? g.kp_cap : c.max_rows;
     TRY(alloc_frames(ctx, ctx->sb, 1, sync_stride, sync_stride, true));
@@ -509,6 +513,7 @@ int svo_match_greedy(svo_ctx *ctx, const uint8_t *rows, int M, const uint8_t *cu
         return fail(ctx, SVO_E_INVALID, "svo_match_greedy: bad argument");
     FrameBufs &s = ctx->sb;
     if (M > s.row_stride || N > s.col_stride) return fail(ctx, SVO_E_CAPACITY, "svo_match_greedy: %d x %d exceeds capacity %d", M, N, s.col_stride);
+    if (N > greedy_max_cols()) return fail(ctx, SVO_E_CAPACITY, "svo_match_greedy: at most %d columns", greedy_max_cols());
     if (veto && (veto->n_boxes > 256 || veto->n_boxes < 0)) return fail(ctx, SVO_E_CAPACITY, "svo_match_greedy: at most 256 boxes");
     if (M == 0) return 0;
     CU(cudaSetDevice(ctx->cfg.device));
@@ -539,6 +544,7 @@ int svo_match_greedy(svo_ctx *ctx, const uint8_t *rows, int M, const uint8_t *cu
     a.best_idx = s.p2_best_idx; a.best = s.p2_best; a.second = s.p2_second;
     a.row_claimed = s.p2_row_claimed; a.row_bad = s.p1_row_bad;
     a.shortlist = s.shortlist; a.shortlist_hi = s.shortlist_hi; a.short_cnt = s.short_cnt;
+    a.res_rows = s.res_rows; a.res_off = s.res_off; a.res_want = s.res_want;
     a.win_uvr = win_uvr ? s.win : nullptr;
     a.cur_xy = (win_uvr || use_veto) ? s.cur_xy : nullptr;
     if (use_veto) { a.boxes = s.boxes; a.n_boxes = veto->n_boxes; a.F = s.F; a.row_xy = s.row_xy; }
@@ -668,6 +674,8 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
     ga.claim_time = fb.claim_time + (size_t)L.frame0 * K;
     ga.shortlist = fb.shortlist + (size_t)L.frame0 * R * 32; ga.shortlist_hi = fb.shortlist_hi + (size_t)L.frame0 * R * (SVO_SHORT_CAP - 32);
     ga.short_cnt = fb.short_cnt + (size_t)L.frame0 * R;
+    ga.res_rows = fb.res_rows + (size_t)L.frame0 * R; ga.res_off = fb.res_off + (size_t)L.frame0 * R;
+    ga.res_want = fb.res_want + (size_t)L.frame0 * R;
     if (any_prev) {
         ga.rows = make_set(fb.prev + (size_t)L.frame0 * R * 32, d_nprev, 1, R, 0);
         ga.mode = SVO_GREEDY_PASS1; ga.row_base = 0; ga.row_base_arr = nullptr;

@@ -136,6 +136,7 @@ struct GreedyArgs {
     uint32_t *shortlist;          // [frame][rows.stride_rows][32]: entries 0..31
     uint32_t *shortlist_hi;       // [frame][rows.stride_rows][SVO_SHORT_CAP - 32]: the rest
     int *short_cnt;               // [frame][rows.stride_rows]
+    int *res_rows, *res_off, *res_want;   // [frame][rows.stride_rows] resolver scratch (candidate rows, CSR offsets, decisions)
     const float *win_uvr;         // [frame][rows.stride_rows][3] or NULL
     const float *cur_xy;          // [frame][cols.stride_rows][2] or NULL
     // veto (pass 1)
@@ -152,3 +153,4 @@ struct BfArgs {
 void launch_bf(const BfArgs &a, int nframes, cudaStream_t st, long long *launches);
 void launch_disp2depth(const float *disp, float *depth, size_t n, float bf, cudaStream_t st, long long *launches);
 int setup_match_attributes();
+int greedy_max_cols();   // most columns (current-frame keypoints) the greedy resolver supports

@@ -195,6 +195,26 @@ def test_match_greedy_vs_oracle(ctxK, mode, seed):
         assert (ref[k][lv] == got[k][lv]).all(), k
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_match_greedy_long_chains_and_list_overflow(ctxK, mode):
+    """200 identical columns and 260 identical rows: every such row's short list overflows (exhaustive
+    re-scan path) and each claim depends on the previous one (the fixed-point resolver needs one sweep per
+    link of the chain); a second family of 90 near-duplicates stays within the short-list capacity."""
+    rng = np.random.default_rng(11 + mode)
+    cur = rng.integers(0, 256, (1500, 32), dtype=np.uint8)
+    cur[400:600] = cur[7]
+    cur[700:790] = cur[9]
+    rows = noisy_copies(rng, cur, 2000)
+    rows[100:360] = cur[7]
+    rows[500:560] = cur[9]
+    rows[900:960] = cur[9] ^ np.uint8(1)
+    ref = O.match_greedy(rows, cur, mode, row_base=3)
+    got = ctxK.match_greedy(rows, cur, mode, row_base=3)
+    for k in ("row_claimed", "claimed", "claim_row", "best_idx", "best", "second"):
+        assert (ref[k] == got[k]).all(), k
+    assert ref["row_claimed"][100:360].sum() >= 150
+
+
 def test_match_greedy_window_and_edge_cases(ctxK):
     rng = np.random.default_rng(3)
     cur = rng.integers(0, 256, (500, 32), dtype=np.uint8)
