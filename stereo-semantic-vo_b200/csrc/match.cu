@@ -299,7 +299,7 @@ __device__ bool veto_dynamic(const GreedyArgs &a, int f, int row, int col)
 // with one thread per row.  One CTA per frame.
 //
 // Rows whose list overflowed SVO_SHORT_CAP are re-scanned exhaustively (a warp per row) in every sweep.
-__global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_cols, int ent_cap)
+__global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_cols, int ent_cap, int unsorted)
 {
     const int f = blockIdx.x;
     const int M = set_count(a.rows, f), N = set_count(a.cols, f);
@@ -371,7 +371,18 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_c
     // ---- stage the short lists in shared memory (rows beyond ent_cap stay in global memory)
     for (int k = tid; k < total; k += RES_THREADS) {
         const int pk = rows_ne[k], r = pk & 0xffff, s = pk >> 16, off = roff[k];
-        if (s > SVO_SHORT_CAP || off + s > ent_cap) continue;
+        if (s > SVO_SHORT_CAP) continue;
+        if (off + s > ent_cap) {
+            // stays in global memory; k_pairs appends in arrival order, the sweeps need ascending columns
+            if (unsorted)
+                for (int i = 1; i < s; ++i) {
+                    const uint32_t e = *short_slot(a, ro + r, i);
+                    int j = i - 1;
+                    for (; j >= 0 && (*short_slot(a, ro + r, j) & 0xffffu) > (e & 0xffffu); --j) *short_slot(a, ro + r, j + 1) = *short_slot(a, ro + r, j);
+                    *short_slot(a, ro + r, j + 1) = e;
+                }
+            continue;
+        }
         const uint4 *lo = reinterpret_cast<const uint4 *>(a.shortlist + (ro + r) * 32);
         const uint4 *hi = reinterpret_cast<const uint4 *>(a.shortlist_hi + (ro + r) * (SVO_SHORT_CAP - 32));
         for (int j = 0; j < s; j += 4) {
@@ -381,6 +392,13 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_c
             if (j + 2 < s) ent[off + j + 2] = v.z;
             if (j + 3 < s) ent[off + j + 3] = v.w;
         }
+        if (unsorted)
+            for (int i = 1; i < s; ++i) {
+                const uint32_t e = ent[off + i];
+                int j = i - 1;
+                for (; j >= 0 && (ent[off + j] & 0xffffu) > (e & 0xffffu); --j) ent[off + j + 1] = ent[off + j];
+                ent[off + j + 1] = e;
+            }
     }
     __syncthreads();
     const uint8_t *rd = set_desc(a.rows, f), *cd = set_desc(a.cols, f);
@@ -515,11 +533,185 @@ __global__ void __launch_bounds__(M_THREADS) k_scores(GreedyArgs a)
     if (live && lane == 0) { a.best_idx[ro + r] = bi; a.best[ro + r] = bd; a.second[ro + r] = sd; }
 }
 
+// ---------------------------------------------------------------------------------------
+// Fused pass-1 front: the previous-frame x current-frame distance matrix is needed three times per
+// frame -- BFMatcher (cur -> prev 1-NN, pnpmatch.cc:266-278), the pass-1 short lists (prev rows over
+// cur columns, d < 15) and the exact (bestIdx, best, second) of every pass-1 row (match_score,
+// pnpmatch.cc:99).  k_pairs computes every distance ONCE: a CTA owns a tile of 256 current-frame
+// columns (8 per lane, lane-blocked) in swizzled shared memory and streams its share of the rows
+// through registers, 4 rows per warp step.  Per step a lane holds 4 x 8 distances: they update the
+// lane's 8 running column minima (BF), are tested against the pass-1 threshold (hits are rare and are
+// appended with an atomic; the resolver sorts each list by column) and are packed into bytes and
+// stored as 256 contiguous bytes per row into the frame's u8 distance matrix (min(d, 255)), which
+// k_scores_m later scans instead of recomputing the popcounts.
+// ---------------------------------------------------------------------------------------
+#define PT_COLS 256
+#define PT_ROWS 4
+
+__device__ __forceinline__ int pt_unit(int j, int h) { const int u = 2 * j + h; return u ^ ((u >> 4) & 7); }
+
+__global__ void __launch_bounds__(M_THREADS) k_pairs(PairArgs p)
+{
+    __shared__ uint4 tile[PT_COLS * 2];
+    __shared__ uint32_t cm[PT_COLS];
+    const GreedyArgs &a = p.g;
+    const int f = blockIdx.z;
+    const int M = set_count(a.rows, f), N = set_count(a.cols, f);
+    const int c0 = blockIdx.x * PT_COLS;
+    if (c0 >= N || M <= 0) return;
+    const int nc = min(PT_COLS, N - c0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint8_t *rd = set_desc(a.rows, f), *cd = set_desc(a.cols, f);
+    const size_t ro = (size_t)f * a.rows.stride_rows;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(cd) + (size_t)c0 * 2;
+        for (int i = tid; i < PT_COLS * 2; i += M_THREADS)
+            tile[i ^ ((i >> 4) & 7)] = i < nc * 2 ? src[i] : make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < PT_COLS; i += M_THREADS) cm[i] = 0xffffffffu;
+    }
+    __syncthreads();
+    uint32_t colmin[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) colmin[t] = 0xffffffffu;
+    const int groups = (M + PT_ROWS - 1) / PT_ROWS;
+    const int per = (groups + gridDim.y - 1) / gridDim.y;
+    const int q0 = blockIdx.y * per, q1 = min(q0 + per, groups);
+    uint8_t *dm = p.dmat + (size_t)f * p.dmat_frame_stride;
+    const bool store_ok = c0 + 8 * lane + 8 <= p.dmat_pitch;
+    const int T = p.T;
+    for (int q = q0 + warp; q < q1; q += M_WARPS) {
+        const int r0 = q * PT_ROWS;
+        Row R[PT_ROWS];
+        bool live[PT_ROWS];
+#pragma unroll
+        for (int k = 0; k < PT_ROWS; ++k) {
+            const int r = min(r0 + k, M - 1);
+            R[k] = load_row(rd, r);
+            live[k] = r0 + k < M && (!a.row_live || a.row_live[ro + r]);
+        }
+        uint32_t lo[PT_ROWS], hi[PT_ROWS];
+#pragma unroll
+        for (int k = 0; k < PT_ROWS; ++k) lo[k] = hi[k] = 0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int j = 8 * lane + t;
+            const uint4 x = tile[pt_unit(j, 0)], y = tile[pt_unit(j, 1)];
+#pragma unroll
+            for (int k = 0; k < PT_ROWS; ++k) {
+                const int d = popc8(R[k].a.x ^ x.x, R[k].a.y ^ x.y, R[k].a.z ^ x.z, R[k].a.w ^ x.w,
+                                    R[k].b.x ^ y.x, R[k].b.y ^ y.y, R[k].b.z ^ y.z, R[k].b.w ^ y.w);
+                if (r0 + k < M) colmin[t] = min(colmin[t], (uint32_t)d * 65536u + (uint32_t)(r0 + k));
+                const uint32_t byte = (uint32_t)min(d, 255);
+                if (t < 4) lo[k] |= byte << (8 * t); else hi[k] |= byte << (8 * (t - 4));
+                if (d < T && live[k] && j < nc) {
+                    const int pos = atomicAdd(a.short_cnt + ro + r0 + k, 1);
+                    if (pos < SVO_SHORT_CAP) *short_slot(a, ro + r0 + k, pos) = ((uint32_t)d << 16) | (uint32_t)(c0 + j);
+                }
+            }
+        }
+        if (store_ok) {
+#pragma unroll
+            for (int k = 0; k < PT_ROWS; ++k)
+                if (r0 + k < M)
+                    *reinterpret_cast<uint2 *>(dm + (size_t)(r0 + k) * p.dmat_pitch + c0 + 8 * lane) = make_uint2(lo[k], hi[k]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) atomicMin(&cm[8 * lane + t], colmin[t]);
+    __syncthreads();
+    for (int i = tid; i < nc; i += M_THREADS) atomicMin(p.bf_key + (size_t)f * a.cols.stride_rows + c0 + i, cm[i]);
+}
+
+// BF epilogue: key -> (trainIdx, distance), min_dist over the frame's queries, keep = d <= max(2*min, 30)
+__global__ void __launch_bounds__(256) k_bf_finish(PairArgs p, BfArgs b)
+{
+    __shared__ int wmin[8];
+    const int f = blockIdx.y;
+    const int nq = set_count(b.q, f), nt = set_count(b.t, f);
+    const uint32_t *key = p.bf_key + (size_t)f * b.q.stride_rows;
+    int m = 10000;
+    for (int i = threadIdx.x; i < nq; i += 256) m = min(m, (int)(key[i] >> 16));
+    m = __reduce_min_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) wmin[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = wmin[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = min(m, wmin[w]);
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= nq) return;
+    const size_t o = (size_t)f * b.q.stride_rows + i;
+    if (nt > 0) {
+        const uint32_t k = key[i];
+        const int d = (int)(k >> 16);
+        b.idx[o] = (int)(k & 0xffffu); b.dist[o] = d;
+        b.keep[o] = (double)d <= fmax(2.0 * (double)m, 30.0) ? 1 : 0;
+    } else { b.idx[o] = -1; b.dist[o] = -1; b.keep[o] = 0; }
+}
+
+// Exact (bestIdx, bestDist, secondBestDist) of every live pass-1 row from the u8 distance matrix: lane l
+// owns the contiguous columns [l W, (l+1) W), scans them in ascending order with the reference's running
+// update, and the 32 partial results compose exactly (see k_scores).  A byte of 255 stands for d >= 255
+// and is recomputed from the descriptors.
+#define SM_ROWS_PER_WARP 4
+__global__ void __launch_bounds__(M_THREADS) k_scores_m(PairArgs p)
+{
+    extern __shared__ int sm_time[];     // claim times, lane-block padded: column j at (j / W) * (W + 1) + j % W
+    const GreedyArgs &a = p.g;
+    const int f = blockIdx.y;
+    const int M = set_count(a.rows, f), N = set_count(a.cols, f);
+    if (blockIdx.x * M_WARPS * SM_ROWS_PER_WARP >= M) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int W = p.lane_cols;           // multiple of 16
+    const size_t ro = (size_t)f * a.rows.stride_rows, co = (size_t)f * a.cols.stride_rows;
+    for (int j = threadIdx.x; j < 32 * W; j += M_THREADS) {
+        const int l = j / W;
+        sm_time[l * (W + 1) + (j - l * W)] = j < N ? a.claim_time[co + j] : INT_MIN;
+    }
+    __syncthreads();
+    const uint8_t *rd = set_desc(a.rows, f), *cd = set_desc(a.cols, f);
+    const uint8_t *dm = p.dmat + (size_t)f * p.dmat_frame_stride;
+    const int rb = a.row_base + (a.row_base_arr ? a.row_base_arr[f] : 0);
+    const int *tl = sm_time + lane * (W + 1);
+    for (int k = 0; k < SM_ROWS_PER_WARP; ++k) {
+        const int r = (blockIdx.x * M_WARPS + warp) * SM_ROWS_PER_WARP + k;
+        if (r >= M) break;
+        if (a.row_live && !a.row_live[ro + r]) continue;
+        const int g = rb + r;
+        const uint4 *src = reinterpret_cast<const uint4 *>(dm + (size_t)r * p.dmat_pitch + lane * W);
+        int lb = 256, ls = 256, li = -1;
+        for (int c = 0; c < W; c += 16) {
+            const uint4 v = src[c >> 4];
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                int d = (int)((w4[i >> 2] >> (8 * (i & 3))) & 0xffu);
+                if (tl[c + i] >= g && d < lb) {
+                    const int j = lane * W + c + i;
+                    if (d == 255) d = ham_global(load_row(rd, r), cd, j);
+                    if (d < lb) { ls = lb; lb = d; li = j; }
+                }
+            }
+        }
+        const uint32_t key = li >= 0 ? (((uint32_t)lb << 16) | (uint32_t)li) : 0xffffffffu;
+        const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
+        int bd = 256, sd = 256, bi = -1;
+        if (kmin != 0xffffffffu) {
+            bd = (int)(kmin >> 16); bi = (int)(kmin & 0xffffu);
+            const int lstar = bi / W;
+            const uint32_t before = __reduce_min_sync(0xffffffffu, lane < lstar ? (uint32_t)lb : 256u);
+            const int ls_star = __shfl_sync(0xffffffffu, ls, lstar);
+            sd = min((int)before, ls_star);
+        }
+        if (lane == 0) { a.best_idx[ro + r] = bi; a.best[ro + r] = bd; a.second[ro + r] = sd; }
+    }
+}
+
 static int g_resolve_smem_limit = 48 * 1024;
 
 int setup_match_attributes()
 {
     g_resolve_smem_limit = 200 * 1024;
+    if (cudaFuncSetAttribute(k_scores_m, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess) return 1;
     return (int)cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, g_resolve_smem_limit);
 }
 
@@ -542,7 +734,7 @@ void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStrea
     const int colsA = (maxN + 3) & ~3;
     const int ent_cap = (g_resolve_smem_limit - colsA * 9 - 64) / 4;
     const size_t smem = (size_t)colsA * 9 + (size_t)ent_cap * 4;
-    k_resolve<<<nframes, RES_THREADS, smem, st>>>(a, colsA, ent_cap);
+    k_resolve<<<nframes, RES_THREADS, smem, st>>>(a, colsA, ent_cap, 0);
     *launches += 3;
     if (want_scores && a.best_idx) {
         dim3 gf((maxM + M_WARPS - 1) / M_WARPS, nframes);
@@ -550,6 +742,34 @@ void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStrea
         else k_scores<false><<<gf, M_THREADS, 0, st>>>(a);
         ++*launches;
     }
+}
+
+// BF + greedy pass 1 of a batch with every distance computed once (k_pairs).
+void launch_pass1_fused(const PairArgs &p0, const BfArgs &b, int nframes, cudaStream_t st, long long *launches)
+{
+    PairArgs p = p0;
+    const GreedyArgs &a = p.g;
+    const int maxM = a.rows.count ? a.rows.stride_rows : a.rows.fixed_count;
+    const int maxN = a.cols.count ? a.cols.stride_rows : a.cols.fixed_count;
+    if (maxM <= 0 || maxN <= 0 || nframes <= 0) return;
+    const int mx = maxM > maxN ? maxM : maxN;
+    dim3 gi((mx + 255) / 256, nframes);
+    k_greedy_init<<<gi, 256, 0, st>>>(a, 1);
+    cudaMemsetAsync(p.bf_key, 0xff, sizeof(uint32_t) * (size_t)nframes * a.cols.stride_rows, st);
+    p.T = 15;
+    const int tiles = (maxN + PT_COLS - 1) / PT_COLS;
+    int splits = (148 * 6 + tiles * nframes - 1) / (tiles * nframes);   // about two waves of 3 CTAs per SM
+    const int max_splits = (maxM + 8 * PT_ROWS - 1) / (8 * PT_ROWS);
+    splits = splits < 1 ? 1 : (splits > max_splits ? max_splits : splits);
+    k_pairs<<<dim3(tiles, splits, nframes), M_THREADS, 0, st>>>(p);
+    k_bf_finish<<<dim3((maxN + 255) / 256, nframes), 256, 0, st>>>(p, b);
+    const int colsA = (maxN + 3) & ~3;
+    const int ent_cap = (g_resolve_smem_limit - colsA * 9 - 64) / 4;
+    k_resolve<<<nframes, RES_THREADS, (size_t)colsA * 9 + (size_t)ent_cap * 4, st>>>(a, colsA, ent_cap, 1);
+    p.lane_cols = (((maxN + 31) / 32) + 15) & ~15;
+    const size_t sm = (size_t)32 * (p.lane_cols + 1) * sizeof(int);
+    k_scores_m<<<dim3((maxM + M_WARPS * SM_ROWS_PER_WARP - 1) / (M_WARPS * SM_ROWS_PER_WARP), nframes), M_THREADS, sm, st>>>(p);
+    *launches += 5;
 }
 
 // ---------------------------------------------------------------------------------------

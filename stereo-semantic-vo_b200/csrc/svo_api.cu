@@ -27,6 +27,7 @@ struct FrameBufs {           // per-frame (stereo pair) device arrays
     int *p2_best_idx, *p2_best, *p2_second; uint8_t *p2_row_claimed;
     uint32_t *shortlist, *shortlist_hi; int *short_cnt;
     int *res_rows, *res_off, *res_want;
+    uint8_t *dmat; uint32_t *bf_key; int dmat_pitch; size_t dmat_frame_stride;   // fused pass-1 front (batch path)
     float *u_right, *depth; int *match_r, *sad, *n_stereo;
     int *params;             // [4][nframes]: n_prev, n_map, bf bits, baseline bits
     // sync-only extras
@@ -227,6 +228,15 @@ int alloc_frames(svo_ctx *ctx, FrameBufs &f, int nframes, int col_stride, int ro
     TRY(dalloc(ctx, &f.sad, C)); TRY(dalloc(ctx, &f.n_stereo, F));
     TRY(dalloc(ctx, &f.params, 4 * F));
     f.cols = nullptr; f.win = f.cur_xy = f.row_xy = nullptr; f.boxes = nullptr; f.F = nullptr;
+    f.dmat = nullptr; f.bf_key = nullptr; f.dmat_pitch = 0; f.dmat_frame_stride = 0;
+    if (!sync_extras) {
+        // u8 distance matrix previous-frame rows x current-frame columns; k_scores_m gives every lane a
+        // 16-byte aligned block of columns, so the pitch is 32 such blocks
+        f.dmat_pitch = 32 * ((((col_stride + 31) / 32) + 15) & ~15);
+        f.dmat_frame_stride = (size_t)col_stride * f.dmat_pitch;
+        TRY(dalloc(ctx, &f.dmat, F * f.dmat_frame_stride));
+        TRY(dalloc(ctx, &f.bf_key, C));
+    }
     if (sync_extras) {
         TRY(dalloc(ctx, &f.cols, C * 32));
         TRY(dalloc(ctx, &f.win, R * 3)); TRY(dalloc(ctx, &f.cur_xy, C * 2)); TRY(dalloc(ctx, &f.row_xy, R * 2));
@@ -660,13 +670,8 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
     // ---- matching: BF (cur -> prev), greedy pass 1 (prev rows), greedy pass 2 (map rows)
     // left images sit in even slots: consecutive frames' descriptor blocks are 2*kp_cap rows apart
     const MatchSet cur = make_set(b.desc + (size_t)L.slot0 * g.kp_cap * 32, b.nkp + L.slot0, 2, g.kp_cap, 0, 2 * g.kp_cap);
-    if (any_prev) {
-        BfArgs ba;
-        ba.q = cur; ba.t = make_set(fb.prev + (size_t)L.frame0 * R * 32, d_nprev, 1, R, 0);
-        ba.idx = fb.bf_idx + (size_t)L.frame0 * K; ba.dist = fb.bf_dist + (size_t)L.frame0 * K;
-        ba.keep = fb.bf_keep + (size_t)L.frame0 * K; ba.min_dist = fb.min_dist + L.frame0;
-        launch_bf(ba, n, st, &ctx->launches);
-    }
+    bool fused = any_prev;
+    for (int i = 0; i < n; ++i) fused = fused && frames[i].n_prev <= K;   // the distance matrix holds kp_cap rows
     GreedyArgs ga;
     memset(&ga, 0, sizeof(ga));
     ga.cols = cur;
@@ -677,13 +682,27 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
     ga.res_rows = fb.res_rows + (size_t)L.frame0 * R; ga.res_off = fb.res_off + (size_t)L.frame0 * R;
     ga.res_want = fb.res_want + (size_t)L.frame0 * R;
     if (any_prev) {
+        BfArgs ba;
+        ba.q = cur; ba.t = make_set(fb.prev + (size_t)L.frame0 * R * 32, d_nprev, 1, R, 0);
+        ba.idx = fb.bf_idx + (size_t)L.frame0 * K; ba.dist = fb.bf_dist + (size_t)L.frame0 * K;
+        ba.keep = fb.bf_keep + (size_t)L.frame0 * K; ba.min_dist = fb.min_dist + L.frame0;
         ga.rows = make_set(fb.prev + (size_t)L.frame0 * R * 32, d_nprev, 1, R, 0);
         ga.mode = SVO_GREEDY_PASS1; ga.row_base = 0; ga.row_base_arr = nullptr;
         ga.row_live = fb.prev_live + (size_t)L.frame0 * R;
         ga.best_idx = fb.p1_best_idx + (size_t)L.frame0 * R; ga.best = fb.p1_best + (size_t)L.frame0 * R;
         ga.second = fb.p1_second + (size_t)L.frame0 * R;
         ga.row_claimed = fb.p1_row_claimed + (size_t)L.frame0 * R; ga.row_bad = nullptr;
-        launch_greedy(ga, n, true, st, &ctx->launches);
+        if (fused) {
+            // BF (cur -> prev) and greedy pass 1 (prev rows over cur columns) share one distance matrix
+            PairArgs pa;
+            pa.g = ga;
+            pa.dmat = fb.dmat + (size_t)L.frame0 * fb.dmat_frame_stride; pa.dmat_frame_stride = fb.dmat_frame_stride;
+            pa.dmat_pitch = fb.dmat_pitch; pa.bf_key = fb.bf_key + (size_t)L.frame0 * K; pa.T = 0; pa.lane_cols = 0;
+            launch_pass1_fused(pa, ba, n, st, &ctx->launches);
+        } else {
+            launch_bf(ba, n, st, &ctx->launches);
+            launch_greedy(ga, n, true, st, &ctx->launches);
+        }
     }
     if (any_map) {
         ga.rows = make_set(fb.map + (size_t)L.frame0 * R * 32, d_nmap, 1, R, 0);

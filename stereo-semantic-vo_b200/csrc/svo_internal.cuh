@@ -151,6 +151,15 @@ struct BfArgs {
     int *min_dist;        // [frame] scratch
 };
 void launch_bf(const BfArgs &a, int nframes, cudaStream_t st, long long *launches);
+struct PairArgs {            // fused BF + pass-1 front of the batch path (match.cu: k_pairs / k_scores_m)
+    GreedyArgs g;            // rows = previous frame, cols = current frame, pass-1 outputs
+    uint8_t *dmat;           // [frame][rows][dmat_pitch] u8 distances, min(d, 255)
+    size_t dmat_frame_stride;
+    int dmat_pitch;          // bytes per matrix row, multiple of 16, >= column capacity
+    uint32_t *bf_key;        // [frame][cols.stride_rows] (d << 16 | prev row) minima
+    int T, lane_cols;        // filled by the launcher
+};
+void launch_pass1_fused(const PairArgs &p, const BfArgs &b, int nframes, cudaStream_t st, long long *launches);
 void launch_disp2depth(const float *disp, float *depth, size_t n, float bf, cudaStream_t st, long long *launches);
 int setup_match_attributes();
 int greedy_max_cols();   // most columns (current-frame keypoints) the greedy resolver supports
