@@ -14,21 +14,81 @@
 
 #define FAST_THREADS 256
 
-// Necessary condition for a FAST-9 corner, cheap first: any 9-arc of the 16-ring holds at
-// least one pixel of every antipodal pair, so "brighter" needs d[k] > t or d[k+8] > t for every
-// k (and likewise "darker").  Four pairs (8 ring pixels) are tested here; survivors go to the
-// full score.  Returns 1 when the pixel may still be a corner.
-__device__ __forceinline__ int fast_quick(const uint8_t *p, int sp, int t)
+// ---- stage A: necessary condition on 4 horizontally adjacent pixels at once (SWAR on bytes) ----
+// Any 9-arc of the 16-ring holds at least one pixel of every antipodal pair, so a "centre brighter"
+// corner needs p[k] < v - t or p[k+8] < v - t for every k, and a "centre darker" corner the mirror
+// image with p > v + t.  Four of the eight pairs are tested (N/S, E/W and the two diagonals).
+// All comparisons are unsigned-byte compares in bit 7 of each byte; LOP3/IADD only, no SIMD video ops
+// (sm_100a emulates those).
+#define SW_H 0x80808080u
+#define SW_L 0x7f7f7f7fu
+
+// bit 7 of each byte: x < y (unsigned).  xh = x | H and yl = y & L are passed in so they can be shared.
+__device__ __forceinline__ uint32_t swar_lt(uint32_t x, uint32_t xh, uint32_t y, uint32_t yl)
 {
-    const int v = p[0];
-    const int d0 = v - p[3 * sp], d8 = v - p[-3 * sp], d4 = v - p[3], d12 = v - p[-3];
-    bool pb = (d0 > t || d8 > t) && (d4 > t || d12 > t);
-    bool pd = (d0 < -t || d8 < -t) && (d4 < -t || d12 < -t);
-    if (!pb && !pd) return 0;
-    const int d2 = v - p[2 * sp + 2], d10 = v - p[-2 * sp - 2], d6 = v - p[-2 * sp + 2], d14 = v - p[2 * sp - 2];
-    pb = pb && (d2 > t || d10 > t) && (d6 > t || d14 > t);
-    pd = pd && (d2 < -t || d10 < -t) && (d6 < -t || d14 < -t);
-    return (pb || pd) ? 1 : 0;
+    const uint32_t t1 = xh - yl;                      // bit 7: (x & 0x7f) >= (y & 0x7f); no cross-byte borrow
+    return (~x & y) | (~(x ^ y) & ~t1);
+}
+// per-byte min(v + t, 255) and max(v - t, 0) for 0 < t < 128
+__device__ __forceinline__ uint32_t swar_addsat(uint32_t v, uint32_t t4)
+{
+    const uint32_t s = (v & SW_L) + t4;               // low 7 bits + t: < 256 per byte
+    const uint32_t ovf = v & s & SW_H;
+    return (s ^ (v & SW_H)) | ((ovf << 1) - (ovf >> 7));
+}
+__device__ __forceinline__ uint32_t swar_subsat(uint32_t v, uint32_t t4)
+{
+    const uint32_t d = (v | SW_H) - t4;
+    const uint32_t m = (v | d) & SW_H;                // bytes that did not underflow
+    return (d & (m - (m >> 7))) | (d & v & SW_H);
+}
+// q: address of the quad's first pixel in the staged rows (4-byte aligned); returns bit 7 flags
+__device__ __forceinline__ uint32_t fast_quick4(const uint8_t *q, int sp, uint32_t t4)
+{
+    const uint32_t *c = reinterpret_cast<const uint32_t *>(q);
+    const int sw = sp >> 2;
+    const uint32_t v = c[0];
+    const uint32_t lo = swar_subsat(v, t4), hi = swar_addsat(v, t4);
+    const uint32_t lol = lo & SW_L, hih = hi | SW_H;
+    uint32_t pb = SW_H, pd = SW_H;
+#define FAST_PAIR(P, Q) { \
+        const uint32_t p_ = (P), q_ = (Q); \
+        pb &= swar_lt(p_, p_ | SW_H, lo, lol) | swar_lt(q_, q_ | SW_H, lo, lol); \
+        pd &= swar_lt(hi, hih, p_, p_ & SW_L) | swar_lt(hi, hih, q_, q_ & SW_L); }
+    FAST_PAIR(c[3 * sw], c[-3 * sw]);                                                   // ring 0 / 8
+    {
+        const uint32_t wl = c[-1], wr = c[1];
+        FAST_PAIR(__byte_perm(v, wr, 0x6543), __byte_perm(wl, v, 0x4321));              // ring 4 (x+3) / 12 (x-3)
+    }
+    {
+        const uint32_t al = c[2 * sw - 1], a0 = c[2 * sw], ar = c[2 * sw + 1];
+        const uint32_t bl = c[-2 * sw - 1], b0 = c[-2 * sw], br = c[-2 * sw + 1];
+        FAST_PAIR(__byte_perm(a0, ar, 0x5432), __byte_perm(bl, b0, 0x5432));            // ring 2 (+2,+2) / 10 (-2,-2)
+        FAST_PAIR(__byte_perm(b0, br, 0x5432), __byte_perm(al, a0, 0x5432));            // ring 6 (+2,-2) / 14 (-2,+2)
+    }
+#undef FAST_PAIR
+    return (pb | pd) & SW_H;
+}
+
+// ---- stage B1: exact arc test on a candidate, one polarity per pass (sgn = +1: ring darker than the
+// centre by more than t, -1: brighter).  The 16 sign bits are shifted into a mask; a corner needs 9
+// contiguous ones on the circular mask.
+__device__ __forceinline__ bool fast_arc(const uint8_t *p, int sp, int t, int sgn)
+{
+    const int c = sgn * (int)p[0] - t;     // sgn*(v - q) > t  <=>  sgn*q - c < 0
+    uint32_t m = 0;
+#define FAST_BIT(off) m = __funnelshift_l((uint32_t)(sgn * (int)p[off] - c), m, 1)
+    FAST_BIT(3 * sp);      FAST_BIT(3 * sp + 1);  FAST_BIT(2 * sp + 2);   FAST_BIT(sp + 3);
+    FAST_BIT(3);           FAST_BIT(-sp + 3);     FAST_BIT(-2 * sp + 2);  FAST_BIT(-3 * sp + 1);
+    FAST_BIT(-3 * sp);     FAST_BIT(-3 * sp - 1); FAST_BIT(-2 * sp - 2);  FAST_BIT(-sp - 3);
+    FAST_BIT(-3);          FAST_BIT(sp - 3);      FAST_BIT(2 * sp - 2);   FAST_BIT(3 * sp - 1);
+#undef FAST_BIT
+    m |= m << 16;
+    uint32_t a = m & (m >> 1);
+    a &= a >> 2;
+    a &= a >> 4;            // runs of 8
+    a &= m >> 8;            // runs of 9
+    return (a & 0xffffu) != 0;
 }
 
 // Exact score: max over the 16 arcs of 9 contiguous ring pixels of min(v - p) (brighter) and of
@@ -75,7 +135,7 @@ extern __shared__ __align__(16) uint8_t fast_smem[];
 // shared-memory carve-up for a level of pitch sp (bytes)
 __host__ __device__ inline int fast_off_sc(int sp) { return (SVO_FAST_BAND + 8) * sp; }
 __host__ __device__ inline int fast_off_cand(int sp) { return fast_off_sc(sp) + (SVO_FAST_BAND + 2) * sp; }
-__host__ __device__ inline int fast_off_mask(int sp) { return fast_off_cand(sp) + 2 * (SVO_FAST_BAND + 2) * sp + 512; }
+__host__ __device__ inline int fast_off_mask(int sp) { return fast_off_cand(sp) + 2 * ((SVO_FAST_BAND + 2) * (sp + 128) + 8 * 128); }
 __host__ __device__ inline int fast_mask_words(int sp) { return SVO_FAST_BAND * ((sp + 31) / 32); }
 
 __global__ void __launch_bounds__(FAST_THREADS) k_fast(Bufs b, Geom g, int slot0)
@@ -110,24 +170,61 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(Bufs b, Geom g, int slot0
         for (int i = tid; i < nrow * wpr; i += FAST_THREADS) mask[i] = 0;
     }
     __syncthreads();
-    // A. cheap necessary test on every pixel of rows yb-1..ye, columns x0-1..x1, in 32-pixel chunks
-    //    dealt round-robin to the warps; each warp appends survivors to its OWN candidate list (no
-    //    atomics, no block barrier) and then
-    // B. exact-scores its own candidates, densely packed over the lanes.
-    const int sw = L.x1 - L.x0 + 2;
-    const int cpr = (sw + 31) >> 5;
+    // A. SWAR necessary test on every pixel of rows yb-1..ye, columns x0-1..x1, four pixels per thread, in
+    //    128-pixel chunks dealt round-robin to the warps; each warp appends survivors to its OWN candidate
+    //    list (no atomics, no block barrier), then
+    // B1. runs the exact arc test on its candidates (densely packed over the lanes) and compacts the true
+    //    corners in place, and
+    // B2. scores the corners.
+    const int xq0 = (L.x0 - 1) & ~3;
+    const int nq = (L.x1 + 1 - xq0 + 3) >> 2;
+    const int cpr = (nq + 31) >> 5;
     const int nchunks = (nrow + 2) * cpr;
-    const int wcap = ((nchunks + nwarps - 1) / nwarps) << 5;
+    const int wcap = ((nchunks + nwarps - 1) / nwarps) << 7;
     uint16_t *mine = cand + warp * wcap;
+    const uint32_t t4 = (uint32_t)t * 0x01010101u;
+    const uint32_t ltm = (1u << lane) - 1u;
     int nmine = 0;
-    for (int c = warp; c < nchunks; c += nwarps) {
-        const int r = c / cpr, x = L.x0 - 1 + ((c - r * cpr) << 5) + lane;
-        const bool ok = x < L.x1 + 1 && fast_quick(pix + (r + 3) * sp + x, sp, t);
-        const uint32_t m = __ballot_sync(0xffffffffu, ok);
-        if (ok) mine[nmine + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(r * sp + x);
-        nmine += __popc(m);
+    {
+        int r = 0, ch = warp;
+        while (ch >= cpr) { ch -= cpr; ++r; }
+        for (int c = warp; c < nchunks; c += nwarps) {
+            const int qi = (ch << 5) + lane;
+            const int x = xq0 + (qi << 2);
+            uint32_t pass = 0;
+            if (qi < nq) pass = fast_quick4(pix + (r + 3) * sp + x, sp, t4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool ok = ((pass >> (8 * k + 7)) & 1u) && x + k >= L.x0 - 1 && x + k < L.x1 + 1;
+                const uint32_t m = __ballot_sync(0xffffffffu, ok);
+                if (ok) mine[nmine + __popc(m & ltm)] = (uint16_t)(r * sp + x + k);
+                nmine += __popc(m);
+            }
+            ch += nwarps;
+            while (ch >= cpr) { ch -= cpr; ++r; }
+        }
     }
     __syncwarp();
+    int ncorn = 0;
+    for (int i0 = 0; i0 < nmine; i0 += 32) {
+        const int i = i0 + lane;
+        bool corner = false;
+        int pos = 0;
+        if (i < nmine) {
+            pos = mine[i];
+            const uint8_t *p = pix + pos + 3 * sp;
+            const int v = p[0], d0 = v - p[3 * sp], d8 = v - p[-3 * sp];
+            const bool sb = d0 > t || d8 > t, sd = d0 < -t || d8 < -t;   // polarities the first antipodal pair allows
+            if (sb || sd) corner = fast_arc(p, sp, t, sb ? 1 : -1);
+            if (sb && sd && !corner) corner = fast_arc(p, sp, t, -1);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, corner);
+        __syncwarp();
+        if (corner) mine[ncorn + __popc(m & ltm)] = (uint16_t)pos;       // in place: ncorn <= i0
+        ncorn += __popc(m);
+        __syncwarp();
+    }
+    nmine = ncorn;
     for (int i = lane; i < nmine; i += 32) {
         const int pos = mine[i];
         const int s = fast_score(pix + pos + 3 * sp, sp, t);
