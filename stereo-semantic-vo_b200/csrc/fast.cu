@@ -70,63 +70,41 @@ __device__ __forceinline__ uint32_t fast_quick4(const uint8_t *q, int sp, uint32
     return (pb | pd) & SW_H;
 }
 
-// ---- stage B1: exact arc test on a candidate, one polarity per pass (sgn = +1: ring darker than the
-// centre by more than t, -1: brighter).  The 16 sign bits are shifted into a mask; a corner needs 9
-// contiguous ones on the circular mask.
-__device__ __forceinline__ bool fast_arc(const uint8_t *p, int sp, int t, int sgn)
-{
-    const int c = sgn * (int)p[0] - t;     // sgn*(v - q) > t  <=>  sgn*q - c < 0
-    uint32_t m = 0;
-#define FAST_BIT(off) m = __funnelshift_l((uint32_t)(sgn * (int)p[off] - c), m, 1)
-    FAST_BIT(3 * sp);      FAST_BIT(3 * sp + 1);  FAST_BIT(2 * sp + 2);   FAST_BIT(sp + 3);
-    FAST_BIT(3);           FAST_BIT(-sp + 3);     FAST_BIT(-2 * sp + 2);  FAST_BIT(-3 * sp + 1);
-    FAST_BIT(-3 * sp);     FAST_BIT(-3 * sp - 1); FAST_BIT(-2 * sp - 2);  FAST_BIT(-sp - 3);
-    FAST_BIT(-3);          FAST_BIT(sp - 3);      FAST_BIT(2 * sp - 2);   FAST_BIT(3 * sp - 1);
-#undef FAST_BIT
-    m |= m << 16;
-    uint32_t a = m & (m >> 1);
-    a &= a >> 2;
-    a &= a >> 4;            // runs of 8
-    a &= m >> 8;            // runs of 9
-    return (a & 0xffffu) != 0;
-}
-
-// Exact score: max over the 16 arcs of 9 contiguous ring pixels of min(v - p) (brighter) and of
-// min(p - v) (darker), minus 1; 0 unless >= t.  Sliding 9-minimum as min3 of min3 (VIMNMX3).
+// Exact score: max over the 16 arcs of 9 contiguous ring pixels of min(v - p) (centre brighter) and of
+// min(p - v) (centre darker), minus 1; 0 unless >= t.  Both polarities at once, branch-free, on packed
+// s16x2 values with the DPX min3/max3 instructions (VIMNMX3.S16x2): register X[k] holds the biased
+// differences e = v + 256 - p of ring pixels k (low half) and k + 8 (high half), so one instruction
+// advances two arcs.  Sliding 9-minimum = min3 of min3 (windows of 3, then offsets 0/3/6).
+__device__ __forceinline__ uint32_t swap16(uint32_t x) { return __byte_perm(x, 0, 0x1032); }
 __device__ __forceinline__ int fast_score(const uint8_t *p, int sp, int t)
 {
-    const int v = p[0];
-    int d[16];
-    d[0] = v - p[3 * sp];       d[1] = v - p[3 * sp + 1];   d[2] = v - p[2 * sp + 2];   d[3] = v - p[sp + 3];
-    d[4] = v - p[3];            d[5] = v - p[-sp + 3];      d[6] = v - p[-2 * sp + 2];  d[7] = v - p[-3 * sp + 1];
-    d[8] = v - p[-3 * sp];      d[9] = v - p[-3 * sp - 1];  d[10] = v - p[-2 * sp - 2]; d[11] = v - p[-sp - 3];
-    d[12] = v - p[-3];          d[13] = v - p[sp - 3];      d[14] = v - p[2 * sp - 2];  d[15] = v - p[3 * sp - 1];
-    bool pb = true, pd = true;   // all 8 antipodal pairs: exact-score only the polarity that can still win
+    const uint32_t vb = ((uint32_t)p[0] + 256u) * 0x10001u;
+    uint32_t X[16];
+#define FAST_E(k, lo, hi) X[k] = vb - ((uint32_t)p[lo] + ((uint32_t)p[hi] << 16))
+    FAST_E(0, 3 * sp, -3 * sp);          FAST_E(1, 3 * sp + 1, -3 * sp - 1);
+    FAST_E(2, 2 * sp + 2, -2 * sp - 2);  FAST_E(3, sp + 3, -sp - 3);
+    FAST_E(4, 3, -3);                    FAST_E(5, -sp + 3, sp - 3);
+    FAST_E(6, -2 * sp + 2, 2 * sp - 2);  FAST_E(7, -3 * sp + 1, 3 * sp - 1);
+#undef FAST_E
+#pragma unroll
+    for (int k = 0; k < 8; ++k) X[k + 8] = swap16(X[k]);
+    uint32_t a[14], b[14];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        pb = pb && (d[k] > t || d[k + 8] > t);
-        pd = pd && (d[k] < -t || d[k + 8] < -t);
+        a[k] = __vimin3_s16x2(X[k], X[k + 1], X[k + 2]);
+        b[k] = __vimax3_s16x2(X[k], X[k + 1], X[k + 2]);
     }
-    int best = 0;
-    if (pb) {  // max over arcs of min d (centre brighter)
-        int a[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) a[k] = __vimin3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-        int m = -256;
+    for (int k = 0; k < 6; ++k) { a[k + 8] = swap16(a[k]); b[k + 8] = swap16(b[k]); }
+    uint32_t mx = 0u, mn = 0x7fff7fffu;     // max over arcs of the arc minimum / min over arcs of the arc maximum
 #pragma unroll
-        for (int k = 0; k < 16; ++k) m = max(m, __vimin3_s32(a[k], a[(k + 3) & 15], a[(k + 6) & 15]));
-        best = m;
+    for (int k = 0; k < 8; ++k) {
+        mx = __vmaxs2(mx, __vimin3_s16x2(a[k], a[k + 3], a[k + 6]));
+        mn = __vmins2(mn, __vimax3_s16x2(b[k], b[k + 3], b[k + 6]));
     }
-    if (pd) {  // max over arcs of min -d (centre darker)
-        int a[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) a[k] = __vimax3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-        int m = 256;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) m = min(m, __vimax3_s32(a[k], a[(k + 3) & 15], a[(k + 6) & 15]));
-        best = max(best, -m);
-    }
-    const int s = best - 1;
+    const int bright = max((int)(mx & 0xffffu), (int)(mx >> 16)) - 256;   // max arc-min of (v - p)
+    const int dark = 256 - min((int)(mn & 0xffffu), (int)(mn >> 16));     // max arc-min of (p - v)
+    const int s = max(bright, dark) - 1;
     return s >= t ? s : 0;
 }
 
@@ -173,9 +151,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(Bufs b, Geom g, int slot0
     // A. SWAR necessary test on every pixel of rows yb-1..ye, columns x0-1..x1, four pixels per thread, in
     //    128-pixel chunks dealt round-robin to the warps; each warp appends survivors to its OWN candidate
     //    list (no atomics, no block barrier), then
-    // B1. runs the exact arc test on its candidates (densely packed over the lanes) and compacts the true
-    //    corners in place, and
-    // B2. scores the corners.
+    // B. exact-scores its own candidates, densely packed over the lanes.
     const int xq0 = (L.x0 - 1) & ~3;
     const int nq = (L.x1 + 1 - xq0 + 3) >> 2;
     const int cpr = (nq + 31) >> 5;
@@ -192,10 +168,14 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(Bufs b, Geom g, int slot0
             const int qi = (ch << 5) + lane;
             const int x = xq0 + (qi << 2);
             uint32_t pass = 0;
-            if (qi < nq) pass = fast_quick4(pix + (r + 3) * sp + x, sp, t4);
+            if (qi < nq) {
+                pass = fast_quick4(pix + (r + 3) * sp + x, sp, t4);
+                if (x < L.x0 - 1) pass &= 0xffffffffu << (8 * (L.x0 - 1 - x));        // first quad of the row
+                if (x + 3 > L.x1) pass &= 0xffffffffu >> (8 * (x + 3 - L.x1));        // last quad of the row
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const bool ok = ((pass >> (8 * k + 7)) & 1u) && x + k >= L.x0 - 1 && x + k < L.x1 + 1;
+                const bool ok = (pass >> (8 * k + 7)) & 1u;
                 const uint32_t m = __ballot_sync(0xffffffffu, ok);
                 if (ok) mine[nmine + __popc(m & ltm)] = (uint16_t)(r * sp + x + k);
                 nmine += __popc(m);
@@ -205,26 +185,6 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(Bufs b, Geom g, int slot0
         }
     }
     __syncwarp();
-    int ncorn = 0;
-    for (int i0 = 0; i0 < nmine; i0 += 32) {
-        const int i = i0 + lane;
-        bool corner = false;
-        int pos = 0;
-        if (i < nmine) {
-            pos = mine[i];
-            const uint8_t *p = pix + pos + 3 * sp;
-            const int v = p[0], d0 = v - p[3 * sp], d8 = v - p[-3 * sp];
-            const bool sb = d0 > t || d8 > t, sd = d0 < -t || d8 < -t;   // polarities the first antipodal pair allows
-            if (sb || sd) corner = fast_arc(p, sp, t, sb ? 1 : -1);
-            if (sb && sd && !corner) corner = fast_arc(p, sp, t, -1);
-        }
-        const uint32_t m = __ballot_sync(0xffffffffu, corner);
-        __syncwarp();
-        if (corner) mine[ncorn + __popc(m & ltm)] = (uint16_t)pos;       // in place: ncorn <= i0
-        ncorn += __popc(m);
-        __syncwarp();
-    }
-    nmine = ncorn;
     for (int i = lane; i < nmine; i += 32) {
         const int pos = mine[i];
         const int s = fast_score(pix + pos + 3 * sp, sp, t);
