@@ -229,12 +229,18 @@ __global__ void __launch_bounds__(M_THREADS) k_shortlist(GreedyArgs a, int T)
             const uint4 x = tile[unit_of(jj, 0)], y = tile[unit_of(jj, 1)];
             float cu = 0.f, cv = 0.f;
             if (WIN && inb) { cu = cxy[2 * (c0 + j)]; cv = cxy[2 * (c0 + j) + 1]; }
+            int d[SL_ROWS_PER_WARP];
+#pragma unroll
+            for (int k = 0; k < SL_ROWS_PER_WARP; ++k)
+                d[k] = popc8(R[k].a.x ^ x.x, R[k].a.y ^ x.y, R[k].a.z ^ x.z, R[k].a.w ^ x.w,
+                             R[k].b.x ^ y.x, R[k].b.y ^ y.y, R[k].b.z ^ y.z, R[k].b.w ^ y.w);
+            // one vote for the 4 rows: most 32-column steps hold no entry below T at all
+            const int dmin = min(min(d[0], d[1]), min(d[2], d[3]));
+            if (!__any_sync(0xffffffffu, inb && dmin < T)) continue;
 #pragma unroll
             for (int k = 0; k < SL_ROWS_PER_WARP; ++k) {
                 if (!live[k]) continue;   // warp-uniform
-                int d = popc8(R[k].a.x ^ x.x, R[k].a.y ^ x.y, R[k].a.z ^ x.z, R[k].a.w ^ x.w,
-                              R[k].b.x ^ y.x, R[k].b.y ^ y.y, R[k].b.z ^ y.z, R[k].b.w ^ y.w);
-                bool hit = inb && d < T;
+                bool hit = inb && d[k] < T;
                 if (WIN) {
                     const float du = cu - wu[k], dv = cv - wv[k];
                     hit = hit && !(du < -wr[k] || du > wr[k] || dv < -wr[k] || dv > wr[k]);
@@ -243,7 +249,7 @@ __global__ void __launch_bounds__(M_THREADS) k_shortlist(GreedyArgs a, int T)
                 if (m) {
                     if (hit) {
                         const int pos = cnt[k] + __popc(m & ((1u << lane) - 1u));
-                        if (pos < SVO_SHORT_CAP) *short_slot(a, ro + r0 + k, pos) = ((uint32_t)d << 16) | (uint32_t)(c0 + j);
+                        if (pos < SVO_SHORT_CAP) *short_slot(a, ro + r0 + k, pos) = ((uint32_t)d[k] << 16) | (uint32_t)(c0 + j);
                     }
                     cnt[k] += __popc(m);
                 }
@@ -596,17 +602,26 @@ __global__ void __launch_bounds__(M_THREADS) k_pairs(PairArgs p)
         for (int t = 0; t < 8; ++t) {
             const int j = 8 * lane + t;
             const uint4 x = tile[pt_unit(j, 0)], y = tile[pt_unit(j, 1)];
+            int d[PT_ROWS];
+            uint32_t key[PT_ROWS];
 #pragma unroll
             for (int k = 0; k < PT_ROWS; ++k) {
-                const int d = popc8(R[k].a.x ^ x.x, R[k].a.y ^ x.y, R[k].a.z ^ x.z, R[k].a.w ^ x.w,
-                                    R[k].b.x ^ y.x, R[k].b.y ^ y.y, R[k].b.z ^ y.z, R[k].b.w ^ y.w);
-                if (r0 + k < M) colmin[t] = min(colmin[t], (uint32_t)d * 65536u + (uint32_t)(r0 + k));
-                const uint32_t byte = (uint32_t)min(d, 255);
-                if (t < 4) lo[k] |= byte << (8 * t); else hi[k] |= byte << (8 * (t - 4));
-                if (d < T && live[k] && j < nc) {
-                    const int pos = atomicAdd(a.short_cnt + ro + r0 + k, 1);
-                    if (pos < SVO_SHORT_CAP) *short_slot(a, ro + r0 + k, pos) = ((uint32_t)d << 16) | (uint32_t)(c0 + j);
-                }
+                d[k] = popc8(R[k].a.x ^ x.x, R[k].a.y ^ x.y, R[k].a.z ^ x.z, R[k].a.w ^ x.w,
+                             R[k].b.x ^ y.x, R[k].b.y ^ y.y, R[k].b.z ^ y.z, R[k].b.w ^ y.w);
+                // rows past M are copies of row M-1 with a larger index: they can never win the (d, row) minimum
+                key[k] = (uint32_t)d[k] * 65536u + (uint32_t)(r0 + k);
+                const uint32_t byte = (uint32_t)min(d[k], 255);
+                if (t < 4) lo[k] = byte * (1u << (8 * t)) + lo[k]; else hi[k] = byte * (1u << (8 * (t - 4))) + hi[k];
+            }
+            const uint32_t kk = min(min(key[0], key[1]), min(key[2], key[3]));
+            colmin[t] = min(colmin[t], kk);
+            if (kk < (uint32_t)T << 16) {   // rare: some row of this lane's column is below the pass-1 threshold
+#pragma unroll
+                for (int k = 0; k < PT_ROWS; ++k)
+                    if (d[k] < T && live[k] && j < nc) {
+                        const int pos = atomicAdd(a.short_cnt + ro + r0 + k, 1);
+                        if (pos < SVO_SHORT_CAP) *short_slot(a, ro + r0 + k, pos) = ((uint32_t)d[k] << 16) | (uint32_t)(c0 + j);
+                    }
             }
         }
         if (store_ok) {

@@ -6,27 +6,78 @@
 // Its semantics are DEFINED by oracle/svo_oracle.c:svo_o_stereo_sparse (parity unpinned
 // against the reference: no such code or vectors exist there).
 //
-// One warp per left keypoint: lanes stride the right keypoints in ascending index, test the
-// row-band / octave / disparity-range predicate, and reduce (dist << 20 | iR) minima so the
-// first minimum wins; the same warp then evaluates the 11 SAD windows (121 px each, lanes
+// k_stereo_rows first bins the right keypoints by image row (every right keypoint is a candidate for
+// the rows [floor(y - r), ceil(y + r)], r = 2 * scale[octave]; CSR lists built with shared-memory
+// counters, one CTA per frame).  Then one warp per left keypoint: lanes stride the candidates of the
+// keypoint's row, test the octave / disparity-range predicate, and reduce (dist << 20 | iR) minima so
+// the first minimum wins (the key makes the result independent of the list order); the same warp then evaluates the 11 SAD windows (121 px each, lanes
 // over pixels, integer sums via redux.sync) and lane 0 fits the parabola.
 // A second kernel applies the 1.5*1.4*median SAD cut per frame.
 #include "svo_internal.cuh"
 
 #define ST_WARPS 8
 
+__global__ void __launch_bounds__(1024) k_stereo_rows(Bufs b, Geom g, int slot0, StereoArgs a)
+{
+    extern __shared__ int row_cnt[];       // [H + 1] counts, then exclusive offsets, then fill cursors
+    __shared__ int wsum[32];
+    const int f = blockIdx.x, sr = slot0 + 2 * f + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nr = min(b.nkp[sr], g.kp_cap), H = g.H;
+    const svo_keypoint *kr = b.kp + (size_t)sr * g.kp_cap;
+    int *off = a.row_off + (size_t)f * (H + 1);
+    uint16_t *list = a.row_list + (size_t)f * a.row_list_stride;
+    for (int i = tid; i <= H; i += 1024) row_cnt[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < nr; i += 1024) {
+        const svo_keypoint q = kr[i];
+        const float r = __fmul_rn(2.0f, g.lv[q.octave].scale);
+        const int maxr = min((int)ceilf(__fadd_rn(q.y, r)), H - 1), minr = max((int)floorf(__fsub_rn(q.y, r)), 0);
+        for (int y = minr; y <= maxr; ++y) atomicAdd(&row_cnt[y], 1);
+    }
+    __syncthreads();
+    // exclusive scan over H + 1 counters (each thread owns a contiguous chunk)
+    const int per = (H + 1 + 1023) / 1024;
+    const int i0 = min(tid * per, H + 1), i1 = min(i0 + per, H + 1);
+    int sum = 0;
+    for (int i = i0; i < i1; ++i) sum += row_cnt[i];
+    int inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += v;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    int base = inc - sum;
+    for (int w = 0; w < warp; ++w) base += wsum[w];
+    for (int i = i0; i < i1; ++i) { const int c = row_cnt[i]; row_cnt[i] = base; off[i] = base; base += c; }
+    __syncthreads();
+    for (int i = tid; i < nr; i += 1024) {
+        const svo_keypoint q = kr[i];
+        const float r = __fmul_rn(2.0f, g.lv[q.octave].scale);
+        const int maxr = min((int)ceilf(__fadd_rn(q.y, r)), H - 1), minr = max((int)floorf(__fsub_rn(q.y, r)), 0);
+        for (int y = minr; y <= maxr; ++y) {
+            const int pos = atomicAdd(&row_cnt[y], 1);
+            if (pos < a.row_list_stride) list[pos] = (uint16_t)i;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo(Bufs b, Geom g, int slot0, StereoArgs a)
 {
     const int f = blockIdx.y;
     const int sl = slot0 + 2 * f, sr = sl + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nl = min(b.nkp[sl], g.kp_cap), nr = min(b.nkp[sr], g.kp_cap);
+    const int nl = min(b.nkp[sl], g.kp_cap);
     const svo_keypoint *kl = b.kp + (size_t)sl * g.kp_cap, *kr = b.kp + (size_t)sr * g.kp_cap;
     const uint4 *dl = reinterpret_cast<const uint4 *>(b.desc + (size_t)sl * g.kp_cap * 32);
     const uint4 *dr = reinterpret_cast<const uint4 *>(b.desc + (size_t)sr * g.kp_cap * 32);
     const float bf = a.bf[f], base = a.baseline[f];
     const float minD = 0.f, maxD = __fdiv_rn(bf, base);
     const int rows = g.H;
+    const int *row_off = a.row_off + (size_t)f * (rows + 1);
+    const uint16_t *row_list = a.row_list + (size_t)f * a.row_list_stride;
     for (int iL = blockIdx.x * ST_WARPS + warp; iL < nl; iL += gridDim.x * ST_WARPS) {
         const size_t o = (size_t)f * a.stride + iL;
         const svo_keypoint kp = kl[iL];
@@ -40,13 +91,13 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo(Bufs b, Geom g, int sl
         uint32_t key = (100u << 20);  // TH_HIGH, bestIdxR = 0
         if (go) {
             const uint4 a0 = dl[2 * iL], a1 = dl[2 * iL + 1];
-            for (int iR = lane; iR < nr; iR += 32) {
-                const svo_keypoint q = kr[iR];
-                const float r = __fmul_rn(2.0f, g.lv[q.octave].scale);
-                const int maxr = (int)ceilf(__fadd_rn(q.y, r)), minr = (int)floorf(__fsub_rn(q.y, r));
-                if (row < minr || row > maxr) continue;
-                if (q.octave < levelL - 1 || q.octave > levelL + 1) continue;
-                if (q.x >= minU && q.x <= maxU) {
+            const int c0 = row_off[row], c1 = min(row_off[row + 1], a.row_list_stride);
+            for (int c = c0 + lane; c < c1; c += 32) {
+                const int iR = row_list[c];               // right keypoints whose row band holds `row`
+                const float qx = kr[iR].x;
+                const int qo = kr[iR].octave;
+                if (qo < levelL - 1 || qo > levelL + 1) continue;
+                if (qx >= minU && qx <= maxU) {
                     const uint4 x = dr[2 * iR], y = dr[2 * iR + 1];
                     const int d = __popc(a0.x ^ x.x) + __popc(a0.y ^ x.y) + __popc(a0.z ^ x.z) + __popc(a0.w ^ x.w) +
                                   __popc(a1.x ^ y.x) + __popc(a1.y ^ y.y) + __popc(a1.z ^ y.z) + __popc(a1.w ^ y.w);
@@ -181,7 +232,8 @@ void launch_stereo(const Bufs &b, const Geom &g, int slot0, int nframes, const S
     int quota = 0;
     for (int l = 0; l < g.nlevels; ++l) quota += g.lv[l].quota;
     dim3 grid((quota + 64 + ST_WARPS - 1) / ST_WARPS, nframes);
+    k_stereo_rows<<<nframes, 1024, (size_t)(g.H + 1) * sizeof(int), st>>>(b, g, slot0, a);
     k_stereo<<<grid, ST_WARPS * 32, 0, st>>>(b, g, slot0, a);
     k_stereo_median<<<nframes, 1024, 0, st>>>(b, g, slot0, a);
-    *launches += 2;
+    *launches += 3;
 }

@@ -29,6 +29,7 @@ struct FrameBufs {           // per-frame (stereo pair) device arrays
     int *res_rows, *res_off, *res_want;
     uint8_t *dmat; uint32_t *bf_key; int dmat_pitch; size_t dmat_frame_stride;   // fused pass-1 front (batch path)
     float *u_right, *depth; int *match_r, *sad, *n_stereo;
+    int *row_off; uint16_t *row_list; int row_list_stride;
     int *params;             // [4][nframes]: n_prev, n_map, bf bits, baseline bits
     // sync-only extras
     uint8_t *cols;           // [col_stride][32] caller-provided column descriptors
@@ -226,6 +227,12 @@ int alloc_frames(svo_ctx *ctx, FrameBufs &f, int nframes, int col_stride, int ro
     TRY(dalloc(ctx, &f.res_rows, R)); TRY(dalloc(ctx, &f.res_off, R)); TRY(dalloc(ctx, &f.res_want, R));
     TRY(dalloc(ctx, &f.u_right, C)); TRY(dalloc(ctx, &f.depth, C)); TRY(dalloc(ctx, &f.match_r, C));
     TRY(dalloc(ctx, &f.sad, C)); TRY(dalloc(ctx, &f.n_stereo, F));
+    {   // a right keypoint is a candidate for rows floor(y - r) .. ceil(y + r), r = 2 * scale[octave]
+        int band = 2 * (int)ceilf(2.f * ctx->g.lv[ctx->g.nlevels - 1].scale) + 2;
+        if (band > ctx->g.H) band = ctx->g.H;
+        f.row_list_stride = ctx->g.kp_cap * band;
+    }
+    TRY(dalloc(ctx, &f.row_off, F * (ctx->g.H + 1))); TRY(dalloc(ctx, &f.row_list, F * f.row_list_stride));
     TRY(dalloc(ctx, &f.params, 4 * F));
     f.cols = nullptr; f.win = f.cur_xy = f.row_xy = nullptr; f.boxes = nullptr; f.F = nullptr;
     f.dmat = nullptr; f.bf_key = nullptr; f.dmat_pitch = 0; f.dmat_frame_stride = 0;
@@ -473,6 +480,7 @@ int svo_stereo_sparse(svo_ctx *ctx, float bf, float baseline, float *u_right, fl
     StereoArgs a;
     a.u_right = s.u_right; a.depth = s.depth; a.match_r = s.match_r; a.sad = s.sad; a.n_stereo = s.n_stereo;
     a.stride = s.col_stride;
+    a.row_off = s.row_off; a.row_list = s.row_list; a.row_list_stride = s.row_list_stride;
     a.bf = reinterpret_cast<const float *>(s.params + 2); a.baseline = reinterpret_cast<const float *>(s.params + 3);
     launch_stereo(ctx->b, g, ctx->sync_slot0, 1, a, st, &ctx->launches);
     int n = 0;
@@ -663,6 +671,8 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
     sa.u_right = fb.u_right + (size_t)L.frame0 * K; sa.depth = fb.depth + (size_t)L.frame0 * K;
     sa.match_r = fb.match_r + (size_t)L.frame0 * K; sa.sad = fb.sad + (size_t)L.frame0 * K;
     sa.n_stereo = fb.n_stereo + L.frame0; sa.stride = K;
+    sa.row_off = fb.row_off + (size_t)L.frame0 * (g.H + 1); sa.row_list = fb.row_list + (size_t)L.frame0 * fb.row_list_stride;
+    sa.row_list_stride = fb.row_list_stride;
     sa.bf = reinterpret_cast<const float *>(fb.params + 2 * (size_t)FT + L.frame0);
     sa.baseline = reinterpret_cast<const float *>(fb.params + 3 * (size_t)FT + L.frame0);
     launch_stereo(b, g, L.slot0, n, sa, st, &ctx->launches);

@@ -106,6 +106,9 @@ struct StereoArgs {
     int *n_stereo;            // [frame]
     int stride;               // entries per frame in the arrays above
     const float *bf, *baseline;  // [frame]
+    int *row_off;             // [frame][H + 1] CSR offsets of the per-row candidate lists (right keypoints)
+    uint16_t *row_list;       // [frame][row_list_stride]
+    int row_list_stride;      // kp_cap * (rows one right keypoint can cover)
 };
 void launch_stereo(const Bufs &b, const Geom &g, int slot0, int nframes, const StereoArgs &a, cudaStream_t st,
                    long long *launches);

@@ -1,30 +1,43 @@
 #!/usr/bin/env python3
-"""Summarise one batch step (and one single-frame step) from an ncu launch list (--csv, gpu__time_duration.sum)."""
+"""Summarise one batch step (and one single-frame step) from an ncu launch list (--csv, gpu__time_duration.sum).
+A step starts at k_unpack (first kernel of svo_batch_submit) and ends before the next k_unpack."""
 import csv
 import sys
 
 
-def main(path, nframes):
+def steps(rows):
+    cur = None
+    for r in rows:
+        name = r["Kernel Name"].split("(")[0].replace("void ", "")
+        if name.startswith("k_unpack"):
+            if cur:
+                yield cur
+            cur = []
+        if cur is not None:
+            cur.append((name, r["Grid Size"], float(r["Metric Value"].replace(",", "")) / 1000.0))
+    if cur:
+        yield cur
+
+
+def nframes(step):
+    for n, g, _ in step:
+        if n.startswith("k_stereo") and not n.startswith("k_stereo_median"):
+            return int(g.strip("()").split(",")[1])
+    return 0
+
+
+def main(path, want):
     lines = [l for l in open(path) if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
-    names = [r["Kernel Name"] for r in rows]
-    for want in (nframes, 1):
-        last = None
-        for i, r in enumerate(rows):
-            g = r["Grid Size"].strip("()").split(",")
-            if names[i].startswith("k_bf(") and int(g[1]) == want:
-                last = i
-        if last is None:
+    allsteps = list(steps(rows))
+    for nf in (want, 1):
+        sel = [s for s in allsteps if nframes(s) == nf and any(n.startswith("k_pairs") or n.startswith("k_bf") for n, _, _ in s)]
+        if not sel:
             continue
-        start = max(i for i in range(1, last) if names[i].startswith("k_resize") and not names[i - 1].startswith("k_resize"))
-        tot = 0.0
-        out = []
-        for r in rows[start:start + 25]:
-            t = float(r["Metric Value"].replace(",", "")) / 1000.0
-            tot += t
-            out.append((r["Kernel Name"].split("(")[0], r["Grid Size"], t))
-        print("---- step with %d frame(s): %d launches, %.1f us total, %.1f us/frame" % (want, len(out), tot, tot / want))
-        for n, g, t in out:
+        st = sel[-1]
+        tot = sum(t for _, _, t in st)
+        print("---- step with %d frame(s): %d launches, %.1f us total, %.1f us/frame" % (nf, len(st), tot, tot / nf))
+        for n, g, t in st:
             print("%-18s grid=%-16s %9.1f us  %5.1f%%" % (n, g, t, 100 * t / tot))
 
 
