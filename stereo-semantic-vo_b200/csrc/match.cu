@@ -30,7 +30,22 @@
 __device__ __forceinline__ int unit_of(int j, int h) { return 2 * j + (h ^ ((j >> 2) & 1)); }
 
 __device__ __forceinline__ int set_count(const MatchSet &s, int f) { return s.count ? min(s.count[(size_t)f * s.count_stride], s.stride_rows) : s.fixed_count; }
-__device__ __forceinline__ const uint8_t *set_desc(const MatchSet &s, int f) { return s.desc + (size_t)f * s.desc_stride * 32; }
+__device__ __forceinline__ const uint8_t *set_desc(const MatchSet &s, int f)
+{
+    if (s.tab) return *reinterpret_cast<const uint8_t *const *>(reinterpret_cast<const char *>(s.tab) + (size_t)f * sizeof(FramePtrs));
+    return s.desc + (size_t)f * s.desc_stride * 32;
+}
+// per-frame row_live / map_prev_row arrays (NULL = all live / no link)
+__device__ __forceinline__ const uint8_t *live_of(const GreedyArgs &a, int f)
+{
+    if (a.fp) return a.use_live ? a.fp[f].prev_live : nullptr;
+    return a.row_live ? a.row_live + (size_t)f * a.rows.stride_rows : nullptr;
+}
+__device__ __forceinline__ const int *map_prev_of(const GreedyArgs &a, int f)
+{
+    if (a.fp) return a.use_map_prev ? a.fp[f].map_prev_row : nullptr;
+    return a.map_prev_row ? a.map_prev_row + (size_t)f * a.rows.stride_rows : nullptr;
+}
 
 // stage columns [c0, c0+nc) of a descriptor set into the swizzled shared tile
 __device__ __forceinline__ void load_tile(uint4 *tile, const uint8_t *desc, int c0, int nc)
@@ -204,6 +219,7 @@ __global__ void __launch_bounds__(M_THREADS) k_shortlist(GreedyArgs a, int T)
     const uint8_t *rd = set_desc(a.rows, f), *cd = set_desc(a.cols, f);
     const float *cxy = WIN ? a.cur_xy + (size_t)f * a.cols.stride_rows * 2 : nullptr;
     const size_t ro = (size_t)f * a.rows.stride_rows;
+    const uint8_t *rl = live_of(a, f);
     Row R[SL_ROWS_PER_WARP];
     int cnt[SL_ROWS_PER_WARP];
     bool live[SL_ROWS_PER_WARP];
@@ -212,7 +228,7 @@ __global__ void __launch_bounds__(M_THREADS) k_shortlist(GreedyArgs a, int T)
     for (int k = 0; k < SL_ROWS_PER_WARP; ++k) {
         const int r = r0 + k;
         cnt[k] = 0;
-        live[k] = r < M && (!a.row_live || a.row_live[ro + r]);
+        live[k] = r < M && (!rl || rl[r]);
         R[k] = load_row(rd, min(r, M - 1));
         wu[k] = wv[k] = wr[k] = 0.f;
         if (WIN && r < M) { wu[k] = a.win_uvr[(ro + r) * 3]; wv[k] = a.win_uvr[(ro + r) * 3 + 1]; wr[k] = a.win_uvr[(ro + r) * 3 + 2]; }
@@ -327,12 +343,13 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_c
     }
     if (tid == 0) s_novf = 0;
 
+    const int *mpr = map_prev_of(a, f);
     auto row_size = [&](int r) -> int {   // 0 = cannot claim, else min(cnt, CAP+1)
         if (r >= M) return 0;
         const int c = a.short_cnt[ro + r];
         if (c == 0) return 0;
-        if (a.map_prev_row) {
-            const int pr = a.map_prev_row[ro + r];
+        if (mpr) {
+            const int pr = mpr[r];
             if (pr >= 0 && a.prev_row_claimed[(size_t)f * a.prev_stride + pr]) return 0;
         }
         return min(c, SVO_SHORT_CAP + 1);
@@ -500,9 +517,11 @@ __global__ void __launch_bounds__(M_THREADS) k_scores(GreedyArgs a)
     const size_t ro = (size_t)f * a.rows.stride_rows, co = (size_t)f * a.cols.stride_rows;
     const uint8_t *rd = set_desc(a.rows, f), *cd = set_desc(a.cols, f);
     const float *cxy = a.cur_xy ? a.cur_xy + co * 2 : nullptr;
-    bool live = r < M && (!a.row_live || a.row_live[ro + r]);
-    if (live && a.map_prev_row) {
-        const int pr = a.map_prev_row[ro + r];
+    const uint8_t *rl = live_of(a, f);
+    const int *mpr = map_prev_of(a, f);
+    bool live = r < M && (!rl || rl[r]);
+    if (live && mpr) {
+        const int pr = mpr[r];
         if (pr >= 0 && a.prev_row_claimed[(size_t)f * a.prev_stride + pr]) live = false;
     }
     const Row R = load_row(rd, min(r, M - 1));
@@ -569,6 +588,7 @@ __global__ void __launch_bounds__(M_THREADS) k_pairs(PairArgs p)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint8_t *rd = set_desc(a.rows, f), *cd = set_desc(a.cols, f);
     const size_t ro = (size_t)f * a.rows.stride_rows;
+    const uint8_t *rl = live_of(a, f);
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(cd) + (size_t)c0 * 2;
         for (int i = tid; i < PT_COLS * 2; i += M_THREADS)
@@ -593,7 +613,7 @@ __global__ void __launch_bounds__(M_THREADS) k_pairs(PairArgs p)
         for (int k = 0; k < PT_ROWS; ++k) {
             const int r = min(r0 + k, M - 1);
             R[k] = load_row(rd, r);
-            live[k] = r0 + k < M && (!a.row_live || a.row_live[ro + r]);
+            live[k] = r0 + k < M && (!rl || rl[r]);
         }
         uint32_t lo[PT_ROWS], hi[PT_ROWS];
 #pragma unroll
@@ -687,10 +707,11 @@ __global__ void __launch_bounds__(M_THREADS) k_scores_m(PairArgs p)
     const uint8_t *dm = p.dmat + (size_t)f * p.dmat_frame_stride;
     const int rb = a.row_base + (a.row_base_arr ? a.row_base_arr[f] : 0);
     const int *tl = sm_time + lane * (W + 1);
+    const uint8_t *rl = live_of(a, f);
     for (int k = 0; k < SM_ROWS_PER_WARP; ++k) {
         const int r = (blockIdx.x * M_WARPS + warp) * SM_ROWS_PER_WARP + k;
         if (r >= M) break;
-        if (a.row_live && !a.row_live[ro + r]) continue;
+        if (rl && !rl[r]) continue;
         const int g = rb + r;
         const uint4 *src = reinterpret_cast<const uint4 *>(dm + (size_t)r * p.dmat_pitch + lane * W);
         int lb = 256, ls = 256, li = -1;

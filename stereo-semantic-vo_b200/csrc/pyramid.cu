@@ -43,10 +43,11 @@ __global__ void __launch_bounds__(256) k_resize(Bufs b, Geom g, int l, int slot0
     *reinterpret_cast<uint32_t *>(dst + (size_t)y * d.pitch + x) = out;
 }
 
-// Level 0 arrives as one contiguous H2D copy (rows `stride` bytes apart, any alignment); this
-// repacks it into the 16-byte-pitched level-0 layout.  One thread per 16 output bytes.
-__global__ void __launch_bounds__(256) k_unpack(Bufs b, Geom g, int slot0, const uint8_t *__restrict__ stage,
-                                                size_t stage_img_bytes, const int *__restrict__ strides)
+// Level 0 is read where it lies in device memory (the caller's device buffer, or the lane's landing zone
+// for host inputs; rows `stride` bytes apart, any alignment) and repacked into the 16-byte-pitched level-0
+// layout.  One thread per 16 output bytes.
+__global__ void __launch_bounds__(256) k_unpack(Bufs b, Geom g, int slot0, const FramePtrs *__restrict__ fp,
+                                                const int *__restrict__ strides)
 {
     const LevelGeom &L = g.lv[0];
     const int per_row = L.pitch >> 4;
@@ -55,7 +56,8 @@ __global__ void __launch_bounds__(256) k_unpack(Bufs b, Geom g, int slot0, const
     const int y = i / per_row, x = (i - y * per_row) << 4;
     const int stride = strides[blockIdx.y];
     if (stride <= 0) return;                      // this image was uploaded with a 2-D copy
-    const uint8_t *src = stage + (size_t)blockIdx.y * stage_img_bytes + (size_t)y * stride + x;
+    const FramePtrs &F = fp[blockIdx.y >> 1];
+    const uint8_t *src = ((blockIdx.y & 1) ? F.right : F.left) + (size_t)y * stride + x;
     uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int k = 0; k < 16; ++k)
@@ -64,12 +66,12 @@ __global__ void __launch_bounds__(256) k_unpack(Bufs b, Geom g, int slot0, const
         make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-void launch_unpack(const Bufs &b, const Geom &g, int slot0, int nimg, const uint8_t *stage, size_t stage_img_bytes,
+void launch_unpack(const Bufs &b, const Geom &g, int slot0, int nimg, const FramePtrs *fp,
                    const int *strides, cudaStream_t st, long long *launches)
 {
     const int n = (g.lv[0].pitch >> 4) * g.lv[0].h;
     dim3 grid((n + 255) / 256, nimg);
-    k_unpack<<<grid, 256, 0, st>>>(b, g, slot0, stage, stage_img_bytes, strides);
+    k_unpack<<<grid, 256, 0, st>>>(b, g, slot0, fp, strides);
     ++*launches;
 }
 

@@ -8,6 +8,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -54,8 +55,10 @@ struct Lane {
     bool busy;
     HostArena h;
     std::vector<svo_frame_in> in;
-    uint8_t *d_stage;          // contiguous landing zone for the images of a batch (2 per frame)
-    int *d_strides, *h_strides; // per image: row stride in the landing zone, 0 = uploaded with a 2-D copy
+    uint8_t *d_stage;          // landing zone for the host inputs of a batch (images, descriptors, flags)
+    size_t stage_cap;
+    FramePtrs *d_fp, *h_fp;    // per-frame input pointers (device table + pinned staging)
+    int *d_strides, *h_strides; // per image: row stride at its source, 0 = uploaded with a 2-D copy
 };
 
 }  // namespace
@@ -286,9 +289,20 @@ int upload_image(svo_ctx *ctx, int slot, const uint8_t *img, int stride, cudaStr
 MatchSet make_set(const uint8_t *desc, const int *count, int count_stride, int stride_rows, int fixed, int desc_stride = -1)
 {
     MatchSet s; s.desc = desc; s.count = count; s.count_stride = count_stride; s.stride_rows = stride_rows; s.fixed_count = fixed;
+    s.tab = nullptr;
     s.desc_stride = desc_stride < 0 ? stride_rows : desc_stride;
     return s;
 }
+
+// true when kernels can read `p` in place (device or managed memory)
+bool device_readable(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+struct Seg { const uint8_t *src; size_t bytes; const void **field; bool need16; };
 
 }  // namespace
 
@@ -395,7 +409,9 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
         TRY(halloc(ctx, &h.p1_row_claimed, B * R)); TRY(halloc(ctx, &h.p2_row_claimed, B * R));
         TRY(halloc(ctx, &h.claim_row, B * K));
         TRY(halloc(ctx, &h.params, 4 * B));
-        TRY(dalloc(ctx, &l.d_stage, I * ctx->stage_img_bytes));
+        l.stage_cap = I * ctx->stage_img_bytes + B * (R * 32 * 2 + R * 5) + (6 * B + 8) * 512;
+        TRY(dalloc(ctx, &l.d_stage, l.stage_cap));
+        TRY(dalloc(ctx, &l.d_fp, B)); TRY(halloc(ctx, &l.h_fp, B));
         TRY(dalloc(ctx, &l.d_strides, I)); TRY(halloc(ctx, &l.h_strides, I));
     }
     CU(cudaDeviceSynchronize());
@@ -624,43 +640,68 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
     L.in.assign(frames, frames + n);
     L.nframes = n;
     if (ev) cudaEventRecord(ev[0], st);
-    // ---- H2D
+    // ---- inputs: device-resident buffers are read in place; host buffers are gathered into the lane's
+    // landing zone with one H2D copy per maximal run of adjacent source ranges (a strided 2-D copy of
+    // 1241-byte rows, or 32 separate 466 kB copies, run at a fraction of PCIe speed); kernels reach every
+    // input through the per-frame pointer table.
     int *hp = L.h.params;
+    std::vector<Seg> segs;
+    segs.reserve(6 * (size_t)n);
+    auto place = [&](const void *p, size_t bytes, const void **field, bool need16) {
+        *field = nullptr;
+        if (!p || !bytes) return;
+        if (device_readable(p) && (!need16 || ((uintptr_t)p & 15) == 0)) { *field = p; return; }
+        segs.push_back(Seg{(const uint8_t *)p, bytes, field, need16});
+    };
     for (int i = 0; i < n; ++i) {
         const svo_frame_in &f = frames[i];
-        const int fi = L.frame0 + i;
-        // one contiguous copy per image (a strided 2-D H2D copy of 1241-byte rows runs at a fraction of
-        // PCIe speed); k_unpack re-pitches on the device.  Oversized strides fall back to the 2-D copy.
+        FramePtrs &P = L.h_fp[i];
         const size_t img_bytes = (size_t)f.stride * (g.H - 1) + g.W;
         const uint8_t *srcs[2] = {f.left, f.right};
+        const void **fld[2] = {(const void **)&P.left, (const void **)&P.right};
         for (int s = 0; s < 2; ++s) {
-            if (img_bytes <= ctx->stage_img_bytes) {
-                CU(cudaMemcpyAsync(L.d_stage + (size_t)(2 * i + s) * ctx->stage_img_bytes, srcs[s], img_bytes, cudaMemcpyDefault, st));
+            if (img_bytes <= ctx->stage_img_bytes || device_readable(srcs[s])) {
+                place(srcs[s], img_bytes, fld[s], false);
                 L.h_strides[2 * i + s] = f.stride;
-            } else {
+            } else {   // oversized stride: 2-D copy straight into the level-0 slot
+                *fld[s] = nullptr;
                 TRY(upload_image(ctx, L.slot0 + 2 * i + s, srcs[s], f.stride, st));
                 L.h_strides[2 * i + s] = 0;
             }
         }
-        if (f.n_prev) {
-            CU(cudaMemcpyAsync(fb.prev + (size_t)fi * R * 32, f.prev_desc, (size_t)f.n_prev * 32, cudaMemcpyDefault, st));
-            if (f.prev_live) CU(cudaMemcpyAsync(fb.prev_live + (size_t)fi * R, f.prev_live, (size_t)f.n_prev, cudaMemcpyDefault, st));
-            else CU(cudaMemsetAsync(fb.prev_live + (size_t)fi * R, 1, (size_t)f.n_prev, st));
-        }
-        if (f.n_map) {
-            CU(cudaMemcpyAsync(fb.map + (size_t)fi * R * 32, f.map_desc, (size_t)f.n_map * 32, cudaMemcpyDefault, st));
-            if (f.map_prev_row && f.n_prev) CU(cudaMemcpyAsync(fb.map_prev + (size_t)fi * R, f.map_prev_row, sizeof(int) * f.n_map, cudaMemcpyDefault, st));
-            else CU(cudaMemsetAsync(fb.map_prev + (size_t)fi * R, 0xff, sizeof(int) * f.n_map, st));
-        }
+        place(f.n_prev ? f.prev_desc : nullptr, (size_t)f.n_prev * 32, (const void **)&P.prev, true);
+        place(f.n_prev ? f.prev_live : nullptr, (size_t)f.n_prev, (const void **)&P.prev_live, false);
+        place(f.n_map ? f.map_desc : nullptr, (size_t)f.n_map * 32, (const void **)&P.map, true);
+        place((f.n_map && f.n_prev) ? f.map_prev_row : nullptr, sizeof(int) * (size_t)f.n_map, (const void **)&P.map_prev_row, true);
         hp[i] = f.n_prev; hp[B + i] = f.n_map;
         memcpy(&hp[2 * B + i], &f.bf, 4); memcpy(&hp[3 * B + i], &f.baseline, 4);
     }
+    std::sort(segs.begin(), segs.end(), [](const Seg &x, const Seg &y) { return x.src < y.src; });
+    size_t cursor = 0;
+    for (size_t i = 0; i < segs.size();) {
+        // a run: source ranges that touch or overlap (never bridges a gap: only the caller's bytes are read)
+        const uint8_t *run_src = segs[i].src, *run_end = run_src + segs[i].bytes;
+        size_t j = i + 1;
+        const bool solo = segs[i].need16 && ((uintptr_t)run_src & 15);      // misaligned descriptors: realigned, alone
+        while (!solo && j < segs.size() && segs[j].src <= run_end && !(segs[j].need16 && ((uintptr_t)segs[j].src & 15))) {
+            run_end = std::max(run_end, segs[j].src + segs[j].bytes);
+            ++j;
+        }
+        const size_t dst = ((cursor + 255) & ~(size_t)255) + (solo ? 0 : ((uintptr_t)run_src & 255));
+        const size_t len = (size_t)(run_end - run_src);
+        if (dst + len > L.stage_cap) return fail(ctx, SVO_E_CAPACITY, "svo_batch_submit: inputs exceed the staging capacity");
+        CU(cudaMemcpyAsync(L.d_stage + dst, run_src, len, cudaMemcpyDefault, st));
+        for (size_t k = i; k < j; ++k) *segs[k].field = L.d_stage + dst + (segs[k].src - run_src);
+        cursor = dst + len;
+        i = j;
+    }
+    CU(cudaMemcpyAsync(L.d_fp, L.h_fp, sizeof(FramePtrs) * n, cudaMemcpyHostToDevice, st));
     // params live as [4][nframes_total] on the device; this lane owns columns frame0..frame0+B
     const int FT = fb.nframes;
     for (int k = 0; k < 4; ++k)
         CU(cudaMemcpyAsync(fb.params + (size_t)k * FT + L.frame0, hp + (size_t)k * B, sizeof(int) * n, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(L.d_strides, L.h_strides, sizeof(int) * 2 * n, cudaMemcpyHostToDevice, st));
-    launch_unpack(b, g, L.slot0, 2 * n, L.d_stage, ctx->stage_img_bytes, L.d_strides, st, &ctx->launches);
+    launch_unpack(b, g, L.slot0, 2 * n, L.d_fp, L.d_strides, st, &ctx->launches);
     CU(cudaMemsetAsync(fb.claimed + (size_t)L.frame0 * K, 0, (size_t)n * K, st));
     CU(cudaMemsetAsync(fb.claim_row + (size_t)L.frame0 * K, 0xff, sizeof(int) * (size_t)n * K, st));
     // ---- extraction of 2n images
@@ -693,12 +734,14 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
     ga.res_want = fb.res_want + (size_t)L.frame0 * R;
     if (any_prev) {
         BfArgs ba;
-        ba.q = cur; ba.t = make_set(fb.prev + (size_t)L.frame0 * R * 32, d_nprev, 1, R, 0);
+        MatchSet prev_set = make_set(nullptr, d_nprev, 1, R, 0);
+        prev_set.tab = reinterpret_cast<const uint8_t *const *>(&L.d_fp->prev);
+        ba.q = cur; ba.t = prev_set;
         ba.idx = fb.bf_idx + (size_t)L.frame0 * K; ba.dist = fb.bf_dist + (size_t)L.frame0 * K;
         ba.keep = fb.bf_keep + (size_t)L.frame0 * K; ba.min_dist = fb.min_dist + L.frame0;
-        ga.rows = make_set(fb.prev + (size_t)L.frame0 * R * 32, d_nprev, 1, R, 0);
+        ga.rows = prev_set;
         ga.mode = SVO_GREEDY_PASS1; ga.row_base = 0; ga.row_base_arr = nullptr;
-        ga.row_live = fb.prev_live + (size_t)L.frame0 * R;
+        ga.fp = L.d_fp; ga.use_live = 1; ga.use_map_prev = 0;
         ga.best_idx = fb.p1_best_idx + (size_t)L.frame0 * R; ga.best = fb.p1_best + (size_t)L.frame0 * R;
         ga.second = fb.p1_second + (size_t)L.frame0 * R;
         ga.row_claimed = fb.p1_row_claimed + (size_t)L.frame0 * R; ga.row_bad = nullptr;
@@ -715,10 +758,10 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
         }
     }
     if (any_map) {
-        ga.rows = make_set(fb.map + (size_t)L.frame0 * R * 32, d_nmap, 1, R, 0);
+        ga.rows = make_set(nullptr, d_nmap, 1, R, 0);
+        ga.rows.tab = reinterpret_cast<const uint8_t *const *>(&L.d_fp->map);
         ga.mode = SVO_GREEDY_PASS2; ga.row_base = 0; ga.row_base_arr = d_nprev;
-        ga.row_live = nullptr;
-        ga.map_prev_row = any_prev ? fb.map_prev + (size_t)L.frame0 * R : nullptr;
+        ga.fp = L.d_fp; ga.use_live = 0; ga.use_map_prev = any_prev ? 1 : 0;
         ga.prev_row_claimed = fb.p1_row_claimed + (size_t)L.frame0 * R; ga.prev_stride = R;
         ga.best_idx = nullptr; ga.best = nullptr; ga.second = nullptr;
         ga.row_claimed = fb.p2_row_claimed + (size_t)L.frame0 * R; ga.row_bad = nullptr;

@@ -80,8 +80,18 @@ __host__ __device__ inline int unpack_x(uint32_t v) { return (int)(v & 0xfffu); 
 __host__ __device__ inline int unpack_y(uint32_t v) { return (int)((v >> 12) & 0xfffu); }
 __host__ __device__ inline int unpack_s(uint32_t v) { return (int)(v >> 24); }
 
+// Per-frame input pointers of a batch (device table).  Inputs that already live in device memory are read in
+// place; host inputs are gathered into the lane's landing zone with as few H2D copies as their layout allows.
+struct FramePtrs {
+    const uint8_t *left, *right;   // gray images (rows `stride` bytes apart)
+    const uint8_t *prev;           // n_prev x 32, 16-byte aligned
+    const uint8_t *prev_live;      // n_prev or NULL (all live)
+    const uint8_t *map;            // n_map x 32, 16-byte aligned
+    const int *map_prev_row;       // n_map or NULL
+};
+
 // ---- stage launchers (each enqueues on `st` for images [slot0, slot0 + nimg)) ----
-void launch_unpack(const Bufs &b, const Geom &g, int slot0, int nimg, const uint8_t *stage, size_t stage_img_bytes,
+void launch_unpack(const Bufs &b, const Geom &g, int slot0, int nimg, const FramePtrs *fp,
                    const int *strides, cudaStream_t st, long long *launches);
 void launch_pyramid(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches);
 void launch_fast(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches);
@@ -121,6 +131,7 @@ struct MatchSet {            // one descriptor set per frame, fixed stride
     int stride_rows;         // rows per frame in the per-row/per-column side arrays
     int desc_stride;         // descriptor rows between consecutive frames' blocks
     int fixed_count;
+    const uint8_t *const *tab;   // optional per-frame descriptor pointers (a field of FramePtrs[frame]); overrides desc
 };
 struct GreedyArgs {
     MatchSet rows, cols;
@@ -128,6 +139,8 @@ struct GreedyArgs {
     const int *row_base_arr;      // [frame] or NULL: per-frame row base added to row_base
     const uint8_t *row_live;      // [frame][rows.stride_rows] or NULL
     const int *map_prev_row;      // [frame][rows.stride_rows] or NULL (pass 2)
+    const FramePtrs *fp;          // batch path: row_live / map_prev_row come from fp[frame] (use_live / use_map_prev)
+    int use_live, use_map_prev;
     const uint8_t *prev_row_claimed;  // [frame][prev stride] (pass 2, with map_prev_row)
     int prev_stride;
     uint8_t *claimed;             // [frame][cols.stride_rows] in/out
