@@ -90,75 +90,94 @@ __device__ __forceinline__ int reflect101(int i, int n)
     return i;
 }
 
-__device__ __forceinline__ float byte_to_float(uint32_t word, int sel)
+// bytes {b, 00, 00, 4B} = 2^23 + b as a float; subtracting 2^23 is exact
+__device__ __forceinline__ float byte_magic(uint32_t word, int sel)
 {
-    // bytes {b, 00, 00, 4B} = 2^23 + b as a float; subtracting 2^23 is exact
-    return __fsub_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440 | sel)), 8388608.f);
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440 | sel));
 }
 
+// Products and tap-free sums are packed (FMUL2 / FADD2, two pixels per instruction; every lane of a packed op is
+// rounded separately, exactly like the scalar _rn ops).  An add that consumes a product stays SCALAR: ptxas
+// (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false, which would change bits.
+__device__ __forceinline__ float2 add_prod(float2 acc, float2 prod)
+{
+    return make_float2(__fadd_rn(acc.x, prod.x), __fadd_rn(acc.y, prod.y));
+}
 __global__ void __launch_bounds__(BLUR_THREADS) k_blur(Bufs b, Geom g, int slot0)
 {
     int blk = blockIdx.x, l = 0;
     while (l + 1 < g.nlevels && blk >= g.lv[l + 1].blur_tile_off) ++l;
-    const LevelGeom &L = g.lv[l];
-    blk -= L.blur_tile_off;
-    const int quads = (L.w + 3) >> 2;                 // blur_tiles_x holds this too
+    const int Lw = g.lv[l].w, Lh = g.lv[l].h, sp = g.lv[l].pitch, Loff = g.lv[l].off;
+    blk -= g.lv[l].blur_tile_off;
+    const int quads = (Lw + 3) >> 2;
     const int item = blk * BLUR_THREADS + threadIdx.x;
     const int strip = item / quads, cg = item - strip * quads;
     const int y0 = strip * BLUR_ROWS, x0 = cg << 2;
-    if (y0 >= L.h) return;
+    if (y0 >= Lh) return;
     const int slot = slot0 + blockIdx.y;
-    const uint8_t *img = b.pyr + (size_t)slot * g.pyr_bytes + L.off;
-    uint8_t *out = b.blur + (size_t)slot * g.pyr_bytes + L.off;
-    const int sp = L.pitch;
-    float gk[7];
+    const uint8_t *__restrict__ img = b.pyr + (size_t)slot * g.pyr_bytes + Loff;
+    uint8_t *__restrict__ out = b.blur + (size_t)slot * g.pyr_bytes + Loff;
+    float2 gk[7];
 #pragma unroll
-    for (int k = 0; k < 7; ++k) gk[k] = __uint_as_float(c_gauss[k]);
-    const bool interior = x0 >= 4 && x0 + 6 < L.w;   // bytes x0-3 .. x0+6 all inside the row
-    float win[7][4];
+    for (int k = 0; k < 7; ++k) gk[k] = make_float2(__uint_as_float(c_gauss[k]), __uint_as_float(c_gauss[k]));
+    const float2 two23 = make_float2(-8388608.f, -8388608.f), rnd = make_float2(12582912.f, 12582912.f);
+    const bool interior = x0 >= 4 && x0 + 6 < Lw;   // bytes x0-3 .. x0+6 all inside the row
+    float2 win[7][2];                               // horizontal sums of the last 7 rows: pixels (0,1) and (2,3)
 #pragma unroll
-    for (int k = 0; k < 7; ++k)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) win[k][j] = 0.f;
-    const int rows = min(BLUR_ROWS, L.h - y0);
+    for (int k = 0; k < 7; ++k) win[k][0] = win[k][1] = make_float2(0.f, 0.f);
+    const int rows = min(BLUR_ROWS, Lh - y0);
+    // the three words of the NEXT window row are fetched one iteration ahead (software pipelining: the
+    // kernel is otherwise bound by the latency of these loads)
+    uint32_t n0 = 0, n1 = 0, n2 = 0;
+    if (interior) {
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(img + (size_t)reflect101(y0 - 3, Lh) * sp + x0 - 4);
+        n0 = w[0]; n1 = w[1]; n2 = w[2];
+    }
     for (int r0 = 0; r0 < rows + 6; r0 += 7) {
 #pragma unroll
         for (int k = 0; k < 7; ++k) {
             const int r = r0 + k;                       // window row r <-> image row y0 + r - 3
             if (r < rows + 6) {
-                const int yy = reflect101(y0 + r - 3, L.h);
-                const uint8_t *row = img + (size_t)yy * sp;
-                float f[10];
+                float m[10];                            // 2^23 + pixel x0-3+j
                 if (interior) {
-                    const uint32_t *w = reinterpret_cast<const uint32_t *>(row + x0 - 4);
-                    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-                    f[0] = byte_to_float(w0, 1); f[1] = byte_to_float(w0, 2); f[2] = byte_to_float(w0, 3);
-                    f[3] = byte_to_float(w1, 0); f[4] = byte_to_float(w1, 1); f[5] = byte_to_float(w1, 2); f[6] = byte_to_float(w1, 3);
-                    f[7] = byte_to_float(w2, 0); f[8] = byte_to_float(w2, 1); f[9] = byte_to_float(w2, 2);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 10; ++j) f[j] = (float)row[reflect101(x0 - 3 + j, L.w)];
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float acc = __fmul_rn(gk[0], f[j]);
-#pragma unroll
-                    for (int t = 1; t < 7; ++t) acc = __fadd_rn(acc, __fmul_rn(gk[t], f[j + t]));
-                    win[k][j] = acc;
-                }
-                if (r >= 6) {                           // rows r-6 .. r are in the window: emit image row y0 + r - 6
-                    uint32_t packed = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float acc = __fmul_rn(gk[3], win[(k + 4) % 7][j]);
-                        acc = __fadd_rn(acc, __fmul_rn(gk[4], __fadd_rn(win[(k + 5) % 7][j], win[(k + 3) % 7][j])));
-                        acc = __fadd_rn(acc, __fmul_rn(gk[5], __fadd_rn(win[(k + 6) % 7][j], win[(k + 2) % 7][j])));
-                        acc = __fadd_rn(acc, __fmul_rn(gk[6], __fadd_rn(win[k][j], win[(k + 1) % 7][j])));
-                        int v = __float2int_rn(acc);
-                        v = max(0, min(255, v));
-                        packed |= (uint32_t)v << (8 * j);
+                    const uint32_t w0 = n0, w1 = n1, w2 = n2;
+                    if (r + 1 < rows + 6) {
+                        const uint32_t *w = reinterpret_cast<const uint32_t *>(img + (size_t)reflect101(y0 + r - 2, Lh) * sp + x0 - 4);
+                        n0 = w[0]; n1 = w[1]; n2 = w[2];
                     }
-                    *reinterpret_cast<uint32_t *>(out + (size_t)(y0 + r - 6) * sp + x0) = packed;
+                    m[0] = byte_magic(w0, 1); m[1] = byte_magic(w0, 2); m[2] = byte_magic(w0, 3);
+                    m[3] = byte_magic(w1, 0); m[4] = byte_magic(w1, 1); m[5] = byte_magic(w1, 2); m[6] = byte_magic(w1, 3);
+                    m[7] = byte_magic(w2, 0); m[8] = byte_magic(w2, 1); m[9] = byte_magic(w2, 2);
+                } else {
+                    const uint8_t *row = img + (size_t)reflect101(y0 + r - 3, Lh) * sp;
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) m[j] = __uint_as_float(0x4B000000u | row[reflect101(x0 - 3 + j, Lw)]);
+                }
+                float2 P[9];                            // P[t] = pixels (x0-3+t, x0-2+t)
+#pragma unroll
+                for (int t = 0; t < 9; ++t) P[t] = __fadd2_rn(make_float2(m[t], m[t + 1]), two23);
+                float2 a01 = __fmul2_rn(gk[0], P[0]), a23 = __fmul2_rn(gk[0], P[2]);
+#pragma unroll
+                for (int t = 1; t < 7; ++t) {
+                    a01 = add_prod(a01, __fmul2_rn(gk[t], P[t]));
+                    a23 = add_prod(a23, __fmul2_rn(gk[t], P[t + 2]));
+                }
+                win[k][0] = a01; win[k][1] = a23;
+                if (r >= 6) {                           // rows r-6 .. r are in the window: emit image row y0 + r - 6
+                    float2 o[2];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        float2 acc = __fmul2_rn(gk[3], win[(k + 4) % 7][j]);
+                        acc = add_prod(acc, __fmul2_rn(gk[4], __fadd2_rn(win[(k + 5) % 7][j], win[(k + 3) % 7][j])));
+                        acc = add_prod(acc, __fmul2_rn(gk[5], __fadd2_rn(win[(k + 6) % 7][j], win[(k + 2) % 7][j])));
+                        acc = add_prod(acc, __fmul2_rn(gk[6], __fadd2_rn(win[k][j], win[(k + 1) % 7][j])));
+                        // round to nearest even by adding 1.5 * 2^23: the low mantissa byte is the pixel
+                        // (0 <= acc <= 255 * (sum of taps) < 255.5, so no clamp is needed)
+                        o[j] = __fadd2_rn(acc, rnd);
+                    }
+                    const uint32_t p01 = __byte_perm(__float_as_uint(o[0].x), __float_as_uint(o[0].y), 0x0040);
+                    const uint32_t p23 = __byte_perm(__float_as_uint(o[1].x), __float_as_uint(o[1].y), 0x0040);
+                    *reinterpret_cast<uint32_t *>(out + (size_t)(y0 + r - 6) * sp + x0) = __byte_perm(p01, p23, 0x5410);
                 }
             }
         }

@@ -75,6 +75,16 @@ __device__ __forceinline__ int popc8(uint32_t x0, uint32_t x1, uint32_t x2, uint
     const uint32_t s2 = x3 ^ x4 ^ x5, c2 = maj3(x3, x4, x5);
     return __popc(s1) + __popc(s2) + __popc(x6) + __popc(x7) + 2 * (__popc(c1) + __popc(c2));
 }
+// Three carry-save adders: 5 POPC + 6 extra LOP3.  For kernels whose ALU pipe has head-room (k_shortlist) this
+// is the balance point of the two pipes (XU 5/16 clk per pair against ~20/64 on the ALU).
+__device__ __forceinline__ int popc8_5(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t x4, uint32_t x5,
+                                       uint32_t x6, uint32_t x7)
+{
+    const uint32_t s1 = x0 ^ x1 ^ x2, c1 = maj3(x0, x1, x2);
+    const uint32_t s2 = x3 ^ x4 ^ x5, c2 = maj3(x3, x4, x5);
+    const uint32_t s3 = s1 ^ s2 ^ x6, c3 = maj3(s1, s2, x6);
+    return __popc(s3) + __popc(x7) + 2 * (__popc(c1) + __popc(c2) + __popc(c3));
+}
 __device__ __forceinline__ int ham(const Row &R, const uint4 *tile, int j)
 {
     const uint4 x = tile[unit_of(j, 0)], y = tile[unit_of(j, 1)];
@@ -248,7 +258,7 @@ __global__ void __launch_bounds__(M_THREADS) k_shortlist(GreedyArgs a, int T)
             int d[SL_ROWS_PER_WARP];
 #pragma unroll
             for (int k = 0; k < SL_ROWS_PER_WARP; ++k)
-                d[k] = popc8(R[k].a.x ^ x.x, R[k].a.y ^ x.y, R[k].a.z ^ x.z, R[k].a.w ^ x.w,
+                d[k] = popc8_5(R[k].a.x ^ x.x, R[k].a.y ^ x.y, R[k].a.z ^ x.z, R[k].a.w ^ x.w,
                              R[k].b.x ^ y.x, R[k].b.y ^ y.y, R[k].b.z ^ y.z, R[k].b.w ^ y.w);
             // one vote for the 4 rows: most 32-column steps hold no entry below T at all
             const int dmin = min(min(d[0], d[1]), min(d[2], d[3]));

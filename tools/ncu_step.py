@@ -21,7 +21,7 @@ def steps(rows):
 
 def nframes(step):
     for n, g, _ in step:
-        if n.startswith("k_stereo") and not n.startswith("k_stereo_median"):
+        if n == "k_stereo":
             return int(g.strip("()").split(",")[1])
     return 0
 
