@@ -188,7 +188,8 @@ long long svo_launch_count(const svo_ctx *ctx);
 /* Device times (ms) of the lane's last batch, measured with CUDA events on the lane's own
  * stream (profiling must be on): ms[0] whole batch (H2D..D2H), [1] H2D, [2] pyramid,
  * [3] FAST, [4] first cull, [5] Harris, [6] second cull, [7] blur, [8] orient+BRIEF,
- * [9] stereo, [10] matching, [11] D2H.  Writes min(n, 12) values. */
+ * [9] stereo, [10] matching, [11] D2H; then two single kernels of the matching stage:
+ * [12] k_pairs (fused BF + pass-1 distances), [13] k_shortlist of pass 2.  Writes min(n, 14) values. */
 int svo_batch_stage_ms(svo_ctx *ctx, int lane, float *ms, int n);
 /* Turn per-stage event recording on (1) or off (0, default). */
 int svo_set_profiling(svo_ctx *ctx, int on);

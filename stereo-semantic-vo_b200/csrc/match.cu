@@ -343,6 +343,7 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_c
     uint8_t *pre = reinterpret_cast<uint8_t *>(ent + ent_cap);    // 1 = claimed before this pass
     __shared__ int wrow[RES_WARPS], went[RES_WARPS];
     __shared__ int s_total, s_novf;
+    __shared__ int s_hist[SVO_SHORT_CAP + 2];
     const size_t ro = (size_t)f * a.rows.stride_rows, co = (size_t)f * a.cols.stride_rows;
     int *rows_ne = a.res_rows + ro;    // (row | min(cnt, CAP+1) << 16) of the rows that can claim, ascending
     int *roff = a.res_off + ro;        // CSR offset of the row's entries
@@ -401,8 +402,33 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_c
     __syncthreads();
     const int total = s_total;
     const bool any_ovf = s_novf > 0;
+    // ---- processing order: candidate rows sorted by list length (counting sort), so the 32 rows a warp walks
+    // in lock step have equal trip counts.  The order of evaluation inside a sweep is free.
+    int *perm = a.res_perm + ro;
+    for (int i = tid; i < SVO_SHORT_CAP + 2; i += RES_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    for (int k = tid; k < total; k += RES_THREADS) atomicAdd(&s_hist[rows_ne[k] >> 16], 1);
+    __syncthreads();
+    if (warp == 0) {
+        int carry = 0;
+        for (int b0 = 0; b0 < SVO_SHORT_CAP + 2; b0 += 32) {
+            const int c = b0 + lane < SVO_SHORT_CAP + 2 ? s_hist[b0 + lane] : 0;
+            int inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += v;
+            }
+            if (b0 + lane < SVO_SHORT_CAP + 2) s_hist[b0 + lane] = carry + inc - c;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < total; k += RES_THREADS) perm[atomicAdd(&s_hist[rows_ne[k] >> 16], 1)] = k;
+    __syncthreads();
     // ---- stage the short lists in shared memory (rows beyond ent_cap stay in global memory)
-    for (int k = tid; k < total; k += RES_THREADS) {
+    for (int i = tid; i < total; i += RES_THREADS) {
+        const int k = perm[i];
         const int pk = rows_ne[k], r = pk & 0xffff, s = pk >> 16, off = roff[k];
         if (s > SVO_SHORT_CAP) continue;
         if (off + s > ent_cap) {
@@ -443,7 +469,8 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_c
     // ---- sweeps
     for (;;) {
         int changed = 0;
-        for (int k = tid; k < total; k += RES_THREADS) {
+        for (int i = tid; i < total; i += RES_THREADS) {
+            const int k = perm[i];
             const int pk = rows_ne[k], r = pk & 0xffff, s = pk >> 16;
             if (s > SVO_SHORT_CAP) continue;
             const int off = roff[k];
@@ -585,7 +612,7 @@ __global__ void __launch_bounds__(M_THREADS) k_scores(GreedyArgs a)
 
 __device__ __forceinline__ int pt_unit(int j, int h) { const int u = 2 * j + h; return u ^ ((u >> 4) & 7); }
 
-__global__ void __launch_bounds__(M_THREADS) k_pairs(PairArgs p)
+__global__ void __launch_bounds__(M_THREADS, 3) k_pairs(PairArgs p)
 {
     __shared__ uint4 tile[PT_COLS * 2];
     __shared__ uint32_t cm[PT_COLS];
@@ -764,7 +791,8 @@ int setup_match_attributes()
 // k_resolve keeps 9 bytes per column in shared memory next to the staged short lists
 int greedy_max_cols() { return (200 * 1024 - 16 * 1024) / 9; }
 
-void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStream_t st, long long *launches)
+void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStream_t st, long long *launches,
+                   cudaEvent_t ev0, cudaEvent_t ev1)
 {
     const int maxM = a.rows.count ? a.rows.stride_rows : a.rows.fixed_count;
     const int maxN = a.cols.count ? a.cols.stride_rows : a.cols.fixed_count;
@@ -774,8 +802,10 @@ void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStrea
     k_greedy_init<<<gi, 256, 0, st>>>(a, 1);
     const int T = a.mode == SVO_GREEDY_PASS1 ? 15 : 60;
     dim3 gs((maxM + M_WARPS * SL_ROWS_PER_WARP - 1) / (M_WARPS * SL_ROWS_PER_WARP), nframes);
+    if (ev0) cudaEventRecord(ev0, st);
     if (a.win_uvr) k_shortlist<true><<<gs, M_THREADS, 0, st>>>(a, T);
     else k_shortlist<false><<<gs, M_THREADS, 0, st>>>(a, T);
+    if (ev1) cudaEventRecord(ev1, st);
     // shared memory: two claim-time arrays + pre-claimed bytes + as many short-list entries as fit
     const int colsA = (maxN + 3) & ~3;
     const int ent_cap = (g_resolve_smem_limit - colsA * 9 - 64) / 4;
@@ -791,7 +821,8 @@ void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStrea
 }
 
 // BF + greedy pass 1 of a batch with every distance computed once (k_pairs).
-void launch_pass1_fused(const PairArgs &p0, const BfArgs &b, int nframes, cudaStream_t st, long long *launches)
+void launch_pass1_fused(const PairArgs &p0, const BfArgs &b, int nframes, cudaStream_t st, long long *launches,
+                        cudaEvent_t ev0, cudaEvent_t ev1)
 {
     PairArgs p = p0;
     const GreedyArgs &a = p.g;
@@ -807,7 +838,9 @@ void launch_pass1_fused(const PairArgs &p0, const BfArgs &b, int nframes, cudaSt
     int splits = (148 * 6 + tiles * nframes - 1) / (tiles * nframes);   // about two waves of 3 CTAs per SM
     const int max_splits = (maxM + 8 * PT_ROWS - 1) / (8 * PT_ROWS);
     splits = splits < 1 ? 1 : (splits > max_splits ? max_splits : splits);
+    if (ev0) cudaEventRecord(ev0, st);
     k_pairs<<<dim3(tiles, splits, nframes), M_THREADS, 0, st>>>(p);
+    if (ev1) cudaEventRecord(ev1, st);
     k_bf_finish<<<dim3((maxN + 255) / 256, nframes), 256, 0, st>>>(p, b);
     const int colsA = (maxN + 3) & ~3;
     const int ent_cap = (g_resolve_smem_limit - colsA * 9 - 64) / 4;

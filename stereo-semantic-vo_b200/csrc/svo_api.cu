@@ -12,7 +12,7 @@
 #include <string>
 #include <vector>
 
-#define N_EVENTS 12
+#define N_EVENTS 16
 
 namespace {
 
@@ -27,7 +27,7 @@ struct FrameBufs {           // per-frame (stereo pair) device arrays
     int *p1_best_idx, *p1_best, *p1_second; uint8_t *p1_row_claimed, *p1_row_bad;
     int *p2_best_idx, *p2_best, *p2_second; uint8_t *p2_row_claimed;
     uint32_t *shortlist, *shortlist_hi; int *short_cnt;
-    int *res_rows, *res_off, *res_want;
+    int *res_rows, *res_off, *res_want, *res_perm;
     uint8_t *dmat; uint32_t *bf_key; int dmat_pitch; size_t dmat_frame_stride;   // fused pass-1 front (batch path)
     float *u_right, *depth; int *match_r, *sad, *n_stereo;
     int *row_off; uint16_t *row_list; int row_list_stride;
@@ -227,7 +227,7 @@ int alloc_frames(svo_ctx *ctx, FrameBufs &f, int nframes, int col_stride, int ro
     TRY(dalloc(ctx, &f.p2_best_idx, R)); TRY(dalloc(ctx, &f.p2_best, R)); TRY(dalloc(ctx, &f.p2_second, R));
     TRY(dalloc(ctx, &f.p2_row_claimed, R));
     TRY(dalloc(ctx, &f.shortlist, R * 32)); TRY(dalloc(ctx, &f.shortlist_hi, R * (SVO_SHORT_CAP - 32))); TRY(dalloc(ctx, &f.short_cnt, R));
-    TRY(dalloc(ctx, &f.res_rows, R)); TRY(dalloc(ctx, &f.res_off, R)); TRY(dalloc(ctx, &f.res_want, R));
+    TRY(dalloc(ctx, &f.res_rows, R)); TRY(dalloc(ctx, &f.res_off, R)); TRY(dalloc(ctx, &f.res_want, R)); TRY(dalloc(ctx, &f.res_perm, R));
     TRY(dalloc(ctx, &f.u_right, C)); TRY(dalloc(ctx, &f.depth, C)); TRY(dalloc(ctx, &f.match_r, C));
     TRY(dalloc(ctx, &f.sad, C)); TRY(dalloc(ctx, &f.n_stereo, F));
     {   // a right keypoint is a candidate for rows floor(y - r) .. ceil(y + r), r = 2 * scale[octave]
@@ -578,7 +578,7 @@ int svo_match_greedy(svo_ctx *ctx, const uint8_t *rows, int M, const uint8_t *cu
     a.best_idx = s.p2_best_idx; a.best = s.p2_best; a.second = s.p2_second;
     a.row_claimed = s.p2_row_claimed; a.row_bad = s.p1_row_bad;
     a.shortlist = s.shortlist; a.shortlist_hi = s.shortlist_hi; a.short_cnt = s.short_cnt;
-    a.res_rows = s.res_rows; a.res_off = s.res_off; a.res_want = s.res_want;
+    a.res_rows = s.res_rows; a.res_off = s.res_off; a.res_want = s.res_want; a.res_perm = s.res_perm;
     a.win_uvr = win_uvr ? s.win : nullptr;
     a.cur_xy = (win_uvr || use_veto) ? s.cur_xy : nullptr;
     if (use_veto) { a.boxes = s.boxes; a.n_boxes = veto->n_boxes; a.F = s.F; a.row_xy = s.row_xy; }
@@ -731,7 +731,7 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
     ga.shortlist = fb.shortlist + (size_t)L.frame0 * R * 32; ga.shortlist_hi = fb.shortlist_hi + (size_t)L.frame0 * R * (SVO_SHORT_CAP - 32);
     ga.short_cnt = fb.short_cnt + (size_t)L.frame0 * R;
     ga.res_rows = fb.res_rows + (size_t)L.frame0 * R; ga.res_off = fb.res_off + (size_t)L.frame0 * R;
-    ga.res_want = fb.res_want + (size_t)L.frame0 * R;
+    ga.res_want = fb.res_want + (size_t)L.frame0 * R; ga.res_perm = fb.res_perm + (size_t)L.frame0 * R;
     if (any_prev) {
         BfArgs ba;
         MatchSet prev_set = make_set(nullptr, d_nprev, 1, R, 0);
@@ -751,7 +751,7 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
             pa.g = ga;
             pa.dmat = fb.dmat + (size_t)L.frame0 * fb.dmat_frame_stride; pa.dmat_frame_stride = fb.dmat_frame_stride;
             pa.dmat_pitch = fb.dmat_pitch; pa.bf_key = fb.bf_key + (size_t)L.frame0 * K; pa.T = 0; pa.lane_cols = 0;
-            launch_pass1_fused(pa, ba, n, st, &ctx->launches);
+            launch_pass1_fused(pa, ba, n, st, &ctx->launches, ev ? ev[12] : nullptr, ev ? ev[13] : nullptr);
         } else {
             launch_bf(ba, n, st, &ctx->launches);
             launch_greedy(ga, n, true, st, &ctx->launches);
@@ -765,7 +765,7 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
         ga.prev_row_claimed = fb.p1_row_claimed + (size_t)L.frame0 * R; ga.prev_stride = R;
         ga.best_idx = nullptr; ga.best = nullptr; ga.second = nullptr;
         ga.row_claimed = fb.p2_row_claimed + (size_t)L.frame0 * R; ga.row_bad = nullptr;
-        launch_greedy(ga, n, false, st, &ctx->launches);
+        launch_greedy(ga, n, false, st, &ctx->launches, ev ? ev[14] : nullptr, ev ? ev[15] : nullptr);
     }
     if (ev) cudaEventRecord(ev[10], st);
     // ---- D2H: one copy per output array for the whole batch
@@ -842,11 +842,15 @@ int svo_batch_stage_ms(svo_ctx *ctx, int lane_i, float *ms, int n)
     if (!ctx->profiling) return fail(ctx, SVO_E_INVALID, "svo_batch_stage_ms: profiling is off");
     Lane &L = ctx->lanes[lane_i];
     if (L.busy) return fail(ctx, SVO_E_INVALID, "svo_batch_stage_ms: call svo_batch_wait first");
-    float v[12];
+    float v[14];
     CU(cudaEventElapsedTime(&v[0], L.ev[0], L.ev[11]));
     for (int k = 1; k < 12; ++k) CU(cudaEventElapsedTime(&v[k], L.ev[k - 1], L.ev[k]));
-    for (int k = 0; k < n && k < 12; ++k) ms[k] = v[k];
-    return n < 12 ? n : 12;
+    // single kernels inside the matching stage (0 when the batch had no previous frame / no map)
+    v[12] = v[13] = 0.f;
+    if (cudaEventElapsedTime(&v[12], L.ev[12], L.ev[13]) != cudaSuccess) { cudaGetLastError(); v[12] = 0.f; }
+    if (cudaEventElapsedTime(&v[13], L.ev[14], L.ev[15]) != cudaSuccess) { cudaGetLastError(); v[13] = 0.f; }
+    for (int k = 0; k < n && k < 14; ++k) ms[k] = v[k];
+    return n < 14 ? n : 14;
 }
 
 // ----------------------------------------------------------------------------- debug taps

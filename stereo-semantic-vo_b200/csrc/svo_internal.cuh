@@ -152,13 +152,15 @@ struct GreedyArgs {
     uint32_t *shortlist;          // [frame][rows.stride_rows][32]: entries 0..31
     uint32_t *shortlist_hi;       // [frame][rows.stride_rows][SVO_SHORT_CAP - 32]: the rest
     int *short_cnt;               // [frame][rows.stride_rows]
-    int *res_rows, *res_off, *res_want;   // [frame][rows.stride_rows] resolver scratch (candidate rows, CSR offsets, decisions)
+    int *res_rows, *res_off, *res_want, *res_perm;   // [frame][rows.stride_rows] resolver scratch (candidate rows, CSR offsets,
+                                                      // decisions, length-sorted processing order)
     const float *win_uvr;         // [frame][rows.stride_rows][3] or NULL
     const float *cur_xy;          // [frame][cols.stride_rows][2] or NULL
     // veto (pass 1)
     const int *boxes; int n_boxes; const double *F; const float *row_xy;
 };
-void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStream_t st, long long *launches);
+void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStream_t st, long long *launches,
+                   cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);   // optional events around k_shortlist
 
 struct BfArgs {
     MatchSet q, t;
@@ -175,7 +177,8 @@ struct PairArgs {            // fused BF + pass-1 front of the batch path (match
     uint32_t *bf_key;        // [frame][cols.stride_rows] (d << 16 | prev row) minima
     int T, lane_cols;        // filled by the launcher
 };
-void launch_pass1_fused(const PairArgs &p, const BfArgs &b, int nframes, cudaStream_t st, long long *launches);
+void launch_pass1_fused(const PairArgs &p, const BfArgs &b, int nframes, cudaStream_t st, long long *launches,
+                        cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);   // optional events around k_pairs
 void launch_disp2depth(const float *disp, float *depth, size_t n, float bf, cudaStream_t st, long long *launches);
 int setup_match_attributes();
 int greedy_max_cols();   // most columns (current-frame keypoints) the greedy resolver supports

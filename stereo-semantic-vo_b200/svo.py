@@ -18,7 +18,7 @@ OK, E_INVALID, E_CUDA, E_CAPACITY, E_NOMEM = 0, -1, -2, -3, -4
 TAP_LEVEL, TAP_BLUR, TAP_FAST, TAP_SELECT1, TAP_SELECT2 = 0, 1, 2, 3, 4
 PASS1, PASS2 = 0, 1
 STAGES = ("total", "h2d", "pyramid", "fast", "select1", "harris", "select2", "blur", "describe",
-          "stereo", "match", "d2h")
+          "stereo", "match", "d2h", "k_pairs", "k_shortlist2")
 
 
 class Config(C.Structure):
@@ -286,8 +286,8 @@ class Context:
         return r
 
     def stage_ms(self, lane):
-        ms = np.zeros(12, np.float32)
-        self._chk(self.lib.svo_batch_stage_ms(self.h, lane, _p(ms), 12))
+        ms = np.zeros(14, np.float32)
+        self._chk(self.lib.svo_batch_stage_ms(self.h, lane, _p(ms), 14))
         return dict(zip(STAGES, ms.tolist()))
 
     def set_profiling(self, on):
