@@ -282,6 +282,40 @@ __global__ void __launch_bounds__(M_THREADS) k_shortlist(GreedyArgs a, int T)
             }
         }
     }
+    // Pass 2 prunes each finished list to what can influence the row's decision: a row claims only a column
+    // with d < 30, and the ratio test second > 2 * best can only be broken by an entry with d <= 2 * best
+    // <= 2 * dmax, dmax = the largest d < 30 in the list.  Entries above that bound (the bulk of a T = 60
+    // list) are dropped, and a list without any d < 30 entry is emptied.  Overflowed lists are left alone
+    // (they are incomplete; the resolver re-scans those rows exhaustively).
+    if (a.mode == SVO_GREEDY_PASS2) {
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < SL_ROWS_PER_WARP; ++k) {
+            const int c = cnt[k];
+            if (!live[k] || c == 0 || c > SVO_SHORT_CAP) continue;   // warp-uniform
+            uint32_t e[SVO_SHORT_CAP / 32];
+            int dmax = -1;
+#pragma unroll
+            for (int t = 0; t < SVO_SHORT_CAP / 32; ++t) {
+                e[t] = lane + 32 * t < c ? *short_slot(a, ro + r0 + k, lane + 32 * t) : 0xffffffffu;
+                const int d = (int)(e[t] >> 16);
+                if (d < 30) dmax = max(dmax, d);
+            }
+            dmax = __reduce_max_sync(0xffffffffu, dmax);
+            __syncwarp();
+            int n = 0;
+            if (dmax >= 0) {
+#pragma unroll
+                for (int t = 0; t < SVO_SHORT_CAP / 32; ++t) {
+                    const bool keep = e[t] != 0xffffffffu && (int)(e[t] >> 16) <= 2 * dmax;
+                    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+                    if (keep) *short_slot(a, ro + r0 + k, n + __popc(m & ((1u << lane) - 1u))) = e[t];
+                    n += __popc(m);
+                }
+            }
+            cnt[k] = n;
+        }
+    }
     if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < SL_ROWS_PER_WARP; ++k)
@@ -319,6 +353,7 @@ __device__ bool veto_dynamic(const GreedyArgs &a, int f, int row, int col)
 #define RES_THREADS 1024
 #define RES_WARPS (RES_THREADS / 32)
 #define RES_FREE 0x7fffffff
+#define RES_RC 6     // candidate rows per thread whose state stays in registers (6 * 1024 rows per frame)
 
 // The greedy scan is sequential in the reference (a claim hides the column from every later row), but
 // its result is the unique fixed point of a fully parallel map.  Let want[k] be the column the k-th
@@ -426,71 +461,99 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_c
     __syncthreads();
     for (int k = tid; k < total; k += RES_THREADS) perm[atomicAdd(&s_hist[rows_ne[k] >> 16], 1)] = k;
     __syncthreads();
-    // ---- stage the short lists in shared memory (rows beyond ent_cap stay in global memory)
-    for (int i = tid; i < total; i += RES_THREADS) {
-        const int k = perm[i];
-        const int pk = rows_ne[k], r = pk & 0xffff, s = pk >> 16, off = roff[k];
-        if (s > SVO_SHORT_CAP) continue;
-        if (off + s > ent_cap) {
-            // stays in global memory; k_pairs appends in arrival order, the sweeps need ascending columns
-            if (unsorted)
-                for (int i = 1; i < s; ++i) {
-                    const uint32_t e = *short_slot(a, ro + r, i);
-                    int j = i - 1;
-                    for (; j >= 0 && (*short_slot(a, ro + r, j) & 0xffffu) > (e & 0xffffu); --j) *short_slot(a, ro + r, j + 1) = *short_slot(a, ro + r, j);
-                    *short_slot(a, ro + r, j + 1) = e;
-                }
-            continue;
-        }
-        const uint4 *lo = reinterpret_cast<const uint4 *>(a.shortlist + (ro + r) * 32);
-        const uint4 *hi = reinterpret_cast<const uint4 *>(a.shortlist_hi + (ro + r) * (SVO_SHORT_CAP - 32));
-        for (int j = 0; j < s; j += 4) {
-            const uint4 v = j < 32 ? lo[j >> 2] : hi[(j - 32) >> 2];
-            ent[off + j] = v.x;
-            if (j + 1 < s) ent[off + j + 1] = v.y;
-            if (j + 2 < s) ent[off + j + 2] = v.z;
-            if (j + 3 < s) ent[off + j + 3] = v.w;
-        }
-        if (unsorted)
-            for (int i = 1; i < s; ++i) {
-                const uint32_t e = ent[off + i];
-                int j = i - 1;
-                for (; j >= 0 && (ent[off + j] & 0xffffu) > (e & 0xffffu); --j) ent[off + j + 1] = ent[off + j];
-                ent[off + j + 1] = e;
-            }
-    }
-    __syncthreads();
+    // ---- each thread owns the sorted positions pos(j) = j * 1024 + (tid, or 1023 - tid on odd j: the snake keeps
+    // the per-warp work even although the positions are length-sorted).  The rows' metadata and decisions of the
+    // first RES_RC rounds live in registers, so a sweep touches shared memory only.
     const uint8_t *rd = set_desc(a.rows, f), *cd = set_desc(a.cols, f);
     const float *cxy = a.cur_xy ? a.cur_xy + co * 2 : nullptr;
     const int rbase = a.row_base + (a.row_base_arr ? a.row_base_arr[f] : 0);
     const bool pass1 = a.mode == SVO_GREEDY_PASS1;
     const bool use_veto = pass1 && a.n_boxes > 0 && a.F;
+    auto pos_of = [&](int j) -> int { return j * RES_THREADS + ((j & 1) ? RES_THREADS - 1 - tid : tid); };
+    const int rounds = (total + RES_THREADS - 1) / RES_THREADS;
+    int mk[RES_RC], mrs[RES_RC], moff[RES_RC], mw[RES_RC];   // k, row | s << 16, CSR offset, decision
+#pragma unroll
+    for (int j = 0; j < RES_RC; ++j) {
+        mk[j] = -1; mrs[j] = 0; moff[j] = 0; mw[j] = -1;
+        const int i = pos_of(j);
+        if (i < total) { mk[j] = perm[i]; mrs[j] = rows_ne[mk[j]]; moff[j] = roff[mk[j]]; }
+    }
+    // stage the short lists in shared memory (rows beyond ent_cap stay in global memory)
+    auto stage_row = [&](int r, int sz, int off) {
+        if (sz > SVO_SHORT_CAP) return;
+        if (off + sz > ent_cap) {
+            // stays in global memory; k_pairs appends in arrival order, the sweeps need ascending columns
+            if (unsorted)
+                for (int i = 1; i < sz; ++i) {
+                    const uint32_t e = *short_slot(a, ro + r, i);
+                    int j = i - 1;
+                    for (; j >= 0 && (*short_slot(a, ro + r, j) & 0xffffu) > (e & 0xffffu); --j) *short_slot(a, ro + r, j + 1) = *short_slot(a, ro + r, j);
+                    *short_slot(a, ro + r, j + 1) = e;
+                }
+            return;
+        }
+        const uint4 *lo = reinterpret_cast<const uint4 *>(a.shortlist + (ro + r) * 32);
+        const uint4 *hi = reinterpret_cast<const uint4 *>(a.shortlist_hi + (ro + r) * (SVO_SHORT_CAP - 32));
+        for (int j = 0; j < sz; j += 4) {
+            const uint4 v = j < 32 ? lo[j >> 2] : hi[(j - 32) >> 2];
+            ent[off + j] = v.x;
+            if (j + 1 < sz) ent[off + j + 1] = v.y;
+            if (j + 2 < sz) ent[off + j + 2] = v.z;
+            if (j + 3 < sz) ent[off + j + 3] = v.w;
+        }
+        if (unsorted)
+            for (int i = 1; i < sz; ++i) {
+                const uint32_t e = ent[off + i];
+                int j = i - 1;
+                for (; j >= 0 && (ent[off + j] & 0xffffu) > (e & 0xffffu); --j) ent[off + j + 1] = ent[off + j];
+                ent[off + j + 1] = e;
+            }
+    };
+#pragma unroll
+    for (int j = 0; j < RES_RC; ++j)
+        if (mk[j] >= 0) stage_row(mrs[j] & 0xffff, mrs[j] >> 16, moff[j]);
+    for (int j = RES_RC; j < rounds; ++j) {
+        const int i = pos_of(j);
+        if (i < total) { const int k = perm[i]; stage_row(rows_ne[k] & 0xffff, rows_ne[k] >> 16, roff[k]); }
+    }
+    __syncthreads();
     int *ctc = ct0, *ctn = ct1;
+    // one row's decision against the claim times of the previous sweep
+    auto decide_row = [&](int k, int r, int sz, int off) -> int {
+        int bd = 256, sd = 256, bi = -1;
+        if (off + sz <= ent_cap) {
+            for (int j = 0; j < sz; ++j) {
+                const uint32_t e = ent[off + j];
+                const int col = (int)(e & 0xffffu), d = (int)(e >> 16);
+                if (ctc[col] >= k && d < bd) { sd = bd; bd = d; bi = col; }
+            }
+        } else {
+            for (int j = 0; j < sz; ++j) {
+                const uint32_t e = *short_slot(a, ro + r, j);
+                const int col = (int)(e & 0xffffu), d = (int)(e >> 16);
+                if (ctc[col] >= k && d < bd) { sd = bd; bd = d; bi = col; }
+            }
+        }
+        int w = (bi >= 0 && (pass1 ? bd < 15 : (bd < 30 && sd > 2 * bd))) ? bi : -1;
+        if (w >= 0 && use_veto && veto_dynamic(a, f, r, w)) w = -2;
+        if (w >= 0) atomicMin(&ctn[w], k);
+        return w;
+    };
     // ---- sweeps
     for (;;) {
         int changed = 0;
-        for (int i = tid; i < total; i += RES_THREADS) {
-            const int k = perm[i];
-            const int pk = rows_ne[k], r = pk & 0xffff, s = pk >> 16;
-            if (s > SVO_SHORT_CAP) continue;
-            const int off = roff[k];
-            int bd = 256, sd = 256, bi = -1;
-            if (off + s <= ent_cap) {
-                for (int j = 0; j < s; ++j) {
-                    const uint32_t e = ent[off + j];
-                    const int col = (int)(e & 0xffffu), d = (int)(e >> 16);
-                    if (ctc[col] >= k && d < bd) { sd = bd; bd = d; bi = col; }
-                }
-            } else {
-                for (int j = 0; j < s; ++j) {
-                    const uint32_t e = *short_slot(a, ro + r, j);
-                    const int col = (int)(e & 0xffffu), d = (int)(e >> 16);
-                    if (ctc[col] >= k && d < bd) { sd = bd; bd = d; bi = col; }
-                }
-            }
-            int w = (bi >= 0 && (pass1 ? bd < 15 : (bd < 30 && sd > 2 * bd))) ? bi : -1;
-            if (w >= 0 && use_veto && veto_dynamic(a, f, r, w)) w = -2;
-            if (w >= 0) atomicMin(&ctn[w], k);
+#pragma unroll
+        for (int j = 0; j < RES_RC; ++j) {
+            if (mk[j] < 0 || (mrs[j] >> 16) > SVO_SHORT_CAP) continue;
+            const int w = decide_row(mk[j], mrs[j] & 0xffff, mrs[j] >> 16, moff[j]);
+            if (w != mw[j]) { mw[j] = w; changed = 1; }
+        }
+        for (int j = RES_RC; j < rounds; ++j) {     // more than RES_RC * 1024 candidate rows: metadata from global memory
+            const int i = pos_of(j);
+            if (i >= total) continue;
+            const int k = perm[i], pk = rows_ne[k];
+            if ((pk >> 16) > SVO_SHORT_CAP) continue;
+            const int w = decide_row(k, pk & 0xffff, pk >> 16, roff[k]);
             if (w != want[k]) { want[k] = w; changed = 1; }
         }
         if (any_ovf) {   // rows with an unknown list: exhaustive scan, one warp per row
@@ -525,6 +588,10 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_c
         __syncthreads();
     }
     // ---- fixed point reached: publish the claims
+#pragma unroll
+    for (int j = 0; j < RES_RC; ++j)
+        if (mk[j] >= 0 && (mrs[j] >> 16) <= SVO_SHORT_CAP) want[mk[j]] = mw[j];
+    __syncthreads();
     for (int k = tid; k < total; k += RES_THREADS) {
         const int w = want[k], r = rows_ne[k] & 0xffff;
         if (w >= 0) {
