@@ -210,7 +210,9 @@ __device__ int block_retain_best(float *key, uint32_t *val, int n, int n_points,
 }
 
 // ---- first cull: gather the level's band lists (raster order) and keep 2*quota by FAST score
-__global__ void __launch_bounds__(SEL_THREADS) k_select1(Bufs b, Geom g, int slot0)
+extern __shared__ __align__(16) uint32_t sel_dyn[];   // [key | val | lpos | rasc], smem_cap entries each
+
+__global__ void __launch_bounds__(SEL_THREADS) k_select1(Bufs b, Geom g, int slot0, int smem_cap)
 {
     __shared__ SelSmem sh;
     __shared__ int band_base[512];
@@ -242,10 +244,15 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select1(Bufs b, Geom g, int slo
     }
     __syncthreads();
     const int n = band_base[L.nbands];
-    float *key = b.ckey + (size_t)slot * g.cand_total + L.cand_off;
-    uint32_t *val = b.cval + (size_t)slot * g.cand_total + L.cand_off;
-    uint32_t *lpos = b.lpos + (size_t)slot * g.cand_total + L.cand_off;
-    uint32_t *rasc = b.rpos + (size_t)slot * g.cand_total + L.cand_off;
+    float *gkey = b.ckey + (size_t)slot * g.cand_total + L.cand_off;
+    uint32_t *gval = b.cval + (size_t)slot * g.cand_total + L.cand_off;
+    // the replay is a chain of short dependent phases: with the arrays in shared memory a phase costs a
+    // shared-memory round trip instead of an L2 one (falls back to global memory when n exceeds the carve-out)
+    const bool in_smem = n <= smem_cap;
+    float *key = in_smem ? reinterpret_cast<float *>(sel_dyn) : gkey;
+    uint32_t *val = in_smem ? sel_dyn + smem_cap : gval;
+    uint32_t *lpos = in_smem ? sel_dyn + 2 * smem_cap : b.lpos + (size_t)slot * g.cand_total + L.cand_off;
+    uint32_t *rasc = in_smem ? sel_dyn + 3 * smem_cap : b.rpos + (size_t)slot * g.cand_total + L.cand_off;
     const uint32_t *bands = b.bands + (size_t)slot * g.band_total + L.band_off;
     for (int bi = warp; bi < L.nbands; bi += SEL_WARPS) {
         const int c = bc[bi], o = band_base[bi];
@@ -259,21 +266,36 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select1(Bufs b, Geom g, int slo
     __syncthreads();
     const int kept = block_retain_best(key, val, n, 2 * L.quota, -1, lpos, rasc, sh, b.status + slot);
     if (tid == 0) { cnt1[l] = n; kept1[l] = kept; }
+    if (in_smem) {
+        __syncthreads();
+        for (int i = tid; i < kept; i += SEL_THREADS) { gkey[i] = key[i]; gval[i] = val[i]; }
+    }
 }
 
 // ---- second cull: keep quota by Harris response
-__global__ void __launch_bounds__(SEL_THREADS) k_select2(Bufs b, Geom g, int slot0)
+__global__ void __launch_bounds__(SEL_THREADS) k_select2(Bufs b, Geom g, int slot0, int smem_cap)
 {
     __shared__ SelSmem sh;
     const int l = blockIdx.x, slot = slot0 + blockIdx.y;
     const LevelGeom &L = g.lv[l];
     const int n = min(b.kept1[(size_t)slot * SVO_MAX_LEVELS + l], L.cap2);
-    float *key = b.key2 + (size_t)slot * g.total2 + L.off2;
-    uint32_t *val = b.val2 + (size_t)slot * g.total2 + L.off2;
-    uint32_t *lpos = b.lpos + (size_t)slot * g.cand_total + L.cand_off;
-    uint32_t *rasc = b.rpos + (size_t)slot * g.cand_total + L.cand_off;
+    float *gkey = b.key2 + (size_t)slot * g.total2 + L.off2;
+    uint32_t *gval = b.val2 + (size_t)slot * g.total2 + L.off2;
+    const bool in_smem = n <= smem_cap;
+    float *key = in_smem ? reinterpret_cast<float *>(sel_dyn) : gkey;
+    uint32_t *val = in_smem ? sel_dyn + smem_cap : gval;
+    uint32_t *lpos = in_smem ? sel_dyn + 2 * smem_cap : b.lpos + (size_t)slot * g.cand_total + L.cand_off;
+    uint32_t *rasc = in_smem ? sel_dyn + 3 * smem_cap : b.rpos + (size_t)slot * g.cand_total + L.cand_off;
+    if (in_smem) {
+        for (int i = threadIdx.x; i < n; i += SEL_THREADS) { key[i] = gkey[i]; val[i] = gval[i]; }
+        __syncthreads();
+    }
     const int kept = block_retain_best(key, val, n, L.quota, -1, lpos, rasc, sh, b.status + slot);
     if (threadIdx.x == 0) b.kept2[(size_t)slot * SVO_MAX_LEVELS + l] = kept;
+    if (in_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < kept; i += SEL_THREADS) { gkey[i] = key[i]; gval[i] = val[i]; }
+    }
 }
 
 __global__ void __launch_bounds__(SEL_THREADS) k_retain_best_raw(float *key, uint32_t *val, int n, int n_points,
@@ -285,17 +307,40 @@ __global__ void __launch_bounds__(SEL_THREADS) k_retain_best_raw(float *key, uin
     if (threadIdx.x == 0) *kept_out = kept;
 }
 
+#define SEL_SMEM_MAX 12000   // entries: 4 arrays x 4 B x 12000 = 187.5 KB
+
+static int sel_cap1(const Geom &g)
+{
+    int mx = 0;
+    for (int l = 0; l < g.nlevels; ++l) mx = g.lv[l].cand_cap > mx ? g.lv[l].cand_cap : mx;
+    return mx < SEL_SMEM_MAX ? mx : SEL_SMEM_MAX;
+}
+static int sel_cap2(const Geom &g)
+{
+    int mx = 0;
+    for (int l = 0; l < g.nlevels; ++l) mx = g.lv[l].cap2 > mx ? g.lv[l].cap2 : mx;
+    return mx < SEL_SMEM_MAX ? mx : SEL_SMEM_MAX;
+}
+
+int setup_select_attributes()
+{
+    if (cudaFuncSetAttribute(k_select1, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * SEL_SMEM_MAX) != cudaSuccess) return 1;
+    return (int)cudaFuncSetAttribute(k_select2, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * SEL_SMEM_MAX);
+}
+
 void launch_select1(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches)
 {
     dim3 grid(g.nlevels, nimg);
-    k_select1<<<grid, SEL_THREADS, 0, st>>>(b, g, slot0);
+    const int cap = sel_cap1(g);
+    k_select1<<<grid, SEL_THREADS, (size_t)16 * cap, st>>>(b, g, slot0, cap);
     ++*launches;
 }
 
 void launch_select2(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches)
 {
     dim3 grid(g.nlevels, nimg);
-    k_select2<<<grid, SEL_THREADS, 0, st>>>(b, g, slot0);
+    const int cap = sel_cap2(g);
+    k_select2<<<grid, SEL_THREADS, (size_t)16 * cap, st>>>(b, g, slot0, cap);
     ++*launches;
 }
 

@@ -385,7 +385,7 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
     TRY(alloc_frames(ctx, ctx->fb, nbatch_frames, g.kp_cap, c.max_rows, false));
     const int sync_stride = g.kp_cap > c.max_rows ? g.kp_cap : c.max_rows;
     TRY(alloc_frames(ctx, ctx->sb, 1, sync_stride, sync_stride, true));
-    if (setup_fast_attributes(g) != 0 || setup_match_attributes() != 0 || setup_describe() != 0)
+    if (setup_fast_attributes(g) != 0 || setup_match_attributes() != 0 || setup_describe() != 0 || setup_select_attributes() != 0)
         return fail(ctx, SVO_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
     CU(cudaStreamCreateWithFlags(&ctx->sync_st, cudaStreamNonBlocking));
     ctx->stage_img_bytes = (size_t)g.H * (g.W + 256);

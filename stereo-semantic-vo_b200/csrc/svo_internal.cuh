@@ -103,6 +103,7 @@ void launch_describe(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStre
 int fast_smem_bytes(const Geom &g);
 int setup_fast_attributes(const Geom &g);
 int setup_describe();
+int setup_select_attributes();
 
 // bare retainBest replay (debug/test entry)
 void launch_retain_best_raw(float *key, uint32_t *val, int n, int n_points, int depth_limit,
