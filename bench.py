@@ -177,14 +177,10 @@ def run_gpu(args, rank, world, local_rank):
         return dict(left=hl[t], right=hr[t], bf=BF, baseline=BASELINE, prev_desc=h_prev[t, :n_prev[t]],
                     prev_live=h_live[t, :n_prev[t]], map_desc=h_map[t], map_prev_row=h_mpr[t])
 
-    class Raw:  # minimal stand-in so svo.batch_submit takes raw device addresses
-        def __init__(self, addr):
-            self.ctypes = type("c", (), {"data": addr})()
-
     def frame_dev(t):
         return dict(left=d_l + t * img_b, right=d_r + t * img_b, stride=pitch, bf=BF, baseline=BASELINE,
-                    prev_desc=d_prev + t * K * 32, n_prev=int(n_prev[t]), prev_live=Raw(d_live + t * K),
-                    map_desc=d_map + t * MAP_ROWS * 32, n_map=MAP_ROWS, map_prev_row=Raw(d_mpr + t * MAP_ROWS * 4))
+                    prev_desc=d_prev + t * K * 32, n_prev=int(n_prev[t]), prev_live=d_live + t * K,
+                    map_desc=d_map + t * MAP_ROWS * 32, n_map=MAP_ROWS, map_prev_row=d_mpr + t * MAP_ROWS * 4)
 
     streams = [torch.cuda.ExternalStream(ctx.lane_stream(l), device=dev) for l in range(args.lanes)]
 

@@ -11,6 +11,7 @@
 // Algorithmic bytes: each level pixel read once (+ (8/SVO_FAST_BAND) halo re-read),
 // 4 B written per corner.
 #include "svo_internal.cuh"
+#include <cuda/barrier>
 
 #define FAST_THREADS 256
 
@@ -108,7 +109,7 @@ __device__ __forceinline__ int fast_score(const uint8_t *p, int sp, int t)
     return s >= t ? s : 0;
 }
 
-extern __shared__ __align__(16) uint8_t fast_smem[];
+extern __shared__ __align__(128) uint8_t fast_smem[];
 
 // shared-memory carve-up for a level of pitch sp (bytes)
 __host__ __device__ inline int fast_off_sc(int sp) { return (SVO_FAST_BAND + 8) * sp; }
@@ -137,15 +138,27 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(Bufs b, Geom g, int slot0
     const int wpr = (wv + 31) >> 5;   // bitmap words per row
     __shared__ int wsum[FAST_THREADS / 32];
 
-    {   // stage pixel rows with 128-bit loads; clear the score tile and the bitmap
-        const uint4 *src = reinterpret_cast<const uint4 *>(b.pyr + (size_t)slot * g.pyr_bytes + L.off + (size_t)(yb - 4) * sp);
-        uint4 *dst = reinterpret_cast<uint4 *>(pix);
-        const int n16 = ((nrow + 8) * sp) >> 4;
-        for (int i = tid; i < n16; i += FAST_THREADS) dst[i] = src[i];
+    {   // The band's pixel rows are contiguous in HBM (16-byte pitched rows): one TMA bulk copy
+        // (cp.async.bulk, completes on an mbarrier) stages them while the threads clear the score tile and the
+        // bitmap.
+        __shared__ cuda::barrier<cuda::thread_scope_block> bar;
+        const uint8_t *src = b.pyr + (size_t)slot * g.pyr_bytes + L.off + (size_t)(yb - 4) * sp;
+        const uint32_t bytes = (uint32_t)((nrow + 8) * sp);
+        if (tid == 0) {
+            init(&bar, 1);
+            cuda::device::experimental::fence_proxy_async_shared_cta();
+        }
+        __syncthreads();
+        cuda::barrier<cuda::thread_scope_block>::arrival_token tok;
+        if (tid == 0) {
+            cuda::device::memcpy_async_tx(pix, src, cuda::aligned_size_t<16>(bytes), bar);
+            tok = cuda::device::barrier_arrive_tx(bar, 1, bytes);
+        }
         uint4 *z = reinterpret_cast<uint4 *>(sc);
         const int z16 = ((nrow + 2) * sp) >> 4;
         for (int i = tid; i < z16; i += FAST_THREADS) z[i] = make_uint4(0, 0, 0, 0);
         for (int i = tid; i < nrow * wpr; i += FAST_THREADS) mask[i] = 0;
+        if (tid == 0) bar.wait(std::move(tok));
     }
     __syncthreads();
     // A. SWAR necessary test on every pixel of rows yb-1..ye, columns x0-1..x1, four pixels per thread, in

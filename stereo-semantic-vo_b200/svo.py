@@ -253,9 +253,11 @@ class Context:
                     setattr(fi, name, v); setattr(fi, cnt, f[cnt])
             for name in ("prev_live", "map_prev_row"):
                 v = f.get(name)
-                if v is not None:
+                if isinstance(v, np.ndarray):
                     keep.append(v)
                     setattr(fi, name, v.ctypes.data)
+                elif v is not None:
+                    setattr(fi, name, int(v))          # raw (device) address
         self._keep[("lane", lane)] = (arr, keep)
         self._chk(self.lib.svo_batch_submit(self.h, lane, arr, len(frames)))
 

@@ -308,3 +308,73 @@ def test_batch_pipeline_vs_oracle(ctxK):
         assert (r["p2_row_claimed"] == p2["row_claimed"]).all()
         assert (r["claim_row"] == p2["claim_row"]).all()
         assert p1["row_claimed"].sum() > 50 and p2["row_claimed"].sum() > 50
+
+
+def _same_result(a, b):
+    for k in a:
+        if isinstance(a[k], np.ndarray):
+            assert a[k].shape == b[k].shape and a[k].tobytes() == b[k].tobytes(), k
+        else:
+            assert a[k] == b[k], k
+
+
+def test_batch_inputs_any_residency_and_layout(ctxK):
+    """svo_batch_submit reads device buffers in place and gathers host buffers run by run: the results must not
+    depend on where the inputs live or how they are laid out (device pointers, one contiguous host block shared by
+    consecutive frames, strided image views, descriptor blocks at addresses that are not 16-byte aligned)."""
+    cal = synth.KITTI_04_12
+    bf, b = float(np.float32(cal["bf"])), float(np.float32(cal["bf"] / cal["fx"]))
+    seq = synth.Sequence(seed=5)
+    H, W = synth.K_SHAPE
+    frames = [seq.frame(t) for t in range(3)]
+    prevs = [ctxK.extract(frames[t][0], cam=0)[1] for t in range(3)]
+    rng = np.random.default_rng(12)
+    jobs = []
+    for t in (1, 2):
+        prev = prevs[t - 1]
+        mp = synth.local_map(prevs[:t], rows=3000, seed=t)
+        mpr = np.full(3000, -1, np.int32)
+        take = rng.permutation(3000)[:400]; src = rng.integers(0, len(prev), 400)
+        mp[take] = prev[src]; mpr[take] = src
+        live = (rng.random(len(prev)) < 0.8).astype(np.uint8)
+        jobs.append(dict(left=frames[t][0], right=frames[t][1], bf=bf, baseline=b, prev_desc=prev, prev_live=live,
+                         map_desc=mp, map_prev_row=mpr))
+    ctxK.batch_submit(0, jobs); ctxK.batch_wait(0)
+    base = [ctxK.batch_result(0, i) for i in range(2)]
+    assert base[0]["p1_row_claimed"].sum() > 20 and base[0]["p2_row_claimed"].sum() > 20
+
+    # (1) everything device resident, passed as raw addresses
+    dev = []
+    for j in jobs:
+        dev.append(dict(left=ctxK.to_device(j["left"]), right=ctxK.to_device(j["right"]), stride=W, bf=bf, baseline=b,
+                        prev_desc=ctxK.to_device(j["prev_desc"]), n_prev=len(j["prev_desc"]),
+                        prev_live=ctxK.to_device(j["prev_live"]),
+                        map_desc=ctxK.to_device(j["map_desc"]), n_map=len(j["map_desc"]),
+                        map_prev_row=ctxK.to_device(j["map_prev_row"])))
+    ctxK.batch_submit(1, dev); ctxK.batch_wait(1)
+    for i in range(2):
+        _same_result(base[i], ctxK.batch_result(1, i))
+
+    # (2) host inputs in awkward layouts: frame 0's left and right images adjacent in one block (one gathered run),
+    # frame 1's images as strided views, descriptors at odd addresses, the same map block given to both frames
+    block = np.zeros((2, H, W), np.uint8)
+    wide = np.zeros((2, H, W + 37), np.uint8)
+    raw = np.zeros(2 * (len(jobs[0]["prev_desc"]) + len(jobs[1]["prev_desc"])) * 32 + 64, np.uint8)
+    odd, off = [], 4
+    for i, j in enumerate(jobs):
+        if i == 0:
+            block[0] = j["left"]; block[1] = j["right"]; imgs = (block[0], block[1])
+        else:
+            wide[0, :, :W] = j["left"]; wide[1, :, :W] = j["right"]; imgs = (wide[0, :, :W], wide[1, :, :W])
+        n = len(j["prev_desc"])
+        v = raw[off:off + n * 32].reshape(n, 32); v[:] = j["prev_desc"]
+        off += n * 32 + 4
+        odd.append(dict(left=imgs[0], right=imgs[1], bf=bf, baseline=b, prev_desc=v, prev_live=j["prev_live"],
+                        map_desc=jobs[0]["map_desc"], map_prev_row=None))
+        assert v.ctypes.data % 16 != 0
+    ref2 = [dict(j, map_desc=jobs[0]["map_desc"], map_prev_row=None) for j in jobs]
+    ctxK.batch_submit(0, ref2); ctxK.batch_wait(0)
+    want = [ctxK.batch_result(0, i) for i in range(2)]
+    ctxK.batch_submit(1, odd); ctxK.batch_wait(1)
+    for i in range(2):
+        _same_result(want[i], ctxK.batch_result(1, i))
