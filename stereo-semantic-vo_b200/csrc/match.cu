@@ -197,11 +197,37 @@ __global__ void k_greedy_init(GreedyArgs a, int reset_time)
         a.claim_time[o] = a.claimed[o] ? INT_MIN : INT_MAX;
     }
     if (i < M) {
-        const size_t o = (size_t)f * a.rows.stride_rows + i;
+        const size_t ro = (size_t)f * a.rows.stride_rows, o = ro + i;
         a.row_claimed[o] = 0;
         if (a.row_bad) a.row_bad[o] = 0;
         a.short_cnt[o] = 0;
         if (a.best_idx) { a.best_idx[o] = -1; a.best[o] = 256; a.second[o] = 256; }
+        if (a.need_list) {
+            // Work lists of the batch path's pass 2.  A row that is the map point of pass-1 row `pr`
+            // (src/pnpmatch.cc:167: the same mappoint object, hence the same frozen m_descriptor in both passes) is
+            // dropped when pass 1 matched it; otherwise, if the two descriptors really are equal, its distances
+            // already sit in row `pr` of the matrix k_pairs wrote (k_reuse thresholds that row); every other
+            // live row goes to k_shortlist.  The lists are unordered: rows are independent until k_resolve.
+            const uint8_t *rl = live_of(a, f);
+            const int *mpr = map_prev_of(a, f);
+            bool live = !rl || rl[i];
+            int reuse = -1;
+            if (live && mpr) {
+                const int pr = mpr[i];
+                if (pr >= 0) {
+                    if (a.prev_row_claimed[(size_t)f * a.prev_stride + pr]) live = false;
+                    else if (a.dmat && pr < set_count(a.prev, f)) {
+                        const Row P = load_row(set_desc(a.prev, f), pr), Q = load_row(set_desc(a.rows, f), i);
+                        if (P.a.x == Q.a.x && P.a.y == Q.a.y && P.a.z == Q.a.z && P.a.w == Q.a.w &&
+                            P.b.x == Q.b.x && P.b.y == Q.b.y && P.b.z == Q.b.z && P.b.w == Q.b.w) reuse = pr;
+                    }
+                }
+            }
+            if (live) {
+                if (reuse >= 0) a.reuse_list[ro + atomicAdd(a.list_cnt + 2 * f + 1, 1)] = i | (reuse << 16);
+                else a.need_list[ro + atomicAdd(a.list_cnt + 2 * f, 1)] = i;
+            }
+        }
     }
 }
 
@@ -217,31 +243,67 @@ __device__ __forceinline__ uint32_t *short_slot(const GreedyArgs &a, size_t row,
     return pos < 32 ? a.shortlist + row * 32 + pos : a.shortlist_hi + row * (SVO_SHORT_CAP - 32) + (pos - 32);
 }
 
+// Pass 2 prunes each finished list to what can influence the row's decision: a row claims only a column
+// with d < 30, and the ratio test second > 2 * best can only be broken by an entry with d <= 2 * best
+// <= 2 * dmax, dmax = the largest d < 30 in the list.  Entries above that bound (the bulk of a T = 60
+// list) are dropped, and a list without any d < 30 entry is emptied.  Overflowed lists are left alone
+// (they are incomplete; the resolver re-scans those rows exhaustively).  Whole warp; returns the new count.
+__device__ __forceinline__ int prune_list(const GreedyArgs &a, size_t row, int c, int lane)
+{
+    if (c == 0 || c > SVO_SHORT_CAP) return c;   // warp-uniform
+    uint32_t e[SVO_SHORT_CAP / 32];
+    int dmax = -1;
+#pragma unroll
+    for (int t = 0; t < SVO_SHORT_CAP / 32; ++t) {
+        e[t] = lane + 32 * t < c ? *short_slot(a, row, lane + 32 * t) : 0xffffffffu;
+        const int d = (int)(e[t] >> 16);
+        if (d < 30) dmax = max(dmax, d);
+    }
+    dmax = __reduce_max_sync(0xffffffffu, dmax);
+    __syncwarp();
+    int n = 0;
+    if (dmax >= 0) {
+#pragma unroll
+        for (int t = 0; t < SVO_SHORT_CAP / 32; ++t) {
+            const bool keep = e[t] != 0xffffffffu && (int)(e[t] >> 16) <= 2 * dmax;
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            if (keep) *short_slot(a, row, n + __popc(m & ((1u << lane) - 1u))) = e[t];
+            n += __popc(m);
+        }
+    }
+    return n;
+}
+
 template <bool WIN>
-__global__ void __launch_bounds__(M_THREADS) k_shortlist(GreedyArgs a, int T)
+__global__ void __launch_bounds__(M_THREADS, 3) k_shortlist(GreedyArgs a, int T)
 {
     __shared__ uint4 tile[COL_TILE * 2];
     const int f = blockIdx.y;
     const int M = set_count(a.rows, f), N = set_count(a.cols, f);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (blockIdx.x * M_WARPS * SL_ROWS_PER_WARP >= M) return;
+    const size_t ro = (size_t)f * a.rows.stride_rows;
+    // rows to process: all of them, or (batch pass 2) the work list k_greedy_init compacted
+    const int *list = a.need_list ? a.need_list + ro : nullptr;
+    const int nrows = list ? min(a.list_cnt[2 * f], M) : M;
+    if (blockIdx.x * M_WARPS * SL_ROWS_PER_WARP >= nrows) return;
     const int r0 = (blockIdx.x * M_WARPS + warp) * SL_ROWS_PER_WARP;
     const uint8_t *rd = set_desc(a.rows, f), *cd = set_desc(a.cols, f);
     const float *cxy = WIN ? a.cur_xy + (size_t)f * a.cols.stride_rows * 2 : nullptr;
-    const size_t ro = (size_t)f * a.rows.stride_rows;
-    const uint8_t *rl = live_of(a, f);
+    const uint8_t *rl = list ? nullptr : live_of(a, f);   // the work list holds live rows only
     Row R[SL_ROWS_PER_WARP];
-    int cnt[SL_ROWS_PER_WARP];
+    int cnt[SL_ROWS_PER_WARP], rid[SL_ROWS_PER_WARP];
     bool live[SL_ROWS_PER_WARP];
     float wu[SL_ROWS_PER_WARP], wv[SL_ROWS_PER_WARP], wr[SL_ROWS_PER_WARP];
 #pragma unroll
     for (int k = 0; k < SL_ROWS_PER_WARP; ++k) {
-        const int r = r0 + k;
+        const int i = r0 + k;
+        const int r = i < nrows ? (list ? list[i] : i) : (list ? list[nrows - 1] : M - 1);
+        rid[k] = r;
         cnt[k] = 0;
-        live[k] = r < M && (!rl || rl[r]);
-        R[k] = load_row(rd, min(r, M - 1));
+        live[k] = i < nrows && (!rl || rl[r]);
+        R[k] = load_row(rd, r);
         wu[k] = wv[k] = wr[k] = 0.f;
-        if (WIN && r < M) { wu[k] = a.win_uvr[(ro + r) * 3]; wv[k] = a.win_uvr[(ro + r) * 3 + 1]; wr[k] = a.win_uvr[(ro + r) * 3 + 2]; }
+        if (WIN && i < nrows) { wu[k] = a.win_uvr[(ro + r) * 3]; wv[k] = a.win_uvr[(ro + r) * 3 + 1]; wr[k] = a.win_uvr[(ro + r) * 3 + 2]; }
     }
     for (int c0 = 0; c0 < N; c0 += COL_TILE) {
         const int nc = min(COL_TILE, N - c0);
@@ -275,51 +337,75 @@ __global__ void __launch_bounds__(M_THREADS) k_shortlist(GreedyArgs a, int T)
                 if (m) {
                     if (hit) {
                         const int pos = cnt[k] + __popc(m & ((1u << lane) - 1u));
-                        if (pos < SVO_SHORT_CAP) *short_slot(a, ro + r0 + k, pos) = ((uint32_t)d[k] << 16) | (uint32_t)(c0 + j);
+                        if (pos < SVO_SHORT_CAP) *short_slot(a, ro + rid[k], pos) = ((uint32_t)d[k] << 16) | (uint32_t)(c0 + j);
                     }
                     cnt[k] += __popc(m);
                 }
             }
         }
     }
-    // Pass 2 prunes each finished list to what can influence the row's decision: a row claims only a column
-    // with d < 30, and the ratio test second > 2 * best can only be broken by an entry with d <= 2 * best
-    // <= 2 * dmax, dmax = the largest d < 30 in the list.  Entries above that bound (the bulk of a T = 60
-    // list) are dropped, and a list without any d < 30 entry is emptied.  Overflowed lists are left alone
-    // (they are incomplete; the resolver re-scans those rows exhaustively).
     if (a.mode == SVO_GREEDY_PASS2) {
         __syncwarp();
 #pragma unroll
-        for (int k = 0; k < SL_ROWS_PER_WARP; ++k) {
-            const int c = cnt[k];
-            if (!live[k] || c == 0 || c > SVO_SHORT_CAP) continue;   // warp-uniform
-            uint32_t e[SVO_SHORT_CAP / 32];
-            int dmax = -1;
-#pragma unroll
-            for (int t = 0; t < SVO_SHORT_CAP / 32; ++t) {
-                e[t] = lane + 32 * t < c ? *short_slot(a, ro + r0 + k, lane + 32 * t) : 0xffffffffu;
-                const int d = (int)(e[t] >> 16);
-                if (d < 30) dmax = max(dmax, d);
-            }
-            dmax = __reduce_max_sync(0xffffffffu, dmax);
-            __syncwarp();
-            int n = 0;
-            if (dmax >= 0) {
-#pragma unroll
-                for (int t = 0; t < SVO_SHORT_CAP / 32; ++t) {
-                    const bool keep = e[t] != 0xffffffffu && (int)(e[t] >> 16) <= 2 * dmax;
-                    const uint32_t m = __ballot_sync(0xffffffffu, keep);
-                    if (keep) *short_slot(a, ro + r0 + k, n + __popc(m & ((1u << lane) - 1u))) = e[t];
-                    n += __popc(m);
-                }
-            }
-            cnt[k] = n;
-        }
+        for (int k = 0; k < SL_ROWS_PER_WARP; ++k)
+            if (live[k]) cnt[k] = prune_list(a, ro + rid[k], cnt[k], lane);   // warp-uniform
     }
     if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < SL_ROWS_PER_WARP; ++k)
-            if (r0 + k < M) a.short_cnt[ro + r0 + k] = live[k] ? cnt[k] : 0;
+            if (r0 + k < nrows) a.short_cnt[ro + rid[k]] = live[k] ? cnt[k] : 0;
+    }
+}
+
+// Batch pass 2, rows whose distances k_pairs already computed (reuse_list): threshold the row of the u8 matrix,
+// 4 columns per lane and step, 8 steps in flight (the matrix is not cache resident).  One warp per row.
+__global__ void __launch_bounds__(M_THREADS) k_reuse(GreedyArgs a, int T)
+{
+    const int f = blockIdx.y;
+    const int N = set_count(a.cols, f);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t ro = (size_t)f * a.rows.stride_rows;
+    const int nre = a.list_cnt[2 * f + 1];
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int i = blockIdx.x * M_WARPS + warp; i < nre; i += gridDim.x * M_WARPS) {
+    const int e = a.reuse_list[ro + i], r = e & 0xffff, pr = e >> 16;
+    const uint8_t *drow = a.dmat + (size_t)f * a.dmat_frame_stride + (size_t)pr * a.dmat_pitch;
+    int cnt = 0;
+    for (int cb = 0; cb < N; cb += 8 * 128) {
+        uint32_t w8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int col = cb + 128 * u + 4 * lane;
+            w8[u] = col < N ? __ldg(reinterpret_cast<const uint32_t *>(drow + col)) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int col = cb + 128 * u + 4 * lane;
+            uint32_t w = w8[u];
+            if (col + 4 > N && col < N) w |= 0xffffffffu << (8 * (N - col));          // columns past N hold no distances
+            const bool any = ((w - (uint32_t)T * 0x01010101u) & ~w & 0x80808080u) != 0;   // some byte < T (T <= 128)
+            if (!__any_sync(0xffffffffu, any)) continue;
+            int before = 0, tot = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t m = __ballot_sync(0xffffffffu, (int)((w >> (8 * q)) & 0xffu) < T);
+                before += __popc(m & lt); tot += __popc(m);
+            }
+            int pos = cnt + before;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int d = (int)((w >> (8 * q)) & 0xffu);
+                if (d < T) {
+                    if (pos < SVO_SHORT_CAP) *short_slot(a, ro + r, pos) = ((uint32_t)d << 16) | (uint32_t)(col + q);
+                    ++pos;
+                }
+            }
+            cnt += tot;
+        }
+    }
+    __syncwarp();
+    cnt = prune_list(a, ro + r, cnt, lane);
+    if (lane == 0) a.short_cnt[ro + r] = cnt;
     }
 }
 
@@ -866,12 +952,18 @@ void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStrea
     if (maxM <= 0 || nframes <= 0) return;
     const int mx = maxM > maxN ? maxM : maxN;
     dim3 gi((mx + 255) / 256, nframes);
+    if (a.need_list) cudaMemsetAsync(a.list_cnt, 0, sizeof(int) * 2 * nframes, st);
     k_greedy_init<<<gi, 256, 0, st>>>(a, 1);
     const int T = a.mode == SVO_GREEDY_PASS1 ? 15 : 60;
     dim3 gs((maxM + M_WARPS * SL_ROWS_PER_WARP - 1) / (M_WARPS * SL_ROWS_PER_WARP), nframes);
     if (ev0) cudaEventRecord(ev0, st);
     if (a.win_uvr) k_shortlist<true><<<gs, M_THREADS, 0, st>>>(a, T);
     else k_shortlist<false><<<gs, M_THREADS, 0, st>>>(a, T);
+    if (a.need_list && a.dmat) {
+        const int gx = (maxM + M_WARPS - 1) / M_WARPS;
+        k_reuse<<<dim3(gx < 24 ? gx : 24, nframes), M_THREADS, 0, st>>>(a, T);   // warps stride over the frame's reuse list
+        ++*launches;
+    }
     if (ev1) cudaEventRecord(ev1, st);
     // shared memory: two claim-time arrays + pre-claimed bytes + as many short-list entries as fit
     const int colsA = (maxN + 3) & ~3;

@@ -28,6 +28,7 @@ struct FrameBufs {           // per-frame (stereo pair) device arrays
     int *p2_best_idx, *p2_best, *p2_second; uint8_t *p2_row_claimed;
     uint32_t *shortlist, *shortlist_hi; int *short_cnt;
     int *res_rows, *res_off, *res_want, *res_perm;
+    int *need_list, *reuse_list, *list_cnt;
     uint8_t *dmat; uint32_t *bf_key; int dmat_pitch; size_t dmat_frame_stride;   // fused pass-1 front (batch path)
     float *u_right, *depth; int *match_r, *sad, *n_stereo;
     int *row_off; uint16_t *row_list; int row_list_stride;
@@ -231,6 +232,7 @@ int alloc_frames(svo_ctx *ctx, FrameBufs &f, int nframes, int col_stride, int ro
     TRY(dalloc(ctx, &f.p2_row_claimed, R));
     TRY(dalloc(ctx, &f.shortlist, R * 32)); TRY(dalloc(ctx, &f.shortlist_hi, R * (SVO_SHORT_CAP - 32))); TRY(dalloc(ctx, &f.short_cnt, R));
     TRY(dalloc(ctx, &f.res_rows, R)); TRY(dalloc(ctx, &f.res_off, R)); TRY(dalloc(ctx, &f.res_want, R)); TRY(dalloc(ctx, &f.res_perm, R));
+    TRY(dalloc(ctx, &f.need_list, R)); TRY(dalloc(ctx, &f.reuse_list, R)); TRY(dalloc(ctx, &f.list_cnt, 2 * F));
     TRY(dalloc(ctx, &f.u_right, C)); TRY(dalloc(ctx, &f.depth, C)); TRY(dalloc(ctx, &f.match_r, C));
     TRY(dalloc(ctx, &f.sad, C)); TRY(dalloc(ctx, &f.n_stereo, F));
     {   // a right keypoint is a candidate for rows floor(y - r) .. ceil(y + r), r = 2 * scale[octave]
@@ -375,6 +377,14 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
         ga.rows.tab = reinterpret_cast<const uint8_t *const *>(&L.d_fp->map);
         ga.mode = SVO_GREEDY_PASS2; ga.row_base = 0; ga.row_base_arr = d_nprev;
         ga.fp = L.d_fp; ga.use_live = 0; ga.use_map_prev = any_prev ? 1 : 0;
+        ga.need_list = fb.need_list + (size_t)L.frame0 * R; ga.reuse_list = fb.reuse_list + (size_t)L.frame0 * R;
+        ga.list_cnt = fb.list_cnt + 2 * (size_t)L.frame0;
+        if (fused) {
+            ga.dmat = fb.dmat + (size_t)L.frame0 * fb.dmat_frame_stride; ga.dmat_frame_stride = fb.dmat_frame_stride;
+            ga.dmat_pitch = fb.dmat_pitch;
+            ga.prev = make_set(nullptr, d_nprev, 1, R, 0);
+            ga.prev.tab = reinterpret_cast<const uint8_t *const *>(&L.d_fp->prev);
+        }
         ga.prev_row_claimed = fb.p1_row_claimed + (size_t)L.frame0 * R; ga.prev_stride = R;
         ga.best_idx = nullptr; ga.best = nullptr; ga.second = nullptr;
         ga.row_claimed = fb.p2_row_claimed + (size_t)L.frame0 * R; ga.row_bad = nullptr;

@@ -142,6 +142,13 @@ struct GreedyArgs {
     const int *map_prev_row;      // [frame][rows.stride_rows] or NULL (pass 2)
     const FramePtrs *fp;          // batch path: row_live / map_prev_row come from fp[frame] (use_live / use_map_prev)
     int use_live, use_map_prev;
+    // batch pass 2: work lists built by k_greedy_init (NULL: every row goes through k_shortlist), the u8
+    // previous x current distance matrix k_pairs wrote (NULL: none) and the previous-frame set, so that rows
+    // repeating a pass-1 row (map_prev_row) reuse its distances
+    int *need_list, *reuse_list;  // [frame][rows.stride_rows]
+    int *list_cnt;                // [frame][2]
+    const uint8_t *dmat; size_t dmat_frame_stride; int dmat_pitch;
+    MatchSet prev;
     const uint8_t *prev_row_claimed;  // [frame][prev stride] (pass 2, with map_prev_row)
     int prev_stride;
     uint8_t *claimed;             // [frame][cols.stride_rows] in/out

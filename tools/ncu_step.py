@@ -35,6 +35,8 @@ def main(path, want):
         if not sel:
             continue
         st = sel[-1]
+        if len(sel) > 1 and len(sel[-2]) > len(st):
+            st = sel[-2]            # the capture limit cut the last step short
         tot = sum(t for _, _, t in st)
         print("---- step with %d frame(s): %d launches, %.1f us total, %.1f us/frame" % (nf, len(st), tot, tot / nf))
         for n, g, t in st:
