@@ -186,13 +186,19 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(Bufs b, Geom g, int slot0
                 if (x < L.x0 - 1) pass &= 0xffffffffu << (8 * (L.x0 - 1 - x));        // first quad of the row
                 if (x + 3 > L.x1) pass &= 0xffffffffu >> (8 * (x + 3 - L.x1));        // last quad of the row
             }
+            // compaction: 4-bit hit mask per lane, warp prefix sum of the hit counts from three ballots
+            // (a count is at most 4), then up to four stores
+            const uint32_t nib = (((pass >> 7) & 0x01010101u) * 0x10204080u) >> 28;
+            const int hc = __popc(nib);
+            const uint32_t b0 = __ballot_sync(0xffffffffu, hc & 1), b1 = __ballot_sync(0xffffffffu, hc & 2),
+                           b2 = __ballot_sync(0xffffffffu, hc & 4);
+            if ((b0 | b1 | b2) == 0) { ch += nwarps; while (ch >= cpr) { ch -= cpr; ++r; } continue; }
+            int pos = nmine + __popc(b0 & ltm) + 2 * __popc(b1 & ltm) + 4 * __popc(b2 & ltm);
+            const int p0 = r * sp + x;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const bool ok = (pass >> (8 * k + 7)) & 1u;
-                const uint32_t m = __ballot_sync(0xffffffffu, ok);
-                if (ok) mine[nmine + __popc(m & ltm)] = (uint16_t)(r * sp + x + k);
-                nmine += __popc(m);
-            }
+            for (int k = 0; k < 4; ++k)
+                if (nib & (1u << k)) mine[pos++] = (uint16_t)(p0 + k);
+            nmine += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
             ch += nwarps;
             while (ch >= cpr) { ch -= cpr; ++r; }
         }

@@ -961,7 +961,7 @@ void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStrea
     else k_shortlist<false><<<gs, M_THREADS, 0, st>>>(a, T);
     if (a.need_list && a.dmat) {
         const int gx = (maxM + M_WARPS - 1) / M_WARPS;
-        k_reuse<<<dim3(gx < 24 ? gx : 24, nframes), M_THREADS, 0, st>>>(a, T);   // warps stride over the frame's reuse list
+        k_reuse<<<dim3(gx < 128 ? gx : 128, nframes), M_THREADS, 0, st>>>(a, T);   // warps stride over the frame's reuse list
         ++*launches;
     }
     if (ev1) cudaEventRecord(ev1, st);
