@@ -49,8 +49,12 @@ def kp_cap(nf):
 
 
 def level_sizes():
-    # cv::ORB geometry for 1241x376, scale 1.2, 8 levels
-    return [(1241, 376), (1034, 313), (862, 261), (718, 218), (598, 181), (499, 151), (416, 126), (346, 105)]
+    # cv::ORB geometry, scale 1.2: cvRound(size / (float)pow(1.2, l)); 1241x376 gives the SURVEY.md section 8 table
+    out = []
+    for l in range(NLEVELS):
+        s = float(np.float32(pow(float(np.float32(1.2)), l)))
+        out.append((int(np.rint(np.float32(W_IMG) / np.float32(s))), int(np.rint(np.float32(H_IMG) / np.float32(s)))))
+    return out
 
 
 def algorithmic_bytes_per_image():
@@ -139,7 +143,7 @@ def run_gpu(args, rank, world, local_rank):
     grp = replicas.Group(backend="nccl", device=dev)   # barrier + max-over-ranks only; no data-path collective
     B, P = args.batch, args.pool
     ctx = svo.Context(W_IMG, H_IMG, nfeatures=NFEAT, nlevels=NLEVELS, max_batch=B, lanes=args.lanes,
-                      max_rows=MAP_ROWS, device=dev)
+                      max_rows=max(MAP_ROWS, kp_cap(NFEAT)), device=dev)
     # ---- synthetic sequence (one per rank): pool of P distinct stereo frames in pinned memory
     seq_id = replicas.assign_sequences(world, world, rank)[0]
     seq = synth.Sequence((H_IMG, W_IMG), seed=seq_id)
@@ -296,15 +300,17 @@ def run_gpu(args, rank, world, local_rank):
                     "peak_gpopc_s": peak_popc / 1e9, "frac": pairs * per_pair / (dur_ms * 1e-3) / peak_popc,
                     "peak_source": "148 SMs x 16 POPC/clk/SM x sampled SM clock"}
         h2d = B * (2 * W_IMG * H_IMG + int(n_prev.mean()) * 33 + MAP_ROWS * 36 + 16)
-        d2h = 2 * B * (K * 56 + 8) + B * (K * 21 + 4) + B * MAP_ROWS * 14
+        d2h = 2 * B * (K * 56 + 8) + B * (K * 21 + 4) + B * max(MAP_ROWS, K) * 14
         out = {
             "metric": METRIC, "value": frames_total / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (f32 for response, angle, sub-pixel)",
             "data": "synthetic",
-            "config": {"workload": "configs[1]: synthetic KITTI-shape 1241x376 stereo sequence, KITTI04-12 intrinsics, "
-                                   "2000 ORB features / 8 levels / 1.2, full front-end: extract L+R, sparse stereo + SAD, "
-                                   "BF match vs previous frame, greedy pass 1 + pass 2 vs 5000-row local map",
+            "config": {"workload": "%s: synthetic %s %dx%d stereo sequence, KITTI04-12 intrinsics, "
+                                   "%d ORB features / 8 levels / 1.2, full front-end: extract L+R, sparse stereo + SAD, "
+                                   "BF match vs previous frame, greedy pass 1 + pass 2 vs %d-row local map"
+                                   % ("configs[1]" if (W_IMG, H_IMG, NFEAT, MAP_ROWS) == (1241, 376, 2000, 5000) else "non-headline configuration",
+                                      "KITTI-shape" if (W_IMG, H_IMG) == (1241, 376) else "high-res", W_IMG, H_IMG, NFEAT, MAP_ROWS),
                        "frames_per_step": B, "lanes": args.lanes, "pool_frames": P,
                        "l2": "inputs larger than L2: %d-frame pool = %.0f MB of images + %.0f MB of descriptors cycled"
                              % (P, 2 * P * img_b / 1e6, P * (K * 33 + MAP_ROWS * 36) / 1e6),
@@ -443,7 +449,14 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-frames", type=int, default=0, help="--impl reference: frames per step (default: one per host core)")
+    # other BASELINE.json configurations (parity-test / breakdown cases, not the headline): e.g. configs[2]
+    # `--features 4000`, configs[3] `--width 2560 --height 720 --features 8000 --batch 8 --pool 48`
+    ap.add_argument("--width", type=int, default=1241)
+    ap.add_argument("--height", type=int, default=376)
+    ap.add_argument("--features", type=int, default=2000)
+    ap.add_argument("--map-rows", type=int, default=5000)
     args = ap.parse_args()
+    globals().update(W_IMG=args.width, H_IMG=args.height, NFEAT=args.features, MAP_ROWS=args.map_rows)
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
