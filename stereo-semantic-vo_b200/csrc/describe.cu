@@ -243,13 +243,15 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(Bufs b, Geom g, in
     const uint8_t *ctr = img + (size_t)y * sp + x;
     const int u = lane - 15;
     const int vm = lane < 31 ? c_umax[u < 0 ? -u : u] : -1;
+    // rows +v and -v are taken together (as cv::ORB's IC_Angle does): sum += a + b, m01 += v * (a - b)
     int sum = 0, m01 = 0;
+    if (0 <= vm) sum = ctr[u];
 #pragma unroll
-    for (int v = -15; v <= 15; ++v) {
-        if ((v < 0 ? -v : v) <= vm) {
-            const int val = ctr[v * sp + u];
-            sum += val;
-            m01 += v * val;
+    for (int v = 1; v <= 15; ++v) {
+        if (v <= vm) {
+            const int a = ctr[v * sp + u], c = ctr[-v * sp + u];
+            sum += a + c;
+            m01 += v * (a - c);
         }
     }
     const int m10 = __reduce_add_sync(0xffffffffu, u * sum);
