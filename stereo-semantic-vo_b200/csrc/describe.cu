@@ -7,6 +7,7 @@
 // operation separately and that is what the oracle is pinned to.
 #include "svo_internal.cuh"
 #include <float.h>
+#include <cuda/barrier>
 
 #define DESC_WARPS 8
 
@@ -103,55 +104,74 @@ __device__ __forceinline__ float2 add_prod(float2 acc, float2 prod)
 {
     return make_float2(__fadd_rn(acc.x, prod.x), __fadd_rn(acc.y, prod.y));
 }
+#define BLUR_RB (4 * 128 + 32)   // staged bytes per tile row: 128 quads + a 16-byte aligned halo on each side
+
 __global__ void __launch_bounds__(BLUR_THREADS) k_blur(Bufs b, Geom g, int slot0)
 {
+    // The tile's source rows (32 + 6 halo rows, reflect-101 at the image top/bottom folded into the row choice)
+    // are staged in shared memory by TMA bulk copies, one per row, all completing on one mbarrier: the kernel
+    // was bound by the latency of its global loads (ncu: long-scoreboard stalls at 28 % occupancy), shared
+    // memory removes that from the per-row loop.
+    __shared__ __align__(128) uint8_t tile[(BLUR_ROWS + 6) * BLUR_RB];
+    __shared__ cuda::barrier<cuda::thread_scope_block> bar;
     int blk = blockIdx.x, l = 0;
     while (l + 1 < g.nlevels && blk >= g.lv[l + 1].blur_tile_off) ++l;
     const int Lw = g.lv[l].w, Lh = g.lv[l].h, sp = g.lv[l].pitch, Loff = g.lv[l].off;
+    const int tiles_x = g.lv[l].blur_tiles_x, tq = g.lv[l].blur_tq;
     blk -= g.lv[l].blur_tile_off;
-    const int quads = (Lw + 3) >> 2;
-    const int item = blk * BLUR_THREADS + threadIdx.x;
-    const int strip = item / quads, cg = item - strip * quads;
-    const int y0 = strip * BLUR_ROWS, x0 = cg << 2;
-    if (y0 >= Lh) return;
+    const int strip = blk / tiles_x, tx = blk - strip * tiles_x;
+    const int y0 = strip * BLUR_ROWS;
+    const int rows = min(BLUR_ROWS, Lh - y0);
+    const int nst = rows + 6;
+    const int xa = 4 * tq * tx;                                   // first pixel of the tile (multiple of 16)
+    const int xs = max(xa - 16, 0), xe = min(xa + 4 * tq + 16, sp);
+    const uint32_t rowbytes = (uint32_t)(xe - xs);                // multiple of 16
     const int slot = slot0 + blockIdx.y;
     const uint8_t *__restrict__ img = b.pyr + (size_t)slot * g.pyr_bytes + Loff;
     uint8_t *__restrict__ out = b.blur + (size_t)slot * g.pyr_bytes + Loff;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        init(&bar, BLUR_THREADS);
+        cuda::device::experimental::fence_proxy_async_shared_cta();
+    }
+    __syncthreads();
+    cuda::barrier<cuda::thread_scope_block>::arrival_token tok;
+    if (tid < 32) {
+        for (int r = tid; r < nst; r += 32)
+            cuda::device::memcpy_async_tx(tile + r * BLUR_RB, img + (size_t)reflect101(y0 + r - 3, Lh) * sp + xs,
+                                          cuda::aligned_size_t<16>(rowbytes), bar);
+    }
+    if (tid == 0) tok = cuda::device::barrier_arrive_tx(bar, 1, rowbytes * (uint32_t)nst);
+    else tok = bar.arrive();
     float2 gk[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) gk[k] = make_float2(__uint_as_float(c_gauss[k]), __uint_as_float(c_gauss[k]));
     const float2 two23 = make_float2(-8388608.f, -8388608.f), rnd = make_float2(12582912.f, 12582912.f);
+    const int x0 = xa + 4 * tid;
+    const bool active = tid < tq && x0 < Lw;
     const bool interior = x0 >= 4 && x0 + 6 < Lw;   // bytes x0-3 .. x0+6 all inside the row
+    const int lx = x0 - xs;
     float2 win[7][2];                               // horizontal sums of the last 7 rows: pixels (0,1) and (2,3)
 #pragma unroll
     for (int k = 0; k < 7; ++k) win[k][0] = win[k][1] = make_float2(0.f, 0.f);
-    const int rows = min(BLUR_ROWS, Lh - y0);
-    // the three words of the NEXT window row are fetched one iteration ahead (software pipelining: the
-    // kernel is otherwise bound by the latency of these loads)
-    uint32_t n0 = 0, n1 = 0, n2 = 0;
-    if (interior) {
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(img + (size_t)reflect101(y0 - 3, Lh) * sp + x0 - 4);
-        n0 = w[0]; n1 = w[1]; n2 = w[2];
-    }
-    for (int r0 = 0; r0 < rows + 6; r0 += 7) {
+    bar.wait(std::move(tok));
+    if (!active) return;
+    for (int r0 = 0; r0 < nst; r0 += 7) {
 #pragma unroll
         for (int k = 0; k < 7; ++k) {
             const int r = r0 + k;                       // window row r <-> image row y0 + r - 3
-            if (r < rows + 6) {
+            if (r < nst) {
+                const uint8_t *row = tile + r * BLUR_RB;
                 float m[10];                            // 2^23 + pixel x0-3+j
                 if (interior) {
-                    const uint32_t w0 = n0, w1 = n1, w2 = n2;
-                    if (r + 1 < rows + 6) {
-                        const uint32_t *w = reinterpret_cast<const uint32_t *>(img + (size_t)reflect101(y0 + r - 2, Lh) * sp + x0 - 4);
-                        n0 = w[0]; n1 = w[1]; n2 = w[2];
-                    }
+                    const uint32_t *w = reinterpret_cast<const uint32_t *>(row + lx - 4);
+                    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
                     m[0] = byte_magic(w0, 1); m[1] = byte_magic(w0, 2); m[2] = byte_magic(w0, 3);
                     m[3] = byte_magic(w1, 0); m[4] = byte_magic(w1, 1); m[5] = byte_magic(w1, 2); m[6] = byte_magic(w1, 3);
                     m[7] = byte_magic(w2, 0); m[8] = byte_magic(w2, 1); m[9] = byte_magic(w2, 2);
                 } else {
-                    const uint8_t *row = img + (size_t)reflect101(y0 + r - 3, Lh) * sp;
 #pragma unroll
-                    for (int j = 0; j < 10; ++j) m[j] = __uint_as_float(0x4B000000u | row[reflect101(x0 - 3 + j, Lw)]);
+                    for (int j = 0; j < 10; ++j) m[j] = __uint_as_float(0x4B000000u | row[reflect101(x0 - 3 + j, Lw) - xs]);
                 }
                 float2 P[9];                            // P[t] = pixels (x0-3+t, x0-2+t)
 #pragma unroll

@@ -200,9 +200,13 @@ int build_geometry(svo_ctx *ctx)
         L.cap2 = 4 * L.quota + 1024 < L.cand_cap ? 4 * L.quota + 1024 : L.cand_cap;
         L.off2 = off2; off2 += align_up(L.cap2, 4);
         L.tab_off = tab_off; if (l) tab_off += L.w + L.h;
-        L.blur_tiles_x = (L.w + 3) / 4;                      // quads per row
-        L.blur_tile_off = tiles;                             // first blur CTA of the level (128 strips of 4 x 32 px each)
-        tiles += (L.blur_tiles_x * ((L.h + 31) / 32) + 127) / 128;
+        {   // blur tiles: 32 rows x blur_tq quads, the quads of a row split evenly over the fewest tiles of <= 128 quads
+            const int quads = (L.w + 3) / 4;
+            L.blur_tiles_x = (quads + 127) / 128;
+            L.blur_tq = align_up((quads + L.blur_tiles_x - 1) / L.blur_tiles_x, 4);
+            L.blur_tile_off = tiles;                         // first blur CTA of the level
+            tiles += L.blur_tiles_x * ((L.h + 31) / 32);
+        }
         g.fast_bands += L.nbands;
     }
     if (lw[0] >= 4096 || lh[0] >= 4096) return fail(ctx, SVO_E_INVALID, "images up to 4095x4095 are supported");

@@ -38,7 +38,8 @@ struct LevelGeom {
     int off2;          // entry offset of key2/val2
     int tab_off;       // offset of this level's resize tables (x table then y table), level >= 1
     int blur_tile_off; // first blur tile index of this level
-    int blur_tiles_x;  // blur tiles per row of tiles
+    int blur_tiles_x;  // blur tiles per strip of 32 rows
+    int blur_tq;       // pixel quads per blur tile (multiple of 4, <= 128)
 };
 
 struct Geom {
