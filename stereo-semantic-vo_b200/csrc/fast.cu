@@ -219,9 +219,10 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(Bufs b, Geom g, int slot0
         if (r < 1 || r > nrow || x < L.x0 || x >= L.x1) continue;
         const uint8_t *q = sc + pos;
         const int s = q[0];
-        if (s > q[-1] && s > q[1] && s > q[-sp - 1] && s > q[-sp] && s > q[-sp + 1] &&
-            s > q[sp - 1] && s > q[sp] && s > q[sp + 1])
-            atomicOr(&mask[(r - 1) * wpr + ((x - L.x0) >> 5)], 1u << ((x - L.x0) & 31));
+        // branch-free: the largest of the 8 neighbours (a short-circuit chain diverges on every comparison)
+        const int m = __vimax3_s32(__vimax3_s32(q[-sp - 1], q[-sp], q[-sp + 1]), __vimax3_s32(q[-1], q[1], q[sp - 1]),
+                                   max((int)q[sp], (int)q[sp + 1]));
+        if (s > m) atomicOr(&mask[(r - 1) * wpr + ((x - L.x0) >> 5)], 1u << ((x - L.x0) & 31));
     }
     __syncthreads();
     // D. raster-ordered emission from the bitmap (words are in raster order)
