@@ -22,6 +22,9 @@ __constant__ uint32_t c_gauss[7] = {0x3d8fafb1u, 0x3e06387eu, 0x3e434a39u, 0x3e5
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(DESC_WARPS * 32) k_harris(Bufs b, Geom g, int slot0)
 {
+    // per warp: the candidate's 9x9 patch as 9 rows of three aligned words (the 9 columns x-4..x+4 always lie
+    // inside three words), fetched with 27 word loads instead of 8 byte loads for each of the 49 positions
+    __shared__ uint32_t patch[DESC_WARPS][9 * 3 + 1];
     const int l = blockIdx.y, slot = slot0 + blockIdx.z;
     const LevelGeom &L = g.lv[l];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -35,19 +38,27 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_harris(Bufs b, Geom g, int 
     float *key2 = b.key2 + (size_t)slot * g.total2 + L.off2;
     uint32_t *val2 = b.val2 + (size_t)slot * g.total2 + L.off2;
     const int sp = L.pitch;
+    const uint8_t *pb = reinterpret_cast<const uint8_t *>(patch[warp]);
     for (int c = blockIdx.x * DESC_WARPS + warp; c < n; c += gridDim.x * DESC_WARPS) {
         const uint32_t e = cval[c];
         const int x = unpack_x(e), y = unpack_y(e);
+        const int xw = (x - 4) & ~3, xo = (x - 4) & 3;          // first word column, byte offset of column x-4 in it
+        __syncwarp();
+        if (lane < 27) {
+            const int r = lane / 3, w = lane - 3 * r;
+            patch[warp][lane] = *reinterpret_cast<const uint32_t *>(img + (size_t)(y - 4 + r) * sp + xw + 4 * w);
+        }
+        __syncwarp();
         int a = 0, bb = 0, cc = 0;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int k = lane + 32 * r;
             if (k < 49) {
-                const int dy = k / 7 - 3, dx = k % 7 - 3;
-                const uint8_t *p = img + (size_t)(y + dy) * sp + (x + dx);
-                const int p00 = p[-sp - 1], p01 = p[-sp], p02 = p[-sp + 1];
+                const int dy = k / 7, dx = k % 7;                // block position: rows dy..dy+2, columns dx..dx+2 of the patch
+                const uint8_t *p = pb + (dy + 1) * 12 + xo + dx + 1;
+                const int p00 = p[-13], p01 = p[-12], p02 = p[-11];
                 const int p10 = p[-1], p12 = p[1];
-                const int p20 = p[sp - 1], p21 = p[sp], p22 = p[sp + 1];
+                const int p20 = p[11], p21 = p[12], p22 = p[13];
                 const int Ix = (p12 - p10) * 2 + (p02 - p00) + (p22 - p20);
                 const int Iy = (p21 - p01) * 2 + (p20 - p00) + (p22 - p02);
                 a += Ix * Ix; bb += Iy * Iy; cc += Ix * Iy;
