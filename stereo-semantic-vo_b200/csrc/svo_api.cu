@@ -114,6 +114,7 @@ int dalloc(svo_ctx *ctx, T **p, size_t n)
     cudaError_t e = cudaMalloc(&q, n * sizeof(T));
     if (e != cudaSuccess) return fail(ctx, SVO_E_NOMEM, "cudaMalloc(%zu) -> %s", n * sizeof(T), cudaGetErrorString(e));
     ctx->dev_allocs.push_back(q);
+    cudaMemset(q, 0, n * sizeof(T));   // defined contents: vector loads may touch (and ignore) entries past a list's end
     *p = (T *)q;
     return SVO_OK;
 }
