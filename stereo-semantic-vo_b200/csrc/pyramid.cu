@@ -8,39 +8,63 @@
 // px(l-1) read + px(l) written.
 #include "svo_internal.cuh"
 
-__global__ void __launch_bounds__(256) k_resize(Bufs b, Geom g, int l, int slot0)
+
+// One thread produces a 4-pixel wide, `rs` rows tall column strip (8 rows on the large levels, 4 on the small ones,
+// which need the parallelism more).  The horizontal Q8 pass of a source row is
+// shared by the two output rows that straddle it: walking down the strip, the lower source row of one output row
+// is usually the upper source row of the next (scale 1.2: 1.2 horizontal passes per output row instead of 2),
+// and the four x-table entries are decoded once per strip.  Same integer arithmetic as the per-pixel form.
+__global__ void __launch_bounds__(256) k_resize(Bufs b, Geom g, int l, int slot0, int rs)
 {
     const LevelGeom &d = g.lv[l];
     const LevelGeom &s = g.lv[l - 1];
     const int qpr = d.pitch >> 2;  // quads per (padded) row
+    const int strips = (d.h + rs - 1) / rs;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= qpr * d.h) return;
-    const int y = q / qpr, x = (q - y * qpr) << 2;
+    if (q >= qpr * strips) return;
+    const int st = q / qpr, x = (q - st * qpr) << 2;
+    const int y0 = st * rs, y1 = min(y0 + rs, d.h);
     const size_t base = (size_t)(slot0 + blockIdx.y) * g.pyr_bytes;
     const uint8_t *src = b.pyr + base + s.off;
     uint8_t *dst = b.pyr + base + d.off;
     const uint32_t *xt = b.rtab + d.tab_off;
-    const uint32_t ty = xt[d.w + y];
-    const int yo = ty >> 9;
-    const uint32_t wy1 = ty & 511u, wy0 = 256u - wy1;
-    const uint8_t *r0 = src + (size_t)yo * s.pitch;
-    const uint8_t *r1 = wy1 ? r0 + s.pitch : r0;
-    uint32_t out = 0;
+    const int sp = s.pitch;
+    int i0[4], i1[4];
+    uint32_t wx0[4], wx1[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int xx = x + k;
-        if (xx < d.w) {
-            const uint32_t tx = xt[xx];
-            const int i0 = tx >> 9;
-            const uint32_t wx1 = tx & 511u, wx0 = 256u - wx1;
-            const int i1 = wx1 ? i0 + 1 : i0;
-            const uint32_t h0 = r0[i0] * wx0 + r0[i1] * wx1;
-            const uint32_t h1 = r1[i0] * wx0 + r1[i1] * wx1;
-            const uint32_t v = (h0 * wy0 + h1 * wy1 + 32768u) >> 16;
-            out |= v << (8 * k);
-        }
+        const uint32_t tx = x + k < d.w ? xt[x + k] : 0u;
+        i0[k] = tx >> 9; wx1[k] = tx & 511u; wx0[k] = 256u - wx1[k];
+        i1[k] = wx1[k] ? i0[k] + 1 : i0[k];
+        if (x + k >= d.w) { wx0[k] = 0; wx1[k] = 0; }          // padding columns hold 0
     }
-    *reinterpret_cast<uint32_t *>(dst + (size_t)y * d.pitch + x) = out;
+    auto hrow = [&](int yy, uint32_t (&h)[4]) {
+        const uint8_t *r = src + (size_t)yy * sp;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h[k] = r[i0[k]] * wx0[k] + r[i1[k]] * wx1[k];
+    };
+    uint32_t ha[4], hb[4];
+    int ya = -1, ybr = -1;                                     // source rows currently held in ha / hb
+    for (int y = y0; y < y1; ++y) {
+        const uint32_t ty = xt[d.w + y];
+        const int yo = ty >> 9;
+        const uint32_t wy1 = ty & 511u, wy0 = 256u - wy1;
+        const int yn = wy1 ? yo + 1 : yo;
+        if (yo == ybr) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ha[k] = hb[k];
+        } else if (yo != ya) hrow(yo, ha);
+        ya = yo;
+        if (yn == yo) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) hb[k] = ha[k];
+        } else hrow(yn, hb);
+        ybr = yn;
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) out |= ((ha[k] * wy0 + hb[k] * wy1 + 32768u) >> 16) << (8 * k);
+        *reinterpret_cast<uint32_t *>(dst + (size_t)y * d.pitch + x) = out;
+    }
 }
 
 // Level 0 is read where it lies in device memory (the caller's device buffer, or the lane's landing zone
@@ -78,9 +102,10 @@ void launch_unpack(const Bufs &b, const Geom &g, int slot0, int nimg, const Fram
 void launch_pyramid(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches)
 {
     for (int l = 1; l < g.nlevels; ++l) {
-        const int quads = (g.lv[l].pitch >> 2) * g.lv[l].h;
+        const int rs = (size_t)g.lv[l].w * g.lv[l].h * nimg >= (size_t)8 << 20 ? 8 : 4;   // fewer rows per thread when the launch is small
+        const int quads = (g.lv[l].pitch >> 2) * ((g.lv[l].h + rs - 1) / rs);
         dim3 grid((quads + 255) / 256, nimg);
-        k_resize<<<grid, 256, 0, st>>>(b, g, l, slot0);
+        k_resize<<<grid, 256, 0, st>>>(b, g, l, slot0, rs);
         ++*launches;
     }
 }
