@@ -275,11 +275,14 @@ def run_gpu(args, rank, world, local_rank):
         kernels = {k: stage.get(k, 0.0) for k in ("pyramid", "fast", "select1", "harris", "select2", "blur", "describe", "stereo", "match")}
         nimg = 2 * B
         npv = float(n_prev.mean())
+        # pass-2 rows k_shortlist really scans: rows linked to a pass-1 row are skipped or served from the pass-1
+        # distance matrix (k_reuse); in this workload those are exactly the rows with map_prev_row >= 0
+        need_rows = float((h_mpr < 0).sum()) / P
         # single kernels bracketed by their own events on the lane's stream (DESIGN.md section 4 lists the bytes)
         single = {"k_fast": ("fast", ab["fast"] * nimg), "k_blur": ("blur", ab["blur"] * nimg),
                   "k_describe": ("describe", ab["describe"] * nimg), "k_harris": ("harris", ab["harris"] * nimg),
                   "k_pairs": ("k_pairs", B * (npv + NFEAT) * 32 + B * npv * NFEAT),      # descriptors in, u8 matrix out
-                  "k_shortlist(pass 2)": ("k_shortlist2", B * (MAP_ROWS + NFEAT) * 32)}
+                  "k_shortlist(pass 2)": ("k_shortlist2", B * (need_rows + NFEAT) * 32)}
         dom = max(single, key=lambda k: stage.get(single[k][0], 0.0))
         dur_ms = stage.get(single[dom][0], 0.0)
         alg_bytes = float(single[dom][1])
@@ -292,7 +295,7 @@ def run_gpu(args, rank, world, local_rank):
         # the matchers are bound by the XU pipe (POPC, 16 lanes/clk/SM), not by bytes: report that ceiling too
         popc = None
         if dom in ("k_pairs", "k_shortlist(pass 2)") and dur_ms > 0:
-            pairs = B * (npv * NFEAT if dom == "k_pairs" else MAP_ROWS * NFEAT)
+            pairs = B * (npv * NFEAT if dom == "k_pairs" else need_rows * NFEAT)
             per_pair = 6 if dom == "k_pairs" else 5
             sm_clock = (sampler.result()["sm_mhz"] or 1965) * 1e6
             peak_popc = 148 * 16 * sm_clock
@@ -326,7 +329,8 @@ def run_gpu(args, rank, world, local_rank):
                          "launch_ms": dur_ms, "algorithmic_bytes_per_launch": alg_bytes, "xu_popc": popc,
                          "note": "per-frame working sets are L2-resident and the dominant kernels are issue/XU-pipe bound, "
                                  "so the HBM fraction is small by construction (DESIGN.md section 4); launch_ms is measured "
-                                 "with both lanes running concurrently"},
+                                 "while the other lanes' kernels share the GPU (alone under ncu the kernel is ~40 % shorter: "
+                                 "profiles/r1_step_summary.txt)"},
             "profiled_pass": {"steps": psteps, "ms_per_step": ms_prof / psteps,
                               "note": "stage_ms_per_step, kernel_ms_per_launch and roofline.launch_ms come from this pass"},
             "stage_ms_per_step": kernels, "kernel_ms_per_launch": {k: stage.get(v[0], 0.0) for k, v in single.items()}, "p50_ms_per_frame_single": p50, "wall_ms_per_step": wall_dev / args.steps,

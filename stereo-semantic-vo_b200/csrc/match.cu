@@ -959,12 +959,12 @@ void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStrea
     if (ev0) cudaEventRecord(ev0, st);
     if (a.win_uvr) k_shortlist<true><<<gs, M_THREADS, 0, st>>>(a, T);
     else k_shortlist<false><<<gs, M_THREADS, 0, st>>>(a, T);
+    if (ev1) cudaEventRecord(ev1, st);
     if (a.need_list && a.dmat) {
         const int gx = (maxM + M_WARPS - 1) / M_WARPS;
         k_reuse<<<dim3(gx < 128 ? gx : 128, nframes), M_THREADS, 0, st>>>(a, T);   // warps stride over the frame's reuse list
         ++*launches;
     }
-    if (ev1) cudaEventRecord(ev1, st);
     // shared memory: two claim-time arrays + pre-claimed bytes + as many short-list entries as fit
     const int colsA = (maxN + 3) & ~3;
     const int ent_cap = (g_resolve_smem_limit - colsA * 9 - 64) / 4;
