@@ -378,3 +378,52 @@ def test_batch_inputs_any_residency_and_layout(ctxK):
     ctxK.batch_submit(1, odd); ctxK.batch_wait(1)
     for i in range(2):
         _same_result(want[i], ctxK.batch_result(1, i))
+
+
+def test_batch_stage_combinations_and_fallback_path(ctxK):
+    """Frames without a previous frame, without a map, with more previous rows than current keypoints can hold
+    (the un-fused BF / pass-1 path), batches of different sizes on the same lane (each (n, stages) combination is
+    its own captured graph) -- all against the oracle."""
+    cal = synth.KITTI_04_12
+    bf, b = float(np.float32(cal["bf"])), float(np.float32(cal["bf"] / cal["fx"]))
+    seq = synth.Sequence(seed=8)
+    frames = [seq.frame(t) for t in range(3)]
+    descs = [ctxK.extract(f[0], cam=0)[1] for f in frames]
+    rng = np.random.default_rng(5)
+    big_prev = np.concatenate([descs[0], noisy_copies(rng, descs[1], 3000 - len(descs[0]))], 0)   # 3000 rows > kp_cap
+    small_map = synth.local_map(descs[:2], rows=700, seed=3)
+
+    def check(job, r):
+        dl = r["desc_left"]
+        assert r["status"] == 0
+        if job.get("prev_desc") is not None:
+            oi, od, ok = O.match_bf(dl, job["prev_desc"])
+            assert (r["bf_idx"] == oi).all() and (r["bf_dist"] == od).all() and (r["bf_keep"] == ok).all()
+            p1 = O.match_greedy(job["prev_desc"], dl, 0)
+            assert (r["p1_row_claimed"] == p1["row_claimed"]).all()
+            for k in ("best_idx", "best", "second"):
+                assert (r["p1_" + k] == p1[k]).all(), k
+            claimed, claim_row, base = p1["claimed"], p1["claim_row"], len(job["prev_desc"])
+        else:
+            claimed, claim_row, base = None, None, 0
+        if job.get("map_desc") is not None:
+            p2 = O.match_greedy(job["map_desc"], dl, 1, claimed=claimed, claim_row=claim_row, row_base=base)
+            assert (r["p2_row_claimed"] == p2["row_claimed"]).all()
+            assert (r["claim_row"] == p2["claim_row"]).all()
+
+    def img(t):
+        return dict(left=frames[t][0], right=frames[t][1], bf=bf, baseline=b)
+
+    batches = [
+        [dict(img(1))],                                                               # extraction + stereo only
+        [dict(img(1), prev_desc=descs[0]), dict(img(2), prev_desc=descs[1])],         # no map
+        [dict(img(2), map_desc=small_map)],                                           # no previous frame
+        [dict(img(2), prev_desc=big_prev, map_desc=small_map)],                       # n_prev > kp_cap: un-fused path
+        [dict(img(1), prev_desc=descs[0], map_desc=small_map), dict(img(2), prev_desc=descs[1], map_desc=small_map),
+         dict(img(2), prev_desc=descs[0], map_desc=small_map)],                       # three frames, fused path
+        [dict(img(1), prev_desc=descs[0]), dict(img(2), prev_desc=descs[1])],         # replay of a cached graph
+    ]
+    for jobs in batches:
+        ctxK.batch_submit(0, jobs); ctxK.batch_wait(0)
+        for i, job in enumerate(jobs):
+            check(job, ctxK.batch_result(0, i))
