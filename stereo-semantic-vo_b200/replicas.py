@@ -40,7 +40,22 @@ class Group:
                 kw = {}
                 if backend == "nccl" and device is not None:
                     kw["device_id"] = torch.device("cuda", device)
-                dist.init_process_group(backend or "gloo", **kw)
+                # NCCL prints its version banner on the process's stdout when the communicator is created; bench.py's
+                # stdout must carry exactly one JSON line, so fd 1 points at stderr while the group comes up
+                import sys
+                sys.stdout.flush()
+                saved = os.dup(1)
+                os.dup2(2, 1)
+                try:
+                    dist.init_process_group(backend or "gloo", **kw)
+                    if (backend or "gloo") == "nccl":
+                        torch.cuda.synchronize()
+                        dist.barrier()          # forces communicator creation now
+                        torch.cuda.synchronize()
+                finally:
+                    sys.stdout.flush()
+                    os.dup2(saved, 1)
+                    os.close(saved)
             self.dist = dist
             self.backend = dist.get_backend()
         else:
