@@ -427,3 +427,13 @@ def test_batch_stage_combinations_and_fallback_path(ctxK):
         ctxK.batch_submit(0, jobs); ctxK.batch_wait(0)
         for i, job in enumerate(jobs):
             check(job, ctxK.batch_result(0, i))
+    # a featureless stereo pair next to a normal one: zero keypoints, nothing matched, nothing claimed, no error
+    flat = np.full(synth.K_SHAPE, 117, np.uint8)
+    jobs = [dict(left=flat, right=flat, bf=bf, baseline=b, prev_desc=descs[0], map_desc=small_map),
+            dict(img(1), prev_desc=descs[0], map_desc=small_map)]
+    ctxK.batch_submit(1, jobs); ctxK.batch_wait(1)
+    r = ctxK.batch_result(1, 0)
+    assert r["status"] == 0 and r["n_left"] == 0 and r["n_right"] == 0 and r["n_stereo"] == 0
+    assert not r["p1_row_claimed"].any() and not r["p2_row_claimed"].any()
+    assert (r["p1_best_idx"] == -1).all() and (r["p1_best"] == 256).all() and (r["p1_second"] == 256).all()
+    check(jobs[1], ctxK.batch_result(1, 1))
