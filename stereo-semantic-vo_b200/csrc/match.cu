@@ -439,6 +439,7 @@ __device__ bool veto_dynamic(const GreedyArgs &a, int f, int row, int col)
 #define RES_THREADS 1024
 #define RES_WARPS (RES_THREADS / 32)
 #define RES_FREE 0x7fffffff
+#define RES_SC 8     // compaction: list sizes cached in registers for rows up to 8 * 1024
 #define RES_RC 6     // candidate rows per thread whose state stays in registers (6 * 1024 rows per frame)
 
 // The greedy scan is sequential in the reference (a claim hides the column from every later row), but
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_c
     }
     if (tid == 0) s_novf = 0;
 
-    const int *mpr = map_prev_of(a, f);
+    const int *mpr = a.need_list ? nullptr : map_prev_of(a, f);   // with work lists, rows pass 1 matched keep a zero count
     auto row_size = [&](int r) -> int {   // 0 = cannot claim, else min(cnt, CAP+1)
         if (r >= M) return 0;
         const int c = a.short_cnt[ro + r];
@@ -490,8 +491,13 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_c
     const int seg = (((M + RES_WARPS - 1) / RES_WARPS) + 31) & ~31;
     const int beg = warp * seg, end = min(beg + seg, M);
     int cr = 0, ce = 0, novf = 0;
-    for (int base = beg; base < end; base += 32) {
+    int sc[RES_SC];                       // list sizes of this thread's first RES_SC rows (second pass reuses them)
+#pragma unroll
+    for (int u = 0; u < RES_SC; ++u) sc[u] = 0;
+    for (int base = beg, u = 0; base < end; base += 32, ++u) {
         const int s = base + lane < end ? row_size(base + lane) : 0;
+#pragma unroll
+        for (int v = 0; v < RES_SC; ++v) if (v == u) sc[v] = s;
         cr += __popc(__ballot_sync(0xffffffffu, s > 0));
         ce += __reduce_add_sync(0xffffffffu, s > SVO_SHORT_CAP ? 0 : s);
         novf += __popc(__ballot_sync(0xffffffffu, s > SVO_SHORT_CAP));
@@ -500,8 +506,12 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_c
     __syncthreads();
     int orow = 0, oent = 0, tot = 0;
     for (int w = 0; w < RES_WARPS; ++w) { if (w < warp) { orow += wrow[w]; oent += went[w]; } tot += wrow[w]; }
-    for (int base = beg; base < end; base += 32) {
-        const int s = base + lane < end ? row_size(base + lane) : 0;
+    for (int base = beg, u = 0; base < end; base += 32, ++u) {
+        int s = 0;
+        if (u < RES_SC) {
+#pragma unroll
+            for (int v = 0; v < RES_SC; ++v) if (v == u) s = sc[v];
+        } else s = base + lane < end ? row_size(base + lane) : 0;
         const uint32_t m = __ballot_sync(0xffffffffu, s > 0);
         const int e = s > SVO_SHORT_CAP ? 0 : s;
         int inc = e;
