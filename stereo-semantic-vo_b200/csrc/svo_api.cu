@@ -588,15 +588,15 @@ int svo_extract(svo_ctx *ctx, int cam, const uint8_t *gray, int stride, int w, i
     int hdr[2] = {0, 0};
     CU(cudaMemcpyAsync(&hdr[0], ctx->b.nkp + slot, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&hdr[1], ctx->b.status + slot, sizeof(int), cudaMemcpyDeviceToHost, st));
+    // the outputs ride the same stream, sized by the caller's capacity (rows past the count are ignored): one sync
+    const int mcap = cap < g.kp_cap ? cap : g.kp_cap;
+    if (mcap > 0 && kp_out) CU(cudaMemcpyAsync(kp_out, ctx->b.kp + (size_t)slot * g.kp_cap, sizeof(svo_keypoint) * mcap, cudaMemcpyDeviceToHost, st));
+    if (mcap > 0 && desc_out) CU(cudaMemcpyAsync(desc_out, ctx->b.desc + (size_t)slot * g.kp_cap * 32, 32 * (size_t)mcap, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
     if (hdr[1] & SVO_STATUS_OVERFLOW) return fail(ctx, SVO_E_CAPACITY, "svo_extract: internal capacity exceeded (status %d, n %d)", hdr[1], hdr[0]);
-    const int n = hdr[0];
-    const int m = n < cap ? n : cap;
-    if (m > 0 && kp_out) CU(cudaMemcpy(kp_out, ctx->b.kp + (size_t)slot * g.kp_cap, sizeof(svo_keypoint) * m, cudaMemcpyDeviceToHost));
-    if (m > 0 && desc_out) CU(cudaMemcpy(desc_out, ctx->b.desc + (size_t)slot * g.kp_cap * 32, 32 * (size_t)m, cudaMemcpyDeviceToHost));
     ctx->sync_have[cam] = true;
-    return n;
+    return hdr[0];
 }
 
 int svo_stereo_sparse(svo_ctx *ctx, float bf, float baseline, float *u_right, float *depth,
