@@ -133,6 +133,43 @@ int svo_match_greedy(svo_ctx *ctx, const uint8_t *rows, int M, const uint8_t *cu
 int svo_disp2depth(svo_ctx *ctx, const float *disp, float *depth, size_t n, float bf);
 
 /* ---------------------------------------------------------------------------
+ * Pose stage (the step right after the matchers in
+ * Tracking::Tracklastframe, src/Tracking.cc:108-121).  Batched: one CUDA block per problem.
+ * ------------------------------------------------------------------------- */
+typedef struct svo_pose_problem {
+    const float *pts3d; /* n x 3: mapp->worldpos of CurrentFrame->MapPoints[j] (src/pnpmatch.cc:221, src/Optimizer.cc:62-65) */
+    const float *pts2d; /* n x 2: CurrentFrame->keypoints_l[j].pt          (src/pnpmatch.cc:220, src/Optimizer.cc:47-48) */
+    int n;              /* host or device pointers                                                     */
+    float fx, fy, cx, cy;
+    float Tcw[16];      /* svo_pose_optimize only: pFrame->Tcw, row-major 4x4 (cv::Mat CV_32F)          */
+} svo_pose_problem;
+
+typedef struct svo_pnp_result {
+    double R[9];            /* cv::Rodrigues(rvec) (src/pnpmatch.cc:237-238), row-major               */
+    double t[3];            /* tvec                                                                   */
+    int32_t n_inliers;      /* inliers.rows (:229); 0 = no model                                      */
+    int32_t best_iteration; /* sample that won, its P3P solution index, hypotheses scored             */
+    int32_t best_solution;
+    int32_t n_hypotheses;
+} svo_pnp_result;
+
+/* The role of cv::solvePnPRansac(pts3d, pts2d, K, Mat(), rvec, tvec, false, 100, 8.0, 0.99, inliers)
+ * (src/pnpmatch.cc:227) as a data-parallel RANSAC: `iterations` 3-point samples (counter-based hash of
+ * `seed`), P3P on each, every solution scored against all points with squared reprojection error
+ * <= reproj_err^2, first maximum wins, Gauss-Newton refit (<= refine_iters steps) on its inliers.
+ * NOT OpenCV's sampler/EPnP: results agree with cv2 statistically, not bit for bit (opt-in stage).
+ * inliers: sum(n) flags, problems back to back (may be NULL).  Returns nproblems or a negative status. */
+int svo_pnp_ransac(svo_ctx *ctx, const svo_pose_problem *problems, int nproblems, int iterations,
+                   float reproj_err, uint32_t seed, int refine_iters, svo_pnp_result *results, uint8_t *inliers);
+
+/* Optimizer::PoseOptimization (src/Optimizer.cc:15-86): g2o Levenberg-Marquardt (optimize(iterations),
+ * reference: 10) on the frame pose over EdgeSE3ProjectXYZOnlyPose edges with Huber(sqrt(5.991)).
+ * Tcw_out: 16 floats per problem (the pose SetPose receives); stats (may be NULL): per problem
+ * {outer iterations run, final robust chi2}.  Returns nproblems or a negative status. */
+int svo_pose_optimize(svo_ctx *ctx, const svo_pose_problem *problems, int nproblems, int iterations,
+                      float *Tcw_out, double *stats);
+
+/* ---------------------------------------------------------------------------
  * Batched, pipelined front-end: what Tracking::Track runs per stereo pair
  * (src/Tracking.cc:225-231): extract L+R, sparse stereo, BF match against the
  * previous frame, greedy pass 1 (previous frame's map points) and pass 2

@@ -161,3 +161,26 @@ def stereo_sparse(kl, dl, pl, kr, dr, pr, bf, b):
     lib().svo_o_stereo_sparse(_p(kl), _p(dl), n, _p(kr), _p(dr), len(kr), C.byref(pl), C.byref(pr),
                               C.c_float(bf), C.c_float(b), _p(ur), _p(dep), _p(mr), _p(sad))
     return ur, dep, mr, sad
+
+
+def pose_optimize(Xw, obs, K4, Tcw, iterations=10):
+    """Optimizer::PoseOptimization restatement -> (Tcw_out[4,4] f32, outer iterations, robust chi2)."""
+    Xw = np.ascontiguousarray(Xw, np.float32).reshape(-1, 3); obs = np.ascontiguousarray(obs, np.float32).reshape(-1, 2)
+    Tin = np.ascontiguousarray(Tcw, np.float32).reshape(4, 4); Tout = np.empty((4, 4), np.float32)
+    stats = np.zeros(2, np.float64)
+    fx, fy, cx, cy = [C.c_float(float(v)) for v in K4]
+    L = lib(); L.svo_o_pose_optimize.restype = C.c_int
+    L.svo_o_pose_optimize(_p(Xw), _p(obs), len(Xw), fx, fy, cx, cy, _p(Tin), _p(Tout), iterations, _p(stats))
+    return Tout, int(stats[0]), float(stats[1])
+
+
+def pnp_ransac(pts3d, pts2d, K4, iterations=100, reproj_err=8.0, seed=1, refine_iters=10):
+    """P3P RANSAC stand-in for cv::solvePnPRansac -> (n_inliers, R[3,3] f64, t[3] f64, mask[n] u8, info[3])."""
+    p3 = np.ascontiguousarray(pts3d, np.float32).reshape(-1, 3); p2 = np.ascontiguousarray(pts2d, np.float32).reshape(-1, 2)
+    R = np.zeros((3, 3), np.float64); t = np.zeros(3, np.float64)
+    mask = np.zeros(len(p3), np.uint8); info = np.zeros(3, np.int32)
+    fx, fy, cx, cy = [C.c_float(float(v)) for v in K4]
+    L = lib(); L.svo_o_pnp_ransac.restype = C.c_int
+    n = L.svo_o_pnp_ransac(_p(p3), _p(p2), len(p3), fx, fy, cx, cy, iterations, C.c_float(reproj_err),
+                           C.c_uint32(seed), refine_iters, _p(R), _p(t), _p(mask), _p(info))
+    return n, R, t, mask, info

@@ -47,6 +47,17 @@ struct HostArena {           // pinned mirror of one lane's outputs
     int *params;             // staging for the per-batch parameter upload
 };
 
+struct PoseBufs {            // pose stage: packed problems of one call (device) + pinned staging
+    int cap_prob; size_t cap_pts;
+    PoseHdr *d_hdr, *h_hdr;
+    float *d_p3, *d_p2, *h_p3, *h_p2;
+    uint8_t *d_mask;
+    double *d_hyp; float *d_hypf;
+    int *d_info, *h_info;
+    double *d_pose, *h_pose, *d_stats, *h_stats;
+    float *d_T, *h_T;
+};
+
 struct LaneGraph { int key; cudaGraphExec_t exec; long long launches; };
 
 struct Lane {
@@ -73,6 +84,7 @@ struct svo_ctx {
     Bufs b;
     FrameBufs fb;            // batch frames
     FrameBufs sb;            // the single synchronous frame
+    PoseBufs pb;
     std::vector<Lane> lanes;
     cudaStream_t sync_st;
     int sync_slot0;          // two slots: cam 0 / cam 1
@@ -503,7 +515,22 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
     TRY(alloc_frames(ctx, ctx->fb, nbatch_frames, g.kp_cap, c.max_rows, false));
     const int sync_stride = g.kp_cap > c.max_rows ? g.kp_cap : c.max_rows;
     TRY(alloc_frames(ctx, ctx->sb, 1, sync_stride, sync_stride, true));
-    if (setup_fast_attributes(g) != 0 || setup_match_attributes() != 0 || setup_describe() != 0 || setup_select_attributes() != 0)
+    {
+        PoseBufs &p = ctx->pb;
+        p.cap_prob = c.max_batch; p.cap_pts = (size_t)c.max_batch * g.kp_cap;
+        const size_t NP = p.cap_prob, PTS = p.cap_pts, HY = NP * pose_max_iterations() * 4 * 12;
+        TRY(dalloc(ctx, &p.d_hdr, NP)); TRY(halloc(ctx, &p.h_hdr, NP));
+        TRY(dalloc(ctx, &p.d_p3, PTS * 3)); TRY(dalloc(ctx, &p.d_p2, PTS * 2));
+        TRY(halloc(ctx, &p.h_p3, PTS * 3)); TRY(halloc(ctx, &p.h_p2, PTS * 2));
+        TRY(dalloc(ctx, &p.d_mask, PTS));
+        TRY(dalloc(ctx, &p.d_hyp, HY)); TRY(dalloc(ctx, &p.d_hypf, HY));
+        TRY(dalloc(ctx, &p.d_info, NP * 4)); TRY(halloc(ctx, &p.h_info, NP * 4));
+        TRY(dalloc(ctx, &p.d_pose, NP * 12)); TRY(halloc(ctx, &p.h_pose, NP * 12));
+        TRY(dalloc(ctx, &p.d_stats, NP * 2)); TRY(halloc(ctx, &p.h_stats, NP * 2));
+        TRY(dalloc(ctx, &p.d_T, NP * 16)); TRY(halloc(ctx, &p.h_T, NP * 16));
+    }
+    if (setup_fast_attributes(g) != 0 || setup_match_attributes() != 0 || setup_describe() != 0 || setup_select_attributes() != 0 ||
+        setup_pose() != 0)
         return fail(ctx, SVO_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
     CU(cudaStreamCreateWithFlags(&ctx->sync_st, cudaStreamNonBlocking));
     ctx->stage_img_bytes = (size_t)g.H * (g.W + 256);
@@ -712,6 +739,115 @@ int svo_match_greedy(svo_ctx *ctx, const uint8_t *rows, int M, const uint8_t *cu
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
     return M;
+}
+
+namespace {
+// Pack the problems of one pose call into the device arrays: host points go through the pinned staging
+// (one H2D copy per array for the whole call), device points are copied in place.
+int stage_pose_problems(svo_ctx *ctx, const char *who, const svo_pose_problem *pr, int np, int *max_n, size_t *total)
+{
+    PoseBufs &p = ctx->pb;
+    if (np > p.cap_prob) return fail(ctx, SVO_E_CAPACITY, "%s: %d problems exceed max_batch %d", who, np, p.cap_prob);
+    size_t off = 0; int mx = 0; bool any_host = false;
+    for (int i = 0; i < np; ++i) {
+        if (pr[i].n < 0 || (pr[i].n && (!pr[i].pts3d || !pr[i].pts2d))) return fail(ctx, SVO_E_INVALID, "%s: bad problem %d", who, i);
+        if (off + pr[i].n > p.cap_pts) return fail(ctx, SVO_E_CAPACITY, "%s: more than %zu points in one call", who, p.cap_pts);
+        PoseHdr &h = p.h_hdr[i];
+        h.off = (int)off; h.n = pr[i].n; h.fx = pr[i].fx; h.fy = pr[i].fy; h.cx = pr[i].cx; h.cy = pr[i].cy;
+        memcpy(h.Tcw, pr[i].Tcw, sizeof h.Tcw);
+        off += pr[i].n; mx = std::max(mx, pr[i].n);
+    }
+    cudaStream_t st = ctx->sync_st;
+    for (int i = 0; i < np; ++i) {
+        const size_t o = p.h_hdr[i].off, n = pr[i].n;
+        if (!n) continue;
+        if (device_readable(pr[i].pts3d)) CU(cudaMemcpyAsync(p.d_p3 + 3 * o, pr[i].pts3d, 12 * n, cudaMemcpyDeviceToDevice, st));
+        else { memcpy(p.h_p3 + 3 * o, pr[i].pts3d, 12 * n); any_host = true; }
+        if (device_readable(pr[i].pts2d)) CU(cudaMemcpyAsync(p.d_p2 + 2 * o, pr[i].pts2d, 8 * n, cudaMemcpyDeviceToDevice, st));
+        else memcpy(p.h_p2 + 2 * o, pr[i].pts2d, 8 * n), any_host = true;
+    }
+    if (any_host) {
+        // host ranges of device-resident problems are left untouched on the device: copy per maximal host run
+        for (int i = 0; i < np;) {
+            if (!pr[i].n || device_readable(pr[i].pts3d)) { ++i; continue; }
+            int j = i; size_t o = p.h_hdr[i].off, m = 0;
+            while (j < np && (!pr[j].n || !device_readable(pr[j].pts3d))) { m += pr[j].n; ++j; }
+            CU(cudaMemcpyAsync(p.d_p3 + 3 * o, p.h_p3 + 3 * o, 12 * m, cudaMemcpyHostToDevice, st));
+            i = j;
+        }
+        for (int i = 0; i < np;) {
+            if (!pr[i].n || device_readable(pr[i].pts2d)) { ++i; continue; }
+            int j = i; size_t o = p.h_hdr[i].off, m = 0;
+            while (j < np && (!pr[j].n || !device_readable(pr[j].pts2d))) { m += pr[j].n; ++j; }
+            CU(cudaMemcpyAsync(p.d_p2 + 2 * o, p.h_p2 + 2 * o, 8 * m, cudaMemcpyHostToDevice, st));
+            i = j;
+        }
+    }
+    CU(cudaMemcpyAsync(p.d_hdr, p.h_hdr, sizeof(PoseHdr) * np, cudaMemcpyHostToDevice, st));
+    *max_n = mx; *total = off;
+    return SVO_OK;
+}
+
+PoseArgs pose_args(svo_ctx *ctx)
+{
+    PoseBufs &p = ctx->pb;
+    PoseArgs a;
+    a.hdr = p.d_hdr; a.p3 = p.d_p3; a.p2 = p.d_p2; a.hyp = p.d_hyp; a.hypf = p.d_hypf; a.mask = p.d_mask; a.info = p.d_info;
+    a.pose_out = p.d_pose; a.ransac_iterations = 0; a.thr2 = 0; a.seed = 0; a.refine_iterations = 0;
+    a.lm_iterations = 0; a.Tcw_out = p.d_T; a.lm_stats = p.d_stats;
+    return a;
+}
+}  // namespace
+
+int svo_pnp_ransac(svo_ctx *ctx, const svo_pose_problem *problems, int nproblems, int iterations,
+                   float reproj_err, uint32_t seed, int refine_iters, svo_pnp_result *results, uint8_t *inliers)
+{
+    if (!ctx || nproblems < 0 || (nproblems && !problems) || !results || iterations < 1 || !(reproj_err > 0) || refine_iters < 0)
+        return fail(ctx, SVO_E_INVALID, "svo_pnp_ransac: bad argument");
+    if (iterations > pose_max_iterations()) return fail(ctx, SVO_E_CAPACITY, "svo_pnp_ransac: at most %d iterations", pose_max_iterations());
+    if (nproblems == 0) return 0;
+    CU(cudaSetDevice(ctx->cfg.device));
+    int max_n = 0; size_t total = 0;
+    TRY(stage_pose_problems(ctx, "svo_pnp_ransac", problems, nproblems, &max_n, &total));
+    PoseBufs &p = ctx->pb;
+    cudaStream_t st = ctx->sync_st;
+    PoseArgs a = pose_args(ctx);
+    a.ransac_iterations = iterations; a.thr2 = reproj_err * reproj_err; a.seed = seed; a.refine_iterations = refine_iters;
+    launch_pnp_ransac(a, nproblems, max_n, st, &ctx->launches);
+    CU(cudaMemcpyAsync(p.h_pose, p.d_pose, sizeof(double) * 12 * nproblems, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(p.h_info, p.d_info, sizeof(int) * 4 * nproblems, cudaMemcpyDeviceToHost, st));
+    if (inliers && total) CU(cudaMemcpyAsync(inliers, p.d_mask, total, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    for (int i = 0; i < nproblems; ++i) {
+        svo_pnp_result &r = results[i];
+        memcpy(r.R, p.h_pose + 12 * i, sizeof r.R); memcpy(r.t, p.h_pose + 12 * i + 9, sizeof r.t);
+        r.n_inliers = p.h_info[4 * i]; r.best_iteration = p.h_info[4 * i + 1]; r.best_solution = p.h_info[4 * i + 2];
+        r.n_hypotheses = p.h_info[4 * i + 3];
+    }
+    return nproblems;
+}
+
+int svo_pose_optimize(svo_ctx *ctx, const svo_pose_problem *problems, int nproblems, int iterations, float *Tcw_out, double *stats)
+{
+    if (!ctx || nproblems < 0 || (nproblems && !problems) || !Tcw_out || iterations < 0)
+        return fail(ctx, SVO_E_INVALID, "svo_pose_optimize: bad argument");
+    if (nproblems == 0) return 0;
+    CU(cudaSetDevice(ctx->cfg.device));
+    int max_n = 0; size_t total = 0;
+    TRY(stage_pose_problems(ctx, "svo_pose_optimize", problems, nproblems, &max_n, &total));
+    PoseBufs &p = ctx->pb;
+    cudaStream_t st = ctx->sync_st;
+    PoseArgs a = pose_args(ctx);
+    a.lm_iterations = iterations;
+    launch_pose_lm(a, nproblems, st, &ctx->launches);
+    CU(cudaMemcpyAsync(p.h_T, p.d_T, sizeof(float) * 16 * nproblems, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(p.h_stats, p.d_stats, sizeof(double) * 2 * nproblems, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    memcpy(Tcw_out, p.h_T, sizeof(float) * 16 * nproblems);
+    if (stats) memcpy(stats, p.h_stats, sizeof(double) * 2 * nproblems);
+    return nproblems;
 }
 
 int svo_disp2depth(svo_ctx *ctx, const float *disp, float *depth, size_t n, float bf)

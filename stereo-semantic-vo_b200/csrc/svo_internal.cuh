@@ -188,6 +188,22 @@ struct PairArgs {            // fused BF + pass-1 front of the batch path (match
 };
 void launch_pass1_fused(const PairArgs &p, const BfArgs &b, int nframes, cudaStream_t st, long long *launches,
                         cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);   // optional events around k_pairs
+// ---- pose stage (pose.cu) ----
+struct PoseHdr { int off, n; float fx, fy, cx, cy; float Tcw[16]; };   // one problem: points [off, off + n) of the packed arrays
+struct PoseArgs {
+    const PoseHdr *hdr;
+    const float *p3, *p2;      // packed n x 3 world points / n x 2 pixels of all problems
+    double *hyp; float *hypf;  // [problem][iterations * 4][12] P3P solutions (R row-major, t), f64 and the f32 copy that is scored
+    uint8_t *mask;             // packed inlier flags
+    int *info;                 // [problem][4]: inliers, winning iteration, its solution index, hypotheses scored
+    double *pose_out;          // [problem][12]: refined R (row-major), t
+    int ransac_iterations; float thr2; uint32_t seed; int refine_iterations;
+    int lm_iterations; float *Tcw_out; double *lm_stats;   // k_pose_lm: [problem][16] pose out, [problem][2] (iterations, chi2)
+};
+void launch_pnp_ransac(const PoseArgs &a, int nproblems, int max_n, cudaStream_t st, long long *launches);
+void launch_pose_lm(const PoseArgs &a, int nproblems, cudaStream_t st, long long *launches);
+int setup_pose();
+int pose_max_iterations();
 void launch_disp2depth(const float *disp, float *depth, size_t n, float bf, cudaStream_t st, long long *launches);
 int setup_match_attributes();
 int greedy_max_cols();   // most columns (current-frame keypoints) the greedy resolver supports

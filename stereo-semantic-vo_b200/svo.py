@@ -48,6 +48,16 @@ class FrameOut(C.Structure):
                 ("p1_row_claimed", C.c_void_p), ("p2_row_claimed", C.c_void_p), ("claim_row", C.c_void_p)]
 
 
+class PoseProblem(C.Structure):
+    _fields_ = [("pts3d", C.c_void_p), ("pts2d", C.c_void_p), ("n", C.c_int),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("Tcw", C.c_float * 16)]
+
+
+class PnpResult(C.Structure):
+    _fields_ = [("R", C.c_double * 9), ("t", C.c_double * 3), ("n_inliers", C.c_int32),
+                ("best_iteration", C.c_int32), ("best_solution", C.c_int32), ("n_hypotheses", C.c_int32)]
+
+
 class SvoError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("svo_b200 error %d: %s" % (code, msg))
@@ -58,7 +68,8 @@ EXPORTS = ["svo_default_config", "svo_version", "svo_create", "svo_destroy", "sv
            "svo_extract", "svo_stereo_sparse", "svo_match_bf", "svo_match_greedy", "svo_disp2depth",
            "svo_batch_submit", "svo_batch_wait", "svo_batch_result", "svo_alloc_pinned", "svo_free_pinned",
            "svo_alloc_device", "svo_free_device", "svo_copy_to_device", "svo_launch_count", "svo_batch_stage_ms",
-           "svo_set_profiling", "svo_lane_stream", "svo_debug_tap", "svo_debug_retain_best"]
+           "svo_set_profiling", "svo_lane_stream", "svo_debug_tap", "svo_debug_retain_best",
+           "svo_pnp_ransac", "svo_pose_optimize"]
 
 _lib = None
 
@@ -106,6 +117,9 @@ def load():
     L.svo_debug_tap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     L.svo_debug_tap.restype = C.c_longlong
     L.svo_debug_retain_best.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.svo_pnp_ransac.argtypes = [C.c_void_p, C.POINTER(PoseProblem), C.c_int, C.c_int, C.c_float, C.c_uint32, C.c_int,
+                                 C.POINTER(PnpResult), C.c_void_p]
+    L.svo_pose_optimize.argtypes = [C.c_void_p, C.POINTER(PoseProblem), C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -223,6 +237,46 @@ class Context:
         out = np.empty_like(disp)
         self._chk(self.lib.svo_disp2depth(self.h, _p(disp), _p(out), disp.size, bf))
         return out
+
+    # ---- pose stage -------------------------------------------------------------------
+    def _pose_problems(self, problems):
+        """problems: list of dicts with pts3d (n,3), pts2d (n,2), K=(fx,fy,cx,cy) and optional Tcw (4,4)."""
+        arr = (PoseProblem * len(problems))()
+        keep = []
+        for i, q in enumerate(problems):
+            p3 = np.ascontiguousarray(q["pts3d"], np.float32).reshape(-1, 3)
+            p2 = np.ascontiguousarray(q["pts2d"], np.float32).reshape(-1, 2)
+            assert len(p3) == len(p2)
+            keep += [p3, p2]
+            arr[i].pts3d, arr[i].pts2d, arr[i].n = p3.ctypes.data, p2.ctypes.data, len(p3)
+            arr[i].fx, arr[i].fy, arr[i].cx, arr[i].cy = [float(v) for v in q["K"]]
+            T = np.ascontiguousarray(q.get("Tcw", np.eye(4)), np.float32).reshape(16)
+            for k in range(16):
+                arr[i].Tcw[k] = float(T[k])
+        return arr, keep
+
+    def pnp_ransac(self, problems, iterations=100, reproj_err=8.0, seed=1, refine_iters=10):
+        """cv::solvePnPRansac's role (src/pnpmatch.cc:227) -> list of dicts (n_inliers, R, t, inliers, info)."""
+        arr, keep = self._pose_problems(problems)
+        res = (PnpResult * len(problems))()
+        total = sum(a.n for a in arr)
+        mask = np.zeros(max(total, 1), np.uint8)
+        self._chk(self.lib.svo_pnp_ransac(self.h, arr, len(problems), iterations, reproj_err, seed, refine_iters, res, _p(mask)))
+        out, off = [], 0
+        for i in range(len(problems)):
+            r = res[i]
+            out.append(dict(n_inliers=r.n_inliers, R=np.array(r.R[:]).reshape(3, 3), t=np.array(r.t[:]),
+                            inliers=mask[off:off + arr[i].n].copy(),
+                            info=(r.best_iteration, r.best_solution, r.n_hypotheses)))
+            off += arr[i].n
+        return out
+
+    def pose_optimize(self, problems, iterations=10):
+        """Optimizer::PoseOptimization (src/Optimizer.cc:15-86) -> list of (Tcw[4,4] f32, iterations run, robust chi2)."""
+        arr, keep = self._pose_problems(problems)
+        T = np.zeros((len(problems), 4, 4), np.float32); st = np.zeros((len(problems), 2), np.float64)
+        self._chk(self.lib.svo_pose_optimize(self.h, arr, len(problems), iterations, _p(T), _p(st)))
+        return [(T[i].copy(), int(st[i, 0]), float(st[i, 1])) for i in range(len(problems))]
 
     # ---- batched pipeline ------------------------------------------------------------
     def batch_submit(self, lane, frames):

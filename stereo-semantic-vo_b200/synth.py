@@ -116,3 +116,31 @@ def local_map(desc_frames, rows=5000, seed=0):
         out.append(src ^ flips)
         need -= take; k += 1
     return np.ascontiguousarray(np.concatenate(out, 0))
+
+
+def rodrigues(w):
+    """Rotation matrix of the axis-angle vector w (float64)."""
+    w = np.asarray(w, np.float64)
+    th = np.linalg.norm(w)
+    Kx = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if th < 1e-12:
+        return np.eye(3) + Kx
+    return np.eye(3) + np.sin(th) / th * Kx + (1 - np.cos(th)) / th ** 2 * (Kx @ Kx)
+
+
+def pose_problem(n, seed, outlier_frac=0.3, noise=0.5, cal=None, shape=K_SHAPE, rot=0.05, trans=0.3):
+    """Synthetic input of the pose stage (src/pnpmatch.cc:211-227): n map points seen by a camera at a
+    random pose (Xc = R Xw + t), pixel noise N(0, noise) and a fraction of gross mismatches.
+    -> (Xw[n,3] f32, obs[n,2] f32, K=(fx,fy,cx,cy), R, t, outlier flags)."""
+    cal = cal or KITTI_04_12
+    fx, fy, cx, cy = cal["fx"], cal["fy"], cal["cx"], cal["cy"]
+    rng = np.random.default_rng(seed)
+    R = rodrigues(rng.normal(0, rot, 3)); t = rng.normal(0, trans, 3)
+    uv = np.stack([rng.uniform(0, shape[1], n), rng.uniform(0, shape[0], n)], 1)
+    z = rng.uniform(4, 60, n)
+    Xc = np.stack([(uv[:, 0] - cx) / fx * z, (uv[:, 1] - cy) / fy * z, z], 1)
+    Xw = (Xc - t) @ R
+    obs = uv + rng.normal(0, noise, (n, 2))
+    bad = rng.random(n) < outlier_frac
+    obs[bad] = np.stack([rng.uniform(0, shape[1], int(bad.sum())), rng.uniform(0, shape[0], int(bad.sum()))], 1)
+    return Xw.astype(np.float32), obs.astype(np.float32), (fx, fy, cx, cy), R, t, bad
