@@ -3,6 +3,7 @@
 // descriptors and distances are produced by libsvo_b200.so; this file moves results into the
 // public fields the rest of the reference (Tracking.cc, Optimizer.cc) reads.
 #include "pnpmatch.h"
+#include "Optimizer.h"
 
 #include <cmath>
 #include <cstdio>
@@ -24,6 +25,12 @@ thread_local std::map<std::tuple<int, int>, svo_ctx *> g_engines;
 {
     std::string msg = std::string(what) + " failed (" + std::to_string(rc) + "): " + (c ? svo_last_error(c) : "no context");
     throw std::runtime_error(msg);
+}
+
+svo_ctx *any_engine()
+{
+    if (g_engines.empty()) throw std::runtime_error("no engine yet: extract a frame first");
+    return g_engines.begin()->second;
 }
 
 cv::Mat eye4()
@@ -258,7 +265,35 @@ void frame::createmappoint(std::set<mappoint *> &localmap)
 // ------------------------------------------------------------------------------- pnpmatch
 cv::Mat pnpmatch::Cur_Tcw;
 std::function<cv::Mat(const std::vector<cv::Point2f> &, const std::vector<cv::Point2f> &)> pnpmatch::fundamental_solver;
-std::function<bool(const std::vector<cv::Mat> &, const std::vector<cv::Point2f> &, const cv::Mat &, cv::Mat &, int &)> pnpmatch::pnp_solver;
+std::function<bool(const std::vector<cv::Mat> &, const std::vector<cv::Point2f> &, const cv::Mat &, cv::Mat &, int &)> pnpmatch::pnp_solver =
+    pnpmatch::device_pnp;
+std::vector<unsigned char> pnpmatch::last_pnp_inliers;
+
+// cv::solvePnPRansac(pts3d, pts2d, K, Mat(), rvec, tvec, false, 100, 8.0, 0.99, inliers) + Rodrigues + the 4x4
+// Tcl of src/pnpmatch.cc:227-245, on the device.
+bool pnpmatch::device_pnp(const std::vector<cv::Mat> &pts3d, const std::vector<cv::Point2f> &pts2d, const cv::Mat &K,
+                          cv::Mat &Tcl, int &inliers)
+{
+    const int n = (int)pts2d.size();
+    std::vector<float> p3((size_t)n * 3), p2((size_t)n * 2);
+    for (int i = 0; i < n; ++i) {
+        for (int k = 0; k < 3; ++k) p3[(size_t)i * 3 + k] = pts3d[(size_t)i].at<float>(k, 0);
+        p2[(size_t)i * 2] = pts2d[(size_t)i].x; p2[(size_t)i * 2 + 1] = pts2d[(size_t)i].y;
+    }
+    svo_pose_problem pr{};
+    pr.pts3d = p3.data(); pr.pts2d = p2.data(); pr.n = n;
+    pr.fx = K.at<float>(0, 0); pr.fy = K.at<float>(1, 1); pr.cx = K.at<float>(0, 2); pr.cy = K.at<float>(1, 2);
+    svo_pnp_result res{};
+    last_pnp_inliers.assign((size_t)n, 0);
+    svo_ctx *ctx = any_engine();
+    const int rc = svo_pnp_ransac(ctx, &pr, 1, 100, 8.0f, 1u, 10, &res, last_pnp_inliers.data());
+    if (rc < 0) die(ctx, "svo_pnp_ransac", rc);
+    inliers = res.n_inliers;
+    if (res.n_inliers == 0) return false;
+    Tcl = eye4();
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) Tcl.at<float>(r, c) = (float)res.R[r * 3 + c]; Tcl.at<float>(r, 3) = (float)res.t[r]; }
+    return true;
+}
 
 int pnpmatch::DescriptorDistance(const cv::Mat &a, const cv::Mat &b)
 {
@@ -420,4 +455,28 @@ int pnpmatch::poseEstimationPnP(frame *cur, frame &last, std::set<mappoint *> &l
         }
     }
     return (int)pts2d.size();
+}
+
+// ------------------------------------------------------------------------------- Optimizer
+int Optimizer::PoseOptimization(frame *pFrame)
+{
+    std::vector<float> p3, p2;
+    const int n = (int)pFrame->keypoints_l.size() < pFrame->N ? (int)pFrame->keypoints_l.size() : pFrame->N;
+    for (int i = 0; i < n; ++i)
+        if (mappoint *mp = pFrame->MapPoints[(size_t)i]) {                       // src/Optimizer.cc:42-71
+            p2.push_back(pFrame->keypoints_l[(size_t)i].pt.x); p2.push_back(pFrame->keypoints_l[(size_t)i].pt.y);
+            for (int k = 0; k < 3; ++k) p3.push_back(mp->worldpos.at<float>(k, 0));
+        }
+    svo_pose_problem pr{};
+    pr.pts3d = p3.data(); pr.pts2d = p2.data(); pr.n = (int)(p2.size() / 2);
+    pr.fx = pFrame->fx; pr.fy = pFrame->fy; pr.cx = pFrame->cx; pr.cy = pFrame->cy;
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) pr.Tcw[r * 4 + c] = pFrame->Tcw.at<float>(r, c);
+    float T[16];
+    svo_ctx *ctx = any_engine();
+    const int rc = svo_pose_optimize(ctx, &pr, 1, 10, T, nullptr);
+    if (rc < 0) die(ctx, "svo_pose_optimize", rc);
+    cv::Mat pose(4, 4, CV_32F, 0.0);
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) pose.at<float>(r, c) = T[r * 4 + c];
+    pFrame->SetPose(pose);                                                       // :82-84
+    return pr.n;
 }

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <map>
 #include "pnpmatch.h"
+#include "Optimizer.h"
 
 static cv::Mat load_raw(const char *path, int w, int h)
 {
@@ -67,6 +68,26 @@ int main(int argc, char **argv)
         for (mappoint *mp : localmap) fprintf(o, "map %d %d\n", rank++, src[mp]);
         for (size_t i = 0; i < last.MapPoints.size(); ++i)
             if (last.MapPoints[i]) fprintf(o, "score %zu %.9g\n", i, f1->match_score[i]);
+        // the pose stage as Tracking::Tracklastframe runs it (src/Tracking.cc:114-120): PnP RANSAC on the matched
+        // 3D-2D pairs (src/pnpmatch.cc:211-247), SetPose(Tcl * Tcw), then the pose-only optimisation
+        std::vector<cv::Mat> pts3d;
+        std::vector<cv::Point2f> pts2d;
+        for (size_t j = 0; j < f1->keypoints_l.size(); ++j)
+            if (mappoint *mp = f1->MapPoints[j]) { pts2d.push_back(f1->keypoints_l[j].pt); pts3d.push_back(mp->worldpos); }
+        for (size_t k = 0; k < pts2d.size(); ++k)
+            fprintf(o, "pair %zu %.9g %.9g %.9g %.9g %.9g\n", k, pts3d[k].at<float>(0, 0), pts3d[k].at<float>(1, 0),
+                    pts3d[k].at<float>(2, 0), pts2d[k].x, pts2d[k].y);
+        cv::Mat Tcl;
+        int inl = 0;
+        const bool ok = pnpmatch::pnp_solver(pts3d, pts2d, K, Tcl, inl);
+        fprintf(o, "pnp %d %d", ok ? 1 : 0, inl);
+        if (ok) for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) fprintf(o, " %.9g", Tcl.at<float>(r, c));
+        fprintf(o, "\n");
+        if (ok) f1->SetPose(Tcl);                           // f1->Tcw is the identity here, so Tcl * Tcw = Tcl
+        const int nc = Optimizer::PoseOptimization(f1);
+        fprintf(o, "lm %d", nc);
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) fprintf(o, " %.9g", f1->Tcw.at<float>(r, c));
+        fprintf(o, "\n");
         fclose(o);
         frame::shutdown();
     } catch (const std::exception &e) {

@@ -1,7 +1,7 @@
 // pnpmatch.h — drop-in for the reference's include/pnpmatch.h.  The Hamming work of
 // poseEstimationPnP (src/pnpmatch.cc:61-199) and find_feature_matches (:253-300) runs on the
-// device; findFundamentalMat / solvePnPRansac stay with whatever OpenCV the integrator links and
-// are reached through the two hooks below (they are outside the hot path).
+// device; findFundamentalMat stays with whatever OpenCV the integrator links (hook below); the PnP hook
+// defaults to the device RANSAC (svo_pnp_ransac) and can be pointed back at cv::solvePnPRansac.
 #pragma once
 #include <functional>
 #include <set>
@@ -24,9 +24,13 @@ public:
     static int match_last_frame(frame *cur, frame &last, const cv::Mat &fundamental_matrix);        // pass 1
     static int match_local_map(frame *cur, std::set<mappoint *> &localmappoints);                   // pass 2
 
-    // Host hooks (unset: the step is skipped).  F from matched points (cv::findFundamentalMat, :336);
+    // Hooks (unset: the step is skipped).  F from matched points (cv::findFundamentalMat, :336);
     // pose from 3D-2D pairs (cv::solvePnPRansac + Rodrigues, :227-247) returning a 4x4 CV_32F Tcl.
+    // pnp_solver starts out as device_pnp: 100 samples, 8 px, like the reference's arguments.
     static std::function<cv::Mat(const std::vector<cv::Point2f> &, const std::vector<cv::Point2f> &)> fundamental_solver;
     static std::function<bool(const std::vector<cv::Mat> &pts3d, const std::vector<cv::Point2f> &pts2d, const cv::Mat &K,
                               cv::Mat &Tcl, int &inliers)> pnp_solver;
+    static bool device_pnp(const std::vector<cv::Mat> &pts3d, const std::vector<cv::Point2f> &pts2d, const cv::Mat &K,
+                           cv::Mat &Tcl, int &inliers);
+    static std::vector<unsigned char> last_pnp_inliers;   // flags of the last device_pnp call, pts2d order
 };

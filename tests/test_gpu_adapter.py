@@ -54,7 +54,7 @@ def test_adapter_two_frames(tmp_path):
         paths.append(p)
     out = str(tmp_path / "out.txt")
     subprocess.check_call([exe, str(W), str(H), str(NF)] + paths + [out])
-    kp_rows, map_rank, scores = [], {}, {}
+    kp_rows, map_rank, scores, pairs, pnp, lm = [], {}, {}, [], None, None
     for line in open(out):
         t = line.split()
         if t[0] == "counts":
@@ -65,6 +65,12 @@ def test_adapter_two_frames(tmp_path):
             map_rank[int(t[1])] = int(t[2])
         elif t[0] == "score":
             scores[int(t[1])] = np.float32(t[2])
+        elif t[0] == "pair":
+            pairs.append([np.float32(v) for v in t[2:7]])
+        elif t[0] == "pnp":
+            pnp = t[1:]
+        elif t[0] == "lm":
+            lm = t[1:]
     cal = synth.KITTI_04_12
     bf = np.float32(379.8145)
     b = np.float32(bf / np.float32(707.0912))
@@ -108,5 +114,18 @@ def test_adapter_two_frames(tmp_path):
     for j in np.nonzero(g2["claim_row"] >= 10 ** 6)[0]:
         expect[j] = rows2[g2["claim_row"][j] - 10 ** 6]
     assert ([int(r[8]) for r in kp_rows] == expect).all()
+    # pose stage: device PnP RANSAC on the matched 3D-2D pairs, SetPose, Optimizer::PoseOptimization
+    pairs = np.array(pairs, np.float32)
+    nm = int((expect >= 0).sum())
+    assert len(pairs) == nm and int(lm[0]) == nm
+    assert (pairs[:, 3] == k1["x"][expect >= 0]).all() and (pairs[:, 4] == k1["y"][expect >= 0]).all()
+    K4 = (np.float32(707.0912), np.float32(707.0912), np.float32(601.8873), np.float32(183.1104))
+    n, Ro, to, mask, info = O.pnp_ransac(pairs[:, :3], pairs[:, 3:], K4, 100, 8.0, 1, 10)
+    assert int(pnp[0]) == 1 and int(pnp[1]) == n and n > 30
+    Tcl = np.array([np.float32(v) for v in pnp[2:18]], np.float32).reshape(4, 4)
+    assert np.abs(Tcl[:3, :3] - Ro).max() < 1e-5 and np.abs(Tcl[:3, 3] - to).max() < 1e-5
+    To, its, chi = O.pose_optimize(pairs[:, :3], pairs[:, 3:], K4, Tcl)
+    Tlm = np.array([np.float32(v) for v in lm[1:17]], np.float32).reshape(4, 4)
+    assert np.abs(Tlm - To).max() < 1e-5
     for p in (p0, p0r, p1, p1r):
         O.pyramid_free(p)
