@@ -260,6 +260,29 @@ def run_gpu(args, rank, world, local_rank):
         lat.append((time.perf_counter() - t0) * 1e3)
     p50 = float(np.median(lat))
 
+    # pose stage (not part of the headline metric): PnP RANSAC + pose-only LM for a batch of
+    # B frames with ~1000 matched map points each, through the synchronous C-ABI calls (host buffers, copies included)
+    pose = None
+    if rank == 0:
+        probs = []
+        for i in range(B):
+            Xw, obs, K4, Rt, tt, _ = synth.pose_problem(1000, 500 + i, 0.3, 0.5, cal=CAL)
+            probs.append(dict(pts3d=Xw, pts2d=obs, K=K4))
+        for _ in range(3):
+            rr = ctx.pnp_ransac(probs); ctx.pose_optimize(probs)
+        t_r, t_l = [], []
+        for _ in range(10):
+            t0 = time.perf_counter(); rr = ctx.pnp_ransac(probs); t1 = time.perf_counter()
+            for q, r in zip(probs, rr):
+                T = np.eye(4, dtype=np.float32); T[:3, :3] = r["R"]; T[:3, 3] = r["t"]; q["Tcw"] = T
+            t2 = time.perf_counter(); ctx.pose_optimize(probs); t3 = time.perf_counter()
+            t_r.append((t1 - t0) * 1e3); t_l.append((t3 - t2) * 1e3)
+        pose = {"frames_per_call": B, "points_per_frame": 1000, "outlier_fraction": 0.3,
+                "pnp_ransac_ms_per_call": float(np.median(t_r)), "pose_optimize_ms_per_call": float(np.median(t_l)),
+                "frames_per_s": B / ((np.median(t_r) + np.median(t_l)) * 1e-3),
+                "note": "wall clock around svo_pnp_ransac (100 samples, 8 px, refit) and svo_pose_optimize (g2o LM, 10 iterations), "
+                        "host buffers in and out; includes the Python binding's packing"}
+
     ms_dev, ms_e2e = grp.max_over_ranks([ms_dev, ms_e2e])
     frames_total = int(grp.sum_over_ranks([args.steps * B])[0])
     out = None
@@ -335,6 +358,7 @@ def run_gpu(args, rank, world, local_rank):
                               "note": "stage_ms_per_step, kernel_ms_per_launch and roofline.launch_ms come from this pass"},
             "stage_ms_per_step": kernels, "kernel_ms_per_launch": {k: stage.get(v[0], 0.0) for k, v in single.items()}, "p50_ms_per_frame_single": p50, "wall_ms_per_step": wall_dev / args.steps,
         }
+        out["pose_stage"] = pose
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(seq, cores=1, budget_s=args.cpu_seconds)
     ctx.close()

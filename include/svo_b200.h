@@ -60,6 +60,7 @@ typedef struct svo_config {
     int lanes;           /* independent pipeline lanes (stream + buffers each), >= 1              */
     int max_rows;        /* capacity of one greedy row set / BF train set (e.g. 5000-row local map)*/
     void *stream;        /* optional cudaStream_t for lane 0 (NULL: the context creates its own)  */
+    int max_channels;    /* 1 (default) or 3: 3 sizes the input staging for interleaved BGR images  */
 } svo_config;
 
 void svo_default_config(svo_config *cfg);
@@ -85,6 +86,14 @@ int svo_get_geometry(const svo_ctx *ctx, int *lw, int *lh, float *lscale, int *q
  * The pyramid/keypoints of `cam` stay resident for svo_stereo_sparse. */
 int svo_extract(svo_ctx *ctx, int cam, const uint8_t *gray, int stride, int w, int h,
                 svo_keypoint *kp_out, uint8_t *desc_out, int cap);
+
+/* Same for an interleaved 8-bit BGR image (cv::imread of a colour KITTI frame, main.cpp:160-161):
+ * cv::ORB converts colour input with cvtColor(BGR2GRAY) before anything else; the conversion runs on the
+ * device while the image is repacked, gray = (B*3735 + G*19235 + R*9798 + 16384) >> 15 (OpenCV 4.x's
+ * 15-bit fixed point, equal to cv2.cvtColor on all 2^24 colours; OpenCV 3.2 used 14-bit weights that
+ * differ on 0.3 % of colours).  Needs svo_config.max_channels = 3.  stride in bytes (>= 3*w). */
+int svo_extract_bgr(svo_ctx *ctx, int cam, const uint8_t *bgr, int stride, int w, int h,
+                    svo_keypoint *kp_out, uint8_t *desc_out, int cap);
 
 /* north_star's ComputeStereoMatches stage: fills what frame::computekeypoint_r and
  * frame::disp2Depth deliver at keypoint pixels (src/frame.cc:122-164): u_right[i]
@@ -188,6 +197,8 @@ typedef struct svo_frame_in {
     const int32_t *map_prev_row; /* n_map (may be NULL): index of the pass-1 row holding the
                                     same map point, -1 if none; such rows are skipped in pass 2
                                     when pass 1 claimed them (observations.count, :167)   */
+    int channels;                /* 0 or 1: gray; 3: interleaved BGR (both images), converted on
+                                    the device like svo_extract_bgr                        */
 } svo_frame_in;
 
 typedef struct svo_frame_out {

@@ -184,3 +184,12 @@ def pnp_ransac(pts3d, pts2d, K4, iterations=100, reproj_err=8.0, seed=1, refine_
     n = L.svo_o_pnp_ransac(_p(p3), _p(p2), len(p3), fx, fy, cx, cy, iterations, C.c_float(reproj_err),
                            C.c_uint32(seed), refine_iters, _p(R), _p(t), _p(mask), _p(info))
     return n, R, t, mask, info
+
+
+def bgr2gray(bgr):
+    """cv::cvtColor(BGR2GRAY) restatement (what cv::ORB applies to colour input)."""
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    h, w, _ = bgr.shape
+    out = np.empty((h, w), np.uint8)
+    lib().svo_o_bgr2gray(_p(bgr), w, h, bgr.strides[0], _p(out), w)
+    return out

@@ -646,3 +646,17 @@ int svo_o_stereo_sparse(const svo_o_keypoint *kl, const uint8_t *dl, int nl,
     free(acc);
     return nacc;
 }
+
+/* cv::cvtColor(BGR2GRAY) on 8-bit input, the first thing cv::ORB::detectAndCompute does with a colour image
+ * (the reference passes whatever cv::imread(.., CV_LOAD_IMAGE_UNCHANGED) returned, main.cpp:160-161, to
+ * frame::featuredetect, src/frame.cc:75-79).  OpenCV 4.x fixed point: 15-bit weights B 3735, G 19235, R 9798,
+ * round to nearest.  Pinned against cv2.cvtColor on all 2^24 colours (tests/test_oracle_vs_cv2.py).
+ * (OpenCV 3.2 used the 14-bit weights 1868/9617/4899, which differ on 0.3 % of colours.) */
+void svo_o_bgr2gray(const uint8_t *bgr, int w, int h, int sstride, uint8_t *gray, int dstride)
+{
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const uint8_t *p = bgr + (size_t)y * sstride + 3 * x;
+            gray[(size_t)y * dstride + x] = (uint8_t)((p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + 16384) >> 15);
+        }
+}

@@ -56,6 +56,7 @@ int svo_o_stereo_sparse(const svo_o_keypoint *kl, const uint8_t *dl, int nl,
                         const svo_o_keypoint *kr, const uint8_t *dr, int nr,
                         const svo_o_pyramid *pl, const svo_o_pyramid *pr,
                         float bf, float b, float *u_right, float *depth, int32_t *match_r, int32_t *sad);
+void svo_o_bgr2gray(const uint8_t *bgr, int w, int h, int sstride, uint8_t *gray, int dstride);
 /* pose stage (svo_pose_oracle.c) */
 int svo_o_pose_optimize(const float *Xw, const float *obs, int n, float fx, float fy, float cx, float cy,
                         const float *Tcw_in, float *Tcw_out, int iterations, double *stats);

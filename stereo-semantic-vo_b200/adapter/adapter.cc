@@ -73,6 +73,7 @@ svo_ctx *frame::engine(int width, int height)
     cfg.device = g_set.device; cfg.width = width; cfg.height = height;
     cfg.nfeatures = g_set.nfeatures; cfg.nlevels = g_set.nlevels; cfg.scale_factor = g_set.scale;
     cfg.fast_threshold = g_set.fast; cfg.max_batch = 1; cfg.lanes = 1; cfg.max_rows = g_set.max_rows;
+    cfg.max_channels = 3;   // colour KITTI frames (image_2/image_3) are converted on the device
     svo_ctx *ctx = nullptr;
     const int rc = svo_create(&cfg, &ctx);
     if (rc != SVO_OK) {
@@ -97,11 +98,21 @@ cv::Mat svo_to_gray(const cv::Mat &img)
     for (int y = 0; y < img.rows; ++y) {
         const uint8_t *s = img.ptr(y);
         uint8_t *d = g.ptr(y);
-        for (int x = 0; x < img.cols; ++x)   // OpenCV BGR2GRAY, 14-bit fixed point
-            d[x] = (uint8_t)((s[3 * x] * 1868 + s[3 * x + 1] * 9617 + s[3 * x + 2] * 4899 + 8192) >> 14);
+        for (int x = 0; x < img.cols; ++x)   // OpenCV 4.x BGR2GRAY, 15-bit fixed point (same weights as the device path)
+            d[x] = (uint8_t)((s[3 * x] * 3735 + s[3 * x + 1] * 19235 + s[3 * x + 2] * 9798 + 16384) >> 15);
     }
     return g;
 }
+
+namespace {
+// cv::ORB on a gray or BGR image: colour input is converted on the device (svo_extract_bgr)
+int extract_any(svo_ctx *ctx, int cam, const cv::Mat &img, svo_keypoint *kp, uint8_t *desc, int cap)
+{
+    if (img.channels() == 3)
+        return svo_extract_bgr(ctx, cam, img.data, (int)img.step, img.cols, img.rows, kp, desc, cap);
+    return svo_extract(ctx, cam, img.data, (int)img.step, img.cols, img.rows, kp, desc, cap);
+}
+}  // namespace
 
 frame::frame() : N(0), timestamp(0), id(0), have_detected(false), width(0), height(0), fx(0), fy(0), cx(0), cy(0), bf(0) {}
 
@@ -162,12 +173,12 @@ void frame::SetPose(cv::Mat mTcw)
 
 void frame::featuredetect(cv::Mat &img)
 {
-    cv::Mat gray = svo_to_gray(img);
+    const cv::Mat &gray = img;
     svo_ctx *ctx = engine(gray.cols, gray.rows);
     const int cap = g_set.nfeatures * 2 + 1024;
     std::vector<svo_keypoint> kp((size_t)cap);
     cv::Mat desc(cap, 32, CV_8U);
-    const int n = svo_extract(ctx, SVO_CAM_LEFT, gray.data, (int)gray.step, gray.cols, gray.rows, kp.data(), desc.data, cap);
+    const int n = extract_any(ctx, SVO_CAM_LEFT, gray, kp.data(), desc.data, cap);
     if (n < 0) die(ctx, "svo_extract", n);
     const int m = n < cap ? n : cap;
     keypoints_l.resize((size_t)m);
@@ -187,9 +198,9 @@ cv::Mat frame::MB(cv::Mat &left, cv::Mat &right)
     // Sparse replacement of the dense MSA solve: extract the right image, run the row-band
     // Hamming + SAD stage, and scatter disparity / depth at the left keypoints' pixels.
     (void)left;
-    cv::Mat gray = svo_to_gray(right);
+    const cv::Mat &gray = right;
     svo_ctx *ctx = engine(gray.cols, gray.rows);
-    int n = svo_extract(ctx, SVO_CAM_RIGHT, gray.data, (int)gray.step, gray.cols, gray.rows, nullptr, nullptr, 0);
+    int n = extract_any(ctx, SVO_CAM_RIGHT, gray, nullptr, nullptr, 0);
     if (n < 0) die(ctx, "svo_extract(right)", n);
     const int cap = (int)keypoints_l.size();
     u_right.assign((size_t)cap, -1.f); kp_depth.assign((size_t)cap, -1.f);
@@ -308,14 +319,14 @@ void pnpmatch::find_feature_matches(const cv::Mat &img_1, const cv::Mat &img_2, 
 {
     // The reference re-runs ORB on both images here (4 redundant passes, src/pnpmatch.cc:268-273);
     // same results, so this does too but on the device, then BF-matches and filters.
-    const cv::Mat g1 = svo_to_gray(img_1), g2 = svo_to_gray(img_2);
+    const cv::Mat &g1 = img_1, &g2 = img_2;
     svo_ctx *ctx = frame::engine(g1.cols, g1.rows);
     const int cap = g_set.nfeatures * 2 + 1024;
     std::vector<svo_keypoint> k1((size_t)cap), k2((size_t)cap);
     cv::Mat d1(cap, 32, CV_8U), d2(cap, 32, CV_8U);
-    int n1 = svo_extract(ctx, SVO_CAM_LEFT, g1.data, (int)g1.step, g1.cols, g1.rows, k1.data(), d1.data, cap);
+    int n1 = extract_any(ctx, SVO_CAM_LEFT, g1, k1.data(), d1.data, cap);
     if (n1 < 0) die(ctx, "svo_extract", n1);
-    int n2 = svo_extract(ctx, SVO_CAM_RIGHT, g2.data, (int)g2.step, g2.cols, g2.rows, k2.data(), d2.data, cap);
+    int n2 = extract_any(ctx, SVO_CAM_RIGHT, g2, k2.data(), d2.data, cap);
     if (n2 < 0) die(ctx, "svo_extract", n2);
     auto fill = [](std::vector<cv::KeyPoint> &out, const std::vector<svo_keypoint> &in, int n) {
         out.resize((size_t)n);

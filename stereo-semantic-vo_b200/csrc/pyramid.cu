@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(256) k_resize(Bufs b, Geom g, int l, int slot0
 
 // Level 0 is read where it lies in device memory (the caller's device buffer, or the lane's landing zone
 // for host inputs; rows `stride` bytes apart, any alignment) and repacked into the 16-byte-pitched level-0
-// layout.  One thread per 16 output bytes.
+// layout.  One thread per 16 output bytes.  Interleaved BGR sources (SVO_STRIDE_BGR set in the stride word) are
+// converted on the way with OpenCV's 15-bit fixed-point weights (cv::ORB's cvtColor(BGR2GRAY) of colour input).
 __global__ void __launch_bounds__(256) k_unpack(Bufs b, Geom g, int slot0, const FramePtrs *__restrict__ fp,
                                                 const int *__restrict__ strides)
 {
@@ -78,14 +79,26 @@ __global__ void __launch_bounds__(256) k_unpack(Bufs b, Geom g, int slot0, const
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= per_row * L.h) return;
     const int y = i / per_row, x = (i - y * per_row) << 4;
-    const int stride = strides[blockIdx.y];
-    if (stride <= 0) return;                      // this image was uploaded with a 2-D copy
+    const int sraw = strides[blockIdx.y];
+    if (sraw <= 0) return;                        // this image was uploaded with a 2-D copy
+    const int stride = sraw & (SVO_STRIDE_BGR - 1);
     const FramePtrs &F = fp[blockIdx.y >> 1];
-    const uint8_t *src = ((blockIdx.y & 1) ? F.right : F.left) + (size_t)y * stride + x;
+    const uint8_t *img = (blockIdx.y & 1) ? F.right : F.left;
     uint32_t w[4] = {0, 0, 0, 0};
+    if (sraw & SVO_STRIDE_BGR) {
+        const uint8_t *src = img + (size_t)y * stride + 3 * x;
 #pragma unroll
-    for (int k = 0; k < 16; ++k)
-        if (x + k < L.w) w[k >> 2] |= (uint32_t)src[k] << (8 * (k & 3));
+        for (int k = 0; k < 16; ++k)
+            if (x + k < L.w) {
+                const uint32_t v = (src[3 * k] * 3735u + src[3 * k + 1] * 19235u + src[3 * k + 2] * 9798u + 16384u) >> 15;
+                w[k >> 2] |= v << (8 * (k & 3));
+            }
+    } else {
+        const uint8_t *src = img + (size_t)y * stride + x;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (x + k < L.w) w[k >> 2] |= (uint32_t)src[k] << (8 * (k & 3));
+    }
     *reinterpret_cast<uint4 *>(b.pyr + (size_t)(slot0 + blockIdx.y) * g.pyr_bytes + L.off + (size_t)y * L.pitch + x) =
         make_uint4(w[0], w[1], w[2], w[3]);
 }

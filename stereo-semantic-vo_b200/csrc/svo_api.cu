@@ -93,6 +93,9 @@ struct svo_ctx {
     std::vector<uint32_t> rtab_host;
     long long launches;
     size_t stage_img_bytes;
+    uint8_t *sync_stage;     // landing zone of svo_extract_bgr (one colour image)
+    FramePtrs *sync_fp_d, *sync_fp_h;
+    int *sync_str_d, *sync_str_h;
     bool profiling;
     bool sync_have[2];
     char err[512];
@@ -443,7 +446,7 @@ void svo_default_config(svo_config *c)
     memset(c, 0, sizeof(*c));
     c->device = 0; c->width = 1241; c->height = 376;
     c->nfeatures = 2000; c->nlevels = 8; c->scale_factor = 1.2f; c->fast_threshold = 20;
-    c->max_batch = 1; c->lanes = 1; c->max_rows = 5000; c->stream = nullptr;
+    c->max_batch = 1; c->lanes = 1; c->max_rows = 5000; c->stream = nullptr; c->max_channels = 1;
 }
 
 const char *svo_version(void) { return "svo_b200 0.1 (sm_100a)"; }
@@ -474,10 +477,13 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
     svo_ctx *ctx = new svo_ctx();
     ctx->cfg = *cfg; ctx->launches = 0; ctx->profiling = false; ctx->err[0] = 0;
     ctx->sync_st = nullptr; ctx->sync_have[0] = ctx->sync_have[1] = false;
+    ctx->sync_stage = nullptr;
+    if (ctx->cfg.max_channels == 0) ctx->cfg.max_channels = 1;
     *out = ctx;  // returned even on failure so the caller can read svo_last_error, then svo_destroy
     const svo_config &c = ctx->cfg;
     if (c.nlevels < 1 || c.nlevels > SVO_MAX_LEVELS || c.nfeatures < 1 || c.nfeatures > 60000 || c.max_batch < 1 ||
-        c.lanes < 1 || c.max_rows < 1 || c.max_rows > 40000 || c.width < 64 || c.height < 64 || !(c.scale_factor > 1.f))
+        c.lanes < 1 || c.max_rows < 1 || c.max_rows > 40000 || c.width < 64 || c.height < 64 || !(c.scale_factor > 1.f) ||
+        (c.max_channels != 1 && c.max_channels != 3))
         return fail(ctx, SVO_E_INVALID, "invalid configuration");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -533,7 +539,12 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
         setup_pose() != 0)
         return fail(ctx, SVO_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
     CU(cudaStreamCreateWithFlags(&ctx->sync_st, cudaStreamNonBlocking));
-    ctx->stage_img_bytes = (size_t)g.H * (g.W + 256);
+    ctx->stage_img_bytes = (size_t)g.H * ((size_t)g.W * c.max_channels + 256);
+    if (c.max_channels == 3) {
+        TRY(dalloc(ctx, &ctx->sync_stage, ctx->stage_img_bytes));
+        TRY(dalloc(ctx, &ctx->sync_fp_d, 1)); TRY(halloc(ctx, &ctx->sync_fp_h, 1));
+        TRY(dalloc(ctx, &ctx->sync_str_d, 2)); TRY(halloc(ctx, &ctx->sync_str_h, 2));
+    }
     ctx->lanes.resize(c.lanes);
     for (int i = 0; i < c.lanes; ++i) {
         Lane &l = ctx->lanes[i];
@@ -601,16 +612,53 @@ int svo_copy_to_device(svo_ctx *ctx, void *dst, const void *src, size_t bytes)
 }
 
 // ------------------------------------------------------------------------------ sync API
+namespace {
+int extract_sync(svo_ctx *ctx, int cam, const uint8_t *img, int stride, int w, int h, int ch,
+                 svo_keypoint *kp_out, uint8_t *desc_out, int cap);
+}
+
 int svo_extract(svo_ctx *ctx, int cam, const uint8_t *gray, int stride, int w, int h,
                 svo_keypoint *kp_out, uint8_t *desc_out, int cap)
 {
+    return extract_sync(ctx, cam, gray, stride, w, h, 1, kp_out, desc_out, cap);
+}
+
+int svo_extract_bgr(svo_ctx *ctx, int cam, const uint8_t *bgr, int stride, int w, int h,
+                    svo_keypoint *kp_out, uint8_t *desc_out, int cap)
+{
+    if (ctx && ctx->cfg.max_channels < 3) return fail(ctx, SVO_E_INVALID, "svo_extract_bgr: the context was created with max_channels = 1");
+    return extract_sync(ctx, cam, bgr, stride, w, h, 3, kp_out, desc_out, cap);
+}
+
+namespace {
+int extract_sync(svo_ctx *ctx, int cam, const uint8_t *gray, int stride, int w, int h, int ch,
+                 svo_keypoint *kp_out, uint8_t *desc_out, int cap)
+{
     if (!ctx || !gray || cam < 0 || cam > 1 || cap < 0) return fail(ctx, SVO_E_INVALID, "svo_extract: bad argument");
     const Geom &g = ctx->g;
-    if (w != g.W || h != g.H || stride < w) return fail(ctx, SVO_E_INVALID, "svo_extract: image is %dx%d, context is %dx%d", w, h, g.W, g.H);
+    if (w != g.W || h != g.H || stride < w * ch || stride >= SVO_STRIDE_BGR)
+        return fail(ctx, SVO_E_INVALID, "svo_extract: image is %dx%d (stride %d), context is %dx%d", w, h, stride, g.W, g.H);
     CU(cudaSetDevice(ctx->cfg.device));
     const int slot = ctx->sync_slot0 + cam;
     cudaStream_t st = ctx->sync_st;
-    TRY(upload_image(ctx, slot, gray, stride, st));
+    if (ch == 1) TRY(upload_image(ctx, slot, gray, stride, st));
+    else {
+        // colour: the rows land as they are (one contiguous copy, or read in place when already on the device) and
+        // k_unpack converts while it repacks
+        const size_t bytes = (size_t)stride * (h - 1) + (size_t)w * 3;
+        const uint8_t *src = gray;
+        if (!device_readable(gray)) {
+            if (bytes > ctx->stage_img_bytes) return fail(ctx, SVO_E_CAPACITY, "svo_extract_bgr: rows %d bytes apart exceed the staging capacity", stride);
+            CU(cudaMemcpyAsync(ctx->sync_stage, gray, bytes, cudaMemcpyHostToDevice, st));
+            src = ctx->sync_stage;
+        }
+        memset(ctx->sync_fp_h, 0, sizeof(FramePtrs));
+        ctx->sync_fp_h->left = src; ctx->sync_fp_h->right = src;
+        ctx->sync_str_h[0] = ctx->sync_str_h[1] = stride | SVO_STRIDE_BGR;
+        CU(cudaMemcpyAsync(ctx->sync_fp_d, ctx->sync_fp_h, sizeof(FramePtrs), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->sync_str_d, ctx->sync_str_h, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
+        launch_unpack(ctx->b, g, slot, 1, ctx->sync_fp_d, ctx->sync_str_d, st, &ctx->launches);
+    }
     enqueue_extract(ctx, slot, 1, st, nullptr);
     int hdr[2] = {0, 0};
     CU(cudaMemcpyAsync(&hdr[0], ctx->b.nkp + slot, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -625,6 +673,7 @@ int svo_extract(svo_ctx *ctx, int cam, const uint8_t *gray, int stride, int w, i
     ctx->sync_have[cam] = true;
     return hdr[0];
 }
+}  // namespace
 
 int svo_stereo_sparse(svo_ctx *ctx, float bf, float baseline, float *u_right, float *depth,
                       int32_t *match_r, int32_t *sad, int cap)
@@ -886,9 +935,12 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
     bool any_prev = false, any_map = false;
     for (int i = 0; i < n; ++i) {
         const svo_frame_in &f = frames[i];
-        if (!f.left || !f.right || f.stride < g.W || f.n_prev < 0 || f.n_map < 0 || f.n_prev > R || f.n_map > R ||
-            (f.n_prev && !f.prev_desc) || (f.n_map && !f.map_desc) || !(f.baseline > 0.f))
-            return fail(ctx, SVO_E_INVALID, "svo_batch_submit: frame %d has bad inputs", i);
+        const int ch = f.channels == 3 ? 3 : 1;
+        if (!f.left || !f.right || f.stride < g.W * ch || f.stride >= SVO_STRIDE_BGR || f.n_prev < 0 || f.n_map < 0 || f.n_prev > R ||
+            f.n_map > R || (f.n_prev && !f.prev_desc) || (f.n_map && !f.map_desc) || !(f.baseline > 0.f) ||
+            (f.channels != 0 && f.channels != 1 && f.channels != 3) || ch > ctx->cfg.max_channels)
+            return fail(ctx, SVO_E_INVALID, "svo_batch_submit: frame %d has bad inputs%s", i,
+                        ch > ctx->cfg.max_channels ? " (BGR input needs svo_config.max_channels = 3)" : "");
         any_prev |= f.n_prev > 0; any_map |= f.n_map > 0;
     }
     L.in.assign(frames, frames + n);
@@ -910,13 +962,16 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
     for (int i = 0; i < n; ++i) {
         const svo_frame_in &f = frames[i];
         FramePtrs &P = L.h_fp[i];
-        const size_t img_bytes = (size_t)f.stride * (g.H - 1) + g.W;
+        const int ch = f.channels == 3 ? 3 : 1;
+        const size_t img_bytes = (size_t)f.stride * (g.H - 1) + (size_t)g.W * ch;
         const uint8_t *srcs[2] = {f.left, f.right};
         const void **fld[2] = {(const void **)&P.left, (const void **)&P.right};
         for (int s = 0; s < 2; ++s) {
             if (img_bytes <= ctx->stage_img_bytes || device_readable(srcs[s])) {
                 place(srcs[s], img_bytes, fld[s], false);
-                L.h_strides[2 * i + s] = f.stride;
+                L.h_strides[2 * i + s] = f.stride | (ch == 3 ? SVO_STRIDE_BGR : 0);
+            } else if (ch == 3) {
+                return fail(ctx, SVO_E_CAPACITY, "svo_batch_submit: frame %d: BGR rows %d bytes apart exceed the staging capacity", i, f.stride);
             } else {   // oversized stride: 2-D copy straight into the level-0 slot
                 *fld[s] = nullptr;
                 TRY(upload_image(ctx, L.slot0 + 2 * i + s, srcs[s], f.stride, st));

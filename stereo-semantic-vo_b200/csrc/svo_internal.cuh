@@ -17,6 +17,7 @@
 #define SVO_EDGE 31            // cv::ORB edgeThreshold
 #define SVO_FAST_BAND 8        // output rows per FAST band (one CTA each)
 #define SVO_SHORT_CAP 128      // short-list entries per greedy row before the full-scan path
+#define SVO_STRIDE_BGR (1 << 30)  // flag in a per-image stride word: the source is interleaved BGR
 #define SVO_STATUS_OVERFLOW 1  // bit set in the per-image status word on a capacity overflow
 #define SVO_STATUS_DEPTH 2     // introselect reached its depth limit (heap-select path ran)
 

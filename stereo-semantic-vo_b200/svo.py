@@ -24,7 +24,8 @@ STAGES = ("total", "h2d", "pyramid", "fast", "select1", "harris", "select2", "bl
 class Config(C.Structure):
     _fields_ = [("device", C.c_int), ("width", C.c_int), ("height", C.c_int), ("nfeatures", C.c_int),
                 ("nlevels", C.c_int), ("scale_factor", C.c_float), ("fast_threshold", C.c_int),
-                ("max_batch", C.c_int), ("lanes", C.c_int), ("max_rows", C.c_int), ("stream", C.c_void_p)]
+                ("max_batch", C.c_int), ("lanes", C.c_int), ("max_rows", C.c_int), ("stream", C.c_void_p),
+                ("max_channels", C.c_int)]
 
 
 class Veto(C.Structure):
@@ -36,7 +37,7 @@ class FrameIn(C.Structure):
     _fields_ = [("left", C.c_void_p), ("right", C.c_void_p), ("stride", C.c_int),
                 ("bf", C.c_float), ("baseline", C.c_float),
                 ("prev_desc", C.c_void_p), ("n_prev", C.c_int), ("prev_live", C.c_void_p),
-                ("map_desc", C.c_void_p), ("n_map", C.c_int), ("map_prev_row", C.c_void_p)]
+                ("map_desc", C.c_void_p), ("n_map", C.c_int), ("map_prev_row", C.c_void_p), ("channels", C.c_int)]
 
 
 class FrameOut(C.Structure):
@@ -65,7 +66,7 @@ class SvoError(RuntimeError):
 
 
 EXPORTS = ["svo_default_config", "svo_version", "svo_create", "svo_destroy", "svo_last_error", "svo_get_geometry",
-           "svo_extract", "svo_stereo_sparse", "svo_match_bf", "svo_match_greedy", "svo_disp2depth",
+           "svo_extract", "svo_extract_bgr", "svo_stereo_sparse", "svo_match_bf", "svo_match_greedy", "svo_disp2depth",
            "svo_batch_submit", "svo_batch_wait", "svo_batch_result", "svo_alloc_pinned", "svo_free_pinned",
            "svo_alloc_device", "svo_free_device", "svo_copy_to_device", "svo_launch_count", "svo_batch_stage_ms",
            "svo_set_profiling", "svo_lane_stream", "svo_debug_tap", "svo_debug_retain_best",
@@ -90,6 +91,7 @@ def load():
     L.svo_destroy.restype = None
     L.svo_get_geometry.argtypes = [C.c_void_p] + [C.c_void_p] * 4
     L.svo_extract.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.svo_extract_bgr.argtypes = L.svo_extract.argtypes
     L.svo_stereo_sparse.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.svo_match_bf.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.svo_match_greedy.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
@@ -140,13 +142,14 @@ class Context:
     """One svo_ctx: device buffers, streams and pipeline lanes for one image size."""
 
     def __init__(self, width=1241, height=376, nfeatures=2000, nlevels=8, scale_factor=1.2, fast_threshold=20,
-                 max_batch=1, lanes=1, max_rows=5000, device=0, stream=None):
+                 max_batch=1, lanes=1, max_rows=5000, device=0, stream=None, max_channels=1):
         self.lib = load()
         cfg = Config()
         self.lib.svo_default_config(C.byref(cfg))
         cfg.device, cfg.width, cfg.height, cfg.nfeatures = device, width, height, nfeatures
         cfg.nlevels, cfg.scale_factor, cfg.fast_threshold = nlevels, scale_factor, fast_threshold
         cfg.max_batch, cfg.lanes, cfg.max_rows, cfg.stream = max_batch, lanes, max_rows, stream
+        cfg.max_channels = max_channels
         self.cfg = cfg
         self.h = C.c_void_p()
         rc = self.lib.svo_create(C.byref(cfg), C.byref(self.h))
@@ -182,12 +185,15 @@ class Context:
 
     # ---- synchronous drop-ins -------------------------------------------------------
     def extract(self, gray, cam=0, cap=None):
-        """frame::featuredetect -> (keypoints[KP_DTYPE], descriptors[n,32])."""
-        gray = np.ascontiguousarray(gray, np.uint8)
-        h, w = gray.shape
+        """frame::featuredetect -> (keypoints[KP_DTYPE], descriptors[n,32]).  (h, w) gray or (h, w, 3) BGR."""
+        gray = np.asarray(gray, np.uint8)
+        if gray.strides[-1] != 1 or (gray.ndim == 3 and gray.strides[1] != 3):
+            gray = np.ascontiguousarray(gray)
+        h, w = gray.shape[:2]
         cap = cap or (self.nfeatures * 2 + 1024)
         kp = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8)
-        n = self._chk(self.lib.svo_extract(self.h, cam, _p(gray), gray.strides[0], w, h, _p(kp), _p(desc), cap))
+        fn = self.lib.svo_extract_bgr if gray.ndim == 3 else self.lib.svo_extract
+        n = self._chk(fn(self.h, cam, _p(gray), gray.strides[0], w, h, _p(kp), _p(desc), cap))
         n = min(n, cap)
         return kp[:n].copy(), desc[:n].copy()
 
@@ -292,9 +298,11 @@ class Context:
                     keep.append(v)
                     setattr(fi, side, v.ctypes.data)
                     fi.stride = v.strides[0]
+                    fi.channels = 3 if v.ndim == 3 else 1
                 else:
                     setattr(fi, side, v)
                     fi.stride = f["stride"]
+                    fi.channels = f.get("channels", 1)
             fi.bf, fi.baseline = f["bf"], f["baseline"]
             for name, cnt in (("prev_desc", "n_prev"), ("map_desc", "n_map")):
                 v = f.get(name)

@@ -144,3 +144,15 @@ def pose_problem(n, seed, outlier_frac=0.3, noise=0.5, cal=None, shape=K_SHAPE, 
     bad = rng.random(n) < outlier_frac
     obs[bad] = np.stack([rng.uniform(0, shape[1], int(bad.sum())), rng.uniform(0, shape[0], int(bad.sum()))], 1)
     return Xw.astype(np.float32), obs.astype(np.float32), (fx, fy, cx, cy), R, t, bad
+
+
+def colourise(gray, seed):
+    """Interleaved BGR image whose channels are seeded per-pixel perturbations of `gray` (a colour KITTI frame
+    stand-in: image_2 / image_3 read with cv::imread(.., UNCHANGED), main.cpp:160-161)."""
+    rng = np.random.default_rng(seed)
+    g = gray.astype(np.int16)
+    out = np.empty(gray.shape + (3,), np.uint8)
+    gains = (0.85, 1.0, 1.15)
+    for c in range(3):
+        out[..., c] = np.clip(g * gains[c] + rng.integers(-12, 13, gray.shape) + (8, 0, -8)[c], 0, 255).astype(np.uint8)
+    return out

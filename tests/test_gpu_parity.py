@@ -437,3 +437,55 @@ def test_batch_stage_combinations_and_fallback_path(ctxK):
     assert not r["p1_row_claimed"].any() and not r["p2_row_claimed"].any()
     assert (r["p1_best_idx"] == -1).all() and (r["p1_best"] == 256).all() and (r["p1_second"] == 256).all()
     check(jobs[1], ctxK.batch_result(1, 1))
+
+
+# ---- colour input (the staging step before the path) -----------------------------
+def test_extract_bgr_matches_oracle_and_gray_path(svo):
+    H, W = 240, 400
+    c = svo.Context(W, H, nfeatures=500, max_batch=2, lanes=1, max_rows=1000, max_channels=3)
+    try:
+        gray = synth.texture((H, W), 33)
+        col = synth.colourise(gray, 1)
+        g = O.bgr2gray(col)
+        ref, rdesc, _ = O.orb(g, 500)
+        kp, desc = c.extract(col)
+        assert_kp_equal(kp, ref)
+        assert (desc == rdesc).all()
+        assert (c.tap_image(0, 0) == g).all()
+        # strided colour rows (a padded cv::Mat), right camera slot
+        pad = np.zeros((H, W + 7, 3), np.uint8); pad[:, :W] = col
+        kp2, desc2 = c.extract(pad[:, :W], cam=1)
+        assert_kp_equal(kp2, ref)
+        assert (desc2 == rdesc).all()
+        # the same context still takes gray input
+        kp3, desc3 = c.extract(g)
+        assert_kp_equal(kp3, ref)
+        # batch: BGR host frames, BGR device frames and a gray frame in one call
+        colr = synth.colourise(synth.texture((H, W), 34), 2)
+        gr = O.bgr2gray(colr)
+        rr, rrd, _ = O.orb(gr, 500)
+        dl, dr = c.to_device(col), c.to_device(colr)
+        c.batch_submit(0, [dict(left=col, right=colr, bf=100.0, baseline=0.5),
+                           dict(left=dl, right=dr, stride=3 * W, channels=3, bf=100.0, baseline=0.5)])
+        c.batch_wait(0)
+        for i in range(2):
+            r = c.batch_result(0, i)
+            assert r["status"] == 0
+            assert_kp_equal(r["kp_left"], ref); assert_kp_equal(r["kp_right"], rr)
+            assert (r["desc_left"] == rdesc).all() and (r["desc_right"] == rrd).all()
+        c.batch_submit(0, [dict(left=g, right=gr, bf=100.0, baseline=0.5)])
+        c.batch_wait(0)
+        r = c.batch_result(0, 0)
+        assert_kp_equal(r["kp_left"], ref); assert_kp_equal(r["kp_right"], rr)
+    finally:
+        c.close()
+
+
+def test_bgr_needs_a_colour_context(svo, ctxK):
+    col = synth.colourise(synth.texture(synth.K_SHAPE, 3), 1)
+    with pytest.raises(svo.SvoError) as e:
+        ctxK.extract(col)
+    assert e.value.code == svo.E_INVALID
+    with pytest.raises(svo.SvoError) as e:
+        ctxK.batch_submit(0, [dict(left=col, right=col, bf=100.0, baseline=0.5)])
+    assert e.value.code == svo.E_INVALID

@@ -45,3 +45,21 @@ def test_sequence_frames_equal_cv2():
             kp, desc, _ = O.orb(img, 2000)
             assert len(kp) == len(ref) and (desc == rdesc).all()
             assert (kp["x"] == ref["x"]).all() and (kp["angle"].view(np.uint32) == ref["angle"].view(np.uint32)).all()
+
+
+def test_bgr2gray_equals_cvtcolor_on_every_colour():
+    v = np.arange(256, dtype=np.uint8)
+    for b in range(0, 256):
+        img = np.empty((256, 256, 3), np.uint8)
+        img[..., 0] = b; img[..., 1] = v[:, None]; img[..., 2] = v[None, :]
+        assert (O.bgr2gray(img) == cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)).all(), b
+
+
+def test_orb_on_colour_input_equals_orb_on_converted_gray():
+    """cv::ORB converts colour input itself: detectAndCompute(BGR) == oracle ORB on the oracle's gray."""
+    col = synth.colourise(synth.texture((240, 400), 33), 1)
+    ref, rdesc = cv_orb(col, 500)
+    kp, desc, _ = O.orb(O.bgr2gray(col), 500)
+    assert len(kp) == len(ref) and (desc == rdesc).all()
+    for f in ("x", "y", "angle", "response"):
+        assert (kp[f].view(np.uint32) == ref[f].view(np.uint32)).all(), f
