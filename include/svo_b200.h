@@ -199,6 +199,12 @@ typedef struct svo_frame_in {
                                     when pass 1 claimed them (observations.count, :167)   */
     int channels;                /* 0 or 1: gray; 3: interleaved BGR (both images), converted on
                                     the device like svo_extract_bgr                        */
+    const float *map_win_uvr;    /* OPT-IN, changes results: 3 x n_map projection windows (u, v, r)
+                                    for pass 2 — row i only sees current keypoints with |x-u| <= r and
+                                    |y-v| <= r (the window of svo_match_greedy); the keypoints are
+                                    binned into cells on the device and each row gathers its candidates
+                                    instead of scanning all columns.  NULL (every frame of the batch or
+                                    none) reproduces the reference's brute-force scan.          */
 } svo_frame_in;
 
 typedef struct svo_frame_out {

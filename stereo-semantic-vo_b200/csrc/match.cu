@@ -216,7 +216,7 @@ __global__ void k_greedy_init(GreedyArgs a, int reset_time)
                 const int pr = mpr[i];
                 if (pr >= 0) {
                     if (a.prev_row_claimed[(size_t)f * a.prev_stride + pr]) live = false;
-                    else if (a.dmat && pr < set_count(a.prev, f)) {
+                    else if (a.dmat && !a.win_gather && pr < set_count(a.prev, f)) {
                         const Row P = load_row(set_desc(a.prev, f), pr), Q = load_row(set_desc(a.rows, f), i);
                         if (P.a.x == Q.a.x && P.a.y == Q.a.y && P.a.z == Q.a.z && P.a.w == Q.a.w &&
                             P.b.x == Q.b.x && P.b.y == Q.b.y && P.b.z == Q.b.z && P.b.w == Q.b.w) reuse = pr;
@@ -354,6 +354,118 @@ __global__ void __launch_bounds__(M_THREADS, 3) k_shortlist(GreedyArgs a, int T)
 #pragma unroll
         for (int k = 0; k < SL_ROWS_PER_WARP; ++k)
             if (r0 + k < nrows) a.short_cnt[ro + rid[k]] = live[k] ? cnt[k] : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Batch pass 2 with projection windows (opt-in; the reference scans every column, src/pnpmatch.cc:173-190).
+// k_win_prepare, one CTA per frame: the frame's windows and the current keypoints' positions go into the
+// [frame][stride] arrays the resolver reads, and the keypoints are binned into square cells (CSR).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_win_prepare(GreedyArgs a)
+{
+    __shared__ int cell[SVO_WIN_CELLS + 1];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int N = set_count(a.cols, f), M = set_count(a.rows, f);
+    const size_t ro = (size_t)f * a.rows.stride_rows, co = (size_t)f * a.cols.stride_rows;
+    const int ncell = a.ncx * a.ncy;
+    const svo_keypoint *kp = a.kp + (size_t)f * a.kp_frame_stride;
+    const float *win = a.fp[f].map_win;
+    for (int i = tid; i < 3 * M; i += 256) a.win_out[ro * 3 + i] = win[i];
+    for (int c = tid; c <= ncell; c += 256) cell[c] = 0;
+    __syncthreads();
+    auto cell_of = [&](float x, float y) {
+        const int cx = min(max((int)x, 0) >> a.cell_shift, a.ncx - 1), cy = min(max((int)y, 0) >> a.cell_shift, a.ncy - 1);
+        return cy * a.ncx + cx;
+    };
+    for (int j = tid; j < N; j += 256) {
+        const float x = kp[j].x, y = kp[j].y;
+        a.cur_xy_out[(co + j) * 2] = x; a.cur_xy_out[(co + j) * 2 + 1] = y;
+        atomicAdd(&cell[cell_of(x, y)], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {                                      // exclusive scan of the cell counts
+        int carry = 0;
+        for (int b0 = 0; b0 <= ncell; b0 += 32) {
+            const int c = b0 + tid <= ncell ? cell[b0 + tid] : 0;
+            int inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, d);
+                if (tid >= d) inc += v;
+            }
+            if (b0 + tid <= ncell) cell[b0 + tid] = carry + inc - c;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    }
+    __syncthreads();
+    int *off = a.cell_off + (size_t)f * (SVO_WIN_CELLS + 1);
+    for (int c = tid; c <= ncell; c += 256) off[c] = cell[c];
+    __syncthreads();
+    uint16_t *list = a.cell_list + co;
+    for (int j = tid; j < N; j += 256) list[atomicAdd(&cell[cell_of(kp[j].x, kp[j].y)], 1)] = (uint16_t)j;   // order inside a cell is free
+}
+
+// One warp per live row: the cells under the row's window are contiguous per cell row in the CSR; lanes take 32
+// candidates at a time, test the window exactly as in_window() does, and only then touch the descriptor.  Hits
+// (d < T) are collected in shared memory and written in ascending column order (the resolver's invariant).
+__global__ void __launch_bounds__(M_THREADS) k_shortlist_win(GreedyArgs a, int T)
+{
+    __shared__ uint32_t hits[M_WARPS][SVO_SHORT_CAP];
+    const int f = blockIdx.y;
+    const int M = set_count(a.rows, f);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t ro = (size_t)f * a.rows.stride_rows, co = (size_t)f * a.cols.stride_rows;
+    const int *list = a.need_list + ro;
+    const int nrows = min(a.list_cnt[2 * f], M);
+    const uint8_t *rd = set_desc(a.rows, f), *cd = set_desc(a.cols, f);
+    const float *cxy = a.cur_xy + co * 2;
+    const int *coff = a.cell_off + (size_t)f * (SVO_WIN_CELLS + 1);
+    const uint16_t *clist = a.cell_list + co;
+    const uint32_t lt = (1u << lane) - 1u;
+    const float fw = (float)(a.ncx << a.cell_shift), fh = (float)(a.ncy << a.cell_shift);
+    for (int i = blockIdx.x * M_WARPS + warp; i < nrows; i += gridDim.x * M_WARPS) {
+        const int r = list[i];
+        const Row R = load_row(rd, r);
+        const float wu = a.win_uvr[(ro + r) * 3], wv = a.win_uvr[(ro + r) * 3 + 1], wr = a.win_uvr[(ro + r) * 3 + 2];
+        // conservative cell range: anything that is not provably outside (NaN bounds included) is scanned
+        const float xl = wu - wr, xh = wu + wr, yl = wv - wr, yh = wv + wr;
+        const int cx0 = xl >= 0.f ? (xl < fw ? (int)xl >> a.cell_shift : a.ncx) : 0;
+        const int cx1 = xh < fw ? (xh >= 0.f ? (int)xh >> a.cell_shift : -1) : a.ncx - 1;
+        const int cy0 = yl >= 0.f ? (yl < fh ? (int)yl >> a.cell_shift : a.ncy) : 0;
+        const int cy1 = yh < fh ? (yh >= 0.f ? (int)yh >> a.cell_shift : -1) : a.ncy - 1;
+        int cnt = 0;
+        if (cx0 <= cx1)
+            for (int cy = cy0; cy <= cy1; ++cy) {
+                const int b0 = coff[cy * a.ncx + cx0], b1 = coff[cy * a.ncx + cx1 + 1];
+                for (int base = b0; base < b1; base += 32) {
+                    const int idx = base + lane;
+                    bool hit = false; int d = 0, col = 0;
+                    if (idx < b1) {
+                        col = clist[idx];
+                        const float du = cxy[2 * col] - wu, dv = cxy[2 * col + 1] - wv;
+                        if (!(du < -wr || du > wr || dv < -wr || dv > wr)) { d = ham_global(R, cd, col); hit = d < T; }
+                    }
+                    const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                    if (hit) {
+                        const int pos = cnt + __popc(m & lt);
+                        if (pos < SVO_SHORT_CAP) hits[warp][pos] = ((uint32_t)d << 16) | (uint32_t)col;
+                    }
+                    cnt += __popc(m);
+                }
+            }
+        __syncwarp();
+        const int n = min(cnt, SVO_SHORT_CAP);
+        for (int t = lane; t < n; t += 32) {             // rank by column (columns are distinct)
+            const uint32_t e = hits[warp][t];
+            int rank = 0;
+            for (int u = 0; u < n; ++u) rank += (hits[warp][u] & 0xffffu) < (e & 0xffffu);
+            *short_slot(a, ro + r, rank) = e;
+        }
+        __syncwarp();
+        if (a.mode == SVO_GREEDY_PASS2) cnt = prune_list(a, ro + r, cnt, lane);
+        if (lane == 0) a.short_cnt[ro + r] = cnt;
+        __syncwarp();
     }
 }
 
@@ -963,14 +1075,18 @@ void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStrea
     const int mx = maxM > maxN ? maxM : maxN;
     dim3 gi((mx + 255) / 256, nframes);
     if (a.need_list) cudaMemsetAsync(a.list_cnt, 0, sizeof(int) * 2 * nframes, st);
+    if (a.win_gather) { k_win_prepare<<<nframes, 256, 0, st>>>(a); ++*launches; }
     k_greedy_init<<<gi, 256, 0, st>>>(a, 1);
     const int T = a.mode == SVO_GREEDY_PASS1 ? 15 : 60;
     dim3 gs((maxM + M_WARPS * SL_ROWS_PER_WARP - 1) / (M_WARPS * SL_ROWS_PER_WARP), nframes);
     if (ev0) cudaEventRecord(ev0, st);
-    if (a.win_uvr) k_shortlist<true><<<gs, M_THREADS, 0, st>>>(a, T);
+    if (a.win_gather) {
+        const int gx = (maxM + M_WARPS - 1) / M_WARPS;
+        k_shortlist_win<<<dim3(gx < 160 ? gx : 160, nframes), M_THREADS, 0, st>>>(a, T);
+    } else if (a.win_uvr) k_shortlist<true><<<gs, M_THREADS, 0, st>>>(a, T);
     else k_shortlist<false><<<gs, M_THREADS, 0, st>>>(a, T);
     if (ev1) cudaEventRecord(ev1, st);
-    if (a.need_list && a.dmat) {
+    if (a.need_list && a.dmat && !a.win_gather) {
         const int gx = (maxM + M_WARPS - 1) / M_WARPS;
         k_reuse<<<dim3(gx < 128 ? gx : 128, nframes), M_THREADS, 0, st>>>(a, T);   // warps stride over the frame's reuse list
         ++*launches;

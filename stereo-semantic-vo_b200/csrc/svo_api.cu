@@ -36,6 +36,8 @@ struct FrameBufs {           // per-frame (stereo pair) device arrays
     // sync-only extras
     uint8_t *cols;           // [col_stride][32] caller-provided column descriptors
     float *win, *cur_xy, *row_xy; int *boxes; double *F;
+    // batch extras: keypoint grid of the windowed pass 2 (win / cur_xy are allocated for batch frames too)
+    int *cell_off; uint16_t *cell_list;
 };
 
 struct HostArena {           // pinned mirror of one lane's outputs
@@ -264,7 +266,10 @@ int alloc_frames(svo_ctx *ctx, FrameBufs &f, int nframes, int col_stride, int ro
     TRY(dalloc(ctx, &f.params, 4 * F));
     f.cols = nullptr; f.win = f.cur_xy = f.row_xy = nullptr; f.boxes = nullptr; f.F = nullptr;
     f.dmat = nullptr; f.bf_key = nullptr; f.dmat_pitch = 0; f.dmat_frame_stride = 0;
+    f.cell_off = nullptr; f.cell_list = nullptr;
     if (!sync_extras) {
+        TRY(dalloc(ctx, &f.win, R * 3)); TRY(dalloc(ctx, &f.cur_xy, C * 2));
+        TRY(dalloc(ctx, &f.cell_off, F * (SVO_WIN_CELLS + 1))); TRY(dalloc(ctx, &f.cell_list, C));
         // u8 distance matrix previous-frame rows x current-frame columns; k_scores_m gives every lane a
         // 16-byte aligned block of columns, so the pitch is 32 such blocks
         f.dmat_pitch = 32 * ((((col_stride + 31) / 32) + 15) & ~15);
@@ -330,7 +335,7 @@ bool device_readable(const void *p)
 struct Seg { const uint8_t *src; size_t bytes; const void **field; bool need16; };
 
 // Kernels, memsets and D2H copies of one batch on the lane's stream (capturable: no host-dependent arguments).
-int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, bool fused, cudaEvent_t *ev)
+int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, bool fused, bool windowed, cudaEvent_t *ev)
 {
     const Geom &g = ctx->g;
     const Bufs &b = ctx->b;
@@ -408,6 +413,15 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
         ga.prev_row_claimed = fb.p1_row_claimed + (size_t)L.frame0 * R; ga.prev_stride = R;
         ga.best_idx = nullptr; ga.best = nullptr; ga.second = nullptr;
         ga.row_claimed = fb.p2_row_claimed + (size_t)L.frame0 * R; ga.row_bad = nullptr;
+        if (windowed) {   // opt-in projection windows: gather from the keypoint grid instead of scanning every column
+            int shift = 5;
+            while (((g.W >> shift) + 1) * ((g.H >> shift) + 1) > SVO_WIN_CELLS) ++shift;
+            ga.win_gather = 1; ga.cell_shift = shift; ga.ncx = (g.W >> shift) + 1; ga.ncy = (g.H >> shift) + 1;
+            ga.cell_off = fb.cell_off + (size_t)L.frame0 * (SVO_WIN_CELLS + 1); ga.cell_list = fb.cell_list + (size_t)L.frame0 * K;
+            ga.kp = b.kp + (size_t)L.slot0 * g.kp_cap; ga.kp_frame_stride = 2 * (size_t)g.kp_cap;
+            ga.win_out = fb.win + (size_t)L.frame0 * R * 3; ga.cur_xy_out = fb.cur_xy + (size_t)L.frame0 * K * 2;
+            ga.win_uvr = ga.win_out; ga.cur_xy = ga.cur_xy_out;
+        }
         launch_greedy(ga, n, false, st, &ctx->launches, ev ? ev[14] : nullptr, ev ? ev[15] : nullptr);
     }
     if (ev) cudaEventRecord(ev[10], st);
@@ -565,7 +579,7 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
         TRY(halloc(ctx, &h.p1_row_claimed, B * R)); TRY(halloc(ctx, &h.p2_row_claimed, B * R));
         TRY(halloc(ctx, &h.claim_row, B * K));
         TRY(halloc(ctx, &h.params, 4 * B));
-        l.stage_cap = I * ctx->stage_img_bytes + B * (R * 32 * 2 + R * 5) + (6 * B + 8) * 512;
+        l.stage_cap = I * ctx->stage_img_bytes + B * (R * 32 * 2 + R * 5 + R * 12) + (7 * B + 8) * 512;
         TRY(dalloc(ctx, &l.d_stage, l.stage_cap));
         TRY(dalloc(ctx, &l.d_fp, B)); TRY(halloc(ctx, &l.h_fp, B));
         TRY(dalloc(ctx, &l.d_strides, I)); TRY(halloc(ctx, &l.h_strides, I));
@@ -933,8 +947,10 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
     const int R = fb.row_stride, K = fb.col_stride, B = ctx->cfg.max_batch;
     cudaEvent_t *ev = ctx->profiling ? L.ev : nullptr;
     bool any_prev = false, any_map = false;
+    int n_win = 0, n_mapped = 0;
     for (int i = 0; i < n; ++i) {
         const svo_frame_in &f = frames[i];
+        if (f.n_map > 0) { ++n_mapped; if (f.map_win_uvr) ++n_win; }
         const int ch = f.channels == 3 ? 3 : 1;
         if (!f.left || !f.right || f.stride < g.W * ch || f.stride >= SVO_STRIDE_BGR || f.n_prev < 0 || f.n_map < 0 || f.n_prev > R ||
             f.n_map > R || (f.n_prev && !f.prev_desc) || (f.n_map && !f.map_desc) || !(f.baseline > 0.f) ||
@@ -943,6 +959,9 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
                         ch > ctx->cfg.max_channels ? " (BGR input needs svo_config.max_channels = 3)" : "");
         any_prev |= f.n_prev > 0; any_map |= f.n_map > 0;
     }
+    if (n_win != 0 && n_win != n_mapped)
+        return fail(ctx, SVO_E_INVALID, "svo_batch_submit: map_win_uvr must be given for every frame with a map, or for none");
+    const bool windowed = n_win > 0;
     L.in.assign(frames, frames + n);
     L.nframes = n;
     if (ev) cudaEventRecord(ev[0], st);
@@ -982,6 +1001,7 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
         place(f.n_prev ? f.prev_live : nullptr, (size_t)f.n_prev, (const void **)&P.prev_live, false);
         place(f.n_map ? f.map_desc : nullptr, (size_t)f.n_map * 32, (const void **)&P.map, true);
         place((f.n_map && f.n_prev) ? f.map_prev_row : nullptr, sizeof(int) * (size_t)f.n_map, (const void **)&P.map_prev_row, true);
+        place((f.n_map && windowed) ? f.map_win_uvr : nullptr, 3 * sizeof(float) * (size_t)f.n_map, (const void **)&P.map_win, false);
         hp[i] = f.n_prev; hp[B + i] = f.n_map;
         memcpy(&hp[2 * B + i], &f.bf, 4); memcpy(&hp[3 * B + i], &f.baseline, 4);
     }
@@ -1016,16 +1036,16 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
     // stages run): every per-frame input is reached through device tables filled above.  Outside profiling runs
     // the sequence is therefore captured once into a CUDA graph and replayed (one launch instead of ~45 calls).
     if (ev) {
-        TRY(enqueue_compute(ctx, L, n, any_prev, any_map, fused, ev));
+        TRY(enqueue_compute(ctx, L, n, any_prev, any_map, fused, windowed, ev));
     } else {
-        const int key = n | (any_prev ? 1 << 20 : 0) | (any_map ? 1 << 21 : 0) | (fused ? 1 << 22 : 0);
+        const int key = n | (any_prev ? 1 << 20 : 0) | (any_map ? 1 << 21 : 0) | (fused ? 1 << 22 : 0) | (windowed ? 1 << 23 : 0);
         LaneGraph *lg = nullptr;
         for (LaneGraph &c : L.graphs) if (c.key == key) lg = &c;
         if (!lg) {
             const long long before = ctx->launches;
             cudaGraph_t graph = nullptr;
             CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            const int rc = enqueue_compute(ctx, L, n, any_prev, any_map, fused, nullptr);
+            const int rc = enqueue_compute(ctx, L, n, any_prev, any_map, fused, windowed, nullptr);
             const cudaError_t ce = cudaStreamEndCapture(st, &graph);
             if (rc != SVO_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
             if (ce != cudaSuccess) return fail(ctx, SVO_E_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));

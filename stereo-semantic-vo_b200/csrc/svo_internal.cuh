@@ -18,6 +18,7 @@
 #define SVO_FAST_BAND 8        // output rows per FAST band (one CTA each)
 #define SVO_SHORT_CAP 128      // short-list entries per greedy row before the full-scan path
 #define SVO_STRIDE_BGR (1 << 30)  // flag in a per-image stride word: the source is interleaved BGR
+#define SVO_WIN_CELLS 4096     // most cells of the keypoint grid used by the windowed pass 2
 #define SVO_STATUS_OVERFLOW 1  // bit set in the per-image status word on a capacity overflow
 #define SVO_STATUS_DEPTH 2     // introselect reached its depth limit (heap-select path ran)
 
@@ -90,6 +91,7 @@ struct FramePtrs {
     const uint8_t *prev_live;      // n_prev or NULL (all live)
     const uint8_t *map;            // n_map x 32, 16-byte aligned
     const int *map_prev_row;       // n_map or NULL
+    const float *map_win;          // 3 x n_map (u, v, r) projection windows of pass 2, or NULL
 };
 
 // ---- stage launchers (each enqueues on `st` for images [slot0, slot0 + nimg)) ----
@@ -166,6 +168,14 @@ struct GreedyArgs {
                                                       // decisions, length-sorted processing order)
     const float *win_uvr;         // [frame][rows.stride_rows][3] or NULL
     const float *cur_xy;          // [frame][cols.stride_rows][2] or NULL
+    // batch pass 2 with projection windows (opt-in): k_win_prepare copies the windows and the current keypoints'
+    // positions into win_out / cur_xy_out (= win_uvr / cur_xy) and bins the keypoints into square cells, then
+    // k_shortlist_win gathers each row's candidates from the cells under its window
+    int win_gather, cell_shift, ncx, ncy;
+    int *cell_off;                // [frame][SVO_WIN_CELLS + 1]
+    uint16_t *cell_list;          // [frame][cols.stride_rows]
+    const svo_keypoint *kp; size_t kp_frame_stride;   // current (left) keypoints of frame f at kp + f * kp_frame_stride
+    float *win_out, *cur_xy_out;
     // veto (pass 1)
     const int *boxes; int n_boxes; const double *F; const float *row_xy;
 };

@@ -37,7 +37,8 @@ class FrameIn(C.Structure):
     _fields_ = [("left", C.c_void_p), ("right", C.c_void_p), ("stride", C.c_int),
                 ("bf", C.c_float), ("baseline", C.c_float),
                 ("prev_desc", C.c_void_p), ("n_prev", C.c_int), ("prev_live", C.c_void_p),
-                ("map_desc", C.c_void_p), ("n_map", C.c_int), ("map_prev_row", C.c_void_p), ("channels", C.c_int)]
+                ("map_desc", C.c_void_p), ("n_map", C.c_int), ("map_prev_row", C.c_void_p), ("channels", C.c_int),
+                ("map_win_uvr", C.c_void_p)]
 
 
 class FrameOut(C.Structure):
@@ -313,9 +314,11 @@ class Context:
                     setattr(fi, name, v.ctypes.data); setattr(fi, cnt, len(v))
                 else:
                     setattr(fi, name, v); setattr(fi, cnt, f[cnt])
-            for name in ("prev_live", "map_prev_row"):
+            for name in ("prev_live", "map_prev_row", "map_win_uvr"):
                 v = f.get(name)
                 if isinstance(v, np.ndarray):
+                    if name == "map_win_uvr":
+                        v = np.ascontiguousarray(v, np.float32)
                     keep.append(v)
                     setattr(fi, name, v.ctypes.data)
                 elif v is not None:

@@ -489,3 +489,87 @@ def test_bgr_needs_a_colour_context(svo, ctxK):
     with pytest.raises(svo.SvoError) as e:
         ctxK.batch_submit(0, [dict(left=col, right=col, bf=100.0, baseline=0.5)])
     assert e.value.code == svo.E_INVALID
+
+
+# ---- opt-in projection windows in the batch path ----------------------------------
+def test_batch_pass2_projection_windows_vs_oracle(ctxK):
+    """map_win_uvr restricts every pass-2 row to the current keypoints under its window; the device gathers the
+    candidates from a keypoint grid, the oracle scans every column with the same predicate: same claims."""
+    cal = synth.KITTI_04_12
+    bf, b = float(np.float32(cal["bf"])), float(np.float32(cal["bf"] / cal["fx"]))
+    seq = synth.Sequence(seed=7)
+    frames = [seq.frame(t) for t in range(3)]
+    ext = [ctxK.extract(frames[t][0], cam=0) for t in range(3)]
+    rng = np.random.default_rng(21)
+    H, W = synth.K_SHAPE
+    jobs = []
+    for t in (1, 2):
+        kp_prev, prev = ext[t - 1]
+        kp_cur, cur = ext[t]
+        M = 4000
+        # map rows: descriptors of current keypoints with a few bits flipped (so windows decide who may match),
+        # windows centred near the keypoint they came from, radius by octave; plus far-away, NaN, negative-radius,
+        # image-covering and out-of-image windows
+        src = rng.integers(0, len(cur), M)
+        flips = np.packbits(rng.random((M, 256)) < 0.03, axis=1, bitorder="little")
+        mp = cur[src] ^ flips
+        uvr = np.stack([kp_cur["x"][src] + rng.normal(0, 6, M), kp_cur["y"][src] + rng.normal(0, 6, M),
+                        15.0 * np.float32(1.2) ** kp_cur["octave"][src]], 1).astype(np.float32)
+        far = rng.permutation(M)[:300]
+        uvr[far, 0] = rng.uniform(0, W, 300); uvr[far, 1] = rng.uniform(0, H, 300)
+        uvr[rng.permutation(M)[:20], 0] = np.nan
+        uvr[rng.permutation(M)[:20], 2] = -1.0
+        uvr[rng.permutation(M)[:5], 2] = 5000.0
+        uvr[rng.permutation(M)[:20], 0] = -300.0
+        uvr[rng.permutation(M)[:20], 1] = 4000.0
+        mpr = np.full(M, -1, np.int32)
+        take = rng.permutation(M)[:500]; psrc = rng.integers(0, len(prev), 500)
+        mp[take] = prev[psrc]; mpr[take] = psrc
+        live = (rng.random(len(prev)) < 0.8).astype(np.uint8)
+        jobs.append(dict(left=frames[t][0], right=frames[t][1], bf=bf, baseline=b, prev_desc=prev, prev_live=live,
+                         map_desc=mp, map_prev_row=mpr, map_win_uvr=uvr))
+    ctxK.batch_submit(0, jobs); ctxK.batch_wait(0)
+    total = 0
+    for i, (job, t) in enumerate(zip(jobs, (1, 2))):
+        r = ctxK.batch_result(0, i)
+        kp_cur, cur = ext[t]
+        assert (r["desc_left"] == cur).all()
+        cxy = np.stack([kp_cur["x"], kp_cur["y"]], 1).astype(np.float32)
+        p1 = O.match_greedy(job["prev_desc"], cur, 0, row_live=job["prev_live"])
+        assert (r["p1_row_claimed"] == p1["row_claimed"]).all()
+        live2 = np.ones(len(job["map_desc"]), np.uint8)
+        m = job["map_prev_row"] >= 0
+        live2[m] = 1 - p1["row_claimed"][job["map_prev_row"][m]]
+        p2 = O.match_greedy(job["map_desc"], cur, 1, claimed=p1["claimed"], claim_row=p1["claim_row"], row_live=live2,
+                            row_base=len(job["prev_desc"]), win_uvr=job["map_win_uvr"], cur_xy=cxy)
+        assert (r["p2_row_claimed"] == p2["row_claimed"]).all()
+        assert (r["claim_row"] == p2["claim_row"]).all()
+        total += int(p2["row_claimed"].sum())
+        # and the windows matter: the brute-force scan claims a different set
+        p2b = O.match_greedy(job["map_desc"], cur, 1, claimed=p1["claimed"], claim_row=p1["claim_row"], row_live=live2,
+                             row_base=len(job["prev_desc"]))
+        assert (p2b["claim_row"] != p2["claim_row"]).any()
+    assert total > 300
+    # the same frames without windows still take the brute-force path (graph keyed on the mode)
+    plain = [{k: v for k, v in j.items() if k != "map_win_uvr"} for j in jobs]
+    ctxK.batch_submit(0, plain); ctxK.batch_wait(0)
+    r = ctxK.batch_result(0, 0)
+    kp_cur, cur = ext[1]
+    p1 = O.match_greedy(jobs[0]["prev_desc"], cur, 0, row_live=jobs[0]["prev_live"])
+    live2 = np.ones(len(jobs[0]["map_desc"]), np.uint8)
+    m = jobs[0]["map_prev_row"] >= 0
+    live2[m] = 1 - p1["row_claimed"][jobs[0]["map_prev_row"][m]]
+    p2b = O.match_greedy(jobs[0]["map_desc"], cur, 1, claimed=p1["claimed"], claim_row=p1["claim_row"], row_live=live2,
+                         row_base=len(jobs[0]["prev_desc"]))
+    assert (r["claim_row"] == p2b["claim_row"]).all()
+
+
+def test_batch_windows_all_or_none(svo, ctxK):
+    seq = synth.Sequence(seed=7)
+    L, R = seq.frame(0)
+    mp = np.zeros((10, 32), np.uint8)
+    a = dict(left=L, right=R, bf=100.0, baseline=0.5, map_desc=mp, map_win_uvr=np.zeros((10, 3), np.float32))
+    c = dict(left=L, right=R, bf=100.0, baseline=0.5, map_desc=mp)
+    with pytest.raises(svo.SvoError) as e:
+        ctxK.batch_submit(0, [a, c])
+    assert e.value.code == svo.E_INVALID
