@@ -275,7 +275,17 @@ void launch_fast(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t
     ++*launches;
 }
 
+// The attribute belongs to the kernel, not to a context: it only ever grows, so a context created for a small
+// image never lowers the limit under one that is already serving a larger geometry.
 int setup_fast_attributes(const Geom &g)
 {
-    return (int)cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, fast_smem_bytes(g));
+    static int granted[64] = {0};   // per device (function attributes are per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    const int need = fast_smem_bytes(g);
+    if (need <= granted[dev]) return 0;
+    const cudaError_t e = cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+    if (e == cudaSuccess) granted[dev] = need;
+    return (int)e;
 }

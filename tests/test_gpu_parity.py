@@ -491,6 +491,25 @@ def test_bgr_needs_a_colour_context(svo, ctxK):
     assert e.value.code == svo.E_INVALID
 
 
+def test_context_for_a_small_image_leaves_a_larger_one_working(svo, ctxK):
+    """Kernel attributes (k_fast's dynamic shared-memory limit) are per kernel, not per context: creating a context
+    for a smaller geometry must not lower them under a context that is already serving 1241x376."""
+    img = synth.texture(synth.K_SHAPE, 5)
+    kp0, d0 = ctxK.extract(img)
+    small = svo.Context(400, 240, nfeatures=300, max_batch=1, lanes=1, max_rows=500)
+    try:
+        kp1, d1 = ctxK.extract(img)
+        s = synth.texture((240, 400), 6)
+        ks, ds = small.extract(s)
+        ref, rdesc, _ = O.orb(s, 300)
+        assert_kp_equal(ks, ref); assert (ds == rdesc).all()
+    finally:
+        small.close()
+    kp2, d2 = ctxK.extract(img)
+    for kp, d in ((kp1, d1), (kp2, d2)):
+        assert_kp_equal(kp, kp0); assert (d == d0).all()
+
+
 # ---- opt-in projection windows in the batch path (SURVEY.md section 8f rank 3) ----------------------------------
 def test_batch_pass2_projection_windows_vs_oracle(ctxK):
     """map_win_uvr restricts every pass-2 row to the current keypoints under its window; the device gathers the
