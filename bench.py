@@ -143,7 +143,8 @@ def run_gpu(args, rank, world, local_rank):
     grp = replicas.Group(backend="nccl", device=dev)   # barrier + max-over-ranks only; no data-path collective
     B, P = args.batch, args.pool
     ctx = svo.Context(W_IMG, H_IMG, nfeatures=NFEAT, nlevels=NLEVELS, max_batch=B, lanes=args.lanes,
-                      max_rows=max(MAP_ROWS, kp_cap(NFEAT)), device=dev)
+                      max_rows=max(MAP_ROWS, kp_cap(NFEAT)), device=dev,
+                      distribution=svo.DIST_OCTREE if args.distribution == "octree" else svo.DIST_RETAIN_BEST)
     # ---- synthetic sequence (one per rank): pool of P distinct stereo frames in pinned memory
     seq_id = replicas.assign_sequences(world, world, rank)[0]
     seq = synth.Sequence((H_IMG, W_IMG), seed=seq_id)
@@ -335,7 +336,8 @@ def run_gpu(args, rank, world, local_rank):
             "config": {"workload": "%s: synthetic %s %dx%d stereo sequence, KITTI04-12 intrinsics, "
                                    "%d ORB features / 8 levels / 1.2, full front-end: extract L+R, sparse stereo + SAD, "
                                    "BF match vs previous frame, greedy pass 1 + pass 2 vs %d-row local map"
-                                   % ("configs[1]" if (W_IMG, H_IMG, NFEAT, MAP_ROWS) == (1241, 376, 2000, 5000) else "non-headline configuration",
+                                   % ("configs[1]" if (W_IMG, H_IMG, NFEAT, MAP_ROWS, args.distribution) == (1241, 376, 2000, 5000, "retainbest")
+                                      else "non-headline configuration" + (" (opt-in octree distribution)" if args.distribution == "octree" else ""),
                                       "KITTI-shape" if (W_IMG, H_IMG) == (1241, 376) else "high-res", W_IMG, H_IMG, NFEAT, MAP_ROWS),
                        "frames_per_step": B, "lanes": args.lanes, "pool_frames": P,
                        "l2": "inputs larger than L2: %d-frame pool = %.0f MB of images + %.0f MB of descriptors cycled"
@@ -483,6 +485,8 @@ def main():
     ap.add_argument("--height", type=int, default=376)
     ap.add_argument("--features", type=int, default=2000)
     ap.add_argument("--map-rows", type=int, default=5000)
+    ap.add_argument("--distribution", default="retainbest", choices=["retainbest", "octree"],
+                    help="keypoint selection: cv::ORB retainBest (headline, parity) or the opt-in quadtree distribution")
     args = ap.parse_args()
     globals().update(W_IMG=args.width, H_IMG=args.height, NFEAT=args.features, MAP_ROWS=args.map_rows)
     args.warmup = max(args.warmup, 3)

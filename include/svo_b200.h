@@ -61,7 +61,19 @@ typedef struct svo_config {
     int max_rows;        /* capacity of one greedy row set / BF train set (e.g. 5000-row local map)*/
     void *stream;        /* optional cudaStream_t for lane 0 (NULL: the context creates its own)  */
     int max_channels;    /* 1 (default) or 3: 3 sizes the input staging for interleaved BGR images  */
+    int distribution;    /* SVO_DIST_RETAIN_BEST (default, cv::ORB parity) or SVO_DIST_OCTREE (opt-in)  */
 } svo_config;
+
+/* Keypoint selection per pyramid level.
+ * SVO_DIST_RETAIN_BEST: what the reference runs (src/frame.cc:77-78 -> cv::ORB): KeyPointsFilter::retainBest
+ *   twice (2*quota by FAST score, quota by Harris response), output order included.  Bit-exact parity path.
+ * SVO_DIST_OCTREE: north_star's "grid/octree distribution".  The reference has no such stage, so this is an
+ *   opt-in, non-parity mode: the level's FAST corners go through ORB-SLAM2's DistributeOctTree scheme (quadtree
+ *   split until the level quota is reached, best FAST score per node) with its pointer-order tie-breaks fixed
+ *   (oracle/svo_octree_oracle.c is the definition); a level may return quota + 2 keypoints; `response` is still
+ *   the Harris response.  Needs every level quota <= 4093 and a keypoint rectangle no wider than 16.5 x its height. */
+#define SVO_DIST_RETAIN_BEST 0
+#define SVO_DIST_OCTREE 1
 
 void svo_default_config(svo_config *cfg);
 const char *svo_version(void);

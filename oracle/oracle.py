@@ -99,18 +99,28 @@ def blur7(img):
     return out
 
 
-def orb(gray, nfeatures=500, scale=1.2, nlevels=8, fast_threshold=20, with_pyramid=False):
-    """cv::ORB::detectAndCompute restatement -> (keypoints[KP_DTYPE], descriptors[n,32], Pyramid|None)."""
+def orb(gray, nfeatures=500, scale=1.2, nlevels=8, fast_threshold=20, with_pyramid=False, distribution=0):
+    """cv::ORB::detectAndCompute restatement -> (keypoints[KP_DTYPE], descriptors[n,32], Pyramid|None).
+    distribution=1: the opt-in quadtree distribution (svo_octree_oracle.c) instead of the two retainBest culls."""
     gray = np.ascontiguousarray(gray, np.uint8)
     H, W = gray.shape
     cap = 4 * nfeatures + 4096
     kps = np.zeros(cap, KP_DTYPE)
     desc = np.zeros((cap, 32), np.uint8)
     pyr = Pyramid() if with_pyramid else None
-    n = lib().svo_o_orb(_p(gray), W, H, W, nfeatures, C.c_float(scale), nlevels, fast_threshold,
-                        _p(kps), _p(desc), cap, C.byref(pyr) if pyr is not None else None)
+    n = lib().svo_o_orb_ex(_p(gray), W, H, W, nfeatures, C.c_float(scale), nlevels, fast_threshold, distribution,
+                           _p(kps), _p(desc), cap, C.byref(pyr) if pyr is not None else None)
     assert 0 <= n <= cap, n
     return kps[:n].copy(), desc[:n].copy(), pyr
+
+
+def distribute_octree(xs, ys, score, rect, N):
+    """Quadtree distribution of raster-ordered points inside rect = (x0, y0, x1, y1) -> kept indices (node order)."""
+    xs = np.ascontiguousarray(xs, np.int32); ys = np.ascontiguousarray(ys, np.int32)
+    score = np.ascontiguousarray(score, np.int32)
+    out = np.zeros(max(len(xs), 1), np.int32)
+    k = lib().svo_o_distribute_octree(_p(xs), _p(ys), _p(score), len(xs), rect[0], rect[1], rect[2], rect[3], N, _p(out))
+    return out[:k].copy()
 
 
 def pyramid_free(pyr):

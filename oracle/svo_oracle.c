@@ -363,6 +363,17 @@ int svo_o_orb(const uint8_t *gray, int W, int H, int stride, int nfeatures, floa
               int nlevels, int fast_threshold, svo_o_keypoint *kps, uint8_t *desc, int cap,
               svo_o_pyramid *pyr_out)
 {
+    return svo_o_orb_ex(gray, W, H, stride, nfeatures, scale_factor, nlevels, fast_threshold, 0, kps, desc, cap, pyr_out);
+}
+
+/* distribution 0: cv::ORB's two retainBest culls (the reference's behaviour).
+ * distribution 1 (opt-in, parity unpinned): the level's FAST corners go through the quadtree distribution of
+ * svo_octree_oracle.c with N = the level quota; the survivors keep node (Z) order, get their Harris response
+ * (reported, not used for selection) and the rest of the pipeline is unchanged. */
+int svo_o_orb_ex(const uint8_t *gray, int W, int H, int stride, int nfeatures, float scale_factor,
+                 int nlevels, int fast_threshold, int distribution, svo_o_keypoint *kps, uint8_t *desc, int cap,
+                 svo_o_pyramid *pyr_out)
+{
     const int edge = 31;
     int lw[SVO_O_MAX_LEVELS], lh[SVO_O_MAX_LEVELS], quota[SVO_O_MAX_LEVELS];
     float ls[SVO_O_MAX_LEVELS];
@@ -388,13 +399,14 @@ int svo_o_orb(const uint8_t *gray, int W, int H, int stride, int nfeatures, floa
         float *resp = (float *)malloc(sizeof(float) * (size_t)capl);
         int n = svo_o_fast_nms(L[l].img, w, h, L[l].stride, fast_threshold, edge, xs, ys, sc, capl);
         for (int i = 0; i < n; ++i) { idx[i] = i; resp[i] = (float)sc[i]; }
-        n = svo_o_retain_best(resp, idx, n, 2 * quota[l]);
+        if (distribution == 1) n = svo_o_distribute_octree(xs, ys, sc, n, edge, edge, w - edge, h - edge, quota[l], idx);
+        else n = svo_o_retain_best(resp, idx, n, 2 * quota[l]);
         /* Harris on the survivors, in their post-retainBest order */
         int32_t *hx = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n + 1) * 3);
         int32_t *hy = hx + n + 1, *hidx = hy + n + 1;
         for (int i = 0; i < n; ++i) { hx[i] = xs[idx[i]]; hy[i] = ys[idx[i]]; hidx[i] = i; }
         svo_o_harris(L[l].img, L[l].stride, hx, hy, n, resp);
-        int m = svo_o_retain_best(resp, hidx, n, quota[l]);
+        int m = distribution == 1 ? n : svo_o_retain_best(resp, hidx, n, quota[l]);
         float *ang = (float *)malloc(sizeof(float) * (size_t)(m + 1));
         int32_t *fx = (int32_t *)malloc(sizeof(int32_t) * (size_t)(m + 1) * 2);
         int32_t *fy = fx + m + 1;

@@ -42,7 +42,15 @@ void svo_o_brief(const uint8_t *blur, int stride, int cx, int cy, float angle_de
 int svo_o_orb(const uint8_t *gray, int W, int H, int stride, int nfeatures, float scale_factor,
               int nlevels, int fast_threshold, svo_o_keypoint *kps, uint8_t *desc, int cap,
               svo_o_pyramid *pyr_out);
+int svo_o_orb_ex(const uint8_t *gray, int W, int H, int stride, int nfeatures, float scale_factor,
+                 int nlevels, int fast_threshold, int distribution, svo_o_keypoint *kps, uint8_t *desc, int cap,
+                 svo_o_pyramid *pyr_out);
 void svo_o_pyramid_free(svo_o_pyramid *p);
+/* opt-in quadtree keypoint distribution (svo_octree_oracle.c): points in raster order inside the rectangle
+ * [x0,x1) x [y0,y1); writes the kept indices (node order) into out_idx[n] and returns their number */
+#define SVO_O_OCT_MAXD 12
+int svo_o_distribute_octree(const int32_t *xs, const int32_t *ys, const int32_t *score, int n,
+                            int x0, int y0, int x1, int y1, int N, int32_t *out_idx);
 
 int svo_o_hamming(const uint8_t *a, const uint8_t *b);
 int svo_o_hamming_popcnt(const uint8_t *a, const uint8_t *b);

@@ -210,6 +210,12 @@ int build_geometry(svo_ctx *ctx)
         if (L.x1 <= L.x0 || L.y1 <= L.y0) { L.x1 = L.x0; L.y1 = L.y0; L.nbands = 0; }
         else L.nbands = (L.y1 - L.y0 + SVO_FAST_BAND - 1) / SVO_FAST_BAND;
         if (L.nbands > 500) return fail(ctx, SVO_E_INVALID, "image too tall");
+        {   // octree mode: nIni = round(width / height) roots of float width hX (ORB-SLAM2 DistributeOctTree)
+            const int ow = L.x1 - L.x0, oh = L.y1 - L.y0;
+            int ni = oh > 0 ? (int)roundf((float)ow / (float)oh) : 1;
+            ni = ni < 1 ? 1 : (ni > 16 ? 16 : ni);
+            L.oct_nini = ni; L.oct_hx = (float)ow / (float)ni;
+        }
         L.band_cap = ((SVO_FAST_BAND + 1) / 2) * ((L.x1 - L.x0 + 1) / 2) + 1;
         L.band_off = band_off; band_off += L.nbands * L.band_cap;
         L.bandcnt_off = bandcnt_off; bandcnt_off += L.nbands;
@@ -296,11 +302,14 @@ void enqueue_extract(svo_ctx *ctx, int slot0, int nimg, cudaStream_t st, cudaEve
     if (ev) cudaEventRecord(ev[2], st);
     launch_fast(b, g, slot0, nimg, st, n);
     if (ev) cudaEventRecord(ev[3], st);
-    launch_select1(b, g, slot0, nimg, st, n);
+    const bool octree = ctx->cfg.distribution == SVO_DIST_OCTREE;
+    if (octree) launch_octree(b, g, slot0, nimg, st, n);
+    else launch_select1(b, g, slot0, nimg, st, n);
     if (ev) cudaEventRecord(ev[4], st);
     launch_harris(b, g, slot0, nimg, st, n);
     if (ev) cudaEventRecord(ev[5], st);
-    launch_select2(b, g, slot0, nimg, st, n);
+    if (octree) launch_keep_all(b, g, slot0, nimg, st, n);
+    else launch_select2(b, g, slot0, nimg, st, n);
     if (ev) cudaEventRecord(ev[6], st);
     launch_blur(b, g, slot0, nimg, st, n);
     if (ev) cudaEventRecord(ev[7], st);
@@ -460,7 +469,7 @@ void svo_default_config(svo_config *c)
     memset(c, 0, sizeof(*c));
     c->device = 0; c->width = 1241; c->height = 376;
     c->nfeatures = 2000; c->nlevels = 8; c->scale_factor = 1.2f; c->fast_threshold = 20;
-    c->max_batch = 1; c->lanes = 1; c->max_rows = 5000; c->stream = nullptr; c->max_channels = 1;
+    c->max_batch = 1; c->lanes = 1; c->max_rows = 5000; c->stream = nullptr; c->max_channels = 1; c->distribution = SVO_DIST_RETAIN_BEST;
 }
 
 const char *svo_version(void) { return "svo_b200 0.1 (sm_100a)"; }
@@ -497,7 +506,7 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
     const svo_config &c = ctx->cfg;
     if (c.nlevels < 1 || c.nlevels > SVO_MAX_LEVELS || c.nfeatures < 1 || c.nfeatures > 60000 || c.max_batch < 1 ||
         c.lanes < 1 || c.max_rows < 1 || c.max_rows > 40000 || c.width < 64 || c.height < 64 || !(c.scale_factor > 1.f) ||
-        (c.max_channels != 1 && c.max_channels != 3))
+        (c.max_channels != 1 && c.max_channels != 3) || (c.distribution != SVO_DIST_RETAIN_BEST && c.distribution != SVO_DIST_OCTREE))
         return fail(ctx, SVO_E_INVALID, "invalid configuration");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -549,8 +558,16 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
         TRY(dalloc(ctx, &p.d_stats, NP * 2)); TRY(halloc(ctx, &p.h_stats, NP * 2));
         TRY(dalloc(ctx, &p.d_T, NP * 16)); TRY(halloc(ctx, &p.h_T, NP * 16));
     }
+    if (c.distribution == SVO_DIST_OCTREE) {
+        for (int l = 0; l < g.nlevels; ++l) {
+            if (g.lv[l].quota > octree_max_quota())
+                return fail(ctx, SVO_E_CAPACITY, "octree distribution: level %d quota %d exceeds %d", l, g.lv[l].quota, octree_max_quota());
+            if (g.lv[l].nbands && (float)(g.lv[l].x1 - g.lv[l].x0) / (float)(g.lv[l].y1 - g.lv[l].y0) >= 16.5f)
+                return fail(ctx, SVO_E_INVALID, "octree distribution: level %d is wider than 16.5 x its height", l);
+        }
+    }
     if (setup_fast_attributes(g) != 0 || setup_match_attributes() != 0 || setup_describe() != 0 || setup_select_attributes() != 0 ||
-        setup_pose() != 0)
+        setup_pose() != 0 || setup_octree_attributes() != 0)
         return fail(ctx, SVO_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
     CU(cudaStreamCreateWithFlags(&ctx->sync_st, cudaStreamNonBlocking));
     ctx->stage_img_bytes = (size_t)g.H * ((size_t)g.W * c.max_channels + 256);

@@ -42,6 +42,8 @@ struct LevelGeom {
     int blur_tile_off; // first blur tile index of this level
     int blur_tiles_x;  // blur tiles per strip of 32 rows
     int blur_tq;       // pixel quads per blur tile (multiple of 4, <= 128)
+    int oct_nini;      // octree mode: root nodes = round(width / height) of the keypoint rectangle
+    float oct_hx;      // octree mode: root width (float), (x1 - x0) / oct_nini
 };
 
 struct Geom {
@@ -104,6 +106,11 @@ void launch_harris(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream
 void launch_select2(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches);
 void launch_blur(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches);
 void launch_describe(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches);
+// opt-in quadtree distribution (octree.cu): replaces launch_select1 / launch_select2
+void launch_octree(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches);
+void launch_keep_all(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches);
+int setup_octree_attributes();
+int octree_max_quota();
 int fast_smem_bytes(const Geom &g);
 int setup_fast_attributes(const Geom &g);
 int setup_describe();

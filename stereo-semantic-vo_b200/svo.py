@@ -15,6 +15,7 @@ KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4
                      ("response", "<f4"), ("octave", "<i4")])
 
 OK, E_INVALID, E_CUDA, E_CAPACITY, E_NOMEM = 0, -1, -2, -3, -4
+DIST_RETAIN_BEST, DIST_OCTREE = 0, 1     # svo_config.distribution
 TAP_LEVEL, TAP_BLUR, TAP_FAST, TAP_SELECT1, TAP_SELECT2 = 0, 1, 2, 3, 4
 PASS1, PASS2 = 0, 1
 STAGES = ("total", "h2d", "pyramid", "fast", "select1", "harris", "select2", "blur", "describe",
@@ -25,7 +26,7 @@ class Config(C.Structure):
     _fields_ = [("device", C.c_int), ("width", C.c_int), ("height", C.c_int), ("nfeatures", C.c_int),
                 ("nlevels", C.c_int), ("scale_factor", C.c_float), ("fast_threshold", C.c_int),
                 ("max_batch", C.c_int), ("lanes", C.c_int), ("max_rows", C.c_int), ("stream", C.c_void_p),
-                ("max_channels", C.c_int)]
+                ("max_channels", C.c_int), ("distribution", C.c_int)]
 
 
 class Veto(C.Structure):
@@ -143,7 +144,7 @@ class Context:
     """One svo_ctx: device buffers, streams and pipeline lanes for one image size."""
 
     def __init__(self, width=1241, height=376, nfeatures=2000, nlevels=8, scale_factor=1.2, fast_threshold=20,
-                 max_batch=1, lanes=1, max_rows=5000, device=0, stream=None, max_channels=1):
+                 max_batch=1, lanes=1, max_rows=5000, device=0, stream=None, max_channels=1, distribution=0):
         self.lib = load()
         cfg = Config()
         self.lib.svo_default_config(C.byref(cfg))
@@ -151,6 +152,7 @@ class Context:
         cfg.nlevels, cfg.scale_factor, cfg.fast_threshold = nlevels, scale_factor, fast_threshold
         cfg.max_batch, cfg.lanes, cfg.max_rows, cfg.stream = max_batch, lanes, max_rows, stream
         cfg.max_channels = max_channels
+        cfg.distribution = distribution      # DIST_RETAIN_BEST (cv::ORB parity) or DIST_OCTREE (opt-in, non-parity)
         self.cfg = cfg
         self.h = C.c_void_p()
         rc = self.lib.svo_create(C.byref(cfg), C.byref(self.h))

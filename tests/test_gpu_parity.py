@@ -592,3 +592,73 @@ def test_batch_windows_all_or_none(svo, ctxK):
     with pytest.raises(svo.SvoError) as e:
         ctxK.batch_submit(0, [a, c])
     assert e.value.code == svo.E_INVALID
+
+
+# ---- opt-in quadtree ("octree") keypoint distribution (non-parity mode) -----------------
+def octree_images(shape, seed):
+    """Dense texture, texture confined to one corner (deep, unbalanced tree) and a featureless image."""
+    h, w = shape
+    dense = synth.texture(shape, seed)
+    weak = 128 + (dense.astype(np.float32) - 128) * 0.3
+    weak[: h // 3, : w // 4] = dense[: h // 3, : w // 4]
+    return [dense, np.clip(np.rint(weak), 0, 255).astype(np.uint8), np.full(shape, 90, np.uint8)]
+
+
+@pytest.mark.parametrize("shape,nf", [((240, 400), 500), ((376, 1241), 2000), ((203, 317), 300)])
+def test_octree_extract_vs_oracle(svo, shape, nf):
+    """svo_config.distribution = SVO_DIST_OCTREE: k_octree (sorted path codes, runs as nodes) against the oracle's
+    explicit-node quadtree — same keypoints in the same order, same angles, responses and descriptors."""
+    c = svo.Context(shape[1], shape[0], nfeatures=nf, max_batch=2, lanes=1, max_rows=1000, distribution=svo.DIST_OCTREE)
+    try:
+        imgs = octree_images(shape, 40 + nf)
+        for img in imgs:
+            ref, rdesc, _ = O.orb(img, nf, distribution=1)
+            kp, desc = c.extract(img)
+            assert_kp_equal(kp, ref)
+            assert (desc == rdesc).all()
+        assert len(c.extract(imgs[0])[0]) > nf // 2
+        # the batch path runs the same stage
+        ref0, d0, _ = O.orb(imgs[0], nf, distribution=1)
+        ref1, d1, _ = O.orb(imgs[1], nf, distribution=1)
+        c.batch_submit(0, [dict(left=imgs[0], right=imgs[1], bf=100.0, baseline=0.5),
+                           dict(left=imgs[1], right=imgs[2], bf=100.0, baseline=0.5)])
+        c.batch_wait(0)
+        r = c.batch_result(0, 0)
+        assert r["status"] == 0
+        assert_kp_equal(r["kp_left"], ref0); assert_kp_equal(r["kp_right"], ref1)
+        assert (r["desc_left"] == d0).all() and (r["desc_right"] == d1).all()
+        r = c.batch_result(0, 1)
+        assert_kp_equal(r["kp_left"], ref1); assert r["n_right"] == 0
+    finally:
+        c.close()
+
+
+def test_octree_highres_uses_global_scratch(svo):
+    """2560x720 / 8000: level 0 holds more corners than the shared-memory carve-out (12288 points), so the sort and
+    the per-point state run from the level's global scratch arrays."""
+    shape = (720, 2560)
+    img = synth.texture(shape, 77)
+    c = svo.Context(shape[1], shape[0], nfeatures=8000, max_batch=1, lanes=1, max_rows=1000, distribution=svo.DIST_OCTREE)
+    try:
+        kp, desc = c.extract(img)
+        n0 = len(c.tap_list(0, svo.TAP_FAST, 0))
+        assert n0 > 12288, n0
+        ref, rdesc, _ = O.orb(img, 8000, distribution=1)
+        assert_kp_equal(kp, ref)
+        assert (desc == rdesc).all()
+    finally:
+        c.close()
+
+
+def test_octree_mode_limits_and_default(svo, ctxK):
+    with pytest.raises(svo.SvoError) as e:
+        svo.Context(1241, 376, nfeatures=20000, distribution=svo.DIST_OCTREE)   # level-0 quota 4342 > 4093 nodes
+    assert e.value.code == svo.E_CAPACITY
+    with pytest.raises(svo.SvoError) as e:
+        svo.Context(1241, 376, nfeatures=2000, distribution=7)
+    assert e.value.code == svo.E_INVALID
+    # the default stays the parity path: an octree context changes nothing for a retainBest one
+    img = synth.texture(synth.K_SHAPE, 9)
+    ref, rdesc, _ = O.orb(img, 2000)
+    kp, desc = ctxK.extract(img)
+    assert_kp_equal(kp, ref); assert (desc == rdesc).all()
