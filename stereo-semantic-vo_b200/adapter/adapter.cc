@@ -15,7 +15,7 @@
 namespace {
 
 struct Settings {
-    int nfeatures = 500, nlevels = 8, fast = 20, max_rows = 8192, device = 0;
+    int nfeatures = 500, nlevels = 8, fast = 20, max_rows = 8192, device = 0, distribution = SVO_DIST_RETAIN_BEST;
     float scale = 1.2f;
 };
 thread_local Settings g_set;
@@ -56,11 +56,13 @@ void mappoint::AddObservation(frame *fm, size_t idx)
 }
 
 // ---------------------------------------------------------------------------------- frame
-void frame::configure(int nfeatures, int nlevels, float scaleFactor, int fastThreshold, int max_map_rows, int device)
+void frame::configure(int nfeatures, int nlevels, float scaleFactor, int fastThreshold, int max_map_rows, int device,
+                      int distribution)
 {
     shutdown();
     g_set.nfeatures = nfeatures; g_set.nlevels = nlevels; g_set.scale = scaleFactor;
     g_set.fast = fastThreshold; g_set.max_rows = max_map_rows; g_set.device = device;
+    g_set.distribution = distribution;   // SVO_DIST_OCTREE: north_star's opt-in quadtree distribution (not the reference's cv::ORB)
 }
 
 svo_ctx *frame::engine(int width, int height)
@@ -73,6 +75,7 @@ svo_ctx *frame::engine(int width, int height)
     cfg.device = g_set.device; cfg.width = width; cfg.height = height;
     cfg.nfeatures = g_set.nfeatures; cfg.nlevels = g_set.nlevels; cfg.scale_factor = g_set.scale;
     cfg.fast_threshold = g_set.fast; cfg.max_batch = 1; cfg.lanes = 1; cfg.max_rows = g_set.max_rows;
+    cfg.distribution = g_set.distribution;
     cfg.max_channels = 3;   // colour KITTI frames (image_2/image_3) are converted on the device
     svo_ctx *ctx = nullptr;
     const int rc = svo_create(&cfg, &ctx);

@@ -24,7 +24,7 @@ public:
     // Extraction settings used by every frame constructed afterwards (the YAML's ORBextractor.*
     // keys, which the reference never reads: Stereo/KITTI00-02.yaml:38-51).
     static void configure(int nfeatures, int nlevels = 8, float scaleFactor = 1.2f, int fastThreshold = 20,
-                          int max_map_rows = 8192, int device = 0);
+                          int max_map_rows = 8192, int device = 0, int distribution = SVO_DIST_RETAIN_BEST);
     // The context shared by all frames of one image size on this thread (created on demand).
     static svo_ctx *engine(int width, int height);
     static void shutdown();

@@ -652,7 +652,7 @@ def test_octree_highres_uses_global_scratch(svo):
 
 def test_octree_mode_limits_and_default(svo, ctxK):
     with pytest.raises(svo.SvoError) as e:
-        svo.Context(1241, 376, nfeatures=20000, distribution=svo.DIST_OCTREE)   # level-0 quota 4342 > 4093 nodes
+        svo.Context(1241, 376, nfeatures=8000, nlevels=2, distribution=svo.DIST_OCTREE)   # level-0 quota 4364 > 4093 nodes
     assert e.value.code == svo.E_CAPACITY
     with pytest.raises(svo.SvoError) as e:
         svo.Context(1241, 376, nfeatures=2000, distribution=7)
