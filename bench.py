@@ -187,6 +187,17 @@ def run_gpu(args, rank, world, local_rank):
                     prev_desc=d_prev + t * K * 32, n_prev=int(n_prev[t]), prev_live=d_live + t * K,
                     map_desc=d_map + t * MAP_ROWS * 32, n_map=MAP_ROWS, map_prev_row=d_mpr + t * MAP_ROWS * 4)
 
+    # untimed: columns pass 1 leaves free in this workload (pass 2 scans only those; roofline work count below)
+    free_cols = []
+    for t0 in range(0, min(P, 2 * B), B):
+        n = min(B, P - t0)
+        ctx.batch_submit(0, [frame_host(t0 + i) for i in range(n)])
+        ctx.batch_wait(0)
+        for i in range(n):
+            r = ctx.batch_result(0, i)
+            free_cols.append(int(r["n_left"]) - int(np.asarray(r["p1_row_claimed"]).sum()))
+    free_cols = float(np.mean(free_cols))
+
     streams = [torch.cuda.ExternalStream(ctx.lane_stream(l), device=dev) for l in range(args.lanes)]
 
     barrier = grp.barrier
@@ -306,7 +317,7 @@ def run_gpu(args, rank, world, local_rank):
         single = {"k_fast": ("fast", ab["fast"] * nimg), "k_blur": ("blur", ab["blur"] * nimg),
                   "k_describe": ("describe", ab["describe"] * nimg), "k_harris": ("harris", ab["harris"] * nimg),
                   "k_pairs": ("k_pairs", B * (npv + NFEAT) * 32 + B * npv * NFEAT),      # descriptors in, u8 matrix out
-                  "k_shortlist(pass 2)": ("k_shortlist2", B * (need_rows + NFEAT) * 32)}
+                  "k_shortlist(pass 2)": ("k_shortlist2", B * (need_rows + free_cols) * 32)}   # rows + free columns in
         dom = max(single, key=lambda k: stage.get(single[k][0], 0.0))
         dur_ms = stage.get(single[dom][0], 0.0)
         alg_bytes = float(single[dom][1])
@@ -319,7 +330,7 @@ def run_gpu(args, rank, world, local_rank):
         # the matchers are bound by the XU pipe (POPC, 16 lanes/clk/SM), not by bytes: report that ceiling too
         popc = None
         if dom in ("k_pairs", "k_shortlist(pass 2)") and dur_ms > 0:
-            pairs = B * (npv * NFEAT if dom == "k_pairs" else need_rows * NFEAT)
+            pairs = B * (npv * NFEAT if dom == "k_pairs" else need_rows * free_cols)
             per_pair = 6 if dom == "k_pairs" else 5
             sm_clock = (sampler.result()["sm_mhz"] or 1965) * 1e6
             peak_popc = 148 * 16 * sm_clock

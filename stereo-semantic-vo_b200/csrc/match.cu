@@ -232,6 +232,56 @@ __global__ void k_greedy_init(GreedyArgs a, int reset_time)
 }
 
 // ---------------------------------------------------------------------------------------
+// batch pass 2: the columns pass 1 left free, ascending.  The reference's scan skips a claimed column before it
+// computes anything (src/pnpmatch.cc:176 `if (CurrentFrame->MapPoints[j]) continue`), and every claim made before
+// pass 2 starts is final, so those columns are invisible to all pass-2 rows: k_shortlist stages and scans only
+// the free ones (a third of the columns are claimed by pass 1 on the bench sequence).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_free_cols(GreedyArgs a)
+{
+    __shared__ int wsum[32];
+    __shared__ int base;
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = set_count(a.cols, f);
+    const uint8_t *claimed = a.claimed + (size_t)f * a.cols.stride_rows;
+    uint16_t *out = a.free_col + (size_t)f * a.cols.stride_rows;
+    if (tid == 0) base = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < N; c0 += 1024) {
+        const int c = c0 + tid;
+        const bool fr = c < N && !claimed[c];
+        const uint32_t m = __ballot_sync(0xffffffffu, fr);
+        if (lane == 0) wsum[warp] = __popc(m);
+        __syncthreads();
+        int v = wsum[lane], inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        const int off = base + __shfl_sync(0xffffffffu, inc - v, warp);
+        const int tot = __shfl_sync(0xffffffffu, inc, 31);
+        if (fr) out[off + __popc(m & ((1u << lane) - 1u))] = (uint16_t)c;
+        __syncthreads();
+        if (tid == 0) base += tot;
+        __syncthreads();
+    }
+    if (tid == 0) a.free_cnt[f] = base;
+}
+
+// stage the columns idx[c0 .. c0+nc) of a descriptor set (and their indices) into the swizzled shared tile
+__device__ __forceinline__ void load_tile_indexed(uint4 *tile, uint16_t *tcol, const uint8_t *desc, const uint16_t *idx, int c0, int nc)
+{
+    const uint4 *src = reinterpret_cast<const uint4 *>(desc);
+    for (int i = threadIdx.x; i < nc * 2; i += blockDim.x) {
+        const int j = i >> 1, h = i & 1;
+        const int c = idx[c0 + j];
+        tile[unit_of(j, h)] = src[(size_t)c * 2 + h];
+        if (h == 0) tcol[j] = (uint16_t)c;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // greedy step 1: short lists (ascending column) of columns with d < T
 // ---------------------------------------------------------------------------------------
 #define SL_ROWS_PER_WARP 4
@@ -274,12 +324,15 @@ __device__ __forceinline__ int prune_list(const GreedyArgs &a, size_t row, int c
     return n;
 }
 
-template <bool WIN>
+template <bool WIN, bool FREE>
 __global__ void __launch_bounds__(M_THREADS, 3) k_shortlist(GreedyArgs a, int T)
 {
     __shared__ uint4 tile[COL_TILE * 2];
+    __shared__ uint16_t tcol[FREE ? COL_TILE : 2];
     const int f = blockIdx.y;
-    const int M = set_count(a.rows, f), N = set_count(a.cols, f);
+    // FREE: the columns are the frame's free-column list (k_free_cols), entries carry the original index
+    const int M = set_count(a.rows, f), N = FREE ? a.free_cnt[f] : set_count(a.cols, f);
+    const uint16_t *fcol = FREE ? a.free_col + (size_t)f * a.cols.stride_rows : nullptr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t ro = (size_t)f * a.rows.stride_rows;
     // rows to process: all of them, or (batch pass 2) the work list k_greedy_init compacted
@@ -308,7 +361,8 @@ __global__ void __launch_bounds__(M_THREADS, 3) k_shortlist(GreedyArgs a, int T)
     for (int c0 = 0; c0 < N; c0 += COL_TILE) {
         const int nc = min(COL_TILE, N - c0);
         __syncthreads();
-        load_tile(tile, cd, c0, nc);
+        if (FREE) load_tile_indexed(tile, tcol, cd, fcol, c0, nc);
+        else load_tile(tile, cd, c0, nc);
         __syncthreads();
         for (int jb = 0; jb < nc; jb += 32) {
             const int j = jb + lane;
@@ -337,7 +391,8 @@ __global__ void __launch_bounds__(M_THREADS, 3) k_shortlist(GreedyArgs a, int T)
                 if (m) {
                     if (hit) {
                         const int pos = cnt[k] + __popc(m & ((1u << lane) - 1u));
-                        if (pos < SVO_SHORT_CAP) *short_slot(a, ro + rid[k], pos) = ((uint32_t)d[k] << 16) | (uint32_t)(c0 + j);
+                        if (pos < SVO_SHORT_CAP)
+                            *short_slot(a, ro + rid[k], pos) = ((uint32_t)d[k] << 16) | (FREE ? (uint32_t)tcol[j] : (uint32_t)(c0 + j));
                     }
                     cnt[k] += __popc(m);
                 }
@@ -1077,14 +1132,16 @@ void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStrea
     if (a.need_list) cudaMemsetAsync(a.list_cnt, 0, sizeof(int) * 2 * nframes, st);
     if (a.win_gather) { k_win_prepare<<<nframes, 256, 0, st>>>(a); ++*launches; }
     k_greedy_init<<<gi, 256, 0, st>>>(a, 1);
+    if (a.free_col && !a.win_gather && !a.win_uvr) { k_free_cols<<<nframes, 1024, 0, st>>>(a); ++*launches; }
     const int T = a.mode == SVO_GREEDY_PASS1 ? 15 : 60;
     dim3 gs((maxM + M_WARPS * SL_ROWS_PER_WARP - 1) / (M_WARPS * SL_ROWS_PER_WARP), nframes);
     if (ev0) cudaEventRecord(ev0, st);
     if (a.win_gather) {
         const int gx = (maxM + M_WARPS - 1) / M_WARPS;
         k_shortlist_win<<<dim3(gx < 160 ? gx : 160, nframes), M_THREADS, 0, st>>>(a, T);
-    } else if (a.win_uvr) k_shortlist<true><<<gs, M_THREADS, 0, st>>>(a, T);
-    else k_shortlist<false><<<gs, M_THREADS, 0, st>>>(a, T);
+    } else if (a.win_uvr) k_shortlist<true, false><<<gs, M_THREADS, 0, st>>>(a, T);
+    else if (a.free_col) k_shortlist<false, true><<<gs, M_THREADS, 0, st>>>(a, T);
+    else k_shortlist<false, false><<<gs, M_THREADS, 0, st>>>(a, T);
     if (ev1) cudaEventRecord(ev1, st);
     if (a.need_list && a.dmat && !a.win_gather) {
         const int gx = (maxM + M_WARPS - 1) / M_WARPS;

@@ -38,6 +38,7 @@ struct FrameBufs {           // per-frame (stereo pair) device arrays
     float *win, *cur_xy, *row_xy; int *boxes; double *F;
     // batch extras: keypoint grid of the windowed pass 2 (win / cur_xy are allocated for batch frames too)
     int *cell_off; uint16_t *cell_list;
+    uint16_t *free_col; int *free_cnt;   // batch pass 2: columns pass 1 left free
 };
 
 struct HostArena {           // pinned mirror of one lane's outputs
@@ -273,7 +274,9 @@ int alloc_frames(svo_ctx *ctx, FrameBufs &f, int nframes, int col_stride, int ro
     f.cols = nullptr; f.win = f.cur_xy = f.row_xy = nullptr; f.boxes = nullptr; f.F = nullptr;
     f.dmat = nullptr; f.bf_key = nullptr; f.dmat_pitch = 0; f.dmat_frame_stride = 0;
     f.cell_off = nullptr; f.cell_list = nullptr;
+    f.free_col = nullptr; f.free_cnt = nullptr;
     if (!sync_extras) {
+        TRY(dalloc(ctx, &f.free_col, C)); TRY(dalloc(ctx, &f.free_cnt, F));
         TRY(dalloc(ctx, &f.win, R * 3)); TRY(dalloc(ctx, &f.cur_xy, C * 2));
         TRY(dalloc(ctx, &f.cell_off, F * (SVO_WIN_CELLS + 1))); TRY(dalloc(ctx, &f.cell_list, C));
         // u8 distance matrix previous-frame rows x current-frame columns; k_scores_m gives every lane a
@@ -430,6 +433,9 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
             ga.kp = b.kp + (size_t)L.slot0 * g.kp_cap; ga.kp_frame_stride = 2 * (size_t)g.kp_cap;
             ga.win_out = fb.win + (size_t)L.frame0 * R * 3; ga.cur_xy_out = fb.cur_xy + (size_t)L.frame0 * K * 2;
             ga.win_uvr = ga.win_out; ga.cur_xy = ga.cur_xy_out;
+        }
+        else if (any_prev) {   // pass 1 ran: its claims hide columns from every pass-2 row
+            ga.free_col = fb.free_col + (size_t)L.frame0 * K; ga.free_cnt = fb.free_cnt + L.frame0;
         }
         launch_greedy(ga, n, false, st, &ctx->launches, ev ? ev[14] : nullptr, ev ? ev[15] : nullptr);
     }

@@ -181,6 +181,9 @@ struct GreedyArgs {
     int win_gather, cell_shift, ncx, ncy;
     int *cell_off;                // [frame][SVO_WIN_CELLS + 1]
     uint16_t *cell_list;          // [frame][cols.stride_rows]
+    // batch pass 2 without windows: the ascending list of columns pass 1 left free (k_free_cols); k_shortlist scans only those
+    uint16_t *free_col;           // [frame][cols.stride_rows] or NULL
+    int *free_cnt;                // [frame]
     const svo_keypoint *kp; size_t kp_frame_stride;   // current (left) keypoints of frame f at kp + f * kp_frame_stride
     float *win_out, *cur_xy_out;
     // veto (pass 1)
