@@ -324,91 +324,145 @@ __device__ __forceinline__ int prune_list(const GreedyArgs &a, size_t row, int c
     return n;
 }
 
+// Persistent form: the work of a launch is the list of (frame, group of 48 rows) items, frame major, and every
+// CTA takes a contiguous, equal share of it, so the frame's columns are staged ONCE per CTA (twice when its share
+// straddles a frame boundary) instead of once per 32 rows, and the column loop runs without barriers.  When a
+// frame has more columns than the tile holds, the tile is re-staged per item as before.
+#define SLN_THREADS 384
+#define SLN_WARPS (SLN_THREADS / 32)
+#define SLN_GROUP (SLN_WARPS * SL_ROWS_PER_WARP)
+
 template <bool WIN, bool FREE>
-__global__ void __launch_bounds__(M_THREADS, 3) k_shortlist(GreedyArgs a, int T)
+__global__ void __launch_bounds__(SLN_THREADS, 2) k_shortlist(GreedyArgs a, int T, int tile_cap, int nframes)
 {
-    __shared__ uint4 tile[COL_TILE * 2];
-    __shared__ uint16_t tcol[FREE ? COL_TILE : 2];
-    const int f = blockIdx.y;
-    // FREE: the columns are the frame's free-column list (k_free_cols), entries carry the original index
-    const int M = set_count(a.rows, f), N = FREE ? a.free_cnt[f] : set_count(a.cols, f);
-    const uint16_t *fcol = FREE ? a.free_col + (size_t)f * a.cols.stride_rows : nullptr;
+    extern __shared__ __align__(16) uint8_t sl_dyn[];
+    uint4 *tile = reinterpret_cast<uint4 *>(sl_dyn);
+    uint16_t *tcol = reinterpret_cast<uint16_t *>(sl_dyn + (size_t)tile_cap * 32);
+    int *pref = reinterpret_cast<int *>(sl_dyn + (size_t)tile_cap * 34);      // [nframes + 1] first work item of a frame
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t ro = (size_t)f * a.rows.stride_rows;
-    // rows to process: all of them, or (batch pass 2) the work list k_greedy_init compacted
-    const int *list = a.need_list ? a.need_list + ro : nullptr;
-    const int nrows = list ? min(a.list_cnt[2 * f], M) : M;
-    if (blockIdx.x * M_WARPS * SL_ROWS_PER_WARP >= nrows) return;
-    const int r0 = (blockIdx.x * M_WARPS + warp) * SL_ROWS_PER_WARP;
-    const uint8_t *rd = set_desc(a.rows, f), *cd = set_desc(a.cols, f);
-    const float *cxy = WIN ? a.cur_xy + (size_t)f * a.cols.stride_rows * 2 : nullptr;
-    const uint8_t *rl = list ? nullptr : live_of(a, f);   // the work list holds live rows only
-    Row R[SL_ROWS_PER_WARP];
-    int cnt[SL_ROWS_PER_WARP], rid[SL_ROWS_PER_WARP];
-    bool live[SL_ROWS_PER_WARP];
-    float wu[SL_ROWS_PER_WARP], wv[SL_ROWS_PER_WARP], wr[SL_ROWS_PER_WARP];
+    if (warp == 0) {
+        int run = 0;
+        for (int base = 0; base < nframes; base += 32) {
+            const int f = base + lane;
+            int gcount = 0;
+            if (f < nframes) {
+                const int Mf = set_count(a.rows, f);
+                const int nr = a.need_list ? min(a.list_cnt[2 * f], Mf) : Mf;
+                gcount = (nr + SLN_GROUP - 1) / SLN_GROUP;
+            }
+            int inc = gcount;
 #pragma unroll
-    for (int k = 0; k < SL_ROWS_PER_WARP; ++k) {
-        const int i = r0 + k;
-        const int r = i < nrows ? (list ? list[i] : i) : (list ? list[nrows - 1] : M - 1);
-        rid[k] = r;
-        cnt[k] = 0;
-        live[k] = i < nrows && (!rl || rl[r]);
-        R[k] = load_row(rd, r);
-        wu[k] = wv[k] = wr[k] = 0.f;
-        if (WIN && i < nrows) { wu[k] = a.win_uvr[(ro + r) * 3]; wv[k] = a.win_uvr[(ro + r) * 3 + 1]; wr[k] = a.win_uvr[(ro + r) * 3 + 2]; }
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            if (f < nframes) pref[f] = run + inc - gcount;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) pref[nframes] = run;
     }
-    for (int c0 = 0; c0 < N; c0 += COL_TILE) {
-        const int nc = min(COL_TILE, N - c0);
-        __syncthreads();
-        if (FREE) load_tile_indexed(tile, tcol, cd, fcol, c0, nc);
-        else load_tile(tile, cd, c0, nc);
-        __syncthreads();
-        for (int jb = 0; jb < nc; jb += 32) {
-            const int j = jb + lane;
-            const bool inb = j < nc;
-            const int jj = inb ? j : 0;
-            const uint4 x = tile[unit_of(jj, 0)], y = tile[unit_of(jj, 1)];
-            float cu = 0.f, cv = 0.f;
-            if (WIN && inb) { cu = cxy[2 * (c0 + j)]; cv = cxy[2 * (c0 + j) + 1]; }
-            int d[SL_ROWS_PER_WARP];
+    __syncthreads();
+    const int W = pref[nframes];
+    const int w0 = (int)((long long)blockIdx.x * W / gridDim.x), w1 = (int)((long long)(blockIdx.x + 1) * W / gridDim.x);
+    int f = 0, cur_f = -1, N = 0;
+    bool single = false;
+    const uint8_t *cd = nullptr;
+    const uint16_t *fcol = nullptr;
+    for (int w = w0; w < w1; ++w) {
+        while (pref[f + 1] <= w) ++f;
+        if (f != cur_f) {
+            cur_f = f;
+            // FREE: the columns are the frame's free-column list (k_free_cols), entries carry the original index
+            N = FREE ? a.free_cnt[f] : set_count(a.cols, f);
+            cd = set_desc(a.cols, f);
+            fcol = FREE ? a.free_col + (size_t)f * a.cols.stride_rows : nullptr;
+            single = N <= tile_cap;
+            if (single) {
+                __syncthreads();
+                if (FREE) load_tile_indexed(tile, tcol, cd, fcol, 0, N);
+                else load_tile(tile, cd, 0, N);
+                __syncthreads();
+            }
+        }
+        const int grp = w - pref[f];
+        const int M = set_count(a.rows, f);
+        const size_t ro = (size_t)f * a.rows.stride_rows;
+        // rows to process: all of them, or (batch pass 2) the work list k_greedy_init compacted
+        const int *list = a.need_list ? a.need_list + ro : nullptr;
+        const int nrows = list ? min(a.list_cnt[2 * f], M) : M;
+        const int r0 = (grp * SLN_WARPS + warp) * SL_ROWS_PER_WARP;
+        const uint8_t *rd = set_desc(a.rows, f);
+        const float *cxy = WIN ? a.cur_xy + (size_t)f * a.cols.stride_rows * 2 : nullptr;
+        const uint8_t *rl = list ? nullptr : live_of(a, f);   // the work list holds live rows only
+        Row R[SL_ROWS_PER_WARP];
+        int cnt[SL_ROWS_PER_WARP], rid[SL_ROWS_PER_WARP];
+        bool live[SL_ROWS_PER_WARP];
+        float wu[SL_ROWS_PER_WARP], wv[SL_ROWS_PER_WARP], wr[SL_ROWS_PER_WARP];
 #pragma unroll
-            for (int k = 0; k < SL_ROWS_PER_WARP; ++k)
-                d[k] = popc8_5(R[k].a.x ^ x.x, R[k].a.y ^ x.y, R[k].a.z ^ x.z, R[k].a.w ^ x.w,
-                             R[k].b.x ^ y.x, R[k].b.y ^ y.y, R[k].b.z ^ y.z, R[k].b.w ^ y.w);
-            // one vote for the 4 rows: most 32-column steps hold no entry below T at all
-            const int dmin = min(min(d[0], d[1]), min(d[2], d[3]));
-            if (!__any_sync(0xffffffffu, inb && dmin < T)) continue;
+        for (int k = 0; k < SL_ROWS_PER_WARP; ++k) {
+            const int i = r0 + k;
+            const int r = i < nrows ? (list ? list[i] : i) : (list ? list[nrows - 1] : M - 1);
+            rid[k] = r;
+            cnt[k] = 0;
+            live[k] = i < nrows && (!rl || rl[r]);
+            R[k] = load_row(rd, r);
+            wu[k] = wv[k] = wr[k] = 0.f;
+            if (WIN && i < nrows) { wu[k] = a.win_uvr[(ro + r) * 3]; wv[k] = a.win_uvr[(ro + r) * 3 + 1]; wr[k] = a.win_uvr[(ro + r) * 3 + 2]; }
+        }
+        for (int c0 = 0; c0 < N; c0 += tile_cap) {
+            const int nc = min(tile_cap, N - c0);
+            if (!single) {
+                __syncthreads();
+                if (FREE) load_tile_indexed(tile, tcol, cd, fcol, c0, nc);
+                else load_tile(tile, cd, c0, nc);
+                __syncthreads();
+            }
+            for (int jb = 0; jb < nc; jb += 32) {
+                const int j = jb + lane;
+                const bool inb = j < nc;
+                const int jj = inb ? j : 0;
+                const uint4 x = tile[unit_of(jj, 0)], y = tile[unit_of(jj, 1)];
+                float cu = 0.f, cv = 0.f;
+                if (WIN && inb) { cu = cxy[2 * (c0 + j)]; cv = cxy[2 * (c0 + j) + 1]; }
+                int d[SL_ROWS_PER_WARP];
 #pragma unroll
-            for (int k = 0; k < SL_ROWS_PER_WARP; ++k) {
-                if (!live[k]) continue;   // warp-uniform
-                bool hit = inb && d[k] < T;
-                if (WIN) {
-                    const float du = cu - wu[k], dv = cv - wv[k];
-                    hit = hit && !(du < -wr[k] || du > wr[k] || dv < -wr[k] || dv > wr[k]);
-                }
-                const uint32_t m = __ballot_sync(0xffffffffu, hit);
-                if (m) {
-                    if (hit) {
-                        const int pos = cnt[k] + __popc(m & ((1u << lane) - 1u));
-                        if (pos < SVO_SHORT_CAP)
-                            *short_slot(a, ro + rid[k], pos) = ((uint32_t)d[k] << 16) | (FREE ? (uint32_t)tcol[j] : (uint32_t)(c0 + j));
+                for (int k = 0; k < SL_ROWS_PER_WARP; ++k)
+                    d[k] = popc8_5(R[k].a.x ^ x.x, R[k].a.y ^ x.y, R[k].a.z ^ x.z, R[k].a.w ^ x.w,
+                                 R[k].b.x ^ y.x, R[k].b.y ^ y.y, R[k].b.z ^ y.z, R[k].b.w ^ y.w);
+                // one vote for the 4 rows: most 32-column steps hold no entry below T at all
+                const int dmin = min(min(d[0], d[1]), min(d[2], d[3]));
+                if (!__any_sync(0xffffffffu, inb && dmin < T)) continue;
+#pragma unroll
+                for (int k = 0; k < SL_ROWS_PER_WARP; ++k) {
+                    if (!live[k]) continue;   // warp-uniform
+                    bool hit = inb && d[k] < T;
+                    if (WIN) {
+                        const float du = cu - wu[k], dv = cv - wv[k];
+                        hit = hit && !(du < -wr[k] || du > wr[k] || dv < -wr[k] || dv > wr[k]);
                     }
-                    cnt[k] += __popc(m);
+                    const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                    if (m) {
+                        if (hit) {
+                            const int pos = cnt[k] + __popc(m & ((1u << lane) - 1u));
+                            if (pos < SVO_SHORT_CAP)
+                                *short_slot(a, ro + rid[k], pos) = ((uint32_t)d[k] << 16) | (FREE ? (uint32_t)tcol[j] : (uint32_t)(c0 + j));
+                        }
+                        cnt[k] += __popc(m);
+                    }
                 }
             }
         }
-    }
-    if (a.mode == SVO_GREEDY_PASS2) {
-        __syncwarp();
+        if (a.mode == SVO_GREEDY_PASS2) {
+            __syncwarp();
 #pragma unroll
-        for (int k = 0; k < SL_ROWS_PER_WARP; ++k)
-            if (live[k]) cnt[k] = prune_list(a, ro + rid[k], cnt[k], lane);   // warp-uniform
-    }
-    if (lane == 0) {
+            for (int k = 0; k < SL_ROWS_PER_WARP; ++k)
+                if (live[k]) cnt[k] = prune_list(a, ro + rid[k], cnt[k], lane);   // warp-uniform
+        }
+        if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < SL_ROWS_PER_WARP; ++k)
-            if (r0 + k < nrows) a.short_cnt[ro + rid[k]] = live[k] ? cnt[k] : 0;
+            for (int k = 0; k < SL_ROWS_PER_WARP; ++k)
+                if (r0 + k < nrows) a.short_cnt[ro + rid[k]] = live[k] ? cnt[k] : 0;
+        }
     }
 }
 
@@ -1110,9 +1164,19 @@ __global__ void __launch_bounds__(M_THREADS) k_scores_m(PairArgs p)
 }
 
 static int g_resolve_smem_limit = 48 * 1024;
+static int g_shortlist_smem_limit = 48 * 1024;   // dynamic shared memory of one k_shortlist CTA (two per SM)
+static int g_num_sms = 148;
 
 int setup_match_attributes()
 {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) g_num_sms = sms;
+    g_shortlist_smem_limit = 110 * 1024;
+    if (cudaFuncSetAttribute(k_shortlist<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_shortlist_smem_limit) != cudaSuccess ||
+        cudaFuncSetAttribute(k_shortlist<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_shortlist_smem_limit) != cudaSuccess ||
+        cudaFuncSetAttribute(k_shortlist<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_shortlist_smem_limit) != cudaSuccess)
+        return 1;
     g_resolve_smem_limit = 200 * 1024;
     if (cudaFuncSetAttribute(k_scores_m, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess) return 1;
     return (int)cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, g_resolve_smem_limit);
@@ -1134,14 +1198,22 @@ void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStrea
     k_greedy_init<<<gi, 256, 0, st>>>(a, 1);
     if (a.free_col && !a.win_gather && !a.win_uvr) { k_free_cols<<<nframes, 1024, 0, st>>>(a); ++*launches; }
     const int T = a.mode == SVO_GREEDY_PASS1 ? 15 : 60;
-    dim3 gs((maxM + M_WARPS * SL_ROWS_PER_WARP - 1) / (M_WARPS * SL_ROWS_PER_WARP), nframes);
+    // k_shortlist: two persistent CTAs per SM share the (frame, row group) items; the tile holds a whole frame's columns
+    // when they fit (34 bytes per column)
+    int tile_cap = (maxN + 31) & ~31;
+    const int tile_max = ((g_shortlist_smem_limit - 4 * (nframes + 1)) / 34) & ~31;
+    if (tile_cap > tile_max) tile_cap = tile_max;
+    if (tile_cap < 32) tile_cap = 32;
+    const size_t sl_smem = (size_t)tile_cap * 34 + sizeof(int) * (size_t)(nframes + 1);
+    const int items = nframes * ((maxM + SLN_GROUP - 1) / SLN_GROUP);
+    const int gs = items < 2 * g_num_sms ? items : 2 * g_num_sms;
     if (ev0) cudaEventRecord(ev0, st);
     if (a.win_gather) {
         const int gx = (maxM + M_WARPS - 1) / M_WARPS;
         k_shortlist_win<<<dim3(gx < 160 ? gx : 160, nframes), M_THREADS, 0, st>>>(a, T);
-    } else if (a.win_uvr) k_shortlist<true, false><<<gs, M_THREADS, 0, st>>>(a, T);
-    else if (a.free_col) k_shortlist<false, true><<<gs, M_THREADS, 0, st>>>(a, T);
-    else k_shortlist<false, false><<<gs, M_THREADS, 0, st>>>(a, T);
+    } else if (a.win_uvr) k_shortlist<true, false><<<gs, SLN_THREADS, sl_smem, st>>>(a, T, tile_cap, nframes);
+    else if (a.free_col) k_shortlist<false, true><<<gs, SLN_THREADS, sl_smem, st>>>(a, T, tile_cap, nframes);
+    else k_shortlist<false, false><<<gs, SLN_THREADS, sl_smem, st>>>(a, T, tile_cap, nframes);
     if (ev1) cudaEventRecord(ev1, st);
     if (a.need_list && a.dmat && !a.win_gather) {
         const int gx = (maxM + M_WARPS - 1) / M_WARPS;
