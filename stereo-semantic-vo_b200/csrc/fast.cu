@@ -15,60 +15,49 @@
 
 #define FAST_THREADS 256
 
-// ---- stage A: necessary condition on 4 horizontally adjacent pixels at once (SWAR on bytes) ----
+// ---- stage A: necessary condition on 4 horizontally adjacent pixels at once ----
 // Any 9-arc of the 16-ring holds at least one pixel of every antipodal pair, so a "centre brighter"
-// corner needs p[k] < v - t or p[k+8] < v - t for every k, and a "centre darker" corner the mirror
-// image with p > v + t.  Four of the eight pairs are tested (N/S, E/W and the two diagonals).
-// All comparisons are unsigned-byte compares in bit 7 of each byte; LOP3/IADD only, no SIMD video ops
-// (sm_100a emulates those).
+// corner needs min(p[k], p[k+8]) < v - t for every k, and a "centre darker" corner max(p[k], p[k+8]) > v + t
+// for every k.  Four of the eight pairs are tested (N/S, E/W and the two diagonals):
+//     bright  <=>  max over pairs of min(pair) + t < v          dark  <=>  min over pairs of max(pair) > v + t
+// The pixels are widened to u16x2 (PRMT) so the min/max trees run on the packed DPX instructions
+// (VIMNMX3.U16x2, two pixels per instruction) and the two final compares are packed subtractions whose
+// bit 15 cannot borrow across halves.  (An earlier all-byte SWAR version built every compare from LOP3/IADD —
+// sm_100a emulates the byte-wise video compares — and cost 2.2x the instructions; ncu: 167 -> 76 per quad.)
 #define SW_H 0x80808080u
-#define SW_L 0x7f7f7f7fu
+#define U16_H 0x80008000u
 
-// bit 7 of each byte: x < y (unsigned).  xh = x | H and yl = y & L are passed in so they can be shared.
-__device__ __forceinline__ uint32_t swar_lt(uint32_t x, uint32_t xh, uint32_t y, uint32_t yl)
+// two pixels (one u16x2 half of the quad): bit 15 of a half is set when that pixel passes
+__device__ __forceinline__ uint32_t fast_quick2(uint32_t v, uint32_t n0, uint32_t n8, uint32_t n4, uint32_t n12,
+                                                uint32_t n2, uint32_t n10, uint32_t n6, uint32_t n14, uint32_t t1)
 {
-    const uint32_t t1 = xh - yl;                      // bit 7: (x & 0x7f) >= (y & 0x7f); no cross-byte borrow
-    return (~x & y) | (~(x ^ y) & ~t1);
+    const uint32_t mn = __vmaxu2(__vimax3_u16x2(__vminu2(n0, n8), __vminu2(n4, n12), __vminu2(n2, n10)), __vminu2(n6, n14));
+    const uint32_t mx = __vminu2(__vimin3_u16x2(__vmaxu2(n0, n8), __vmaxu2(n4, n12), __vmaxu2(n2, n10)), __vmaxu2(n6, n14));
+    // halves stay below 2^15, so (a | H) - b keeps bit 15 exactly when a >= b, independently per half
+    const uint32_t bright = (v | U16_H) - (mn + t1);      // v >= maxmin + t + 1
+    const uint32_t dark = (mx | U16_H) - (v + t1);        // minmax >= v + t + 1
+    return (bright | dark) & U16_H;
 }
-// per-byte min(v + t, 255) and max(v - t, 0) for 0 < t < 128
-__device__ __forceinline__ uint32_t swar_addsat(uint32_t v, uint32_t t4)
-{
-    const uint32_t s = (v & SW_L) + t4;               // low 7 bits + t: < 256 per byte
-    const uint32_t ovf = v & s & SW_H;
-    return (s ^ (v & SW_H)) | ((ovf << 1) - (ovf >> 7));
-}
-__device__ __forceinline__ uint32_t swar_subsat(uint32_t v, uint32_t t4)
-{
-    const uint32_t d = (v | SW_H) - t4;
-    const uint32_t m = (v | d) & SW_H;                // bytes that did not underflow
-    return (d & (m - (m >> 7))) | (d & v & SW_H);
-}
-// q: address of the quad's first pixel in the staged rows (4-byte aligned); returns bit 7 flags
-__device__ __forceinline__ uint32_t fast_quick4(const uint8_t *q, int sp, uint32_t t4)
+// q: address of the quad's first pixel in the staged rows (4-byte aligned); returns bit 7 flags; t1 = (t + 1) * 0x10001
+__device__ __forceinline__ uint32_t fast_quick4(const uint8_t *q, int sp, uint32_t t1)
 {
     const uint32_t *c = reinterpret_cast<const uint32_t *>(q);
     const int sw = sp >> 2;
     const uint32_t v = c[0];
-    const uint32_t lo = swar_subsat(v, t4), hi = swar_addsat(v, t4);
-    const uint32_t lol = lo & SW_L, hih = hi | SW_H;
-    uint32_t pb = SW_H, pd = SW_H;
-#define FAST_PAIR(P, Q) { \
-        const uint32_t p_ = (P), q_ = (Q); \
-        pb &= swar_lt(p_, p_ | SW_H, lo, lol) | swar_lt(q_, q_ | SW_H, lo, lol); \
-        pd &= swar_lt(hi, hih, p_, p_ & SW_L) | swar_lt(hi, hih, q_, q_ & SW_L); }
-    FAST_PAIR(c[3 * sw], c[-3 * sw]);                                                   // ring 0 / 8
-    {
-        const uint32_t wl = c[-1], wr = c[1];
-        FAST_PAIR(__byte_perm(v, wr, 0x6543), __byte_perm(wl, v, 0x4321));              // ring 4 (x+3) / 12 (x-3)
-    }
-    {
-        const uint32_t al = c[2 * sw - 1], a0 = c[2 * sw], ar = c[2 * sw + 1];
-        const uint32_t bl = c[-2 * sw - 1], b0 = c[-2 * sw], br = c[-2 * sw + 1];
-        FAST_PAIR(__byte_perm(a0, ar, 0x5432), __byte_perm(bl, b0, 0x5432));            // ring 2 (+2,+2) / 10 (-2,-2)
-        FAST_PAIR(__byte_perm(b0, br, 0x5432), __byte_perm(al, a0, 0x5432));            // ring 6 (+2,-2) / 14 (-2,+2)
-    }
-#undef FAST_PAIR
-    return (pb | pd) & SW_H;
+    const uint32_t r0 = c[3 * sw], r8 = c[-3 * sw];                                     // ring 0 / 8
+    const uint32_t wl = c[-1], wr = c[1];
+    const uint32_t r4 = __byte_perm(v, wr, 0x6543), r12 = __byte_perm(wl, v, 0x4321);   // ring 4 (x+3) / 12 (x-3)
+    const uint32_t al = c[2 * sw - 1], a0 = c[2 * sw], ar = c[2 * sw + 1];
+    const uint32_t bl = c[-2 * sw - 1], b0 = c[-2 * sw], br = c[-2 * sw + 1];
+    const uint32_t r2 = __byte_perm(a0, ar, 0x5432), r10 = __byte_perm(bl, b0, 0x5432); // ring 2 (+2,+2) / 10 (-2,-2)
+    const uint32_t r6 = __byte_perm(b0, br, 0x5432), r14 = __byte_perm(al, a0, 0x5432); // ring 6 (+2,-2) / 14 (-2,+2)
+#define LO2(w) __byte_perm(w, 0, 0x4140)
+#define HI2(w) __byte_perm(w, 0, 0x4342)
+    const uint32_t f01 = fast_quick2(LO2(v), LO2(r0), LO2(r8), LO2(r4), LO2(r12), LO2(r2), LO2(r10), LO2(r6), LO2(r14), t1);
+    const uint32_t f23 = fast_quick2(HI2(v), HI2(r0), HI2(r8), HI2(r4), HI2(r12), HI2(r2), HI2(r10), HI2(r6), HI2(r14), t1);
+#undef LO2
+#undef HI2
+    return __byte_perm(f01, f23, 0x7531) & SW_H;     // bit 15 of each half -> bit 7 of the pixel's byte
 }
 
 // Exact score: max over the 16 arcs of 9 contiguous ring pixels of min(v - p) (centre brighter) and of
@@ -171,7 +160,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(Bufs b, Geom g, int slot0
     const int nchunks = (nrow + 2) * cpr;
     const int wcap = ((nchunks + nwarps - 1) / nwarps) << 7;
     uint16_t *mine = cand + warp * wcap;
-    const uint32_t t4 = (uint32_t)t * 0x01010101u;
+    const uint32_t t4 = (uint32_t)(t + 1) * 0x10001u;     // fast_quick4's packed threshold
     const uint32_t ltm = (1u << lane) - 1u;
     int nmine = 0;
     {
