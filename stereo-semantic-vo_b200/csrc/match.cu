@@ -1236,7 +1236,7 @@ void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStrea
 
 // BF + greedy pass 1 of a batch with every distance computed once (k_pairs).
 void launch_pass1_fused(const PairArgs &p0, const BfArgs &b, int nframes, cudaStream_t st, long long *launches,
-                        cudaEvent_t ev0, cudaEvent_t ev1)
+                        cudaEvent_t ev0, cudaEvent_t ev1, cudaStream_t st_scores, cudaEvent_t e_resolved)
 {
     PairArgs p = p0;
     const GreedyArgs &a = p.g;
@@ -1261,7 +1261,13 @@ void launch_pass1_fused(const PairArgs &p0, const BfArgs &b, int nframes, cudaSt
     k_resolve<<<nframes, RES_THREADS, (size_t)colsA * 9 + (size_t)ent_cap * 4, st>>>(a, colsA, ent_cap, 1);
     p.lane_cols = (((maxN + 31) / 32) + 15) & ~15;
     const size_t sm = (size_t)32 * (p.lane_cols + 1) * sizeof(int);
-    k_scores_m<<<dim3((maxM + M_WARPS * SM_ROWS_PER_WARP - 1) / (M_WARPS * SM_ROWS_PER_WARP), nframes), M_THREADS, sm, st>>>(p);
+    cudaStream_t sq = st;
+    if (st_scores) {   // the scores only leave the device: another branch of the graph, beside pass 2
+        cudaEventRecord(e_resolved, st);
+        cudaStreamWaitEvent(st_scores, e_resolved, 0);
+        sq = st_scores;
+    }
+    k_scores_m<<<dim3((maxM + M_WARPS * SM_ROWS_PER_WARP - 1) / (M_WARPS * SM_ROWS_PER_WARP), nframes), M_THREADS, sm, sq>>>(p);
     *launches += 5;
 }
 

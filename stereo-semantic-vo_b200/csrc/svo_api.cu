@@ -22,7 +22,7 @@ struct FrameBufs {           // per-frame (stereo pair) device arrays
     uint8_t *prev_live;      // [f][row_stride]
     int *map_prev;           // [f][row_stride]
     uint8_t *claimed;        // [f][col_stride]
-    int *claim_row, *claim_time;
+    int *claim_row, *claim_time, *claim_time2;
     int *bf_idx, *bf_dist; uint8_t *bf_keep; int *min_dist;
     int *p1_best_idx, *p1_best, *p1_second; uint8_t *p1_row_claimed, *p1_row_bad;
     int *p2_best_idx, *p2_best, *p2_second; uint8_t *p2_row_claimed;
@@ -68,7 +68,7 @@ struct Lane {
     cudaStream_t st;
     bool own_stream;
     cudaStream_t side;         // second branch of the batch graph: blur beside FAST/selection, stereo + keypoint D2H beside matching
-    cudaEvent_t fk[4];         // fork/join events of the two branches
+    cudaEvent_t fk[6];         // fork/join events of the two branches
     cudaEvent_t done;
     cudaEvent_t ev[N_EVENTS];
     int slot0, frame0, nframes;
@@ -254,7 +254,7 @@ int alloc_frames(svo_ctx *ctx, FrameBufs &f, int nframes, int col_stride, int ro
     const size_t F = nframes, C = (size_t)col_stride * F, R = (size_t)row_stride * F;
     TRY(dalloc(ctx, &f.prev, R * 32)); TRY(dalloc(ctx, &f.map, R * 32));
     TRY(dalloc(ctx, &f.prev_live, R)); TRY(dalloc(ctx, &f.map_prev, R));
-    TRY(dalloc(ctx, &f.claimed, C)); TRY(dalloc(ctx, &f.claim_row, C)); TRY(dalloc(ctx, &f.claim_time, C));
+    TRY(dalloc(ctx, &f.claimed, C)); TRY(dalloc(ctx, &f.claim_row, C)); TRY(dalloc(ctx, &f.claim_time, C)); TRY(dalloc(ctx, &f.claim_time2, C));
     TRY(dalloc(ctx, &f.bf_idx, C)); TRY(dalloc(ctx, &f.bf_dist, C)); TRY(dalloc(ctx, &f.bf_keep, C));
     TRY(dalloc(ctx, &f.min_dist, F));
     TRY(dalloc(ctx, &f.p1_best_idx, R)); TRY(dalloc(ctx, &f.p1_best, R)); TRY(dalloc(ctx, &f.p1_second, R));
@@ -398,7 +398,6 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
         CU(cudaMemcpyAsync(h.u_right, sa.u_right, sizeof(float) * n * KC, cudaMemcpyDeviceToHost, ss));
         CU(cudaMemcpyAsync(h.depth, sa.depth, sizeof(float) * n * KC, cudaMemcpyDeviceToHost, ss));
         CU(cudaMemcpyAsync(h.n_stereo, sa.n_stereo, sizeof(int) * n, cudaMemcpyDeviceToHost, ss));
-        CU(cudaEventRecord(L.fk[3], ss));
     }
     // ---- matching: BF (cur -> prev), greedy pass 1 (prev rows), greedy pass 2 (map rows)
     // left images sit in even slots: consecutive frames' descriptor blocks are 2*kp_cap rows apart
@@ -431,7 +430,9 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
             pa.g = ga;
             pa.dmat = fb.dmat + (size_t)L.frame0 * fb.dmat_frame_stride; pa.dmat_frame_stride = fb.dmat_frame_stride;
             pa.dmat_pitch = fb.dmat_pitch; pa.bf_key = fb.bf_key + (size_t)L.frame0 * K; pa.T = 0; pa.lane_cols = 0;
-            launch_pass1_fused(pa, ba, n, st, &ctx->launches, ev ? ev[12] : nullptr, ev ? ev[13] : nullptr);
+            // match_score (k_scores_m) feeds nothing downstream: on the side branch it runs beside pass 2
+            launch_pass1_fused(pa, ba, n, st, &ctx->launches, ev ? ev[12] : nullptr, ev ? ev[13] : nullptr,
+                               fork ? ss : nullptr, L.fk[4]);
         } else {
             launch_bf(ba, n, st, &ctx->launches);
             launch_greedy(ga, n, true, st, &ctx->launches);
@@ -441,6 +442,7 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
         ga.rows = make_set(nullptr, d_nmap, 1, R, 0);
         ga.rows.tab = reinterpret_cast<const uint8_t *const *>(&L.d_fp->map);
         ga.mode = SVO_GREEDY_PASS2; ga.row_base = 0; ga.row_base_arr = d_nprev;
+        ga.claim_time = fb.claim_time2 + (size_t)L.frame0 * K;   // pass 1's claim times stay readable for k_scores_m
         ga.fp = L.d_fp; ga.use_live = 0; ga.use_map_prev = any_prev ? 1 : 0;
         ga.need_list = fb.need_list + (size_t)L.frame0 * R; ga.reuse_list = fb.reuse_list + (size_t)L.frame0 * R;
         ga.list_cnt = fb.list_cnt + 2 * (size_t)L.frame0;
@@ -469,7 +471,7 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
     }
     if (ev) cudaEventRecord(ev[10], st);
     // ---- D2H: one copy per output array for the whole batch
-    if (fork) CU(cudaStreamWaitEvent(st, L.fk[3], 0));     // join the stereo branch
+    if (fork) { CU(cudaEventRecord(L.fk[3], ss)); CU(cudaStreamWaitEvent(st, L.fk[3], 0)); }   // join the side branch
     CU(cudaMemcpyAsync(h.status, b.status + L.slot0, sizeof(int) * I, cudaMemcpyDeviceToHost, st));
     if (!fork) {
         CU(cudaMemcpyAsync(h.nkp, b.nkp + L.slot0, sizeof(int) * I, cudaMemcpyDeviceToHost, st));
@@ -522,7 +524,7 @@ void svo_destroy(svo_ctx *ctx)
         for (int i = 0; i < N_EVENTS; ++i) if (l.ev[i]) cudaEventDestroy(l.ev[i]);
         if (l.own_stream && l.st) cudaStreamDestroy(l.st);
         if (l.side) cudaStreamDestroy(l.side);
-        for (int i = 0; i < 4; ++i) if (l.fk[i]) cudaEventDestroy(l.fk[i]);
+        for (int i = 0; i < 6; ++i) if (l.fk[i]) cudaEventDestroy(l.fk[i]);
     }
     if (ctx->sync_st) cudaStreamDestroy(ctx->sync_st);
     for (void *p : ctx->dev_allocs) cudaFree(p);
@@ -616,14 +618,14 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
     ctx->lanes.resize(c.lanes);
     for (int i = 0; i < c.lanes; ++i) {
         Lane &l = ctx->lanes[i];
-        l.st = nullptr; l.own_stream = true; l.done = nullptr; l.side = nullptr; for (int k = 0; k < 4; ++k) l.fk[k] = nullptr; l.busy = false; l.nframes = 0;
+        l.st = nullptr; l.own_stream = true; l.done = nullptr; l.side = nullptr; for (int k = 0; k < 6; ++k) l.fk[k] = nullptr; l.busy = false; l.nframes = 0;
         for (int k = 0; k < N_EVENTS; ++k) l.ev[k] = nullptr;
         l.slot0 = 2 * i * c.max_batch; l.frame0 = i * c.max_batch;
         if (i == 0 && c.stream) { l.st = (cudaStream_t)c.stream; l.own_stream = false; }
         else CU(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
         CU(cudaStreamCreateWithFlags(&l.side, cudaStreamNonBlocking));
-        for (int k = 0; k < 4; ++k) CU(cudaEventCreateWithFlags(&l.fk[k], cudaEventDisableTiming));
+        for (int k = 0; k < 6; ++k) CU(cudaEventCreateWithFlags(&l.fk[k], cudaEventDisableTiming));
         for (int k = 0; k < N_EVENTS; ++k) CU(cudaEventCreate(&l.ev[k]));
         const size_t B = c.max_batch, I = 2 * B, K = g.kp_cap, R = c.max_rows;
         HostArena &h = l.h;

@@ -208,7 +208,8 @@ struct PairArgs {            // fused BF + pass-1 front of the batch path (match
     int T, lane_cols;        // filled by the launcher
 };
 void launch_pass1_fused(const PairArgs &p, const BfArgs &b, int nframes, cudaStream_t st, long long *launches,
-                        cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);   // optional events around k_pairs
+                        cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,   // optional events around k_pairs
+                        cudaStream_t st_scores = nullptr, cudaEvent_t e_resolved = nullptr);   // k_scores_m on another stream
 // ---- pose stage (pose.cu) ----
 struct PoseHdr { int off, n; float fx, fy, cx, cy; float Tcw[16]; };   // one problem: points [off, off + n) of the packed arrays
 struct PoseArgs {
