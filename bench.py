@@ -140,6 +140,13 @@ def run_gpu(args, rank, world, local_rank):
     import svo
     dev = local_rank
     torch.cuda.set_device(dev)
+    bus = None
+    try:
+        pr = torch.cuda.get_device_properties(dev)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+    except Exception:
+        pass
+    near = replicas.bind_near_gpu(dev, bus)   # before any pinned allocation: host buffers land on the GPU's NUMA node
     grp = replicas.Group(backend="nccl", device=dev)   # barrier + max-over-ranks only; no data-path collective
     B, P = args.batch, args.pool
     ctx = svo.Context(W_IMG, H_IMG, nfeatures=NFEAT, nlevels=NLEVELS, max_batch=B, lanes=args.lanes,
@@ -353,7 +360,8 @@ def run_gpu(args, rank, world, local_rank):
                        "frames_per_step": B, "lanes": args.lanes, "pool_frames": P,
                        "l2": "inputs larger than L2: %d-frame pool = %.0f MB of images + %.0f MB of descriptors cycled"
                              % (P, 2 * P * img_b / 1e6, P * (K * 33 + MAP_ROWS * 36) / 1e6),
-                       "parallelism": "replicas only: one independent sequence per GPU, no collective"},
+                       "parallelism": "replicas only: one independent sequence per GPU, no collective",
+                       "host_placement": ("process bound to the %d cores NVML reports local to its GPU" % len(near)) if near else "unbound"},
             "e2e": {"value": frames_total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_e2e / args.steps,
                     "h2d_ms_per_step": stage_e2e.get("h2d"), "d2h_ms_per_step": stage_e2e.get("d2h"),

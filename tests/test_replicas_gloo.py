@@ -39,6 +39,15 @@ def test_assign_sequences_partitions_exactly():
         replicas.assign_sequences(8, 2, 2)
 
 
+def test_bind_near_gpu_is_safe_without_a_gpu():
+    """Placement helper: without NVML / a GPU it reports None and leaves the affinity mask alone."""
+    import replicas
+    before = os.sched_getaffinity(0)
+    assert replicas.bind_near_gpu(0) is None
+    assert replicas.bind_near_gpu(0, "00000000:ff:1f.0") is None
+    assert os.sched_getaffinity(0) == before
+
+
 def test_single_process_group_is_a_no_op():
     import replicas
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
