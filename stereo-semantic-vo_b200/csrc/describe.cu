@@ -240,6 +240,8 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
     return a;
 }
 
+__device__ __forceinline__ int rint_small(float v) { return __float_as_int(__fadd_rn(v, 12582912.f)) - 0x4B400000; }
+
 __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(Bufs b, Geom g, int slot0, const int *__restrict__ pattern)
 {
     const int slot = slot0 + blockIdx.y;
@@ -312,10 +314,12 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(Bufs b, Geom g, in
     for (int j = 0; j < 8; ++j) {
         const float x0 = (float)(int8_t)(pat[j] & 0xff), y0 = (float)(int8_t)((pat[j] >> 8) & 0xff);
         const float x1 = (float)(int8_t)((pat[j] >> 16) & 0xff), y1 = (float)(int8_t)((pat[j] >> 24) & 0xff);
-        const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sa)));
-        const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sa), __fmul_rn(y0, ca)));
-        const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sa)));
-        const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sa), __fmul_rn(y1, ca)));
+        // cvRound without the XU pipe: |v| < 19, so v + 1.5 * 2^23 rounds to the nearest integer (ties to even, like
+        // cvRound / F2I.RN) and the integer sits in the low mantissa bits
+        const int ix0 = rint_small(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sa)));
+        const int iy0 = rint_small(__fadd_rn(__fmul_rn(x0, sa), __fmul_rn(y0, ca)));
+        const int ix1 = rint_small(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sa)));
+        const int iy1 = rint_small(__fadd_rn(__fmul_rn(x1, sa), __fmul_rn(y1, ca)));
         const int v0 = bc[iy0 * sp + ix0], v1 = bc[iy1 * sp + ix1];
         byte |= (v0 < v1) << j;
     }

@@ -662,3 +662,38 @@ def test_octree_mode_limits_and_default(svo, ctxK):
     ref, rdesc, _ = O.orb(img, 2000)
     kp, desc = ctxK.extract(img)
     assert_kp_equal(kp, ref); assert (desc == rdesc).all()
+
+
+def test_batch_pass2_scans_only_the_columns_pass1_left_free(ctxK):
+    """k_free_cols / the indexed tile of k_shortlist at their extremes, in one batch: every column claimed by pass 1
+    (the previous frame IS the current one: nothing is left for pass 2), no column claimed (unrelated previous
+    frame), and a frame without a previous frame; the oracle scans all columns and skips the claimed ones."""
+    seq = synth.Sequence(seed=4)
+    L, R = seq.frame(0)
+    kl, dl, _ = O.orb(L, 2000)
+    rng = np.random.default_rng(5)
+    mp = synth.local_map([dl], rows=3000, seed=1)
+    unrelated = rng.integers(0, 256, (1500, 32), dtype=np.uint8)
+    near = dl[rng.permutation(len(dl))[:1200]].copy()
+    near[:, 0] ^= 1                                            # one bit away: pass 1 claims 1200 distinct columns
+    jobs = [dict(left=L, right=R, bf=100.0, baseline=0.5, prev_desc=dl.copy(), map_desc=mp),
+            dict(left=L, right=R, bf=100.0, baseline=0.5, prev_desc=unrelated, map_desc=mp),
+            dict(left=L, right=R, bf=100.0, baseline=0.5, prev_desc=near, map_desc=mp),
+            dict(left=L, right=R, bf=100.0, baseline=0.5, map_desc=mp)]
+    ctxK.batch_submit(0, jobs)
+    ctxK.batch_wait(0)
+    claimed_by_p1 = []
+    for i, job in enumerate(jobs):
+        r = ctxK.batch_result(0, i)
+        assert r["status"] == 0 and (r["desc_left"] == dl).all()
+        if "prev_desc" in job:
+            p1 = O.match_greedy(job["prev_desc"], dl, 0)
+            assert (r["p1_row_claimed"] == p1["row_claimed"]).all()
+            claimed, claim_row, base = p1["claimed"], p1["claim_row"], len(job["prev_desc"])
+        else:
+            claimed, claim_row, base = None, None, 0
+        claimed_by_p1.append(0 if claimed is None else int(claimed.sum()))
+        p2 = O.match_greedy(mp, dl, 1, claimed=claimed, claim_row=claim_row, row_base=base)
+        assert (r["p2_row_claimed"] == p2["row_claimed"]).all(), i
+        assert (r["claim_row"] == p2["claim_row"]).all(), i
+    assert claimed_by_p1[0] == len(dl) and claimed_by_p1[1] == 0 and claimed_by_p1[2] == 1200 and claimed_by_p1[3] == 0
