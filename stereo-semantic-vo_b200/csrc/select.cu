@@ -19,6 +19,7 @@
 // tools/model_retain_best.py is the executable design model of this file; the oracle
 // (oracle/retain_best.cpp) calls the real std:: algorithms.
 #include "svo_internal.cuh"
+#include <stdlib.h>
 
 #define SEL_THREADS 1024
 #define SEL_WARPS (SEL_THREADS / 32)
@@ -28,22 +29,34 @@ struct SelSmem {
     int m;
 };
 
-struct Greater {
-    __device__ __forceinline__ bool operator()(float a, float b) const { return a > b; }
+// Element stores.  The replay only needs "key of element i" and moves of whole elements, so the two culls use
+// different layouts: the first cull's key IS the FAST score packed in the candidate's top byte (no key array at
+// all: 8 bytes of shared memory per candidate with 16-bit position scratch), the second cull carries separate
+// float Harris responses.
+struct Item { float k; uint32_t v; };
+struct KeyVal {
+    float *key; uint32_t *val;
+    __device__ __forceinline__ float k(int i) const { return key[i]; }
+    __device__ __forceinline__ Item get(int i) const { Item t; t.k = key[i]; t.v = val[i]; return t; }
+    __device__ __forceinline__ void put(int i, Item t) const { key[i] = t.k; val[i] = t.v; }
+    __device__ __forceinline__ void copy(int dst, int src) const { key[dst] = key[src]; val[dst] = val[src]; }
+    __device__ __forceinline__ void swap(int i, int j) const { const Item t = get(i); copy(i, j); put(j, t); }
 };
-
-__device__ __forceinline__ void sel_swap(float *key, uint32_t *val, int i, int j)
-{
-    const float k = key[i]; key[i] = key[j]; key[j] = k;
-    const uint32_t v = val[i]; val[i] = val[j]; val[j] = v;
-}
+struct ScoreInVal {
+    uint32_t *val;
+    __device__ __forceinline__ float k(int i) const { return (float)(val[i] >> 24); }
+    __device__ __forceinline__ Item get(int i) const { Item t; t.v = val[i]; t.k = (float)(t.v >> 24); return t; }
+    __device__ __forceinline__ void put(int i, Item t) const { val[i] = t.v; }
+    __device__ __forceinline__ void copy(int dst, int src) const { val[dst] = val[src]; }
+    __device__ __forceinline__ void swap(int i, int j) const { const uint32_t t = val[i]; val[i] = val[j]; val[j] = t; }
+};
 
 // Two-pointer swap round over [lo, hi).  MODE 0: Hoare step against `pivot` (left scan stops
 // on !(x > pivot), right scan on !(pivot > x)).  MODE 1: std::partition with x >= pivot (left
 // stops on false, right on true).  Returns through nl/nr the stopper totals and `cut`.
-template <int MODE>
-__device__ void two_pointer_round(float *key, uint32_t *val, int lo, int hi, float pivot,
-                                  uint32_t *lpos, uint32_t *rasc, SelSmem &sh, int &nl, int &nr, int &cut)
+// P: position scratch type (uint16_t when the arrays live in shared memory, n < 65536).
+template <int MODE, class A, class P>
+__device__ void two_pointer_round(const A &e, int lo, int hi, float pivot, P *lpos, P *rasc, SelSmem &sh, int &nl, int &nr, int &cut)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int len = hi - lo;
@@ -51,7 +64,7 @@ __device__ void two_pointer_round(float *key, uint32_t *val, int lo, int hi, flo
     const int beg = lo + warp * seg, end = min(beg + seg, hi);
     auto flags = [&](int i, bool &fl, bool &fr) {
         if (i < end) {
-            const float x = key[i];
+            const float x = e.k(i);
             if (MODE == 0) { fl = !(x > pivot); fr = !(pivot > x); }
             else { fr = x >= pivot; fl = !fr; }
         } else { fl = false; fr = false; }
@@ -83,8 +96,8 @@ __device__ void two_pointer_round(float *key, uint32_t *val, int lo, int hi, flo
         flags(base + lane, fl, fr);
         const uint32_t ml = __ballot_sync(0xffffffffu, fl), mr = __ballot_sync(0xffffffffu, fr);
         const uint32_t lt = (1u << lane) - 1u;
-        if (fl) lpos[ol + __popc(ml & lt)] = base + lane;
-        if (fr) rasc[orr + __popc(mr & lt)] = base + lane;
+        if (fl) lpos[ol + __popc(ml & lt)] = (P)(base + lane);
+        if (fr) rasc[orr + __popc(mr & lt)] = (P)(base + lane);
         ol += __popc(ml); orr += __popc(mr);
     }
     __syncthreads();
@@ -99,69 +112,72 @@ __device__ void two_pointer_round(float *key, uint32_t *val, int lo, int hi, flo
     const int c1 = m < nl ? (int)lpos[m] : 0x7fffffff;
     const int c2 = m >= 1 ? (int)rasc[nr - m] : 0x7fffffff;
     cut = min(c1, c2);
-    for (int k = tid; k < m; k += SEL_THREADS) sel_swap(key, val, lpos[k], rasc[nr - 1 - k]);
+    for (int k = tid; k < m; k += SEL_THREADS) e.swap((int)lpos[k], (int)rasc[nr - 1 - k]);
     __syncthreads();
 }
 
 // libstdc++ __adjust_heap + __push_heap with comp = greater (min-heap on response)
-__device__ void adjust_heap(float *key, uint32_t *val, int first, int hole, int len, float vk, uint32_t vv)
+template <class A>
+__device__ void adjust_heap(const A &e, int first, int hole, int len, Item v)
 {
     const int top = hole;
     int child = hole;
     while (child < (len - 1) / 2) {
         child = 2 * (child + 1);
-        if (key[first + child] > key[first + child - 1]) --child;
-        key[first + hole] = key[first + child]; val[first + hole] = val[first + child];
+        if (e.k(first + child) > e.k(first + child - 1)) --child;
+        e.copy(first + hole, first + child);
         hole = child;
     }
     if ((len & 1) == 0 && child == (len - 2) / 2) {
         child = 2 * (child + 1);
-        key[first + hole] = key[first + child - 1]; val[first + hole] = val[first + child - 1];
+        e.copy(first + hole, first + child - 1);
         hole = child - 1;
     }
     int parent = (hole - 1) / 2;
-    while (hole > top && key[first + parent] > vk) {
-        key[first + hole] = key[first + parent]; val[first + hole] = val[first + parent];
+    while (hole > top && e.k(first + parent) > v.k) {
+        e.copy(first + hole, first + parent);
         hole = parent;
         parent = (hole - 1) / 2;
     }
-    key[first + hole] = vk; val[first + hole] = vv;
+    e.put(first + hole, v);
 }
 
-__device__ void heap_select(float *key, uint32_t *val, int first, int middle, int last)
+template <class A>
+__device__ void heap_select(const A &e, int first, int middle, int last)
 {
     const int len = middle - first;
     if (len >= 2) {
         int parent = (len - 2) / 2;
         while (true) {
-            adjust_heap(key, val, first, parent, len, key[first + parent], val[first + parent]);
+            adjust_heap(e, first, parent, len, e.get(first + parent));
             if (parent == 0) break;
             --parent;
         }
     }
     for (int i = middle; i < last; ++i)
-        if (key[i] > key[first]) {
-            const float vk = key[i]; const uint32_t vv = val[i];
-            key[i] = key[first]; val[i] = val[first];
-            adjust_heap(key, val, first, 0, len, vk, vv);
+        if (e.k(i) > e.k(first)) {
+            const Item v = e.get(i);
+            e.copy(i, first);
+            adjust_heap(e, first, 0, len, v);
         }
 }
 
-__device__ void move_median_to_first(float *key, uint32_t *val, int r, int a, int b, int c)
+template <class A>
+__device__ void move_median_to_first(const A &e, int r, int a, int b, int c)
 {
-    const float ka = key[a], kb = key[b], kc = key[c];
+    const float ka = e.k(a), kb = e.k(b), kc = e.k(c);
     if (ka > kb) {
-        if (kb > kc) sel_swap(key, val, r, b);
-        else if (ka > kc) sel_swap(key, val, r, c);
-        else sel_swap(key, val, r, a);
-    } else if (ka > kc) sel_swap(key, val, r, a);
-    else if (kb > kc) sel_swap(key, val, r, c);
-    else sel_swap(key, val, r, b);
+        if (kb > kc) e.swap(r, b);
+        else if (ka > kc) e.swap(r, c);
+        else e.swap(r, a);
+    } else if (ka > kc) e.swap(r, a);
+    else if (kb > kc) e.swap(r, c);
+    else e.swap(r, b);
 }
 
 // Whole retainBest; every thread of the block must call it; returns the kept count.
-__device__ int block_retain_best(float *key, uint32_t *val, int n, int n_points, int depth_limit,
-                                 uint32_t *lpos, uint32_t *rasc, SelSmem &sh, int *status)
+template <class A, class P>
+__device__ int block_retain_best(const A &e, int n, int n_points, int depth_limit, P *lpos, P *rasc, SelSmem &sh, int *status)
 {
     if (n_points < 0 || n <= n_points) return n;
     if (n_points == 0) return 0;
@@ -172,8 +188,8 @@ __device__ int block_retain_best(float *key, uint32_t *val, int n, int n_points,
     while (last - first > 3) {
         if (depth_limit == 0) {
             if (threadIdx.x == 0) {
-                heap_select(key, val, first, nth + 1, last);
-                sel_swap(key, val, first, nth);
+                heap_select(e, first, nth + 1, last);
+                e.swap(first, nth);
                 if (status) atomicOr(status, SVO_STATUS_DEPTH);
             }
             __syncthreads();
@@ -181,37 +197,38 @@ __device__ int block_retain_best(float *key, uint32_t *val, int n, int n_points,
             break;
         }
         --depth_limit;
-        if (threadIdx.x == 0) move_median_to_first(key, val, first, first + 1, first + (last - first) / 2, last - 1);
+        if (threadIdx.x == 0) move_median_to_first(e, first, first + 1, first + (last - first) / 2, last - 1);
         __syncthreads();
-        const float pivot = key[first];
+        const float pivot = e.k(first);
         int nl, nr, cut;
-        two_pointer_round<0>(key, val, first + 1, last, pivot, lpos, rasc, sh, nl, nr, cut);
+        two_pointer_round<0>(e, first + 1, last, pivot, lpos, rasc, sh, nl, nr, cut);
         if (cut <= nth) first = cut; else last = cut;
     }
     if (!done) {
         if (threadIdx.x == 0) {  // __insertion_sort on <= 3 elements
             for (int i = first + 1; i < last; ++i) {
-                const float k = key[i]; const uint32_t v = val[i];
+                const Item v = e.get(i);
                 int j = i;
-                if (k > key[first]) {
-                    while (j > first) { key[j] = key[j - 1]; val[j] = val[j - 1]; --j; }
+                if (v.k > e.k(first)) {
+                    while (j > first) { e.copy(j, j - 1); --j; }
                 } else {
-                    while (k > key[j - 1]) { key[j] = key[j - 1]; val[j] = val[j - 1]; --j; }
+                    while (v.k > e.k(j - 1)) { e.copy(j, j - 1); --j; }
                 }
-                key[j] = k; val[j] = v;
+                e.put(j, v);
             }
         }
         __syncthreads();
     }
-    const float amb = key[n_points - 1];
+    const float amb = e.k(n_points - 1);
     int nl, nr, cut;
-    two_pointer_round<1>(key, val, n_points, n, amb, lpos, rasc, sh, nl, nr, cut);
+    two_pointer_round<1>(e, n_points, n, amb, lpos, rasc, sh, nl, nr, cut);
     return n_points + nr;
 }
 
 // ---- first cull: gather the level's band lists (raster order) and keep 2*quota by FAST score
-extern __shared__ __align__(16) uint32_t sel_dyn[];   // [key | val | lpos | rasc], smem_cap entries each
+extern __shared__ __align__(16) uint32_t sel_dyn[];
 
+// shared layout of the first cull: [val: cap u32][lpos: cap u16][rasc: cap u16] = 8 bytes per candidate
 __global__ void __launch_bounds__(SEL_THREADS) k_select1(Bufs b, Geom g, int slot0, int smem_cap)
 {
     __shared__ SelSmem sh;
@@ -244,35 +261,35 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select1(Bufs b, Geom g, int slo
     }
     __syncthreads();
     const int n = band_base[L.nbands];
-    float *gkey = b.ckey + (size_t)slot * g.cand_total + L.cand_off;
     uint32_t *gval = b.cval + (size_t)slot * g.cand_total + L.cand_off;
     // the replay is a chain of short dependent phases: with the arrays in shared memory a phase costs a
     // shared-memory round trip instead of an L2 one (falls back to global memory when n exceeds the carve-out)
     const bool in_smem = n <= smem_cap;
-    float *key = in_smem ? reinterpret_cast<float *>(sel_dyn) : gkey;
-    uint32_t *val = in_smem ? sel_dyn + smem_cap : gval;
-    uint32_t *lpos = in_smem ? sel_dyn + 2 * smem_cap : b.lpos + (size_t)slot * g.cand_total + L.cand_off;
-    uint32_t *rasc = in_smem ? sel_dyn + 3 * smem_cap : b.rpos + (size_t)slot * g.cand_total + L.cand_off;
+    uint32_t *val = in_smem ? sel_dyn : gval;
     const uint32_t *bands = b.bands + (size_t)slot * g.band_total + L.band_off;
     for (int bi = warp; bi < L.nbands; bi += SEL_WARPS) {
         const int c = bc[bi], o = band_base[bi];
         const uint32_t *src = bands + (size_t)bi * L.band_cap;
-        for (int i = lane; i < c; i += 32) {
-            const uint32_t e = src[i];
-            val[o + i] = e;
-            key[o + i] = (float)unpack_s(e);
-        }
+        for (int i = lane; i < c; i += 32) val[o + i] = src[i];
     }
     __syncthreads();
-    const int kept = block_retain_best(key, val, n, 2 * L.quota, -1, lpos, rasc, sh, b.status + slot);
+    const ScoreInVal e{val};
+    int kept;
+    if (in_smem) {
+        uint16_t *lpos = reinterpret_cast<uint16_t *>(sel_dyn + smem_cap), *rasc = lpos + smem_cap;
+        kept = block_retain_best(e, n, 2 * L.quota, -1, lpos, rasc, sh, b.status + slot);
+    } else {
+        kept = block_retain_best(e, n, 2 * L.quota, -1, b.lpos + (size_t)slot * g.cand_total + L.cand_off,
+                                 b.rpos + (size_t)slot * g.cand_total + L.cand_off, sh, b.status + slot);
+    }
     if (tid == 0) { cnt1[l] = n; kept1[l] = kept; }
     if (in_smem) {
         __syncthreads();
-        for (int i = tid; i < kept; i += SEL_THREADS) { gkey[i] = key[i]; gval[i] = val[i]; }
+        for (int i = tid; i < kept; i += SEL_THREADS) gval[i] = val[i];
     }
 }
 
-// ---- second cull: keep quota by Harris response
+// ---- second cull: keep quota by Harris response.  shared: [key: cap f32][val: cap u32][lpos: cap u16][rasc: cap u16]
 __global__ void __launch_bounds__(SEL_THREADS) k_select2(Bufs b, Geom g, int slot0, int smem_cap)
 {
     __shared__ SelSmem sh;
@@ -282,20 +299,21 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select2(Bufs b, Geom g, int slo
     float *gkey = b.key2 + (size_t)slot * g.total2 + L.off2;
     uint32_t *gval = b.val2 + (size_t)slot * g.total2 + L.off2;
     const bool in_smem = n <= smem_cap;
-    float *key = in_smem ? reinterpret_cast<float *>(sel_dyn) : gkey;
-    uint32_t *val = in_smem ? sel_dyn + smem_cap : gval;
-    uint32_t *lpos = in_smem ? sel_dyn + 2 * smem_cap : b.lpos + (size_t)slot * g.cand_total + L.cand_off;
-    uint32_t *rasc = in_smem ? sel_dyn + 3 * smem_cap : b.rpos + (size_t)slot * g.cand_total + L.cand_off;
+    int kept;
     if (in_smem) {
-        for (int i = threadIdx.x; i < n; i += SEL_THREADS) { key[i] = gkey[i]; val[i] = gval[i]; }
+        const KeyVal e{reinterpret_cast<float *>(sel_dyn), sel_dyn + smem_cap};
+        uint16_t *lpos = reinterpret_cast<uint16_t *>(sel_dyn + 2 * smem_cap), *rasc = lpos + smem_cap;
+        for (int i = threadIdx.x; i < n; i += SEL_THREADS) { e.key[i] = gkey[i]; e.val[i] = gval[i]; }
         __syncthreads();
+        kept = block_retain_best(e, n, L.quota, -1, lpos, rasc, sh, b.status + slot);
+        __syncthreads();
+        for (int i = threadIdx.x; i < kept; i += SEL_THREADS) { gkey[i] = e.key[i]; gval[i] = e.val[i]; }
+    } else {
+        const KeyVal e{gkey, gval};
+        kept = block_retain_best(e, n, L.quota, -1, b.lpos + (size_t)slot * g.cand_total + L.cand_off,
+                                 b.rpos + (size_t)slot * g.cand_total + L.cand_off, sh, b.status + slot);
     }
-    const int kept = block_retain_best(key, val, n, L.quota, -1, lpos, rasc, sh, b.status + slot);
     if (threadIdx.x == 0) b.kept2[(size_t)slot * SVO_MAX_LEVELS + l] = kept;
-    if (in_smem) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < kept; i += SEL_THREADS) { gkey[i] = key[i]; gval[i] = val[i]; }
-    }
 }
 
 __global__ void __launch_bounds__(SEL_THREADS) k_retain_best_raw(float *key, uint32_t *val, int n, int n_points,
@@ -303,11 +321,12 @@ __global__ void __launch_bounds__(SEL_THREADS) k_retain_best_raw(float *key, uin
                                                                  int *kept_out, int *status)
 {
     __shared__ SelSmem sh;
-    const int kept = block_retain_best(key, val, n, n_points, depth_limit, lpos, rasc, sh, status);
+    const KeyVal e{key, val};
+    const int kept = block_retain_best(e, n, n_points, depth_limit, lpos, rasc, sh, status);
     if (threadIdx.x == 0) *kept_out = kept;
 }
 
-#define SEL_SMEM_MAX 12000   // entries: 4 arrays x 4 B x 12000 = 187.5 KB
+#define SEL_SMEM_MAX 12000   // candidates held in shared memory: 8 B each in the first cull (94 KB), 12 B in the second
 
 static int sel_cap1(const Geom &g)
 {
@@ -324,15 +343,15 @@ static int sel_cap2(const Geom &g)
 
 int setup_select_attributes()
 {
-    if (cudaFuncSetAttribute(k_select1, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * SEL_SMEM_MAX) != cudaSuccess) return 1;
-    return (int)cudaFuncSetAttribute(k_select2, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * SEL_SMEM_MAX);
+    if (cudaFuncSetAttribute(k_select1, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * SEL_SMEM_MAX) != cudaSuccess) return 1;
+    return (int)cudaFuncSetAttribute(k_select2, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * SEL_SMEM_MAX);
 }
 
 void launch_select1(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches)
 {
     dim3 grid(g.nlevels, nimg);
     const int cap = sel_cap1(g);
-    k_select1<<<grid, SEL_THREADS, (size_t)16 * cap, st>>>(b, g, slot0, cap);
+    k_select1<<<grid, SEL_THREADS, (size_t)8 * cap, st>>>(b, g, slot0, cap);
     ++*launches;
 }
 
@@ -340,7 +359,7 @@ void launch_select2(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStrea
 {
     dim3 grid(g.nlevels, nimg);
     const int cap = sel_cap2(g);
-    k_select2<<<grid, SEL_THREADS, (size_t)16 * cap, st>>>(b, g, slot0, cap);
+    k_select2<<<grid, SEL_THREADS, (size_t)12 * cap, st>>>(b, g, slot0, cap);
     ++*launches;
 }
 
