@@ -57,3 +57,32 @@ def test_product_never_touches_the_oracle():
                     if needle == "svo_o_" and f == "stereo.cu":
                         continue  # a comment cites the oracle function that defines the stage
                     assert needle not in src, (f, needle)
+
+
+def test_binding_structs_match_the_header_layout(tmp_path):
+    """The ctypes mirrors in svo.py must have the size and field offsets a C compiler gives the structs of
+    include/svo_b200.h (a field added on one side only would silently shift every later argument)."""
+    import subprocess
+    import svo
+    pairs = {"svo_config": svo.Config, "svo_veto": svo.Veto, "svo_frame_in": svo.FrameIn, "svo_frame_out": svo.FrameOut,
+             "svo_pose_problem": svo.PoseProblem, "svo_pnp_result": svo.PnpResult}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "svo_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append('printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines.append('return 0; }')
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = {}
+    for ln in subprocess.check_output([str(exe)], text=True).splitlines():
+        a, b, c = ln.split()
+        got[(a, b)] = int(c)
+    for cname, cls in pairs.items():
+        assert got[(cname, "size")] == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+    kp = svo.KP_DTYPE
+    assert kp.itemsize == 24 and [kp.fields[n][1] for n in ("x", "y", "size", "angle", "response", "octave")] == [0, 4, 8, 12, 16, 20]
