@@ -170,11 +170,10 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(Bufs b, Geom g, int slot0
             const int qi = (ch << 5) + lane;
             const int x = xq0 + (qi << 2);
             uint32_t pass = 0;
-            if (qi < nq) {
-                pass = fast_quick4(pix + (r + 3) * sp + x, sp, t4);
-                if (x < L.x0 - 1) pass &= 0xffffffffu << (8 * (L.x0 - 1 - x));        // first quad of the row
-                if (x + 3 > L.x1) pass &= 0xffffffffu >> (8 * (x + 3 - L.x1));        // last quad of the row
-            }
+            // The first and last quad of a row reach up to 3 pixels outside [x0 - 1, x1]; those pixels may become
+            // candidates and get a score, which nothing reads: stage C only suppresses and emits x0 <= x < x1, whose
+            // neighbours lie inside [x0 - 1, x1] (masking them here cost 12 instructions on every quad).
+            if (qi < nq) pass = fast_quick4(pix + (r + 3) * sp + x, sp, t4);
             // compaction: 4-bit hit mask per lane, warp prefix sum of the hit counts from three ballots
             // (a count is at most 4), then up to four stores
             const uint32_t nib = (((pass >> 7) & 0x01010101u) * 0x10204080u) >> 28;
