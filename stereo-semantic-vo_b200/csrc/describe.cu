@@ -308,7 +308,26 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(Bufs b, Geom g, in
         ca = (float)dc; sa = (float)ds;
     }
     ca = __shfl_sync(0xffffffffu, ca, 0); sa = __shfl_sync(0xffffffffu, sa, 0);
-    const uint8_t *bc = blr + (size_t)cy * sp + cx;
+    // The 512 samples of a keypoint fall in the 37 x 37 window around (cx, cy) (the pattern's radius is 18.4, so a
+    // rotated and rounded coordinate stays within +-18).  The window is staged in shared memory with word loads laid
+    // out along the rows (12 warp loads touching ~75 sectors) and the scattered samples are byte reads from shared
+    // memory, instead of 16 global byte gathers per lane that each touch up to 32 sectors (ncu: the gathers kept
+    // L1TEX 65 % busy and the warps on the long scoreboard).
+    __shared__ uint32_t patch[DESC_WARPS][37 * 10];
+    const int a0 = (cx - 18) & ~3;                      // first staged column, word aligned (the level base is 256-B aligned)
+    {
+        const uint8_t *prow = blr + (size_t)(cy - 18) * sp + a0;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const int t = lane + 32 * k;
+            if (t < 370) {
+                const int row = (t * 205) >> 11, w = t - row * 10;       // t / 10 for t < 384
+                patch[warp][t] = *reinterpret_cast<const uint32_t *>(prow + (size_t)row * sp + 4 * w);
+            }
+        }
+    }
+    __syncwarp();
+    const uint8_t *bc = reinterpret_cast<const uint8_t *>(patch[warp]) + 18 * 40 + (cx - a0);
     int byte = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -320,7 +339,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(Bufs b, Geom g, in
         const int iy0 = rint_small(__fadd_rn(__fmul_rn(x0, sa), __fmul_rn(y0, ca)));
         const int ix1 = rint_small(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sa)));
         const int iy1 = rint_small(__fadd_rn(__fmul_rn(x1, sa), __fmul_rn(y1, ca)));
-        const int v0 = bc[iy0 * sp + ix0], v1 = bc[iy1 * sp + ix1];
+        const int v0 = bc[iy0 * 40 + ix0], v1 = bc[iy1 * 40 + ix1];
         byte |= (v0 < v1) << j;
     }
     b.desc[((size_t)slot * g.kp_cap + oi) * 32 + lane] = (uint8_t)byte;
