@@ -25,6 +25,8 @@
  *     src/Tracking.cc:226).  north_star asks for ORB-SLAM2-lineage
  *     ComputeStereoMatches; this file DEFINES it.
  *     PARITY UNPINNED for that stage: no reference code or vectors exist.
+ *   - the pose stage (svo_pose_oracle.c) and the opt-in quadtree keypoint distribution
+ *     (svo_octree_oracle.c) live in their own files; each header states what pins it.
  *
  * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off; no -march=native so
  * every float op is separately rounded, which is what reproduces cv2's bits).
