@@ -88,3 +88,28 @@ def test_disp2depth():
     z = O.disp2depth(d, 379.8145)
     assert z[0] == -1.0 and z[1] == np.float32(379.8145) / np.float32(-1.0)
     assert z[2] == np.float32(379.8145) / np.float32(2.0)
+
+
+def test_pass2_over_the_free_columns_only_is_the_same_scan():
+    """The invariant behind k_free_cols: a column claimed before pass 2 starts is skipped by
+    every pass-2 row (src/pnpmatch.cc:176), so scanning only the free columns — in ascending order, carrying the
+    original index — gives the same claims, the same claim rows and the same (best, second) as scanning all of them."""
+    rng = np.random.default_rng(11)
+    for trial in range(6):
+        M, N = int(rng.integers(50, 400)), int(rng.integers(60, 500))
+        rows, cur = make_case(rng, M, N)
+        claimed = (rng.random(N) < (0.0, 0.35, 0.8, 1.0, 0.5, 0.1)[trial]).astype(np.uint8)
+        claim_row = np.where(claimed, rng.integers(0, 1000, N), -1).astype(np.int32)
+        full = O.match_greedy(rows, cur, 1, claimed=claimed.copy(), claim_row=claim_row.copy(), row_base=1000)
+        free = np.nonzero(claimed == 0)[0]
+        sub = O.match_greedy(rows, cur[free], 1, row_base=1000)
+        assert (full["row_claimed"] == sub["row_claimed"]).all()
+        # claims of the compacted scan, mapped back to original column indices
+        back = claim_row.copy()
+        took = sub["claim_row"] >= 0
+        back[free[took]] = sub["claim_row"][took]
+        assert (full["claim_row"] == back).all()
+        idx = sub["best_idx"].copy()
+        ok = idx >= 0
+        idx[ok] = free[idx[ok]]
+        assert (full["best_idx"] == idx).all() and (full["best"] == sub["best"]).all() and (full["second"] == sub["second"]).all()
