@@ -140,7 +140,9 @@ def match_bf(q, t):
 
 
 def match_greedy(rows, cur, mode, claimed=None, row_live=None, row_base=0, claim_row=None,
-                 win_uvr=None, cur_xy=None):
+                 win_uvr=None, cur_xy=None, veto=None):
+    """veto (pass 1): dict(boxes (n,4) int32 left/right/top/bottom, F (3,3) f64, row_xy (M,2), cur_xy (N,2)) —
+    the YOLO-box + epipolar "dynamic" test of src/pnpmatch.cc:103-144; row_bad marks map points turned bad."""
     rows = np.ascontiguousarray(rows, np.uint8).reshape(-1, 32); cur = np.ascontiguousarray(cur, np.uint8).reshape(-1, 32)
     M, N = len(rows), len(cur)
     claimed = np.zeros(N, np.uint8) if claimed is None else np.ascontiguousarray(claimed, np.uint8).copy()
@@ -150,9 +152,18 @@ def match_greedy(rows, cur, mode, claimed=None, row_live=None, row_base=0, claim
     if win_uvr is not None:
         win_uvr = np.ascontiguousarray(win_uvr, np.float32); cur_xy = np.ascontiguousarray(cur_xy, np.float32)
     bi = np.empty(M, np.int32); b = np.empty(M, np.int32); s = np.empty(M, np.int32); rc = np.empty(M, np.uint8)
-    lib().svo_o_match_greedy(_p(rows), M, _p(cur), N, mode, _p(row_live), _p(claimed), _p(claim_row), row_base,
-                             _p(bi), _p(b), _p(s), _p(rc), _p(win_uvr), _p(cur_xy))
-    return dict(best_idx=bi, best=b, second=s, row_claimed=rc, claimed=claimed, claim_row=claim_row)
+    bad = np.zeros(M, np.uint8)
+    boxes = F = rxy = vxy = None
+    if veto is not None:
+        boxes = np.ascontiguousarray(veto["boxes"], np.int32).reshape(-1, 4)
+        F = np.ascontiguousarray(veto["F"], np.float64).reshape(9)
+        rxy = np.ascontiguousarray(veto["row_xy"], np.float32).reshape(-1, 2)
+        vxy = np.ascontiguousarray(veto["cur_xy"], np.float32).reshape(-1, 2)
+        assert len(rxy) == M and len(vxy) == N
+    lib().svo_o_match_greedy_veto(_p(rows), M, _p(cur), N, mode, _p(row_live), _p(claimed), _p(claim_row), row_base,
+                                  _p(bi), _p(b), _p(s), _p(rc), _p(win_uvr), _p(cur_xy),
+                                  _p(boxes), 0 if boxes is None else len(boxes), _p(F), _p(rxy), _p(vxy), _p(bad))
+    return dict(best_idx=bi, best=b, second=s, row_claimed=rc, claimed=claimed, claim_row=claim_row, row_bad=bad)
 
 
 def disp2depth(disp, bf):

@@ -59,6 +59,13 @@ void svo_o_match_greedy(const uint8_t *rows, int M, const uint8_t *cur, int N, i
                         const uint8_t *row_live, uint8_t *claimed, int32_t *claim_row, int row_base,
                         int32_t *best_idx, int32_t *best, int32_t *second, uint8_t *row_claimed,
                         const float *win_uvr, const float *cur_xy);
+int svo_o_veto_dynamic(const int32_t *boxes, int n_boxes, const double *F, float lx, float ly, float cx, float cy);
+void svo_o_match_greedy_veto(const uint8_t *rows, int M, const uint8_t *cur, int N, int mode,
+                             const uint8_t *row_live, uint8_t *claimed, int32_t *claim_row, int row_base,
+                             int32_t *best_idx, int32_t *best, int32_t *second, uint8_t *row_claimed,
+                             const float *win_uvr, const float *cur_xy,
+                             const int32_t *boxes, int n_boxes, const double *F, const float *row_xy,
+                             const float *vcur_xy, uint8_t *row_bad);
 void svo_o_disp2depth(const float *disp, float *depth, size_t n, float bf);
 int svo_o_stereo_sparse(const svo_o_keypoint *kl, const uint8_t *dl, int nl,
                         const svo_o_keypoint *kr, const uint8_t *dr, int nr,

@@ -156,3 +156,17 @@ def colourise(gray, seed):
     for c in range(3):
         out[..., c] = np.clip(g * gains[c] + rng.integers(-12, 13, gray.shape) + (8, 0, -8)[c], 0, 255).astype(np.uint8)
     return out
+
+
+def dense_disparity(shape, seed, holes=0.15, zeros=0.05):
+    """A dense CV_32F disparity image standing in for frame::MB's output (src/frame.cc:82-91): piece-wise constant
+    values in [2, 48], with a fraction of -1 pixels ("no disparity", which makes computekeypoint_r's rx stick,
+    src/frame.cc:133) and of exact zeros (which disp2Depth skips, src/frame.cc:158)."""
+    h, w = shape
+    r = np.random.default_rng(seed + 4241)
+    g = r.uniform(2, 48, ((h + 46) // 47, (w + 72) // 73)).astype(np.float32)
+    d = np.kron(g, np.ones((47, 73), np.float32))[:h, :w].copy()
+    m = r.random((h, w))
+    d[m < holes] = -1
+    d[(m >= holes) & (m < holes + zeros)] = 0
+    return d
