@@ -90,6 +90,48 @@ def build_map(descs, live_prev, rng):
     return np.ascontiguousarray(rows[order]), np.ascontiguousarray(prow[order])
 
 
+def workload_string(distribution="retainbest"):
+    head = ("configs[1]" if (W_IMG, H_IMG, NFEAT, MAP_ROWS, distribution) == (1241, 376, 2000, 5000, "retainbest")
+            else "non-headline configuration" + (" (opt-in octree distribution)" if distribution == "octree" else ""))
+    return ("%s: synthetic %s %dx%d stereo sequence, KITTI04-12 intrinsics, %d ORB features / 8 levels / 1.2, full front-end: "
+            "extract L+R, sparse stereo + SAD, BF match vs previous frame, greedy pass 1 + pass 2 vs %d-row local map"
+            % (head, "KITTI-shape" if (W_IMG, H_IMG) == (1241, 376) else "high-res", W_IMG, H_IMG, NFEAT, MAP_ROWS))
+
+
+def verify_frame(r, job):
+    """Checker for the bench's own configuration (not timed): one frame's results against the CPU oracle —
+    keypoints and descriptors bit for bit, stereo validity / match-level agreement within 1e-3, BF, pass 1, pass 2."""
+    from oracle import oracle as O
+    kl, dl, pl = O.orb(job["left"], NFEAT, with_pyramid=True)
+    kr, dr, pr = O.orb(job["right"], NFEAT, with_pyramid=True)
+    ur, dep, mr, sad = O.stereo_sparse(kl, dl, pl, kr, dr, pr, BF, BASELINE)
+    O.pyramid_free(pl); O.pyramid_free(pr)
+    assert r["status"] == 0 and r["n_left"] == len(kl) and r["n_right"] == len(kr), "keypoint counts"
+    for f in ("x", "y", "size", "angle", "response"):
+        assert (r["kp_left"][f].view(np.uint32) == kl[f].view(np.uint32)).all(), "left keypoints: " + f
+        assert (r["kp_right"][f].view(np.uint32) == kr[f].view(np.uint32)).all(), "right keypoints: " + f
+    assert (r["kp_left"]["octave"] == kl["octave"]).all() and (r["desc_left"] == dl).all() and (r["desc_right"] == dr).all(), "descriptors"
+    valid = dep > 0
+    assert ((r["depth"] > 0) == valid).all(), "stereo validity"
+    if valid.any():
+        assert np.abs(r["u_right"][valid] - ur[valid]).max() <= 1e-3, "u_right"
+        assert (np.abs(r["depth"][valid] - dep[valid]) <= 1e-3 * np.abs(dep[valid])).all(), "depth"
+    oi, od, ok = O.match_bf(dl, job["prev_desc"])
+    assert (r["bf_idx"] == oi).all() and (r["bf_dist"] == od).all() and (r["bf_keep"] == ok).all(), "BF"
+    p1 = O.match_greedy(job["prev_desc"], dl, 0, row_live=job["prev_live"])
+    lv = job["prev_live"].astype(bool)
+    assert (r["p1_row_claimed"] == p1["row_claimed"]).all(), "pass 1 claims"
+    for k in ("best_idx", "best", "second"):
+        assert (r["p1_" + k][lv] == p1[k][lv]).all(), "pass 1 " + k
+    live2 = np.ones(len(job["map_desc"]), np.uint8)
+    m = job["map_prev_row"] >= 0
+    live2[m] = 1 - p1["row_claimed"][job["map_prev_row"][m]]
+    p2 = O.match_greedy(job["map_desc"], dl, 1, claimed=p1["claimed"], claim_row=p1["claim_row"], row_live=live2,
+                        row_base=len(job["prev_desc"]))
+    assert (r["p2_row_claimed"] == p2["row_claimed"]).all() and (r["claim_row"] == p2["claim_row"]).all(), "pass 2"
+    return int(p1["row_claimed"].sum()), int(p2["row_claimed"].sum())
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons during the timed region (NVML)."""
 
@@ -208,6 +250,19 @@ def run_gpu(args, rank, world, local_rank):
     streams = [torch.cuda.ExternalStream(ctx.lane_stream(l), device=dev) for l in range(args.lanes)]
 
     barrier = grp.barrier
+    last_ts = {}
+
+    def verify_last_batches(per_lane):
+        """After a timed region: the results still sitting in each lane's arena (the LAST timed batch of every lane, at
+        the bench's own batch size / lane count / graph replay) are checked against the oracle."""
+        nv = claims = 0
+        for lane in range(args.lanes):
+            if lane not in last_ts:
+                continue
+            for i in sorted(set(np.linspace(0, B - 1, per_lane).astype(int).tolist())):
+                c1, c2 = verify_frame(ctx.batch_result(lane, i), frame_host(last_ts[lane][i]))
+                nv += 1; claims += c1 + c2
+        return nv, claims
 
     def timed(make_frame, steps, warmup, profile):
         cursor = [0]
@@ -215,6 +270,7 @@ def run_gpu(args, rank, world, local_rank):
         def submit(lane):
             ts = [(cursor[0] + i) % P for i in range(B)]
             cursor[0] = (cursor[0] + B) % P
+            last_ts[lane] = ts
             ctx.batch_submit(lane, [make_frame(t) for t in ts])
 
         for s in range(warmup):
@@ -260,7 +316,13 @@ def run_gpu(args, rank, world, local_rank):
     sampler.start()
     # headline numbers: graph replay, no per-stage events
     ms_dev, wall_dev, launches, _ = timed(frame_dev, args.steps, args.warmup, 0)
+    verified = claims = 0
+    if args.verify and rank == 0:
+        verified, claims = verify_last_batches(args.verify)      # resident-input pass: last timed batch of every lane
     ms_e2e, wall_e2e, _, _ = timed(frame_host, args.steps, args.warmup, 0)
+    if args.verify and rank == 0:
+        v2, c2 = verify_last_batches(args.verify)                # host-input pass
+        verified += v2; claims += c2
     # per-stage / per-kernel durations: the same steps again with CUDA events on the lanes' own streams (the events
     # split the captured graph into plain launches, so this pass is a few percent slower than the headline)
     psteps = max(args.lanes + 2, min(args.steps, 24))
@@ -351,12 +413,7 @@ def run_gpu(args, rank, world, local_rank):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (f32 for response, angle, sub-pixel)",
             "data": "synthetic",
-            "config": {"workload": "%s: synthetic %s %dx%d stereo sequence, KITTI04-12 intrinsics, "
-                                   "%d ORB features / 8 levels / 1.2, full front-end: extract L+R, sparse stereo + SAD, "
-                                   "BF match vs previous frame, greedy pass 1 + pass 2 vs %d-row local map"
-                                   % ("configs[1]" if (W_IMG, H_IMG, NFEAT, MAP_ROWS, args.distribution) == (1241, 376, 2000, 5000, "retainbest")
-                                      else "non-headline configuration" + (" (opt-in octree distribution)" if args.distribution == "octree" else ""),
-                                      "KITTI-shape" if (W_IMG, H_IMG) == (1241, 376) else "high-res", W_IMG, H_IMG, NFEAT, MAP_ROWS),
+            "config": {"workload": workload_string(args.distribution),
                        "frames_per_step": B, "lanes": args.lanes, "pool_frames": P,
                        "l2": "inputs larger than L2: %d-frame pool = %.0f MB of images + %.0f MB of descriptors cycled"
                              % (P, 2 * P * img_b / 1e6, P * (K * 33 + MAP_ROWS * 36) / 1e6),
@@ -367,6 +424,10 @@ def run_gpu(args, rank, world, local_rank):
                     "h2d_ms_per_step": stage_e2e.get("h2d"), "d2h_ms_per_step": stage_e2e.get("d2h"),
                     "lane_total_ms_per_step": stage_e2e.get("total")},
             "gpu_launches": launches,
+            "verified_frames": verified,
+            "verified_note": ("frames of the LAST timed batch of every lane (resident-input and host-input passes, batch %d, %d lanes, "
+                              "graph replay) checked bit for bit against the CPU oracle after the timed regions: keypoints, descriptors, "
+                              "stereo, BF, pass 1, pass 2 (%d claims among them)" % (B, args.lanes, claims)) if verified else "verification off",
             "clocks": sampler.result(),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
@@ -389,8 +450,10 @@ def run_gpu(args, rank, world, local_rank):
 
 # ------------------------------------------------------------------------------------------
 def _cpu_worker_init():
-    global _O, _cv2
+    global _O, _cv2, _NAT, _GEOM
     from oracle import oracle as _O  # noqa: F401  (bench's cpu legs may execute oracle/)
+    _NAT = _O.native_matchers()      # svo_matchers.c built on this host with -O3 -march=native
+    _GEOM = _O.geometry(W_IMG, H_IMG, NLEVELS, 1.2, NFEAT)
     try:
         import cv2 as _cv2
         _cv2.setNumThreads(1)
@@ -398,38 +461,62 @@ def _cpu_worker_init():
         _cv2 = None
 
 
-def _cpu_extract(img):
-    if _cv2 is not None:
-        kp, desc = _cv2.ORB_create(nfeatures=NFEAT, scaleFactor=1.2, nlevels=NLEVELS).detectAndCompute(img, None)
-        k = np.array([(p.pt[0], p.pt[1], p.size, p.angle, p.response, p.octave) for p in kp], dtype=_O.KP_DTYPE)
-        return k, desc
-    k, d, _ = _O.orb(img, NFEAT)
-    return k, d
+CPU_STAGES = ("orb_x2", "pyramids_x2", "stereo", "bf", "pass1", "pass2")
+
+
+def _cpu_pyramid(img):
+    """Un-blurred levels for the sparse-stereo stage: chained INTER_LINEAR_EXACT resizes, byte-identical to the
+    oracle's (tests/test_oracle_vs_cv2.py) — cv::ORB builds the same levels internally but does not hand them out."""
+    lw, lh, ls, _ = _GEOM
+    levels = [img]
+    for l in range(1, NLEVELS):
+        levels.append(_cv2.resize(levels[-1], (int(lw[l]), int(lh[l])), interpolation=_cv2.INTER_LINEAR_EXACT))
+    return _O.pyramid_from_levels(levels, ls)
 
 
 def _cpu_frame(job):
     """The reference's per-frame CPU front-end on one core (GUI, drawing, sleeps and per-row vector copies of
-    pnpmatch.cc removed): ORB on L and R, sparse stereo, BF match + greedy pass 1 + pass 2."""
+    pnpmatch.cc removed, SURVEY.md Appendix D): cv::ORB on L and R (src/frame.cc:77), sparse stereo, BFMatcher +
+    greedy pass 1 + pass 2 (src/pnpmatch.cc, -O3 -march=native).  Returns the per-stage seconds."""
     L, R, prev_desc, prev_live, map_desc = job
-    t0 = time.perf_counter()
-    kl, dl = _cpu_extract(L)
-    kr, dr = _cpu_extract(R)
-    # the stereo stage needs the un-blurred pyramids; the oracle rebuilds them (cv2 does not expose them)
-    _, _, pl = _O.orb(L, 1, with_pyramid=True)
-    _, _, pr = _O.orb(R, 1, with_pyramid=True)
-    _O.stereo_sparse(kl, dl, pl, kr, dr, pr, BF, BASELINE)
-    _O.pyramid_free(pl); _O.pyramid_free(pr)
-    _O.match_bf(dl, prev_desc)
-    p1 = _O.match_greedy(prev_desc, dl, 0, row_live=prev_live)
-    _O.match_greedy(map_desc, dl, 1, claimed=p1["claimed"], claim_row=p1["claim_row"], row_base=len(prev_desc))
-    return time.perf_counter() - t0
+    t = [time.perf_counter()]
+    if _cv2 is not None:
+        orb = _cv2.ORB_create(nfeatures=NFEAT, scaleFactor=1.2, nlevels=NLEVELS)
+        out = []
+        for img in (L, R):
+            kp, desc = orb.detectAndCompute(img, None)
+            out.append((np.array([(p.pt[0], p.pt[1], p.size, p.angle, p.response, p.octave) for p in kp], dtype=_O.KP_DTYPE), desc))
+        (kl, dl), (kr, dr) = out
+        t.append(time.perf_counter())
+        pl, pr = _cpu_pyramid(L), _cpu_pyramid(R)
+        t.append(time.perf_counter())
+        _O.stereo_sparse(kl, dl, pl, kr, dr, pr, BF, BASELINE)
+    else:   # no cv2 on this host: the oracle's own extractor (slower; says so in `sample`)
+        kl, dl, pl = _O.orb(L, NFEAT, with_pyramid=True)
+        kr, dr, pr = _O.orb(R, NFEAT, with_pyramid=True)
+        t.append(time.perf_counter()); t.append(time.perf_counter())
+        _O.stereo_sparse(kl, dl, pl, kr, dr, pr, BF, BASELINE)
+        _O.pyramid_free(pl); _O.pyramid_free(pr)
+    t.append(time.perf_counter())
+    _O.match_bf(dl, prev_desc, L=_NAT)
+    t.append(time.perf_counter())
+    p1 = _O.match_greedy(prev_desc, dl, 0, row_live=prev_live, L=_NAT)
+    t.append(time.perf_counter())
+    _O.match_greedy(map_desc, dl, 1, claimed=p1["claimed"], claim_row=p1["claim_row"], row_base=len(prev_desc), L=_NAT)
+    t.append(time.perf_counter())
+    return [t[i + 1] - t[i] for i in range(6)]
 
 
 def _cpu_jobs(seq, n):
     _cpu_worker_init()
     rng = np.random.default_rng(77)
     frames = [seq.frame(t) for t in range(n + 1)]
-    descs = [_cpu_extract(f[0])[1] for f in frames]
+    descs = []
+    for f in frames:
+        if _cv2 is not None:
+            descs.append(_cv2.ORB_create(nfeatures=NFEAT, scaleFactor=1.2, nlevels=NLEVELS).detectAndCompute(f[0], None)[1])
+        else:
+            descs.append(_O.orb(f[0], NFEAT)[1])
     jobs = []
     for t in range(1, n + 1):
         prev = [descs[max(t - a, 0)] for a in range(1, 5)]
@@ -438,19 +525,24 @@ def _cpu_jobs(seq, n):
     return jobs
 
 
+def _cpu_sample_text():
+    return ("%s ORB x2 (what src/frame.cc:77 calls) + chained cv2.resize pyramids + sparse stereo (oracle/, -O2) + BFMatcher / greedy "
+            "pass 1 / pass 2 (oracle/svo_matchers.c, -O3 -march=native, popcnt)" % ("cv2 %s" % _cv2.__version__ if _cv2 else "oracle C"))
+
+
 def cpu_baseline(seq, cores, budget_s):
     """Bounded sample of the same workload on the host (reported beside the GPU number; not the target)."""
     jobs = _cpu_jobs(seq, 4)
-    t1 = _cpu_frame(jobs[0])                                 # warm-up + per-frame cost estimate
-    n = int(max(2, min(len(jobs) * 8, budget_s / max(t1, 1e-3))))
+    t1 = sum(_cpu_frame(jobs[0]))                            # warm-up + per-frame cost estimate
+    n = int(max(4, min(400, budget_s / max(t1, 1e-3))))
+    acc = np.zeros(6)
     t0 = time.perf_counter()
     for i in range(n):
-        _cpu_frame(jobs[i % len(jobs)])
+        acc += _cpu_frame(jobs[i % len(jobs)])
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d frames of the same synthetic sequence on 1 core: %s ORB x2 + C port of pnpmatch.cc loops "
-                      "(-O2, popcnt) + sparse stereo (oracle/)" % (n, "cv2 %s" % _cv2.__version__ if _cv2 else "oracle C"),
-            "ms_per_frame": dt / n * 1e3}
+            "sample": "%d frames of the same synthetic sequence on 1 core: %s" % (n, _cpu_sample_text()),
+            "ms_per_frame": dt / n * 1e3, "stage_ms_per_frame": dict(zip(CPU_STAGES, (acc / n * 1e3).round(3).tolist()))}
 
 
 def run_reference(args, rank, world):
@@ -459,30 +551,35 @@ def run_reference(args, rank, world):
         return None
     import multiprocessing as mp
     cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
     seq = synth.Sequence((H_IMG, W_IMG), seed=0)
     jobs = _cpu_jobs(seq, 4)
-    per_step = args.ref_frames or cores                        # one frame per core per step
+    per_step = args.ref_frames or cores                        # a bounded sample: one frame per core per step
     cores = min(cores, per_step)
     pool = mp.get_context("fork").Pool(cores, initializer=_cpu_worker_init)
     work = [jobs[i % len(jobs)] for i in range(per_step)]
-    steps = max(1, min(args.steps, 12)); warm = max(1, min(args.warmup, 2))
+    steps, warm = args.steps, args.warmup                      # the driver's --steps / --warmup, as given
     for _ in range(warm):
         pool.map(_cpu_frame, work)
+    acc = np.zeros(6)
     t0 = time.perf_counter()
     for _ in range(steps):
-        pool.map(_cpu_frame, work)
+        for st in pool.map(_cpu_frame, work):
+            acc += st
     dt = time.perf_counter() - t0
     pool.close()
     v = steps * per_step / dt
-    sample = ("%d steps x %d frames (one per host core) of the same synthetic sequence; %s ORB x2 (what frame.cc:77 calls) + "
-              "C port of the pnpmatch.cc matching loops + sparse stereo" % (steps, per_step, "cv2 %s" % _cv2.__version__ if _cv2 else "oracle C"))
+    sample = "%d steps x %d frames (one per host core) of the same synthetic sequence; %s" % (steps, per_step, _cpu_sample_text())
     return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
             "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/int32 (f32 for response, angle, sub-pixel)", "data": "synthetic",
-            "config": {"workload": "configs[1]: synthetic KITTI-shape 1241x376 stereo sequence, 2000 ORB features, full front-end "
-                                   "(extract L+R, sparse stereo, BF + greedy pass 1 + pass 2 vs 5000-row map) on host cores",
-                       "frames_per_step": per_step},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": workload_string(), "frames_per_step": per_step,
+                       "note": "each step is a bounded sample of the workload (one frame per host core), CPU only"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "stage_ms_per_frame": dict(zip(CPU_STAGES, (acc / (steps * per_step) * 1e3).round(3).tolist()))},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
@@ -497,6 +594,7 @@ def main():
     ap.add_argument("--pool", type=int, default=160, help="distinct synthetic frames cycled (must exceed L2)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", type=int, default=2, help="frames per lane of the last timed batch checked against the oracle (0: off)")
     ap.add_argument("--ref-frames", type=int, default=0, help="--impl reference: frames per step (default: one per host core)")
     # other BASELINE.json configurations (parity-test / breakdown cases, not the headline): e.g. configs[2]
     # `--features 4000`, configs[3] `--width 2560 --height 720 --features 8000 --batch 8 --pool 48`

@@ -31,6 +31,7 @@ extern "C" {
 #define SVO_E_NOMEM (-4)
 
 #define SVO_MAX_LEVELS 8
+#define SVO_MAX_BOXES 256    /* offline YOLO boxes per frame (veto of pass 1) */
 #define SVO_CAM_LEFT 0
 #define SVO_CAM_RIGHT 1
 
@@ -217,6 +218,16 @@ typedef struct svo_frame_in {
                                     binned into cells on the device and each row gathers its candidates
                                     instead of scanning all columns.  NULL (every frame of the batch or
                                     none) reproduces the reference's brute-force scan.          */
+    /* Pass-1 "dynamic" veto (src/pnpmatch.cc:103-144), the batch form of svo_veto: a would-be match whose
+       current keypoint lies inside an offline YOLO box (+-10 px) and whose f64 epipolar distance under F
+       exceeds 0.1 claims nothing and marks the map point bad (p1_row_bad); pass 2 then skips the local-map
+       rows linked to it (map_prev_row), as it skips bad points in the reference (:163).  The current keypoint
+       positions are the extractor's own output.  Runs when boxes, F and prev_xy are all given.          */
+    const int32_t *boxes;        /* n_boxes x 4: left, right, top, bottom (CurrentFrame->offline_box,
+                                    main.cpp:59-97); at most SVO_MAX_BOXES                               */
+    int n_boxes;
+    const double *F;             /* 3x3 row-major fundamental matrix (findFundamentalMat, :336)         */
+    const float *prev_xy;        /* 2 x n_prev: LastFrame.keypoints_l[i].pt                              */
 } svo_frame_in;
 
 typedef struct svo_frame_out {
@@ -230,6 +241,7 @@ typedef struct svo_frame_out {
     const uint8_t *bf_keep;                      /* n_left                                */
     const int32_t *p1_best_idx, *p1_best, *p1_second; /* n_prev; match_score = second/best */
     const uint8_t *p1_row_claimed;               /* n_prev                                */
+    const uint8_t *p1_row_bad;                   /* n_prev: 1 where the veto marked the row's map point bad (mp->bad, :141) */
     const uint8_t *p2_row_claimed;               /* n_map                                 */
     const int32_t *claim_row;                    /* n_left: row that claimed column j     */
                                                  /* (0..n_prev-1 pass 1, n_prev+i pass 2), -1 = free */

@@ -42,6 +42,50 @@ def lib():
     return _LIB
 
 
+_NATIVE = None
+
+
+def native_matchers():
+    """bench.py's CPU arm only: the same svo_matchers.c built ON THE RUNNING HOST with -O3 -march=native (what the
+    reference's CMakeLists.txt:10-11 passes), used for the integer matchers (BF, pass 1, pass 2).  The float stages keep
+    the portable -O2 -ffp-contract=off build, whose bits are what the parity tests pin.  Built into oracle/_native/
+    (git-ignored) and keyed by the CPU model so a snapshot built elsewhere is never run on a CPU it was not built for."""
+    global _NATIVE
+    if _NATIVE is None:
+        import hashlib
+        try:
+            model = [ln for ln in open("/proc/cpuinfo") if ln.startswith(("model name", "flags"))][:2]
+        except OSError:
+            model = []
+        tag = hashlib.sha1("".join(model).encode()).hexdigest()[:10]
+        d = os.path.join(_HERE, "_native")
+        so = os.path.join(d, "libsvo_matchers_%s.so" % tag)
+        if not os.path.exists(so):
+            os.makedirs(d, exist_ok=True)
+            subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-shared", "-std=c11", "-D_GNU_SOURCE",
+                                   os.path.join(_HERE, "svo_matchers.c"),
+                                   "-o", so + ".tmp", "-lm"])
+            os.replace(so + ".tmp", so)
+        _NATIVE = C.CDLL(so)
+    return _NATIVE
+
+
+def pyramid_from_levels(levels, scales):
+    """A Pyramid over caller-built un-blurred levels (contiguous u8 arrays), e.g. a chained
+    cv2.resize(INTER_LINEAR_EXACT) — identical to the oracle's own levels (tests/test_oracle_vs_cv2.py).
+    The arrays must outlive the struct (they are kept on it)."""
+    pyr = Pyramid()
+    pyr.nlevels = len(levels)
+    keep = []
+    for l, (a, s) in enumerate(zip(levels, scales)):
+        a = np.ascontiguousarray(a, np.uint8)
+        keep.append(a)
+        pyr.w[l], pyr.h[l], pyr.scale[l] = a.shape[1], a.shape[0], float(s)
+        pyr.img[l] = a.ctypes.data_as(C.POINTER(C.c_uint8))
+    pyr._keep = keep
+    return pyr
+
+
 def _p(a, t=C.c_void_p):
     return a.ctypes.data_as(t) if a is not None else None
 
@@ -132,15 +176,15 @@ def hamming(a, b):
     return lib().svo_o_hamming(_p(a), _p(b))
 
 
-def match_bf(q, t):
+def match_bf(q, t, L=None):
     q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
     idx = np.empty(len(q), np.int32); dist = np.empty(len(q), np.int32); keep = np.empty(len(q), np.uint8)
-    lib().svo_o_match_bf(_p(q), len(q), _p(t), len(t), _p(idx), _p(dist), _p(keep))
+    (L or lib()).svo_o_match_bf(_p(q), len(q), _p(t), len(t), _p(idx), _p(dist), _p(keep))
     return idx, dist, keep
 
 
 def match_greedy(rows, cur, mode, claimed=None, row_live=None, row_base=0, claim_row=None,
-                 win_uvr=None, cur_xy=None, veto=None):
+                 win_uvr=None, cur_xy=None, veto=None, L=None):
     """veto (pass 1): dict(boxes (n,4) int32 left/right/top/bottom, F (3,3) f64, row_xy (M,2), cur_xy (N,2)) —
     the YOLO-box + epipolar "dynamic" test of src/pnpmatch.cc:103-144; row_bad marks map points turned bad."""
     rows = np.ascontiguousarray(rows, np.uint8).reshape(-1, 32); cur = np.ascontiguousarray(cur, np.uint8).reshape(-1, 32)
@@ -160,7 +204,7 @@ def match_greedy(rows, cur, mode, claimed=None, row_live=None, row_base=0, claim
         rxy = np.ascontiguousarray(veto["row_xy"], np.float32).reshape(-1, 2)
         vxy = np.ascontiguousarray(veto["cur_xy"], np.float32).reshape(-1, 2)
         assert len(rxy) == M and len(vxy) == N
-    lib().svo_o_match_greedy_veto(_p(rows), M, _p(cur), N, mode, _p(row_live), _p(claimed), _p(claim_row), row_base,
+    (L or lib()).svo_o_match_greedy_veto(_p(rows), M, _p(cur), N, mode, _p(row_live), _p(claimed), _p(claim_row), row_base,
                                   _p(bi), _p(b), _p(s), _p(rc), _p(win_uvr), _p(cur_xy),
                                   _p(boxes), 0 if boxes is None else len(boxes), _p(F), _p(rxy), _p(vxy), _p(bad))
     return dict(best_idx=bi, best=b, second=s, row_claimed=rc, claimed=claimed, claim_row=claim_row, row_bad=bad)

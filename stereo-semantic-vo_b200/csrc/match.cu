@@ -48,6 +48,14 @@ __device__ __forceinline__ const int *map_prev_of(const GreedyArgs &a, int f)
     return a.map_prev_row ? a.map_prev_row + (size_t)f * a.rows.stride_rows : nullptr;
 }
 
+// Pass 2 skips a local-map row whose map point is the one pass-1 row `pr` owns when pass 1 matched it
+// (observations.count(CurrentFrame), src/pnpmatch.cc:165) or marked it bad (mp_local->bad, :163, set at :141).
+__device__ __forceinline__ bool prev_row_done(const GreedyArgs &a, int f, int pr)
+{
+    const size_t o = (size_t)f * a.prev_stride + pr;
+    return a.prev_row_claimed[o] || (a.prev_row_bad && a.prev_row_bad[o]);
+}
+
 // stage columns [c0, c0+nc) of a descriptor set into the swizzled shared tile
 __device__ __forceinline__ void load_tile(uint4 *tile, const uint8_t *desc, int c0, int nc)
 {
@@ -215,9 +223,9 @@ __global__ void k_greedy_init(GreedyArgs a, int reset_time)
             int reuse = -1;
             if (live && mpr) {
                 const int pr = mpr[i];
-                if (pr >= 0) {
-                    if (a.prev_row_claimed[(size_t)f * a.prev_stride + pr]) live = false;
-                    else if (a.dmat && !a.win_gather && pr < set_count(a.prev, f)) {
+                if (pr >= 0 && pr < a.prev_count[f]) {   // a link past the previous set is no link
+                    if (prev_row_done(a, f, pr)) live = false;
+                    else if (a.dmat && !a.win_gather) {
                         const Row P = load_row(set_desc(a.prev, f), pr), Q = load_row(set_desc(a.rows, f), i);
                         if (P.a.x == Q.a.x && P.a.y == Q.a.y && P.a.z == Q.a.z && P.a.w == Q.a.w &&
                             P.b.x == Q.b.x && P.b.y == Q.b.y && P.b.z == Q.b.z && P.b.w == Q.b.w) reuse = pr;
@@ -636,15 +644,33 @@ __global__ void __launch_bounds__(M_THREADS) k_reuse(GreedyArgs a, int T)
 // ---------------------------------------------------------------------------------------
 extern __shared__ __align__(16) uint8_t resolve_smem[];
 
+// true when pass 1 of frame f runs the "dynamic" test at all
+__device__ __forceinline__ bool veto_active(const GreedyArgs &a, int f)
+{
+    if (a.mode != SVO_GREEDY_PASS1) return false;
+    if (a.fp) return a.use_veto && a.fp[f].n_boxes > 0 && a.fp[f].boxes && a.fp[f].F && a.fp[f].prev_xy;
+    return a.n_boxes > 0 && a.F;
+}
+
 __device__ bool veto_dynamic(const GreedyArgs &a, int f, int row, int col)
 {
-    // src/pnpmatch.cc:103-122
-    const float *cxy = a.cur_xy + ((size_t)f * a.cols.stride_rows + col) * 2;
-    const float *lxy = a.row_xy + ((size_t)f * a.rows.stride_rows + row) * 2;
-    const float cx = cxy[0], cy = cxy[1], lx = lxy[0], ly = lxy[1];
-    const double *F = a.F + (size_t)f * 9;
-    for (int k = 0; k < a.n_boxes; ++k) {
-        const int *bx = a.boxes + ((size_t)f * a.n_boxes + k) * 4;
+    // src/pnpmatch.cc:103-122.  Single call: boxes / F / row_xy / cur_xy arrays of the one frame; batch: the frame's
+    // entries of the pointer table, current keypoint positions straight from the extractor's output.
+    const int *boxes; const double *F; int nb; float cx, cy, lx, ly;
+    if (a.fp) {
+        const FramePtrs &P = a.fp[f];
+        boxes = P.boxes; nb = P.n_boxes; F = P.F;
+        lx = P.prev_xy[2 * row]; ly = P.prev_xy[2 * row + 1];
+        const svo_keypoint &k = a.kp[(size_t)f * a.kp_frame_stride + col];
+        cx = k.x; cy = k.y;
+    } else {
+        boxes = a.boxes + (size_t)f * a.n_boxes * 4; nb = a.n_boxes; F = a.F + (size_t)f * 9;
+        const float *cxy = a.cur_xy + ((size_t)f * a.cols.stride_rows + col) * 2;
+        const float *lxy = a.row_xy + ((size_t)f * a.rows.stride_rows + row) * 2;
+        cx = cxy[0]; cy = cxy[1]; lx = lxy[0]; ly = lxy[1];
+    }
+    for (int k = 0; k < nb; ++k) {
+        const int *bx = boxes + 4 * k;
         const int left = bx[0], right = bx[1], top = bx[2], bottom = bx[3];
         if (cx > left - 10 && cx < right + 10 && cy > top - 10 && cy < bottom + 10) {
             const double A = __dadd_rn(__dadd_rn(__dmul_rn(F[0], lx), __dmul_rn(F[1], ly)), F[2]);
@@ -705,7 +731,7 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_c
         if (c == 0) return 0;
         if (mpr) {
             const int pr = mpr[r];
-            if (pr >= 0 && a.prev_row_claimed[(size_t)f * a.prev_stride + pr]) return 0;
+            if (pr >= 0 && pr < a.prev_count[f] && prev_row_done(a, f, pr)) return 0;
         }
         return min(c, SVO_SHORT_CAP + 1);
     };
@@ -786,7 +812,7 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_c
     const float *cxy = a.cur_xy ? a.cur_xy + co * 2 : nullptr;
     const int rbase = a.row_base + (a.row_base_arr ? a.row_base_arr[f] : 0);
     const bool pass1 = a.mode == SVO_GREEDY_PASS1;
-    const bool use_veto = pass1 && a.n_boxes > 0 && a.F;
+    const bool use_veto = veto_active(a, f);
     auto pos_of = [&](int j) -> int { return j * RES_THREADS + ((j & 1) ? RES_THREADS - 1 - tid : tid); };
     const int rounds = (total + RES_THREADS - 1) / RES_THREADS;
     int mk[RES_RC], mrs[RES_RC], moff[RES_RC], mw[RES_RC];   // k, row | s << 16, CSR offset, decision
@@ -944,7 +970,7 @@ __global__ void __launch_bounds__(M_THREADS) k_scores(GreedyArgs a)
     bool live = r < M && (!rl || rl[r]);
     if (live && mpr) {
         const int pr = mpr[r];
-        if (pr >= 0 && a.prev_row_claimed[(size_t)f * a.prev_stride + pr]) live = false;
+        if (pr >= 0 && pr < a.prev_count[f] && prev_row_done(a, f, pr)) live = false;
     }
     const Row R = load_row(rd, min(r, M - 1));
     const float *win = (a.win_uvr && r < M) ? a.win_uvr + (ro + r) * 3 : nullptr;

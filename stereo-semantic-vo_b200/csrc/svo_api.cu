@@ -45,7 +45,7 @@ struct HostArena {           // pinned mirror of one lane's outputs
     svo_keypoint *kp; uint8_t *desc; int *nkp, *status;
     float *u_right, *depth; int *n_stereo;
     int *bf_idx, *bf_dist; uint8_t *bf_keep;
-    int *p1_best_idx, *p1_best, *p1_second; uint8_t *p1_row_claimed, *p2_row_claimed;
+    int *p1_best_idx, *p1_best, *p1_second; uint8_t *p1_row_claimed, *p1_row_bad, *p2_row_claimed;
     int *claim_row;
     int *params;             // staging for the per-batch parameter upload
 };
@@ -72,7 +72,7 @@ struct Lane {
     cudaEvent_t done;
     cudaEvent_t ev[N_EVENTS];
     int slot0, frame0, nframes;
-    bool busy;
+    bool busy, veto;
     HostArena h;
     std::vector<svo_frame_in> in;
     uint8_t *d_stage;          // landing zone for the host inputs of a batch (images, descriptors, flags)
@@ -359,7 +359,7 @@ bool device_readable(const void *p)
 struct Seg { const uint8_t *src; size_t bytes; const void **field; bool need16; };
 
 // Kernels, memsets and D2H copies of one batch on the lane's stream (capturable: no host-dependent arguments).
-int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, bool fused, bool windowed, cudaEvent_t *ev)
+int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, bool fused, bool windowed, bool veto, cudaEvent_t *ev)
 {
     const Geom &g = ctx->g;
     const Bufs &b = ctx->b;
@@ -423,7 +423,11 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
         ga.fp = L.d_fp; ga.use_live = 1; ga.use_map_prev = 0;
         ga.best_idx = fb.p1_best_idx + (size_t)L.frame0 * R; ga.best = fb.p1_best + (size_t)L.frame0 * R;
         ga.second = fb.p1_second + (size_t)L.frame0 * R;
-        ga.row_claimed = fb.p1_row_claimed + (size_t)L.frame0 * R; ga.row_bad = nullptr;
+        ga.row_claimed = fb.p1_row_claimed + (size_t)L.frame0 * R;
+        // the "dynamic" veto: boxes / F / prev_xy of each frame sit behind the pointer table, the current keypoints'
+        // positions are the extractor's output
+        ga.row_bad = fb.p1_row_bad + (size_t)L.frame0 * R; ga.use_veto = veto ? 1 : 0;
+        ga.kp = b.kp + (size_t)L.slot0 * g.kp_cap; ga.kp_frame_stride = 2 * (size_t)g.kp_cap;
         if (fused) {
             // BF (cur -> prev) and greedy pass 1 (prev rows over cur columns) share one distance matrix
             PairArgs pa;
@@ -453,6 +457,8 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
             ga.prev.tab = reinterpret_cast<const uint8_t *const *>(&L.d_fp->prev);
         }
         ga.prev_row_claimed = fb.p1_row_claimed + (size_t)L.frame0 * R; ga.prev_stride = R;
+        ga.prev_row_bad = (any_prev && veto) ? fb.p1_row_bad + (size_t)L.frame0 * R : nullptr;
+        ga.prev_count = d_nprev; ga.use_veto = 0;
         ga.best_idx = nullptr; ga.best = nullptr; ga.second = nullptr;
         ga.row_claimed = fb.p2_row_claimed + (size_t)L.frame0 * R; ga.row_bad = nullptr;
         if (windowed) {   // opt-in projection windows: gather from the keypoint grid instead of scanning every column
@@ -489,6 +495,7 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
         CU(cudaMemcpyAsync(h.p1_best, fb.p1_best + (size_t)L.frame0 * R, sizeof(int) * n * R, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(h.p1_second, fb.p1_second + (size_t)L.frame0 * R, sizeof(int) * n * R, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(h.p1_row_claimed, fb.p1_row_claimed + (size_t)L.frame0 * R, (size_t)n * R, cudaMemcpyDeviceToHost, st));
+        if (veto) CU(cudaMemcpyAsync(h.p1_row_bad, fb.p1_row_bad + (size_t)L.frame0 * R, (size_t)n * R, cudaMemcpyDeviceToHost, st));
     }
     if (any_map) CU(cudaMemcpyAsync(h.p2_row_claimed, fb.p2_row_claimed + (size_t)L.frame0 * R, (size_t)n * R, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h.claim_row, fb.claim_row + (size_t)L.frame0 * K, sizeof(int) * n * KC, cudaMemcpyDeviceToHost, st));
@@ -634,10 +641,10 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
         TRY(halloc(ctx, &h.u_right, B * K)); TRY(halloc(ctx, &h.depth, B * K)); TRY(halloc(ctx, &h.n_stereo, B));
         TRY(halloc(ctx, &h.bf_idx, B * K)); TRY(halloc(ctx, &h.bf_dist, B * K)); TRY(halloc(ctx, &h.bf_keep, B * K));
         TRY(halloc(ctx, &h.p1_best_idx, B * R)); TRY(halloc(ctx, &h.p1_best, B * R)); TRY(halloc(ctx, &h.p1_second, B * R));
-        TRY(halloc(ctx, &h.p1_row_claimed, B * R)); TRY(halloc(ctx, &h.p2_row_claimed, B * R));
+        TRY(halloc(ctx, &h.p1_row_claimed, B * R)); TRY(halloc(ctx, &h.p1_row_bad, B * R)); TRY(halloc(ctx, &h.p2_row_claimed, B * R));
         TRY(halloc(ctx, &h.claim_row, B * K));
         TRY(halloc(ctx, &h.params, 4 * B));
-        l.stage_cap = I * ctx->stage_img_bytes + B * (R * 32 * 2 + R * 5 + R * 12) + (7 * B + 8) * 512;
+        l.stage_cap = I * ctx->stage_img_bytes + B * (R * 32 * 2 + R * 5 + R * 12 + R * 8 + SVO_MAX_BOXES * 16 + 72) + (10 * B + 8) * 512;
         TRY(dalloc(ctx, &l.d_stage, l.stage_cap));
         TRY(dalloc(ctx, &l.d_fp, B)); TRY(halloc(ctx, &l.h_fp, B));
         TRY(dalloc(ctx, &l.d_strides, I)); TRY(halloc(ctx, &l.h_strides, I));
@@ -1006,8 +1013,13 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
     cudaEvent_t *ev = ctx->profiling ? L.ev : nullptr;
     bool any_prev = false, any_map = false;
     int n_win = 0, n_mapped = 0;
+    bool veto = false;
     for (int i = 0; i < n; ++i) {
         const svo_frame_in &f = frames[i];
+        if (f.n_boxes < 0 || f.n_boxes > SVO_MAX_BOXES || (f.n_boxes && !f.boxes))
+            return fail(ctx, SVO_E_INVALID, "svo_batch_submit: frame %d: n_boxes %d (at most %d)", i, f.n_boxes, SVO_MAX_BOXES);
+        if (f.F && ((uintptr_t)f.F & 7)) return fail(ctx, SVO_E_INVALID, "svo_batch_submit: frame %d: F must be 8-byte aligned", i);
+        veto |= f.n_prev > 0 && f.n_boxes > 0 && f.F && f.prev_xy;
         if (f.n_map > 0) { ++n_mapped; if (f.map_win_uvr) ++n_win; }
         const int ch = f.channels == 3 ? 3 : 1;
         if (!f.left || !f.right || f.stride < g.W * ch || f.stride >= SVO_STRIDE_BGR || f.n_prev < 0 || f.n_map < 0 || f.n_prev > R ||
@@ -1021,7 +1033,7 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
         return fail(ctx, SVO_E_INVALID, "svo_batch_submit: map_win_uvr must be given for every frame with a map, or for none");
     const bool windowed = n_win > 0;
     L.in.assign(frames, frames + n);
-    L.nframes = n;
+    L.nframes = n; L.veto = veto;
     if (ev) cudaEventRecord(ev[0], st);
     // ---- inputs: device-resident buffers are read in place; host buffers are gathered into the lane's
     // landing zone with one H2D copy per maximal run of adjacent source ranges (a strided 2-D copy of
@@ -1060,6 +1072,11 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
         place(f.n_map ? f.map_desc : nullptr, (size_t)f.n_map * 32, (const void **)&P.map, true);
         place((f.n_map && f.n_prev) ? f.map_prev_row : nullptr, sizeof(int) * (size_t)f.n_map, (const void **)&P.map_prev_row, true);
         place((f.n_map && windowed) ? f.map_win_uvr : nullptr, 3 * sizeof(float) * (size_t)f.n_map, (const void **)&P.map_win, false);
+        const bool fv = f.n_prev > 0 && f.n_boxes > 0 && f.F && f.prev_xy;
+        place(fv ? f.boxes : nullptr, 4 * sizeof(int) * (size_t)f.n_boxes, (const void **)&P.boxes, false);
+        place(fv ? f.F : nullptr, 9 * sizeof(double), (const void **)&P.F, false);
+        place(fv ? f.prev_xy : nullptr, 2 * sizeof(float) * (size_t)f.n_prev, (const void **)&P.prev_xy, false);
+        P.n_boxes = fv ? f.n_boxes : 0;
         hp[i] = f.n_prev; hp[B + i] = f.n_map;
         memcpy(&hp[2 * B + i], &f.bf, 4); memcpy(&hp[3 * B + i], &f.baseline, 4);
     }
@@ -1094,16 +1111,16 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
     // stages run): every per-frame input is reached through device tables filled above.  Outside profiling runs
     // the sequence is therefore captured once into a CUDA graph and replayed (one launch instead of ~45 calls).
     if (ev) {
-        TRY(enqueue_compute(ctx, L, n, any_prev, any_map, fused, windowed, ev));
+        TRY(enqueue_compute(ctx, L, n, any_prev, any_map, fused, windowed, veto, ev));
     } else {
-        const int key = n | (any_prev ? 1 << 20 : 0) | (any_map ? 1 << 21 : 0) | (fused ? 1 << 22 : 0) | (windowed ? 1 << 23 : 0);
+        const int key = n | (any_prev ? 1 << 20 : 0) | (any_map ? 1 << 21 : 0) | (fused ? 1 << 22 : 0) | (windowed ? 1 << 23 : 0) | (veto ? 1 << 24 : 0);
         LaneGraph *lg = nullptr;
         for (LaneGraph &c : L.graphs) if (c.key == key) lg = &c;
         if (!lg) {
             const long long before = ctx->launches;
             cudaGraph_t graph = nullptr;
             CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            const int rc = enqueue_compute(ctx, L, n, any_prev, any_map, fused, windowed, nullptr);
+            const int rc = enqueue_compute(ctx, L, n, any_prev, any_map, fused, windowed, veto, nullptr);
             const cudaError_t ce = cudaStreamEndCapture(st, &graph);
             if (rc != SVO_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
             if (ce != cudaSuccess) return fail(ctx, SVO_E_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
@@ -1159,6 +1176,7 @@ int svo_batch_result(svo_ctx *ctx, int lane_i, int i, svo_frame_out *o)
         o->bf_idx = h.bf_idx + (size_t)i * K; o->bf_dist = h.bf_dist + (size_t)i * K; o->bf_keep = h.bf_keep + (size_t)i * K;
         o->p1_best_idx = h.p1_best_idx + (size_t)i * R; o->p1_best = h.p1_best + (size_t)i * R;
         o->p1_second = h.p1_second + (size_t)i * R; o->p1_row_claimed = h.p1_row_claimed + (size_t)i * R;
+        if (L.veto) o->p1_row_bad = h.p1_row_bad + (size_t)i * R;     // NULL: no frame of the batch ran the veto
     }
     if (in.n_map) o->p2_row_claimed = h.p2_row_claimed + (size_t)i * R;
     o->claim_row = h.claim_row + (size_t)i * K;

@@ -94,6 +94,11 @@ struct FramePtrs {
     const uint8_t *map;            // n_map x 32, 16-byte aligned
     const int *map_prev_row;       // n_map or NULL
     const float *map_win;          // 3 x n_map (u, v, r) projection windows of pass 2, or NULL
+    // pass-1 "dynamic" veto (src/pnpmatch.cc:103-144): offline YOLO boxes, fundamental matrix, last frame's keypoint positions
+    const int *boxes;              // n_boxes x 4 (left, right, top, bottom) or NULL
+    const double *F;               // 3x3 row-major, 8-byte aligned, or NULL
+    const float *prev_xy;          // 2 x n_prev or NULL
+    int n_boxes;
 };
 
 // ---- stage launchers (each enqueues on `st` for images [slot0, slot0 + nimg)) ----
@@ -161,6 +166,8 @@ struct GreedyArgs {
     const uint8_t *dmat; size_t dmat_frame_stride; int dmat_pitch;
     MatchSet prev;
     const uint8_t *prev_row_claimed;  // [frame][prev stride] (pass 2, with map_prev_row)
+    const uint8_t *prev_row_bad;      // [frame][prev stride] or NULL: pass-1 rows whose map point turned bad
+    const int *prev_count;            // [frame] rows of the previous set (pass 2, with map_prev_row): larger links are ignored
     int prev_stride;
     uint8_t *claimed;             // [frame][cols.stride_rows] in/out
     int *claim_row;               // [frame][cols.stride_rows] in/out
@@ -186,8 +193,9 @@ struct GreedyArgs {
     int *free_cnt;                // [frame]
     const svo_keypoint *kp; size_t kp_frame_stride;   // current (left) keypoints of frame f at kp + f * kp_frame_stride
     float *win_out, *cur_xy_out;
-    // veto (pass 1)
+    // veto (pass 1).  Single call: the arrays below; batch (fp != NULL, use_veto): fp[frame].boxes / F / prev_xy and kp
     const int *boxes; int n_boxes; const double *F; const float *row_xy;
+    int use_veto;
 };
 void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStream_t st, long long *launches,
                    cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);   // optional events around k_shortlist

@@ -39,7 +39,8 @@ class FrameIn(C.Structure):
                 ("bf", C.c_float), ("baseline", C.c_float),
                 ("prev_desc", C.c_void_p), ("n_prev", C.c_int), ("prev_live", C.c_void_p),
                 ("map_desc", C.c_void_p), ("n_map", C.c_int), ("map_prev_row", C.c_void_p), ("channels", C.c_int),
-                ("map_win_uvr", C.c_void_p)]
+                ("map_win_uvr", C.c_void_p),
+                ("boxes", C.c_void_p), ("n_boxes", C.c_int), ("F", C.c_void_p), ("prev_xy", C.c_void_p)]
 
 
 class FrameOut(C.Structure):
@@ -48,7 +49,8 @@ class FrameOut(C.Structure):
                 ("u_right", C.c_void_p), ("depth", C.c_void_p),
                 ("bf_idx", C.c_void_p), ("bf_dist", C.c_void_p), ("bf_keep", C.c_void_p),
                 ("p1_best_idx", C.c_void_p), ("p1_best", C.c_void_p), ("p1_second", C.c_void_p),
-                ("p1_row_claimed", C.c_void_p), ("p2_row_claimed", C.c_void_p), ("claim_row", C.c_void_p)]
+                ("p1_row_claimed", C.c_void_p), ("p1_row_bad", C.c_void_p), ("p2_row_claimed", C.c_void_p),
+                ("claim_row", C.c_void_p)]
 
 
 class PoseProblem(C.Structure):
@@ -290,7 +292,8 @@ class Context:
     # ---- batched pipeline ------------------------------------------------------------
     def batch_submit(self, lane, frames):
         """frames: list of dicts with left,right (u8 arrays or raw pointers + stride), bf, baseline and optional
-        prev_desc, prev_live, map_desc, map_prev_row.  Arrays are kept alive until the lane's next submit."""
+        prev_desc, prev_live, map_desc, map_prev_row, map_win_uvr and the pass-1 veto inputs boxes (n,4 int32),
+        F (3,3 f64), prev_xy (n_prev,2 f32).  Arrays are kept alive until the lane's next submit."""
         arr = (FrameIn * len(frames))()
         keep = []
         for i, f in enumerate(frames):
@@ -325,6 +328,22 @@ class Context:
                     setattr(fi, name, v.ctypes.data)
                 elif v is not None:
                     setattr(fi, name, int(v))          # raw (device) address
+            if f.get("boxes") is not None:
+                v = f["boxes"]
+                if isinstance(v, np.ndarray) or isinstance(v, (list, tuple)):
+                    v = np.ascontiguousarray(v, np.int32).reshape(-1, 4)
+                    keep.append(v)
+                    fi.boxes, fi.n_boxes = v.ctypes.data, len(v)
+                else:
+                    fi.boxes, fi.n_boxes = int(v), f["n_boxes"]
+            for name, dt in (("F", np.float64), ("prev_xy", np.float32)):
+                v = f.get(name)
+                if isinstance(v, np.ndarray):
+                    v = np.ascontiguousarray(v, dt)
+                    keep.append(v)
+                    setattr(fi, name, v.ctypes.data)
+                elif v is not None:
+                    setattr(fi, name, int(v))
         self._keep[("lane", lane)] = (arr, keep)
         self._chk(self.lib.svo_batch_submit(self.h, lane, arr, len(frames)))
 
@@ -347,7 +366,8 @@ class Context:
                      bf_keep=_view(o.bf_keep, np.uint8, (nl,)),
                      p1_best_idx=_view(o.p1_best_idx, np.int32, (n_prev,)), p1_best=_view(o.p1_best, np.int32, (n_prev,)),
                      p1_second=_view(o.p1_second, np.int32, (n_prev,)),
-                     p1_row_claimed=_view(o.p1_row_claimed, np.uint8, (n_prev,)))
+                     p1_row_claimed=_view(o.p1_row_claimed, np.uint8, (n_prev,)),
+                     p1_row_bad=_view(o.p1_row_bad, np.uint8, (n_prev,)))
         if n_map:
             r.update(p2_row_claimed=_view(o.p2_row_claimed, np.uint8, (n_map,)))
         if copy:
