@@ -237,3 +237,26 @@ class Frame:
         disp = np.zeros((h, w), np.float32); depth = np.zeros((h, w), np.float32)
         lib().ref_frame_get_images(self.h, _p(disp), _p(depth))
         return disp, depth
+
+
+def run_two_frames(frames, disps, K, bf, boxes, pose0=None):
+    """Two stereo frames through the reference exactly as Tracking::Track / Tracklastframe drive it
+    (src/Tracking.cc:184, :225-238, :114).  frames = ((L0, R0), (L1, R1)); disps = the dense disparity images standing
+    in for frame::MB's output.  Returns everything the pin tests and the golden fixtures compare."""
+    (L0, R0), (L1, R1) = frames
+    LOG["fundamental"].clear(); LOG["pnp"].clear()
+    f0 = Frame(L0, R0, K, bf, boxes, 0.0, 0)
+    if pose0 is not None:
+        f0.set_pose(pose0)
+    f0.featuredetect(); f0.set_disp(disps[0]); f0.stereo()
+    s0 = f0.state()
+    last = f0.copy()                                  # Tracking.cc:237
+    lm = LocalMap()
+    created = last.createmappoint(lm)                 # :238
+    before = dict(last=last.state(), map=lm.list())
+    f1 = Frame(L1, R1, K, bf, boxes, 0.1, 1)
+    f1.featuredetect(); f1.set_disp(disps[1]); f1.stereo()
+    f1.pose_estimation_pnp(last, lm, K)               # Tracking.cc:114
+    d0, z0 = f0.images()
+    return dict(f0=s0, created=created, before=before, cur=f1.state(), last=last.state(), map=lm.list(),
+                F=dict(LOG["fundamental"][-1]), pnp=dict(LOG["pnp"][-1]), disp0=d0, depth0=z0)

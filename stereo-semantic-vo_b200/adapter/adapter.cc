@@ -245,11 +245,14 @@ cv::Mat frame::UnprojectStereo(const float &u, const float &v, const float &z)
 {
     if (!(z > 0)) return cv::Mat();
     const float xc[3] = {(u - cx) * z * (1 / fx), (v - cy) * z * (1 / fy), z};
+    // x3D = Rwc * x3Dc + twc as OpenCV evaluates it (one gemm with the addend, small-matrix path): the float products
+    // summed left to right, then + twc — the order matters for the last bit (tests/test_ref_pin.py checks it on cv2.gemm)
     cv::Mat x3D(3, 1, CV_32F);
     for (int r = 0; r < 3; ++r) {
-        float s = twc.at<float>(r, 0);
-        for (int c = 0; c < 3; ++c) s += Rwc.at<float>(r, c) * xc[c];
-        x3D.at<float>(r, 0) = s;
+        float s = Rwc.at<float>(r, 0) * xc[0];
+        s = s + Rwc.at<float>(r, 1) * xc[1];
+        s = s + Rwc.at<float>(r, 2) * xc[2];
+        x3D.at<float>(r, 0) = s + twc.at<float>(r, 0);
     }
     return x3D;
 }
@@ -388,6 +391,14 @@ int pnpmatch::match_last_frame(frame *cur, frame &last, const cv::Mat &F)
     for (const auto &b : cur->offline_box) for (int k = 0; k < 4; ++k) boxes.push_back(b[(size_t)k]);
     double Fd[9] = {0};
     svo_veto veto = {nullptr, 0, nullptr, nullptr, nullptr};
+    // The reference always has an F here (src/pnpmatch.cc:36) and reads it for every would-be match inside a box
+    // (:110-112); without one the "dynamic" test cannot run, and skipping it silently would change which map points
+    // turn bad.  F comes from the fundamental_solver hook (cv::findFundamentalMat stays with the integrator's OpenCV).
+    if (!boxes.empty() && F.empty())
+        throw std::runtime_error("pnpmatch: offline_box is not empty but no fundamental matrix was produced "
+                                 "(install pnpmatch::fundamental_solver, e.g. cv::findFundamentalMat(p1, p2, CV_FM_8POINT))");
+    if (!F.empty() && (F.rows != 3 || F.cols != 3 || F.depth() != CV_64F))
+        throw std::runtime_error("pnpmatch: the fundamental matrix must be 3x3 CV_64F (what cv::findFundamentalMat returns)");
     const bool use_veto = !boxes.empty() && !F.empty();
     if (use_veto) {
         for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Fd[3 * r + c] = reinterpret_cast<const double *>(F.ptr(r))[c];

@@ -18,6 +18,7 @@ namespace cv {
 enum { CV_8U_ = 0, CV_32F_ = 5 };
 #define CV_8U 0
 #define CV_32F 5
+#define CV_64F 6
 #define CV_8UC1 0
 #define CV_8UC3 16
 
@@ -60,7 +61,7 @@ public:
     int type() const { return type_; }
     int depth() const { return type_ & 7; }
     int channels() const { return (type_ >> 3) + 1; }
-    size_t elemSize() const { return (size_t)channels() * (depth() == 5 ? 4 : 1); }
+    size_t elemSize() const { return (size_t)channels() * (depth() == 6 ? 8 : depth() == 5 ? 4 : 1); }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
     Mat clone() const
     {
@@ -85,7 +86,8 @@ public:
     {
         for (int r = 0; r < rows; ++r)
             for (int c = 0; c < cols * channels(); ++c) {
-                if (depth() == 5) ptr<float>(r)[c] = (float)v;
+                if (depth() == 6) ptr<double>(r)[c] = v;
+                else if (depth() == 5) ptr<float>(r)[c] = (float)v;
                 else ptr(r)[c] = (uint8_t)v;
             }
     }

@@ -129,3 +129,125 @@ def test_adapter_two_frames(tmp_path):
     assert np.abs(Tlm - To).max() < 1e-5
     for p in (p0, p0r, p1, p1r):
         O.pyramid_free(p)
+
+
+# ---- the drop-in entry points exactly as Tracking::Tracklastframe calls them, against the reference's own code ----
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.mark.parametrize("seed", [5, 9])
+def test_adapter_pose_estimation_pnp_vs_reference_golden(tmp_path, seed):
+    """pnpmatch::poseEstimationPnP / poseEstimation2D_2D / find_feature_matches through the adapter, with non-empty
+    offline_box (src/Tracking.cc:114, src/pnpmatch.cc:33-251, :253-337), against tests/golden/ref_track_seed*.npz —
+    what the reference's own compiled code (oracle/_ref) produced on the same inputs: ORB output after the re-extraction,
+    keypoints_r, depthimg at the keypoints, createmappoint's selection and world positions (UnprojectStereo), the
+    point lists handed to findFundamentalMat, match_score and the map points pass 1 turned bad.  The final
+    CurrentFrame->MapPoints depends on the std::set's pointer order in pass 2, so it is checked against the oracle
+    (pinned to the reference in tests/test_ref_pin.py) run in the adapter's own set order."""
+    exe = os.path.join(ADAPTER, "adapter_track_test")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", ADAPTER, "-s"])
+    g = np.load(os.path.join(GOLD, "ref_track_seed%d.npz" % seed))
+    import hashlib
+    H, W = synth.K_SHAPE
+    seq = synth.Sequence((H, W), seed=seed)
+    (L0, R0), (L1, R1) = seq.frame(0), seq.frame(1)
+    D0, D1 = synth.dense_disparity((H, W), 2 * seed), synth.dense_disparity((H, W), 2 * seed + 1)
+    for a, want in zip((L0, R0, L1, R1, D0, D1), g["input_sha"]):
+        assert hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest() == str(want), "synthetic inputs changed: regenerate the golden"
+    paths = []
+    for name, im in (("L0", L0), ("R0", R0), ("L1", L1), ("R1", R1), ("D0", D0), ("D1", D1)):
+        p = str(tmp_path / (name + ".raw")); im.tofile(p); paths.append(p)
+    bx = str(tmp_path / "boxes.txt"); np.savetxt(bx, g["boxes"].reshape(-1, 4), fmt="%d")
+    fp = str(tmp_path / "F.txt"); open(fp, "w").write(" ".join(repr(float(v)) for v in g["F"].reshape(9)))
+    out = str(tmp_path / "out.txt")
+    subprocess.check_call([exe, str(W), str(H), "500"] + paths + [bx, fp, out])
+    f0, mp, kp, row, fpt, pose = [], [], [], {}, [], None
+    for line in open(out):
+        t = line.split()
+        if t[0] == "f0":
+            f0.append([np.float32(v) for v in t[2:6]])
+        elif t[0] == "map":
+            mp.append((int(t[2]), [np.float32(v) for v in t[3:6]]))
+        elif t[0] == "kp":
+            kp.append(t[1:])
+        elif t[0] == "row":
+            row[int(t[1])] = (np.float32(t[2]), int(t[3]))
+        elif t[0] == "fpt":
+            fpt.append([np.float32(v) for v in t[2:6]])
+        elif t[0] == "counts":
+            counts = list(map(int, t[1:]))
+    f0 = np.array(f0, np.float32)
+
+    def same(a, b):
+        a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+        return a.shape == b.shape and (a.view(np.uint32) == b.view(np.uint32)).all()
+
+    # first frame: keypoints, keypoints_r (sticky rx included), depthimg at the keypoints
+    assert same(f0[:, 0], g["f0_kps"][:, 0]) and same(f0[:, 1], g["f0_kps"][:, 1])
+    assert same(f0[:, 2], g["f0_keypoints_r"][:, 0])
+    assert same(f0[:, 3], g["f0_depth_at_kp"])
+    # createmappoint: same keypoints get a map point, same world positions (set order differs: compare by keypoint index)
+    assert counts[2] == int(g["created"]) == len(mp)
+    got_pos = {i: np.array(p, np.float32) for i, p in mp}
+    assert sorted(got_pos) == sorted(int(i) for i in g["map_idx"])
+    for i, pos in zip(g["map_idx"], g["map_worldpos"]):
+        assert same(got_pos[int(i)], pos), i
+    # find_feature_matches + the box filter of poseEstimation2D_2D: the point lists given to findFundamentalMat
+    fpt = np.array(fpt, np.float32).reshape(-1, 4)
+    assert same(fpt[:, :2], g["F_p1"]) and same(fpt[:, 2:], g["F_p2"])
+    # second frame after the re-extraction: keypoints and descriptors
+    assert same([np.float32(r[1]) for r in kp], g["cur_kps"][:, 0]) and same([np.float32(r[2]) for r in kp], g["cur_kps"][:, 1])
+    desc = np.array([[int(v) for v in r[4:36]] for r in kp], np.uint8)
+    assert (desc == g["cur_desc"]).all()
+    # pass 1: match_score for every row with a map point, and the rows the veto turned bad
+    has = g["last_has_mp"].astype(bool)
+    assert sorted(row) == list(np.nonzero(has)[0])
+    for i, (score, bad) in row.items():
+        assert np.float32(score).view(np.uint32) == g["cur_match_score"][i].view(np.uint32), i
+        assert bad == int(g["last_mp_bad"][i]), i
+    assert int(g["last_mp_bad"].sum()) == sum(b for _, b in row.values())
+    # final MapPoints: oracle replay with the adapter's own pass-2 order
+    live = has.astype(np.uint8)
+    rows1 = np.zeros((len(has), 32), np.uint8); rows1[:len(g["f0_desc"])] = g["f0_desc"][:len(has)]
+    veto = dict(boxes=g["boxes"], F=g["F"], row_xy=g["f0_kps"][:len(has), :2], cur_xy=g["cur_kps"][:, :2]) if len(g["boxes"]) else None
+    p1 = O.match_greedy(rows1, g["cur_desc"], 0, row_live=live, veto=veto)
+    order = np.array([i for i, _ in mp], np.int64)
+    live2 = np.ones(len(order), np.uint8)
+    live2[(p1["row_bad"][order] == 1) | (p1["row_claimed"][order] == 1)] = 0
+    p2 = O.match_greedy(g["f0_desc"][order], g["cur_desc"], 1, claimed=p1["claimed"], claim_row=p1["claim_row"], row_live=live2,
+                        row_base=10 ** 6)
+    expect = np.full(len(kp), -1, np.int64)
+    for j in np.nonzero(p2["claim_row"] >= 0)[0]:
+        r = int(p2["claim_row"][j])
+        expect[j] = r if r < 10 ** 6 else order[r - 10 ** 6]
+    assert ([int(r[3]) for r in kp] == expect).all()
+    assert (expect >= 0).sum() > 40
+    # and the golden's own final assignment is the oracle's in the reference's set order (runs without /root/reference)
+    ordg = g["map_idx"].astype(np.int64)
+    l2 = np.ones(len(ordg), np.uint8); l2[(p1["row_bad"][ordg] == 1) | (p1["row_claimed"][ordg] == 1)] = 0
+    q2 = O.match_greedy(g["map_desc"], g["cur_desc"], 1, claimed=p1["claimed"], claim_row=p1["claim_row"], row_live=l2, row_base=10 ** 6)
+    eg = np.full(len(kp), -1, np.int64)
+    for j in np.nonzero(q2["claim_row"] >= 0)[0]:
+        r = int(q2["claim_row"][j])
+        eg[j] = r if r < 10 ** 6 else ordg[r - 10 ** 6]
+    assert (eg == g["cur_mp_idx"][:len(kp)]).all()
+
+
+def test_adapter_refuses_boxes_without_F(tmp_path):
+    """offline_box given but no fundamental matrix (ADVICE): the reference would dereference an empty Mat; the
+    adapter raises instead of silently skipping the veto."""
+    exe = os.path.join(ADAPTER, "adapter_track_test")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", ADAPTER, "-s"])
+    H, W = synth.K_SHAPE
+    seq = synth.Sequence((H, W), seed=5)
+    (L0, R0), (L1, R1) = seq.frame(0), seq.frame(1)
+    D = synth.dense_disparity((H, W), 10)
+    paths = []
+    for name, im in (("L0", L0), ("R0", R0), ("L1", L1), ("R1", R1), ("D0", D), ("D1", D)):
+        p = str(tmp_path / (name + ".raw")); im.tofile(p); paths.append(p)
+    bx = str(tmp_path / "boxes.txt"); open(bx, "w").write("300 700 100 300\n")
+    fp = str(tmp_path / "F.txt"); open(fp, "w").write("")
+    r = subprocess.run([exe, str(W), str(H), "500"] + paths + [bx, fp, str(tmp_path / "out.txt")], capture_output=True, text=True)
+    assert r.returncode == 1 and "fundamental" in r.stderr

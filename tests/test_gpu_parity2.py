@@ -249,7 +249,7 @@ def test_batch_pipeline_other_baseline_configs(svo, shape, nf, rows, veto):
     ora = [stereo_oracle(L, R, nf, bf, b) for L, R in frames]
     rng = np.random.default_rng(23)
     jobs = make_jobs(frames, ora, rows, rng, rows // 5, veto)
-    c = svo.Context(W, H, nfeatures=nf, max_batch=2, lanes=2, max_rows=rows)
+    c = svo.Context(W, H, nfeatures=nf, max_batch=2, lanes=2, max_rows=max(rows, nf + nf // 8 + 128))   # rows of a set: map or previous frame
     try:
         c.batch_submit(0, jobs)
         c.batch_submit(1, jobs[1:])                     # a one-frame batch on the other lane at the same time

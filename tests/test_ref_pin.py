@@ -21,27 +21,12 @@ BF = np.float32(CAL["bf"])
 BOXES = [[300, 700, 100, 300], [900, 1100, 50, 200], [20, 180, 200, 360]]
 
 
-def run_reference(seed, boxes, shape=synth.K_SHAPE, pose=None):
+def run_reference(seed, boxes, shape=synth.K_SHAPE):
     """Two frames through the reference exactly as Tracking::Track does; returns everything the tests compare."""
     seq = synth.Sequence(shape, seed=seed)
-    (L0, R0), (L1, R1) = seq.frame(0), seq.frame(1)
-    R.LOG["fundamental"].clear(); R.LOG["pnp"].clear()
-    f0 = R.Frame(L0, R0, K, BF, boxes, 0.0, 0)
-    if pose is not None:
-        f0.set_pose(pose)
-    f0.featuredetect(); f0.set_disp(synth.dense_disparity(shape, 2 * seed)); f0.stereo()
-    s0 = f0.state()
-    last = f0.copy()                                  # Tracking.cc:237
-    lm = R.LocalMap()
-    created = last.createmappoint(lm)                 # :238
-    before = dict(last=last.state(), map=lm.list())
-    f1 = R.Frame(L1, R1, K, BF, boxes, 0.1, 1)
-    f1.featuredetect(); f1.set_disp(synth.dense_disparity(shape, 2 * seed + 1)); f1.stereo()
-    s1_pre = f1.state()
-    f1.pose_estimation_pnp(last, lm, K)               # Tracking.cc:114
-    return dict(images=(L0, R0, L1, R1), f0=s0, created=created, before=before, cur_pre=s1_pre, cur=f1.state(), last=last.state(),
-                map=lm.list(), F=R.LOG["fundamental"][-1], pnp=R.LOG["pnp"][-1], disp0=f0.images()[0], depth0=f0.images()[1],
-                frames=(f0, last, f1))
+    frames = (seq.frame(0), seq.frame(1))
+    disps = (synth.dense_disparity(shape, 2 * seed), synth.dense_disparity(shape, 2 * seed + 1))
+    return R.run_two_frames(frames, disps, K, BF, boxes)
 
 
 @pytest.fixture(scope="module")
