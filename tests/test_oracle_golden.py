@@ -9,7 +9,7 @@ import pytest
 from oracle import oracle as O
 
 G = os.path.join(os.path.dirname(__file__), "golden")
-ORB_CASES = sorted(glob.glob(os.path.join(G, "*seed*.npz")))
+ORB_CASES = sorted(p for p in glob.glob(os.path.join(G, "*seed*.npz")) if not os.path.basename(p).startswith("ref_track"))
 
 
 def bits(a):
