@@ -291,6 +291,11 @@ long long svo_debug_tap(svo_ctx *ctx, int cam, int what, int level, void *out, s
 int svo_debug_retain_best(svo_ctx *ctx, const float *resp, int n, int n_points, int depth_limit,
                           int32_t *idx_out);
 
+/* Test tap of the tensor-core Hamming tiles the batch matchers run on (csrc/tcham.cu: tcgen05.mma.kind::i8 over
+ * +-1-expanded descriptors): the full na x nb matrix of DescriptorDistance (src/pnpmatch.cc:14-30) values, row-major
+ * into dist.  na, nb within the context's single-call capacities.  Returns na or a negative status. */
+int svo_debug_hamming_matrix(svo_ctx *ctx, const uint8_t *a, int na, const uint8_t *b, int nb, int32_t *dist);
+
 #ifdef __cplusplus
 }
 #endif

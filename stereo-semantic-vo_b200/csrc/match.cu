@@ -21,6 +21,7 @@
 #include "svo_internal.cuh"
 #include <limits.h>
 #include <stdlib.h>
+#include <string.h>
 #include <cuda_pipeline.h>
 
 #define COL_TILE 992          // 31 columns per lane
@@ -211,7 +212,7 @@ __global__ void k_greedy_init(GreedyArgs a, int reset_time)
         if (a.row_bad) a.row_bad[o] = 0;
         a.short_cnt[o] = 0;
         if (a.best_idx) { a.best_idx[o] = -1; a.best[o] = 256; a.second[o] = 256; }
-        if (a.need_list) {
+        if (a.need_list || a.row_need) {
             // Work lists of the batch path's pass 2.  A row that is the map point of pass-1 row `pr`
             // (src/pnpmatch.cc:167: the same mappoint object, hence the same frozen m_descriptor in both passes) is
             // dropped when pass 1 matched it; otherwise, if the two descriptors really are equal, its distances
@@ -232,7 +233,8 @@ __global__ void k_greedy_init(GreedyArgs a, int reset_time)
                     }
                 }
             }
-            if (live) {
+            if (a.row_need) a.row_need[o] = live ? 1 : 0;          // tensor-core pass 2: every live row is scanned
+            else if (live) {
                 if (reuse >= 0) a.reuse_list[ro + atomicAdd(a.list_cnt + 2 * f + 1, 1)] = i | (reuse << 16);
                 else a.need_list[ro + atomicAdd(a.list_cnt + 2 * f, 1)] = i;
             }
@@ -724,7 +726,7 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(GreedyArgs a, int max_c
     }
     if (tid == 0) s_novf = 0;
 
-    const int *mpr = a.need_list ? nullptr : map_prev_of(a, f);   // with work lists, rows pass 1 matched keep a zero count
+    const int *mpr = (a.need_list || a.row_need) ? nullptr : map_prev_of(a, f);   // with work lists, rows pass 1 matched keep a zero count
     auto row_size = [&](int r) -> int {   // 0 = cannot claim, else min(cnt, CAP+1)
         if (r >= M) return 0;
         const int c = a.short_cnt[ro + r];
@@ -1190,6 +1192,30 @@ __global__ void __launch_bounds__(M_THREADS) k_scores_m(PairArgs p)
     }
 }
 
+// Tensor-core pass 2: the lists TC_SHORT wrote (ascending column, d < 60) are pruned exactly as k_shortlist prunes its own.
+__global__ void __launch_bounds__(M_THREADS) k_prune_lists(GreedyArgs a)
+{
+    const int f = blockIdx.y;
+    const int M = set_count(a.rows, f);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t ro = (size_t)f * a.rows.stride_rows;
+    for (int r = blockIdx.x * M_WARPS + warp; r < M; r += gridDim.x * M_WARPS) {
+        const int c = a.short_cnt[ro + r];
+        if (c == 0 || c > SVO_SHORT_CAP) continue;       // warp-uniform
+        const int n = prune_list(a, ro + r, c, lane);
+        if (lane == 0) a.short_cnt[ro + r] = n;
+    }
+}
+
+void launch_prune_lists(const GreedyArgs &a, int nframes, cudaStream_t st, long long *launches)
+{
+    const int maxM = a.rows.count ? a.rows.stride_rows : a.rows.fixed_count;
+    if (maxM <= 0 || nframes <= 0) return;
+    const int gx = (maxM + M_WARPS - 1) / M_WARPS;
+    k_prune_lists<<<dim3(gx < 64 ? gx : 64, nframes), M_THREADS, 0, st>>>(a);
+    ++*launches;
+}
+
 static int g_resolve_smem_limit = 48 * 1024;
 static int g_shortlist_smem_limit = 48 * 1024;   // dynamic shared memory of one k_shortlist CTA (two per SM)
 static int g_num_sms = 148;
@@ -1206,6 +1232,7 @@ int setup_match_attributes()
         return 1;
     g_resolve_smem_limit = 200 * 1024;
     if (cudaFuncSetAttribute(k_scores_m, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess) return 1;
+    if (setup_tc_attributes() != 0) return 1;
     return (int)cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, g_resolve_smem_limit);
 }
 
@@ -1230,7 +1257,7 @@ void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStrea
     if (maxM <= 0 || nframes <= 0) return;
     const int mx = maxM > maxN ? maxM : maxN;
     dim3 gi((mx + 255) / 256, nframes);
-    if (a.need_list) cudaMemsetAsync(a.list_cnt, 0, sizeof(int) * 2 * nframes, st);
+    if (a.need_list && !a.row_need) cudaMemsetAsync(a.list_cnt, 0, sizeof(int) * 2 * nframes, st);
     if (a.win_gather) { k_win_prepare<<<nframes, 256, 0, st>>>(a); ++*launches; }
     k_greedy_init<<<gi, 256, 0, st>>>(a, 1);
     if (a.free_col && !a.win_gather && !a.win_uvr) { k_free_cols<<<nframes, 1024, 0, st>>>(a); ++*launches; }
@@ -1245,14 +1272,23 @@ void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStrea
     const int items = nframes * ((maxM + SLN_GROUP - 1) / SLN_GROUP);
     const int gs = items < 2 * g_num_sms ? items : 2 * g_num_sms;
     if (ev0) cudaEventRecord(ev0, st);
-    if (a.win_gather) {
+    if (a.row_need) {
+        // tensor-core tiles: rows = local map (tile rows), columns = the free columns in ascending order
+        TcArgs tc;
+        memset(&tc, 0, sizeof(tc));
+        tc.A = a.rows; tc.B = a.cols; tc.g = a; tc.T = T; tc.row_need = a.row_need;
+        if (a.free_col) { tc.b_index = a.free_col; tc.b_index_cnt = a.free_cnt; tc.b_index_stride = a.cols.stride_rows; }
+        launch_tc_hamming(tc, TC_SHORT, nframes, st, launches);
+        launch_prune_lists(a, nframes, st, launches);
+        --*launches;   // the common tail below counts three launches
+    } else if (a.win_gather) {
         const int gx = (maxM + M_WARPS - 1) / M_WARPS;
         k_shortlist_win<<<dim3(gx < 160 ? gx : 160, nframes), M_THREADS, 0, st>>>(a, T);
     } else if (a.win_uvr) k_shortlist<true, false><<<gs, SLN_THREADS, sl_smem, st>>>(a, T, tile_cap, nframes);
     else if (a.free_col) k_shortlist<false, true><<<gs, SLN_THREADS, sl_smem, st>>>(a, T, tile_cap, nframes);
     else k_shortlist<false, false><<<gs, SLN_THREADS, sl_smem, st>>>(a, T, tile_cap, nframes);
     if (ev1) cudaEventRecord(ev1, st);
-    if (a.need_list && a.dmat && !a.win_gather) {
+    if (a.need_list && a.dmat && !a.win_gather && !a.row_need) {
         const int gx = (maxM + M_WARPS - 1) / M_WARPS;
         k_reuse<<<dim3(gx < 128 ? gx : 128, nframes), M_THREADS, 0, st>>>(a, T);   // warps stride over the frame's reuse list
         ++*launches;
@@ -1290,7 +1326,14 @@ void launch_pass1_fused(const PairArgs &p0, const BfArgs &b, int nframes, cudaSt
     const int max_splits = (maxM + 8 * PT_ROWS - 1) / (8 * PT_ROWS);
     splits = splits < 1 ? 1 : (splits > max_splits ? max_splits : splits);
     if (ev0) cudaEventRecord(ev0, st);
-    k_pairs<<<dim3(tiles, splits, nframes), M_THREADS, 0, st>>>(p);
+    TcArgs tc;
+    if (p.use_tc) {
+        // queries (current frame) are the tile rows, the previous frame's rows stream past them in ascending order
+        memset(&tc, 0, sizeof(tc));
+        tc.A = a.cols; tc.B = a.rows; tc.g = a; tc.T = p.T; tc.bf_key = p.bf_key;
+        launch_tc_hamming(tc, TC_PAIRS, nframes, st, launches);
+        --*launches;
+    } else k_pairs<<<dim3(tiles, splits, nframes), M_THREADS, 0, st>>>(p);
     if (ev1) cudaEventRecord(ev1, st);
     k_bf_finish<<<dim3((maxN + 255) / 256, nframes), 256, 0, st>>>(p, b);
     const int colsA = (maxN + 3) & ~3;
@@ -1304,7 +1347,11 @@ void launch_pass1_fused(const PairArgs &p0, const BfArgs &b, int nframes, cudaSt
         cudaStreamWaitEvent(st_scores, e_resolved, 0);
         sq = st_scores;
     }
-    k_scores_m<<<dim3((maxM + M_WARPS * SM_ROWS_PER_WARP - 1) / (M_WARPS * SM_ROWS_PER_WARP), nframes), M_THREADS, sm, sq>>>(p);
+    if (p.use_tc) {
+        tc.A = a.rows; tc.B = a.cols;      // previous-frame rows are the tile rows, current columns in ascending order
+        launch_tc_hamming(tc, TC_SCORES, nframes, sq, launches);
+        --*launches;
+    } else k_scores_m<<<dim3((maxM + M_WARPS * SM_ROWS_PER_WARP - 1) / (M_WARPS * SM_ROWS_PER_WARP), nframes), M_THREADS, sm, sq>>>(p);
     *launches += 5;
 }
 

@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <string>
@@ -28,7 +29,7 @@ struct FrameBufs {           // per-frame (stereo pair) device arrays
     int *p2_best_idx, *p2_best, *p2_second; uint8_t *p2_row_claimed;
     uint32_t *shortlist, *shortlist_hi; int *short_cnt;
     int *res_rows, *res_off, *res_want, *res_perm;
-    int *need_list, *reuse_list, *list_cnt;
+    int *need_list, *reuse_list, *list_cnt; uint8_t *row_need;
     uint8_t *dmat; uint32_t *bf_key; int dmat_pitch; size_t dmat_frame_stride;   // fused pass-1 front (batch path)
     float *u_right, *depth; int *match_r, *sad, *n_stereo;
     int *row_off; uint16_t *row_list; int row_list_stride;
@@ -102,6 +103,7 @@ struct svo_ctx {
     FramePtrs *sync_fp_d, *sync_fp_h;
     int *sync_str_d, *sync_str_h;
     bool profiling;
+    bool use_tc;             // tensor-core Hamming tiles in the batch matchers (default; SVO_B200_TC=0 selects the SIMT kernels)
     bool sync_have[2];
     char err[512];
 };
@@ -263,7 +265,7 @@ int alloc_frames(svo_ctx *ctx, FrameBufs &f, int nframes, int col_stride, int ro
     TRY(dalloc(ctx, &f.p2_row_claimed, R));
     TRY(dalloc(ctx, &f.shortlist, R * 32)); TRY(dalloc(ctx, &f.shortlist_hi, R * (SVO_SHORT_CAP - 32))); TRY(dalloc(ctx, &f.short_cnt, R));
     TRY(dalloc(ctx, &f.res_rows, R)); TRY(dalloc(ctx, &f.res_off, R)); TRY(dalloc(ctx, &f.res_want, R)); TRY(dalloc(ctx, &f.res_perm, R));
-    TRY(dalloc(ctx, &f.need_list, R)); TRY(dalloc(ctx, &f.reuse_list, R)); TRY(dalloc(ctx, &f.list_cnt, 2 * F));
+    TRY(dalloc(ctx, &f.need_list, R)); TRY(dalloc(ctx, &f.reuse_list, R)); TRY(dalloc(ctx, &f.list_cnt, 2 * F)); TRY(dalloc(ctx, &f.row_need, R));
     TRY(dalloc(ctx, &f.u_right, C)); TRY(dalloc(ctx, &f.depth, C)); TRY(dalloc(ctx, &f.match_r, C));
     TRY(dalloc(ctx, &f.sad, C)); TRY(dalloc(ctx, &f.n_stereo, F));
     {   // a right keypoint is a candidate for rows floor(y - r) .. ceil(y + r), r = 2 * scale[octave]
@@ -434,6 +436,7 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
             pa.g = ga;
             pa.dmat = fb.dmat + (size_t)L.frame0 * fb.dmat_frame_stride; pa.dmat_frame_stride = fb.dmat_frame_stride;
             pa.dmat_pitch = fb.dmat_pitch; pa.bf_key = fb.bf_key + (size_t)L.frame0 * K; pa.T = 0; pa.lane_cols = 0;
+            pa.use_tc = ctx->use_tc ? 1 : 0;
             // match_score (k_scores_m) feeds nothing downstream: on the side branch it runs beside pass 2
             launch_pass1_fused(pa, ba, n, st, &ctx->launches, ev ? ev[12] : nullptr, ev ? ev[13] : nullptr,
                                fork ? ss : nullptr, L.fk[4]);
@@ -450,7 +453,8 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
         ga.fp = L.d_fp; ga.use_live = 0; ga.use_map_prev = any_prev ? 1 : 0;
         ga.need_list = fb.need_list + (size_t)L.frame0 * R; ga.reuse_list = fb.reuse_list + (size_t)L.frame0 * R;
         ga.list_cnt = fb.list_cnt + 2 * (size_t)L.frame0;
-        if (fused) {
+        if (ctx->use_tc && !windowed) ga.row_need = fb.row_need + (size_t)L.frame0 * R;   // tensor-core tiles scan every live row
+        if (fused && !ga.row_need) {
             ga.dmat = fb.dmat + (size_t)L.frame0 * fb.dmat_frame_stride; ga.dmat_frame_stride = fb.dmat_frame_stride;
             ga.dmat_pitch = fb.dmat_pitch;
             ga.prev = make_set(nullptr, d_nprev, 1, R, 0);
@@ -545,6 +549,7 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
     *out = nullptr;
     svo_ctx *ctx = new svo_ctx();
     ctx->cfg = *cfg; ctx->launches = 0; ctx->profiling = false; ctx->err[0] = 0;
+    { const char *e = getenv("SVO_B200_TC"); ctx->use_tc = !(e && e[0] == '0'); }
     ctx->sync_st = nullptr; ctx->sync_have[0] = ctx->sync_have[1] = false;
     ctx->sync_stage = nullptr;
     if (ctx->cfg.max_channels == 0) ctx->cfg.max_channels = 1;
@@ -1251,6 +1256,36 @@ long long svo_debug_tap(svo_ctx *ctx, int cam, int what, int level, void *out, s
         return n;
     }
     return fail(ctx, SVO_E_INVALID, "svo_debug_tap: unknown tap %d", what);
+}
+
+int svo_debug_hamming_matrix(svo_ctx *ctx, const uint8_t *a, int na, const uint8_t *b, int nb, int32_t *dist)
+{
+    if (!ctx || na < 0 || nb < 0 || (na && !a) || (nb && !b) || !dist) return fail(ctx, SVO_E_INVALID, "svo_debug_hamming_matrix: bad argument");
+    FrameBufs &s = ctx->sb;
+    if (na > s.row_stride || nb > s.col_stride) return fail(ctx, SVO_E_CAPACITY, "svo_debug_hamming_matrix: %d x %d exceeds capacity %d", na, nb, s.col_stride);
+    if (na == 0 || nb == 0) return 0;
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = ctx->sync_st;
+    int *d_dump = nullptr;
+    const int pitch = (nb + 31) & ~31;
+    CU(cudaMalloc((void **)&d_dump, sizeof(int) * (size_t)na * pitch));
+    CU(cudaMemcpyAsync(s.map, a, (size_t)na * 32, cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(s.cols, b, (size_t)nb * 32, cudaMemcpyDefault, st));
+    TcArgs tc;
+    memset(&tc, 0, sizeof(tc));
+    tc.A = make_set(s.map, nullptr, 0, s.row_stride, na);
+    tc.B = make_set(s.cols, nullptr, 0, s.col_stride, nb);
+    tc.g.rows = tc.A; tc.g.cols = tc.B;
+    tc.dump = d_dump; tc.dump_rows = na; tc.dump_pitch = pitch;
+    launch_tc_hamming(tc, TC_DUMP, 1, st, &ctx->launches);
+    std::vector<int> h((size_t)na * pitch);
+    CU(cudaMemcpyAsync(h.data(), d_dump, sizeof(int) * h.size(), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    cudaFree(d_dump);
+    for (int i = 0; i < na; ++i)
+        for (int j = 0; j < nb; ++j) dist[(size_t)i * nb + j] = (256 - h[(size_t)i * pitch + j]) / 2;     // dot = 256 - 2 d
+    return na;
 }
 
 int svo_debug_retain_best(svo_ctx *ctx, const float *resp, int n, int n_points, int depth_limit, int32_t *idx_out)

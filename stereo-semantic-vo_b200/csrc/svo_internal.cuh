@@ -163,6 +163,8 @@ struct GreedyArgs {
     // repeating a pass-1 row (map_prev_row) reuse its distances
     int *need_list, *reuse_list;  // [frame][rows.stride_rows]
     int *list_cnt;                // [frame][2]
+    uint8_t *row_need;            // [frame][rows.stride_rows] or NULL: tensor-core pass 2 (tcham.cu) — k_greedy_init writes 1 for every row
+                                  // that is scanned instead of building the work lists
     const uint8_t *dmat; size_t dmat_frame_stride; int dmat_pitch;
     MatchSet prev;
     const uint8_t *prev_row_claimed;  // [frame][prev stride] (pass 2, with map_prev_row)
@@ -199,6 +201,7 @@ struct GreedyArgs {
 };
 void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStream_t st, long long *launches,
                    cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);   // optional events around k_shortlist
+void launch_prune_lists(const GreedyArgs &a, int nframes, cudaStream_t st, long long *launches);
 
 struct BfArgs {
     MatchSet q, t;
@@ -214,10 +217,27 @@ struct PairArgs {            // fused BF + pass-1 front of the batch path (match
     int dmat_pitch;          // bytes per matrix row, multiple of 16, >= column capacity
     uint32_t *bf_key;        // [frame][cols.stride_rows] (d << 16 | prev row) minima
     int T, lane_cols;        // filled by the launcher
+    int use_tc;              // 1: tensor-core tiles (tcham.cu) instead of k_pairs / k_scores_m; dmat is not touched
 };
 void launch_pass1_fused(const PairArgs &p, const BfArgs &b, int nframes, cudaStream_t st, long long *launches,
                         cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,   // optional events around k_pairs
                         cudaStream_t st_scores = nullptr, cudaEvent_t e_resolved = nullptr);   // k_scores_m on another stream
+// ---- tensor-core Hamming tiles (tcham.cu): tcgen05.mma.kind::i8 over +-1-expanded descriptors ----
+enum { TC_PAIRS = 0, TC_SCORES = 1, TC_SHORT = 2, TC_DUMP = 3 };
+struct TcArgs {
+    MatchSet A, B;               // A rows = tile rows (one epilogue thread each), B rows = the columns they scan in ascending order
+    GreedyArgs g;                // per-row / per-column arrays of the pass the mode serves (rows.stride_rows / cols.stride_rows give the strides)
+    int T;                       // TC_PAIRS: 15 (pass-1 candidates); TC_SHORT: 60
+    uint32_t *bf_key;            // TC_PAIRS: [frame][cols.stride_rows] (d << 16 | first minimum row) per query
+    const uint16_t *b_index;     // TC_SHORT: optional ascending list of the B rows to scan (the free columns), [frame][b_index_stride]
+    const int *b_index_cnt;      //           its length per frame
+    int b_index_stride;
+    const uint8_t *row_need;     // TC_SHORT: [frame][rows.stride_rows] 1 = the row is scanned
+    int *dump; int dump_rows, dump_pitch;   // TC_DUMP: [frame][dump_rows][dump_pitch] dot products (256 - 2 d)
+};
+void launch_tc_hamming(const TcArgs &p, int mode, int nframes, cudaStream_t st, long long *launches);
+int setup_tc_attributes();
+
 // ---- pose stage (pose.cu) ----
 struct PoseHdr { int off, n; float fx, fy, cx, cy; float Tcw[16]; };   // one problem: points [off, off + n) of the packed arrays
 struct PoseArgs {
