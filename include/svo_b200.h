@@ -295,6 +295,9 @@ int svo_debug_retain_best(svo_ctx *ctx, const float *resp, int n, int n_points, 
  * +-1-expanded descriptors): the full na x nb matrix of DescriptorDistance (src/pnpmatch.cc:14-30) values, row-major
  * into dist.  na, nb within the context's single-call capacities.  Returns na or a negative status. */
 int svo_debug_hamming_matrix(svo_ctx *ctx, const uint8_t *a, int na, const uint8_t *b, int nb, int32_t *dist);
+/* Developer tap: clock64 timeline of one CTA of each tensor-core matcher kernel of the last batch (context created
+ * with SVO_B200_TC_PROF=1 in the environment): 1024 stamps = [mode][role][64]; tools/tc_timeline.py prints them. */
+int svo_debug_tc_profile(svo_ctx *ctx, long long *stamps, int n);
 
 #ifdef __cplusplus
 }

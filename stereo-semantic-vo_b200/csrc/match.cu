@@ -1192,19 +1192,49 @@ __global__ void __launch_bounds__(M_THREADS) k_scores_m(PairArgs p)
     }
 }
 
-// Tensor-core pass 2: the lists TC_SHORT wrote (ascending column, d < 60) are pruned exactly as k_shortlist prunes its own.
+// Tensor-core pass 2: TC_SHORT leaves every row's hits (d < 60) in SVO_TC_STREAMS segments of SVO_TC_SEG slots, one per
+// contiguous column range, each ascending, with the segment lengths packed into short_cnt (one byte each).  One warp
+// per row: join the segments into one ascending list and prune it exactly as k_shortlist prunes its own
+// (see prune_list): entries that cannot influence the row's decision go, a list without any d < 30 entry is emptied.
+// A segment that overflowed makes the row an "unknown list" row (count > SVO_SHORT_CAP), which the resolver re-scans
+// exhaustively.
 __global__ void __launch_bounds__(M_THREADS) k_prune_lists(GreedyArgs a)
 {
     const int f = blockIdx.y;
     const int M = set_count(a.rows, f);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t ro = (size_t)f * a.rows.stride_rows;
-    for (int r = blockIdx.x * M_WARPS + warp; r < M; r += gridDim.x * M_WARPS) {
-        const int c = a.short_cnt[ro + r];
-        if (c == 0 || c > SVO_SHORT_CAP) continue;       // warp-uniform
-        const int n = prune_list(a, ro + r, c, lane);
-        if (lane == 0) a.short_cnt[ro + r] = n;
+    const int r = blockIdx.x * M_WARPS + warp;
+    if (r >= M) return;
+    const uint32_t packed = (uint32_t)a.short_cnt[ro + r];
+    if (packed == 0) return;                              // warp-uniform
+    constexpr int PER = SVO_TC_SEG / 32, NE = SVO_TC_STREAMS * PER;
+    uint32_t e[NE];
+    int dmax = -1;
+    bool ovf = false;
+#pragma unroll
+    for (int u = 0; u < NE; ++u) {
+        const int q = u / PER, o = (u % PER) * 32 + lane;
+        const int c = (int)((packed >> (8 * q)) & 0xffu);
+        ovf |= c > SVO_TC_SEG;
+        e[u] = o < min(c, SVO_TC_SEG) ? *short_slot(a, ro + r, q * SVO_TC_SEG + o) : 0xffffffffu;
+        const int d = (int)(e[u] >> 16);
+        if (d < 30) dmax = max(dmax, d);
     }
+    if (ovf) { if (lane == 0) a.short_cnt[ro + r] = SVO_SHORT_CAP + 1; return; }
+    dmax = __reduce_max_sync(0xffffffffu, dmax);
+    __syncwarp();
+    int n = 0;
+    if (dmax >= 0) {
+#pragma unroll
+        for (int u = 0; u < NE; ++u) {
+            const bool keep = e[u] != 0xffffffffu && (int)(e[u] >> 16) <= 2 * dmax;
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            if (keep) *short_slot(a, ro + r, n + __popc(m & ((1u << lane) - 1u))) = e[u];
+            n += __popc(m);
+        }
+    }
+    if (lane == 0) a.short_cnt[ro + r] = n;
 }
 
 void launch_prune_lists(const GreedyArgs &a, int nframes, cudaStream_t st, long long *launches)
@@ -1212,7 +1242,7 @@ void launch_prune_lists(const GreedyArgs &a, int nframes, cudaStream_t st, long 
     const int maxM = a.rows.count ? a.rows.stride_rows : a.rows.fixed_count;
     if (maxM <= 0 || nframes <= 0) return;
     const int gx = (maxM + M_WARPS - 1) / M_WARPS;
-    k_prune_lists<<<dim3(gx < 64 ? gx : 64, nframes), M_THREADS, 0, st>>>(a);
+    k_prune_lists<<<dim3(gx, nframes), M_THREADS, 0, st>>>(a);
     ++*launches;
 }
 
@@ -1275,9 +1305,25 @@ void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStrea
     if (a.row_need) {
         // tensor-core tiles: rows = local map (tile rows), columns = the free columns in ascending order
         TcArgs tc;
-        memset(&tc, 0, sizeof(tc));
-        tc.A = a.rows; tc.B = a.cols; tc.g = a; tc.T = T; tc.row_need = a.row_need;
-        if (a.free_col) { tc.b_index = a.free_col; tc.b_index_cnt = a.free_cnt; tc.b_index_stride = a.cols.stride_rows; }
+        TcExpandArgs ex;
+        memset(&tc, 0, sizeof(tc)); memset(&ex, 0, sizeof(ex));
+        ex.set = a.rows; ex.img = a.img_rows; ex.img_frame_stride = a.img_rows_stride;
+        launch_tc_expand(ex, nframes, st, launches);
+        tc.A = a.rows; tc.B = a.cols; tc.g = a; tc.T = T; tc.row_need = a.row_need; tc.prof = a.tc_prof;
+        tc.a_img = a.img_rows; tc.a_img_frame_stride = a.img_rows_stride;
+        if (a.free_col) {   // the columns pass 1 left free, gathered in ascending order
+            ex.set = a.cols; ex.index = a.free_col; ex.index_cnt = a.free_cnt; ex.index_stride = a.cols.stride_rows;
+            ex.img = a.img_free; ex.img_frame_stride = a.img_free_stride;
+            launch_tc_expand(ex, nframes, st, launches);
+            tc.b_index = a.free_col; tc.b_index_cnt = a.free_cnt; tc.b_index_stride = a.cols.stride_rows;
+            tc.b_img = a.img_free; tc.b_img_frame_stride = a.img_free_stride;
+        } else {
+            if (!a.img_cols_ready) {
+                ex.set = a.cols; ex.img = a.img_cols; ex.img_frame_stride = a.img_cols_stride;
+                launch_tc_expand(ex, nframes, st, launches);
+            }
+            tc.b_img = a.img_cols; tc.b_img_frame_stride = a.img_cols_stride;
+        }
         launch_tc_hamming(tc, TC_SHORT, nframes, st, launches);
         launch_prune_lists(a, nframes, st, launches);
         --*launches;   // the common tail below counts three launches
@@ -1330,7 +1376,15 @@ void launch_pass1_fused(const PairArgs &p0, const BfArgs &b, int nframes, cudaSt
     if (p.use_tc) {
         // queries (current frame) are the tile rows, the previous frame's rows stream past them in ascending order
         memset(&tc, 0, sizeof(tc));
-        tc.A = a.cols; tc.B = a.rows; tc.g = a; tc.T = p.T; tc.bf_key = p.bf_key;
+        TcExpandArgs ex;
+        memset(&ex, 0, sizeof(ex));
+        ex.set = a.cols; ex.img = a.img_cols; ex.img_frame_stride = a.img_cols_stride;
+        launch_tc_expand(ex, nframes, st, launches);
+        ex.set = a.rows; ex.img = a.img_rows; ex.img_frame_stride = a.img_rows_stride;
+        launch_tc_expand(ex, nframes, st, launches);
+        tc.A = a.cols; tc.B = a.rows; tc.g = a; tc.T = p.T; tc.bf_key = p.bf_key; tc.prof = a.tc_prof;
+        tc.a_img = a.img_cols; tc.a_img_frame_stride = a.img_cols_stride;
+        tc.b_img = a.img_rows; tc.b_img_frame_stride = a.img_rows_stride;
         launch_tc_hamming(tc, TC_PAIRS, nframes, st, launches);
         --*launches;
     } else k_pairs<<<dim3(tiles, splits, nframes), M_THREADS, 0, st>>>(p);
@@ -1349,6 +1403,8 @@ void launch_pass1_fused(const PairArgs &p0, const BfArgs &b, int nframes, cudaSt
     }
     if (p.use_tc) {
         tc.A = a.rows; tc.B = a.cols;      // previous-frame rows are the tile rows, current columns in ascending order
+        tc.a_img = a.img_rows; tc.a_img_frame_stride = a.img_rows_stride;
+        tc.b_img = a.img_cols; tc.b_img_frame_stride = a.img_cols_stride;
         launch_tc_hamming(tc, TC_SCORES, nframes, sq, launches);
         --*launches;
     } else k_scores_m<<<dim3((maxM + M_WARPS * SM_ROWS_PER_WARP - 1) / (M_WARPS * SM_ROWS_PER_WARP), nframes), M_THREADS, sm, sq>>>(p);

@@ -30,6 +30,7 @@ struct FrameBufs {           // per-frame (stereo pair) device arrays
     uint32_t *shortlist, *shortlist_hi; int *short_cnt;
     int *res_rows, *res_off, *res_want, *res_perm;
     int *need_list, *reuse_list, *list_cnt; uint8_t *row_need;
+    uint8_t *img_cur, *img_prev, *img_map, *img_free; size_t img_col_stride, img_row_stride;   // tensor-core operand images (tcham.cu)
     uint8_t *dmat; uint32_t *bf_key; int dmat_pitch; size_t dmat_frame_stride;   // fused pass-1 front (batch path)
     float *u_right, *depth; int *match_r, *sad, *n_stereo;
     int *row_off; uint16_t *row_list; int row_list_stride;
@@ -103,6 +104,7 @@ struct svo_ctx {
     FramePtrs *sync_fp_d, *sync_fp_h;
     int *sync_str_d, *sync_str_h;
     bool profiling;
+    long long *tc_prof;      // in-kernel timeline of the tensor-core matchers (SVO_B200_TC_PROF=1), else NULL
     bool use_tc;             // tensor-core Hamming tiles in the batch matchers (default; SVO_B200_TC=0 selects the SIMT kernels)
     bool sync_have[2];
     char err[512];
@@ -275,6 +277,12 @@ int alloc_frames(svo_ctx *ctx, FrameBufs &f, int nframes, int col_stride, int ro
     }
     TRY(dalloc(ctx, &f.row_off, F * (ctx->g.H + 1))); TRY(dalloc(ctx, &f.row_list, F * f.row_list_stride));
     TRY(dalloc(ctx, &f.params, 4 * F));
+    // operand images of the tensor-core matchers: whole tiles of 128 descriptors x 256 int8
+    f.img_col_stride = (size_t)((col_stride + 127) / 128) * SVO_TC_TILE_BYTES;
+    f.img_row_stride = (size_t)((row_stride + 127) / 128) * SVO_TC_TILE_BYTES;
+    TRY(dalloc(ctx, &f.img_cur, F * f.img_col_stride)); TRY(dalloc(ctx, &f.img_map, F * f.img_row_stride));
+    f.img_prev = f.img_free = nullptr;
+    if (!sync_extras) { TRY(dalloc(ctx, &f.img_prev, F * f.img_row_stride)); TRY(dalloc(ctx, &f.img_free, F * f.img_col_stride)); }
     f.cols = nullptr; f.win = f.cur_xy = f.row_xy = nullptr; f.boxes = nullptr; f.F = nullptr;
     f.dmat = nullptr; f.bf_key = nullptr; f.dmat_pitch = 0; f.dmat_frame_stride = 0;
     f.cell_off = nullptr; f.cell_list = nullptr;
@@ -407,6 +415,7 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
     GreedyArgs ga;
     memset(&ga, 0, sizeof(ga));
     ga.cols = cur;
+    ga.tc_prof = ctx->tc_prof;
     ga.claimed = fb.claimed + (size_t)L.frame0 * K; ga.claim_row = fb.claim_row + (size_t)L.frame0 * K;
     ga.claim_time = fb.claim_time + (size_t)L.frame0 * K;
     ga.shortlist = fb.shortlist + (size_t)L.frame0 * R * 32; ga.shortlist_hi = fb.shortlist_hi + (size_t)L.frame0 * R * (SVO_SHORT_CAP - 32);
@@ -430,6 +439,8 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
         // positions are the extractor's output
         ga.row_bad = fb.p1_row_bad + (size_t)L.frame0 * R; ga.use_veto = veto ? 1 : 0;
         ga.kp = b.kp + (size_t)L.slot0 * g.kp_cap; ga.kp_frame_stride = 2 * (size_t)g.kp_cap;
+        ga.img_rows = fb.img_prev + (size_t)L.frame0 * fb.img_row_stride; ga.img_rows_stride = fb.img_row_stride;
+        ga.img_cols = fb.img_cur + (size_t)L.frame0 * fb.img_col_stride; ga.img_cols_stride = fb.img_col_stride;
         if (fused) {
             // BF (cur -> prev) and greedy pass 1 (prev rows over cur columns) share one distance matrix
             PairArgs pa;
@@ -453,7 +464,13 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
         ga.fp = L.d_fp; ga.use_live = 0; ga.use_map_prev = any_prev ? 1 : 0;
         ga.need_list = fb.need_list + (size_t)L.frame0 * R; ga.reuse_list = fb.reuse_list + (size_t)L.frame0 * R;
         ga.list_cnt = fb.list_cnt + 2 * (size_t)L.frame0;
-        if (ctx->use_tc && !windowed) ga.row_need = fb.row_need + (size_t)L.frame0 * R;   // tensor-core tiles scan every live row
+        if (ctx->use_tc && !windowed) {   // tensor-core tiles scan every live row
+            ga.row_need = fb.row_need + (size_t)L.frame0 * R;
+            ga.img_rows = fb.img_map + (size_t)L.frame0 * fb.img_row_stride; ga.img_rows_stride = fb.img_row_stride;
+            ga.img_cols = fb.img_cur + (size_t)L.frame0 * fb.img_col_stride; ga.img_cols_stride = fb.img_col_stride;
+            ga.img_free = fb.img_free + (size_t)L.frame0 * fb.img_col_stride; ga.img_free_stride = fb.img_col_stride;
+            ga.img_cols_ready = (any_prev && fused) ? 1 : 0;
+        }
         if (fused && !ga.row_need) {
             ga.dmat = fb.dmat + (size_t)L.frame0 * fb.dmat_frame_stride; ga.dmat_frame_stride = fb.dmat_frame_stride;
             ga.dmat_pitch = fb.dmat_pitch;
@@ -550,6 +567,7 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
     svo_ctx *ctx = new svo_ctx();
     ctx->cfg = *cfg; ctx->launches = 0; ctx->profiling = false; ctx->err[0] = 0;
     { const char *e = getenv("SVO_B200_TC"); ctx->use_tc = !(e && e[0] == '0'); }
+    ctx->tc_prof = nullptr;
     ctx->sync_st = nullptr; ctx->sync_have[0] = ctx->sync_have[1] = false;
     ctx->sync_stage = nullptr;
     if (ctx->cfg.max_channels == 0) ctx->cfg.max_channels = 1;
@@ -620,6 +638,7 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
     if (setup_fast_attributes(g) != 0 || setup_match_attributes() != 0 || setup_describe() != 0 || setup_select_attributes() != 0 ||
         setup_pose() != 0 || setup_octree_attributes() != 0)
         return fail(ctx, SVO_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (getenv("SVO_B200_TC_PROF")) TRY(dalloc(ctx, &ctx->tc_prof, 4 * 256));
     CU(cudaStreamCreateWithFlags(&ctx->sync_st, cudaStreamNonBlocking));
     ctx->stage_img_bytes = (size_t)g.H * ((size_t)g.W * c.max_channels + 256);
     if (c.max_channels == 3) {
@@ -1276,6 +1295,13 @@ int svo_debug_hamming_matrix(svo_ctx *ctx, const uint8_t *a, int na, const uint8
     tc.A = make_set(s.map, nullptr, 0, s.row_stride, na);
     tc.B = make_set(s.cols, nullptr, 0, s.col_stride, nb);
     tc.g.rows = tc.A; tc.g.cols = tc.B;
+    TcExpandArgs ex;
+    memset(&ex, 0, sizeof(ex));
+    ex.set = tc.A; ex.img = s.img_map; ex.img_frame_stride = s.img_row_stride;
+    launch_tc_expand(ex, 1, st, &ctx->launches);
+    ex.set = tc.B; ex.img = s.img_cur; ex.img_frame_stride = s.img_col_stride;
+    launch_tc_expand(ex, 1, st, &ctx->launches);
+    tc.a_img = s.img_map; tc.a_img_frame_stride = s.img_row_stride; tc.b_img = s.img_cur; tc.b_img_frame_stride = s.img_col_stride;
     tc.dump = d_dump; tc.dump_rows = na; tc.dump_pitch = pitch;
     launch_tc_hamming(tc, TC_DUMP, 1, st, &ctx->launches);
     std::vector<int> h((size_t)na * pitch);
@@ -1286,6 +1312,17 @@ int svo_debug_hamming_matrix(svo_ctx *ctx, const uint8_t *a, int na, const uint8
     for (int i = 0; i < na; ++i)
         for (int j = 0; j < nb; ++j) dist[(size_t)i * nb + j] = (256 - h[(size_t)i * pitch + j]) / 2;     // dot = 256 - 2 d
     return na;
+}
+
+int svo_debug_tc_profile(svo_ctx *ctx, long long *stamps, int n)
+{
+    if (!ctx || !stamps || n < 0) return fail(ctx, SVO_E_INVALID, "svo_debug_tc_profile: bad argument");
+    if (!ctx->tc_prof) return fail(ctx, SVO_E_INVALID, "svo_debug_tc_profile: create the context with SVO_B200_TC_PROF=1 in the environment");
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaDeviceSynchronize());
+    const int m = n < 1024 ? n : 1024;
+    CU(cudaMemcpy(stamps, ctx->tc_prof, sizeof(long long) * m, cudaMemcpyDeviceToHost));
+    return m;
 }
 
 int svo_debug_retain_best(svo_ctx *ctx, const float *resp, int n, int n_points, int depth_limit, int32_t *idx_out)

@@ -19,6 +19,9 @@
 #define SVO_SHORT_CAP 128      // short-list entries per greedy row before the full-scan path
 #define SVO_STRIDE_BGR (1 << 30)  // flag in a per-image stride word: the source is interleaved BGR
 #define SVO_WIN_CELLS 4096     // most cells of the keypoint grid used by the windowed pass 2
+#define SVO_TC_TILE_BYTES 32768  // one tensor-core operand image: 128 descriptors x 256 int8 (tcham.cu)
+#define SVO_TC_STREAMS 4       // column ranges (streams) a tensor-core CTA splits a row's scan into (tcham.cu)
+#define SVO_TC_SEG (SVO_SHORT_CAP / SVO_TC_STREAMS)   // TC_SHORT: short-list slots of each range of a row
 #define SVO_STATUS_OVERFLOW 1  // bit set in the per-image status word on a capacity overflow
 #define SVO_STATUS_DEPTH 2     // introselect reached its depth limit (heap-select path ran)
 
@@ -165,6 +168,11 @@ struct GreedyArgs {
     int *list_cnt;                // [frame][2]
     uint8_t *row_need;            // [frame][rows.stride_rows] or NULL: tensor-core pass 2 (tcham.cu) — k_greedy_init writes 1 for every row
                                   // that is scanned instead of building the work lists
+    // tensor-core path: operand images (tcham.cu) of the row set, of the column set and of the gathered free columns
+    uint8_t *img_rows, *img_cols, *img_free;
+    size_t img_rows_stride, img_cols_stride, img_free_stride;
+    int img_cols_ready;           // the column image was already written by an earlier launcher of this batch
+    long long *tc_prof;           // optional in-kernel timeline buffer (TcArgs.prof)
     const uint8_t *dmat; size_t dmat_frame_stride; int dmat_pitch;
     MatchSet prev;
     const uint8_t *prev_row_claimed;  // [frame][prev stride] (pass 2, with map_prev_row)
@@ -224,17 +232,28 @@ void launch_pass1_fused(const PairArgs &p, const BfArgs &b, int nframes, cudaStr
                         cudaStream_t st_scores = nullptr, cudaEvent_t e_resolved = nullptr);   // k_scores_m on another stream
 // ---- tensor-core Hamming tiles (tcham.cu): tcgen05.mma.kind::i8 over +-1-expanded descriptors ----
 enum { TC_PAIRS = 0, TC_SCORES = 1, TC_SHORT = 2, TC_DUMP = 3 };
+struct TcExpandArgs {            // descriptor set -> operand images ([frame][tile of 128 rows][SVO_TC_TILE_BYTES])
+    MatchSet set;
+    const uint16_t *index;       // optional ascending gather list ([frame][index_stride]) and its length per frame
+    const int *index_cnt;
+    int index_stride;
+    uint8_t *img; size_t img_frame_stride;
+};
 struct TcArgs {
     MatchSet A, B;               // A rows = tile rows (one epilogue thread each), B rows = the columns they scan in ascending order
+    const uint8_t *a_img, *b_img;            // their operand images
+    size_t a_img_frame_stride, b_img_frame_stride;
     GreedyArgs g;                // per-row / per-column arrays of the pass the mode serves (rows.stride_rows / cols.stride_rows give the strides)
     int T;                       // TC_PAIRS: 15 (pass-1 candidates); TC_SHORT: 60
     uint32_t *bf_key;            // TC_PAIRS: [frame][cols.stride_rows] (d << 16 | first minimum row) per query
-    const uint16_t *b_index;     // TC_SHORT: optional ascending list of the B rows to scan (the free columns), [frame][b_index_stride]
+    const uint16_t *b_index;     // TC_SHORT: the ascending list of original column indices b_img was gathered with ([frame][b_index_stride])
     const int *b_index_cnt;      //           its length per frame
     int b_index_stride;
     const uint8_t *row_need;     // TC_SHORT: [frame][rows.stride_rows] 1 = the row is scanned
     int *dump; int dump_rows, dump_pitch;   // TC_DUMP: [frame][dump_rows][dump_pitch] dot products (256 - 2 d)
+    long long *prof;             // optional clock64 timeline of CTA (0, 0): [mode][4 roles][64] (svo_debug_tc_profile)
 };
+void launch_tc_expand(const TcExpandArgs &e, int nframes, cudaStream_t st, long long *launches);
 void launch_tc_hamming(const TcArgs &p, int mode, int nframes, cudaStream_t st, long long *launches);
 int setup_tc_attributes();
 

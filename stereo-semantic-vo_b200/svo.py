@@ -74,7 +74,7 @@ EXPORTS = ["svo_default_config", "svo_version", "svo_create", "svo_destroy", "sv
            "svo_batch_submit", "svo_batch_wait", "svo_batch_result", "svo_alloc_pinned", "svo_free_pinned",
            "svo_alloc_device", "svo_free_device", "svo_copy_to_device", "svo_launch_count", "svo_batch_stage_ms",
            "svo_set_profiling", "svo_lane_stream", "svo_debug_tap", "svo_debug_retain_best",
-           "svo_pnp_ransac", "svo_pose_optimize", "svo_debug_hamming_matrix"]
+           "svo_pnp_ransac", "svo_pose_optimize", "svo_debug_hamming_matrix", "svo_debug_tc_profile"]
 
 _lib = None
 
@@ -126,6 +126,7 @@ def load():
     L.svo_pnp_ransac.argtypes = [C.c_void_p, C.POINTER(PoseProblem), C.c_int, C.c_int, C.c_float, C.c_uint32, C.c_int,
                                  C.POINTER(PnpResult), C.c_void_p]
     L.svo_pose_optimize.argtypes = [C.c_void_p, C.POINTER(PoseProblem), C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.svo_debug_tc_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.svo_debug_hamming_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     _lib = L
     return L
@@ -430,6 +431,11 @@ class Context:
         out = np.zeros((len(a), len(b)), np.int32)
         self._chk(self.lib.svo_debug_hamming_matrix(self.h, _p(a), len(a), _p(b), len(b), _p(out)))
         return out
+
+    def tc_profile(self):
+        st = np.zeros(1024, np.int64)
+        self._chk(self.lib.svo_debug_tc_profile(self.h, _p(st), 1024))
+        return st.reshape(4, 4, 64)
 
     def retain_best(self, resp, n_points, depth_limit=-1):
         resp = np.ascontiguousarray(resp, np.float32)
