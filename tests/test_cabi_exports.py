@@ -86,3 +86,22 @@ def test_binding_structs_match_the_header_layout(tmp_path):
             assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
     kp = svo.KP_DTYPE
     assert kp.itemsize == 24 and [kp.fields[n][1] for n in ("x", "y", "size", "angle", "response", "octave")] == [0, 4, 8, 12, 16, 20]
+
+
+def test_cmake_build_exports_the_same_abi(tmp_path):
+    """The repo's CMakeLists.txt (LANGUAGES CXX CUDA, CMAKE_CUDA_ARCHITECTURES 100a, --fmad=false: what replaces the
+    reference's FindCUDA / sm_35 / -use_fast_math block, CMakeLists.txt:30-33) builds the same library: every symbol of
+    include/svo_b200.h is exported, and the compile commands carry sm_100a and nothing else."""
+    import shutil
+    import subprocess
+    import svo
+    if not shutil.which("cmake") or not shutil.which("ninja"):
+        pytest.skip("cmake / ninja not installed")
+    bdir = tmp_path / "b"
+    subprocess.check_call(["cmake", "-S", ROOT, "-B", str(bdir), "-G", "Ninja"], stdout=subprocess.DEVNULL)
+    ninja = open(bdir / "build.ninja").read()
+    assert "sm_100a" in ninja and "sm_35" not in ninja and "use_fast_math" not in ninja and "--fmad=false" in ninja
+    subprocess.check_call(["cmake", "--build", str(bdir), "--target", "svo_b200"], stdout=subprocess.DEVNULL)
+    lib = C.CDLL(str(bdir / "libsvo_b200.so"))
+    for name in svo.EXPORTS:
+        assert hasattr(lib, name), name
