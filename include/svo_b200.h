@@ -63,6 +63,10 @@ typedef struct svo_config {
     void *stream;        /* optional cudaStream_t for lane 0 (NULL: the context creates its own)  */
     int max_channels;    /* 1 (default) or 3: 3 sizes the input staging for interleaved BGR images  */
     int distribution;    /* SVO_DIST_RETAIN_BEST (default, cv::ORB parity) or SVO_DIST_OCTREE (opt-in)  */
+    int skip_match_score;/* 1: the batch path does not compute CurrentFrame->match_score (src/pnpmatch.cc:99:
+                            p1_best_idx / p1_best / p1_second come back NULL).  Nothing in the reference reads
+                            match_score (its only consumer, src/Optimizer.cc:56, is commented out); claims and
+                            every other output are unchanged.  Default 0: computed, like the reference.     */
 } svo_config;
 
 /* Keypoint selection per pyramid level.
@@ -151,6 +155,16 @@ int svo_match_greedy(svo_ctx *ctx, const uint8_t *rows, int M, const uint8_t *cu
                      const float *win_uvr, const float *cur_xy,
                      const svo_veto *veto, uint8_t *row_bad);
 
+/* OPT-IN projection windows (north_star's "projection-guided" matching; the reference computes Velocity,
+ * src/Tracking.cc:99-106, and never applies it, src/pnpmatch.cc:53-57): map point i at world position xyz[i] is
+ * transformed with the predicted pose Tcw (row-major 4x4, Velocity * LastFrame.Tcw), projected with (fx, fy, cx, cy)
+ * and gets the window (u, v, r = th * scale[octave[i]]) that svo_match_greedy / svo_frame_in.map_win_uvr consume;
+ * points behind the camera or outside the image get r = -1 (matches nothing).  ORB-SLAM2's SearchByProjection form
+ * (th = 7 for stereo); float32, every operation rounded separately in a fixed order.  octave may be NULL (level 0).
+ * Host or device pointers.  Returns n or a negative status. */
+int svo_project_map(svo_ctx *ctx, const float *xyz, const int32_t *octave, int n, const float *Tcw,
+                    float fx, float fy, float cx, float cy, float th, float *uvr_out);
+
 /* frame::disp2Depth (src/frame.cc:140-164): depth = bf/disp where disp != 0 else -1. */
 int svo_disp2depth(svo_ctx *ctx, const float *disp, float *depth, size_t n, float bf);
 
@@ -228,6 +242,13 @@ typedef struct svo_frame_in {
     int n_boxes;
     const double *F;             /* 3x3 row-major fundamental matrix (findFundamentalMat, :336)         */
     const float *prev_xy;        /* 2 x n_prev: LastFrame.keypoints_l[i].pt                              */
+    /* OPT-IN, changes results: the projection windows of pass 2 computed on the device (svo_project_map's
+       arithmetic) instead of given as map_win_uvr: world positions and octaves of the local-map rows, the
+       predicted pose and the intrinsics.  Used when map_xyz and Tcw_pred are given and map_win_uvr is NULL. */
+    const float *map_xyz;        /* 3 x n_map                                                            */
+    const int32_t *map_octave;   /* n_map (may be NULL: level 0)                                         */
+    const float *Tcw_pred;       /* 16, row-major: Velocity * LastFrame.Tcw (src/Tracking.cc:99-106)     */
+    float fx, fy, cx, cy, proj_th;   /* K and the window scale (ORB-SLAM2: 7 for stereo)                 */
 } svo_frame_in;
 
 typedef struct svo_frame_out {

@@ -210,6 +210,18 @@ def match_greedy(rows, cur, mode, claimed=None, row_live=None, row_base=0, claim
     return dict(best_idx=bi, best=b, second=s, row_claimed=rc, claimed=claimed, claim_row=claim_row, row_bad=bad)
 
 
+def project_map(xyz, octave, Tcw, K4, W, H, th=7.0, nlevels=8, scale=1.2):
+    """Projection windows (u, v, r) of map points under the predicted pose (opt-in pass-2 mode; ORB-SLAM2 SearchByProjection)."""
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    octave = np.ascontiguousarray(octave, np.int32)
+    T = np.ascontiguousarray(Tcw, np.float32).reshape(16)
+    _, _, ls, _ = geometry(W, H, nlevels, scale, 500)
+    out = np.zeros((len(xyz), 3), np.float32)
+    fx, fy, cx, cy = [C.c_float(float(v)) for v in K4]
+    lib().svo_o_project_map(_p(xyz), _p(octave), len(xyz), _p(T), fx, fy, cx, cy, W, H, C.c_float(th), _p(ls), nlevels, _p(out))
+    return out
+
+
 def disp2depth(disp, bf):
     disp = np.ascontiguousarray(disp, np.float32)
     out = np.empty_like(disp)

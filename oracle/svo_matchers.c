@@ -144,3 +144,35 @@ void svo_o_disp2depth(const float *disp, float *depth, size_t n, float bf)
     for (size_t i = 0; i < n; ++i) depth[i] = disp[i] != 0.f ? bf / disp[i] : -1.f;
 }
 
+
+/* Projection windows for the opt-in "projection-guided" pass 2 (north_star).  The
+ * reference computes the motion model (Velocity = Tcw * LastTwc, src/Tracking.cc:99-106) but never applies it
+ * (src/pnpmatch.cc:53 is commented out, Rcw/tcw are read and unused, :56-57), so this stage follows ORB-SLAM2's
+ * SearchByProjection, the code the reference descends from: a map point X is transformed with the predicted pose
+ * Tcw (row-major 4x4: Velocity * LastFrame.Tcw), projected with the pinhole intrinsics, and gets a square search
+ * window of half-size th * scale[octave] around (u, v).  Points behind the camera or outside the image get r = -1
+ * (a window nothing falls into).  float32 throughout, every operation rounded separately, in exactly this order.
+ * DEFINED HERE (parity unpinned: there is no reference code to compare with). */
+void svo_o_project_map(const float *xyz, const int32_t *octave, int n, const float *Tcw, float fx, float fy, float cx, float cy,
+                       int W, int H, float th, const float *lscale, int nlevels, float *uvr)
+{
+    for (int i = 0; i < n; ++i) {
+        const float X = xyz[3 * i], Y = xyz[3 * i + 1], Z = xyz[3 * i + 2];
+        float xc = Tcw[0] * X; xc = xc + Tcw[1] * Y; xc = xc + Tcw[2] * Z; xc = xc + Tcw[3];
+        float yc = Tcw[4] * X; yc = yc + Tcw[5] * Y; yc = yc + Tcw[6] * Z; yc = yc + Tcw[7];
+        float zc = Tcw[8] * X; zc = zc + Tcw[9] * Y; zc = zc + Tcw[10] * Z; zc = zc + Tcw[11];
+        float u = 0.f, v = 0.f, r = -1.f;
+        if (zc > 0.f) {
+            const float invz = 1.0f / zc;
+            float pu = fx * xc; pu = pu * invz; pu = pu + cx;
+            float pv = fy * yc; pv = pv * invz; pv = pv + cy;
+            if (pu >= 0.f && pu < (float)W && pv >= 0.f && pv < (float)H) {
+                int o = octave ? octave[i] : 0;
+                if (o < 0) o = 0;
+                if (o > nlevels - 1) o = nlevels - 1;
+                u = pu; v = pv; r = th * lscale[o];
+            }
+        }
+        uvr[3 * i] = u; uvr[3 * i + 1] = v; uvr[3 * i + 2] = r;
+    }
+}

@@ -66,6 +66,8 @@ void svo_o_match_greedy_veto(const uint8_t *rows, int M, const uint8_t *cur, int
                              const float *win_uvr, const float *cur_xy,
                              const int32_t *boxes, int n_boxes, const double *F, const float *row_xy,
                              const float *vcur_xy, uint8_t *row_bad);
+void svo_o_project_map(const float *xyz, const int32_t *octave, int n, const float *Tcw, float fx, float fy, float cx, float cy,
+                       int W, int H, float th, const float *lscale, int nlevels, float *uvr);
 void svo_o_disp2depth(const float *disp, float *depth, size_t n, float bf);
 int svo_o_stereo_sparse(const svo_o_keypoint *kl, const uint8_t *dl, int nl,
                         const svo_o_keypoint *kr, const uint8_t *dr, int nr,

@@ -43,9 +43,10 @@ cv::Mat eye4()
 }  // namespace
 
 // ------------------------------------------------------------------------------- mappoint
-mappoint::mappoint(cv::Mat &pos, frame *pFrame, int id) : worldpos(pos), bad(false), observation_num(0), create_id(-1)
+mappoint::mappoint(cv::Mat &pos, frame *pFrame, int id) : worldpos(pos), bad(false), observation_num(0), create_id(-1), octave(0)
 {
     pFrame->f_descriptor.row(id).copyTo(m_descriptor);
+    if (id >= 0 && id < (int)pFrame->keypoints_l.size()) octave = pFrame->keypoints_l[(size_t)id].octave;
 }
 
 void mappoint::AddObservation(frame *fm, size_t idx)
@@ -285,6 +286,9 @@ std::function<cv::Mat(const std::vector<cv::Point2f> &, const std::vector<cv::Po
 std::function<bool(const std::vector<cv::Mat> &, const std::vector<cv::Point2f> &, const cv::Mat &, cv::Mat &, int &)> pnpmatch::pnp_solver =
     pnpmatch::device_pnp;
 std::vector<unsigned char> pnpmatch::last_pnp_inliers;
+bool pnpmatch::use_projection = false;
+float pnpmatch::projection_th = 7.f;
+cv::Mat pnpmatch::predicted_Tcw;
 
 // cv::solvePnPRansac(pts3d, pts2d, K, Mat(), rvec, tvec, false, 100, 8.0, 0.99, inliers) + Rodrigues + the 4x4
 // Tcl of src/pnpmatch.cc:227-245, on the device.
@@ -439,8 +443,23 @@ int pnpmatch::match_local_map(frame *cur, std::set<mappoint *> &localmappoints)
     std::vector<uint8_t> claimed((size_t)Nc, 0), took((size_t)M, 0);
     for (int j = 0; j < Nc; ++j) claimed[(size_t)j] = cur->MapPoints[(size_t)j] ? 1 : 0;
     std::vector<int32_t> claim_row((size_t)Nc, -1);
+    std::vector<float> win, cxy;
+    if (use_projection && !predicted_Tcw.empty()) {   // opt-in: windows from the predicted pose, computed on the device
+        std::vector<float> xyz((size_t)M * 3), T(16);
+        std::vector<int32_t> oct((size_t)M);
+        for (int i = 0; i < M; ++i) {
+            for (int k = 0; k < 3; ++k) xyz[(size_t)i * 3 + k] = order[(size_t)i]->worldpos.at<float>(k, 0);
+            oct[(size_t)i] = order[(size_t)i]->octave;
+        }
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) T[(size_t)r * 4 + c] = predicted_Tcw.at<float>(r, c);
+        win.resize((size_t)M * 3); cxy.resize((size_t)Nc * 2);
+        const int pr = svo_project_map(ctx, xyz.data(), oct.data(), M, T.data(), cur->fx, cur->fy, cur->cx, cur->cy, projection_th, win.data());
+        if (pr < 0) die(ctx, "svo_project_map", pr);
+        for (int j = 0; j < Nc; ++j) { cxy[2 * (size_t)j] = cur->keypoints_l[(size_t)j].pt.x; cxy[2 * (size_t)j + 1] = cur->keypoints_l[(size_t)j].pt.y; }
+    }
     const int rc = svo_match_greedy(ctx, rows.data, M, cur->f_descriptor.data, Nc, SVO_GREEDY_PASS2, nullptr, claimed.data(),
-                                    claim_row.data(), 0, nullptr, nullptr, nullptr, took.data(), nullptr, nullptr, nullptr, nullptr);
+                                    claim_row.data(), 0, nullptr, nullptr, nullptr, took.data(), win.empty() ? nullptr : win.data(),
+                                    win.empty() ? nullptr : cxy.data(), nullptr, nullptr);
     if (rc < 0) die(ctx, "svo_match_greedy", rc);
     int n = 0;
     for (int j = 0; j < Nc; ++j) {
@@ -455,7 +474,17 @@ int pnpmatch::match_local_map(frame *cur, std::set<mappoint *> &localmappoints)
 
 int pnpmatch::poseEstimationPnP(frame *cur, frame &last, std::set<mappoint *> &localmappoints, cv::Mat &mVelocity, cv::Mat &K)
 {
-    (void)mVelocity;   // the reference never applies it either (src/pnpmatch.cc:53 is commented out)
+    // the reference never applies mVelocity (src/pnpmatch.cc:53 is commented out); with use_projection it predicts the pose
+    predicted_Tcw = cv::Mat();
+    if (use_projection && !mVelocity.empty() && !last.Tcw.empty()) {
+        cv::Mat T(4, 4, CV_32F, 0.0);
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) {
+            float s = 0.f;
+            for (int k = 0; k < 4; ++k) s += mVelocity.at<float>(r, k) * last.Tcw.at<float>(k, c);
+            T.at<float>(r, c) = s;
+        }
+        predicted_Tcw = T;
+    }
     cv::Mat F;
     poseEstimation2D_2D(cur, last, K, F);           // overwrites both frames' keypoints, as the reference does
     match_last_frame(cur, last, F);

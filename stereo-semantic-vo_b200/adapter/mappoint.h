@@ -17,5 +17,6 @@ public:
     bool bad;
     int observation_num;
     int create_id;
+    int octave;             // pyramid level of the keypoint the point was created from (projection windows; not in the reference)
     std::map<frame *, int> observations;
 };

@@ -33,4 +33,13 @@ public:
     static bool device_pnp(const std::vector<cv::Mat> &pts3d, const std::vector<cv::Point2f> &pts2d, const cv::Mat &K,
                            cv::Mat &Tcl, int &inliers);
     static std::vector<unsigned char> last_pnp_inliers;   // flags of the last device_pnp call, pts2d order
+
+    // OPT-IN, changes results (north_star's "projection-guided" matching; off by default = the reference's brute-force
+    // pass 2): when true, poseEstimationPnP predicts the pose as mVelocity * LastFrame.Tcw (the motion model the reference
+    // computes in Tracking::GetVelocity, src/Tracking.cc:99-106, and leaves unused, src/pnpmatch.cc:53), projects the
+    // local-map points with it on the device (svo_project_map) and pass 2 only looks inside each point's window
+    // (half-size projection_th * scale[octave]).
+    static bool use_projection;
+    static float projection_th;
+    static cv::Mat predicted_Tcw;                          // set by poseEstimationPnP, read by match_local_map
 };

@@ -477,6 +477,47 @@ __global__ void __launch_bounds__(SLN_THREADS, 2) k_shortlist(GreedyArgs a, int 
     }
 }
 
+// Projection window of one map point under the predicted pose (opt-in; ORB-SLAM2 SearchByProjection form; every
+// float32 operation rounded separately, in a fixed order, so that the CPU restatement used by the tests gives the same bits).
+__device__ __forceinline__ void project_point(const float *T, float fx, float fy, float cx, float cy, int W, int H, float th,
+                                              const float *lscale, int nlevels, float X, float Y, float Z, int octave, float *uvr)
+{
+    const float xc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], X), __fmul_rn(T[1], Y)), __fmul_rn(T[2], Z)), T[3]);
+    const float yc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[4], X), __fmul_rn(T[5], Y)), __fmul_rn(T[6], Z)), T[7]);
+    const float zc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[8], X), __fmul_rn(T[9], Y)), __fmul_rn(T[10], Z)), T[11]);
+    float u = 0.f, v = 0.f, r = -1.f;
+    if (zc > 0.f) {
+        const float invz = __fdiv_rn(1.0f, zc);
+        const float pu = __fadd_rn(__fmul_rn(__fmul_rn(fx, xc), invz), cx);
+        const float pv = __fadd_rn(__fmul_rn(__fmul_rn(fy, yc), invz), cy);
+        if (pu >= 0.f && pu < (float)W && pv >= 0.f && pv < (float)H) {
+            const int o = min(max(octave, 0), nlevels - 1);
+            u = pu; v = pv; r = __fmul_rn(th, lscale[o]);
+        }
+    }
+    uvr[0] = u; uvr[1] = v; uvr[2] = r;
+}
+
+struct ProjectArgs { const float *xyz; const int *octave; int n; float T[12]; float fx, fy, cx, cy, th; int W, H, nlevels; float lscale[SVO_MAX_LEVELS]; float *uvr; };
+__global__ void k_project(ProjectArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    project_point(a.T, a.fx, a.fy, a.cx, a.cy, a.W, a.H, a.th, a.lscale, a.nlevels, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2],
+                  a.octave ? a.octave[i] : 0, a.uvr + 3 * (size_t)i);
+}
+void launch_project(const float *xyz, const int *octave, int n, const float *Tcw12, float fx, float fy, float cx, float cy, int W, int H,
+                    float th, const float *lscale, int nlevels, float *uvr, cudaStream_t st, long long *launches)
+{
+    if (n <= 0) return;
+    ProjectArgs a;
+    a.xyz = xyz; a.octave = octave; a.n = n; a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy; a.th = th; a.W = W; a.H = H; a.nlevels = nlevels; a.uvr = uvr;
+    for (int k = 0; k < 12; ++k) a.T[k] = Tcw12[k];
+    for (int k = 0; k < SVO_MAX_LEVELS; ++k) a.lscale[k] = k < nlevels ? lscale[k] : 1.f;
+    k_project<<<(n + 255) / 256, 256, 0, st>>>(a);
+    ++*launches;
+}
+
 // ---------------------------------------------------------------------------------------
 // Batch pass 2 with projection windows (opt-in; the reference scans every column, src/pnpmatch.cc:173-190).
 // k_win_prepare, one CTA per frame: the frame's windows and the current keypoints' positions go into the
@@ -491,7 +532,13 @@ __global__ void __launch_bounds__(256) k_win_prepare(GreedyArgs a)
     const int ncell = a.ncx * a.ncy;
     const svo_keypoint *kp = a.kp + (size_t)f * a.kp_frame_stride;
     const float *win = a.fp[f].map_win;
-    for (int i = tid; i < 3 * M; i += 256) a.win_out[ro * 3 + i] = win[i];
+    if (win) { for (int i = tid; i < 3 * M; i += 256) a.win_out[ro * 3 + i] = win[i]; }
+    else {   // windows projected here from the map points' positions and the predicted pose
+        const FramePtrs &P = a.fp[f];
+        for (int i = tid; i < M; i += 256)
+            project_point(P.Tcw, P.fx, P.fy, P.cx, P.cy, a.img_w, a.img_h, P.proj_th, a.lscale, a.nlevels, P.map_xyz[3 * i], P.map_xyz[3 * i + 1],
+                          P.map_xyz[3 * i + 2], P.map_octave ? P.map_octave[i] : 0, a.win_out + (ro + i) * 3);
+    }
     for (int c = tid; c <= ncell; c += 256) cell[c] = 0;
     __syncthreads();
     auto cell_of = [&](float x, float y) {
@@ -1401,6 +1448,7 @@ void launch_pass1_fused(const PairArgs &p0, const BfArgs &b, int nframes, cudaSt
         cudaStreamWaitEvent(st_scores, e_resolved, 0);
         sq = st_scores;
     }
+    if (p.skip_scores) { *launches += 4; return; }
     if (p.use_tc) {
         tc.A = a.rows; tc.B = a.cols;      // previous-frame rows are the tile rows, current columns in ascending order
         tc.a_img = a.img_rows; tc.a_img_frame_stride = a.img_rows_stride;

@@ -447,13 +447,13 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
             pa.g = ga;
             pa.dmat = fb.dmat + (size_t)L.frame0 * fb.dmat_frame_stride; pa.dmat_frame_stride = fb.dmat_frame_stride;
             pa.dmat_pitch = fb.dmat_pitch; pa.bf_key = fb.bf_key + (size_t)L.frame0 * K; pa.T = 0; pa.lane_cols = 0;
-            pa.use_tc = ctx->use_tc ? 1 : 0;
+            pa.use_tc = ctx->use_tc ? 1 : 0; pa.skip_scores = ctx->cfg.skip_match_score ? 1 : 0;
             // match_score (k_scores_m) feeds nothing downstream: on the side branch it runs beside pass 2
             launch_pass1_fused(pa, ba, n, st, &ctx->launches, ev ? ev[12] : nullptr, ev ? ev[13] : nullptr,
                                fork ? ss : nullptr, L.fk[4]);
         } else {
             launch_bf(ba, n, st, &ctx->launches);
-            launch_greedy(ga, n, true, st, &ctx->launches);
+            launch_greedy(ga, n, !ctx->cfg.skip_match_score, st, &ctx->launches);
         }
     }
     if (any_map) {
@@ -486,6 +486,8 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
             int shift = 5;
             while (((g.W >> shift) + 1) * ((g.H >> shift) + 1) > SVO_WIN_CELLS) ++shift;
             ga.win_gather = 1; ga.cell_shift = shift; ga.ncx = (g.W >> shift) + 1; ga.ncy = (g.H >> shift) + 1;
+            ga.img_w = g.W; ga.img_h = g.H; ga.nlevels = g.nlevels;
+            for (int l = 0; l < SVO_MAX_LEVELS; ++l) ga.lscale[l] = l < g.nlevels ? g.lv[l].scale : 1.f;
             ga.cell_off = fb.cell_off + (size_t)L.frame0 * (SVO_WIN_CELLS + 1); ga.cell_list = fb.cell_list + (size_t)L.frame0 * K;
             ga.kp = b.kp + (size_t)L.slot0 * g.kp_cap; ga.kp_frame_stride = 2 * (size_t)g.kp_cap;
             ga.win_out = fb.win + (size_t)L.frame0 * R * 3; ga.cur_xy_out = fb.cur_xy + (size_t)L.frame0 * K * 2;
@@ -512,9 +514,11 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
         CU(cudaMemcpyAsync(h.bf_idx, fb.bf_idx + (size_t)L.frame0 * K, sizeof(int) * n * KC, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(h.bf_dist, fb.bf_dist + (size_t)L.frame0 * K, sizeof(int) * n * KC, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(h.bf_keep, fb.bf_keep + (size_t)L.frame0 * K, (size_t)n * KC, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h.p1_best_idx, fb.p1_best_idx + (size_t)L.frame0 * R, sizeof(int) * n * R, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h.p1_best, fb.p1_best + (size_t)L.frame0 * R, sizeof(int) * n * R, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h.p1_second, fb.p1_second + (size_t)L.frame0 * R, sizeof(int) * n * R, cudaMemcpyDeviceToHost, st));
+        if (!ctx->cfg.skip_match_score) {
+            CU(cudaMemcpyAsync(h.p1_best_idx, fb.p1_best_idx + (size_t)L.frame0 * R, sizeof(int) * n * R, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(h.p1_best, fb.p1_best + (size_t)L.frame0 * R, sizeof(int) * n * R, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(h.p1_second, fb.p1_second + (size_t)L.frame0 * R, sizeof(int) * n * R, cudaMemcpyDeviceToHost, st));
+        }
         CU(cudaMemcpyAsync(h.p1_row_claimed, fb.p1_row_claimed + (size_t)L.frame0 * R, (size_t)n * R, cudaMemcpyDeviceToHost, st));
         if (veto) CU(cudaMemcpyAsync(h.p1_row_bad, fb.p1_row_bad + (size_t)L.frame0 * R, (size_t)n * R, cudaMemcpyDeviceToHost, st));
     }
@@ -668,7 +672,7 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
         TRY(halloc(ctx, &h.p1_row_claimed, B * R)); TRY(halloc(ctx, &h.p1_row_bad, B * R)); TRY(halloc(ctx, &h.p2_row_claimed, B * R));
         TRY(halloc(ctx, &h.claim_row, B * K));
         TRY(halloc(ctx, &h.params, 4 * B));
-        l.stage_cap = I * ctx->stage_img_bytes + B * (R * 32 * 2 + R * 5 + R * 12 + R * 8 + SVO_MAX_BOXES * 16 + 72) + (10 * B + 8) * 512;
+        l.stage_cap = I * ctx->stage_img_bytes + B * (R * 32 * 2 + R * 5 + R * 12 + R * 8 + R * 16 + SVO_MAX_BOXES * 16 + 72) + (12 * B + 8) * 512;
         TRY(dalloc(ctx, &l.d_stage, l.stage_cap));
         TRY(dalloc(ctx, &l.d_fp, B)); TRY(halloc(ctx, &l.h_fp, B));
         TRY(dalloc(ctx, &l.d_strides, I)); TRY(halloc(ctx, &l.h_strides, I));
@@ -1002,6 +1006,34 @@ int svo_pose_optimize(svo_ctx *ctx, const svo_pose_problem *problems, int nprobl
     return nproblems;
 }
 
+int svo_project_map(svo_ctx *ctx, const float *xyz, const int32_t *octave, int n, const float *Tcw,
+                    float fx, float fy, float cx, float cy, float th, float *uvr_out)
+{
+    if (!ctx || n < 0 || (n && (!xyz || !uvr_out)) || !Tcw) return fail(ctx, SVO_E_INVALID, "svo_project_map: bad argument");
+    if (!n) return 0;
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = ctx->sync_st;
+    float T[12];
+    CU(cudaMemcpy(T, Tcw, sizeof T, cudaMemcpyDefault));
+    float *d_xyz = nullptr, *d_out = nullptr; int *d_oct = nullptr;
+    CU(cudaMallocAsync((void **)&d_xyz, 3 * sizeof(float) * (size_t)n, st));
+    CU(cudaMallocAsync((void **)&d_out, 3 * sizeof(float) * (size_t)n, st));
+    CU(cudaMemcpyAsync(d_xyz, xyz, 3 * sizeof(float) * (size_t)n, cudaMemcpyDefault, st));
+    if (octave) {
+        CU(cudaMallocAsync((void **)&d_oct, sizeof(int) * (size_t)n, st));
+        CU(cudaMemcpyAsync(d_oct, octave, sizeof(int) * (size_t)n, cudaMemcpyDefault, st));
+    }
+    float ls[SVO_MAX_LEVELS];
+    for (int l = 0; l < ctx->g.nlevels; ++l) ls[l] = ctx->g.lv[l].scale;
+    launch_project(d_xyz, d_oct, n, T, fx, fy, cx, cy, ctx->g.W, ctx->g.H, th, ls, ctx->g.nlevels, d_out, st, &ctx->launches);
+    CU(cudaMemcpyAsync(uvr_out, d_out, 3 * sizeof(float) * (size_t)n, cudaMemcpyDefault, st));
+    CU(cudaFreeAsync(d_xyz, st)); CU(cudaFreeAsync(d_out, st));
+    if (d_oct) CU(cudaFreeAsync(d_oct, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    return n;
+}
+
 int svo_disp2depth(svo_ctx *ctx, const float *disp, float *depth, size_t n, float bf)
 {
     if (!ctx || (n && (!disp || !depth))) return fail(ctx, SVO_E_INVALID, "svo_disp2depth: bad argument");
@@ -1044,7 +1076,7 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
             return fail(ctx, SVO_E_INVALID, "svo_batch_submit: frame %d: n_boxes %d (at most %d)", i, f.n_boxes, SVO_MAX_BOXES);
         if (f.F && ((uintptr_t)f.F & 7)) return fail(ctx, SVO_E_INVALID, "svo_batch_submit: frame %d: F must be 8-byte aligned", i);
         veto |= f.n_prev > 0 && f.n_boxes > 0 && f.F && f.prev_xy;
-        if (f.n_map > 0) { ++n_mapped; if (f.map_win_uvr) ++n_win; }
+        if (f.n_map > 0) { ++n_mapped; if (f.map_win_uvr || (f.map_xyz && f.Tcw_pred)) ++n_win; }
         const int ch = f.channels == 3 ? 3 : 1;
         if (!f.left || !f.right || f.stride < g.W * ch || f.stride >= SVO_STRIDE_BGR || f.n_prev < 0 || f.n_map < 0 || f.n_prev > R ||
             f.n_map > R || (f.n_prev && !f.prev_desc) || (f.n_map && !f.map_desc) || !(f.baseline > 0.f) ||
@@ -1054,7 +1086,7 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
         any_prev |= f.n_prev > 0; any_map |= f.n_map > 0;
     }
     if (n_win != 0 && n_win != n_mapped)
-        return fail(ctx, SVO_E_INVALID, "svo_batch_submit: map_win_uvr must be given for every frame with a map, or for none");
+        return fail(ctx, SVO_E_INVALID, "svo_batch_submit: map_win_uvr (or map_xyz + Tcw_pred) must be given for every frame with a map, or for none");
     const bool windowed = n_win > 0;
     L.in.assign(frames, frames + n);
     L.nframes = n; L.veto = veto;
@@ -1096,6 +1128,14 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
         place(f.n_map ? f.map_desc : nullptr, (size_t)f.n_map * 32, (const void **)&P.map, true);
         place((f.n_map && f.n_prev) ? f.map_prev_row : nullptr, sizeof(int) * (size_t)f.n_map, (const void **)&P.map_prev_row, true);
         place((f.n_map && windowed) ? f.map_win_uvr : nullptr, 3 * sizeof(float) * (size_t)f.n_map, (const void **)&P.map_win, false);
+        const bool proj = f.n_map && windowed && !f.map_win_uvr && f.map_xyz && f.Tcw_pred;
+        place(proj ? f.map_xyz : nullptr, 3 * sizeof(float) * (size_t)f.n_map, (const void **)&P.map_xyz, false);
+        place(proj ? f.map_octave : nullptr, sizeof(int) * (size_t)f.n_map, (const void **)&P.map_octave, false);
+        if (proj) {
+            if (device_readable(f.Tcw_pred)) return fail(ctx, SVO_E_INVALID, "svo_batch_submit: frame %d: Tcw_pred must be a host pointer", i);
+            memcpy(P.Tcw, f.Tcw_pred, sizeof(P.Tcw));
+            P.fx = f.fx; P.fy = f.fy; P.cx = f.cx; P.cy = f.cy; P.proj_th = f.proj_th;
+        }
         const bool fv = f.n_prev > 0 && f.n_boxes > 0 && f.F && f.prev_xy;
         place(fv ? f.boxes : nullptr, 4 * sizeof(int) * (size_t)f.n_boxes, (const void **)&P.boxes, false);
         place(fv ? f.F : nullptr, 9 * sizeof(double), (const void **)&P.F, false);
@@ -1198,8 +1238,11 @@ int svo_batch_result(svo_ctx *ctx, int lane_i, int i, svo_frame_out *o)
     o->u_right = h.u_right + (size_t)i * K; o->depth = h.depth + (size_t)i * K;
     if (in.n_prev) {
         o->bf_idx = h.bf_idx + (size_t)i * K; o->bf_dist = h.bf_dist + (size_t)i * K; o->bf_keep = h.bf_keep + (size_t)i * K;
-        o->p1_best_idx = h.p1_best_idx + (size_t)i * R; o->p1_best = h.p1_best + (size_t)i * R;
-        o->p1_second = h.p1_second + (size_t)i * R; o->p1_row_claimed = h.p1_row_claimed + (size_t)i * R;
+        if (!ctx->cfg.skip_match_score) {
+            o->p1_best_idx = h.p1_best_idx + (size_t)i * R; o->p1_best = h.p1_best + (size_t)i * R;
+            o->p1_second = h.p1_second + (size_t)i * R;
+        }
+        o->p1_row_claimed = h.p1_row_claimed + (size_t)i * R;
         if (L.veto) o->p1_row_bad = h.p1_row_bad + (size_t)i * R;     // NULL: no frame of the batch ran the veto
     }
     if (in.n_map) o->p2_row_claimed = h.p2_row_claimed + (size_t)i * R;

@@ -102,6 +102,11 @@ struct FramePtrs {
     const double *F;               // 3x3 row-major, 8-byte aligned, or NULL
     const float *prev_xy;          // 2 x n_prev or NULL
     int n_boxes;
+    // opt-in projection windows computed on the device (k_win_prepare): map_xyz != NULL
+    const float *map_xyz;          // 3 x n_map
+    const int *map_octave;         // n_map or NULL
+    float Tcw[12];                 // first three rows of the predicted pose
+    float fx, fy, cx, cy, proj_th;
 };
 
 // ---- stage launchers (each enqueues on `st` for images [slot0, slot0 + nimg)) ----
@@ -196,6 +201,7 @@ struct GreedyArgs {
     // positions into win_out / cur_xy_out (= win_uvr / cur_xy) and bins the keypoints into square cells, then
     // k_shortlist_win gathers each row's candidates from the cells under its window
     int win_gather, cell_shift, ncx, ncy;
+    int img_w, img_h, nlevels; float lscale[SVO_MAX_LEVELS];   // projection on the device (fp[f].map_xyz)
     int *cell_off;                // [frame][SVO_WIN_CELLS + 1]
     uint16_t *cell_list;          // [frame][cols.stride_rows]
     // batch pass 2 without windows: the ascending list of columns pass 1 left free (k_free_cols); k_shortlist scans only those
@@ -225,6 +231,7 @@ struct PairArgs {            // fused BF + pass-1 front of the batch path (match
     int dmat_pitch;          // bytes per matrix row, multiple of 16, >= column capacity
     uint32_t *bf_key;        // [frame][cols.stride_rows] (d << 16 | prev row) minima
     int T, lane_cols;        // filled by the launcher
+    int skip_scores;         // 1: match_score (best_idx / best / second of every row) is not computed
     int use_tc;              // 1: tensor-core tiles (tcham.cu) instead of k_pairs / k_scores_m; dmat is not touched
 };
 void launch_pass1_fused(const PairArgs &p, const BfArgs &b, int nframes, cudaStream_t st, long long *launches,
@@ -273,6 +280,8 @@ void launch_pnp_ransac(const PoseArgs &a, int nproblems, int max_n, cudaStream_t
 void launch_pose_lm(const PoseArgs &a, int nproblems, cudaStream_t st, long long *launches);
 int setup_pose();
 int pose_max_iterations();
+void launch_project(const float *xyz, const int *octave, int n, const float *Tcw12, float fx, float fy, float cx, float cy, int W, int H,
+                    float th, const float *lscale, int nlevels, float *uvr, cudaStream_t st, long long *launches);
 void launch_disp2depth(const float *disp, float *depth, size_t n, float bf, cudaStream_t st, long long *launches);
 int setup_match_attributes();
 int greedy_max_cols();   // most columns (current-frame keypoints) the greedy resolver supports

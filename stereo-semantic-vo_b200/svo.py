@@ -26,7 +26,7 @@ class Config(C.Structure):
     _fields_ = [("device", C.c_int), ("width", C.c_int), ("height", C.c_int), ("nfeatures", C.c_int),
                 ("nlevels", C.c_int), ("scale_factor", C.c_float), ("fast_threshold", C.c_int),
                 ("max_batch", C.c_int), ("lanes", C.c_int), ("max_rows", C.c_int), ("stream", C.c_void_p),
-                ("max_channels", C.c_int), ("distribution", C.c_int)]
+                ("max_channels", C.c_int), ("distribution", C.c_int), ("skip_match_score", C.c_int)]
 
 
 class Veto(C.Structure):
@@ -40,7 +40,9 @@ class FrameIn(C.Structure):
                 ("prev_desc", C.c_void_p), ("n_prev", C.c_int), ("prev_live", C.c_void_p),
                 ("map_desc", C.c_void_p), ("n_map", C.c_int), ("map_prev_row", C.c_void_p), ("channels", C.c_int),
                 ("map_win_uvr", C.c_void_p),
-                ("boxes", C.c_void_p), ("n_boxes", C.c_int), ("F", C.c_void_p), ("prev_xy", C.c_void_p)]
+                ("boxes", C.c_void_p), ("n_boxes", C.c_int), ("F", C.c_void_p), ("prev_xy", C.c_void_p),
+                ("map_xyz", C.c_void_p), ("map_octave", C.c_void_p), ("Tcw_pred", C.c_void_p),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("proj_th", C.c_float)]
 
 
 class FrameOut(C.Structure):
@@ -74,7 +76,7 @@ EXPORTS = ["svo_default_config", "svo_version", "svo_create", "svo_destroy", "sv
            "svo_batch_submit", "svo_batch_wait", "svo_batch_result", "svo_alloc_pinned", "svo_free_pinned",
            "svo_alloc_device", "svo_free_device", "svo_copy_to_device", "svo_launch_count", "svo_batch_stage_ms",
            "svo_set_profiling", "svo_lane_stream", "svo_debug_tap", "svo_debug_retain_best",
-           "svo_pnp_ransac", "svo_pose_optimize", "svo_debug_hamming_matrix", "svo_debug_tc_profile"]
+           "svo_pnp_ransac", "svo_pose_optimize", "svo_debug_hamming_matrix", "svo_debug_tc_profile", "svo_project_map"]
 
 _lib = None
 
@@ -126,6 +128,7 @@ def load():
     L.svo_pnp_ransac.argtypes = [C.c_void_p, C.POINTER(PoseProblem), C.c_int, C.c_int, C.c_float, C.c_uint32, C.c_int,
                                  C.POINTER(PnpResult), C.c_void_p]
     L.svo_pose_optimize.argtypes = [C.c_void_p, C.POINTER(PoseProblem), C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.svo_project_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
     L.svo_debug_tc_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.svo_debug_hamming_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     _lib = L
@@ -148,7 +151,8 @@ class Context:
     """One svo_ctx: device buffers, streams and pipeline lanes for one image size."""
 
     def __init__(self, width=1241, height=376, nfeatures=2000, nlevels=8, scale_factor=1.2, fast_threshold=20,
-                 max_batch=1, lanes=1, max_rows=5000, device=0, stream=None, max_channels=1, distribution=0):
+                 max_batch=1, lanes=1, max_rows=5000, device=0, stream=None, max_channels=1, distribution=0,
+                 skip_match_score=False):
         self.lib = load()
         cfg = Config()
         self.lib.svo_default_config(C.byref(cfg))
@@ -157,6 +161,7 @@ class Context:
         cfg.max_batch, cfg.lanes, cfg.max_rows, cfg.stream = max_batch, lanes, max_rows, stream
         cfg.max_channels = max_channels
         cfg.distribution = distribution      # DIST_RETAIN_BEST (cv::ORB parity) or DIST_OCTREE (opt-in, non-parity)
+        cfg.skip_match_score = int(bool(skip_match_score))
         self.cfg = cfg
         self.h = C.c_void_p()
         rc = self.lib.svo_create(C.byref(cfg), C.byref(self.h))
@@ -244,6 +249,16 @@ class Context:
                                             _p(s) if scores else None, _p(rc), _p(win_uvr), _p(cur_xy),
                                             C.byref(v) if v is not None else None, _p(bad)))
         return dict(best_idx=bi, best=b, second=s, row_claimed=rc, claimed=claimed, claim_row=claim_row, row_bad=bad)
+
+    def project_map(self, xyz, octave, Tcw, K4, th=7.0):
+        """Opt-in projection windows (u, v, r) of map points under the predicted pose."""
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        octave = None if octave is None else np.ascontiguousarray(octave, np.int32)
+        T = np.ascontiguousarray(Tcw, np.float32).reshape(16)
+        out = np.zeros((len(xyz), 3), np.float32)
+        self._chk(self.lib.svo_project_map(self.h, _p(xyz), _p(octave), len(xyz), _p(T), float(K4[0]), float(K4[1]), float(K4[2]),
+                                           float(K4[3]), float(th), _p(out)))
+        return out
 
     def disp2depth(self, disp, bf):
         disp = np.ascontiguousarray(disp, np.float32)
@@ -338,7 +353,11 @@ class Context:
                     fi.boxes, fi.n_boxes = v.ctypes.data, len(v)
                 else:
                     fi.boxes, fi.n_boxes = int(v), f["n_boxes"]
-            for name, dt in (("F", np.float64), ("prev_xy", np.float32)):
+            if f.get("K") is not None:
+                fi.fx, fi.fy, fi.cx, fi.cy = [float(v) for v in f["K"]]
+                fi.proj_th = float(f.get("proj_th", 7.0))
+            for name, dt in (("F", np.float64), ("prev_xy", np.float32), ("map_xyz", np.float32), ("map_octave", np.int32),
+                             ("Tcw_pred", np.float32)):
                 v = f.get(name)
                 if isinstance(v, np.ndarray):
                     v = np.ascontiguousarray(v, dt)

@@ -320,3 +320,112 @@ def test_stated_limits(svo):
         assert e.value.code == svo.E_CAPACITY
     finally:
         c.close()
+
+
+# ---- opt-in projection windows computed on the device ("true projection-guided windows") ----
+def predicted_pose():
+    T = np.eye(4, dtype=np.float32)
+    T[:3, :3] = synth.rodrigues([0.01, -0.03, 0.005]).astype(np.float32); T[:3, 3] = [0.2, -0.05, 0.6]
+    return T
+
+
+def map_points_for(kp, depth_guess, Tcw, K4, rng):
+    """World points that project (under Tcw) near the given keypoints: back-project at a guessed depth, undo the pose."""
+    fx, fy, cx, cy = K4
+    z = depth_guess
+    Xc = np.stack([(kp["x"] - cx) / fx * z, (kp["y"] - cy) / fy * z, z], 1).astype(np.float64)
+    R, t = Tcw[:3, :3].astype(np.float64), Tcw[:3, 3].astype(np.float64)
+    Xw = (Xc - t) @ R                   # R^T (Xc - t)
+    return (Xw + rng.normal(0, 0.02, Xw.shape)).astype(np.float32)
+
+
+def test_project_map_vs_oracle(ctxK):
+    rng = np.random.default_rng(41)
+    cal = synth.KITTI_04_12
+    K4 = tuple(np.float32(cal[k]) for k in ("fx", "fy", "cx", "cy"))
+    T = predicted_pose()
+    n = 6000
+    xyz = np.stack([rng.uniform(-30, 30, n), rng.uniform(-8, 8, n), rng.uniform(-5, 80, n)], 1).astype(np.float32)
+    xyz[:50, 2] = 0.0; xyz[50:60] = 0.0                      # on / behind the camera plane
+    octv = rng.integers(-1, 10, n).astype(np.int32)            # out-of-range levels are clamped
+    ref = O.project_map(xyz, octv, T, K4, 1241, 376, th=7.0)
+    got = ctxK.project_map(xyz, octv, T, K4, th=7.0)
+    assert (got.view(np.uint32) == ref.view(np.uint32)).all()
+    vis = ref[:, 2] > 0
+    assert 500 < vis.sum() < n - 500
+    assert (ref[~vis] == np.array([0, 0, -1], np.float32)).all()
+    # independent numpy float32 restatement of the formula for the visible points
+    X = xyz[vis]
+    xc = ((T[0, 0] * X[:, 0] + T[0, 1] * X[:, 1]) + T[0, 2] * X[:, 2]) + T[0, 3]
+    zc = ((T[2, 0] * X[:, 0] + T[2, 1] * X[:, 1]) + T[2, 2] * X[:, 2]) + T[2, 3]
+    u = (K4[0] * xc) * (np.float32(1) / zc) + K4[2]
+    assert (u.astype(np.float32).view(np.uint32) == ref[vis, 0].view(np.uint32)).all()
+    assert (ctxK.project_map(xyz, None, T, K4)[vis, 2] == np.float32(7.0)).all()
+
+
+def test_batch_pass2_projected_windows_vs_oracle(ctxK):
+    """svo_frame_in.map_xyz / map_octave / Tcw_pred: the windows are projected on the device inside the batch and pass 2
+    gathers from them; same claims as the oracle's windowed scan over the oracle's own projection."""
+    cal = synth.KITTI_04_12
+    bf, b = float(np.float32(cal["bf"])), float(np.float32(cal["bf"] / cal["fx"]))
+    K4 = tuple(np.float32(cal[k]) for k in ("fx", "fy", "cx", "cy"))
+    seq = synth.Sequence(seed=14)
+    frames = [seq.frame(t) for t in range(3)]
+    ext = [ctxK.extract(frames[t][0], cam=0) for t in range(3)]
+    rng = np.random.default_rng(33)
+    T = predicted_pose()
+    jobs = []
+    for t in (1, 2):
+        kp_prev, prev = ext[t - 1]
+        kp_cur, cur = ext[t]
+        M = 3500
+        src = rng.integers(0, len(cur), M)
+        mp = cur[src] ^ np.packbits(rng.random((M, 256)) < 0.03, axis=1, bitorder="little")
+        xyz = map_points_for(kp_cur[src], rng.uniform(4, 60, M).astype(np.float32), T, K4, rng)
+        far = rng.permutation(M)[:400]
+        xyz[far] = np.stack([rng.uniform(-30, 30, 400), rng.uniform(-8, 8, 400), rng.uniform(-5, 80, 400)], 1).astype(np.float32)
+        jobs.append(dict(left=frames[t][0], right=frames[t][1], bf=bf, baseline=b, prev_desc=prev, map_desc=mp,
+                         map_xyz=xyz, map_octave=kp_cur["octave"][src].astype(np.int32), Tcw_pred=T, K=K4, proj_th=7.0))
+    ctxK.batch_submit(0, jobs); ctxK.batch_wait(0)
+    total = 0
+    for i, (job, t) in enumerate(zip(jobs, (1, 2))):
+        r = ctxK.batch_result(0, i)
+        kp_cur, cur = ext[t]
+        assert (r["desc_left"] == cur).all()
+        cxy = np.stack([kp_cur["x"], kp_cur["y"]], 1).astype(np.float32)
+        win = O.project_map(job["map_xyz"], job["map_octave"], T, K4, 1241, 376, th=7.0)
+        p1 = O.match_greedy(job["prev_desc"], cur, 0)
+        assert (r["p1_row_claimed"] == p1["row_claimed"]).all()
+        p2 = O.match_greedy(job["map_desc"], cur, 1, claimed=p1["claimed"], claim_row=p1["claim_row"], row_base=len(job["prev_desc"]),
+                            win_uvr=win, cur_xy=cxy)
+        assert (r["p2_row_claimed"] == p2["row_claimed"]).all()
+        assert (r["claim_row"] == p2["claim_row"]).all()
+        total += int(p2["row_claimed"].sum())
+    assert total > 100, total
+
+
+def test_skip_match_score_changes_nothing_else(svo):
+    """svo_config.skip_match_score: the (bestIdx, best, second) triplet of src/pnpmatch.cc:99 is not produced; claims,
+    BF matches and everything else are byte-identical to the default context's."""
+    cal = synth.KITTI_04_12
+    bf, b = float(np.float32(cal["bf"])), float(np.float32(cal["bf"] / cal["fx"]))
+    seq = synth.Sequence(seed=15)
+    frames = [seq.frame(t) for t in range(2)]
+    res = []
+    for skip in (False, True):
+        c = svo.Context(1241, 376, nfeatures=2000, max_batch=2, lanes=1, max_rows=5000, skip_match_score=skip)
+        try:
+            prev = c.extract(frames[0][0])[1]
+            mp = synth.local_map([prev], rows=3000, seed=2)
+            c.batch_submit(0, [dict(left=frames[1][0], right=frames[1][1], bf=bf, baseline=b, prev_desc=prev, map_desc=mp)])
+            c.batch_wait(0)
+            res.append(c.batch_result(0, 0))
+        finally:
+            c.close()
+    full, lean = res
+    assert full["p1_best"].min() < 15 and (lean["p1_best"] == 0).all()          # absent: the binding shows zeros
+    for k in full:
+        if k.startswith("p1_best") or k == "p1_second":
+            continue
+        a, bb = full[k], lean[k]
+        assert (a.tobytes() == bb.tobytes()) if isinstance(a, np.ndarray) else a == bb, k

@@ -113,3 +113,27 @@ def test_pass2_over_the_free_columns_only_is_the_same_scan():
         ok = idx >= 0
         idx[ok] = free[idx[ok]]
         assert (full["best_idx"] == idx).all() and (full["best"] == sub["best"]).all() and (full["second"] == sub["second"]).all()
+
+
+def test_project_map_formula_and_edge_cases():
+    """The oracle's projection windows (opt-in pass-2 mode) against a plain numpy float32 restatement."""
+    rng = np.random.default_rng(5)
+    T = np.eye(4, dtype=np.float32); T[:3, 3] = [0.1, 0.0, 0.5]; T[0, 1] = np.float32(0.01); T[1, 0] = np.float32(-0.01)
+    K4 = (np.float32(707.0912), np.float32(707.0912), np.float32(601.8873), np.float32(183.1104))
+    xyz = np.stack([rng.uniform(-20, 20, 500), rng.uniform(-5, 5, 500), rng.uniform(-2, 60, 500)], 1).astype(np.float32)
+    octv = rng.integers(0, 8, 500).astype(np.int32)
+    out = O.project_map(xyz, octv, T, K4, 1241, 376, th=7.0)
+    _, _, ls, _ = O.geometry(1241, 376, 8, 1.2, 500)
+    for i in range(500):
+        X, Y, Z = xyz[i]
+        xc = ((T[0, 0] * X + T[0, 1] * Y) + T[0, 2] * Z) + T[0, 3]
+        yc = ((T[1, 0] * X + T[1, 1] * Y) + T[1, 2] * Z) + T[1, 3]
+        zc = ((T[2, 0] * X + T[2, 1] * Y) + T[2, 2] * Z) + T[2, 3]
+        exp = (np.float32(0), np.float32(0), np.float32(-1))
+        if zc > 0:
+            iz = np.float32(1) / zc
+            u = (K4[0] * xc) * iz + K4[2]; v = (K4[1] * yc) * iz + K4[3]
+            if 0 <= u < 1241 and 0 <= v < 376:
+                exp = (u, v, np.float32(7.0) * ls[octv[i]])
+        assert tuple(out[i]) == tuple(np.float32(e) for e in exp), i
+    assert (out[:, 2] > 0).sum() > 50 and (out[:, 2] < 0).sum() > 50
