@@ -67,6 +67,123 @@ __global__ void __launch_bounds__(256) k_resize(Bufs b, Geom g, int l, int slot0
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// All seven resized levels in ONE launch.  A CTA owns a band of rows of the last level and everything below it that the
+// band depends on: the level-0 rows arrive with one TMA bulk copy (the pitched rows of a band are contiguous in HBM),
+// then level 1 is computed from them in shared memory, level 2 from level 1, ... — every level is read from shared
+// memory, never from HBM — and each level's rows this band OWNS are stored with 16-byte writes while the next level is
+// being computed.  Bands overlap by the few rows of halo the 2-tap vertical filter needs (the host precomputes, per
+// band and level, the computed and the owned row range from the same coefficient tables the arithmetic uses), so
+// neighbouring CTAs recompute those rows instead of synchronising.  Same Q8 x Q8 integer arithmetic as k_resize.
+// Replaces 7 dependent launches (126 us of device time per 64 images, and 0.5 ms of queueing inside a pipeline lane).
+// ---------------------------------------------------------------------------------------------------------------------
+#define PYR_THREADS 512
+#define PYR_STRIP 8
+extern __shared__ __align__(128) uint8_t pyr_smem[];
+
+__global__ void __launch_bounds__(PYR_THREADS) k_pyramid(Bufs b, Geom g, int slot0)
+{
+    __shared__ PyrBand bd;
+    if (threadIdx.x == 0) bd = b.pyr_bands[blockIdx.x];
+    const size_t base = (size_t)(slot0 + blockIdx.y) * g.pyr_bytes;
+    const int tid = threadIdx.x;
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+    {   // level 0 rows [clo, chi]: one bulk copy
+        const LevelGeom &L = g.lv[0];
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        const uint32_t bytes = (uint32_t)(bd.chi[0] - bd.clo[0] + 1) * (uint32_t)L.pitch;
+        if (tid == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                             "r"((uint32_t)__cvta_generic_to_shared(pyr_smem + g.pyr_soff[0])),
+                         "l"(b.pyr + base + L.off + (size_t)bd.clo[0] * L.pitch), "r"(bytes), "r"(bar_a)
+                         : "memory");
+        }
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "W_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+            "@p bra D_%=;\n\t"
+            "bra W_%=;\n\t"
+            "D_%=:\n\t"
+            "}\n" ::"r"(bar_a) : "memory");
+    }
+    for (int l = 1; l < g.nlevels; ++l) {
+        const LevelGeom &d = g.lv[l];
+        const LevelGeom &s = g.lv[l - 1];
+        const uint8_t *src = pyr_smem + g.pyr_soff[l - 1];      // rows [clo[l-1], chi[l-1]] of level l-1, pitch s.pitch
+        uint8_t *dst = pyr_smem + g.pyr_soff[l];
+        const uint32_t *xt = b.rtab + d.tab_off;
+        const int qpr = d.pitch >> 2, clo = bd.clo[l], nrows = bd.chi[l] - clo + 1, slo = bd.clo[l - 1], sp = s.pitch;
+        // k_resize's column strips, over shared memory: a thread owns 4 output columns and walks PYR_STRIP rows down, sharing
+        // the horizontal pass of a source row between the two output rows that straddle it
+        const int strips = (nrows + PYR_STRIP - 1) / PYR_STRIP;
+        for (int it = tid; it < qpr * strips; it += PYR_THREADS) {
+            const int st = it / qpr, x = (it - st * qpr) << 2;
+            const int y0 = clo + st * PYR_STRIP, y1 = min(y0 + PYR_STRIP, clo + nrows);
+            int i0[4], i1[4];
+            uint32_t wx0[4], wx1[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t tx = x + k < d.w ? __ldg(xt + x + k) : 0u;
+                i0[k] = tx >> 9; wx1[k] = tx & 511u; wx0[k] = 256u - wx1[k];
+                i1[k] = wx1[k] ? i0[k] + 1 : i0[k];
+                if (x + k >= d.w) { wx0[k] = 0; wx1[k] = 0; }          // padding columns hold 0
+            }
+            auto hrow = [&](int yy, uint32_t (&h)[4]) {
+                const uint8_t *r = src + (size_t)(yy - slo) * sp;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) h[k] = r[i0[k]] * wx0[k] + r[i1[k]] * wx1[k];
+            };
+            uint32_t ha[4], hb[4];
+            int ya = -1, ybr = -1;
+            for (int y = y0; y < y1; ++y) {
+                const uint32_t ty = __ldg(xt + d.w + y);
+                const int yo = ty >> 9;
+                const uint32_t wy1 = ty & 511u, wy0 = 256u - wy1;
+                const int yn = wy1 ? yo + 1 : yo;
+                if (yo == ybr) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ha[k] = hb[k];
+                } else if (yo != ya) hrow(yo, ha);
+                ya = yo;
+                if (yn == yo) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) hb[k] = ha[k];
+                } else hrow(yn, hb);
+                ybr = yn;
+                uint32_t out = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) out |= ((ha[k] * wy0 + hb[k] * wy1 + 32768u) >> 16) << (8 * k);
+                *reinterpret_cast<uint32_t *>(dst + (size_t)(y - clo) * d.pitch + x) = out;
+            }
+        }
+        __syncthreads();
+        // the rows this band owns go to HBM (16-byte stores, whole pitched rows) while the next level is computed from the same tile
+        const int v16 = d.pitch >> 4, own = bd.ohi[l] - bd.olo[l];
+        uint8_t *gdst = b.pyr + base + d.off + (size_t)bd.olo[l] * d.pitch;
+        const uint8_t *sown = dst + (size_t)(bd.olo[l] - clo) * d.pitch;
+        for (int it = tid; it < v16 * own; it += PYR_THREADS)
+            reinterpret_cast<uint4 *>(gdst)[it] = reinterpret_cast<const uint4 *>(sown)[it];
+    }
+}
+
+static int g_pyr_smem_set = 0;
+int setup_pyramid_attributes(const Geom &g)
+{
+    // per kernel, not per context: a context for a smaller geometry must not lower the limit under a larger one
+    if (!g.pyr_nbands || g.pyr_smem <= g_pyr_smem_set) return 0;
+    if (cudaFuncSetAttribute(k_pyramid, cudaFuncAttributeMaxDynamicSharedMemorySize, g.pyr_smem) != cudaSuccess) return 1;
+    g_pyr_smem_set = g.pyr_smem;
+    return 0;
+}
+
 // Level 0 is read where it lies in device memory (the caller's device buffer, or the lane's landing zone
 // for host inputs; rows `stride` bytes apart, any alignment) and repacked into the 16-byte-pitched level-0
 // layout.  One thread per 16 output bytes.  Interleaved BGR sources (SVO_STRIDE_BGR set in the stride word) are
@@ -114,6 +231,11 @@ void launch_unpack(const Bufs &b, const Geom &g, int slot0, int nimg, const Fram
 
 void launch_pyramid(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches)
 {
+    if (g.pyr_nbands && b.pyr_bands) {
+        k_pyramid<<<dim3(g.pyr_nbands, nimg), PYR_THREADS, g.pyr_smem, st>>>(b, g, slot0);
+        ++*launches;
+        return;
+    }
     for (int l = 1; l < g.nlevels; ++l) {
         const int rs = (size_t)g.lv[l].w * g.lv[l].h * nimg >= (size_t)8 << 20 ? 8 : 4;   // fewer rows per thread when the launch is small
         const int quads = (g.lv[l].pitch >> 2) * ((g.lv[l].h + rs - 1) / rs);

@@ -252,6 +252,61 @@ int build_geometry(svo_ctx *ctx)
     return SVO_OK;
 }
 
+// Bands of the fused pyramid kernel (pyramid.cu:k_pyramid).  Band j owns rows [j R, (j + 1) R) of the last level; going
+// down the levels, the rows a band must compute are the rows the level above reads (from the same y tables the kernel
+// uses: source row ofs and, when the second tap's weight is not zero, ofs + 1) plus the rows it owns, and a band owns at
+// each level the rows from its own first needed row up to the next band's.  R is the largest band height whose shared
+// memory fits `budget`; 0 bands = the geometry does not fit at all (very wide images) and the per-level kernels run.
+int build_pyramid_bands(svo_ctx *ctx, std::vector<PyrBand> &bands, int budget)
+{
+    Geom &g = ctx->g;
+    const int NL = g.nlevels;
+    g.pyr_nbands = 0; g.pyr_smem = 0;
+    bands.clear();
+    if (NL < 2) return SVO_OK;
+    const uint32_t *tab = ctx->rtab_host.data();
+    auto yo = [&](int l, int y) { return (int)(tab[g.lv[l].tab_off + g.lv[l].w + y] >> 9); };
+    auto yn = [&](int l, int y) { const uint32_t t = tab[g.lv[l].tab_off + g.lv[l].w + y]; return (int)(t >> 9) + ((t & 511u) ? 1 : 0); };
+    const int hl = g.lv[NL - 1].h;
+    for (int R = hl; R >= 1; --R) {
+        const int nb = (hl + R - 1) / R;
+        if (R > 1 && (long long)nb < 8) continue;          // keep at least a few bands per image
+        std::vector<PyrBand> bs((size_t)nb);
+        std::vector<int> lo((size_t)nb + 1);
+        for (int j = 0; j < nb; ++j) {
+            PyrBand &B = bs[(size_t)j];
+            memset(&B, 0, sizeof(B));
+            B.olo[NL - 1] = B.clo[NL - 1] = (short)(j * R);
+            B.ohi[NL - 1] = (short)std::min((j + 1) * R, hl);
+            B.chi[NL - 1] = (short)(B.ohi[NL - 1] - 1);
+        }
+        for (int l = NL - 2; l >= 0; --l) {
+            for (int j = 0; j < nb; ++j) lo[(size_t)j] = j == 0 ? 0 : yo(l + 1, bs[(size_t)j].clo[l + 1]);
+            lo[(size_t)nb] = g.lv[l].h;
+            for (int j = 0; j < nb; ++j) {
+                PyrBand &B = bs[(size_t)j];
+                const int need_lo = yo(l + 1, B.clo[l + 1]), need_hi = yn(l + 1, B.chi[l + 1]);
+                B.olo[l] = (short)lo[(size_t)j]; B.ohi[l] = (short)std::max(lo[(size_t)j + 1], lo[(size_t)j]);
+                B.clo[l] = (short)std::min(need_lo, (int)B.olo[l]);
+                B.chi[l] = (short)std::min(std::max(need_hi, B.ohi[l] - 1), g.lv[l].h - 1);
+            }
+        }
+        int off = 0, soff[SVO_MAX_LEVELS];
+        for (int l = 0; l < NL; ++l) {
+            int rows = 0;
+            for (int j = 0; j < nb; ++j) rows = std::max(rows, bs[(size_t)j].chi[l] - bs[(size_t)j].clo[l] + 1);
+            soff[l] = off;
+            off += align_up(rows * g.lv[l].pitch, 128);
+        }
+        if (off > budget) continue;
+        bands = bs;
+        g.pyr_nbands = nb; g.pyr_smem = off;
+        for (int l = 0; l < NL; ++l) g.pyr_soff[l] = soff[l];
+        return SVO_OK;
+    }
+    return SVO_OK;
+}
+
 int alloc_frames(svo_ctx *ctx, FrameBufs &f, int nframes, int col_stride, int row_stride, bool sync_extras)
 {
     f.nframes = nframes; f.col_stride = col_stride; f.row_stride = row_stride;
@@ -609,6 +664,24 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
     TRY(dalloc(ctx, &rtab, ctx->rtab_host.size()));
     CU(cudaMemcpy(rtab, ctx->rtab_host.data(), ctx->rtab_host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     b.rtab = rtab;
+    {   // One-launch pyramid (pyramid.cu:k_pyramid), OPT-IN with SVO_B200_PYRAMID_FUSED=1.  Measured on B200 (profiles/
+        // r2_pyramid_fused_experiment.md): 128 us per 64 images against 126 us for the seven per-level launches when run
+        // alone, a 2 % shorter single-frame p50, but 5 % LOWER batch throughput inside the three-lane pipeline, where its
+        // 100 KB CTAs keep the other lanes' kernels off the SMs.  The default stays the per-level kernels.
+        std::vector<PyrBand> bands;
+        b.pyr_bands = nullptr;
+        ctx->g.pyr_nbands = 0;
+        if (getenv("SVO_B200_PYRAMID_FUSED")) {
+            TRY(build_pyramid_bands(ctx, bands, 100 * 1024));
+            if (ctx->g.pyr_nbands == 0) TRY(build_pyramid_bands(ctx, bands, 200 * 1024));
+        }
+        if (ctx->g.pyr_nbands) {
+            PyrBand *d = nullptr;
+            TRY(dalloc(ctx, &d, bands.size()));
+            CU(cudaMemcpy(d, bands.data(), bands.size() * sizeof(PyrBand), cudaMemcpyHostToDevice));
+            b.pyr_bands = d;
+        } else ctx->g.pyr_nbands = 0;
+    }
     CU(cudaMemset(b.pyr, 0, S * g.pyr_bytes)); CU(cudaMemset(b.blur, 0, S * g.pyr_bytes));
     CU(cudaMemset(b.nkp, 0, S * sizeof(int))); CU(cudaMemset(b.status, 0, S * sizeof(int)));
     CU(cudaMemset(b.kept1, 0, S * SVO_MAX_LEVELS * sizeof(int))); CU(cudaMemset(b.kept2, 0, S * SVO_MAX_LEVELS * sizeof(int)));
@@ -639,7 +712,7 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
                 return fail(ctx, SVO_E_INVALID, "octree distribution: level %d is wider than 16.5 x its height", l);
         }
     }
-    if (setup_fast_attributes(g) != 0 || setup_match_attributes() != 0 || setup_describe() != 0 || setup_select_attributes() != 0 ||
+    if (setup_pyramid_attributes(g) != 0 || setup_fast_attributes(g) != 0 || setup_match_attributes() != 0 || setup_describe() != 0 || setup_select_attributes() != 0 ||
         setup_pose() != 0 || setup_octree_attributes() != 0)
         return fail(ctx, SVO_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (getenv("SVO_B200_TC_PROF")) TRY(dalloc(ctx, &ctx->tc_prof, 4 * 256));

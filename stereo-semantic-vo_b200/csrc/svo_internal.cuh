@@ -60,8 +60,15 @@ struct Geom {
     int kp_cap;          // final keypoints per image
     int blur_tiles;      // blur tiles per image
     int fast_bands;      // FAST bands per image (sum of nbands)
+    int pyr_nbands;      // bands of the fused pyramid kernel (0: per-level kernels)
+    int pyr_soff[SVO_MAX_LEVELS];   // shared-memory byte offset of each level's rows in that kernel
+    int pyr_smem;        // its dynamic shared memory
     LevelGeom lv[SVO_MAX_LEVELS];
 };
+
+// One band of the fused pyramid kernel (pyramid.cu): per level the rows the CTA computes in shared memory
+// ([clo, chi], a superset of what the next level needs from it) and the rows it owns, i.e. writes to HBM ([olo, ohi)).
+struct PyrBand { short clo[SVO_MAX_LEVELS], chi[SVO_MAX_LEVELS], olo[SVO_MAX_LEVELS], ohi[SVO_MAX_LEVELS]; };
 
 // Base pointers of the slot arrays (index = slot * per-slot size + offset).
 struct Bufs {
@@ -80,6 +87,7 @@ struct Bufs {
     int *nkp;     // [slot]
     int *status;  // [slot]
     const uint32_t *rtab;  // resize tables: (ofs << 9) | w1
+    const PyrBand *pyr_bands;   // [Geom.pyr_nbands] or NULL: the fused pyramid kernel is not used for this geometry
 };
 
 // packed candidate: x | y << 12 | score << 24
@@ -128,6 +136,7 @@ int fast_smem_bytes(const Geom &g);
 int setup_fast_attributes(const Geom &g);
 int setup_describe();
 int setup_select_attributes();
+int setup_pyramid_attributes(const Geom &g);
 
 // bare retainBest replay (debug/test entry)
 void launch_retain_best_raw(float *key, uint32_t *val, int n, int n_points, int depth_limit,

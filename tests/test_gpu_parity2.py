@@ -429,3 +429,26 @@ def test_skip_match_score_changes_nothing_else(svo):
             continue
         a, bb = full[k], lean[k]
         assert (a.tobytes() == bb.tobytes()) if isinstance(a, np.ndarray) else a == bb, k
+
+
+def test_fused_pyramid_is_byte_exact(svo):
+    """SVO_B200_PYRAMID_FUSED=1: the one-launch pyramid (TMA bulk copy of the band's level-0 rows, levels 1..7 chained in
+    shared memory) gives the same bytes as the oracle on every level, for a KITTI-shape and an odd-sized image, and the
+    whole extractor on top of it is unchanged."""
+    import os
+    os.environ["SVO_B200_PYRAMID_FUSED"] = "1"
+    try:
+        for shape, nf in (((376, 1241), 2000), ((203, 317), 300), ((720, 2560), 4000)):
+            img = synth.texture(shape, 7 + nf)
+            c = svo.Context(shape[1], shape[0], nfeatures=nf, max_batch=1, lanes=1, max_rows=1000)
+            try:
+                kp, desc = c.extract(img)
+                ref, rdesc, pyr = O.orb(img, nf, with_pyramid=True)
+                for l in range(8):
+                    assert (c.tap_image(0, l) == pyr.level(l)).all(), (shape, l)
+                O.pyramid_free(pyr)
+                assert len(kp) == len(ref) and (desc == rdesc).all()
+            finally:
+                c.close()
+    finally:
+        del os.environ["SVO_B200_PYRAMID_FUSED"]
