@@ -249,6 +249,16 @@ typedef struct svo_frame_in {
     const int32_t *map_octave;   /* n_map (may be NULL: level 0)                                         */
     const float *Tcw_pred;       /* 16, row-major: Velocity * LastFrame.Tcw (src/Tracking.cc:99-106)     */
     float fx, fy, cx, cy, proj_th;   /* K and the window scale (ORB-SLAM2: 7 for stereo)                 */
+    /* OPT-IN device-resident tracker state (svo_track_create): track_seq = 1 + the sequence this frame belongs
+       to (0 = none).  prev_desc / n_prev / prev_live / map_desc / n_map / map_prev_row above are then IGNORED:
+       the matchers read the sequence's state where it lies in HBM (pass-1 rows = the frozen descriptors of the
+       map points the last frame's keypoints own, pass-2 rows = the local map) and the state is advanced on
+       the device after the frame (createmappoint + the 4-frame window of src/Tracking.cc:237-250).  Frames of
+       one sequence must be submitted in order, at most one per batch; frame_id is Tracking::frame_num.
+       prev_xy is ignored too (the state holds the last frame's keypoints): the veto runs when boxes and F are
+       given.  boxes also keep createmappoint from making points inside them (src/frame.cc:196-207).        */
+    int track_seq;
+    int frame_id;
 } svo_frame_in;
 
 typedef struct svo_frame_out {
@@ -266,6 +276,12 @@ typedef struct svo_frame_out {
     const uint8_t *p2_row_claimed;               /* n_map                                 */
     const int32_t *claim_row;                    /* n_left: row that claimed column j     */
                                                  /* (0..n_prev-1 pass 1, n_prev+i pass 2), -1 = free */
+    int32_t n_prev, n_map;                       /* rows of the two passes (tracked frames: read from the state) */
+    /* tracked frames only (else NULL): CurrentFrame->MapPoints[j] after the frame and createmappoint, named for the
+       host: create_id of the owned point (-1 = none) and its position in the camera frame of the frame that created
+       it (worldpos = Twc[create_id] * xyz; poses stay with the caller).  fx, fy, cx, cy of svo_frame_in must be set. */
+    const int32_t *mp_create;                    /* n_left                                */
+    const float *mp_xyz;                         /* n_left x 3                            */
 } svo_frame_out;
 
 /* Enqueue H2D + all kernels + one D2H for `n` frames on `lane`; returns at once. */
@@ -274,6 +290,46 @@ int svo_batch_submit(svo_ctx *ctx, int lane, const svo_frame_in *frames, int n);
 int svo_batch_wait(svo_ctx *ctx, int lane);
 /* View of frame `i` of the lane's last batch (valid until the lane's next submit). */
 int svo_batch_result(svo_ctx *ctx, int lane, int i, svo_frame_out *out);
+
+/* ---------------------------------------------------------------------------
+ * Device-resident tracker state (opt-in).  In the reference the previous frame's map points and the local map
+ * are outputs of earlier frames (src/Tracking.cc:237-250: lastframe = frame(currentframe);
+ * lastframe.createmappoint(LocalMapPoints); points with create_id <= frame_num - 4 are erased).  With a tracker
+ * the batch path keeps them in HBM: a frame submitted with svo_frame_in.track_seq reads its pass-1 rows (frozen
+ * map-point descriptors of the last frame's keypoints), their liveness, the local map and the pass-1 links from the
+ * sequence's state, and advances the state on the device afterwards: every current keypoint keeps the point that
+ * claimed it, or gets a new point when its stereo depth is > 0 and it lies outside every offline box grown by
+ * 5 px (frame::createmappoint, src/frame.cc:182-238); points created `window` or more frames ago, and points the
+ * pass-1 veto marked bad, leave the local map.  The BF matcher's train set is the last frame's own descriptors
+ * (find_feature_matches re-extracts both images, src/pnpmatch.cc:253-300), also kept in the state.  Only images
+ * cross PCIe per frame.
+ * The pass-2 scan order is: surviving points in their previous order, then the new points in keypoint order (the
+ * reference walks a std::set<mappoint*> in pointer order, i.e. an arbitrary one).
+ * ------------------------------------------------------------------------- */
+/* n_sequences independent states; map_capacity rows each (<= max_rows); window = 4 in the reference. */
+int svo_track_create(svo_ctx *ctx, int n_sequences, int map_capacity, int window);
+/* Empty state (no previous frame, empty map); optionally seeded with n_ballast map rows that never age out
+ * (ballast: 32 bytes each; benchmarks use it to hold the local map at a fixed size).  Synchronous. */
+int svo_track_reset(svo_ctx *ctx, int seq, const uint8_t *ballast, int n_ballast);
+/* Test tap: the sequence's current state copied to caller buffers (any pointer may be NULL).  prev_* / last_desc:
+ * capacity kp rows (svo_track_kp_capacity), map_*: map_capacity rows.  n_prev / n_map are filled in.  Synchronous. */
+typedef struct svo_track_view {
+    int32_t n_prev, n_map;
+    uint8_t *last_desc;      /* n_prev x 32: the last frame's own descriptors (train set of find_feature_matches)     */
+    uint8_t *prev_desc;      /* n_prev x 32: frozen m_descriptor of the point each keypoint of the last frame owns    */
+    uint8_t *prev_live;      /* n_prev: 1 = LastFrame.MapPoints[i] != NULL                                            */
+    int32_t *prev_map_row;   /* n_prev: the owned point's row in the local map, -1 = none / aged out of the map       */
+    int32_t *prev_create;    /* n_prev: mappoint::create_id of the owned point, -1 = none                             */
+    float *prev_xyz;         /* n_prev x 3: the owned point in the camera frame of its creating frame                  */
+    float *prev_xy;          /* n_prev x 2: keypoints_l[i].pt                                                          */
+    uint8_t *map_desc;       /* n_map x 32                                                                             */
+    int32_t *map_create;     /* n_map: create_id (INT32_MAX = ballast)                                                 */
+    int32_t *map_link;       /* n_map: keypoint of the last frame that owns the same point, -1 = none                  */
+    float *map_xyz;          /* n_map x 3                                                                              */
+} svo_track_view;
+int svo_track_state(svo_ctx *ctx, int seq, svo_track_view *view);
+/* Rows of the per-keypoint arrays (the context's keypoint capacity per image). */
+int svo_track_kp_capacity(const svo_ctx *ctx);
 
 /* Pinned host / device memory helpers for callers that want zero staging. */
 void *svo_alloc_pinned(svo_ctx *ctx, size_t bytes);

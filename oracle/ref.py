@@ -134,6 +134,7 @@ def lib():
         L.ref_localmap_new.restype = C.c_void_p
         L.ref_localmap_size.argtypes = [C.c_void_p]
         L.ref_localmap_list.argtypes = [C.c_void_p] * 6 + [C.c_int]
+        L.ref_localmap_age.argtypes = [C.c_void_p, C.c_int]
         L.ref_frame_createmappoint.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_pose_estimation_pnp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_frame_counts.argtypes = [C.c_void_p] * 4
@@ -161,6 +162,10 @@ class LocalMap:
 
     def __len__(self):
         return lib().ref_localmap_size(self.h)
+
+    def age(self, frame_num):
+        """The 4-frame window of Tracking::Track (src/Tracking.cc:239-250)."""
+        return lib().ref_localmap_age(self.h, int(frame_num))
 
     def list(self):
         """Map points in the set's own iteration order (what pass 2 walks)."""
@@ -260,3 +265,31 @@ def run_two_frames(frames, disps, K, bf, boxes, pose0=None):
     d0, z0 = f0.images()
     return dict(f0=s0, created=created, before=before, cur=f1.state(), last=last.state(), map=lm.list(),
                 F=dict(LOG["fundamental"][-1]), pnp=dict(LOG["pnp"][-1]), disp0=d0, depth0=z0)
+
+
+def run_sequence(frames, disps, K, bf, boxes_per_frame):
+    """n stereo frames through the reference as Tracking::Track drives it (src/Tracking.cc:184, :225-250): per frame
+    featuredetect, the dense disparity standing in for frame::MB, computekeypoint_r, disp2Depth, poseEstimationPnP against
+    the last frame and the local map (frame 0: the map points Tracking::init / createmappoint make), then
+    lastframe = frame(currentframe), createmappoint and the 4-frame window.  Optimizer::PoseOptimization (g2o, not built
+    here) only refines the pose and is left out: nothing on the matching path reads it.
+    Returns one record per frame: the current frame's state after the matching, the fundamental matrix it used, the last
+    frame's state and the local map (in the set's own order) after createmappoint + ageing."""
+    lm = LocalMap()
+    last = None
+    out = []
+    for t, ((L, R), disp) in enumerate(zip(frames, disps)):
+        LOG["fundamental"].clear()
+        cur = Frame(L, R, K, bf, boxes_per_frame[t], 0.1 * t, t)
+        cur.featuredetect(); cur.set_disp(disp); cur.stereo()
+        map_before = lm.list()
+        if last is not None:
+            cur.pose_estimation_pnp(last, lm, K)                  # Tracking.cc:114
+        rec = dict(cur=cur.state(), map_before=map_before, last_after_match=None if last is None else last.state(),
+                   F=dict(LOG["fundamental"][-1])["F"] if LOG["fundamental"] else None)
+        last = cur.copy()                                         # :237
+        rec["created"] = last.createmappoint(lm)                  # :238
+        rec["erased"] = lm.age(t)                                 # :239-250
+        rec["last"] = last.state(); rec["map"] = lm.list()
+        out.append(rec)
+    return out

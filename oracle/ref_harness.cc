@@ -108,6 +108,20 @@ int ref_frame_createmappoint(void *f, void *lm)                                 
     return (int)(s.size() - before);
 }
 
+// The local-map window of Tracking::Track (src/Tracking.cc:239-250), restated here because Tracking.cc itself needs
+// Pangolin and is not compiled: when frame_num >= 4, every point with create_id <= frame_num - 4 leaves the set.
+int ref_localmap_age(void *lm, int frame_num)
+{
+    std::set<mappoint *> &s = *(std::set<mappoint *> *)lm;
+    int erased = 0;
+    if (frame_num >= 4)
+        for (auto it = s.begin(); it != s.end();) {
+            if ((*it)->create_id <= frame_num - 4) { s.erase(it++); ++erased; }
+            else ++it;
+        }
+    return erased;
+}
+
 // pnpmatch::poseEstimationPnP(currentframe, lastframe, localmappoints, mVelocity, K)   (src/Tracking.cc:114)
 int ref_pose_estimation_pnp(void *cur, void *last, void *lm, const float *K9)
 {

@@ -1434,6 +1434,15 @@ void launch_pass1_fused(const PairArgs &p0, const BfArgs &b, int nframes, cudaSt
         tc.b_img = a.img_rows; tc.b_img_frame_stride = a.img_rows_stride;
         launch_tc_hamming(tc, TC_PAIRS, nframes, st, launches);
         --*launches;
+        if (p.bf_last.tab) {   // tracked frames: the per-query minima once more, over the last frame's own descriptors (no candidates: T = 0)
+            MatchSet last = a.rows;
+            last.tab = p.bf_last.tab;
+            ex.set = last; ex.img = p.img_last; ex.img_frame_stride = p.img_last_stride;
+            launch_tc_expand(ex, nframes, st, launches);
+            TcArgs tb = tc;
+            tb.B = last; tb.b_img = p.img_last; tb.b_img_frame_stride = p.img_last_stride; tb.T = 0;
+            launch_tc_hamming(tb, TC_PAIRS, nframes, st, launches);
+        }
     } else k_pairs<<<dim3(tiles, splits, nframes), M_THREADS, 0, st>>>(p);
     if (ev1) cudaEventRecord(ev1, st);
     k_bf_finish<<<dim3((maxN + 255) / 256, nframes), 256, 0, st>>>(p, b);

@@ -49,6 +49,8 @@ struct HostArena {           // pinned mirror of one lane's outputs
     int *bf_idx, *bf_dist; uint8_t *bf_keep;
     int *p1_best_idx, *p1_best, *p1_second; uint8_t *p1_row_claimed, *p1_row_bad, *p2_row_claimed;
     int *claim_row;
+    int *np_out;             // [2][B] n_prev / n_map as the device used them
+    int *mp_create; float *mp_xyz;   // tracked frames (allocated by svo_track_create)
     int *params;             // staging for the per-batch parameter upload
 };
 
@@ -74,7 +76,7 @@ struct Lane {
     cudaEvent_t done;
     cudaEvent_t ev[N_EVENTS];
     int slot0, frame0, nframes;
-    bool busy, veto;
+    bool busy, veto, tracked;
     HostArena h;
     std::vector<svo_frame_in> in;
     uint8_t *d_stage;          // landing zone for the host inputs of a batch (images, descriptors, flags)
@@ -104,6 +106,15 @@ struct svo_ctx {
     FramePtrs *sync_fp_d, *sync_fp_h;
     int *sync_str_d, *sync_str_h;
     bool profiling;
+    // device-resident tracker states (svo_track_create)
+    int trk_n, trk_cap, trk_window;
+    TrackState *trk_d;                   // [seq][2] on the device
+    std::vector<TrackState> trk_h;       // host mirror of the pointer values
+    std::vector<int> trk_parity;         // which copy is current
+    std::vector<int> trk_last_lane;      // lane whose batch last advanced the sequence, -1 = none
+    int *trk_scratch;                    // [batch frames][map_cap]
+    int *trk_mp_create; float *trk_mp_xyz;   // [batch frames][kp_cap], [..][3]: point owned by each current keypoint after the frame
+    uint8_t *trk_img_last;               // [batch frames] operand images of the last frames' own descriptors (BF train set)
     long long *tc_prof;      // in-kernel timeline of the tensor-core matchers (SVO_B200_TC_PROF=1), else NULL
     bool use_tc;             // tensor-core Hamming tiles in the batch matchers (default; SVO_B200_TC=0 selects the SIMT kernels)
     bool sync_have[2];
@@ -424,7 +435,10 @@ bool device_readable(const void *p)
 struct Seg { const uint8_t *src; size_t bytes; const void **field; bool need16; };
 
 // Kernels, memsets and D2H copies of one batch on the lane's stream (capturable: no host-dependent arguments).
-int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, bool fused, bool windowed, bool veto, cudaEvent_t *ev)
+// phase 0: everything; 1: input repack + extraction only; 2: stereo, matching, tracker update and result copies only (the
+// two halves of a TRACKED batch: the second waits for the previous batch to have advanced the tracker states)
+int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, bool fused, bool windowed, bool veto, bool tracked,
+                    int phase, cudaEvent_t *ev)
 {
     const Geom &g = ctx->g;
     const Bufs &b = ctx->b;
@@ -432,14 +446,19 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
     cudaStream_t st = L.st;
     const int R = fb.row_stride, K = fb.col_stride;
     const int FT = fb.nframes;
-    launch_unpack(b, g, L.slot0, 2 * n, L.d_fp, L.d_strides, st, &ctx->launches);
-    CU(cudaMemsetAsync(fb.claimed + (size_t)L.frame0 * K, 0, (size_t)n * K, st));
-    CU(cudaMemsetAsync(fb.claim_row + (size_t)L.frame0 * K, 0xff, sizeof(int) * (size_t)n * K, st));
-    // ---- extraction of 2n images
     // Outside profiling runs the sequence has two branches (it is captured into a graph, so they are graph forks):
     // blur beside the keypoint selection, and stereo + the keypoint/descriptor/stereo D2H beside the matchers.
     const bool fork = ev == nullptr && L.side != nullptr;
-    enqueue_extract(ctx, L.slot0, 2 * n, st, ev, fork ? L.side : nullptr, L.fk[0], L.fk[1]);
+    if (phase != 2) {
+        launch_unpack(b, g, L.slot0, 2 * n, L.d_fp, L.d_strides, st, &ctx->launches);
+        CU(cudaMemsetAsync(fb.claimed + (size_t)L.frame0 * K, 0, (size_t)n * K, st));
+        CU(cudaMemsetAsync(fb.claim_row + (size_t)L.frame0 * K, 0xff, sizeof(int) * (size_t)n * K, st));
+        // ---- extraction of 2n images
+        enqueue_extract(ctx, L.slot0, 2 * n, st, ev, fork ? L.side : nullptr, L.fk[0], L.fk[1]);
+        if (phase == 1) return SVO_OK;
+    }
+    if (tracked)   // the tracked frames' row counts come from their states
+        launch_track_load(L.d_fp, fb.params + L.frame0, fb.params + FT + L.frame0, n, st, &ctx->launches);
     cudaStream_t ss = fork ? L.side : st;     // stream of the stereo branch
     if (fork) { CU(cudaEventRecord(L.fk[2], st)); CU(cudaStreamWaitEvent(ss, L.fk[2], 0)); }
     // ---- sparse stereo
@@ -482,6 +501,7 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
         MatchSet prev_set = make_set(nullptr, d_nprev, 1, R, 0);
         prev_set.tab = reinterpret_cast<const uint8_t *const *>(&L.d_fp->prev);
         ba.q = cur; ba.t = prev_set;
+        if (tracked) ba.t.tab = reinterpret_cast<const uint8_t *const *>(&L.d_fp->last);   // BF train set: the last frame's own descriptors
         ba.idx = fb.bf_idx + (size_t)L.frame0 * K; ba.dist = fb.bf_dist + (size_t)L.frame0 * K;
         ba.keep = fb.bf_keep + (size_t)L.frame0 * K; ba.min_dist = fb.min_dist + L.frame0;
         ga.rows = prev_set;
@@ -504,8 +524,14 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
             pa.dmat_pitch = fb.dmat_pitch; pa.bf_key = fb.bf_key + (size_t)L.frame0 * K; pa.T = 0; pa.lane_cols = 0;
             pa.use_tc = ctx->use_tc ? 1 : 0; pa.skip_scores = ctx->cfg.skip_match_score ? 1 : 0;
             // match_score (k_scores_m) feeds nothing downstream: on the side branch it runs beside pass 2
+            memset(&pa.bf_last, 0, sizeof(pa.bf_last)); pa.img_last = nullptr; pa.img_last_stride = 0;
+            if (tracked && ctx->use_tc) {   // the BF train set (the last frame's own descriptors) is not the pass-1 row set (frozen m_descriptors)
+                pa.bf_last.tab = reinterpret_cast<const uint8_t *const *>(&L.d_fp->last);
+                pa.img_last = ctx->trk_img_last + (size_t)L.frame0 * fb.img_col_stride; pa.img_last_stride = fb.img_col_stride;
+            }
             launch_pass1_fused(pa, ba, n, st, &ctx->launches, ev ? ev[12] : nullptr, ev ? ev[13] : nullptr,
                                fork ? ss : nullptr, L.fk[4]);
+            if (tracked && !ctx->use_tc) launch_bf(ba, n, st, &ctx->launches);   // SIMT matchers: a separate BF scan over that set
         } else {
             launch_bf(ba, n, st, &ctx->launches);
             launch_greedy(ga, n, !ctx->cfg.skip_match_score, st, &ctx->launches);
@@ -556,6 +582,20 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
     if (ev) cudaEventRecord(ev[10], st);
     // ---- D2H: one copy per output array for the whole batch
     if (fork) { CU(cudaEventRecord(L.fk[3], ss)); CU(cudaStreamWaitEvent(st, L.fk[3], 0)); }   // join the side branch
+    if (tracked) {   // advance the tracker states (needs the claims and the stereo depths)
+        TrackUpdateArgs ta;
+        ta.fp = L.d_fp; ta.nkp = b.nkp + L.slot0; ta.kp = b.kp + (size_t)L.slot0 * g.kp_cap; ta.desc = b.desc + (size_t)L.slot0 * g.kp_cap * 32;
+        ta.claim_row = fb.claim_row + (size_t)L.frame0 * K; ta.depth = fb.depth + (size_t)L.frame0 * K; ta.col_stride = K;
+        ta.p1_row_bad = veto ? fb.p1_row_bad + (size_t)L.frame0 * R : nullptr; ta.row_stride = R;
+        ta.kp_cap = g.kp_cap; ta.map_cap = ctx->trk_cap; ta.window = ctx->trk_window;
+        ta.scratch = ctx->trk_scratch + (size_t)L.frame0 * ctx->trk_cap;
+        ta.mp_create = ctx->trk_mp_create + (size_t)L.frame0 * K; ta.mp_xyz = ctx->trk_mp_xyz + (size_t)L.frame0 * K * 3;
+        launch_track_update(ta, n, st, &ctx->launches);
+        CU(cudaMemcpyAsync(h.mp_create, ta.mp_create, sizeof(int) * n * KC, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h.mp_xyz, ta.mp_xyz, sizeof(float) * 3 * n * KC, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaMemcpyAsync(h.np_out, fb.params + L.frame0, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h.np_out + ctx->cfg.max_batch, fb.params + FT + L.frame0, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h.status, b.status + L.slot0, sizeof(int) * I, cudaMemcpyDeviceToHost, st));
     if (!fork) {
         CU(cudaMemcpyAsync(h.nkp, b.nkp + L.slot0, sizeof(int) * I, cudaMemcpyDeviceToHost, st));
@@ -627,6 +667,8 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
     ctx->cfg = *cfg; ctx->launches = 0; ctx->profiling = false; ctx->err[0] = 0;
     { const char *e = getenv("SVO_B200_TC"); ctx->use_tc = !(e && e[0] == '0'); }
     ctx->tc_prof = nullptr;
+    ctx->trk_n = 0; ctx->trk_cap = 0; ctx->trk_window = 4; ctx->trk_d = nullptr; ctx->trk_scratch = nullptr;
+    ctx->trk_mp_create = nullptr; ctx->trk_mp_xyz = nullptr; ctx->trk_img_last = nullptr;
     ctx->sync_st = nullptr; ctx->sync_have[0] = ctx->sync_have[1] = false;
     ctx->sync_stage = nullptr;
     if (ctx->cfg.max_channels == 0) ctx->cfg.max_channels = 1;
@@ -744,7 +786,8 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
         TRY(halloc(ctx, &h.p1_best_idx, B * R)); TRY(halloc(ctx, &h.p1_best, B * R)); TRY(halloc(ctx, &h.p1_second, B * R));
         TRY(halloc(ctx, &h.p1_row_claimed, B * R)); TRY(halloc(ctx, &h.p1_row_bad, B * R)); TRY(halloc(ctx, &h.p2_row_claimed, B * R));
         TRY(halloc(ctx, &h.claim_row, B * K));
-        TRY(halloc(ctx, &h.params, 4 * B));
+        TRY(halloc(ctx, &h.params, 4 * B)); TRY(halloc(ctx, &h.np_out, 2 * B));
+        h.mp_create = nullptr; h.mp_xyz = nullptr; l.tracked = false;
         l.stage_cap = I * ctx->stage_img_bytes + B * (R * 32 * 2 + R * 5 + R * 12 + R * 8 + R * 16 + SVO_MAX_BOXES * 16 + 72) + (12 * B + 8) * 512;
         TRY(dalloc(ctx, &l.d_stage, l.stage_cap));
         TRY(dalloc(ctx, &l.d_fp, B)); TRY(halloc(ctx, &l.h_fp, B));
@@ -1126,6 +1169,87 @@ int svo_disp2depth(svo_ctx *ctx, const float *disp, float *depth, size_t n, floa
     return SVO_OK;
 }
 
+// ----------------------------------------------------------------------------- device-resident tracker state
+int svo_track_kp_capacity(const svo_ctx *ctx) { return ctx ? ctx->g.kp_cap : SVO_E_INVALID; }
+
+int svo_track_create(svo_ctx *ctx, int n_sequences, int map_capacity, int window)
+{
+    if (!ctx || n_sequences < 1 || map_capacity < 1 || map_capacity > ctx->cfg.max_rows || window < 1)
+        return fail(ctx, SVO_E_INVALID, "svo_track_create: bad argument (map_capacity must lie in 1..max_rows = %d)", ctx ? ctx->cfg.max_rows : 0);
+    if (ctx->trk_n) return fail(ctx, SVO_E_INVALID, "svo_track_create: the context already has tracker states");
+    CU(cudaSetDevice(ctx->cfg.device));
+    const size_t S = 2 * (size_t)n_sequences, K = ctx->g.kp_cap, C = map_capacity, FT = ctx->fb.nframes;
+    uint8_t *last_desc, *prev_desc, *prev_live, *map_desc;
+    int *prev_map_row, *prev_create, *n_prev, *map_create, *map_link, *n_map;
+    float *prev_xyz, *prev_xy, *map_xyz;
+    TRY(dalloc(ctx, &last_desc, S * K * 32)); TRY(dalloc(ctx, &prev_desc, S * K * 32)); TRY(dalloc(ctx, &prev_live, S * K));
+    TRY(dalloc(ctx, &prev_map_row, S * K)); TRY(dalloc(ctx, &prev_create, S * K)); TRY(dalloc(ctx, &prev_xyz, S * K * 3));
+    TRY(dalloc(ctx, &prev_xy, S * K * 2)); TRY(dalloc(ctx, &n_prev, S));
+    TRY(dalloc(ctx, &map_desc, S * C * 32)); TRY(dalloc(ctx, &map_create, S * C)); TRY(dalloc(ctx, &map_link, S * C));
+    TRY(dalloc(ctx, &map_xyz, S * C * 3)); TRY(dalloc(ctx, &n_map, S));
+    ctx->trk_h.resize(S);
+    for (size_t i = 0; i < S; ++i) {
+        TrackState &t = ctx->trk_h[i];
+        t.last_desc = last_desc + i * K * 32; t.prev_desc = prev_desc + i * K * 32; t.prev_live = prev_live + i * K;
+        t.prev_map_row = prev_map_row + i * K; t.prev_create = prev_create + i * K; t.prev_xyz = prev_xyz + i * K * 3;
+        t.prev_xy = prev_xy + i * K * 2; t.n_prev = n_prev + i;
+        t.map_desc = map_desc + i * C * 32; t.map_create = map_create + i * C; t.map_link = map_link + i * C;
+        t.map_xyz = map_xyz + i * C * 3; t.n_map = n_map + i;
+    }
+    TRY(dalloc(ctx, &ctx->trk_d, S));
+    CU(cudaMemcpy(ctx->trk_d, ctx->trk_h.data(), sizeof(TrackState) * S, cudaMemcpyHostToDevice));
+    TRY(dalloc(ctx, &ctx->trk_scratch, FT * C));
+    TRY(dalloc(ctx, &ctx->trk_mp_create, FT * K)); TRY(dalloc(ctx, &ctx->trk_mp_xyz, FT * K * 3));
+    TRY(dalloc(ctx, &ctx->trk_img_last, FT * ctx->fb.img_col_stride));
+    for (Lane &l : ctx->lanes) {
+        const size_t B = ctx->cfg.max_batch;
+        TRY(halloc(ctx, &l.h.mp_create, B * K)); TRY(halloc(ctx, &l.h.mp_xyz, B * K * 3));
+    }
+    ctx->trk_parity.assign(n_sequences, 0);
+    ctx->trk_last_lane.assign(n_sequences, -1);
+    ctx->trk_n = n_sequences; ctx->trk_cap = map_capacity; ctx->trk_window = window;
+    return SVO_OK;
+}
+
+int svo_track_reset(svo_ctx *ctx, int seq, const uint8_t *ballast, int n_ballast)
+{
+    if (!ctx || seq < 0 || seq >= ctx->trk_n || n_ballast < 0 || n_ballast > ctx->trk_cap || (n_ballast && !ballast))
+        return fail(ctx, SVO_E_INVALID, "svo_track_reset: bad argument");
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaDeviceSynchronize());                         // no batch may still be reading or advancing the state
+    const TrackState &t = ctx->trk_h[2 * (size_t)seq + ctx->trk_parity[seq]];
+    const int zero = 0;
+    CU(cudaMemcpy(t.n_prev, &zero, sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(t.n_map, &n_ballast, sizeof(int), cudaMemcpyHostToDevice));
+    if (n_ballast) {
+        std::vector<int> v((size_t)n_ballast, INT_MAX);
+        CU(cudaMemcpy(t.map_desc, ballast, (size_t)n_ballast * 32, cudaMemcpyDefault));
+        CU(cudaMemcpy(t.map_create, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice));
+        CU(cudaMemset(t.map_link, 0xff, sizeof(int) * (size_t)n_ballast));
+        CU(cudaMemset(t.map_xyz, 0, sizeof(float) * 3 * (size_t)n_ballast));
+    }
+    ctx->trk_last_lane[seq] = -1;
+    return SVO_OK;
+}
+
+int svo_track_state(svo_ctx *ctx, int seq, svo_track_view *v)
+{
+    if (!ctx || !v || seq < 0 || seq >= ctx->trk_n) return fail(ctx, SVO_E_INVALID, "svo_track_state: bad argument");
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaDeviceSynchronize());
+    const TrackState &t = ctx->trk_h[2 * (size_t)seq + ctx->trk_parity[seq]];
+    CU(cudaMemcpy(&v->n_prev, t.n_prev, sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&v->n_map, t.n_map, sizeof(int), cudaMemcpyDeviceToHost));
+    const size_t np = (size_t)std::min(v->n_prev, ctx->g.kp_cap), nm = (size_t)std::min(v->n_map, ctx->trk_cap);
+    auto get = [&](void *dst, const void *src, size_t bytes) { return (dst && bytes) ? cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) : cudaSuccess; };
+    CU(get(v->last_desc, t.last_desc, np * 32)); CU(get(v->prev_desc, t.prev_desc, np * 32)); CU(get(v->prev_live, t.prev_live, np));
+    CU(get(v->prev_map_row, t.prev_map_row, np * 4)); CU(get(v->prev_create, t.prev_create, np * 4));
+    CU(get(v->prev_xyz, t.prev_xyz, np * 12)); CU(get(v->prev_xy, t.prev_xy, np * 8));
+    CU(get(v->map_desc, t.map_desc, nm * 32)); CU(get(v->map_create, t.map_create, nm * 4)); CU(get(v->map_link, t.map_link, nm * 4));
+    CU(get(v->map_xyz, t.map_xyz, nm * 12));
+    return SVO_OK;
+}
+
 // ----------------------------------------------------------------------------- batch API
 int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n)
 {
@@ -1142,27 +1266,34 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
     cudaEvent_t *ev = ctx->profiling ? L.ev : nullptr;
     bool any_prev = false, any_map = false;
     int n_win = 0, n_mapped = 0;
-    bool veto = false;
+    bool veto = false, tracked = false;
     for (int i = 0; i < n; ++i) {
         const svo_frame_in &f = frames[i];
+        if (f.track_seq) {
+            if (f.track_seq < 0 || f.track_seq > ctx->trk_n) return fail(ctx, SVO_E_INVALID, "svo_batch_submit: frame %d: track_seq %d of %d (svo_track_create)", i, f.track_seq, ctx->trk_n);
+            for (int k = 0; k < i; ++k)
+                if (frames[k].track_seq == f.track_seq) return fail(ctx, SVO_E_INVALID, "svo_batch_submit: sequence %d appears twice in one batch", f.track_seq - 1);
+            tracked = true;
+        }
         if (f.n_boxes < 0 || f.n_boxes > SVO_MAX_BOXES || (f.n_boxes && !f.boxes))
             return fail(ctx, SVO_E_INVALID, "svo_batch_submit: frame %d: n_boxes %d (at most %d)", i, f.n_boxes, SVO_MAX_BOXES);
         if (f.F && ((uintptr_t)f.F & 7)) return fail(ctx, SVO_E_INVALID, "svo_batch_submit: frame %d: F must be 8-byte aligned", i);
-        veto |= f.n_prev > 0 && f.n_boxes > 0 && f.F && f.prev_xy;
-        if (f.n_map > 0) { ++n_mapped; if (f.map_win_uvr || (f.map_xyz && f.Tcw_pred)) ++n_win; }
+        veto |= f.n_boxes > 0 && f.F && (f.track_seq ? true : (f.n_prev > 0 && f.prev_xy != nullptr));
+        if (f.n_map > 0 && !f.track_seq) { ++n_mapped; if (f.map_win_uvr || (f.map_xyz && f.Tcw_pred)) ++n_win; }
         const int ch = f.channels == 3 ? 3 : 1;
-        if (!f.left || !f.right || f.stride < g.W * ch || f.stride >= SVO_STRIDE_BGR || f.n_prev < 0 || f.n_map < 0 || f.n_prev > R ||
-            f.n_map > R || (f.n_prev && !f.prev_desc) || (f.n_map && !f.map_desc) || !(f.baseline > 0.f) ||
+        if (!f.left || !f.right || f.stride < g.W * ch || f.stride >= SVO_STRIDE_BGR || !(f.baseline > 0.f) ||
+            (!f.track_seq && (f.n_prev < 0 || f.n_map < 0 || f.n_prev > R || f.n_map > R || (f.n_prev && !f.prev_desc) || (f.n_map && !f.map_desc))) ||
             (f.channels != 0 && f.channels != 1 && f.channels != 3) || ch > ctx->cfg.max_channels)
             return fail(ctx, SVO_E_INVALID, "svo_batch_submit: frame %d has bad inputs%s", i,
                         ch > ctx->cfg.max_channels ? " (BGR input needs svo_config.max_channels = 3)" : "");
-        any_prev |= f.n_prev > 0; any_map |= f.n_map > 0;
+        any_prev |= f.n_prev > 0 || f.track_seq; any_map |= f.n_map > 0 || f.track_seq;
     }
+    if (tracked && n_win) return fail(ctx, SVO_E_INVALID, "svo_batch_submit: projection windows and tracked frames cannot share a batch");
     if (n_win != 0 && n_win != n_mapped)
         return fail(ctx, SVO_E_INVALID, "svo_batch_submit: map_win_uvr (or map_xyz + Tcw_pred) must be given for every frame with a map, or for none");
     const bool windowed = n_win > 0;
     L.in.assign(frames, frames + n);
-    L.nframes = n; L.veto = veto;
+    L.nframes = n; L.veto = veto; L.tracked = tracked;
     if (ev) cudaEventRecord(ev[0], st);
     // ---- inputs: device-resident buffers are read in place; host buffers are gathered into the lane's
     // landing zone with one H2D copy per maximal run of adjacent source ranges (a strided 2-D copy of
@@ -1196,25 +1327,40 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
                 L.h_strides[2 * i + s] = 0;
             }
         }
-        place(f.n_prev ? f.prev_desc : nullptr, (size_t)f.n_prev * 32, (const void **)&P.prev, true);
-        place(f.n_prev ? f.prev_live : nullptr, (size_t)f.n_prev, (const void **)&P.prev_live, false);
-        place(f.n_map ? f.map_desc : nullptr, (size_t)f.n_map * 32, (const void **)&P.map, true);
-        place((f.n_map && f.n_prev) ? f.map_prev_row : nullptr, sizeof(int) * (size_t)f.n_map, (const void **)&P.map_prev_row, true);
-        place((f.n_map && windowed) ? f.map_win_uvr : nullptr, 3 * sizeof(float) * (size_t)f.n_map, (const void **)&P.map_win, false);
-        const bool proj = f.n_map && windowed && !f.map_win_uvr && f.map_xyz && f.Tcw_pred;
-        place(proj ? f.map_xyz : nullptr, 3 * sizeof(float) * (size_t)f.n_map, (const void **)&P.map_xyz, false);
-        place(proj ? f.map_octave : nullptr, sizeof(int) * (size_t)f.n_map, (const void **)&P.map_octave, false);
-        if (proj) {
-            if (device_readable(f.Tcw_pred)) return fail(ctx, SVO_E_INVALID, "svo_batch_submit: frame %d: Tcw_pred must be a host pointer", i);
-            memcpy(P.Tcw, f.Tcw_pred, sizeof(P.Tcw));
-            P.fx = f.fx; P.fy = f.fy; P.cx = f.cx; P.cy = f.cy; P.proj_th = f.proj_th;
+        P.trk_in = P.trk_out = nullptr; P.frame_id = f.frame_id;
+        P.fx = f.fx; P.fy = f.fy; P.cx = f.cx; P.cy = f.cy; P.proj_th = f.proj_th;
+        if (f.track_seq) {
+            // the sequence's state where it lies: this frame reads the current copy and its update writes the other one
+            const int sq = f.track_seq - 1, cur = ctx->trk_parity[sq];
+            const TrackState &t = ctx->trk_h[2 * (size_t)sq + cur];
+            P.prev = t.prev_desc; P.last = t.last_desc; P.prev_live = t.prev_live; P.map = t.map_desc; P.map_prev_row = t.map_link;
+            P.map_win = nullptr; P.map_xyz = nullptr; P.map_octave = nullptr;
+            P.trk_in = ctx->trk_d + 2 * (size_t)sq + cur; P.trk_out = ctx->trk_d + 2 * (size_t)sq + (cur ^ 1);
+            place(f.n_boxes ? f.boxes : nullptr, 4 * sizeof(int) * (size_t)f.n_boxes, (const void **)&P.boxes, false);   // createmappoint reads them too
+            place((f.n_boxes && f.F) ? f.F : nullptr, 9 * sizeof(double), (const void **)&P.F, false);
+            P.prev_xy = t.prev_xy;
+            P.n_boxes = f.n_boxes;
+            hp[i] = 0; hp[B + i] = 0;                     // k_track_load fills the counts in from the state
+        } else {
+            place(f.n_prev ? f.prev_desc : nullptr, (size_t)f.n_prev * 32, (const void **)&P.prev, true);
+            place(f.n_prev ? f.prev_live : nullptr, (size_t)f.n_prev, (const void **)&P.prev_live, false);
+            place(f.n_map ? f.map_desc : nullptr, (size_t)f.n_map * 32, (const void **)&P.map, true);
+            place((f.n_map && f.n_prev) ? f.map_prev_row : nullptr, sizeof(int) * (size_t)f.n_map, (const void **)&P.map_prev_row, true);
+            place((f.n_map && windowed) ? f.map_win_uvr : nullptr, 3 * sizeof(float) * (size_t)f.n_map, (const void **)&P.map_win, false);
+            const bool proj = f.n_map && windowed && !f.map_win_uvr && f.map_xyz && f.Tcw_pred;
+            place(proj ? f.map_xyz : nullptr, 3 * sizeof(float) * (size_t)f.n_map, (const void **)&P.map_xyz, false);
+            place(proj ? f.map_octave : nullptr, sizeof(int) * (size_t)f.n_map, (const void **)&P.map_octave, false);
+            if (proj) {
+                if (device_readable(f.Tcw_pred)) return fail(ctx, SVO_E_INVALID, "svo_batch_submit: frame %d: Tcw_pred must be a host pointer", i);
+                memcpy(P.Tcw, f.Tcw_pred, sizeof(P.Tcw));
+            }
+            const bool fv = f.n_prev > 0 && f.n_boxes > 0 && f.F && f.prev_xy;
+            place(fv ? f.boxes : nullptr, 4 * sizeof(int) * (size_t)f.n_boxes, (const void **)&P.boxes, false);
+            place(fv ? f.F : nullptr, 9 * sizeof(double), (const void **)&P.F, false);
+            place(fv ? f.prev_xy : nullptr, 2 * sizeof(float) * (size_t)f.n_prev, (const void **)&P.prev_xy, false);
+            P.n_boxes = fv ? f.n_boxes : 0;
+            hp[i] = f.n_prev; hp[B + i] = f.n_map;
         }
-        const bool fv = f.n_prev > 0 && f.n_boxes > 0 && f.F && f.prev_xy;
-        place(fv ? f.boxes : nullptr, 4 * sizeof(int) * (size_t)f.n_boxes, (const void **)&P.boxes, false);
-        place(fv ? f.F : nullptr, 9 * sizeof(double), (const void **)&P.F, false);
-        place(fv ? f.prev_xy : nullptr, 2 * sizeof(float) * (size_t)f.n_prev, (const void **)&P.prev_xy, false);
-        P.n_boxes = fv ? f.n_boxes : 0;
-        hp[i] = f.n_prev; hp[B + i] = f.n_map;
         memcpy(&hp[2 * B + i], &f.bf, 4); memcpy(&hp[3 * B + i], &f.baseline, 4);
     }
     std::sort(segs.begin(), segs.end(), [](const Seg &x, const Seg &y) { return x.src < y.src; });
@@ -1236,6 +1382,8 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
         cursor = dst + len;
         i = j;
     }
+    for (int i = 0; i < n; ++i)
+        if (!frames[i].track_seq) L.h_fp[i].last = L.h_fp[i].prev;      // one set serves the BF matcher and pass 1
     CU(cudaMemcpyAsync(L.d_fp, L.h_fp, sizeof(FramePtrs) * n, cudaMemcpyHostToDevice, st));
     // params live as [4][nframes_total] on the device; this lane owns columns frame0..frame0+B
     const int FT = fb.nframes;
@@ -1244,20 +1392,30 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
     CU(cudaMemcpyAsync(L.d_strides, L.h_strides, sizeof(int) * 2 * n, cudaMemcpyHostToDevice, st));
     bool fused = any_prev;
     for (int i = 0; i < n; ++i) fused = fused && frames[i].n_prev <= K;   // the distance matrix holds kp_cap rows
+    // A tracked frame's matching must see the state its sequence's previous frame left: when that frame ran on another
+    // lane, this lane waits for that lane's batch.  Extraction does not depend on the state, so the batch is split: its
+    // first half (repack + extraction) is enqueued before the wait and overlaps the other lane's matching.
+    std::vector<int> wait_lanes;
+    for (int i = 0; i < n; ++i)
+        if (frames[i].track_seq) {
+            const int ll = ctx->trk_last_lane[frames[i].track_seq - 1];
+            if (ll >= 0 && ll != lane_i && std::find(wait_lanes.begin(), wait_lanes.end(), ll) == wait_lanes.end()) wait_lanes.push_back(ll);
+        }
+    const bool split = !wait_lanes.empty();
     // ---- all kernels, memsets and result copies of the batch.  Their arguments depend only on (lane, n, which
     // stages run): every per-frame input is reached through device tables filled above.  Outside profiling runs
     // the sequence is therefore captured once into a CUDA graph and replayed (one launch instead of ~45 calls).
-    if (ev) {
-        TRY(enqueue_compute(ctx, L, n, any_prev, any_map, fused, windowed, veto, ev));
-    } else {
-        const int key = n | (any_prev ? 1 << 20 : 0) | (any_map ? 1 << 21 : 0) | (fused ? 1 << 22 : 0) | (windowed ? 1 << 23 : 0) | (veto ? 1 << 24 : 0);
+    auto run = [&](int phase) -> int {
+        if (ev) return enqueue_compute(ctx, L, n, any_prev, any_map, fused, windowed, veto, tracked, phase, ev);
+        const int key = n | (any_prev ? 1 << 20 : 0) | (any_map ? 1 << 21 : 0) | (fused ? 1 << 22 : 0) | (windowed ? 1 << 23 : 0) | (veto ? 1 << 24 : 0) |
+                        (tracked ? 1 << 25 : 0) | (phase << 26);
         LaneGraph *lg = nullptr;
         for (LaneGraph &c : L.graphs) if (c.key == key) lg = &c;
         if (!lg) {
             const long long before = ctx->launches;
             cudaGraph_t graph = nullptr;
             CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            const int rc = enqueue_compute(ctx, L, n, any_prev, any_map, fused, windowed, veto, nullptr);
+            const int rc = enqueue_compute(ctx, L, n, any_prev, any_map, fused, windowed, veto, tracked, phase, nullptr);
             const cudaError_t ce = cudaStreamEndCapture(st, &graph);
             if (rc != SVO_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
             if (ce != cudaSuccess) return fail(ctx, SVO_E_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
@@ -1271,10 +1429,18 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
         }
         CU(cudaGraphLaunch(lg->exec, st));
         ctx->launches += lg->launches;
-    }
+        return SVO_OK;
+    };
+    if (split) {
+        TRY(run(1));
+        for (int ll : wait_lanes) CU(cudaStreamWaitEvent(st, ctx->lanes[ll].done, 0));
+        TRY(run(2));
+    } else TRY(run(0));
     if (ev) cudaEventRecord(ev[11], st);
     CU(cudaEventRecord(L.done, st));
     CU(cudaGetLastError());
+    for (int i = 0; i < n; ++i)
+        if (frames[i].track_seq) { ctx->trk_parity[frames[i].track_seq - 1] ^= 1; ctx->trk_last_lane[frames[i].track_seq - 1] = lane_i; }
     L.busy = true;
     return SVO_OK;
 }
@@ -1309,7 +1475,8 @@ int svo_batch_result(svo_ctx *ctx, int lane_i, int i, svo_frame_out *o)
     o->kp_left = h.kp + (2 * (size_t)i) * K; o->kp_right = h.kp + (2 * (size_t)i + 1) * K;
     o->desc_left = h.desc + (2 * (size_t)i) * K * 32; o->desc_right = h.desc + (2 * (size_t)i + 1) * K * 32;
     o->u_right = h.u_right + (size_t)i * K; o->depth = h.depth + (size_t)i * K;
-    if (in.n_prev) {
+    o->n_prev = h.np_out[i]; o->n_map = h.np_out[ctx->cfg.max_batch + i];
+    if (in.n_prev || in.track_seq) {
         o->bf_idx = h.bf_idx + (size_t)i * K; o->bf_dist = h.bf_dist + (size_t)i * K; o->bf_keep = h.bf_keep + (size_t)i * K;
         if (!ctx->cfg.skip_match_score) {
             o->p1_best_idx = h.p1_best_idx + (size_t)i * R; o->p1_best = h.p1_best + (size_t)i * R;
@@ -1318,7 +1485,8 @@ int svo_batch_result(svo_ctx *ctx, int lane_i, int i, svo_frame_out *o)
         o->p1_row_claimed = h.p1_row_claimed + (size_t)i * R;
         if (L.veto) o->p1_row_bad = h.p1_row_bad + (size_t)i * R;     // NULL: no frame of the batch ran the veto
     }
-    if (in.n_map) o->p2_row_claimed = h.p2_row_claimed + (size_t)i * R;
+    if (in.n_map || in.track_seq) o->p2_row_claimed = h.p2_row_claimed + (size_t)i * R;
+    if (in.track_seq) { o->mp_create = h.mp_create + (size_t)i * K; o->mp_xyz = h.mp_xyz + (size_t)i * K * 3; }
     o->claim_row = h.claim_row + (size_t)i * K;
     return SVO_OK;
 }

@@ -96,11 +96,31 @@ __host__ __device__ inline int unpack_x(uint32_t v) { return (int)(v & 0xfffu); 
 __host__ __device__ inline int unpack_y(uint32_t v) { return (int)((v >> 12) & 0xfffu); }
 __host__ __device__ inline int unpack_s(uint32_t v) { return (int)(v >> 24); }
 
+// Device-resident tracker state of one sequence (track.cu), one of its two ping-pong copies.
+struct TrackState {
+    // what Tracking keeps of the last frame (lastframe, src/Tracking.cc:237-238): one entry per keypoint
+    uint8_t *last_desc;      // [kp_cap][32] the last frame's own f_descriptor (train set of find_feature_matches)
+    uint8_t *prev_desc;      // [kp_cap][32] frozen m_descriptor of the map point the keypoint owns (pass-1 rows)
+    uint8_t *prev_live;      // [kp_cap] 1 = owns a live map point
+    int *prev_map_row;       // [kp_cap] that point's row in the local map, -1 = not in the map
+    int *prev_create;        // [kp_cap] id of the frame that created the owned point, -1 = none
+    float *prev_xyz;         // [kp_cap][3] the owned point in the camera frame of its creating frame (UnprojectStereo before Rwc / twc)
+    float *prev_xy;          // [kp_cap][2] keypoints_l[i].pt (the veto's `last`)
+    int *n_prev;             // [1]
+    // LocalMapPoints in scan order
+    uint8_t *map_desc;       // [map_cap][32] frozen descriptors
+    int *map_create;         // [map_cap] id of the frame that created the point (INT_MAX: ballast, never ages out)
+    int *map_link;           // [map_cap] keypoint of the last frame owning the same point, -1 = none (map_prev_row)
+    float *map_xyz;          // [map_cap][3]
+    int *n_map;              // [1]
+};
+
 // Per-frame input pointers of a batch (device table).  Inputs that already live in device memory are read in
 // place; host inputs are gathered into the lane's landing zone with as few H2D copies as their layout allows.
 struct FramePtrs {
     const uint8_t *left, *right;   // gray images (rows `stride` bytes apart)
-    const uint8_t *prev;           // n_prev x 32, 16-byte aligned
+    const uint8_t *prev;           // n_prev x 32, 16-byte aligned: pass-1 rows
+    const uint8_t *last;           // n_prev x 32: train set of the BF matcher (== prev unless the frame is tracked)
     const uint8_t *prev_live;      // n_prev or NULL (all live)
     const uint8_t *map;            // n_map x 32, 16-byte aligned
     const int *map_prev_row;       // n_map or NULL
@@ -115,6 +135,9 @@ struct FramePtrs {
     const int *map_octave;         // n_map or NULL
     float Tcw[12];                 // first three rows of the predicted pose
     float fx, fy, cx, cy, proj_th;
+    // device-resident tracker state (track.cu): the copy this frame reads and the copy its update writes; NULL = untracked
+    const TrackState *trk_in, *trk_out;
+    int frame_id;
 };
 
 // ---- stage launchers (each enqueues on `st` for images [slot0, slot0 + nimg)) ----
@@ -242,6 +265,9 @@ struct PairArgs {            // fused BF + pass-1 front of the batch path (match
     int T, lane_cols;        // filled by the launcher
     int skip_scores;         // 1: match_score (best_idx / best / second of every row) is not computed
     int use_tc;              // 1: tensor-core tiles (tcham.cu) instead of k_pairs / k_scores_m; dmat is not touched
+    // tracked batches (track.cu): the BF train set is another descriptor set than the pass-1 rows (same counts): its
+    // per-frame pointer table and operand images; tab == NULL: the row set serves both
+    MatchSet bf_last; uint8_t *img_last; size_t img_last_stride;
 };
 void launch_pass1_fused(const PairArgs &p, const BfArgs &b, int nframes, cudaStream_t st, long long *launches,
                         cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,   // optional events around k_pairs
@@ -272,6 +298,20 @@ struct TcArgs {
 void launch_tc_expand(const TcExpandArgs &e, int nframes, cudaStream_t st, long long *launches);
 void launch_tc_hamming(const TcArgs &p, int mode, int nframes, cudaStream_t st, long long *launches);
 int setup_tc_attributes();
+
+// ---- device-resident tracker state (track.cu) ----
+struct TrackUpdateArgs {
+    const FramePtrs *fp;
+    const int *nkp;              // [frame * 2] left keypoint counts of the batch's slots
+    const svo_keypoint *kp; const uint8_t *desc;   // left image of frame f at kp + f * 2 * kp_cap
+    const int *claim_row; const float *depth; int col_stride;
+    const uint8_t *p1_row_bad; int row_stride;
+    int kp_cap, map_cap, window;
+    int *scratch;                // [frame][map_cap]
+    int *mp_create; float *mp_xyz;   // [frame][col_stride], [frame][col_stride][3]: the point each current keypoint owns after the frame
+};
+void launch_track_load(const FramePtrs *fp, int *n_prev, int *n_map, int n, cudaStream_t st, long long *launches);
+void launch_track_update(const TrackUpdateArgs &a, int n, cudaStream_t st, long long *launches);
 
 // ---- pose stage (pose.cu) ----
 struct PoseHdr { int off, n; float fx, fy, cx, cy; float Tcw[16]; };   // one problem: points [off, off + n) of the packed arrays

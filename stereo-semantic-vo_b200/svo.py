@@ -42,7 +42,8 @@ class FrameIn(C.Structure):
                 ("map_win_uvr", C.c_void_p),
                 ("boxes", C.c_void_p), ("n_boxes", C.c_int), ("F", C.c_void_p), ("prev_xy", C.c_void_p),
                 ("map_xyz", C.c_void_p), ("map_octave", C.c_void_p), ("Tcw_pred", C.c_void_p),
-                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("proj_th", C.c_float)]
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("proj_th", C.c_float),
+                ("track_seq", C.c_int), ("frame_id", C.c_int)]
 
 
 class FrameOut(C.Structure):
@@ -52,7 +53,15 @@ class FrameOut(C.Structure):
                 ("bf_idx", C.c_void_p), ("bf_dist", C.c_void_p), ("bf_keep", C.c_void_p),
                 ("p1_best_idx", C.c_void_p), ("p1_best", C.c_void_p), ("p1_second", C.c_void_p),
                 ("p1_row_claimed", C.c_void_p), ("p1_row_bad", C.c_void_p), ("p2_row_claimed", C.c_void_p),
-                ("claim_row", C.c_void_p)]
+                ("claim_row", C.c_void_p), ("n_prev", C.c_int32), ("n_map", C.c_int32),
+                ("mp_create", C.c_void_p), ("mp_xyz", C.c_void_p)]
+
+
+class TrackView(C.Structure):
+    _fields_ = [("n_prev", C.c_int32), ("n_map", C.c_int32), ("last_desc", C.c_void_p), ("prev_desc", C.c_void_p),
+                ("prev_live", C.c_void_p), ("prev_map_row", C.c_void_p), ("prev_create", C.c_void_p), ("prev_xyz", C.c_void_p),
+                ("prev_xy", C.c_void_p), ("map_desc", C.c_void_p), ("map_create", C.c_void_p), ("map_link", C.c_void_p),
+                ("map_xyz", C.c_void_p)]
 
 
 class PoseProblem(C.Structure):
@@ -76,7 +85,8 @@ EXPORTS = ["svo_default_config", "svo_version", "svo_create", "svo_destroy", "sv
            "svo_batch_submit", "svo_batch_wait", "svo_batch_result", "svo_alloc_pinned", "svo_free_pinned",
            "svo_alloc_device", "svo_free_device", "svo_copy_to_device", "svo_launch_count", "svo_batch_stage_ms",
            "svo_set_profiling", "svo_lane_stream", "svo_debug_tap", "svo_debug_retain_best",
-           "svo_pnp_ransac", "svo_pose_optimize", "svo_debug_hamming_matrix", "svo_debug_tc_profile", "svo_project_map"]
+           "svo_pnp_ransac", "svo_pose_optimize", "svo_debug_hamming_matrix", "svo_debug_tc_profile", "svo_project_map",
+           "svo_track_create", "svo_track_reset", "svo_track_state", "svo_track_kp_capacity"]
 
 _lib = None
 
@@ -131,6 +141,10 @@ def load():
     L.svo_project_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
     L.svo_debug_tc_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.svo_debug_hamming_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    L.svo_track_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.svo_track_reset.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.svo_track_state.argtypes = [C.c_void_p, C.c_int, C.POINTER(TrackView)]
+    L.svo_track_kp_capacity.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -353,6 +367,8 @@ class Context:
                     fi.boxes, fi.n_boxes = v.ctypes.data, len(v)
                 else:
                     fi.boxes, fi.n_boxes = int(v), f["n_boxes"]
+            if f.get("track_seq") is not None:          # device-resident tracker state: sequence index (0-based here)
+                fi.track_seq, fi.frame_id = int(f["track_seq"]) + 1, int(f.get("frame_id", 0))
             if f.get("K") is not None:
                 fi.fx, fi.fy, fi.cx, fi.cy = [float(v) for v in f["K"]]
                 fi.proj_th = float(f.get("proj_th", 7.0))
@@ -375,13 +391,16 @@ class Context:
         o = FrameOut()
         self._chk(self.lib.svo_batch_result(self.h, lane, i, C.byref(o)))
         arr, _ = self._keep[("lane", lane)]
-        n_prev, n_map = arr[i].n_prev, arr[i].n_map
+        tracked = arr[i].track_seq != 0
+        n_prev, n_map = (o.n_prev, o.n_map) if tracked else (arr[i].n_prev, arr[i].n_map)
         nl, nr = o.n_left, o.n_right
         r = dict(status=o.status, n_left=nl, n_right=nr, n_stereo=o.n_stereo,
                  kp_left=_view(o.kp_left, KP_DTYPE, (nl,)), kp_right=_view(o.kp_right, KP_DTYPE, (nr,)),
                  desc_left=_view(o.desc_left, np.uint8, (nl, 32)), desc_right=_view(o.desc_right, np.uint8, (nr, 32)),
                  u_right=_view(o.u_right, np.float32, (nl,)), depth=_view(o.depth, np.float32, (nl,)),
-                 claim_row=_view(o.claim_row, np.int32, (nl,)))
+                 claim_row=_view(o.claim_row, np.int32, (nl,)), n_prev=n_prev, n_map=n_map)
+        if tracked:
+            r.update(mp_create=_view(o.mp_create, np.int32, (nl,)), mp_xyz=_view(o.mp_xyz, np.float32, (nl, 3)))
         if n_prev:
             r.update(bf_idx=_view(o.bf_idx, np.int32, (nl,)), bf_dist=_view(o.bf_dist, np.int32, (nl,)),
                      bf_keep=_view(o.bf_keep, np.uint8, (nl,)),
@@ -394,6 +413,30 @@ class Context:
         if copy:
             r = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in r.items()}
         return r
+
+    # ---- device-resident tracker state (opt-in) ------------------------------------------
+    def track_create(self, n_sequences, map_capacity=None, window=4):
+        self._chk(self.lib.svo_track_create(self.h, n_sequences, map_capacity or self.max_rows, window))
+        self.track_cap = map_capacity or self.max_rows
+
+    def track_reset(self, seq, ballast=None):
+        b = None if ballast is None else np.ascontiguousarray(ballast, np.uint8).reshape(-1, 32)
+        self._chk(self.lib.svo_track_reset(self.h, seq, _p(b), 0 if b is None else len(b)))
+
+    def track_state(self, seq):
+        """The sequence's current state as host arrays (test tap)."""
+        K = self._chk(self.lib.svo_track_kp_capacity(self.h)); Cp = self.track_cap
+        a = dict(last_desc=np.zeros((K, 32), np.uint8), prev_desc=np.zeros((K, 32), np.uint8), prev_live=np.zeros(K, np.uint8),
+                 prev_map_row=np.zeros(K, np.int32), prev_create=np.zeros(K, np.int32), prev_xyz=np.zeros((K, 3), np.float32),
+                 prev_xy=np.zeros((K, 2), np.float32), map_desc=np.zeros((Cp, 32), np.uint8), map_create=np.zeros(Cp, np.int32),
+                 map_link=np.zeros(Cp, np.int32), map_xyz=np.zeros((Cp, 3), np.float32))
+        v = TrackView()
+        for k, arr in a.items():
+            setattr(v, k, arr.ctypes.data)
+        self._chk(self.lib.svo_track_state(self.h, seq, C.byref(v)))
+        out = {k: (arr[:v.n_map] if k.startswith("map_") else arr[:v.n_prev]) for k, arr in a.items()}
+        out["n_prev"], out["n_map"] = v.n_prev, v.n_map
+        return out
 
     def stage_ms(self, lane):
         ms = np.zeros(14, np.float32)
