@@ -98,12 +98,12 @@ def workload_string(distribution="retainbest"):
             % (head, "KITTI-shape" if (W_IMG, H_IMG) == (1241, 376) else "high-res", W_IMG, H_IMG, NFEAT, MAP_ROWS))
 
 
-def verify_frame(r, job):
-    """Checker for the bench's own configuration (not timed): one frame's results against the CPU oracle —
-    keypoints and descriptors bit for bit, stereo validity / match-level agreement within 1e-3, BF, pass 1, pass 2."""
+def verify_extract(r, left, right):
+    """Checker (not timed): one frame's keypoints and descriptors bit for bit, stereo validity / match-level agreement
+    within 1e-3, against the CPU oracle.  Returns the oracle's left descriptors."""
     from oracle import oracle as O
-    kl, dl, pl = O.orb(job["left"], NFEAT, with_pyramid=True)
-    kr, dr, pr = O.orb(job["right"], NFEAT, with_pyramid=True)
+    kl, dl, pl = O.orb(left, NFEAT, with_pyramid=True)
+    kr, dr, pr = O.orb(right, NFEAT, with_pyramid=True)
     ur, dep, mr, sad = O.stereo_sparse(kl, dl, pl, kr, dr, pr, BF, BASELINE)
     O.pyramid_free(pl); O.pyramid_free(pr)
     assert r["status"] == 0 and r["n_left"] == len(kl) and r["n_right"] == len(kr), "keypoint counts"
@@ -116,6 +116,14 @@ def verify_frame(r, job):
     if valid.any():
         assert np.abs(r["u_right"][valid] - ur[valid]).max() <= 1e-3, "u_right"
         assert (np.abs(r["depth"][valid] - dep[valid]) <= 1e-3 * np.abs(dep[valid])).all(), "depth"
+    return dl
+
+
+def verify_frame(r, job):
+    """Checker for the bench's own configuration (not timed): one frame's results against the CPU oracle —
+    extraction and stereo (verify_extract), BF, pass 1, pass 2."""
+    from oracle import oracle as O
+    dl = verify_extract(r, job["left"], job["right"])
     oi, od, ok = O.match_bf(dl, job["prev_desc"])
     assert (r["bf_idx"] == oi).all() and (r["bf_dist"] == od).all() and (r["bf_keep"] == ok).all(), "BF"
     p1 = O.match_greedy(job["prev_desc"], dl, 0, row_live=job["prev_live"])
@@ -130,6 +138,28 @@ def verify_frame(r, job):
                         row_base=len(job["prev_desc"]))
     assert (r["p2_row_claimed"] == p2["row_claimed"]).all() and (r["claim_row"] == p2["claim_row"]).all(), "pass 2"
     return int(p1["row_claimed"].sum()), int(p2["row_claimed"].sum())
+
+
+def verify_tracked_frame(r, left, right, pre, post, frame_id, map_cap, K4):
+    """Checker for a TRACKED frame (not timed): extraction and stereo against the oracle, then oracle/track.py continued
+    from the state the frame read (`pre`) must give the frame's matches and the state it left (`post`), bit for bit."""
+    from oracle import track as T
+    verify_extract(r, left, right)
+    trk = T.Tracker.from_state(pre, window=4, map_cap=map_cap)
+    xy = np.stack([r["kp_left"]["x"], r["kp_left"]["y"]], 1)
+    o = trk.step(xy, r["desc_left"], r["depth"], frame_id, K4=K4)
+    assert r["n_prev"] == o["n_prev"] and r["n_map"] == o["n_map"], "tracked row counts"
+    keys = ["claim_row", "mp_create"]
+    if o["n_prev"]:
+        keys += ["bf_idx", "bf_dist", "bf_keep", "p1_best_idx", "p1_best", "p1_second", "p1_row_claimed"]
+    if o["n_map"]:
+        keys.append("p2_row_claimed")
+    for k in keys:
+        assert np.array_equal(r[k], o[k]), "tracked " + k
+    assert (r["mp_xyz"].view(np.uint32) == o["mp_xyz"].view(np.uint32)).all(), "tracked mp_xyz"
+    for k in ("last_desc", "prev_desc", "prev_live", "prev_map_row", "prev_create", "map_desc", "map_create", "map_link"):
+        assert np.array_equal(post[k], getattr(trk, k)), "tracked state " + k
+    return int(o["p1_row_claimed"].sum()) if o["n_prev"] else 0, int(o["p2_row_claimed"].sum()) if o["n_map"] else 0
 
 
 class ClockSampler(threading.Thread):
@@ -264,14 +294,19 @@ def run_gpu(args, rank, world, local_rank):
                 nv += 1; claims += c1 + c2
         return nv, claims
 
-    def timed(make_frame, steps, warmup, profile):
-        cursor = [0]
+    cursor = [0]
 
-        def submit(lane):
+    def pool_batch(make_frame):
+        def make(lane):
             ts = [(cursor[0] + i) % P for i in range(B)]
             cursor[0] = (cursor[0] + B) % P
             last_ts[lane] = ts
-            ctx.batch_submit(lane, [make_frame(t) for t in ts])
+            return [make_frame(t) for t in ts]
+        return make
+
+    def timed(make_batch, steps, warmup, profile):
+        def submit(lane):
+            ctx.batch_submit(lane, make_batch(lane))
 
         for s in range(warmup):
             lane = s % args.lanes
@@ -315,19 +350,78 @@ def run_gpu(args, rank, world, local_rank):
     sampler = ClockSampler(dev)
     sampler.start()
     # headline numbers: graph replay, no per-stage events
-    ms_dev, wall_dev, launches, _ = timed(frame_dev, args.steps, args.warmup, 0)
+    ms_dev, wall_dev, launches, _ = timed(pool_batch(frame_dev), args.steps, args.warmup, 0)
     verified = claims = 0
     if args.verify and rank == 0:
         verified, claims = verify_last_batches(args.verify)      # resident-input pass: last timed batch of every lane
-    ms_e2e, wall_e2e, _, _ = timed(frame_host, args.steps, args.warmup, 0)
+    ms_hc, wall_hc, _, _ = timed(pool_batch(frame_host), args.steps, args.warmup, 0)
     if args.verify and rank == 0:
         v2, c2 = verify_last_batches(args.verify)                # host-input pass
         verified += v2; claims += c2
+    # ---- tracked end-to-end pass: the tracker state (last frame's descriptors and map points, local map) stays in HBM
+    # (svo_track_*), so only the images cross PCIe.  Every lane owns B sequences; a step advances each by one frame.
+    trk = None
+    ms_trk = wall_trk = None
+    stage_trk = {}
+    if not args.no_tracked:
+        K4 = (float(CAL["fx"]), float(CAL["fy"]), float(CAL["cx"]), float(CAL["cy"]))
+        NS = args.lanes * B
+        ctx.track_create(NS, MAP_ROWS, 4)
+        step_of = [0] * args.lanes
+        last_k = {}
+        seen = {"n_prev": [], "n_map": []}
+
+        def tracked_batch(lane):
+            k = step_of[lane]; step_of[lane] += 1
+            ts = [((lane * B + i) * 5 + k) % P for i in range(B)]      # sequence s starts at pool frame 5 s
+            last_ts[lane] = ts; last_k[lane] = k
+            return [dict(left=hl[t], right=hr[t], bf=BF, baseline=BASELINE, track_seq=lane * B + i, frame_id=k, K=K4)
+                    for i, t in enumerate(ts)]
+
+        def run_untimed(steps_per_lane, record):
+            for k in range(steps_per_lane):
+                for lane in range(args.lanes):
+                    ctx.batch_submit(lane, tracked_batch(lane))
+                for lane in range(args.lanes):
+                    ctx.batch_wait(lane)
+                    if record:
+                        for i in range(0, B, 4):
+                            r = ctx.batch_result(lane, i, copy=False)
+                            seen["n_prev"].append(r["n_prev"]); seen["n_map"].append(r["n_map"])
+
+        # natural size of the local map in this workload (4 frames of new points), then ballast up to the configured rows
+        for sq in range(NS):
+            ctx.track_reset(sq)
+        run_untimed(6, False); run_untimed(2, True)
+        natural = float(np.mean(seen["n_map"]))
+        n_ballast = int(max(0, min(MAP_ROWS, round(MAP_ROWS - natural))))
+        ballast = rng.integers(0, 256, (max(n_ballast, 1), 32), dtype=np.uint8)
+        for sq in range(NS):
+            ctx.track_reset(sq, ballast[:n_ballast] if n_ballast else None)
+        for lane in range(args.lanes):
+            step_of[lane] = 0
+        run_untimed(6, False)                                           # steady state: the 4-frame window is full
+        ms_trk, wall_trk, _, _ = timed(tracked_batch, args.steps, args.warmup, 0)
+        tv = tc = 0
+        if args.verify and rank == 0:
+            for lane in range(args.lanes):
+                for i in sorted(set(np.linspace(0, B - 1, args.verify).astype(int).tolist())):
+                    sq, t = lane * B + i, last_ts[lane][i]
+                    c1, c2 = verify_tracked_frame(ctx.batch_result(lane, i), hl[t], hr[t], ctx.track_state(sq, previous=True),
+                                                  ctx.track_state(sq), last_k[lane], MAP_ROWS, K4)
+                    tv += 1; tc += c1 + c2
+        seen = {"n_prev": [], "n_map": []}
+        run_untimed(2, True)
+        trk = {"sequences": NS, "natural_map_rows": natural, "ballast_rows": n_ballast, "mean_map_rows": float(np.mean(seen["n_map"])),
+               "mean_prev_rows": float(np.mean(seen["n_prev"])), "verified_frames": tv, "verified_claims": tc}
+        verified += tv; claims += tc
     # per-stage / per-kernel durations: the same steps again with CUDA events on the lanes' own streams (the events
     # split the captured graph into plain launches, so this pass is a few percent slower than the headline)
     psteps = max(args.lanes + 2, min(args.steps, 24))
-    ms_prof, _, _, stage = timed(frame_dev, psteps, 3, 1)
-    _, _, _, stage_e2e = timed(frame_host, psteps, 3, 1)
+    ms_prof, _, _, stage = timed(pool_batch(frame_dev), psteps, 3, 1)
+    _, _, _, stage_hc = timed(pool_batch(frame_host), psteps, 3, 1)
+    if trk is not None:
+        _, _, _, stage_trk = timed(tracked_batch, psteps, 3, 1)
     sampler.stop_flag = True
     sampler.join(timeout=1)
 
@@ -364,7 +458,7 @@ def run_gpu(args, rank, world, local_rank):
                 "note": "wall clock around svo_pnp_ransac (100 samples, 8 px, refit) and svo_pose_optimize (g2o LM, 10 iterations), "
                         "host buffers in and out; includes the Python binding's packing"}
 
-    ms_dev, ms_e2e = grp.max_over_ranks([ms_dev, ms_e2e])
+    ms_dev, ms_hc, ms_trk_m = grp.max_over_ranks([ms_dev, ms_hc, ms_trk if ms_trk is not None else 0.0])
     frames_total = int(grp.sum_over_ranks([args.steps * B])[0])
     out = None
     if rank == 0:
@@ -408,6 +502,24 @@ def run_gpu(args, rank, world, local_rank):
                     "peak_source": "148 SMs x 16 POPC/clk/SM x sampled SM clock"}
         h2d = B * (2 * W_IMG * H_IMG + int(n_prev.mean()) * 33 + MAP_ROWS * 36 + 16)
         d2h = 2 * B * (K * 56 + 8) + B * (K * 21 + 4) + B * max(MAP_ROWS, K) * 14
+        e2e_hc = {"value": frames_total / (ms_hc * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                  "ms_per_step": ms_hc / args.steps, "wall_ms_per_step": wall_hc / args.steps,
+                  "h2d_ms_per_step": stage_hc.get("h2d"), "d2h_ms_per_step": stage_hc.get("d2h"),
+                  "lane_total_ms_per_step": stage_hc.get("total"),
+                  "mode": "the caller chains frames through the host: previous-frame descriptors, liveness, the 5k-row map and its links "
+                          "are uploaded with every frame (svo_frame_in.prev_desc / map_desc)"}
+        e2e_main = e2e_hc
+        if trk is not None:
+            e2e_main = {"value": frames_total / (ms_trk_m * 1e-3), "unit": UNIT,
+                        "h2d_bytes_per_step": B * (2 * W_IMG * H_IMG + 16) + B * 200, "d2h_bytes_per_step": d2h + B * K * 16,
+                        "ms_per_step": ms_trk_m / args.steps, "wall_ms_per_step": wall_trk / args.steps,
+                        "h2d_ms_per_step": stage_trk.get("h2d"), "d2h_ms_per_step": stage_trk.get("d2h"),
+                        "lane_total_ms_per_step": stage_trk.get("total"),
+                        "mode": "device-resident tracker state (svo_track_*, svo_frame_in.track_seq): pinned host images in, every result "
+                                "out; the last frame's descriptors and map points and the local map are advanced in HBM as "
+                                "src/Tracking.cc:237-250 does on the host (%d sequences, one frame of each per step; mean %.0f pass-1 rows, "
+                                "%.0f local-map rows of which %d ballast)" % (trk["sequences"], trk["mean_prev_rows"], trk["mean_map_rows"],
+                                                                              trk["ballast_rows"])}
         out = {
             "metric": METRIC, "value": frames_total / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
@@ -419,15 +531,15 @@ def run_gpu(args, rank, world, local_rank):
                              % (P, 2 * P * img_b / 1e6, P * (K * 33 + MAP_ROWS * 36) / 1e6),
                        "parallelism": "replicas only: one independent sequence per GPU, no collective",
                        "host_placement": ("process bound to the %d cores NVML reports local to its GPU" % len(near)) if near else "unbound"},
-            "e2e": {"value": frames_total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_e2e / args.steps,
-                    "h2d_ms_per_step": stage_e2e.get("h2d"), "d2h_ms_per_step": stage_e2e.get("d2h"),
-                    "lane_total_ms_per_step": stage_e2e.get("total")},
+            "e2e": e2e_main,
+            "e2e_host_chained": e2e_hc,
+            "tracked": trk,
             "gpu_launches": launches,
             "verified_frames": verified,
-            "verified_note": ("frames of the LAST timed batch of every lane (resident-input and host-input passes, batch %d, %d lanes, "
-                              "graph replay) checked bit for bit against the CPU oracle after the timed regions: keypoints, descriptors, "
-                              "stereo, BF, pass 1, pass 2 (%d claims among them)" % (B, args.lanes, claims)) if verified else "verification off",
+            "verified_note": ("frames of the LAST timed batch of every lane (resident-input, host-chained and tracked passes, batch %d, "
+                              "%d lanes, graph replay) checked bit for bit against the CPU oracle after the timed regions: keypoints, "
+                              "descriptors, stereo, BF, pass 1, pass 2, and for tracked frames the state they left (%d claims among them)"
+                              % (B, args.lanes, claims)) if verified else "verification off",
             "clocks": sampler.result(),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
@@ -594,6 +706,7 @@ def main():
     ap.add_argument("--pool", type=int, default=160, help="distinct synthetic frames cycled (must exceed L2)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tracked", action="store_true", help="skip the tracked end-to-end pass (e2e is then the host-chained one)")
     ap.add_argument("--verify", type=int, default=2, help="frames per lane of the last timed batch checked against the oracle (0: off)")
     ap.add_argument("--ref-frames", type=int, default=0, help="--impl reference: frames per step (default: one per host core)")
     # other BASELINE.json configurations (parity-test / breakdown cases, not the headline): e.g. configs[2]

@@ -326,6 +326,8 @@ typedef struct svo_track_view {
     int32_t *map_create;     /* n_map: create_id (INT32_MAX = ballast)                                                 */
     int32_t *map_link;       /* n_map: keypoint of the last frame that owns the same point, -1 = none                  */
     float *map_xyz;          /* n_map x 3                                                                              */
+    int32_t previous;        /* IN: 0 = the current state; 1 = the state the sequence's last frame read (the other
+                                ping-pong copy: intact until the sequence's next frame is submitted)                  */
 } svo_track_view;
 int svo_track_state(svo_ctx *ctx, int seq, svo_track_view *view);
 /* Rows of the per-keypoint arrays (the context's keypoint capacity per image). */

@@ -42,6 +42,16 @@ class Tracker:
         self.map_link = np.full(nb, -1, np.int32)
         self.map_xyz = np.zeros((nb, 3), np.float32)
 
+    @classmethod
+    def from_state(cls, st, window=4, map_cap=None):
+        """A tracker continuing from a state dump (svo.Context.track_state); the points' keypoint-index names are unknown (-1)."""
+        t = cls(window=window, map_cap=map_cap)
+        for k in ("last_desc", "prev_desc", "prev_live", "prev_map_row", "prev_create", "prev_xyz", "prev_xy", "map_desc", "map_create",
+                  "map_link", "map_xyz"):
+            setattr(t, k, np.array(st[k]))
+        t.prev_idx = np.full(len(t.prev_desc), -1, np.int32); t.map_idx = np.full(len(t.map_desc), -1, np.int32)
+        return t
+
     # ------------------------------------------------------------------------------------------------------------
     def names(self):
         return list(zip(self.map_create.tolist(), self.map_idx.tolist()))

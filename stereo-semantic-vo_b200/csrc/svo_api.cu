@@ -1237,7 +1237,7 @@ int svo_track_state(svo_ctx *ctx, int seq, svo_track_view *v)
     if (!ctx || !v || seq < 0 || seq >= ctx->trk_n) return fail(ctx, SVO_E_INVALID, "svo_track_state: bad argument");
     CU(cudaSetDevice(ctx->cfg.device));
     CU(cudaDeviceSynchronize());
-    const TrackState &t = ctx->trk_h[2 * (size_t)seq + ctx->trk_parity[seq]];
+    const TrackState &t = ctx->trk_h[2 * (size_t)seq + (ctx->trk_parity[seq] ^ (v->previous ? 1 : 0))];
     CU(cudaMemcpy(&v->n_prev, t.n_prev, sizeof(int), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(&v->n_map, t.n_map, sizeof(int), cudaMemcpyDeviceToHost));
     const size_t np = (size_t)std::min(v->n_prev, ctx->g.kp_cap), nm = (size_t)std::min(v->n_map, ctx->trk_cap);

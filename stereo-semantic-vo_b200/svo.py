@@ -61,7 +61,7 @@ class TrackView(C.Structure):
     _fields_ = [("n_prev", C.c_int32), ("n_map", C.c_int32), ("last_desc", C.c_void_p), ("prev_desc", C.c_void_p),
                 ("prev_live", C.c_void_p), ("prev_map_row", C.c_void_p), ("prev_create", C.c_void_p), ("prev_xyz", C.c_void_p),
                 ("prev_xy", C.c_void_p), ("map_desc", C.c_void_p), ("map_create", C.c_void_p), ("map_link", C.c_void_p),
-                ("map_xyz", C.c_void_p)]
+                ("map_xyz", C.c_void_p), ("previous", C.c_int32)]
 
 
 class PoseProblem(C.Structure):
@@ -423,14 +423,15 @@ class Context:
         b = None if ballast is None else np.ascontiguousarray(ballast, np.uint8).reshape(-1, 32)
         self._chk(self.lib.svo_track_reset(self.h, seq, _p(b), 0 if b is None else len(b)))
 
-    def track_state(self, seq):
-        """The sequence's current state as host arrays (test tap)."""
+    def track_state(self, seq, previous=False):
+        """The sequence's current state as host arrays (test tap); previous=True: the state its last frame read."""
         K = self._chk(self.lib.svo_track_kp_capacity(self.h)); Cp = self.track_cap
         a = dict(last_desc=np.zeros((K, 32), np.uint8), prev_desc=np.zeros((K, 32), np.uint8), prev_live=np.zeros(K, np.uint8),
                  prev_map_row=np.zeros(K, np.int32), prev_create=np.zeros(K, np.int32), prev_xyz=np.zeros((K, 3), np.float32),
                  prev_xy=np.zeros((K, 2), np.float32), map_desc=np.zeros((Cp, 32), np.uint8), map_create=np.zeros(Cp, np.int32),
                  map_link=np.zeros(Cp, np.int32), map_xyz=np.zeros((Cp, 3), np.float32))
         v = TrackView()
+        v.previous = int(bool(previous))
         for k, arr in a.items():
             setattr(v, k, arr.ctypes.data)
         self._chk(self.lib.svo_track_state(self.h, seq, C.byref(v)))
