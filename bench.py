@@ -109,8 +109,11 @@ def verify_extract(r, left, right):
     assert r["status"] == 0 and r["n_left"] == len(kl) and r["n_right"] == len(kr), "keypoint counts"
     for f in ("x", "y", "size", "angle", "response"):
         assert (r["kp_left"][f].view(np.uint32) == kl[f].view(np.uint32)).all(), "left keypoints: " + f
-        assert (r["kp_right"][f].view(np.uint32) == kr[f].view(np.uint32)).all(), "right keypoints: " + f
-    assert (r["kp_left"]["octave"] == kl["octave"]).all() and (r["desc_left"] == dl).all() and (r["desc_right"] == dr).all(), "descriptors"
+    assert (r["kp_left"]["octave"] == kl["octave"]).all() and (r["desc_left"] == dl).all(), "descriptors"
+    if r["kp_right"] is not None:      # SVO_OUT_NO_RIGHT leaves them on the device: the stereo results below still depend on them
+        for f in ("x", "y", "size", "angle", "response"):
+            assert (r["kp_right"][f].view(np.uint32) == kr[f].view(np.uint32)).all(), "right keypoints: " + f
+        assert (r["desc_right"] == dr).all(), "right descriptors"
     valid = dep > 0
     assert ((r["depth"] > 0) == valid).all(), "stereo validity"
     if valid.any():
@@ -401,6 +404,9 @@ def run_gpu(args, rank, world, local_rank):
         for lane in range(args.lanes):
             step_of[lane] = 0
         run_untimed(6, False)                                           # steady state: the 4-frame window is full
+        # results: nfeatures + 32 rows per array instead of the capacities, and no right-image features (the reference's
+        # frame keeps none); every other output of the path comes back
+        ctx.set_outputs(svo.OUT_COMPACT | svo.OUT_NO_RIGHT)
         ms_trk, wall_trk, _, _ = timed(tracked_batch, args.steps, args.warmup, 0)
         tv = tc = 0
         if args.verify and rank == 0:
@@ -415,13 +421,16 @@ def run_gpu(args, rank, world, local_rank):
         trk = {"sequences": NS, "natural_map_rows": natural, "ballast_rows": n_ballast, "mean_map_rows": float(np.mean(seen["n_map"])),
                "mean_prev_rows": float(np.mean(seen["n_prev"])), "verified_frames": tv, "verified_claims": tc}
         verified += tv; claims += tc
+        ctx.set_outputs(0)
     # per-stage / per-kernel durations: the same steps again with CUDA events on the lanes' own streams (the events
     # split the captured graph into plain launches, so this pass is a few percent slower than the headline)
     psteps = max(args.lanes + 2, min(args.steps, 24))
     ms_prof, _, _, stage = timed(pool_batch(frame_dev), psteps, 3, 1)
     _, _, _, stage_hc = timed(pool_batch(frame_host), psteps, 3, 1)
     if trk is not None:
+        ctx.set_outputs(svo.OUT_COMPACT | svo.OUT_NO_RIGHT)
         _, _, _, stage_trk = timed(tracked_batch, psteps, 3, 1)
+        ctx.set_outputs(0)
     sampler.stop_flag = True
     sampler.join(timeout=1)
 
@@ -511,12 +520,14 @@ def run_gpu(args, rank, world, local_rank):
         e2e_main = e2e_hc
         if trk is not None:
             e2e_main = {"value": frames_total / (ms_trk_m * 1e-3), "unit": UNIT,
-                        "h2d_bytes_per_step": B * (2 * W_IMG * H_IMG + 16) + B * 200, "d2h_bytes_per_step": d2h + B * K * 16,
+                        "h2d_bytes_per_step": B * (2 * W_IMG * H_IMG + 16) + B * 200,
+                        "d2h_bytes_per_step": B * ((NFEAT + 32) * 106 + MAP_ROWS + 40),
                         "ms_per_step": ms_trk_m / args.steps, "wall_ms_per_step": wall_trk / args.steps,
                         "h2d_ms_per_step": stage_trk.get("h2d"), "d2h_ms_per_step": stage_trk.get("d2h"),
                         "lane_total_ms_per_step": stage_trk.get("total"),
                         "mode": "device-resident tracker state (svo_track_*, svo_frame_in.track_seq): pinned host images in, every result "
-                                "out; the last frame's descriptors and map points and the local map are advanced in HBM as "
+                                "of the reference's frame / pnpmatch out (compact copies, right-image features stay on the device: "
+                                "svo_set_outputs); the last frame's descriptors and map points and the local map are advanced in HBM as "
                                 "src/Tracking.cc:237-250 does on the host (%d sequences, one frame of each per step; mean %.0f pass-1 rows, "
                                 "%.0f local-map rows of which %d ballast)" % (trk["sequences"], trk["mean_prev_rows"], trk["mean_map_rows"],
                                                                               trk["ballast_rows"])}

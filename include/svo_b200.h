@@ -348,6 +348,17 @@ long long svo_launch_count(const svo_ctx *ctx);
  * [9] stereo, [10] matching, [11] D2H; then two single kernels of the matching stage:
  * [12] k_pairs (fused BF + pass-1 distances), [13] k_shortlist of pass 2.  Writes min(n, 14) values. */
 int svo_batch_stage_ms(svo_ctx *ctx, int lane, float *ms, int n);
+/* Which results svo_batch_submit copies back, for the batches submitted from now on (default 0: every array at its
+ * capacity, as one contiguous copy each).
+ *   SVO_OUT_COMPACT   per frame only nfeatures + 32 rows of every per-keypoint and pass-1 array cross PCIe (strided
+ *                     copies); a frame that holds more (response ties can push a level past its quota) gets the rest
+ *                     fetched by svo_batch_wait.  Same results, ~15 % fewer bytes.
+ *   SVO_OUT_NO_RIGHT  the right image's keypoints and descriptors stay on the device (kp_right / desc_right come back
+ *                     NULL; n_right, u_right and depth are still filled).  The reference's frame keeps no right-image
+ *                     features either: keypoints_r is keypoints_l shifted by the disparity (src/frame.cc:122-138). */
+#define SVO_OUT_COMPACT 1
+#define SVO_OUT_NO_RIGHT 2
+int svo_set_outputs(svo_ctx *ctx, int flags);
 /* Turn per-stage event recording on (1) or off (0, default). */
 int svo_set_profiling(svo_ctx *ctx, int on);
 void *svo_lane_stream(svo_ctx *ctx, int lane);

@@ -77,6 +77,7 @@ struct Lane {
     cudaEvent_t ev[N_EVENTS];
     int slot0, frame0, nframes;
     bool busy, veto, tracked;
+    int out_flags, out_w, out_wp;   // of the batch in flight: output selection and the rows its result copies carried
     HostArena h;
     std::vector<svo_frame_in> in;
     uint8_t *d_stage;          // landing zone for the host inputs of a batch (images, descriptors, flags)
@@ -106,6 +107,8 @@ struct svo_ctx {
     FramePtrs *sync_fp_d, *sync_fp_h;
     int *sync_str_d, *sync_str_h;
     bool profiling;
+    int out_flags;           // svo_set_outputs
+    int compact_rows;        // rows per frame of a compact result copy (nfeatures + 32; SVO_B200_COMPACT_ROWS overrides it for tests)
     // device-resident tracker states (svo_track_create)
     int trk_n, trk_cap, trk_window;
     TrackState *trk_d;                   // [seq][2] on the device
@@ -437,6 +440,17 @@ struct Seg { const uint8_t *src; size_t bytes; const void **field; bool need16; 
 // Kernels, memsets and D2H copies of one batch on the lane's stream (capturable: no host-dependent arguments).
 // phase 0: everything; 1: input repack + extraction only; 2: stereo, matching, tracker update and result copies only (the
 // two halves of a TRACKED batch: the second waits for the previous batch to have advanced the tracker states)
+// Result copies.  out_w rows of every per-keypoint array and out_wp rows of every pass-1 array leave per frame: the
+// capacities by default, or (SVO_OUT_COMPACT) nfeatures + 32 rows as strided 2-D copies — svo_batch_wait fetches the
+// rest of a frame that went over (response ties can push a level past its quota).  SVO_OUT_NO_RIGHT leaves the right
+// image's keypoints and descriptors on the device (the reference's frame has none: src/frame.cc:122-138 keeps only
+// keypoints_r = u_right).
+cudaError_t copy_rows(void *dst, const void *src, size_t elem, size_t pitch_rows, size_t rows, size_t frames, cudaStream_t st)
+{
+    if (rows >= pitch_rows) return cudaMemcpyAsync(dst, src, elem * pitch_rows * frames, cudaMemcpyDeviceToHost, st);
+    return cudaMemcpy2DAsync(dst, elem * pitch_rows, src, elem * pitch_rows, elem * rows, frames, cudaMemcpyDeviceToHost, st);
+}
+
 int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, bool fused, bool windowed, bool veto, bool tracked,
                     int phase, cudaEvent_t *ev)
 {
@@ -475,14 +489,23 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
     if (ev) cudaEventRecord(ev[9], st);
     HostArena &h = L.h;
     const size_t I = 2 * (size_t)n, KC = g.kp_cap;
-    if (fork) {   // everything extraction and stereo produced leaves while the matchers run
-        CU(cudaMemcpyAsync(h.nkp, b.nkp + L.slot0, sizeof(int) * I, cudaMemcpyDeviceToHost, ss));
-        CU(cudaMemcpyAsync(h.kp, b.kp + (size_t)L.slot0 * KC, sizeof(svo_keypoint) * I * KC, cudaMemcpyDeviceToHost, ss));
-        CU(cudaMemcpyAsync(h.desc, b.desc + (size_t)L.slot0 * KC * 32, I * KC * 32, cudaMemcpyDeviceToHost, ss));
-        CU(cudaMemcpyAsync(h.u_right, sa.u_right, sizeof(float) * n * KC, cudaMemcpyDeviceToHost, ss));
-        CU(cudaMemcpyAsync(h.depth, sa.depth, sizeof(float) * n * KC, cudaMemcpyDeviceToHost, ss));
-        CU(cudaMemcpyAsync(h.n_stereo, sa.n_stereo, sizeof(int) * n, cudaMemcpyDeviceToHost, ss));
-    }
+    const size_t W = (size_t)L.out_w, WP = (size_t)L.out_wp;
+    const bool no_right = (L.out_flags & SVO_OUT_NO_RIGHT) != 0;
+    auto copy_extract = [&](cudaStream_t cs) -> int {   // everything extraction and stereo produced
+        CU(cudaMemcpyAsync(h.nkp, b.nkp + L.slot0, sizeof(int) * I, cudaMemcpyDeviceToHost, cs));
+        if (no_right) {   // left images sit in the even slots
+            CU(copy_rows(h.kp, b.kp + (size_t)L.slot0 * KC, sizeof(svo_keypoint), 2 * KC, W, n, cs));
+            CU(copy_rows(h.desc, b.desc + (size_t)L.slot0 * KC * 32, 32, 2 * KC, W, n, cs));
+        } else {
+            CU(copy_rows(h.kp, b.kp + (size_t)L.slot0 * KC, sizeof(svo_keypoint), KC, W, I, cs));
+            CU(copy_rows(h.desc, b.desc + (size_t)L.slot0 * KC * 32, 32, KC, W, I, cs));
+        }
+        CU(copy_rows(h.u_right, sa.u_right, sizeof(float), KC, W, n, cs));
+        CU(copy_rows(h.depth, sa.depth, sizeof(float), KC, W, n, cs));
+        CU(cudaMemcpyAsync(h.n_stereo, sa.n_stereo, sizeof(int) * n, cudaMemcpyDeviceToHost, cs));
+        return SVO_OK;
+    };
+    if (fork) TRY(copy_extract(ss));   // leaves while the matchers run
     // ---- matching: BF (cur -> prev), greedy pass 1 (prev rows), greedy pass 2 (map rows)
     // left images sit in even slots: consecutive frames' descriptor blocks are 2*kp_cap rows apart
     const MatchSet cur = make_set(b.desc + (size_t)L.slot0 * g.kp_cap * 32, b.nkp + L.slot0, 2, g.kp_cap, 0, 2 * g.kp_cap);
@@ -591,34 +614,27 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
         ta.scratch = ctx->trk_scratch + (size_t)L.frame0 * ctx->trk_cap;
         ta.mp_create = ctx->trk_mp_create + (size_t)L.frame0 * K; ta.mp_xyz = ctx->trk_mp_xyz + (size_t)L.frame0 * K * 3;
         launch_track_update(ta, n, st, &ctx->launches);
-        CU(cudaMemcpyAsync(h.mp_create, ta.mp_create, sizeof(int) * n * KC, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h.mp_xyz, ta.mp_xyz, sizeof(float) * 3 * n * KC, cudaMemcpyDeviceToHost, st));
+        CU(copy_rows(h.mp_create, ta.mp_create, sizeof(int), KC, W, n, st));
+        CU(copy_rows(h.mp_xyz, ta.mp_xyz, 3 * sizeof(float), KC, W, n, st));
     }
     CU(cudaMemcpyAsync(h.np_out, fb.params + L.frame0, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h.np_out + ctx->cfg.max_batch, fb.params + FT + L.frame0, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h.status, b.status + L.slot0, sizeof(int) * I, cudaMemcpyDeviceToHost, st));
-    if (!fork) {
-        CU(cudaMemcpyAsync(h.nkp, b.nkp + L.slot0, sizeof(int) * I, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h.kp, b.kp + (size_t)L.slot0 * KC, sizeof(svo_keypoint) * I * KC, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h.desc, b.desc + (size_t)L.slot0 * KC * 32, I * KC * 32, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h.u_right, sa.u_right, sizeof(float) * n * KC, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h.depth, sa.depth, sizeof(float) * n * KC, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h.n_stereo, sa.n_stereo, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
-    }
+    if (!fork) TRY(copy_extract(st));
     if (any_prev) {
-        CU(cudaMemcpyAsync(h.bf_idx, fb.bf_idx + (size_t)L.frame0 * K, sizeof(int) * n * KC, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h.bf_dist, fb.bf_dist + (size_t)L.frame0 * K, sizeof(int) * n * KC, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h.bf_keep, fb.bf_keep + (size_t)L.frame0 * K, (size_t)n * KC, cudaMemcpyDeviceToHost, st));
+        CU(copy_rows(h.bf_idx, fb.bf_idx + (size_t)L.frame0 * K, sizeof(int), KC, W, n, st));
+        CU(copy_rows(h.bf_dist, fb.bf_dist + (size_t)L.frame0 * K, sizeof(int), KC, W, n, st));
+        CU(copy_rows(h.bf_keep, fb.bf_keep + (size_t)L.frame0 * K, 1, KC, W, n, st));
         if (!ctx->cfg.skip_match_score) {
-            CU(cudaMemcpyAsync(h.p1_best_idx, fb.p1_best_idx + (size_t)L.frame0 * R, sizeof(int) * n * R, cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(h.p1_best, fb.p1_best + (size_t)L.frame0 * R, sizeof(int) * n * R, cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(h.p1_second, fb.p1_second + (size_t)L.frame0 * R, sizeof(int) * n * R, cudaMemcpyDeviceToHost, st));
+            CU(copy_rows(h.p1_best_idx, fb.p1_best_idx + (size_t)L.frame0 * R, sizeof(int), R, WP, n, st));
+            CU(copy_rows(h.p1_best, fb.p1_best + (size_t)L.frame0 * R, sizeof(int), R, WP, n, st));
+            CU(copy_rows(h.p1_second, fb.p1_second + (size_t)L.frame0 * R, sizeof(int), R, WP, n, st));
         }
-        CU(cudaMemcpyAsync(h.p1_row_claimed, fb.p1_row_claimed + (size_t)L.frame0 * R, (size_t)n * R, cudaMemcpyDeviceToHost, st));
-        if (veto) CU(cudaMemcpyAsync(h.p1_row_bad, fb.p1_row_bad + (size_t)L.frame0 * R, (size_t)n * R, cudaMemcpyDeviceToHost, st));
+        CU(copy_rows(h.p1_row_claimed, fb.p1_row_claimed + (size_t)L.frame0 * R, 1, R, WP, n, st));
+        if (veto) CU(copy_rows(h.p1_row_bad, fb.p1_row_bad + (size_t)L.frame0 * R, 1, R, WP, n, st));
     }
     if (any_map) CU(cudaMemcpyAsync(h.p2_row_claimed, fb.p2_row_claimed + (size_t)L.frame0 * R, (size_t)n * R, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h.claim_row, fb.claim_row + (size_t)L.frame0 * K, sizeof(int) * n * KC, cudaMemcpyDeviceToHost, st));
+    CU(copy_rows(h.claim_row, fb.claim_row + (size_t)L.frame0 * K, sizeof(int), KC, W, n, st));
     return SVO_OK;
 }
 
@@ -664,8 +680,9 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
     if (!cfg || !out) return SVO_E_INVALID;
     *out = nullptr;
     svo_ctx *ctx = new svo_ctx();
-    ctx->cfg = *cfg; ctx->launches = 0; ctx->profiling = false; ctx->err[0] = 0;
+    ctx->cfg = *cfg; ctx->launches = 0; ctx->profiling = false; ctx->err[0] = 0; ctx->out_flags = 0;
     { const char *e = getenv("SVO_B200_TC"); ctx->use_tc = !(e && e[0] == '0'); }
+    { const char *e = getenv("SVO_B200_COMPACT_ROWS"); ctx->compact_rows = e ? atoi(e) : cfg->nfeatures + 32; if (ctx->compact_rows < 1) ctx->compact_rows = 1; }
     ctx->tc_prof = nullptr;
     ctx->trk_n = 0; ctx->trk_cap = 0; ctx->trk_window = 4; ctx->trk_d = nullptr; ctx->trk_scratch = nullptr;
     ctx->trk_mp_create = nullptr; ctx->trk_mp_xyz = nullptr; ctx->trk_img_last = nullptr;
@@ -810,6 +827,12 @@ int svo_get_geometry(const svo_ctx *ctx, int *lw, int *lh, float *lscale, int *q
 }
 
 long long svo_launch_count(const svo_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int svo_set_outputs(svo_ctx *ctx, int flags)
+{
+    if (!ctx || (flags & ~(SVO_OUT_COMPACT | SVO_OUT_NO_RIGHT))) return fail(ctx, SVO_E_INVALID, "svo_set_outputs: unknown flag");
+    ctx->out_flags = flags;
+    return SVO_OK;
+}
 int svo_set_profiling(svo_ctx *ctx, int on) { if (!ctx) return SVO_E_INVALID; ctx->profiling = on != 0; return SVO_OK; }
 void *svo_lane_stream(svo_ctx *ctx, int lane) { return (ctx && lane >= 0 && lane < (int)ctx->lanes.size()) ? (void *)ctx->lanes[lane].st : nullptr; }
 
@@ -1294,6 +1317,14 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
     const bool windowed = n_win > 0;
     L.in.assign(frames, frames + n);
     L.nframes = n; L.veto = veto; L.tracked = tracked;
+    L.out_flags = ctx->out_flags;
+    L.out_w = g.kp_cap; L.out_wp = R;
+    if (ctx->out_flags & SVO_OUT_COMPACT) {
+        L.out_w = std::min(g.kp_cap, ctx->compact_rows);
+        int mp = L.out_w;                                  // tracked frames: the last frame's keypoints are the pass-1 rows
+        for (int i = 0; i < n; ++i) if (!frames[i].track_seq) mp = std::max(mp, frames[i].n_prev);
+        L.out_wp = mp > L.out_w ? R : L.out_w;
+    }
     if (ev) cudaEventRecord(ev[0], st);
     // ---- inputs: device-resident buffers are read in place; host buffers are gathered into the lane's
     // landing zone with one H2D copy per maximal run of adjacent source ranges (a strided 2-D copy of
@@ -1408,7 +1439,7 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
     auto run = [&](int phase) -> int {
         if (ev) return enqueue_compute(ctx, L, n, any_prev, any_map, fused, windowed, veto, tracked, phase, ev);
         const int key = n | (any_prev ? 1 << 20 : 0) | (any_map ? 1 << 21 : 0) | (fused ? 1 << 22 : 0) | (windowed ? 1 << 23 : 0) | (veto ? 1 << 24 : 0) |
-                        (tracked ? 1 << 25 : 0) | (phase << 26);
+                        (tracked ? 1 << 25 : 0) | (phase << 26) | (L.out_flags << 28) | (L.out_wp == R ? 1 << 30 : 0);
         LaneGraph *lg = nullptr;
         for (LaneGraph &c : L.graphs) if (c.key == key) lg = &c;
         if (!lg) {
@@ -1453,6 +1484,44 @@ int svo_batch_wait(svo_ctx *ctx, int lane_i)
     CU(cudaEventSynchronize(L.done));
     L.busy = false;
     CU(cudaGetLastError());
+    if (L.out_w < ctx->g.kp_cap || L.out_wp < ctx->cfg.max_rows) {
+        // compact result copies: a frame with more keypoints (or pass-1 rows) than the copies carried gets the rest now
+        const Geom &g = ctx->g; const Bufs &b = ctx->b; FrameBufs &fb = ctx->fb; HostArena &h = L.h;
+        const size_t KC = g.kp_cap, R = ctx->cfg.max_rows, W = L.out_w, WP = L.out_wp;
+        const bool no_right = (L.out_flags & SVO_OUT_NO_RIGHT) != 0;
+        bool any = false;
+        auto tail = [&](void *hbase, const void *dbase, size_t elem, size_t row0, size_t rows) {
+            any = true;
+            return cudaMemcpyAsync((char *)hbase + elem * row0, (const char *)dbase + elem * row0, elem * rows, cudaMemcpyDeviceToHost, L.st);
+        };
+        for (int i = 0; i < L.nframes; ++i) {
+            const size_t nl = std::min((size_t)std::max(h.nkp[2 * i], 0), KC), nr = std::min((size_t)std::max(h.nkp[2 * i + 1], 0), KC);
+            const size_t fo = (size_t)L.frame0 + i, so = (size_t)L.slot0 + 2 * i;
+            if (nl > W) {
+                const size_t m = nl - W;
+                CU(tail(h.kp + 2 * i * KC, b.kp + so * KC, sizeof(svo_keypoint), W, m)); CU(tail(h.desc + 2 * i * KC * 32, b.desc + so * KC * 32, 32, W, m));
+                CU(tail(h.u_right + i * KC, fb.u_right + fo * KC, 4, W, m)); CU(tail(h.depth + i * KC, fb.depth + fo * KC, 4, W, m));
+                CU(tail(h.bf_idx + i * KC, fb.bf_idx + fo * KC, 4, W, m)); CU(tail(h.bf_dist + i * KC, fb.bf_dist + fo * KC, 4, W, m));
+                CU(tail(h.bf_keep + i * KC, fb.bf_keep + fo * KC, 1, W, m)); CU(tail(h.claim_row + i * KC, fb.claim_row + fo * KC, 4, W, m));
+                if (L.tracked && h.mp_create) {
+                    CU(tail(h.mp_create + i * KC, ctx->trk_mp_create + fo * KC, 4, W, m)); CU(tail(h.mp_xyz + i * KC * 3, ctx->trk_mp_xyz + fo * KC * 3, 12, W, m));
+                }
+            }
+            if (!no_right && nr > W) {
+                const size_t m = nr - W;
+                CU(tail(h.kp + (2 * i + 1) * KC, b.kp + (so + 1) * KC, sizeof(svo_keypoint), W, m));
+                CU(tail(h.desc + (2 * i + 1) * KC * 32, b.desc + (so + 1) * KC * 32, 32, W, m));
+            }
+            const size_t np = std::min((size_t)std::max(h.np_out[i], 0), R);
+            if (np > WP) {
+                const size_t m = np - WP;
+                CU(tail(h.p1_best_idx + i * R, fb.p1_best_idx + fo * R, 4, WP, m)); CU(tail(h.p1_best + i * R, fb.p1_best + fo * R, 4, WP, m));
+                CU(tail(h.p1_second + i * R, fb.p1_second + fo * R, 4, WP, m)); CU(tail(h.p1_row_claimed + i * R, fb.p1_row_claimed + fo * R, 1, WP, m));
+                CU(tail(h.p1_row_bad + i * R, fb.p1_row_bad + fo * R, 1, WP, m));
+            }
+        }
+        if (any) CU(cudaStreamSynchronize(L.st));
+    }
     return SVO_OK;
 }
 
@@ -1472,8 +1541,8 @@ int svo_batch_result(svo_ctx *ctx, int lane_i, int i, svo_frame_out *o)
     if (o->n_left > (int)K) { o->n_left = (int)K; o->status = SVO_E_CAPACITY; }
     if (o->n_right > (int)K) { o->n_right = (int)K; o->status = SVO_E_CAPACITY; }
     o->n_stereo = h.n_stereo[i];
-    o->kp_left = h.kp + (2 * (size_t)i) * K; o->kp_right = h.kp + (2 * (size_t)i + 1) * K;
-    o->desc_left = h.desc + (2 * (size_t)i) * K * 32; o->desc_right = h.desc + (2 * (size_t)i + 1) * K * 32;
+    o->kp_left = h.kp + (2 * (size_t)i) * K; o->desc_left = h.desc + (2 * (size_t)i) * K * 32;
+    if (!(L.out_flags & SVO_OUT_NO_RIGHT)) { o->kp_right = h.kp + (2 * (size_t)i + 1) * K; o->desc_right = h.desc + (2 * (size_t)i + 1) * K * 32; }
     o->u_right = h.u_right + (size_t)i * K; o->depth = h.depth + (size_t)i * K;
     o->n_prev = h.np_out[i]; o->n_map = h.np_out[ctx->cfg.max_batch + i];
     if (in.n_prev || in.track_seq) {

@@ -16,6 +16,7 @@ KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4
 
 OK, E_INVALID, E_CUDA, E_CAPACITY, E_NOMEM = 0, -1, -2, -3, -4
 DIST_RETAIN_BEST, DIST_OCTREE = 0, 1     # svo_config.distribution
+OUT_COMPACT, OUT_NO_RIGHT = 1, 2         # svo_set_outputs
 TAP_LEVEL, TAP_BLUR, TAP_FAST, TAP_SELECT1, TAP_SELECT2 = 0, 1, 2, 3, 4
 PASS1, PASS2 = 0, 1
 STAGES = ("total", "h2d", "pyramid", "fast", "select1", "harris", "select2", "blur", "describe",
@@ -86,7 +87,7 @@ EXPORTS = ["svo_default_config", "svo_version", "svo_create", "svo_destroy", "sv
            "svo_alloc_device", "svo_free_device", "svo_copy_to_device", "svo_launch_count", "svo_batch_stage_ms",
            "svo_set_profiling", "svo_lane_stream", "svo_debug_tap", "svo_debug_retain_best",
            "svo_pnp_ransac", "svo_pose_optimize", "svo_debug_hamming_matrix", "svo_debug_tc_profile", "svo_project_map",
-           "svo_track_create", "svo_track_reset", "svo_track_state", "svo_track_kp_capacity"]
+           "svo_track_create", "svo_track_reset", "svo_track_state", "svo_track_kp_capacity", "svo_set_outputs"]
 
 _lib = None
 
@@ -130,6 +131,7 @@ def load():
     L.svo_launch_count.restype = C.c_longlong
     L.svo_batch_stage_ms.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     L.svo_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    L.svo_set_outputs.argtypes = [C.c_void_p, C.c_int]
     L.svo_lane_stream.argtypes = [C.c_void_p, C.c_int]
     L.svo_lane_stream.restype = C.c_void_p
     L.svo_debug_tap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
@@ -395,8 +397,8 @@ class Context:
         n_prev, n_map = (o.n_prev, o.n_map) if tracked else (arr[i].n_prev, arr[i].n_map)
         nl, nr = o.n_left, o.n_right
         r = dict(status=o.status, n_left=nl, n_right=nr, n_stereo=o.n_stereo,
-                 kp_left=_view(o.kp_left, KP_DTYPE, (nl,)), kp_right=_view(o.kp_right, KP_DTYPE, (nr,)),
-                 desc_left=_view(o.desc_left, np.uint8, (nl, 32)), desc_right=_view(o.desc_right, np.uint8, (nr, 32)),
+                 kp_left=_view(o.kp_left, KP_DTYPE, (nl,)), kp_right=_view(o.kp_right, KP_DTYPE, (nr,)) if o.kp_right else None,
+                 desc_left=_view(o.desc_left, np.uint8, (nl, 32)), desc_right=_view(o.desc_right, np.uint8, (nr, 32)) if o.desc_right else None,
                  u_right=_view(o.u_right, np.float32, (nl,)), depth=_view(o.depth, np.float32, (nl,)),
                  claim_row=_view(o.claim_row, np.int32, (nl,)), n_prev=n_prev, n_map=n_map)
         if tracked:
@@ -443,6 +445,10 @@ class Context:
         ms = np.zeros(14, np.float32)
         self._chk(self.lib.svo_batch_stage_ms(self.h, lane, _p(ms), 14))
         return dict(zip(STAGES, ms.tolist()))
+
+    def set_outputs(self, flags):
+        """OUT_COMPACT | OUT_NO_RIGHT: what the batches submitted from now on copy back (0: everything at capacity)."""
+        self._chk(self.lib.svo_set_outputs(self.h, int(flags)))
 
     def set_profiling(self, on):
         self._chk(self.lib.svo_set_profiling(self.h, int(bool(on))))

@@ -195,3 +195,49 @@ def test_tracked_kitti_shape_2000_features(svo):
                           shape=synth.K_SHAPE, check_state=False)
     assert st["p1"] > 2000 and st["p2"] > 50, st
     ctx.close()
+
+
+@pytest.mark.parametrize("rows", [None, "100"])
+def test_compact_and_left_only_outputs_are_the_same_results(svo, rows, monkeypatch):
+    """svo_set_outputs: the compact strided copies (SVO_OUT_COMPACT) and leaving the right image's features on the device
+    (SVO_OUT_NO_RIGHT) change what crosses PCIe, not the results.  With SVO_B200_COMPACT_ROWS=100 every frame holds more
+    rows than the copies carry, so svo_batch_wait's tail fetch runs for every array."""
+    if rows:
+        monkeypatch.setenv("SVO_B200_COMPACT_ROWS", rows)
+    ctx = svo.Context(SHAPE[1], SHAPE[0], nfeatures=500, max_batch=2, lanes=1, max_rows=2000)
+    ctx.track_create(2, 2000, 4)
+    seqs = [synth.Sequence(SHAPE, seed=s) for s in (51, 52)]
+    rng = np.random.default_rng(9)
+    results = {}
+    for flags in (0, svo.OUT_COMPACT, svo.OUT_COMPACT | svo.OUT_NO_RIGHT):
+        ctx.set_outputs(flags)
+        ctx.track_reset(0); ctx.track_reset(1)
+        out = []
+        prev = None
+        for t in range(4):
+            # frame 0 of the batch is tracked (with a veto), frame 1 brings 1500 pass-1 rows of its own (> the compact width)
+            fr = [frame_dict(seqs[0].frame(t), 0, t, (BOXES * np.array([0.32, 0.32, 0.64, 0.64])).astype(np.int32), F_TEST),
+                  dict(left=seqs[1].frame(t)[0], right=seqs[1].frame(t)[1], bf=BF, baseline=BASE)]
+            if prev is not None:
+                big = np.concatenate([prev, np.random.default_rng(t).integers(0, 256, (1500 - len(prev), 32), dtype=np.uint8)], 0)
+                fr[1].update(prev_desc=big, map_desc=prev[::2].copy())
+            ctx.batch_submit(0, fr); ctx.batch_wait(0)
+            out.append([ctx.batch_result(0, 0), ctx.batch_result(0, 1)])
+            prev = out[-1][1]["desc_left"].copy()
+        results[flags] = out
+    ctx.set_outputs(0)
+    base = results[0]
+    for flags, out in results.items():
+        for t in range(4):
+            for i in range(2):
+                a, b = base[t][i], out[t][i]
+                for k, v in a.items():
+                    if k in ("kp_right", "desc_right") and flags & svo.OUT_NO_RIGHT:
+                        assert b[k] is None
+                        continue
+                    if isinstance(v, np.ndarray):
+                        assert v.dtype == b[k].dtype and v.shape == b[k].shape and v.tobytes() == b[k].tobytes(), (flags, t, i, k)
+                    else:
+                        assert v == b[k], (flags, t, i, k)
+    assert base[3][1]["n_prev"] == 1500 and base[3][0]["n_prev"] > 300
+    ctx.close()
