@@ -61,16 +61,18 @@ __device__ __forceinline__ uint32_t fast_quick4(const uint8_t *q, int sp, uint32
 }
 
 // Exact score: max over the 16 arcs of 9 contiguous ring pixels of min(v - p) (centre brighter) and of
-// min(p - v) (centre darker), minus 1; 0 unless >= t.  Both polarities at once, branch-free, on packed
-// s16x2 values with the DPX min3/max3 instructions (VIMNMX3.S16x2): register X[k] holds the biased
-// differences e = v + 256 - p of ring pixels k (low half) and k + 8 (high half), so one instruction
-// advances two arcs.  Sliding 9-minimum = min3 of min3 (windows of 3, then offsets 0/3/6).
+// min(p - v) (centre darker), minus 1; 0 unless >= t.  With r the ring values, min over an arc of (v - r) is
+// v - max over the arc of r, so both polarities come from the arcs' maxima and minima of r itself:
+//     bright = v - min over arcs (max over arc r)          dark = max over arcs (min over arc r) - v
+// branch-free on packed u16x2 values with the DPX min3/max3 instructions (VIMNMX3.U16x2): register X[k] holds ring
+// pixels k (low half) and k + 8 (high half), so one instruction advances two arcs.  Sliding 9-extremum = 3-extremum of
+// 3-extrema (windows of 3, then offsets 0/3/6); the eight results per polarity are reduced as a tree.
 __device__ __forceinline__ uint32_t swap16(uint32_t x) { return __byte_perm(x, 0, 0x1032); }
 __device__ __forceinline__ int fast_score(const uint8_t *p, int sp, int t)
 {
-    const uint32_t vb = ((uint32_t)p[0] + 256u) * 0x10001u;
+    const int v = p[0];
     uint32_t X[16];
-#define FAST_E(k, lo, hi) X[k] = vb - ((uint32_t)p[lo] + ((uint32_t)p[hi] << 16))
+#define FAST_E(k, lo, hi) X[k] = (uint32_t)p[lo] + ((uint32_t)p[hi] << 16)
     FAST_E(0, 3 * sp, -3 * sp);          FAST_E(1, 3 * sp + 1, -3 * sp - 1);
     FAST_E(2, 2 * sp + 2, -2 * sp - 2);  FAST_E(3, sp + 3, -sp - 3);
     FAST_E(4, 3, -3);                    FAST_E(5, -sp + 3, sp - 3);
@@ -78,22 +80,24 @@ __device__ __forceinline__ int fast_score(const uint8_t *p, int sp, int t)
 #undef FAST_E
 #pragma unroll
     for (int k = 0; k < 8; ++k) X[k + 8] = swap16(X[k]);
-    uint32_t a[14], b[14];
+    uint32_t a[14], b[14];                  // maxima / minima of ring pixels k, k + 1, k + 2
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        a[k] = __vimin3_s16x2(X[k], X[k + 1], X[k + 2]);
-        b[k] = __vimax3_s16x2(X[k], X[k + 1], X[k + 2]);
+        a[k] = __vimax3_u16x2(X[k], X[k + 1], X[k + 2]);
+        b[k] = __vimin3_u16x2(X[k], X[k + 1], X[k + 2]);
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) { a[k + 8] = swap16(a[k]); b[k + 8] = swap16(b[k]); }
-    uint32_t mx = 0u, mn = 0x7fff7fffu;     // max over arcs of the arc minimum / min over arcs of the arc maximum
+    uint32_t A[8], B[8];                    // arc k (low half) and arc k + 8 (high half): maximum / minimum of its 9 pixels
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        mx = __vmaxs2(mx, __vimin3_s16x2(a[k], a[k + 3], a[k + 6]));
-        mn = __vmins2(mn, __vimax3_s16x2(b[k], b[k + 3], b[k + 6]));
+        A[k] = __vimax3_u16x2(a[k], a[k + 3], a[k + 6]);
+        B[k] = __vimin3_u16x2(b[k], b[k + 3], b[k + 6]);
     }
-    const int bright = max((int)(mx & 0xffffu), (int)(mx >> 16)) - 256;   // max arc-min of (v - p)
-    const int dark = 256 - min((int)(mn & 0xffffu), (int)(mn >> 16));     // max arc-min of (p - v)
+    const uint32_t lo2 = __vimin3_u16x2(__vimin3_u16x2(A[0], A[1], A[2]), __vimin3_u16x2(A[3], A[4], A[5]), __vminu2(A[6], A[7]));
+    const uint32_t hi2 = __vimax3_u16x2(__vimax3_u16x2(B[0], B[1], B[2]), __vimax3_u16x2(B[3], B[4], B[5]), __vmaxu2(B[6], B[7]));
+    const int bright = v - min((int)(lo2 & 0xffffu), (int)(lo2 >> 16));   // max arc-min of (v - p)
+    const int dark = max((int)(hi2 & 0xffffu), (int)(hi2 >> 16)) - v;     // max arc-min of (p - v)
     const int s = max(bright, dark) - 1;
     return s >= t ? s : 0;
 }
@@ -161,9 +165,36 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(Bufs b, Geom g, int slot0
     const int wcap = ((nchunks + nwarps - 1) / nwarps) << 7;
     uint16_t *mine = cand + warp * wcap;
     const uint32_t t4 = (uint32_t)(t + 1) * 0x10001u;     // fast_quick4's packed threshold
-    const uint32_t ltm = (1u << lane) - 1u;
     int nmine = 0;
     {
+        // Survivors are compacted once per 8 chunks: a lane keeps the 4-bit hit masks of its quads in one register (acc) and
+        // the chunks' first positions go to a small per-warp table; a flush is one warp prefix sum of the hit counts plus a
+        // store per hit (compacting every chunk with three ballots cost 70 instructions per chunk against 105 for the test).
+        __shared__ uint16_t cbase[FAST_THREADS / 32][8];
+        uint16_t *wb = cbase[warp];
+        const int l4 = lane << 2;
+        uint32_t acc = 0;
+        int jn = 0;
+        auto flush = [&]() {
+            __syncwarp();
+            const int hc = __popc(acc);
+            int inc = hc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += v;
+            }
+            int pos = nmine + inc - hc;
+            nmine += __shfl_sync(0xffffffffu, inc, 31);
+            uint32_t bits = acc;
+            while (bits) {
+                const int bi = __ffs((int)bits) - 1;
+                bits &= bits - 1;
+                mine[pos++] = (uint16_t)(wb[bi >> 2] + l4 + (bi & 3));
+            }
+            __syncwarp();
+            acc = 0; jn = 0;
+        };
         int r = 0, ch = warp;
         while (ch >= cpr) { ch -= cpr; ++r; }
         for (int c = warp; c < nchunks; c += nwarps) {
@@ -174,22 +205,14 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(Bufs b, Geom g, int slot0
             // candidates and get a score, which nothing reads: stage C only suppresses and emits x0 <= x < x1, whose
             // neighbours lie inside [x0 - 1, x1] (masking them here cost 12 instructions on every quad).
             if (qi < nq) pass = fast_quick4(pix + (r + 3) * sp + x, sp, t4);
-            // compaction: 4-bit hit mask per lane, warp prefix sum of the hit counts from three ballots
-            // (a count is at most 4), then up to four stores
-            const uint32_t nib = (((pass >> 7) & 0x01010101u) * 0x10204080u) >> 28;
-            const int hc = __popc(nib);
-            const uint32_t b0 = __ballot_sync(0xffffffffu, hc & 1), b1 = __ballot_sync(0xffffffffu, hc & 2),
-                           b2 = __ballot_sync(0xffffffffu, hc & 4);
-            if ((b0 | b1 | b2) == 0) { ch += nwarps; while (ch >= cpr) { ch -= cpr; ++r; } continue; }
-            int pos = nmine + __popc(b0 & ltm) + 2 * __popc(b1 & ltm) + 4 * __popc(b2 & ltm);
-            const int p0 = r * sp + x;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (nib & (1u << k)) mine[pos++] = (uint16_t)(p0 + k);
-            nmine += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+            const uint32_t nib = (((pass >> 7) & 0x01010101u) * 0x10204080u) >> 28;   // 4-bit hit mask of the quad
+            acc |= nib << (jn << 2);
+            if (lane == 0) wb[jn] = (uint16_t)(r * sp + xq0 + (ch << 7));             // position of the chunk's first pixel
             ch += nwarps;
             while (ch >= cpr) { ch -= cpr; ++r; }
+            if (++jn == 8) flush();
         }
+        if (jn) flush();
     }
     __syncwarp();
     for (int i = lane; i < nmine; i += 32) {

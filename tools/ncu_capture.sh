@@ -5,7 +5,7 @@
 # Numbers printed by a run under ncu are never bench values.
 set -u
 TAG=${1:-r1}
-CMD="python bench.py --steps 2 --warmup 3 --pool 32 --no-cpu-baseline"
+CMD="python bench.py --steps 2 --warmup 3 --pool 32 --no-cpu-baseline --no-tracked --verify 0"
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu1.log 2>&1
 # first launch of the 5th 32-frame step (setup passes and warm-up come first); the launch ID is ncu's own count
