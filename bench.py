@@ -485,30 +485,51 @@ def run_gpu(args, rank, world, local_rank):
         # pass-2 rows k_shortlist really scans: rows linked to a pass-1 row are skipped or served from the pass-1
         # distance matrix (k_reuse); in this workload those are exactly the rows with map_prev_row >= 0
         need_rows = float((h_mpr < 0).sum()) / P
-        # single kernels bracketed by their own events on the lane's stream (DESIGN.md section 4 lists the bytes)
-        single = {"k_fast": ("fast", ab["fast"] * nimg), "k_blur": ("blur", ab["blur"] * nimg),
-                  "k_describe": ("describe", ab["describe"] * nimg), "k_harris": ("harris", ab["harris"] * nimg),
-                  "k_pairs": ("k_pairs", B * (npv + NFEAT) * 32 + B * npv * NFEAT),      # descriptors in, u8 matrix out
-                  "k_shortlist(pass 2)": ("k_shortlist2", B * (need_rows + free_cols) * 32)}   # rows + free columns in
+        # single kernels bracketed by their own events on the lane's stream (DESIGN.md section 4 lists the bytes); the
+        # second name is the kernel's key in profiles/traffic.json (ncu: DRAM bytes and warp instructions per launch)
+        single = {"k_fast": ("fast", ab["fast"] * nimg, "k_fast"), "k_blur": ("blur", ab["blur"] * nimg, "k_blur"),
+                  "k_describe": ("describe", ab["describe"] * nimg, "k_describe"), "k_harris": ("harris", ab["harris"] * nimg, "k_harris"),
+                  # tensor-core Hamming tiles: descriptors in as operand images (256 B per descriptor), lists / minima out
+                  "k_tc_hamming<PAIRS> (BF + pass-1 distances)": ("k_pairs", B * (npv + NFEAT) * 256, "k_tc_hamming<0>"),
+                  "k_tc_hamming<SHORT> (pass-2 short lists)": ("k_shortlist2", B * (MAP_ROWS + free_cols) * 256, "k_tc_hamming<2>")}
         dom = max(single, key=lambda k: stage.get(single[k][0], 0.0))
         dur_ms = stage.get(single[dom][0], 0.0)
         alg_bytes = float(single[dom][1])
         achieved = alg_bytes / (dur_ms * 1e-3) / 1e9 if dur_ms > 0 else None
         traffic = None
+        counts, ceil = {}, {}
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom, {}).get("dram_bytes_per_launch")
+            counts = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            ceil = json.load(open(os.path.join(ROOT, "profiles", "r2_ceilings.json")))
         except Exception:
             pass
-        # the matchers are bound by the XU pipe (POPC, 16 lanes/clk/SM), not by bytes: report that ceiling too
-        popc = None
-        if dom in ("k_pairs", "k_shortlist(pass 2)") and dur_ms > 0:
-            pairs = B * (npv * NFEAT if dom == "k_pairs" else need_rows * free_cols)
-            per_pair = 6 if dom == "k_pairs" else 5
-            sm_clock = (sampler.result()["sm_mhz"] or 1965) * 1e6
-            peak_popc = 148 * 16 * sm_clock
-            popc = {"pairs_per_launch": pairs, "popc_per_pair": per_pair, "achieved_gpopc_s": pairs * per_pair / (dur_ms * 1e-3) / 1e9,
-                    "peak_gpopc_s": peak_popc / 1e9, "frac": pairs * per_pair / (dur_ms * 1e-3) / peak_popc,
-                    "peak_source": "148 SMs x 16 POPC/clk/SM x sampled SM clock"}
+        headline_cfg = (W_IMG, H_IMG, NFEAT, MAP_ROWS, B, args.distribution) == (1241, 376, 2000, 5000, 32, "retainbest")
+        kc = counts.get("kernels", {}).get(single[dom][2], {}) if headline_cfg else {}
+        traffic = kc.get("dram_bytes_per_launch")
+        # What binds the path is instruction issue, not bytes: the kernel's warp instructions per launch
+        # (ncu, a property of the workload) over its live launch time against the MEASURED issue ceiling of this GPU
+        # (tools/ceilings.cu: 8 independent integer chains per thread, every SM full)
+        issue = None
+        peak_issue = ceil.get("issue_warp_inst_per_s")
+        if kc.get("warp_inst_per_launch") and peak_issue and dur_ms > 0:
+            a_i = kc["warp_inst_per_launch"] / (dur_ms * 1e-3)
+            issue = {"bound": "issue", "warp_inst_per_launch": kc["warp_inst_per_launch"], "achieved_ginst_s": a_i / 1e9,
+                     "peak_ginst_s": peak_issue / 1e9, "frac": a_i / peak_issue,
+                     "peak_source": "measured on this GPU model (tools/ceilings.cu -> profiles/r2_ceilings.json), %.2f warp instructions/clk/SM"
+                                    % ceil.get("issue_per_sm_per_clk_at_max_clock", 0.0),
+                     "alone_under_ncu": {"duration_us": kc.get("ncu_duration_us"), "issue_active_pct": kc.get("issue_active_pct"),
+                                         "pipe_alu_pct": kc.get("pipe_alu_pct"), "pipe_fma_pct": kc.get("pipe_fma_pct"),
+                                         "pipe_xu_pct": kc.get("pipe_xu_pct"), "pipe_lsu_pct": kc.get("pipe_lsu_pct")},
+                     "note": "launch_ms is the kernel's time while the other lanes' kernels share the SMs; alone_under_ncu is the same "
+                             "kernel alone (cold cache, serialised)"}
+        step_issue = None
+        if headline_cfg and counts.get("step_warp_inst") and peak_issue:
+            a_s = counts["step_warp_inst"] / (ms_dev / args.steps * 1e-3)
+            step_issue = {"warp_inst_per_step": counts["step_warp_inst"], "achieved_ginst_s": a_s / 1e9, "peak_ginst_s": peak_issue / 1e9,
+                          "frac": a_s / peak_issue, "dram_bytes_per_step": counts.get("step_dram_bytes"),
+                          "dram_gbs": counts.get("step_dram_bytes", 0) / (ms_dev / args.steps * 1e-3) / 1e9, "hbm_frac":
+                          counts.get("step_dram_bytes", 0) / (ms_dev / args.steps * 1e-3) / 1e9 / peak,
+                          "note": "all kernels of a 32-frame step (ncu: warp instructions and DRAM bytes) over the measured step time"}
         h2d = B * (2 * W_IMG * H_IMG + int(n_prev.mean()) * 33 + MAP_ROWS * 36 + 16)
         d2h = 2 * B * (K * 56 + 8) + B * (K * 21 + 4) + B * max(MAP_ROWS, K) * 14
         e2e_hc = {"value": frames_total / (ms_hc * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -554,11 +575,11 @@ def run_gpu(args, rank, world, local_rank):
             "clocks": sampler.result(),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                         "launch_ms": dur_ms, "algorithmic_bytes_per_launch": alg_bytes, "xu_popc": popc,
-                         "note": "per-frame working sets are L2-resident and the dominant kernels are issue/XU-pipe bound, "
-                                 "so the HBM fraction is small by construction (DESIGN.md section 4); launch_ms is measured "
-                                 "while the other lanes' kernels share the GPU (alone under ncu the kernel is ~40 % shorter: "
-                                 "profiles/r1_step_summary.txt)"},
+                         "launch_ms": dur_ms, "algorithmic_bytes_per_launch": alg_bytes, "issue": issue, "step": step_issue,
+                         "note": "this path is not HBM-bound: per-frame working sets are small and the dominant kernels are bound by "
+                                 "instruction issue / the integer ALU pipe, so the HBM fraction is small by construction; the operative "
+                                 "ceiling is roofline.issue (measured issue rate of the GPU), roofline.step gives both figures for the "
+                                 "whole step (DESIGN.md section 4)"},
             "profiled_pass": {"steps": psteps, "ms_per_step": ms_prof / psteps,
                               "note": "stage_ms_per_step, kernel_ms_per_launch and roofline.launch_ms come from this pass"},
             "stage_ms_per_step": kernels, "kernel_ms_per_launch": {k: stage.get(v[0], 0.0) for k, v in single.items()}, "p50_ms_per_frame_single": p50, "wall_ms_per_step": wall_dev / args.steps,

@@ -20,7 +20,7 @@
 #define SVO_STRIDE_BGR (1 << 30)  // flag in a per-image stride word: the source is interleaved BGR
 #define SVO_WIN_CELLS 4096     // most cells of the keypoint grid used by the windowed pass 2
 #define SVO_TC_TILE_BYTES 32768  // one tensor-core operand image: 128 descriptors x 256 int8 (tcham.cu)
-#define SVO_TC_STREAMS 4       // column ranges (streams) a tensor-core CTA splits a row's scan into (tcham.cu)
+#define SVO_TC_STREAMS 2       // column ranges (streams) a tensor-core CTA splits a row's scan into (tcham.cu)
 #define SVO_TC_SEG (SVO_SHORT_CAP / SVO_TC_STREAMS)   // TC_SHORT: short-list slots of each range of a row
 #define SVO_STATUS_OVERFLOW 1  // bit set in the per-image status word on a capacity overflow
 #define SVO_STATUS_DEPTH 2     // introselect reached its depth limit (heap-select path ran)

@@ -11,19 +11,22 @@
 // K-major, 16-byte chunks XOR-swizzled by the row: the canonical SWIZZLE_128B layout).  A tile is therefore one
 // contiguous bulk copy (cp.async.bulk -> mbarrier complete_tx), no tensor map, no per-tile expansion work.
 //
-// One CTA owns 128 "A" rows (tile rows = TMEM lanes) of one frame and runs FOUR independent streams over the frame's
-// "B" tiles: stream q owns the q-th contiguous quarter of the tiles, one shared-memory stage, one 128-column
-// accumulator buffer (4 x 128 = all 512 TMEM columns) and one epilogue warpgroup:
-//     warp 16     one thread issues the bulk copies (A once, then every stream's tiles) and waits on empty[stream]
-//     warp 17     one thread issues 8 x tcgen05.mma (K = 32 bytes each) per tile, round-robin over the streams, and
+// One CTA owns 128 "A" rows (tile rows = TMEM lanes) of one frame and runs TC_STREAMS (2) independent streams over the
+// frame's "B" tiles: stream q owns the q-th contiguous share of the tiles, one shared-memory stage, one 128-column
+// accumulator buffer and one epilogue warpgroup; two such CTAs fit an SM (111 KB of shared memory and 256 of the 512
+// TMEM columns each):
+//     warp 8      one thread issues the bulk copies (A once, then every stream's tiles) and waits on empty[stream]
+//     warp 9      one thread issues 8 x tcgen05.mma (K = 32 bytes each) per tile, round-robin over the streams, and
 //                 commits to empty[stream] / tfull[stream]; the warp also allocates and frees the TMEM columns
-//     warps 0-15  warp w serves stream w / 4 and TMEM lane quarter w % 4: tcgen05.ld 32 lanes x 32 columns at a time,
+//     warps 0-7   warp w serves stream w / 4 and TMEM lane quarter w % 4: tcgen05.ld 32 lanes x 32 columns at a time,
 //                 the mode's epilogue, arrive on tempty[stream]
 // The tensor pipe needs ~512 cycles per tile; the epilogues need several thousand issue slots per tile, so the kernel is
-// bound by them: sixteen epilogue warps (four per scheduler) keep the issue slots busy, where a single warpgroup left
-// them idle behind instruction latencies (measured: 3x).  Inside a stream a thread meets its row's columns in ascending
-// order, which is the order of the reference's scans (src/pnpmatch.cc:79-95, :177-190); the four contiguous ranges of
-// a row compose in stream order exactly like the lane blocks of match.cu's k_scores.
+// bound by them: sixteen epilogue warps per SM (four per scheduler) keep the issue slots busy, where a single warpgroup
+// left them idle behind instruction latencies (measured: 3x).  Measured in the three-lane pipeline (gpurun_out/
+// bench_r2{r,s,t}*.json): one CTA of four streams per SM (197 KB: nothing of another lane fits beside it) 24.3-24.4 k
+// frames/s, two CTAs of two streams 24.8-24.9 k, three CTAs of one stream 24.6-24.7 k.  Inside a stream a thread meets
+// its row's columns in ascending order, which is the order of the reference's scans (src/pnpmatch.cc:79-95, :177-190);
+// the contiguous ranges of a row compose in stream order exactly like the lane blocks of match.cu's k_scores.
 //
 // Modes (what the epilogue does with dot = 256 - 2 d):
 //   TC_PAIRS   A = current frame (BFMatcher queries), B = previous frame.  Per query the first minimum over the train
@@ -48,7 +51,7 @@
 #define TC_TMEM_COLS (TC_STREAMS * TC_N) // 512: all of the SM's tensor memory
 // A tile + one B stage per stream, alignment slack, per-warp claim-time staging, per-row combine buffers, barriers
 #define TC_WARP_SCRATCH 320              // ints per epilogue warp: claim times of a tile (TC_SCORES) / a chunk's distance bytes [8][32] + columns [32]
-#define TC_HITCAP 768                    // TC_PAIRS: pass-1 candidates buffered per CTA before they go to the rows' lists
+#define TC_HITCAP 128                    // TC_PAIRS: pass-1 candidates buffered per CTA before they go to the rows' lists
 #define TC_SMEM_BYTES ((1 + TC_STREAMS) * SVO_TC_TILE_BYTES + 1024 + TC_EPI_WARPS * TC_WARP_SCRATCH * 4 + TC_STREAMS * TC_M * 12 + TC_HITCAP * 8 + 256)
 
 namespace {
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(256) k_tc_expand(TcExpandArgs e)
 #define TC_STAMP(role, slot) do { if (prof && (slot) < 64) prof[(role) * 64 + (slot)] = clock64(); } while (0)
 
 template <int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_hamming(TcArgs p)
+__global__ void __launch_bounds__(TC_THREADS, 2) k_tc_hamming(TcArgs p)
 {
     extern __shared__ uint8_t tc_smem_raw[];
     const int f = blockIdx.y;
