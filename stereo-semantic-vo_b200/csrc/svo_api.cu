@@ -1641,6 +1641,7 @@ int svo_debug_hamming_matrix(svo_ctx *ctx, const uint8_t *a, int na, const uint8
     int *d_dump = nullptr;
     const int pitch = (nb + 31) & ~31;
     CU(cudaMalloc((void **)&d_dump, sizeof(int) * (size_t)na * pitch));
+    CU(cudaMemsetAsync(d_dump, 0, sizeof(int) * (size_t)na * pitch, st));   // the pitch padding is copied back too
     CU(cudaMemcpyAsync(s.map, a, (size_t)na * 32, cudaMemcpyDefault, st));
     CU(cudaMemcpyAsync(s.cols, b, (size_t)nb * 32, cudaMemcpyDefault, st));
     TcArgs tc;
