@@ -365,7 +365,7 @@ def run_gpu(args, rank, world, local_rank):
     # ---- tracked end-to-end pass: the tracker state (last frame's descriptors and map points, local map) stays in HBM
     # (svo_track_*), so only the images cross PCIe.  Every lane owns B sequences; a step advances each by one frame.
     trk = None
-    ms_trk = wall_trk = None
+    ms_trk = wall_trk = ms_pose = wall_pose = None
     stage_trk = {}
     if not args.no_tracked:
         K4 = (float(CAL["fx"]), float(CAL["fy"]), float(CAL["cx"]), float(CAL["cy"]))
@@ -422,6 +422,10 @@ def run_gpu(args, rank, world, local_rank):
         trk = {"sequences": NS, "natural_map_rows": natural, "ballast_rows": n_ballast, "mean_map_rows": float(np.mean(seen["n_map"])),
                "mean_prev_rows": float(np.mean(seen["n_prev"])), "verified_frames": tv, "verified_claims": tc}
         verified += tv; claims += tc
+        # the same pass returning only what the steps after the matchers read (SVO_OUT_POSE_INPUTS: left keypoints, depth,
+        # claims and the owned points' names / positions); the subset equals the full outputs (tests/test_gpu_track.py)
+        ctx.set_outputs(svo.OUT_COMPACT | svo.OUT_POSE_INPUTS)
+        ms_pose, wall_pose, _, _ = timed(tracked_batch, args.steps, args.warmup, 0)
         ctx.set_outputs(0)
     # per-stage / per-kernel durations: the same steps again with CUDA events on the lanes' own streams (the events
     # split the captured graph into plain launches, so this pass is a few percent slower than the headline)
@@ -468,7 +472,8 @@ def run_gpu(args, rank, world, local_rank):
                 "note": "wall clock around svo_pnp_ransac (100 samples, 8 px, refit) and svo_pose_optimize (g2o LM, 10 iterations), "
                         "host buffers in and out; includes the Python binding's packing"}
 
-    ms_dev, ms_hc, ms_trk_m = grp.max_over_ranks([ms_dev, ms_hc, ms_trk if ms_trk is not None else 0.0])
+    ms_dev, ms_hc, ms_trk_m, ms_pose_m = grp.max_over_ranks([ms_dev, ms_hc, ms_trk if ms_trk is not None else 0.0,
+                                                             ms_pose if ms_pose is not None else 0.0])
     frames_total = int(grp.sum_over_ranks([args.steps * B])[0])
     out = None
     if rank == 0:
@@ -570,6 +575,11 @@ def run_gpu(args, rank, world, local_rank):
                        "host_placement": ("process bound to the %d cores NVML reports local to its GPU" % len(near)) if near else "unbound"},
             "e2e": e2e_main,
             "e2e_host_chained": e2e_hc,
+            "e2e_pose_inputs": None if trk is None else {
+                "value": frames_total / (ms_pose_m * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * (2 * W_IMG * H_IMG + 16) + B * 200,
+                "d2h_bytes_per_step": B * ((NFEAT + 32) * 48 + 40), "ms_per_step": ms_pose_m / args.steps,
+                "mode": "tracked pass returning only what solvePnPRansac / PoseOptimization read (svo_set_outputs: SVO_OUT_POSE_INPUTS): "
+                        "left keypoints, depth, claim_row, mp_create, mp_xyz; descriptors, BF matches, match_score and row flags stay in HBM"},
             "tracked": trk,
             "gpu_launches": launches,
             "verified_frames": verified,

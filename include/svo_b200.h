@@ -355,9 +355,15 @@ int svo_batch_stage_ms(svo_ctx *ctx, int lane, float *ms, int n);
  *                     fetched by svo_batch_wait.  Same results, ~15 % fewer bytes.
  *   SVO_OUT_NO_RIGHT  the right image's keypoints and descriptors stay on the device (kp_right / desc_right come back
  *                     NULL; n_right, u_right and depth are still filled).  The reference's frame keeps no right-image
- *                     features either: keypoints_r is keypoints_l shifted by the disparity (src/frame.cc:122-138). */
+ *                     features either: keypoints_r is keypoints_l shifted by the disparity (src/frame.cc:122-138).
+ *   SVO_OUT_POSE_INPUTS  only what the steps after the matchers read — Tracklastframe's solvePnPRansac and
+ *                     Optimizer::PoseOptimization (src/pnpmatch.cc:215-227, src/Optimizer.cc:40-70): the left keypoints,
+ *                     depth, claim_row and (tracked frames) mp_create / mp_xyz.  Descriptors, u_right, the BF matches,
+ *                     match_score and the row flags stay on the device (their pointers come back NULL); with the
+ *                     tracker state in HBM the next frame does not need them from the host.  Implies SVO_OUT_NO_RIGHT. */
 #define SVO_OUT_COMPACT 1
 #define SVO_OUT_NO_RIGHT 2
+#define SVO_OUT_POSE_INPUTS 4
 int svo_set_outputs(svo_ctx *ctx, int flags);
 /* Turn per-stage event recording on (1) or off (0, default). */
 int svo_set_profiling(svo_ctx *ctx, int on);

@@ -491,16 +491,17 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
     const size_t I = 2 * (size_t)n, KC = g.kp_cap;
     const size_t W = (size_t)L.out_w, WP = (size_t)L.out_wp;
     const bool no_right = (L.out_flags & SVO_OUT_NO_RIGHT) != 0;
+    const bool pose_only = (L.out_flags & SVO_OUT_POSE_INPUTS) != 0;     // implies no_right (svo_set_outputs)
     auto copy_extract = [&](cudaStream_t cs) -> int {   // everything extraction and stereo produced
         CU(cudaMemcpyAsync(h.nkp, b.nkp + L.slot0, sizeof(int) * I, cudaMemcpyDeviceToHost, cs));
         if (no_right) {   // left images sit in the even slots
             CU(copy_rows(h.kp, b.kp + (size_t)L.slot0 * KC, sizeof(svo_keypoint), 2 * KC, W, n, cs));
-            CU(copy_rows(h.desc, b.desc + (size_t)L.slot0 * KC * 32, 32, 2 * KC, W, n, cs));
+            if (!pose_only) CU(copy_rows(h.desc, b.desc + (size_t)L.slot0 * KC * 32, 32, 2 * KC, W, n, cs));
         } else {
             CU(copy_rows(h.kp, b.kp + (size_t)L.slot0 * KC, sizeof(svo_keypoint), KC, W, I, cs));
             CU(copy_rows(h.desc, b.desc + (size_t)L.slot0 * KC * 32, 32, KC, W, I, cs));
         }
-        CU(copy_rows(h.u_right, sa.u_right, sizeof(float), KC, W, n, cs));
+        if (!pose_only) CU(copy_rows(h.u_right, sa.u_right, sizeof(float), KC, W, n, cs));
         CU(copy_rows(h.depth, sa.depth, sizeof(float), KC, W, n, cs));
         CU(cudaMemcpyAsync(h.n_stereo, sa.n_stereo, sizeof(int) * n, cudaMemcpyDeviceToHost, cs));
         return SVO_OK;
@@ -621,7 +622,7 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
     CU(cudaMemcpyAsync(h.np_out + ctx->cfg.max_batch, fb.params + FT + L.frame0, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h.status, b.status + L.slot0, sizeof(int) * I, cudaMemcpyDeviceToHost, st));
     if (!fork) TRY(copy_extract(st));
-    if (any_prev) {
+    if (any_prev && !pose_only) {
         CU(copy_rows(h.bf_idx, fb.bf_idx + (size_t)L.frame0 * K, sizeof(int), KC, W, n, st));
         CU(copy_rows(h.bf_dist, fb.bf_dist + (size_t)L.frame0 * K, sizeof(int), KC, W, n, st));
         CU(copy_rows(h.bf_keep, fb.bf_keep + (size_t)L.frame0 * K, 1, KC, W, n, st));
@@ -633,7 +634,7 @@ int enqueue_compute(svo_ctx *ctx, Lane &L, int n, bool any_prev, bool any_map, b
         CU(copy_rows(h.p1_row_claimed, fb.p1_row_claimed + (size_t)L.frame0 * R, 1, R, WP, n, st));
         if (veto) CU(copy_rows(h.p1_row_bad, fb.p1_row_bad + (size_t)L.frame0 * R, 1, R, WP, n, st));
     }
-    if (any_map) CU(cudaMemcpyAsync(h.p2_row_claimed, fb.p2_row_claimed + (size_t)L.frame0 * R, (size_t)n * R, cudaMemcpyDeviceToHost, st));
+    if (any_map && !pose_only) CU(cudaMemcpyAsync(h.p2_row_claimed, fb.p2_row_claimed + (size_t)L.frame0 * R, (size_t)n * R, cudaMemcpyDeviceToHost, st));
     CU(copy_rows(h.claim_row, fb.claim_row + (size_t)L.frame0 * K, sizeof(int), KC, W, n, st));
     return SVO_OK;
 }
@@ -829,7 +830,8 @@ int svo_get_geometry(const svo_ctx *ctx, int *lw, int *lh, float *lscale, int *q
 long long svo_launch_count(const svo_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int svo_set_outputs(svo_ctx *ctx, int flags)
 {
-    if (!ctx || (flags & ~(SVO_OUT_COMPACT | SVO_OUT_NO_RIGHT))) return fail(ctx, SVO_E_INVALID, "svo_set_outputs: unknown flag");
+    if (!ctx || (flags & ~(SVO_OUT_COMPACT | SVO_OUT_NO_RIGHT | SVO_OUT_POSE_INPUTS))) return fail(ctx, SVO_E_INVALID, "svo_set_outputs: unknown flag");
+    if (flags & SVO_OUT_POSE_INPUTS) flags |= SVO_OUT_NO_RIGHT;
     ctx->out_flags = flags;
     return SVO_OK;
 }
@@ -1438,8 +1440,8 @@ int svo_batch_submit(svo_ctx *ctx, int lane_i, const svo_frame_in *frames, int n
     // the sequence is therefore captured once into a CUDA graph and replayed (one launch instead of ~45 calls).
     auto run = [&](int phase) -> int {
         if (ev) return enqueue_compute(ctx, L, n, any_prev, any_map, fused, windowed, veto, tracked, phase, ev);
-        const int key = n | (any_prev ? 1 << 20 : 0) | (any_map ? 1 << 21 : 0) | (fused ? 1 << 22 : 0) | (windowed ? 1 << 23 : 0) | (veto ? 1 << 24 : 0) |
-                        (tracked ? 1 << 25 : 0) | (phase << 26) | (L.out_flags << 28) | (L.out_wp == R ? 1 << 30 : 0);
+        const int key = n | (any_prev ? 1 << 16 : 0) | (any_map ? 1 << 17 : 0) | (fused ? 1 << 18 : 0) | (windowed ? 1 << 19 : 0) | (veto ? 1 << 20 : 0) |
+                        (tracked ? 1 << 21 : 0) | (phase << 22) | (L.out_flags << 24) | (L.out_wp == R ? 1 << 28 : 0);
         LaneGraph *lg = nullptr;
         for (LaneGraph &c : L.graphs) if (c.key == key) lg = &c;
         if (!lg) {
@@ -1488,7 +1490,7 @@ int svo_batch_wait(svo_ctx *ctx, int lane_i)
         // compact result copies: a frame with more keypoints (or pass-1 rows) than the copies carried gets the rest now
         const Geom &g = ctx->g; const Bufs &b = ctx->b; FrameBufs &fb = ctx->fb; HostArena &h = L.h;
         const size_t KC = g.kp_cap, R = ctx->cfg.max_rows, W = L.out_w, WP = L.out_wp;
-        const bool no_right = (L.out_flags & SVO_OUT_NO_RIGHT) != 0;
+        const bool no_right = (L.out_flags & SVO_OUT_NO_RIGHT) != 0, pose_only = (L.out_flags & SVO_OUT_POSE_INPUTS) != 0;
         bool any = false;
         auto tail = [&](void *hbase, const void *dbase, size_t elem, size_t row0, size_t rows) {
             any = true;
@@ -1499,10 +1501,13 @@ int svo_batch_wait(svo_ctx *ctx, int lane_i)
             const size_t fo = (size_t)L.frame0 + i, so = (size_t)L.slot0 + 2 * i;
             if (nl > W) {
                 const size_t m = nl - W;
-                CU(tail(h.kp + 2 * i * KC, b.kp + so * KC, sizeof(svo_keypoint), W, m)); CU(tail(h.desc + 2 * i * KC * 32, b.desc + so * KC * 32, 32, W, m));
-                CU(tail(h.u_right + i * KC, fb.u_right + fo * KC, 4, W, m)); CU(tail(h.depth + i * KC, fb.depth + fo * KC, 4, W, m));
-                CU(tail(h.bf_idx + i * KC, fb.bf_idx + fo * KC, 4, W, m)); CU(tail(h.bf_dist + i * KC, fb.bf_dist + fo * KC, 4, W, m));
-                CU(tail(h.bf_keep + i * KC, fb.bf_keep + fo * KC, 1, W, m)); CU(tail(h.claim_row + i * KC, fb.claim_row + fo * KC, 4, W, m));
+                CU(tail(h.kp + 2 * i * KC, b.kp + so * KC, sizeof(svo_keypoint), W, m));
+                CU(tail(h.depth + i * KC, fb.depth + fo * KC, 4, W, m)); CU(tail(h.claim_row + i * KC, fb.claim_row + fo * KC, 4, W, m));
+                if (!pose_only) {
+                    CU(tail(h.desc + 2 * i * KC * 32, b.desc + so * KC * 32, 32, W, m)); CU(tail(h.u_right + i * KC, fb.u_right + fo * KC, 4, W, m));
+                    CU(tail(h.bf_idx + i * KC, fb.bf_idx + fo * KC, 4, W, m)); CU(tail(h.bf_dist + i * KC, fb.bf_dist + fo * KC, 4, W, m));
+                    CU(tail(h.bf_keep + i * KC, fb.bf_keep + fo * KC, 1, W, m));
+                }
                 if (L.tracked && h.mp_create) {
                     CU(tail(h.mp_create + i * KC, ctx->trk_mp_create + fo * KC, 4, W, m)); CU(tail(h.mp_xyz + i * KC * 3, ctx->trk_mp_xyz + fo * KC * 3, 12, W, m));
                 }
@@ -1513,7 +1518,7 @@ int svo_batch_wait(svo_ctx *ctx, int lane_i)
                 CU(tail(h.desc + (2 * i + 1) * KC * 32, b.desc + (so + 1) * KC * 32, 32, W, m));
             }
             const size_t np = std::min((size_t)std::max(h.np_out[i], 0), R);
-            if (np > WP) {
+            if (np > WP && !pose_only) {
                 const size_t m = np - WP;
                 CU(tail(h.p1_best_idx + i * R, fb.p1_best_idx + fo * R, 4, WP, m)); CU(tail(h.p1_best + i * R, fb.p1_best + fo * R, 4, WP, m));
                 CU(tail(h.p1_second + i * R, fb.p1_second + fo * R, 4, WP, m)); CU(tail(h.p1_row_claimed + i * R, fb.p1_row_claimed + fo * R, 1, WP, m));
@@ -1543,9 +1548,11 @@ int svo_batch_result(svo_ctx *ctx, int lane_i, int i, svo_frame_out *o)
     o->n_stereo = h.n_stereo[i];
     o->kp_left = h.kp + (2 * (size_t)i) * K; o->desc_left = h.desc + (2 * (size_t)i) * K * 32;
     if (!(L.out_flags & SVO_OUT_NO_RIGHT)) { o->kp_right = h.kp + (2 * (size_t)i + 1) * K; o->desc_right = h.desc + (2 * (size_t)i + 1) * K * 32; }
+    const bool pose_only = (L.out_flags & SVO_OUT_POSE_INPUTS) != 0;
     o->u_right = h.u_right + (size_t)i * K; o->depth = h.depth + (size_t)i * K;
     o->n_prev = h.np_out[i]; o->n_map = h.np_out[ctx->cfg.max_batch + i];
-    if (in.n_prev || in.track_seq) {
+    if (pose_only) { o->desc_left = nullptr; o->u_right = nullptr; }
+    if ((in.n_prev || in.track_seq) && !pose_only) {
         o->bf_idx = h.bf_idx + (size_t)i * K; o->bf_dist = h.bf_dist + (size_t)i * K; o->bf_keep = h.bf_keep + (size_t)i * K;
         if (!ctx->cfg.skip_match_score) {
             o->p1_best_idx = h.p1_best_idx + (size_t)i * R; o->p1_best = h.p1_best + (size_t)i * R;
@@ -1554,7 +1561,7 @@ int svo_batch_result(svo_ctx *ctx, int lane_i, int i, svo_frame_out *o)
         o->p1_row_claimed = h.p1_row_claimed + (size_t)i * R;
         if (L.veto) o->p1_row_bad = h.p1_row_bad + (size_t)i * R;     // NULL: no frame of the batch ran the veto
     }
-    if (in.n_map || in.track_seq) o->p2_row_claimed = h.p2_row_claimed + (size_t)i * R;
+    if ((in.n_map || in.track_seq) && !pose_only) o->p2_row_claimed = h.p2_row_claimed + (size_t)i * R;
     if (in.track_seq) { o->mp_create = h.mp_create + (size_t)i * K; o->mp_xyz = h.mp_xyz + (size_t)i * K * 3; }
     o->claim_row = h.claim_row + (size_t)i * K;
     return SVO_OK;

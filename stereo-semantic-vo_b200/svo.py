@@ -16,7 +16,7 @@ KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4
 
 OK, E_INVALID, E_CUDA, E_CAPACITY, E_NOMEM = 0, -1, -2, -3, -4
 DIST_RETAIN_BEST, DIST_OCTREE = 0, 1     # svo_config.distribution
-OUT_COMPACT, OUT_NO_RIGHT = 1, 2         # svo_set_outputs
+OUT_COMPACT, OUT_NO_RIGHT, OUT_POSE_INPUTS = 1, 2, 4         # svo_set_outputs
 TAP_LEVEL, TAP_BLUR, TAP_FAST, TAP_SELECT1, TAP_SELECT2 = 0, 1, 2, 3, 4
 PASS1, PASS2 = 0, 1
 STAGES = ("total", "h2d", "pyramid", "fast", "select1", "harris", "select2", "blur", "describe",
@@ -398,19 +398,19 @@ class Context:
         nl, nr = o.n_left, o.n_right
         r = dict(status=o.status, n_left=nl, n_right=nr, n_stereo=o.n_stereo,
                  kp_left=_view(o.kp_left, KP_DTYPE, (nl,)), kp_right=_view(o.kp_right, KP_DTYPE, (nr,)) if o.kp_right else None,
-                 desc_left=_view(o.desc_left, np.uint8, (nl, 32)), desc_right=_view(o.desc_right, np.uint8, (nr, 32)) if o.desc_right else None,
-                 u_right=_view(o.u_right, np.float32, (nl,)), depth=_view(o.depth, np.float32, (nl,)),
+                 desc_left=_view(o.desc_left, np.uint8, (nl, 32)) if o.desc_left else None, desc_right=_view(o.desc_right, np.uint8, (nr, 32)) if o.desc_right else None,
+                 u_right=_view(o.u_right, np.float32, (nl,)) if o.u_right else None, depth=_view(o.depth, np.float32, (nl,)),
                  claim_row=_view(o.claim_row, np.int32, (nl,)), n_prev=n_prev, n_map=n_map)
         if tracked:
             r.update(mp_create=_view(o.mp_create, np.int32, (nl,)), mp_xyz=_view(o.mp_xyz, np.float32, (nl, 3)))
-        if n_prev:
+        if n_prev and o.bf_idx:
             r.update(bf_idx=_view(o.bf_idx, np.int32, (nl,)), bf_dist=_view(o.bf_dist, np.int32, (nl,)),
                      bf_keep=_view(o.bf_keep, np.uint8, (nl,)),
                      p1_best_idx=_view(o.p1_best_idx, np.int32, (n_prev,)), p1_best=_view(o.p1_best, np.int32, (n_prev,)),
                      p1_second=_view(o.p1_second, np.int32, (n_prev,)),
                      p1_row_claimed=_view(o.p1_row_claimed, np.uint8, (n_prev,)),
                      p1_row_bad=_view(o.p1_row_bad, np.uint8, (n_prev,)))
-        if n_map:
+        if n_map and o.p2_row_claimed:
             r.update(p2_row_claimed=_view(o.p2_row_claimed, np.uint8, (n_map,)))
         if copy:
             r = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in r.items()}

@@ -209,7 +209,8 @@ def test_compact_and_left_only_outputs_are_the_same_results(svo, rows, monkeypat
     seqs = [synth.Sequence(SHAPE, seed=s) for s in (51, 52)]
     rng = np.random.default_rng(9)
     results = {}
-    for flags in (0, svo.OUT_COMPACT, svo.OUT_COMPACT | svo.OUT_NO_RIGHT):
+    base_desc = []      # frame t's left descriptors of the untracked sequence (the pose-inputs mode does not return them)
+    for flags in (0, svo.OUT_COMPACT, svo.OUT_COMPACT | svo.OUT_NO_RIGHT, svo.OUT_COMPACT | svo.OUT_POSE_INPUTS):
         ctx.set_outputs(flags)
         ctx.track_reset(0); ctx.track_reset(1)
         out = []
@@ -223,7 +224,9 @@ def test_compact_and_left_only_outputs_are_the_same_results(svo, rows, monkeypat
                 fr[1].update(prev_desc=big, map_desc=prev[::2].copy())
             ctx.batch_submit(0, fr); ctx.batch_wait(0)
             out.append([ctx.batch_result(0, 0), ctx.batch_result(0, 1)])
-            prev = out[-1][1]["desc_left"].copy()
+            prev = base_desc[t] if flags else out[-1][1]["desc_left"].copy()
+            if not flags:
+                base_desc.append(prev)
         results[flags] = out
     ctx.set_outputs(0)
     base = results[0]
@@ -232,8 +235,12 @@ def test_compact_and_left_only_outputs_are_the_same_results(svo, rows, monkeypat
             for i in range(2):
                 a, b = base[t][i], out[t][i]
                 for k, v in a.items():
-                    if k in ("kp_right", "desc_right") and flags & svo.OUT_NO_RIGHT:
+                    if k in ("kp_right", "desc_right") and flags & (svo.OUT_NO_RIGHT | svo.OUT_POSE_INPUTS):
                         assert b[k] is None
+                        continue
+                    if flags & svo.OUT_POSE_INPUTS and k not in ("status", "n_left", "n_right", "n_stereo", "kp_left", "depth", "claim_row",
+                                                                  "n_prev", "n_map", "mp_create", "mp_xyz"):
+                        assert b.get(k) is None, k          # stays on the device
                         continue
                     if isinstance(v, np.ndarray):
                         assert v.dtype == b[k].dtype and v.shape == b[k].shape and v.tobytes() == b[k].tobytes(), (flags, t, i, k)
