@@ -449,6 +449,19 @@ def run_gpu(args, rank, world, local_rank):
         lat.append((time.perf_counter() - t0) * 1e3)
     p50 = float(np.median(lat))
 
+    p50_trk = None
+    if trk is not None:   # the same through the tracker state: consecutive frames of ONE sequence, one frame per call
+        ctx.set_outputs(svo.OUT_COMPACT | svo.OUT_NO_RIGHT)
+        lt = []
+        for t in range(min(34, P)):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ctx.batch_submit(0, [dict(left=hl[t], right=hr[t], bf=BF, baseline=BASELINE, track_seq=0, frame_id=1000 + t, K=K4)])
+            ctx.batch_wait(0)
+            lt.append((time.perf_counter() - t0) * 1e3)
+        ctx.set_outputs(0)
+        p50_trk = float(np.median(lt[4:]))
+
     # pose stage (not part of the headline metric): PnP RANSAC + pose-only LM for a batch of
     # B frames with ~1000 matched map points each, through the synchronous C-ABI calls (host buffers, copies included)
     pose = None
@@ -597,7 +610,7 @@ def run_gpu(args, rank, world, local_rank):
                                  "whole step (DESIGN.md section 4)"},
             "profiled_pass": {"steps": psteps, "ms_per_step": ms_prof / psteps,
                               "note": "stage_ms_per_step, kernel_ms_per_launch and roofline.launch_ms come from this pass"},
-            "stage_ms_per_step": kernels, "kernel_ms_per_launch": {k: stage.get(v[0], 0.0) for k, v in single.items()}, "p50_ms_per_frame_single": p50, "wall_ms_per_step": wall_dev / args.steps,
+            "stage_ms_per_step": kernels, "kernel_ms_per_launch": {k: stage.get(v[0], 0.0) for k, v in single.items()}, "p50_ms_per_frame_single": p50, "p50_ms_per_frame_single_tracked": p50_trk, "wall_ms_per_step": wall_dev / args.steps,
         }
         out["pose_stage"] = pose
         if world == 1 and not args.no_cpu_baseline:

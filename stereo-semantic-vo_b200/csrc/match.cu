@@ -1355,20 +1355,20 @@ void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStrea
         TcExpandArgs ex;
         memset(&tc, 0, sizeof(tc)); memset(&ex, 0, sizeof(ex));
         ex.set = a.rows; ex.img = a.img_rows; ex.img_frame_stride = a.img_rows_stride;
-        launch_tc_expand(ex, nframes, st, launches);
         tc.A = a.rows; tc.B = a.cols; tc.g = a; tc.T = T; tc.row_need = a.row_need; tc.prof = a.tc_prof;
         tc.a_img = a.img_rows; tc.a_img_frame_stride = a.img_rows_stride;
+        TcExpandArgs ex1 = ex;
         if (a.free_col) {   // the columns pass 1 left free, gathered in ascending order
-            ex.set = a.cols; ex.index = a.free_col; ex.index_cnt = a.free_cnt; ex.index_stride = a.cols.stride_rows;
-            ex.img = a.img_free; ex.img_frame_stride = a.img_free_stride;
-            launch_tc_expand(ex, nframes, st, launches);
+            ex1.set = a.cols; ex1.index = a.free_col; ex1.index_cnt = a.free_cnt; ex1.index_stride = a.cols.stride_rows;
+            ex1.img = a.img_free; ex1.img_frame_stride = a.img_free_stride;
+            launch_tc_expand2(ex, ex1, nframes, st, launches);
             tc.b_index = a.free_col; tc.b_index_cnt = a.free_cnt; tc.b_index_stride = a.cols.stride_rows;
             tc.b_img = a.img_free; tc.b_img_frame_stride = a.img_free_stride;
         } else {
             if (!a.img_cols_ready) {
-                ex.set = a.cols; ex.img = a.img_cols; ex.img_frame_stride = a.img_cols_stride;
-                launch_tc_expand(ex, nframes, st, launches);
-            }
+                ex1.set = a.cols; ex1.img = a.img_cols; ex1.img_frame_stride = a.img_cols_stride;
+                launch_tc_expand2(ex, ex1, nframes, st, launches);
+            } else launch_tc_expand(ex, nframes, st, launches);
             tc.b_img = a.img_cols; tc.b_img_frame_stride = a.img_cols_stride;
         }
         launch_tc_hamming(tc, TC_SHORT, nframes, st, launches);
@@ -1426,9 +1426,9 @@ void launch_pass1_fused(const PairArgs &p0, const BfArgs &b, int nframes, cudaSt
         TcExpandArgs ex;
         memset(&ex, 0, sizeof(ex));
         ex.set = a.cols; ex.img = a.img_cols; ex.img_frame_stride = a.img_cols_stride;
-        launch_tc_expand(ex, nframes, st, launches);
-        ex.set = a.rows; ex.img = a.img_rows; ex.img_frame_stride = a.img_rows_stride;
-        launch_tc_expand(ex, nframes, st, launches);
+        TcExpandArgs ex1 = ex;
+        ex1.set = a.rows; ex1.img = a.img_rows; ex1.img_frame_stride = a.img_rows_stride;
+        launch_tc_expand2(ex, ex1, nframes, st, launches);
         tc.A = a.cols; tc.B = a.rows; tc.g = a; tc.T = p.T; tc.bf_key = p.bf_key; tc.prof = a.tc_prof;
         tc.a_img = a.img_cols; tc.a_img_frame_stride = a.img_cols_stride;
         tc.b_img = a.img_rows; tc.b_img_frame_stride = a.img_rows_stride;

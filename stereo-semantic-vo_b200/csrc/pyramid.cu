@@ -231,7 +231,7 @@ void launch_unpack(const Bufs &b, const Geom &g, int slot0, int nimg, const Fram
 
 void launch_pyramid(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches)
 {
-    if (g.pyr_nbands && b.pyr_bands) {
+    if (g.pyr_nbands && b.pyr_bands && nimg <= g.pyr_fused_max) {
         k_pyramid<<<dim3(g.pyr_nbands, nimg), PYR_THREADS, g.pyr_smem, st>>>(b, g, slot0);
         ++*launches;
         return;

@@ -724,14 +724,17 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
     TRY(dalloc(ctx, &rtab, ctx->rtab_host.size()));
     CU(cudaMemcpy(rtab, ctx->rtab_host.data(), ctx->rtab_host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     b.rtab = rtab;
-    {   // One-launch pyramid (pyramid.cu:k_pyramid), OPT-IN with SVO_B200_PYRAMID_FUSED=1.  Measured on B200 (profiles/
-        // r2_pyramid_fused_experiment.md): 128 us per 64 images against 126 us for the seven per-level launches when run
-        // alone, a 2 % shorter single-frame p50, but 5 % LOWER batch throughput inside the three-lane pipeline, where its
-        // 100 KB CTAs keep the other lanes' kernels off the SMs.  The default stays the per-level kernels.
+    {   // One-launch pyramid (pyramid.cu:k_pyramid).  Measured on B200 (profiles/r2_pyramid_fused_experiment.md): 128 us per
+        // 64 images against 126 us for the seven per-level launches when run alone and a shorter single-frame critical path
+        // (24 us instead of 50 us + six dependent launches), but 5 % LOWER batch throughput inside the three-lane pipeline,
+        // where its 100 KB CTAs keep the other lanes' kernels off the SMs.  So the launch size decides: up to 4 stereo frames
+        // (8 images) the fused kernel, above that the per-level kernels.  SVO_B200_PYRAMID_FUSED=1 / =0 forces one form.
         std::vector<PyrBand> bands;
         b.pyr_bands = nullptr;
         ctx->g.pyr_nbands = 0;
-        if (getenv("SVO_B200_PYRAMID_FUSED")) {
+        const char *e = getenv("SVO_B200_PYRAMID_FUSED");
+        ctx->g.pyr_fused_max = e ? (e[0] == '0' ? 0 : INT_MAX) : 8;
+        if (ctx->g.pyr_fused_max > 0) {
             TRY(build_pyramid_bands(ctx, bands, 100 * 1024));
             if (ctx->g.pyr_nbands == 0) TRY(build_pyramid_bands(ctx, bands, 200 * 1024));
         }

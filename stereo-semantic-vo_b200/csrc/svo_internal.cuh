@@ -60,7 +60,8 @@ struct Geom {
     int kp_cap;          // final keypoints per image
     int blur_tiles;      // blur tiles per image
     int fast_bands;      // FAST bands per image (sum of nbands)
-    int pyr_nbands;      // bands of the fused pyramid kernel (0: per-level kernels)
+    int pyr_nbands;      // bands of the fused pyramid kernel (0: the geometry does not fit it)
+    int pyr_fused_max;   // launches of at most this many images use the fused kernel, larger ones the per-level kernels
     int pyr_soff[SVO_MAX_LEVELS];   // shared-memory byte offset of each level's rows in that kernel
     int pyr_smem;        // its dynamic shared memory
     LevelGeom lv[SVO_MAX_LEVELS];
@@ -296,6 +297,7 @@ struct TcArgs {
     long long *prof;             // optional clock64 timeline of CTA (0, 0): [mode][4 roles][64] (svo_debug_tc_profile)
 };
 void launch_tc_expand(const TcExpandArgs &e, int nframes, cudaStream_t st, long long *launches);
+void launch_tc_expand2(const TcExpandArgs &e0, const TcExpandArgs &e1, int nframes, cudaStream_t st, long long *launches);
 void launch_tc_hamming(const TcArgs &p, int mode, int nframes, cudaStream_t st, long long *launches);
 int setup_tc_attributes();
 

@@ -203,8 +203,9 @@ __device__ __forceinline__ uint32_t *tc_short_slot(const GreedyArgs &a, size_t r
 // 8-15 K atom 1.  Rows between the set's count and the end of its last tile are written as zeros (dot product 0; the
 // epilogues mask them); `index` gathers rows (the free columns of pass 2, ascending).
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_tc_expand(TcExpandArgs e)
+__global__ void __launch_bounds__(256) k_tc_expand(TcExpandArgs e0, TcExpandArgs e1)
 {
+    const TcExpandArgs &e = blockIdx.z ? e1 : e0;      // up to two descriptor sets per launch
     const int f = blockIdx.y;
     int n = tc_count(e.set, f);
     if (e.index) n = min(n, e.index_cnt[f]);
@@ -541,7 +542,19 @@ void launch_tc_expand(const TcExpandArgs &e, int nframes, cudaStream_t st, long 
     if (maxn <= 0 || nframes <= 0) return;
     int gx = (maxn * 16 + 255) / 256;
     if (gx > 64) gx = 64;
-    k_tc_expand<<<dim3(gx, nframes), 256, 0, st>>>(e);
+    k_tc_expand<<<dim3(gx, nframes, 1), 256, 0, st>>>(e, e);
+    ++*launches;
+}
+
+// two sets in one launch (the operand images of both sides of a matcher)
+void launch_tc_expand2(const TcExpandArgs &e0, const TcExpandArgs &e1, int nframes, cudaStream_t st, long long *launches)
+{
+    const int m0 = e0.set.count ? e0.set.stride_rows : e0.set.fixed_count, m1 = e1.set.count ? e1.set.stride_rows : e1.set.fixed_count;
+    if (m0 <= 0 || nframes <= 0) { launch_tc_expand(e1, nframes, st, launches); return; }
+    if (m1 <= 0) { launch_tc_expand(e0, nframes, st, launches); return; }
+    int gx = ((m0 > m1 ? m0 : m1) * 16 + 255) / 256;
+    if (gx > 64) gx = 64;
+    k_tc_expand<<<dim3(gx, nframes, 2), 256, 0, st>>>(e0, e1);
     ++*launches;
 }
 

@@ -431,12 +431,14 @@ def test_skip_match_score_changes_nothing_else(svo):
         assert (a.tobytes() == bb.tobytes()) if isinstance(a, np.ndarray) else a == bb, k
 
 
-def test_fused_pyramid_is_byte_exact(svo):
+@pytest.mark.parametrize("mode", ["1", "0"])
+def test_both_pyramid_forms_are_byte_exact(svo, mode):
     """SVO_B200_PYRAMID_FUSED=1: the one-launch pyramid (TMA bulk copy of the band's level-0 rows, levels 1..7 chained in
-    shared memory) gives the same bytes as the oracle on every level, for a KITTI-shape and an odd-sized image, and the
-    whole extractor on top of it is unchanged."""
+    shared memory; the default for launches of up to 8 images) and =0: the seven per-level launches (the default above
+    that) give the same bytes as the oracle on every level, for a KITTI-shape, an odd-sized and a high-resolution image,
+    and the whole extractor on top of them is unchanged."""
     import os
-    os.environ["SVO_B200_PYRAMID_FUSED"] = "1"
+    os.environ["SVO_B200_PYRAMID_FUSED"] = mode
     try:
         for shape, nf in (((376, 1241), 2000), ((203, 317), 300), ((720, 2560), 4000)):
             img = synth.texture(shape, 7 + nf)
