@@ -166,3 +166,55 @@ def test_own_order_is_survivors_then_new_points():
     o2 = trk.step(xy, d1, np.full(40, 4, np.float32), 2, K4=K4)                    # window 2: frame-0 points age out of the map
     assert all(c >= 1 for c, _ in trk.names())
     assert (o2["mp_create"][re] == 0).all(), "a point that left the map is still tracked frame to frame (pass 1)"
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_tracker_state_invariants_on_random_frames(seed):
+    """Random frames with controlled re-observations, boxes and a small capacity: after every frame the state is
+    consistent — links and map rows point at each other, a keypoint's frozen descriptor is the descriptor its point had
+    at creation, point names are unique, nothing older than the window is in the map, the capacity holds."""
+    rng = np.random.default_rng(seed)
+    cap, window = 260, 3
+    trk = T.Tracker(window=window, map_cap=cap)
+    born = {}                                   # (create_id, idx) -> descriptor at creation
+    prev = None
+    F = np.array([[0, 0, 0], [0, 0, -1.0], [0, 1.0, 0]])       # epipolar lines are the rows: distance = |dy|
+    for t in range(9):
+        n = int(rng.integers(120, 180))
+        desc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        if prev is not None:                    # re-observe about half of the last frame with 0-3 flipped bits
+            k = min(len(prev), n) // 2
+            src = rng.permutation(len(prev))[:k]
+            flips = np.packbits(rng.random((k, 256)) < 0.006, axis=1, bitorder="little")
+            desc[rng.permutation(n)[:k]] = prev[src] ^ flips
+        xy = np.stack([rng.uniform(0, 400, n), rng.uniform(0, 240, n)], 1).astype(np.float32)
+        depth = np.where(rng.random(n) < 0.8, rng.uniform(1, 50, n), -1).astype(np.float32)
+        boxes = [[100, 220, 50, 150]] if t % 2 else None
+        o = trk.step(xy, desc, depth, t, boxes=boxes, F=F if t % 2 else None, K4=K4)
+        for j in np.nonzero(o["mp_create"] == t)[0]:
+            born[(t, int(j))] = desc[j].copy()
+        # names are unique and every one was born with the descriptor the state holds
+        names = trk.names()
+        assert len(set(names)) == len(names) <= cap
+        for (c, i), d in zip(names, trk.map_desc):
+            assert c > t - window and (born[(c, i)] == d).all()
+        # links: map row r <-> keypoint map_link[r]
+        for r, j in enumerate(trk.map_link):
+            if j >= 0:
+                assert trk.prev_map_row[j] == r and trk.prev_live[j] == 1
+        for j, r in enumerate(trk.prev_map_row):
+            if r >= 0:
+                assert trk.map_link[r] == j
+                assert (trk.prev_desc[j] == trk.map_desc[r]).all() and (trk.prev_create[j], trk.prev_idx[j]) == names[r]
+        # every live keypoint carries the frozen descriptor of its point; the frame's own descriptors are kept beside it
+        lv = trk.prev_live == 1
+        for j in np.nonzero(lv)[0]:
+            assert (trk.prev_desc[j] == born[(int(trk.prev_create[j]), int(trk.prev_idx[j]))]).all()
+        assert (trk.last_desc == desc).all() and (trk.prev_create[~lv] == -1).all()
+        # no new point inside a box grown by 5 px
+        if boxes:
+            b = boxes[0]
+            inside = (xy[:, 0] > b[0] - 5) & (xy[:, 0] < b[1] + 5) & (xy[:, 1] > b[2] - 5) & (xy[:, 1] < b[3] + 5)
+            assert not (o["mp_create"][inside] == t).any()
+        prev = desc
+    assert len(born) > 400

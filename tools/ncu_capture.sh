@@ -18,5 +18,5 @@ print(ids[4] if len(ids) > 4 else ids[-1])
 P
 )
 echo "full capture from launch $SKIP" >> gpurun_out/${TAG}_ncu1.log
-ncu --set full --clock-control none --import-source on --launch-skip $SKIP --launch-count 31 -f -o gpurun_out/${TAG}_full $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on --launch-skip $SKIP --launch-count 29 -f -o gpurun_out/${TAG}_full $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
 ls -la gpurun_out/${TAG}_full.ncu-rep
