@@ -65,7 +65,7 @@ def test_binding_structs_match_the_header_layout(tmp_path):
     import subprocess
     import svo
     pairs = {"svo_config": svo.Config, "svo_veto": svo.Veto, "svo_frame_in": svo.FrameIn, "svo_frame_out": svo.FrameOut,
-             "svo_pose_problem": svo.PoseProblem, "svo_pnp_result": svo.PnpResult}
+             "svo_pose_problem": svo.PoseProblem, "svo_pnp_result": svo.PnpResult, "svo_track_view": svo.TrackView}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "svo_b200.h"', 'int main(void) {']
     for cname, cls in pairs.items():
         lines.append('printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))

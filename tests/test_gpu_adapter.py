@@ -251,3 +251,60 @@ def test_adapter_refuses_boxes_without_F(tmp_path):
     fp = str(tmp_path / "F.txt"); open(fp, "w").write("")
     r = subprocess.run([exe, str(W), str(H), "500"] + paths + [bx, fp, str(tmp_path / "out.txt")], capture_output=True, text=True)
     assert r.returncode == 1 and "fundamental" in r.stderr
+
+
+def test_track_loop_in_cpp_over_the_device_resident_state(tmp_path):
+    """adapter/track_loop_test.cc — the host loop of INTEGRATION.md section 3a in plain C++ over the C ABI: six frames of
+    one sequence through svo_frame_in.track_seq with boxes and F on some frames.  Its dump (claims, the point every
+    keypoint owns, bad rows) must equal oracle/track.py stepped with the keypoints and depths the run itself reports
+    (extraction and stereo have their own parity tests; tests/test_oracle_track.py pins the oracle to the reference)."""
+    from oracle import track as T
+    import svo
+    exe = os.path.join(ADAPTER, "track_loop_test")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", ADAPTER, "-s"])
+    H, W, NF, NT = 240, 400, 500, 6
+    seq = synth.Sequence((H, W), seed=61)
+    frames = [seq.frame(t) for t in range(NT)]
+    np.concatenate([np.stack(f) for f in frames]).tofile(str(tmp_path / "frames.raw"))
+    boxes = {t: [[90, 220, 30, 100], [250, 350, 60, 200]] for t in (1, 3, 4)}
+    with open(tmp_path / "boxes.txt", "w") as f:
+        for t, bl in boxes.items():
+            for b in bl:
+                f.write("%d %d %d %d %d\n" % (t, *b))
+    out = str(tmp_path / "out.txt")
+    subprocess.check_call([exe, str(W), str(H), str(NF), str(NT), str(tmp_path / "frames.raw"), str(tmp_path / "boxes.txt"), out])
+    kps = {t: [] for t in range(NT)}; bad = {t: [] for t in range(NT)}; head = {}
+    for line in open(out):
+        p = line.split()
+        if p[0] == "frame":
+            head[int(p[1])] = [int(v) for v in p[2:]]
+        elif p[0] == "kp":
+            kps[int(p[1])].append([np.float32(v) for v in p[3:6]] + [int(p[6]), int(p[7])] + [np.float32(v) for v in p[8:11]])
+        elif p[0] == "bad":
+            bad[int(p[1])].append(int(p[2]))
+    # the descriptors are not in the dump: take them from the same extractor through the Python binding
+    ctx = svo.Context(W, H, nfeatures=NF, max_batch=1, lanes=1, max_rows=1000)
+    K4 = (707.0912, 707.0912, 601.8873, 183.1104)
+    F = np.array([[1.1e-9, 2.3e-7, -3.1e-4], [-2.2e-7, 0.9e-9, 0.8312], [2.9e-4, -0.8297, 1.0]], np.float64)
+    trk = T.Tracker(window=4, map_cap=3000)
+    total_claims = total_bad = 0
+    for t in range(NT):
+        kp, desc = ctx.extract(frames[t][0])
+        rows = kps[t]
+        n_left, n_prev, n_map, _ = head[t]
+        assert n_left == len(kp) == len(rows)
+        xy = np.array([[r[0], r[1]] for r in rows], np.float32); depth = np.array([r[2] for r in rows], np.float32)
+        assert (xy[:, 0] == kp["x"]).all() and (xy[:, 1] == kp["y"]).all()
+        o = trk.step(xy, desc, depth, t, boxes=boxes.get(t), F=F if t in boxes else None, K4=K4)
+        assert (n_prev, n_map) == (o["n_prev"], o["n_map"]), t
+        assert [r[3] for r in rows] == o["claim_row"].tolist(), t
+        assert [r[4] for r in rows] == o["mp_create"].tolist(), t
+        got_xyz = np.array([r[5:8] for r in rows], np.float32)
+        assert (got_xyz.view(np.uint32) == o["mp_xyz"].view(np.uint32)).all(), t
+        if o["n_prev"]:
+            assert bad[t] == np.nonzero(o["p1_row_bad"])[0].tolist(), t
+            total_bad += len(bad[t])
+        total_claims += int((o["claim_row"] >= 0).sum())
+    ctx.close()
+    assert total_claims > 300
