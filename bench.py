@@ -439,28 +439,36 @@ def run_gpu(args, rank, world, local_rank):
     sampler.stop_flag = True
     sampler.join(timeout=1)
 
-    # single-frame latency through the synchronous drop-in calls (p50 of 30 frames)
-    lat = []
-    for t in range(min(30, P)):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        ctx.batch_submit(0, [frame_host(t)])
-        ctx.batch_wait(0)
-        lat.append((time.perf_counter() - t0) * 1e3)
-    p50 = float(np.median(lat))
-
-    p50_trk = None
-    if trk is not None:   # the same through the tracker state: consecutive frames of ONE sequence, one frame per call
-        ctx.set_outputs(svo.OUT_COMPACT | svo.OUT_NO_RIGHT)
+    # single-frame latency (p50 of 30 frames): one frame per call, submit -> wait, host buffers in and out.  Measured on
+    # the batch context above and on a LATENCY context (max_batch = 1, one lane: what a deployment that serves one
+    # sequence per GPU creates; svo_create then picks the low-latency kernel shapes, e.g. 8-row FAST bands)
+    def p50_single(c, tracked_mode):
         lt = []
+        if tracked_mode:
+            c.set_outputs(svo.OUT_COMPACT | svo.OUT_NO_RIGHT)
         for t in range(min(34, P)):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            ctx.batch_submit(0, [dict(left=hl[t], right=hr[t], bf=BF, baseline=BASELINE, track_seq=0, frame_id=1000 + t, K=K4)])
-            ctx.batch_wait(0)
+            if tracked_mode:   # consecutive frames of ONE sequence through the tracker state
+                c.batch_submit(0, [dict(left=hl[t], right=hr[t], bf=BF, baseline=BASELINE, track_seq=0, frame_id=1000 + t, K=K4)])
+            else:
+                c.batch_submit(0, [frame_host(t)])
+            c.batch_wait(0)
             lt.append((time.perf_counter() - t0) * 1e3)
-        ctx.set_outputs(0)
-        p50_trk = float(np.median(lt[4:]))
+        c.set_outputs(0)
+        return float(np.median(lt[4:]))
+
+    K4 = (float(CAL["fx"]), float(CAL["fy"]), float(CAL["cx"]), float(CAL["cy"]))
+    p50_batch_ctx = p50_single(ctx, False)
+    lctx = svo.Context(W_IMG, H_IMG, nfeatures=NFEAT, nlevels=NLEVELS, max_batch=1, lanes=1, max_rows=max(MAP_ROWS, kp_cap(NFEAT)),
+                       device=dev, distribution=svo.DIST_OCTREE if args.distribution == "octree" else svo.DIST_RETAIN_BEST)
+    p50 = p50_single(lctx, False)
+    p50_trk = None
+    if trk is not None:
+        lctx.track_create(1, MAP_ROWS, 4)
+        lctx.track_reset(0, ballast[:n_ballast] if n_ballast else None)
+        p50_trk = p50_single(lctx, True)
+    lctx.close()
 
     # pose stage (not part of the headline metric): PnP RANSAC + pose-only LM for a batch of
     # B frames with ~1000 matched map points each, through the synchronous C-ABI calls (host buffers, copies included)
@@ -610,7 +618,8 @@ def run_gpu(args, rank, world, local_rank):
                                  "whole step (DESIGN.md section 4)"},
             "profiled_pass": {"steps": psteps, "ms_per_step": ms_prof / psteps,
                               "note": "stage_ms_per_step, kernel_ms_per_launch and roofline.launch_ms come from this pass"},
-            "stage_ms_per_step": kernels, "kernel_ms_per_launch": {k: stage.get(v[0], 0.0) for k, v in single.items()}, "p50_ms_per_frame_single": p50, "p50_ms_per_frame_single_tracked": p50_trk, "wall_ms_per_step": wall_dev / args.steps,
+            "stage_ms_per_step": kernels, "kernel_ms_per_launch": {k: stage.get(v[0], 0.0) for k, v in single.items()}, "p50_ms_per_frame_single": p50, "p50_ms_per_frame_single_tracked": p50_trk,
+            "p50_ms_per_frame_single_on_the_batch_context": p50_batch_ctx, "wall_ms_per_step": wall_dev / args.steps,
         }
         out["pose_stage"] = pose
         if world == 1 and not args.no_cpu_baseline:

@@ -2,18 +2,18 @@
 // level, restricted to cv::ORB's 31-px keypoint box, emitted in raster order.
 // SURVEY.md A.3; runs inside cv::ORB::detectAndCompute (src/frame.cc:75-79).
 //
-// One CTA per (image, level, band of SVO_FAST_BAND output rows).  The band's pixel rows
+// One CTA per (image, level, band of Geom.fast_band output rows).  The band's pixel rows
 // (+4 rows of halo on each side) are staged into shared memory with 128-bit loads.  A cheap
 // necessary test runs on every pixel and compacts the survivors into a shared candidate list;
 // the exact score then runs on densely packed candidates (no intra-warp divergence), corners
 // are suppressed against their 8 neighbours into a bitmap, and the bitmap is emitted in raster
 // order so the downstream retainBest replay sees exactly the order cv::FAST produces.
-// Algorithmic bytes: each level pixel read once (+ (8/SVO_FAST_BAND) halo re-read),
+// Algorithmic bytes: each level pixel read once (+ (8/fast_band) halo re-read),
 // 4 B written per corner.
 #include "svo_internal.cuh"
 #include <cuda/barrier>
 
-#define FAST_THREADS 256
+#define FAST_THREADS 512
 
 // ---- stage A: necessary condition on 4 horizontally adjacent pixels at once ----
 // Any 9-arc of the 16-ring holds at least one pixel of every antipodal pair, so a "centre brighter"
@@ -105,10 +105,13 @@ __device__ __forceinline__ int fast_score(const uint8_t *p, int sp, int t)
 extern __shared__ __align__(128) uint8_t fast_smem[];
 
 // shared-memory carve-up for a level of pitch sp (bytes)
-__host__ __device__ inline int fast_off_sc(int sp) { return (SVO_FAST_BAND + 8) * sp; }
-__host__ __device__ inline int fast_off_cand(int sp) { return fast_off_sc(sp) + (SVO_FAST_BAND + 2) * sp; }
-__host__ __device__ inline int fast_off_mask(int sp) { return fast_off_cand(sp) + 2 * ((SVO_FAST_BAND + 2) * (sp + 128) + 8 * 128); }
-__host__ __device__ inline int fast_mask_words(int sp) { return SVO_FAST_BAND * ((sp + 31) / 32); }
+__host__ __device__ inline int fast_off_sc(int sp, int band) { return (band + 8) * sp; }
+__host__ __device__ inline int fast_off_cand(int sp, int band) { return fast_off_sc(sp, band) + (band + 2) * sp; }
+__host__ __device__ inline int fast_off_mask(int sp, int band)
+{
+    return fast_off_cand(sp, band) + 2 * ((band + 2) * (sp + 128) + (FAST_THREADS / 32) * 128);   // every warp's share is rounded up to a chunk
+}
+__host__ __device__ inline int fast_mask_words(int sp, int band) { return band * ((sp + 31) / 32); }
 
 __global__ void __launch_bounds__(FAST_THREADS) k_fast(Bufs b, Geom g, int slot0)
 {
@@ -117,16 +120,17 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(Bufs b, Geom g, int slot0
     const LevelGeom &L = g.lv[l];
     const int slot = slot0 + blockIdx.y;
     const int sp = L.pitch;
-    const int yb = L.y0 + band * SVO_FAST_BAND;
-    const int ye = min(yb + SVO_FAST_BAND, L.y1);
+    const int FB = g.fast_band;
+    const int yb = L.y0 + band * FB;
+    const int ye = min(yb + FB, L.y1);
     const int nrow = ye - yb;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = FAST_THREADS / 32;
     const int t = g.fast_threshold;
     uint8_t *pix = fast_smem;                                                    // rows yb-4 .. ye+3
-    uint8_t *sc = fast_smem + fast_off_sc(sp);                                   // rows yb-1 .. ye
-    uint16_t *cand = reinterpret_cast<uint16_t *>(fast_smem + fast_off_cand(sp)); // candidate positions in sc
-    uint32_t *mask = reinterpret_cast<uint32_t *>(fast_smem + fast_off_mask(sp)); // kept-corner bitmap, row major
+    uint8_t *sc = fast_smem + fast_off_sc(sp, FB);                                   // rows yb-1 .. ye
+    uint16_t *cand = reinterpret_cast<uint16_t *>(fast_smem + fast_off_cand(sp, FB)); // candidate positions in sc
+    uint32_t *mask = reinterpret_cast<uint32_t *>(fast_smem + fast_off_mask(sp, FB)); // kept-corner bitmap, row major
     const int wv = L.x1 - L.x0;
     const int wpr = (wv + 31) >> 5;   // bitmap words per row
     __shared__ int wsum[FAST_THREADS / 32];
@@ -275,7 +279,7 @@ int fast_smem_bytes(const Geom &g)
 {
     int mx = 0;
     for (int l = 0; l < g.nlevels; ++l) mx = g.lv[l].pitch > mx ? g.lv[l].pitch : mx;
-    return fast_off_mask(mx) + 4 * fast_mask_words(mx) + 16;
+    return fast_off_mask(mx, g.fast_band) + 4 * fast_mask_words(mx, g.fast_band) + 16;
 }
 
 void launch_fast(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches)

@@ -216,6 +216,16 @@ int build_geometry(svo_ctx *ctx)
     Geom &g = ctx->g;
     memset(&g, 0, sizeof(g));
     g.nlevels = c.nlevels; g.W = c.width; g.H = c.height; g.fast_threshold = c.fast_threshold;
+    {   // FAST band height (fast.cu).  16 rows halve the halo work of 8-row bands and keep more warps per SM (k_fast: 340 ->
+        // 312 us per 64 images), but a single frame is spread over half as many CTAs (single-frame p50 +9 us): batch contexts
+        // get 16, latency contexts (max_batch < 8) 8.  Candidate positions are 16-bit offsets into the band's (band + 2)
+        // staged rows, which limits 16-row bands to a level-0 pitch of 3640 bytes.  SVO_B200_FAST_BAND=8|16 overrides.
+        const int pitch0 = align_up(c.width, 16);
+        g.fast_band = (c.max_batch >= 8 && 18 * pitch0 <= 65535) ? 16 : 8;
+        const char *e = getenv("SVO_B200_FAST_BAND");
+        if (e && atoi(e) == 8) g.fast_band = 8;
+        if (e && atoi(e) == 16 && 18 * pitch0 <= 65535) g.fast_band = 16;
+    }
     int lw[SVO_MAX_LEVELS], lh[SVO_MAX_LEVELS], quota[SVO_MAX_LEVELS];
     float ls[SVO_MAX_LEVELS];
     orb_geometry(c.width, c.height, c.nlevels, c.scale_factor, c.nfeatures, lw, lh, ls, quota);
@@ -229,7 +239,7 @@ int build_geometry(svo_ctx *ctx)
         L.scale = ls[l]; L.inv_scale = 1.f / ls[l]; L.quota = quota[l];
         L.x0 = SVO_EDGE; L.x1 = L.w - SVO_EDGE; L.y0 = SVO_EDGE; L.y1 = L.h - SVO_EDGE;
         if (L.x1 <= L.x0 || L.y1 <= L.y0) { L.x1 = L.x0; L.y1 = L.y0; L.nbands = 0; }
-        else L.nbands = (L.y1 - L.y0 + SVO_FAST_BAND - 1) / SVO_FAST_BAND;
+        else L.nbands = (L.y1 - L.y0 + g.fast_band - 1) / g.fast_band;
         if (L.nbands > 500) return fail(ctx, SVO_E_INVALID, "image too tall");
         {   // octree mode: nIni = round(width / height) roots of float width hX (ORB-SLAM2 DistributeOctTree)
             const int ow = L.x1 - L.x0, oh = L.y1 - L.y0;
@@ -237,7 +247,7 @@ int build_geometry(svo_ctx *ctx)
             ni = ni < 1 ? 1 : (ni > 16 ? 16 : ni);
             L.oct_nini = ni; L.oct_hx = (float)ow / (float)ni;
         }
-        L.band_cap = ((SVO_FAST_BAND + 1) / 2) * ((L.x1 - L.x0 + 1) / 2) + 1;
+        L.band_cap = ((g.fast_band + 1) / 2) * ((L.x1 - L.x0 + 1) / 2) + 1;
         L.band_off = band_off; band_off += L.nbands * L.band_cap;
         L.bandcnt_off = bandcnt_off; bandcnt_off += L.nbands;
         L.cand_cap = L.nbands * L.band_cap + 4;

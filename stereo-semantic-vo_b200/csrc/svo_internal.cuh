@@ -15,7 +15,6 @@
 #include "../../include/svo_b200.h"
 
 #define SVO_EDGE 31            // cv::ORB edgeThreshold
-#define SVO_FAST_BAND 8        // output rows per FAST band (one CTA each)
 #define SVO_SHORT_CAP 128      // short-list entries per greedy row before the full-scan path
 #define SVO_STRIDE_BGR (1 << 30)  // flag in a per-image stride word: the source is interleaved BGR
 #define SVO_WIN_CELLS 4096     // most cells of the keypoint grid used by the windowed pass 2
@@ -33,7 +32,7 @@ struct LevelGeom {
     float inv_scale;   // 1.f / scale
     int quota;         // nfeaturesPerLevel[l]
     int x0, x1, y0, y1;  // keypoints live in [x0,x1) x [y0,y1) = [31, w-31) x [31, h-31)
-    int nbands;        // ceil((y1-y0)/SVO_FAST_BAND), 0 when the level is too small
+    int nbands;        // ceil((y1-y0)/Geom.fast_band), 0 when the level is too small
     int band_cap;      // entries per band list
     int band_off;      // entry offset of this level's band lists inside a slot
     int bandcnt_off;   // offset of this level's band counters
@@ -52,6 +51,7 @@ struct LevelGeom {
 struct Geom {
     int nlevels, W, H;
     int fast_threshold;
+    int fast_band;       // output rows per FAST band (one CTA each): 16 for batch contexts, 8 for latency contexts and very wide images
     int pyr_bytes;       // per slot
     int band_total;      // entries per slot
     int bandcnt_total;   // counters per slot

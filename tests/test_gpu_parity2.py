@@ -454,3 +454,42 @@ def test_both_pyramid_forms_are_byte_exact(svo, mode):
                 c.close()
     finally:
         del os.environ["SVO_B200_PYRAMID_FUSED"]
+
+
+@pytest.mark.parametrize("band", ["8", "16"])
+def test_both_fast_band_heights_give_the_same_corners(svo, band):
+    """k_fast works on bands of 8 rows (latency contexts, very wide images) or 16 rows (batch contexts: max_batch >= 8);
+    SVO_B200_FAST_BAND forces one.  Either way the raster-ordered FAST list of every level, and the extractor on top
+    of it, equal the oracle's — for a KITTI-shape, an odd-sized and a high-resolution image (whose band rows are not
+    a multiple of either height) and through the batch path of a max_batch = 8 context."""
+    import os
+    os.environ["SVO_B200_FAST_BAND"] = band
+    try:
+        for shape, nf in (((376, 1241), 2000), ((203, 317), 300), ((720, 2560), 4000)):
+            img = synth.texture(shape, 11 + nf)
+            c = svo.Context(shape[1], shape[0], nfeatures=nf, max_batch=1, lanes=1, max_rows=1000)
+            try:
+                kp, desc = c.extract(img)
+                ref, rdesc, pyr = O.orb(img, nf, with_pyramid=True)
+                for l in range(8):
+                    xs, ys, sc = O.fast_nms(pyr.level(l), 20, 31)
+                    f = c.tap_list(0, svo.TAP_FAST, l)
+                    assert len(f) == len(xs) and (f[:, 0] == xs).all() and (f[:, 1] == ys).all() and (f[:, 2] == sc).all(), (shape, l)
+                O.pyramid_free(pyr)
+                assert len(kp) == len(ref) and (desc == rdesc).all()
+            finally:
+                c.close()
+    finally:
+        del os.environ["SVO_B200_FAST_BAND"]
+    # the default choice of a batch context (16 rows) through svo_batch_submit
+    c = svo.Context(400, 240, nfeatures=500, max_batch=8, lanes=1, max_rows=1000)
+    try:
+        seq = synth.Sequence((240, 400), seed=3)
+        frames = [seq.frame(t) for t in range(8)]
+        c.batch_submit(0, [dict(left=f[0], right=f[1], bf=379.8145, baseline=0.5372) for f in frames]); c.batch_wait(0)
+        for i, f in enumerate(frames):
+            r = c.batch_result(0, i)
+            kl, dl, _ = O.orb(f[0], 500)
+            assert r["n_left"] == len(kl) and (r["desc_left"] == dl).all() and (r["kp_left"]["x"] == kl["x"]).all()
+    finally:
+        c.close()
