@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_harris(Bufs b, Geom g, int 
 // horizontal sums and pushes them into a 7-row register window from which the vertical pass
 // is taken.  No shared memory, no barriers; stores are one aligned word per row.
 // ---------------------------------------------------------------------------------------
-#define BLUR_ROWS 32
+#define BLUR_ROWS SVO_BLUR_ROWS
 #define BLUR_THREADS 128
 
 __device__ __forceinline__ int reflect101(int i, int n)
@@ -119,7 +119,7 @@ __device__ __forceinline__ float2 add_prod(float2 acc, float2 prod)
 
 __global__ void __launch_bounds__(BLUR_THREADS) k_blur(Bufs b, Geom g, int slot0)
 {
-    // The tile's source rows (32 + 6 halo rows, reflect-101 at the image top/bottom folded into the row choice)
+    // The tile's source rows (BLUR_ROWS + 6 halo rows, reflect-101 at the image top/bottom folded into the row choice)
     // are staged in shared memory by TMA bulk copies, one per row, all completing on one mbarrier: the kernel
     // was bound by the latency of its global loads (ncu: long-scoreboard stalls at 28 % occupancy), shared
     // memory removes that from the per-row loop.

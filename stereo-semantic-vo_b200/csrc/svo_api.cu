@@ -255,12 +255,12 @@ int build_geometry(svo_ctx *ctx)
         L.cap2 = 4 * L.quota + 1024 < L.cand_cap ? 4 * L.quota + 1024 : L.cand_cap;
         L.off2 = off2; off2 += align_up(L.cap2, 4);
         L.tab_off = tab_off; if (l) tab_off += L.w + L.h;
-        {   // blur tiles: 32 rows x blur_tq quads, the quads of a row split evenly over the fewest tiles of <= 128 quads
+        {   // blur tiles: SVO_BLUR_ROWS rows x blur_tq quads, the quads of a row split evenly over the fewest tiles of <= 128 quads
             const int quads = (L.w + 3) / 4;
             L.blur_tiles_x = (quads + 127) / 128;
             L.blur_tq = align_up((quads + L.blur_tiles_x - 1) / L.blur_tiles_x, 4);
             L.blur_tile_off = tiles;                         // first blur CTA of the level
-            tiles += L.blur_tiles_x * ((L.h + 31) / 32);
+            tiles += L.blur_tiles_x * ((L.h + SVO_BLUR_ROWS - 1) / SVO_BLUR_ROWS);
         }
         g.fast_bands += L.nbands;
     }

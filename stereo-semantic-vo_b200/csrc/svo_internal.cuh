@@ -15,6 +15,7 @@
 #include "../../include/svo_b200.h"
 
 #define SVO_EDGE 31            // cv::ORB edgeThreshold
+#define SVO_BLUR_ROWS 64       // rows per blur tile (describe.cu:k_blur; 6 halo rows are staged on top)
 #define SVO_SHORT_CAP 128      // short-list entries per greedy row before the full-scan path
 #define SVO_STRIDE_BGR (1 << 30)  // flag in a per-image stride word: the source is interleaved BGR
 #define SVO_WIN_CELLS 4096     // most cells of the keypoint grid used by the windowed pass 2
