@@ -493,6 +493,29 @@ def run_gpu(args, rank, world, local_rank):
                 "note": "wall clock around svo_pnp_ransac (100 samples, 8 px, refit) and svo_pose_optimize (g2o LM, 10 iterations), "
                         "host buffers in and out; includes the Python binding's packing"}
 
+    # input staging beside the path: main.cpp:160-162 reads PNG files; svo_png_decode (host, zlib)
+    # turns them into the pinned buffers the calls above take.  Reported so that the host side can be read against the GPU
+    # rate: at these frame rates frames must arrive raw (or be decoded by many cores).
+    staging = None
+    if rank == 0:
+        try:
+            import cv2
+            files = [cv2.imencode(".png", np.ascontiguousarray(hl[t]))[1].tobytes() for t in range(min(8, P))]
+            dst = ctx.pinned_array((H_IMG, W_IMG))
+            for f in files[:2]:
+                svo.png_decode(f, out=dst)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                for f in files:
+                    svo.png_decode(f, out=dst)
+            ms_img = (time.perf_counter() - t0) * 1e3 / (3 * len(files))
+            staging = {"png_decode_ms_per_image_1_core": ms_img, "png_bytes_per_image": int(np.mean([len(f) for f in files])),
+                       "stereo_frames_per_s_per_core": 1e3 / (2 * ms_img),
+                       "note": "svo_png_decode (host, zlib) of %dx%d 8-bit gray frames encoded by cv2.imencode, into pinned memory; "
+                               "a stereo frame is two images" % (W_IMG, H_IMG)}
+        except Exception as ex:   # no cv2 on this host: nothing to encode the sample files with
+            staging = {"unavailable": str(ex)[:100]}
+
     ms_dev, ms_hc, ms_trk_m, ms_pose_m = grp.max_over_ranks([ms_dev, ms_hc, ms_trk if ms_trk is not None else 0.0,
                                                              ms_pose if ms_pose is not None else 0.0])
     frames_total = int(grp.sum_over_ranks([args.steps * B])[0])
@@ -622,6 +645,7 @@ def run_gpu(args, rank, world, local_rank):
             "p50_ms_per_frame_single_on_the_batch_context": p50_batch_ctx, "wall_ms_per_step": wall_dev / args.steps,
         }
         out["pose_stage"] = pose
+        out["input_staging"] = staging
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(seq, cores=1, budget_s=args.cpu_seconds)
     ctx.close()

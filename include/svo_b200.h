@@ -333,6 +333,19 @@ int svo_track_state(svo_ctx *ctx, int seq, svo_track_view *view);
 /* Rows of the per-keypoint arrays (the context's keypoint capacity per image). */
 int svo_track_kp_capacity(const svo_ctx *ctx);
 
+/* ---------------------------------------------------------------------------
+ * Input staging (host side).  main.cpp:160-162 reads every KITTI frame with
+ * cv::imread(path, CV_LOAD_IMAGE_UNCHANGED); these two calls decode the same PNG file image (bytes in memory) straight
+ * into a caller buffer — ideally pinned (svo_alloc_pinned), so that svo_batch_submit's H2D copy reads it in place —
+ * in cv::imread's memory order: 8-bit gray as is, 8-bit RGB / RGBA as interleaved BGR / BGRA (channels = 3 goes to
+ * svo_extract_bgr / svo_frame_in.channels = 3, which convert on the device), 16-bit gray (the depth / disparity
+ * PNGs) as native-endian uint16.  Host code over zlib: no context and no GPU needed; callers run one decode per core
+ * beside the GPU lanes.  Interlaced and palette images are rejected (SVO_E_INVALID).
+ * ------------------------------------------------------------------------- */
+int svo_png_info(const uint8_t *file, size_t n, int *w, int *h, int *channels, int *bit_depth);
+/* dst: h rows, dst_stride bytes apart (>= w * channels * bit_depth / 8), dst_cap bytes in all. */
+int svo_png_decode(const uint8_t *file, size_t n, uint8_t *dst, size_t dst_stride, size_t dst_cap);
+
 /* Pinned host / device memory helpers for callers that want zero staging. */
 void *svo_alloc_pinned(svo_ctx *ctx, size_t bytes);
 void svo_free_pinned(svo_ctx *ctx, void *p);

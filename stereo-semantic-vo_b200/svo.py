@@ -87,7 +87,8 @@ EXPORTS = ["svo_default_config", "svo_version", "svo_create", "svo_destroy", "sv
            "svo_alloc_device", "svo_free_device", "svo_copy_to_device", "svo_launch_count", "svo_batch_stage_ms",
            "svo_set_profiling", "svo_lane_stream", "svo_debug_tap", "svo_debug_retain_best",
            "svo_pnp_ransac", "svo_pose_optimize", "svo_debug_hamming_matrix", "svo_debug_tc_profile", "svo_project_map",
-           "svo_track_create", "svo_track_reset", "svo_track_state", "svo_track_kp_capacity", "svo_set_outputs"]
+           "svo_track_create", "svo_track_reset", "svo_track_state", "svo_track_kp_capacity", "svo_set_outputs",
+           "svo_png_info", "svo_png_decode"]
 
 _lib = None
 
@@ -132,6 +133,8 @@ def load():
     L.svo_batch_stage_ms.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     L.svo_set_profiling.argtypes = [C.c_void_p, C.c_int]
     L.svo_set_outputs.argtypes = [C.c_void_p, C.c_int]
+    L.svo_png_info.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.svo_png_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t]
     L.svo_lane_stream.argtypes = [C.c_void_p, C.c_int]
     L.svo_lane_stream.restype = C.c_void_p
     L.svo_debug_tap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
@@ -153,6 +156,26 @@ def load():
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def png_decode(data, out=None):
+    """Input staging (host side, no GPU needed): PNG file bytes -> array in cv2.imread(IMREAD_UNCHANGED)'s layout
+    ((h, w) u8 / u16 or (h, w, 3|4) u8 in BGR(A) order).  `out`: optional destination (e.g. a view of pinned memory)."""
+    L = load()
+    buf = np.frombuffer(data, np.uint8)
+    w, h, ch, bd = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    rc = L.svo_png_info(_p(buf), buf.size, C.byref(w), C.byref(h), C.byref(ch), C.byref(bd))
+    if rc < 0:
+        raise SvoError(rc, "svo_png_info: not a PNG this decoder reads (8-bit gray/RGB/RGBA or 16-bit gray, non-interlaced)")
+    shape = (h.value, w.value) if ch.value == 1 else (h.value, w.value, ch.value)
+    dt = np.uint16 if bd.value == 16 else np.uint8
+    if out is None:
+        out = np.empty(shape, dt)
+    assert out.shape == shape and out.dtype == dt and out.strides[-1] == out.itemsize
+    rc = L.svo_png_decode(_p(buf), buf.size, _p(out), out.strides[0], out.strides[0] * h.value)
+    if rc < 0:
+        raise SvoError(rc, "svo_png_decode failed")
+    return out
 
 
 def _view(ptr, dtype, shape):
