@@ -493,3 +493,20 @@ def test_both_fast_band_heights_give_the_same_corners(svo, band):
             assert r["n_left"] == len(kl) and (r["desc_left"] == dl).all() and (r["kp_left"]["x"] == kl["x"]).all()
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("nl,sf,nf,shape", [(5, 1.3, 800, (376, 1241)), (3, 1.5, 300, (240, 400)), (8, 1.1, 1500, (376, 1241)),
+                                            (1, 1.2, 200, (240, 400)), (6, 2.0, 400, (480, 640))])
+def test_other_level_counts_and_scale_factors(svo, nl, sf, nf, shape):
+    """ORBextractor.nLevels / scaleFactor other than KITTI's 8 / 1.2 (the yaml files are the reference's only source of
+    them): the extractor still equals the oracle bit for bit, with 1 to 8 levels and scale factors from 1.1 to 2."""
+    img = synth.texture(shape, 17 + nl)
+    c = svo.Context(shape[1], shape[0], nfeatures=nf, nlevels=nl, scale_factor=sf, max_batch=1, lanes=1, max_rows=500)
+    try:
+        kp, desc = c.extract(img)
+        okp, odesc, _ = O.orb(img, nf, scale=sf, nlevels=nl)
+        assert len(kp) == len(okp) and (desc == odesc).all() and (kp["octave"] == okp["octave"]).all()
+        for f in ("x", "y", "angle", "response", "size"):
+            assert (kp[f].view(np.uint32) == okp[f].view(np.uint32)).all(), f
+    finally:
+        c.close()
