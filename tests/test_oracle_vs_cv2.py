@@ -63,3 +63,18 @@ def test_orb_on_colour_input_equals_orb_on_converted_gray():
     assert len(kp) == len(ref) and (desc == rdesc).all()
     for f in ("x", "y", "angle", "response"):
         assert (kp[f].view(np.uint32) == ref[f].view(np.uint32)).all(), f
+
+
+@pytest.mark.parametrize("nl,sf,nf,shape", [(5, 1.3, 800, (376, 1241)), (3, 1.5, 300, (240, 400)), (8, 1.1, 1500, (376, 1241)),
+                                            (1, 1.2, 200, (240, 400)), (6, 2.0, 400, (480, 640))])
+def test_orb_equals_cv2_at_other_level_counts_and_scale_factors(nl, sf, nf, shape):
+    """The oracle follows cv::ORB for ORBextractor.nLevels / scaleFactor other than KITTI's 8 / 1.2 as well (the cases
+    tests/test_gpu_parity2.py runs on the device)."""
+    img = synth.texture(shape, 17 + nl)
+    cv2.setUseOptimized(False)
+    kp, rdesc = cv2.ORB_create(nfeatures=nf, scaleFactor=sf, nlevels=nl).detectAndCompute(img, None)
+    ref = np.array([(p.pt[0], p.pt[1], p.size, p.angle, p.response, p.octave) for p in kp], dtype=O.KP_DTYPE)
+    okp, desc, _ = O.orb(img, nf, scale=sf, nlevels=nl)
+    assert len(okp) == len(ref) and (desc == rdesc).all() and (okp["octave"] == ref["octave"]).all()
+    for f in ("x", "y", "size", "angle", "response"):
+        assert (okp[f].view(np.uint32) == ref[f].view(np.uint32)).all(), f
