@@ -552,13 +552,20 @@ def run_gpu(args, rank, world, local_rank):
         # the dominant kernel = the largest share of the step when every kernel runs alone (the ncu launch list); the live
         # event brackets are taken while other lanes' kernels share the SMs and the tensor-core brackets include the
         # operand expansion, so they rank kernels less reliably
-        alone = {k: counts.get("kernels", {}).get(v[2], {}).get("ncu_duration_us", 0.0) for k, v in single.items()} if headline_cfg else {}
+        def kcount(name):
+            # traffic.json keys are ncu's kernel names: an exact key, else the first one that extends it (k_harris -> k_harris4,
+            # k_blur -> k_blur<(bool)1>)
+            ks = counts.get("kernels", {})
+            if name in ks:
+                return ks[name]
+            return next((v for k, v in ks.items() if k.startswith(name) and "#" not in k), {})
+        alone = {k: kcount(v[2]).get("ncu_duration_us", 0.0) for k, v in single.items()} if headline_cfg else {}
         dom = max(single, key=lambda k: (alone.get(k, 0.0), stage.get(single[k][0], 0.0)))
         dur_ms = stage.get(single[dom][0], 0.0)
         alg_bytes = float(single[dom][1])
         achieved = alg_bytes / (dur_ms * 1e-3) / 1e9 if dur_ms > 0 else None
         traffic = None
-        kc = counts.get("kernels", {}).get(single[dom][2], {}) if headline_cfg else {}
+        kc = kcount(single[dom][2]) if headline_cfg else {}
         traffic = kc.get("dram_bytes_per_launch")
         # What binds the path is instruction issue, not bytes: the kernel's warp instructions per launch
         # (ncu, a property of the workload) over its live launch time against the MEASURED issue ceiling of this GPU

@@ -83,6 +83,95 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_harris(Bufs b, Geom g, int 
     }
 }
 
+// The same response with EIGHT lanes per candidate (four candidates per warp): lane r of a group owns block row r
+// (7 of 8 lanes busy) and walks its 7 positions from three patch rows held in registers.  With the column sums
+// s[k] = p0[k] + 2 p1[k] + p2[k] and differences v[k] = p2[k] - p0[k] of its three rows,
+//     Ix(dx) = s[dx + 2] - s[dx]            Iy(dx) = v[dx] + 2 v[dx + 1] + v[dx + 2]
+// (the 3x3 Sobel pair written out in k_harris, regrouped; integers, so exact).  The warp-per-candidate form spends
+// its instructions on per-candidate overhead (two passes over 49 positions with 32 lanes, three full-warp reductions):
+// 248 warp instructions per candidate against ~60 here.  The float tail is the one of k_harris.
+__global__ void __launch_bounds__(DESC_WARPS * 32) k_harris4(Bufs b, Geom g, int slot0)
+{
+    __shared__ uint32_t patch[DESC_WARPS][4][28];    // per candidate 9 rows of three aligned words
+    const int l = blockIdx.y, slot = slot0 + blockIdx.z;
+    const LevelGeom &L = g.lv[l];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int n = b.kept1[(size_t)slot * SVO_MAX_LEVELS + l];
+    if (n > L.cap2) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(b.status + slot, SVO_STATUS_OVERFLOW);
+        n = L.cap2;
+    }
+    const uint8_t *img = b.pyr + (size_t)slot * g.pyr_bytes + L.off;
+    const uint32_t *cval = b.cval + (size_t)slot * g.cand_total + L.cand_off;
+    float *key2 = b.key2 + (size_t)slot * g.total2 + L.off2;
+    uint32_t *val2 = b.val2 + (size_t)slot * g.total2 + L.off2;
+    const int sp = L.pitch;
+    const int grp = lane >> 3, r = lane & 7;
+    for (int c0 = (blockIdx.x * DESC_WARPS + warp) * 4; c0 < n; c0 += gridDim.x * DESC_WARPS * 4) {
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                // 4 x 27 words, lane after lane
+            const int t = lane + 32 * i;
+            const int cg = (t * 19) >> 9, w = t - 27 * cg;       // t / 27 for t < 128
+            if (t < 108 && c0 + cg < n) {
+                const uint32_t e = cval[c0 + cg];
+                const int x = unpack_x(e), y = unpack_y(e);
+                const int row = (w * 11) >> 5, col = w - 3 * row; // w / 3 for w < 27
+                patch[warp][cg][w] = *reinterpret_cast<const uint32_t *>(img + (size_t)(y - 4 + row) * sp + ((x - 4) & ~3) + 4 * col);
+            }
+        }
+        __syncwarp();
+        const int c = c0 + grp;
+        const bool have = c < n;
+        const uint32_t e = have ? cval[c] : 0u;
+        int a = 0, bb = 0, cc = 0;
+        if (have && r < 7) {
+            const uint32_t sh = 8u * (uint32_t)((unpack_x(e) - 4) & 3);      // byte offset of column x - 4 in the first word
+            int p[3][9];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const uint32_t *pw = patch[warp][grp] + 3 * (r + j);
+                const uint32_t w0 = pw[0], w1 = pw[1], w2 = pw[2];
+                const uint32_t lo = __funnelshift_r(w0, w1, sh), mid = __funnelshift_r(w1, w2, sh), hi = w2 >> sh;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    p[j][k] = (int)__byte_perm(lo, 0u, 0x4440u + k);       // byte k, zero-extended: one PRMT
+                    p[j][4 + k] = (int)__byte_perm(mid, 0u, 0x4440u + k);
+                }
+                p[j][8] = (int)(hi & 0xffu);
+            }
+            int s[9], v[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { s[k] = p[0][k] + 2 * p[1][k] + p[2][k]; v[k] = p[2][k] - p[0][k]; }
+#pragma unroll
+            for (int dx = 0; dx < 7; ++dx) {
+                const int Ix = s[dx + 2] - s[dx];
+                const int Iy = v[dx] + 2 * v[dx + 1] + v[dx + 2];
+                a += Ix * Ix; bb += Iy * Iy; cc += Ix * Iy;
+            }
+        }
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {            // the 8 lanes of a group
+            a += __shfl_xor_sync(0xffffffffu, a, d);
+            bb += __shfl_xor_sync(0xffffffffu, bb, d);
+            cc += __shfl_xor_sync(0xffffffffu, cc, d);
+        }
+        if (have && r == 0) {
+            const float scale = 1.f / ((1 << 2) * 7 * 255.f);
+            const float s2 = __fmul_rn(scale, scale);
+            const float s4 = __fmul_rn(__fmul_rn(s2, scale), scale);
+            const float fa = (float)a, fb = (float)bb, fc = (float)cc;
+            const float t1 = __fmul_rn(fa, fb);
+            const float t2 = __fmul_rn(fc, fc);
+            const float sm = __fadd_rn(fa, fb);
+            const float t3 = __fmul_rn(__fmul_rn(0.04f, sm), sm);
+            const float val = __fsub_rn(__fsub_rn(t1, t2), t3);
+            key2[c] = __fmul_rn(val, s4);
+            val2[c] = e;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // Blur: u8 -> f32 row pass (taps left to right) -> f32 column pass (centre, then symmetric
 // pairs) -> rint -> u8, reflect-101 borders; every float op separately rounded.
@@ -115,8 +204,22 @@ __device__ __forceinline__ float2 add_prod(float2 acc, float2 prod)
 {
     return make_float2(__fadd_rn(acc.x, prod.x), __fadd_rn(acc.y, prod.y));
 }
+// The same sum as ONE packed instruction: prod * 1 + acc.  The multiplication by one is exact, so the fused result is
+// the separately rounded sum bit for bit, and because the multiplicand comes from constant memory (a value the compiler
+// cannot see) neither NVVM nor ptxas can turn it back into the mul + add pair that ptxas would contract.
+__constant__ float c_one[2] = {1.f, 1.f};
+template <bool PACKED>
+__device__ __forceinline__ float2 add_prod_p(float2 acc, float2 prod, float2 one)
+{
+    return PACKED ? __ffma2_rn(prod, one, acc) : add_prod(acc, prod);
+}
 #define BLUR_RB (4 * 128 + 32)   // staged bytes per tile row: 128 quads + a 16-byte aligned halo on each side
 
+// MARGIN (the current form; <false> is kept for SVO_B200_BLUR_MARGIN=0): sums of products as packed FFMA2 (add_prod_p), and
+// the reflect-101 columns left of pixel 0 and right of the last pixel are written into the staged tile once
+// (3 bytes per row and side), so every quad — also the first and the last of a row — takes the word-load path; without
+// it the warps that hold an edge quad execute both paths on every row (two of the ten warps of a level-0 row).
+template <bool MARGIN>
 __global__ void __launch_bounds__(BLUR_THREADS) k_blur(Bufs b, Geom g, int slot0)
 {
     // The tile's source rows (BLUR_ROWS + 6 halo rows, reflect-101 at the image top/bottom folded into the row choice)
@@ -147,9 +250,10 @@ __global__ void __launch_bounds__(BLUR_THREADS) k_blur(Bufs b, Geom g, int slot0
     }
     __syncthreads();
     cuda::barrier<cuda::thread_scope_block>::arrival_token tok;
+    const int xv = MARGIN ? xa - 16 : xs;          // pixel held by byte 0 of a staged row (MARGIN: also for the first tile, where it is -16)
     if (tid < 32) {
         for (int r = tid; r < nst; r += 32)
-            cuda::device::memcpy_async_tx(tile + r * BLUR_RB, img + (size_t)reflect101(y0 + r - 3, Lh) * sp + xs,
+            cuda::device::memcpy_async_tx(tile + r * BLUR_RB + (xs - xv), img + (size_t)reflect101(y0 + r - 3, Lh) * sp + xs,
                                           cuda::aligned_size_t<16>(rowbytes), bar);
     }
     if (tid == 0) tok = cuda::device::barrier_arrive_tx(bar, 1, rowbytes * (uint32_t)nst);
@@ -158,14 +262,29 @@ __global__ void __launch_bounds__(BLUR_THREADS) k_blur(Bufs b, Geom g, int slot0
 #pragma unroll
     for (int k = 0; k < 7; ++k) gk[k] = make_float2(__uint_as_float(c_gauss[k]), __uint_as_float(c_gauss[k]));
     const float2 two23 = make_float2(-8388608.f, -8388608.f), rnd = make_float2(12582912.f, 12582912.f);
+    const float2 one = make_float2(c_one[0], c_one[1]);
     const int x0 = xa + 4 * tid;
     const bool active = tid < tq && x0 < Lw;
-    const bool interior = x0 >= 4 && x0 + 6 < Lw;   // bytes x0-3 .. x0+6 all inside the row
-    const int lx = x0 - xs;
+    const bool interior = MARGIN || (x0 >= 4 && x0 + 6 < Lw);   // bytes x0-3 .. x0+6 all inside the row (or its margins)
+    const int lx = x0 - xv;
     float2 win[7][2];                               // horizontal sums of the last 7 rows: pixels (0,1) and (2,3)
 #pragma unroll
     for (int k = 0; k < 7; ++k) win[k][0] = win[k][1] = make_float2(0.f, 0.f);
     bar.wait(std::move(tok));
+    if (MARGIN) {
+        // reflect-101: pixel -k = pixel k, pixel Lw - 1 + k = pixel Lw - 1 - k (k = 1..3), one staged row per thread.  The
+        // right margin is written by every tile whose quads can reach it (the row's end lies at most 8 pixels past the
+        // tile's quads); what lies beyond only feeds the padding columns of the output.
+        if (tid < nst) {
+            uint8_t *row = tile + tid * BLUR_RB;
+            if (xa == 0) { row[15] = row[17]; row[14] = row[18]; row[13] = row[19]; }
+            if (Lw > xs + 4 && Lw <= xa + 4 * tq + 8) {
+                const int e = Lw - xv;
+                row[e] = row[e - 2]; row[e + 1] = row[e - 3]; row[e + 2] = row[e - 4];
+            }
+        }
+        __syncthreads();
+    }
     if (!active) return;
     for (int r0 = 0; r0 < nst; r0 += 7) {
 #pragma unroll
@@ -182,7 +301,7 @@ __global__ void __launch_bounds__(BLUR_THREADS) k_blur(Bufs b, Geom g, int slot0
                     m[7] = byte_magic(w2, 0); m[8] = byte_magic(w2, 1); m[9] = byte_magic(w2, 2);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 10; ++j) m[j] = __uint_as_float(0x4B000000u | row[reflect101(x0 - 3 + j, Lw) - xs]);
+                    for (int j = 0; j < 10; ++j) m[j] = __uint_as_float(0x4B000000u | row[reflect101(x0 - 3 + j, Lw) - xv]);
                 }
                 float2 P[9];                            // P[t] = pixels (x0-3+t, x0-2+t)
 #pragma unroll
@@ -190,8 +309,8 @@ __global__ void __launch_bounds__(BLUR_THREADS) k_blur(Bufs b, Geom g, int slot0
                 float2 a01 = __fmul2_rn(gk[0], P[0]), a23 = __fmul2_rn(gk[0], P[2]);
 #pragma unroll
                 for (int t = 1; t < 7; ++t) {
-                    a01 = add_prod(a01, __fmul2_rn(gk[t], P[t]));
-                    a23 = add_prod(a23, __fmul2_rn(gk[t], P[t + 2]));
+                    a01 = add_prod_p<MARGIN>(a01, __fmul2_rn(gk[t], P[t]), one);
+                    a23 = add_prod_p<MARGIN>(a23, __fmul2_rn(gk[t], P[t + 2]), one);
                 }
                 win[k][0] = a01; win[k][1] = a23;
                 if (r >= 6) {                           // rows r-6 .. r are in the window: emit image row y0 + r - 6
@@ -199,9 +318,9 @@ __global__ void __launch_bounds__(BLUR_THREADS) k_blur(Bufs b, Geom g, int slot0
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         float2 acc = __fmul2_rn(gk[3], win[(k + 4) % 7][j]);
-                        acc = add_prod(acc, __fmul2_rn(gk[4], __fadd2_rn(win[(k + 5) % 7][j], win[(k + 3) % 7][j])));
-                        acc = add_prod(acc, __fmul2_rn(gk[5], __fadd2_rn(win[(k + 6) % 7][j], win[(k + 2) % 7][j])));
-                        acc = add_prod(acc, __fmul2_rn(gk[6], __fadd2_rn(win[k][j], win[(k + 1) % 7][j])));
+                        acc = add_prod_p<MARGIN>(acc, __fmul2_rn(gk[4], __fadd2_rn(win[(k + 5) % 7][j], win[(k + 3) % 7][j])), one);
+                        acc = add_prod_p<MARGIN>(acc, __fmul2_rn(gk[5], __fadd2_rn(win[(k + 6) % 7][j], win[(k + 2) % 7][j])), one);
+                        acc = add_prod_p<MARGIN>(acc, __fmul2_rn(gk[6], __fadd2_rn(win[k][j], win[(k + 1) % 7][j])), one);
                         // round to nearest even by adding 1.5 * 2^23: the low mantissa byte is the pixel
                         // (0 <= acc <= 255 * (sum of taps) < 255.5, so no clamp is needed)
                         o[j] = __fadd2_rn(acc, rnd);
@@ -349,15 +468,21 @@ void launch_harris(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream
 {
     int mx = 1;
     for (int l = 0; l < g.nlevels; ++l) mx = g.lv[l].quota * 2 + 64 > mx ? g.lv[l].quota * 2 + 64 : mx;
-    dim3 grid((mx + DESC_WARPS - 1) / DESC_WARPS, g.nlevels, nimg);
-    k_harris<<<grid, DESC_WARPS * 32, 0, st>>>(b, g, slot0);
+    if (g.harris8) {
+        dim3 grid((mx + 4 * DESC_WARPS - 1) / (4 * DESC_WARPS), g.nlevels, nimg);
+        k_harris4<<<grid, DESC_WARPS * 32, 0, st>>>(b, g, slot0);
+    } else {
+        dim3 grid((mx + DESC_WARPS - 1) / DESC_WARPS, g.nlevels, nimg);
+        k_harris<<<grid, DESC_WARPS * 32, 0, st>>>(b, g, slot0);
+    }
     ++*launches;
 }
 
 void launch_blur(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStream_t st, long long *launches)
 {
     dim3 grid(g.blur_tiles, nimg);
-    k_blur<<<grid, BLUR_THREADS, 0, st>>>(b, g, slot0);
+    if (g.blur_margin) k_blur<true><<<grid, BLUR_THREADS, 0, st>>>(b, g, slot0);
+    else k_blur<false><<<grid, BLUR_THREADS, 0, st>>>(b, g, slot0);
     ++*launches;
 }
 

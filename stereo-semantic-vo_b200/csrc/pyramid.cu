@@ -67,8 +67,73 @@ __global__ void __launch_bounds__(256) k_resize(Bufs b, Geom g, int l, int slot0
     }
 }
 
+// The same strips from the quad table (resize_quads.h): the eight horizontal taps of an output quad lie within 8
+// consecutive source bytes, so a source row costs three aligned word loads, two funnel shifts (an 8-byte window that
+// starts at the first tap), two byte permutes (the taps of columns 0,1 and 2,3) and four two-way dot products (dp2a:
+// (256 - w1, w1) as two u16 times two bytes) instead of eight byte loads with 64-bit address arithmetic and eight
+// multiply-adds: 146 -> ~45 warp instructions per output quad row.  The two source rows of an output row live in two
+// register sets whose roles alternate from row to row (the lower row of one output row is usually the upper row of the
+// next), tracked by the source row each set holds, so nothing is copied.  Identical integer arithmetic.
+__device__ __forceinline__ void resize_hrow(const uint8_t *srcq, int sp, int yy, uint32_t sh, uint32_t sel01, uint32_t sel23,
+                                            const uint32_t (&W)[4], uint32_t (&h)[4])
+{
+    const uint32_t *r = reinterpret_cast<const uint32_t *>(srcq + (size_t)yy * sp);
+    const uint32_t w0 = r[0], w1 = r[1], w2 = r[2];     // up to 11 bytes past the row's width: inside the padded row or the next one
+    const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+    const uint32_t p01 = __byte_perm(lo, hi, sel01), p23 = __byte_perm(lo, hi, sel23);
+    h[0] = __dp2a_lo(W[0], p01, 0u); h[1] = __dp2a_hi(W[1], p01, 0u);
+    h[2] = __dp2a_lo(W[2], p23, 0u); h[3] = __dp2a_hi(W[3], p23, 0u);
+}
+__device__ __forceinline__ uint32_t resize_vpack(const uint32_t (&u)[4], const uint32_t (&v)[4], uint32_t wy0, uint32_t wy1)
+{
+    // each sum is below 2^24, so the rounded Q16 result is its byte 2
+    const uint32_t s0 = u[0] * wy0 + v[0] * wy1 + 32768u, s1 = u[1] * wy0 + v[1] * wy1 + 32768u;
+    const uint32_t s2 = u[2] * wy0 + v[2] * wy1 + 32768u, s3 = u[3] * wy0 + v[3] * wy1 + 32768u;
+    return __byte_perm(__byte_perm(s0, s1, 0x0062), __byte_perm(s2, s3, 0x0062), 0x5410);
+}
+
+// one output row y of a strip: upper source row in U (holding source row ru), lower in V (holding rv); `yt` = the level's
+// y table, `srcq` = the strip's first aligned source word in source row 0, `dstq` = the strip's quad in output row 0
+#define RESIZE_ROW(y, U, ru, V, rv)                                                              \
+    if ((y) < y1) {                                                                              \
+        const uint32_t ty = __ldg(yt + (y));                                                     \
+        const int yo = (int)(ty >> 9);                                                           \
+        const uint32_t wy1 = ty & 511u, wy0 = 256u - wy1;                                        \
+        if (ru != yo) { resize_hrow(srcq, sp, yo, sh, sel01, sel23, W, U); ru = yo; }            \
+        if (wy1 && rv != yo + 1) { resize_hrow(srcq, sp, yo + 1, sh, sel01, sel23, W, V); rv = yo + 1; }   \
+        *reinterpret_cast<uint32_t *>(dstq + (size_t)(y) * dp) = resize_vpack(U, V, wy0, wy1);   \
+    }
+
+__global__ void __launch_bounds__(256) k_resize_q(Bufs b, Geom g, int l, int slot0, int rs)
+{
+    const LevelGeom &d = g.lv[l];
+    const LevelGeom &s = g.lv[l - 1];
+    const int qpr = d.pitch >> 2;  // quads per (padded) row
+    const int strips = (d.h + rs - 1) / rs;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= qpr * strips) return;
+    const int st = q / qpr, xq = q - st * qpr;
+    const int y0 = st * rs, y1 = min(y0 + rs, d.h);
+    const size_t base = (size_t)(slot0 + blockIdx.y) * g.pyr_bytes;
+    const uint4 *qe = reinterpret_cast<const uint4 *>(b.rqtab) + 2 * (size_t)(d.rq_off + xq);
+    const uint4 e0 = __ldg(qe);
+    const uint2 e1 = __ldg(reinterpret_cast<const uint2 *>(qe + 1));
+    const uint32_t sh = e0.x >> 16, sel01 = e0.y & 0xffffu, sel23 = e0.y >> 16;
+    const uint32_t W[4] = {e0.z, e0.w, e1.x, e1.y};
+    const uint8_t *srcq = b.pyr + base + s.off + (e0.x & 0xffffu);
+    uint8_t *dstq = b.pyr + base + d.off + 4 * xq;
+    const uint32_t *yt = b.rtab + d.tab_off + d.w;
+    const int sp = s.pitch, dp = d.pitch;
+    uint32_t ha[4], hb[4];
+    int ra = -1, rb = -1;                                       // source rows held in ha / hb
+    for (int y = y0; y < y1; y += 2) {
+        RESIZE_ROW(y, ha, ra, hb, rb)
+        RESIZE_ROW(y + 1, hb, rb, ha, ra)
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
-// All seven resized levels in ONE launch.  A CTA owns a band of rows of the last level and everything below it that the
+// All seven resized levels in ONE launch. A CTA owns a band of rows of the last level and everything below it that the
 // band depends on: the level-0 rows arrive with one TMA bulk copy (the pitched rows of a band are contiguous in HBM),
 // then level 1 is computed from them in shared memory, level 2 from level 1, ... — every level is read from shared
 // memory, never from HBM — and each level's rows this band OWNS are stored with 16-byte writes while the next level is
@@ -124,6 +189,28 @@ __global__ void __launch_bounds__(PYR_THREADS) k_pyramid(Bufs b, Geom g, int slo
         // k_resize's column strips, over shared memory: a thread owns 4 output columns and walks PYR_STRIP rows down, sharing
         // the horizontal pass of a source row between the two output rows that straddle it
         const int strips = (nrows + PYR_STRIP - 1) / PYR_STRIP;
+        const uint4 *qt = reinterpret_cast<const uint4 *>(b.rqtab) + 2 * (size_t)d.rq_off;
+        const uint32_t *yt = xt + d.w;
+        const int dp = d.pitch;
+        if (d.rq_ok) {
+            // the quad-table strips of k_resize_q over shared memory (source rows are addressed relative to the tile's first row)
+            for (int it = tid; it < qpr * strips; it += PYR_THREADS) {
+                const int st = it / qpr, xq = it - st * qpr;
+                const int y0 = clo + st * PYR_STRIP, y1 = min(y0 + PYR_STRIP, clo + nrows);
+                const uint4 e0 = __ldg(qt + 2 * xq);
+                const uint2 e1 = __ldg(reinterpret_cast<const uint2 *>(qt + 2 * xq + 1));
+                const uint32_t sh = e0.x >> 16, sel01 = e0.y & 0xffffu, sel23 = e0.y >> 16;
+                const uint32_t W[4] = {e0.z, e0.w, e1.x, e1.y};
+                const uint8_t *srcq = src + (int)(e0.x & 0xffffu) - slo * sp;
+                uint8_t *dstq = dst + 4 * xq - clo * dp;
+                uint32_t ha[4], hb[4];
+                int ra = -1, rb = -1;
+                for (int y = y0; y < y1; y += 2) {
+                    RESIZE_ROW(y, ha, ra, hb, rb)
+                    RESIZE_ROW(y + 1, hb, rb, ha, ra)
+                }
+            }
+        } else
         for (int it = tid; it < qpr * strips; it += PYR_THREADS) {
             const int st = it / qpr, x = (it - st * qpr) << 2;
             const int y0 = clo + st * PYR_STRIP, y1 = min(y0 + PYR_STRIP, clo + nrows);
@@ -240,7 +327,8 @@ void launch_pyramid(const Bufs &b, const Geom &g, int slot0, int nimg, cudaStrea
         const int rs = (size_t)g.lv[l].w * g.lv[l].h * nimg >= (size_t)8 << 20 ? 8 : 4;   // fewer rows per thread when the launch is small
         const int quads = (g.lv[l].pitch >> 2) * ((g.lv[l].h + rs - 1) / rs);
         dim3 grid((quads + 255) / 256, nimg);
-        k_resize<<<grid, 256, 0, st>>>(b, g, l, slot0, rs);
+        if (g.lv[l].rq_ok) k_resize_q<<<grid, 256, 0, st>>>(b, g, l, slot0, rs);
+        else k_resize<<<grid, 256, 0, st>>>(b, g, l, slot0, rs);
         ++*launches;
     }
 }

@@ -2,6 +2,7 @@
 // (include/svo_b200.h).  Host-side orchestration only; every computation is a kernel in
 // pyramid.cu / fast.cu / select.cu / describe.cu / stereo.cu / match.cu.  No CPU fallback.
 #include "svo_internal.cuh"
+#include "resize_quads.h"
 
 #include <limits.h>
 #include <math.h>
@@ -101,6 +102,7 @@ struct svo_ctx {
     int nslots;
     std::vector<void *> dev_allocs, pinned_allocs;
     std::vector<uint32_t> rtab_host;
+    std::vector<ResizeQuad> rq_host;
     long long launches;
     size_t stage_img_bytes;
     uint8_t *sync_stage;     // landing zone of svo_extract_bgr (one colour image)
@@ -194,22 +196,6 @@ void orb_geometry(int W, int H, int nlevels, float scale_factor_f, int nfeatures
     quota[nlevels - 1] = nfeatures - sum > 0 ? nfeatures - sum : 0;
 }
 
-// INTER_LINEAR_EXACT coefficients: packed (ofs << 9) | w1, w1 in Q8
-void resize_table(int src, int dst, uint32_t *tab)
-{
-    const double scale = (double)src / (double)dst;
-    for (int d = 0; d < dst; ++d) {
-        const double fv = scale * ((double)d + 0.5) - 0.5;
-        int iv = (int)floor(fv);
-        int w1 = 0;
-        if (iv >= 0 && src > 1) {
-            if (iv < src - 1) w1 = (int)lrint((fv - (double)iv) * 256.0);
-            else iv = src - 1;
-        } else iv = 0;
-        tab[d] = ((uint32_t)iv << 9) | (uint32_t)w1;
-    }
-}
-
 int build_geometry(svo_ctx *ctx)
 {
     const svo_config &c = ctx->cfg;
@@ -226,6 +212,8 @@ int build_geometry(svo_ctx *ctx)
         if (e && atoi(e) == 8) g.fast_band = 8;
         if (e && atoi(e) == 16 && 18 * pitch0 <= 65535) g.fast_band = 16;
     }
+    { const char *e = getenv("SVO_B200_HARRIS8"); g.harris8 = !(e && e[0] == '0'); }
+    { const char *e = getenv("SVO_B200_BLUR_MARGIN"); g.blur_margin = !(e && e[0] == '0'); }
     int lw[SVO_MAX_LEVELS], lh[SVO_MAX_LEVELS], quota[SVO_MAX_LEVELS];
     float ls[SVO_MAX_LEVELS];
     orb_geometry(c.width, c.height, c.nlevels, c.scale_factor, c.nfeatures, lw, lh, ls, quota);
@@ -255,10 +243,14 @@ int build_geometry(svo_ctx *ctx)
         L.cap2 = 4 * L.quota + 1024 < L.cand_cap ? 4 * L.quota + 1024 : L.cand_cap;
         L.off2 = off2; off2 += align_up(L.cap2, 4);
         L.tab_off = tab_off; if (l) tab_off += L.w + L.h;
-        {   // blur tiles: SVO_BLUR_ROWS rows x blur_tq quads, the quads of a row split evenly over the fewest tiles of <= 128 quads
+        {   // blur tiles: SVO_BLUR_ROWS rows x blur_tq quads, the quads of a row split over the fewest tiles of <= 128 quads.
+            // The even share is rounded up to whole warps (one lane per quad): every tile but the row's last one is then
+            // made of full warps and the last one's idle warps exit at once — 94 % of the launched lanes hold a quad at
+            // 1241x376 against 86 % for evenly sized tiles (104 quads = 3.25 warps).  SVO_B200_BLUR_PACK=0: even tiles.
             const int quads = (L.w + 3) / 4;
             L.blur_tiles_x = (quads + 127) / 128;
-            L.blur_tq = align_up((quads + L.blur_tiles_x - 1) / L.blur_tiles_x, 4);
+            const char *e = getenv("SVO_B200_BLUR_PACK");
+            L.blur_tq = align_up((quads + L.blur_tiles_x - 1) / L.blur_tiles_x, (e && e[0] == '0') ? 4 : 32);
             L.blur_tile_off = tiles;                         // first blur CTA of the level
             tiles += L.blur_tiles_x * ((L.h + SVO_BLUR_ROWS - 1) / SVO_BLUR_ROWS);
         }
@@ -269,9 +261,15 @@ int build_geometry(svo_ctx *ctx)
     g.cand_total = cand_off; g.total2 = off2; g.blur_tiles = tiles;
     g.kp_cap = align_up(c.nfeatures + c.nfeatures / 8 + 64, 64);
     ctx->rtab_host.assign((size_t)tab_off + 1, 0);
+    int rq_off = 0;
+    for (int l = 1; l < g.nlevels; ++l) { g.lv[l].rq_off = rq_off; rq_off += g.lv[l].pitch / 4; }
+    ctx->rq_host.assign((size_t)rq_off + 1, ResizeQuad());
+    const char *rq_env = getenv("SVO_B200_RESIZE_QUADS");       // =0: the per-byte kernel on every level
     for (int l = 1; l < g.nlevels; ++l) {
         resize_table(lw[l - 1], lw[l], ctx->rtab_host.data() + g.lv[l].tab_off);
         resize_table(lh[l - 1], lh[l], ctx->rtab_host.data() + g.lv[l].tab_off + lw[l]);
+        g.lv[l].rq_ok = build_resize_quads(ctx->rtab_host.data() + g.lv[l].tab_off, lw[l], g.lv[l].pitch, ctx->rq_host.data() + g.lv[l].rq_off);
+        if (rq_env && rq_env[0] == '0') g.lv[l].rq_ok = 0;
     }
     return SVO_OK;
 }
@@ -320,7 +318,7 @@ int build_pyramid_bands(svo_ctx *ctx, std::vector<PyrBand> &bands, int budget)
             int rows = 0;
             for (int j = 0; j < nb; ++j) rows = std::max(rows, bs[(size_t)j].chi[l] - bs[(size_t)j].clo[l] + 1);
             soff[l] = off;
-            off += align_up(rows * g.lv[l].pitch, 128);
+            off += align_up(rows * g.lv[l].pitch + 16, 128);   // + 16: the quad-table loads read whole words up to 11 bytes past a row's width
         }
         if (off > budget) continue;
         bands = bs;
@@ -734,6 +732,12 @@ int svo_create(const svo_config *cfg, svo_ctx **out)
     TRY(dalloc(ctx, &rtab, ctx->rtab_host.size()));
     CU(cudaMemcpy(rtab, ctx->rtab_host.data(), ctx->rtab_host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     b.rtab = rtab;
+    {
+        ResizeQuad *rq = nullptr;
+        TRY(dalloc(ctx, &rq, ctx->rq_host.size()));
+        CU(cudaMemcpy(rq, ctx->rq_host.data(), ctx->rq_host.size() * sizeof(ResizeQuad), cudaMemcpyHostToDevice));
+        b.rqtab = reinterpret_cast<const uint32_t *>(rq);
+    }
     {   // One-launch pyramid (pyramid.cu:k_pyramid).  Measured on B200 (profiles/r2_pyramid_fused_experiment.md): 128 us per
         // 64 images against 126 us for the seven per-level launches when run alone and a shorter single-frame critical path
         // (24 us instead of 50 us + six dependent launches), but 5 % LOWER batch throughput inside the three-lane pipeline,

@@ -42,6 +42,8 @@ struct LevelGeom {
     int cap2;          // capacity after the first cull
     int off2;          // entry offset of key2/val2
     int tab_off;       // offset of this level's resize tables (x table then y table), level >= 1
+    int rq_off;        // first entry of this level's quad table (resize_quads.h), level >= 1
+    int rq_ok;         // 1: every quad's taps fit the 8-byte window, k_resize_q runs; 0: the per-byte k_resize
     int blur_tile_off; // first blur tile index of this level
     int blur_tiles_x;  // blur tiles per strip of 32 rows
     int blur_tq;       // pixel quads per blur tile (multiple of 4, <= 128)
@@ -61,6 +63,8 @@ struct Geom {
     int kp_cap;          // final keypoints per image
     int blur_tiles;      // blur tiles per image
     int fast_bands;      // FAST bands per image (sum of nbands)
+    int blur_margin;     // 1: k_blur<true> (reflected margins in the staged tile); 0 (SVO_B200_BLUR_MARGIN=0): per-lane reflect path
+    int harris8;         // 1: k_harris4 (eight lanes per candidate); 0 (SVO_B200_HARRIS8=0): the warp-per-candidate k_harris
     int pyr_nbands;      // bands of the fused pyramid kernel (0: the geometry does not fit it)
     int pyr_fused_max;   // launches of at most this many images use the fused kernel, larger ones the per-level kernels
     int pyr_soff[SVO_MAX_LEVELS];   // shared-memory byte offset of each level's rows in that kernel
@@ -89,6 +93,7 @@ struct Bufs {
     int *nkp;     // [slot]
     int *status;  // [slot]
     const uint32_t *rtab;  // resize tables: (ofs << 9) | w1
+    const uint32_t *rqtab; // per output quad of every level >= 1: 8 words (resize_quads.h), 32-byte aligned
     const PyrBand *pyr_bands;   // [Geom.pyr_nbands] or NULL: the fused pyramid kernel is not used for this geometry
 };
 

@@ -141,17 +141,15 @@ __device__ __forceinline__ void st_global_if(uint32_t *ptr, uint32_t val, bool p
         "@p st.global.u32 [%0], %1;\n\t"
         "}\n" ::"l"(ptr), "r"(val), "r"((uint32_t)pred) : "memory");
 }
-// maximum of the 32 accumulators of a chunk as a tree (depth 5 instead of a 31-long dependent chain)
+// maximum of the 32 accumulators of a chunk as a tree of three-input maxima (VIMNMX3): 16 instructions, depth 4
 __device__ __forceinline__ int max32(const int (&v)[32])
 {
-    int a[16];
+    int a[12];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) a[i] = max(v[2 * i], v[2 * i + 1]);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = max(a[2 * i], a[2 * i + 1]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = max(a[2 * i], a[2 * i + 1]);
-    return max(max(a[0], a[1]), max(a[2], a[3]));
+    for (int i = 0; i < 10; ++i) a[i] = __vimax3_s32(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+    a[10] = v[30]; a[11] = v[31];
+    return max(__vimax3_s32(__vimax3_s32(a[0], a[1], a[2]), __vimax3_s32(a[3], a[4], a[5]), __vimax3_s32(a[6], a[7], a[8])),
+               __vimax3_s32(a[9], a[10], a[11]));
 }
 
 // The low byte of every accumulator of a chunk, 4 per word, word k of lane l at [k][l] (conflict-free): enough to
@@ -375,8 +373,6 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tc_hamming(TcArgs p)
             for (int c = 0; c < TC_N / 32; ++c) {
                 const int j0 = t * TC_N + c * 32;
                 if (j0 >= nB) break;                                   // warp-uniform
-                int mycol = j0 + lane;                                 // TC_SHORT: the column behind position j0 + lane of the gathered list
-                if (MODE == TC_SHORT && bcol && j0 + lane < nB) mycol = bcol[j0 + lane];
                 int v[32];
                 tmem_ld32(lane_base + (uint32_t)(c * 32), v);
                 const int nv = min(32, nB - j0);                       // valid columns of this chunk (32 except at the very end)
@@ -439,23 +435,32 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tc_hamming(TcArgs p)
                         }
                     }
                 } else if (MODE == TC_SHORT) {
-                    // every column with d < 60 goes to the row's segment of this stream, in scan (= ascending) order: a
-                    // straight-line hit mask (2 instructions per column), then only the set bits are visited; their distance
-                    // comes from the spilled low bytes, their column from the chunk's slice of the gathered column list
-                    uint32_t mask = 0;
+                    // every column with d < 60 goes to the row's segment of this stream, in scan (= ascending) order.
+                    // Most chunks hold no hit for any of the warp's 32 rows (a hit is a true match, not noise: d < 60 lies
+                    // 8 sigma below the mean distance of unrelated descriptors), so the chunk's maximum (16 instructions)
+                    // decides first; only when some row has a hit: a straight-line hit mask (2 instructions per column),
+                    // then the set bits are visited — their distance comes from the spilled low bytes, their column from
+                    // the chunk's slice of the gathered column list.  Padding columns of the last tile (dot product 0) can
+                    // only make the guard fire needlessly; the mask drops them.
+                    const int mx = max32(v);
+                    if (__any_sync(0xffffffffu, live && mx > thr_dot)) {
+                        int mycol = j0 + lane;                         // the column behind position j0 + lane of the gathered list
+                        if (bcol && j0 + lane < nB) mycol = bcol[j0 + lane];
+                        uint32_t mask = 0;
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) mask |= (v[e] > thr_dot ? 1u : 0u) << e;
-                    if (nv < 32) mask &= (1u << nv) - 1u;
-                    if (!live) mask = 0;
-                    __syncwarp();
-                    spill_low_bytes(ct, lane, v);
-                    ct[256 + lane] = mycol;
-                    __syncwarp();
-                    while (mask) {
-                        const int e = __ffs((int)mask) - 1;
-                        mask &= mask - 1;
-                        if (cnt < SVO_TC_SEG) *tc_short_slot(g, ro + row, q * SVO_TC_SEG + cnt) = (hit_distance(ct, lane, e) << 16) | (uint32_t)ct[256 + e];
-                        ++cnt;
+                        for (int e = 0; e < 32; ++e) mask |= (v[e] > thr_dot ? 1u : 0u) << e;
+                        if (nv < 32) mask &= (1u << nv) - 1u;
+                        if (!live) mask = 0;
+                        __syncwarp();
+                        spill_low_bytes(ct, lane, v);
+                        ct[256 + lane] = mycol;
+                        __syncwarp();
+                        while (mask) {
+                            const int e = __ffs((int)mask) - 1;
+                            mask &= mask - 1;
+                            if (cnt < SVO_TC_SEG) *tc_short_slot(g, ro + row, q * SVO_TC_SEG + cnt) = (hit_distance(ct, lane, e) << 16) | (uint32_t)ct[256 + e];
+                            ++cnt;
+                        }
                     }
                 }
             }

@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsvo_b200.so")
+# SVO_B200_LIB: another build of the same library (A/B measurements of two builds in one run); default: the in-tree one
+LIB_PATH = os.environ.get("SVO_B200_LIB") or os.path.join(HERE, "libsvo_b200.so")
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
                      ("response", "<f4"), ("octave", "<i4")])
