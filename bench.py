@@ -802,7 +802,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="stereo frames per step")
-    ap.add_argument("--lanes", type=int, default=3)
+    ap.add_argument("--lanes", type=int, default=4)
     ap.add_argument("--pool", type=int, default=160, help="distinct synthetic frames cycled (must exceed L2)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -9,7 +9,12 @@
 #include <float.h>
 #include <cuda/barrier>
 
-#define DESC_WARPS 8
+// Warps per CTA of k_harris / k_harris4 / k_describe.  Four, not eight: a 4-warp k_describe CTA (5.9 KB of shared memory)
+// fits beside the two 109-KB k_fast CTAs another lane keeps on an SM, an 8-warp one (11.8 KB) does not: 26.86 k -> 27.11 k
+// frames/s in the four-lane pipeline (profiles/r2_experiments.md).
+#ifndef DESC_WARPS
+#define DESC_WARPS 4
+#endif
 
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 // cv::getGaussianKernel(7, 2, CV_32F), exact bits

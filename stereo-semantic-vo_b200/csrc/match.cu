@@ -233,8 +233,10 @@ __global__ void k_greedy_init(GreedyArgs a, int reset_time)
                     }
                 }
             }
-            if (a.row_need) a.row_need[o] = live ? 1 : 0;          // tensor-core pass 2: every live row is scanned
-            else if (live) {
+            if (a.row_need) {                                      // tensor-core pass 2: every live row is scanned
+                a.row_need[o] = live ? 1 : 0;
+                if (SVO_TC_GATHER_ROWS && live) a.need_list[ro + atomicAdd(a.list_cnt + 2 * f, 1)] = i;   // ... as a gathered tile row (any order)
+            } else if (live) {
                 if (reuse >= 0) a.reuse_list[ro + atomicAdd(a.list_cnt + 2 * f + 1, 1)] = i | (reuse << 16);
                 else a.need_list[ro + atomicAdd(a.list_cnt + 2 * f, 1)] = i;
             }
@@ -1334,7 +1336,7 @@ void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStrea
     if (maxM <= 0 || nframes <= 0) return;
     const int mx = maxM > maxN ? maxM : maxN;
     dim3 gi((mx + 255) / 256, nframes);
-    if (a.need_list && !a.row_need) cudaMemsetAsync(a.list_cnt, 0, sizeof(int) * 2 * nframes, st);
+    if (a.need_list && (!a.row_need || SVO_TC_GATHER_ROWS)) cudaMemsetAsync(a.list_cnt, 0, sizeof(int) * 2 * nframes, st);
     if (a.win_gather) { k_win_prepare<<<nframes, 256, 0, st>>>(a); ++*launches; }
     k_greedy_init<<<gi, 256, 0, st>>>(a, 1);
     if (a.free_col && !a.win_gather && !a.win_uvr) { k_free_cols<<<nframes, 1024, 0, st>>>(a); ++*launches; }
@@ -1357,7 +1359,14 @@ void launch_greedy(const GreedyArgs &a, int nframes, bool want_scores, cudaStrea
         ex.set = a.rows; ex.img = a.img_rows; ex.img_frame_stride = a.img_rows_stride;
         tc.A = a.rows; tc.B = a.cols; tc.g = a; tc.T = T; tc.row_need = a.row_need; tc.prof = a.tc_prof;
         tc.a_img = a.img_rows; tc.a_img_frame_stride = a.img_rows_stride;
+        if (SVO_TC_GATHER_ROWS && a.need_list) {
+            // only the rows pass 2 scans become tile rows (a quarter of a 5000-row map is matched by pass 1 on the bench
+            // sequence): k_greedy_init listed them, the expansion gathers them, TC_SHORT maps a tile row back to its map row
+            ex.index32 = a.need_list; ex.index_cnt = a.list_cnt; ex.index_cnt_stride = 2; ex.index_stride = a.rows.stride_rows;
+            tc.a_index = a.need_list; tc.a_index_cnt = a.list_cnt;
+        }
         TcExpandArgs ex1 = ex;
+        ex1.index32 = nullptr; ex1.index_cnt = nullptr; ex1.index_cnt_stride = 0;
         if (a.free_col) {   // the columns pass 1 left free, gathered in ascending order
             ex1.set = a.cols; ex1.index = a.free_col; ex1.index_cnt = a.free_cnt; ex1.index_stride = a.cols.stride_rows;
             ex1.img = a.img_free; ex1.img_frame_stride = a.img_free_stride;

@@ -21,6 +21,9 @@
 #define SVO_WIN_CELLS 4096     // most cells of the keypoint grid used by the windowed pass 2
 #define SVO_TC_TILE_BYTES 32768  // one tensor-core operand image: 128 descriptors x 256 int8 (tcham.cu)
 #define SVO_TC_STREAMS 2       // column ranges (streams) a tensor-core CTA splits a row's scan into (tcham.cu)
+#ifndef SVO_TC_GATHER_ROWS
+#define SVO_TC_GATHER_ROWS 1   // tensor-core pass 2 scans a gathered list of the live rows instead of masking the dead ones (0: the masked form)
+#endif
 #define SVO_TC_SEG (SVO_SHORT_CAP / SVO_TC_STREAMS)   // TC_SHORT: short-list slots of each range of a row
 #define SVO_STATUS_OVERFLOW 1  // bit set in the per-image status word on a capacity overflow
 #define SVO_STATUS_DEPTH 2     // introselect reached its depth limit (heap-select path ran)
@@ -286,6 +289,8 @@ struct TcExpandArgs {            // descriptor set -> operand images ([frame][ti
     const uint16_t *index;       // optional ascending gather list ([frame][index_stride]) and its length per frame
     const int *index_cnt;
     int index_stride;
+    const int *index32;          // the same as 32-bit entries in any order ([frame][index_stride]; length at index_cnt[frame * index_cnt_stride])
+    int index_cnt_stride;        // 0 is read as 1
     uint8_t *img; size_t img_frame_stride;
 };
 struct TcArgs {
@@ -299,6 +304,8 @@ struct TcArgs {
     const int *b_index_cnt;      //           its length per frame
     int b_index_stride;
     const uint8_t *row_need;     // TC_SHORT: [frame][rows.stride_rows] 1 = the row is scanned
+    const int *a_index;          // TC_SHORT: a_img was gathered with this list of scanned rows ([frame][rows.stride_rows], any order;
+    const int *a_index_cnt;      //           length at a_index_cnt[2 * frame]); NULL = a_img holds every row in place
     int *dump; int dump_rows, dump_pitch;   // TC_DUMP: [frame][dump_rows][dump_pitch] dot products (256 - 2 d)
     long long *prof;             // optional clock64 timeline of CTA (0, 0): [mode][4 roles][64] (svo_debug_tc_profile)
 };

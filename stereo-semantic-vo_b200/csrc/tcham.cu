@@ -206,16 +206,17 @@ __global__ void __launch_bounds__(256) k_tc_expand(TcExpandArgs e0, TcExpandArgs
     const TcExpandArgs &e = blockIdx.z ? e1 : e0;      // up to two descriptor sets per launch
     const int f = blockIdx.y;
     int n = tc_count(e.set, f);
-    if (e.index) n = min(n, e.index_cnt[f]);
+    if (e.index || e.index32) n = min(n, e.index_cnt[(size_t)f * (e.index_cnt_stride ? e.index_cnt_stride : 1)]);
     const int ntile_rows = ((n + TC_M - 1) / TC_M) * TC_M;
     const uint8_t *src = tc_desc(e.set, f);
     const uint16_t *idx = e.index ? e.index + (size_t)f * e.index_stride : nullptr;
+    const int *idx32 = e.index32 ? e.index32 + (size_t)f * e.index_stride : nullptr;
     uint8_t *img = e.img + (size_t)f * e.img_frame_stride;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < ntile_rows * 16; i += gridDim.x * 256) {
         const int r = i >> 4, c = i & 15;
         uint4 o = make_uint4(0, 0, 0, 0);
         if (r < n) {
-            const int sr = idx ? (int)idx[r] : r;
+            const int sr = idx ? (int)idx[r] : (idx32 ? idx32[r] : r);
             const uint32_t h = reinterpret_cast<const uint16_t *>(src + (size_t)sr * 32)[c];
             o.x = expand4(h & 15u); o.y = expand4((h >> 4) & 15u); o.z = expand4((h >> 8) & 15u); o.w = expand4(h >> 12);
         }
@@ -237,7 +238,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tc_hamming(TcArgs p)
     extern __shared__ uint8_t tc_smem_raw[];
     const int f = blockIdx.y;
     const int a0 = blockIdx.x * TC_M;
-    const int nA = tc_count(p.A, f);
+    int nA = tc_count(p.A, f);
+    if (MODE == TC_SHORT && p.a_index) nA = min(nA, p.a_index_cnt[2 * f]);     // the scanned rows only, gathered by k_tc_expand
     int nB = tc_count(p.B, f);
     if (MODE == TC_SHORT && p.b_index) nB = min(p.b_index_cnt[f], nB);
     if (a0 >= nA || nB <= 0) return;                                   // whole CTA, before anything is allocated
@@ -327,8 +329,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tc_hamming(TcArgs p)
         // ================= epilogue: thread = one A row of one stream, columns in ascending order =================
         const int q = warp >> 2;                                       // stream; warp & 3 = TMEM lane quarter (== warp % 4)
         const int trow = (warp & 3) * 32 + lane;
-        const int row = a0 + trow;
-        const bool row_ok = row < nA;
+        const bool row_ok = a0 + trow < nA;
+        int row = a0 + trow;
+        if (MODE == TC_SHORT && p.a_index) row = row_ok ? p.a_index[(size_t)f * g.rows.stride_rows + row] : 0;   // tile row -> map row
         const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)q * TC_N;
         const size_t ro = (size_t)f * g.rows.stride_rows, co = (size_t)f * g.cols.stride_rows;
         const int t0 = q * per, nq = max(0, min(per, ntiles - t0));
@@ -349,7 +352,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tc_hamming(TcArgs p)
         }
         const uint16_t *bcol = nullptr;
         if (MODE == TC_SHORT) {
-            live = row_ok && p.row_need[ro + row];
+            live = row_ok && (p.a_index || p.row_need[ro + row]);
             bcol = p.b_index ? p.b_index + (size_t)f * p.b_index_stride : nullptr;
         }
         if (MODE == TC_SCORES && !live) grow = INT_MAX;                // a dead row takes nothing
@@ -435,32 +438,29 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tc_hamming(TcArgs p)
                         }
                     }
                 } else if (MODE == TC_SHORT) {
-                    // every column with d < 60 goes to the row's segment of this stream, in scan (= ascending) order.
-                    // Most chunks hold no hit for any of the warp's 32 rows (a hit is a true match, not noise: d < 60 lies
-                    // 8 sigma below the mean distance of unrelated descriptors), so the chunk's maximum (16 instructions)
-                    // decides first; only when some row has a hit: a straight-line hit mask (2 instructions per column),
-                    // then the set bits are visited — their distance comes from the spilled low bytes, their column from
-                    // the chunk's slice of the gathered column list.  Padding columns of the last tile (dot product 0) can
-                    // only make the guard fire needlessly; the mask drops them.
-                    const int mx = max32(v);
-                    if (__any_sync(0xffffffffu, live && mx > thr_dot)) {
-                        int mycol = j0 + lane;                         // the column behind position j0 + lane of the gathered list
-                        if (bcol && j0 + lane < nB) mycol = bcol[j0 + lane];
-                        uint32_t mask = 0;
+                    // every column with d < 60 goes to the row's segment of this stream, in scan (= ascending) order: a
+                    // straight-line hit mask (2 instructions per column), then only the set bits are visited; their distance
+                    // comes from the spilled low bytes, their column from the chunk's slice of the gathered column list.
+                    // (Deciding per chunk on its maximum first — 16 instructions, then a vote — and building the mask only
+                    // when some row has a hit lowers the instruction count but not the time: 26.6 k against 26.8 k frames/s,
+                    // the kernel alone 128 against 116 us; the vote puts the TMEM load's latency on every chunk's critical
+                    // path.  profiles/r2_experiments.md)
+                    int mycol = j0 + lane;                             // the column behind position j0 + lane of the gathered list
+                    if (bcol && j0 + lane < nB) mycol = bcol[j0 + lane];
+                    uint32_t mask = 0;
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) mask |= (v[e] > thr_dot ? 1u : 0u) << e;
-                        if (nv < 32) mask &= (1u << nv) - 1u;
-                        if (!live) mask = 0;
-                        __syncwarp();
-                        spill_low_bytes(ct, lane, v);
-                        ct[256 + lane] = mycol;
-                        __syncwarp();
-                        while (mask) {
-                            const int e = __ffs((int)mask) - 1;
-                            mask &= mask - 1;
-                            if (cnt < SVO_TC_SEG) *tc_short_slot(g, ro + row, q * SVO_TC_SEG + cnt) = (hit_distance(ct, lane, e) << 16) | (uint32_t)ct[256 + e];
-                            ++cnt;
-                        }
+                    for (int e = 0; e < 32; ++e) mask |= (v[e] > thr_dot ? 1u : 0u) << e;
+                    if (nv < 32) mask &= (1u << nv) - 1u;
+                    if (!live) mask = 0;
+                    __syncwarp();
+                    spill_low_bytes(ct, lane, v);
+                    ct[256 + lane] = mycol;
+                    __syncwarp();
+                    while (mask) {
+                        const int e = __ffs((int)mask) - 1;
+                        mask &= mask - 1;
+                        if (cnt < SVO_TC_SEG) *tc_short_slot(g, ro + row, q * SVO_TC_SEG + cnt) = (hit_distance(ct, lane, e) << 16) | (uint32_t)ct[256 + e];
+                        ++cnt;
                     }
                 }
             }
@@ -516,10 +516,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tc_hamming(TcArgs p)
         }
         if (MODE == TC_SHORT) {
             // per-stream segment lengths, one byte each (k_merge_prune_lists joins the segments, ascending by construction)
+            const int mrow = p.a_index ? p.a_index[ro + row] : row;              // rows outside a gathered list keep the 0 of k_greedy_init
             uint32_t packed = 0;
-            if (p.row_need[ro + row])
+            if (p.a_index || p.row_need[ro + row])
                 for (int q = 0; q < TC_STREAMS; ++q) packed |= (uint32_t)comb[(q * TC_M + tid) * 3] << (8 * q);
-            g.short_cnt[ro + row] = (int)packed;
+            g.short_cnt[ro + mrow] = (int)packed;
         }
     }
     if (tid == 0) TC_STAMP(3, 4);
