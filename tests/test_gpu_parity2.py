@@ -495,6 +495,35 @@ def test_both_fast_band_heights_give_the_same_corners(svo, band):
         c.close()
 
 
+@pytest.mark.parametrize("var", ["SVO_B200_RESIZE_QUADS", "SVO_B200_HARRIS8", "SVO_B200_BLUR_MARGIN", "SVO_B200_BLUR_PACK"])
+def test_previous_kernel_forms_stay_exact(svo, var):
+    """The kernels the instruction-count work replaced stay in the library behind switches (k_resize for levels whose taps do
+    not fit k_resize_q's window, k_harris, k_blur<false>, evenly split blur tiles): with one switched back, pyramid and blur
+    bytes, the Harris-ranked second cull and the extractor on top equal the oracle's, for a KITTI-shape and an odd-sized image."""
+    import os
+    os.environ[var] = "0"
+    try:
+        for shape, nf in (((376, 1241), 2000), ((203, 317), 300)):
+            img = synth.texture(shape, 23 + nf)
+            c = svo.Context(shape[1], shape[0], nfeatures=nf, max_batch=1, lanes=1, max_rows=1000)
+            try:
+                kp, desc = c.extract(img)
+                ref, rdesc, pyr = O.orb(img, nf, with_pyramid=True)
+                for l in range(8):
+                    assert (c.tap_image(0, l) == pyr.level(l)).all(), (var, shape, l)
+                    lh, lw = pyr.level(l).shape
+                    if lh > 62 and lw > 62:      # the oracle blurs only levels that can hold a keypoint (31-px border on each side)
+                        assert (c.tap_image(0, l, blurred=True) == pyr.level(l, True)).all(), (var, shape, l)
+                O.pyramid_free(pyr)
+                assert len(kp) == len(ref) and (desc == rdesc).all()
+                for f in ("x", "y", "angle", "response", "octave"):
+                    assert (kp[f] == ref[f]).all(), (var, shape, f)
+            finally:
+                c.close()
+    finally:
+        del os.environ[var]
+
+
 @pytest.mark.parametrize("nl,sf,nf,shape", [(5, 1.3, 800, (376, 1241)), (3, 1.5, 300, (240, 400)), (8, 1.1, 1500, (376, 1241)),
                                             (1, 1.2, 200, (240, 400)), (6, 2.0, 400, (480, 640))])
 def test_other_level_counts_and_scale_factors(svo, nl, sf, nf, shape):
