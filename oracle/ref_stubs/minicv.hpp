@@ -144,6 +144,9 @@ public:
     template <typename T> const T *ptr(int r = 0) const { return reinterpret_cast<const T *>(data + (size_t)r * step); }
     template <typename T> T &at(int r, int c) { return reinterpret_cast<T *>(data + (size_t)r * step)[c]; }
     template <typename T> const T &at(int r, int c) const { return reinterpret_cast<const T *>(data + (size_t)r * step)[c]; }
+    // single index: element i of a row or column vector (src/Optimizer.cc:67-69 reads Xw.at<float>(k) of a 3x1)
+    template <typename T> T &at(int i) { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
+    template <typename T> const T &at(int i) const { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
     void setTo(const Scalar &s)
     {
         for (int r = 0; r < rows; ++r)

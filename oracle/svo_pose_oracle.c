@@ -17,11 +17,15 @@
  *       oplus, exp, product       types/types_six_dof_expmap.h:73-76, types/se3quat.h:100-113,217-249,274-279
  *       dense solve               solvers/linear_solver_dense.h:63-115 (Eigen::LDLT)
  *       cv::Mat <-> SE3Quat       src/convert.cc:6-17,49-63
- *     g2o cannot be compiled here (it needs Eigen, not installed), so Eigen's pieces are restated
- *     from its published algorithms: Quaterniond(Matrix3d), quaternion * vector, quaternion
- *     product, toRotationMatrix, pivoted LDLT.  PARITY: unpinned against a built g2o; the test
- *     suite checks the restatement against closed-form properties (exact data -> exact pose,
- *     chi2 never increases, Huber limits) and the GPU kernel against this file within 1e-6.
+ *     Eigen is not installed here, so Eigen's pieces are restated from its published algorithms:
+ *     Quaterniond(Matrix3d), quaternion * vector, quaternion product, toRotationMatrix, LDLT.
+ *     PARITY: PINNED to the reference's own code — oracle/_ref/libsvo_ref_g2o.so is src/Optimizer.cc,
+ *     src/convert.cc and the vendored g2o compiled UNMODIFIED (oracle/Makefile `ref_g2o`, against the
+ *     stand-in Eigen header oracle/ref_stubs_g2o/minieigen.hpp), and tests/test_ref_pin_pose.py finds
+ *     the float32 pose Optimizer::PoseOptimization stores equal to this file's bit for bit (6-500
+ *     points, outliers, perturbed starts); tests/golden/ref_pose.npz records those answers.  The test
+ *     suite also checks closed-form properties (exact data -> exact pose, chi2 never increases, Huber
+ *     limits) and the GPU kernel against this file within 1e-6.
  *
  * (2) svo_o_pnp_ransac — the role of cv::solvePnPRansac(pts3d, pts2d, K, noDist, rvec, tvec, false,
  *     100, 8.0, 0.99, inliers) at src/pnpmatch.cc:227.  OpenCV is un-vendored and its RANSAC

@@ -109,6 +109,17 @@ def test_pose_optimize_matches_oracle_batch(ctx):
             assert its == io or iters == 10, (len(q["pts3d"]), iters, its, io)
 
 
+def test_pose_optimize_against_the_references_recorded_poses(ctx):
+    """tests/golden/ref_pose.npz holds what the reference's OWN Optimizer::PoseOptimization (src/Optimizer.cc + the vendored
+    g2o, compiled unmodified: oracle/_ref/libsvo_ref_g2o.so, tests/golden/make_golden_ref_pose.py) stored with SetPose;
+    the oracle reproduces those float32 poses bit for bit (tests/test_ref_pin_pose.py), the kernel to the tolerance above."""
+    z = np.load(os.path.join(G, "ref_pose.npz"))
+    pr = [dict(pts3d=z["Xw%d" % i], pts2d=z["obs%d" % i], K=z["K%d" % i], Tcw=z["T0_%d" % i]) for i in range(int(z["n_problems"]))]
+    res = ctx.pose_optimize(pr)
+    for i, (T, its, chi) in enumerate(res):
+        assert np.abs(T - z["Tref%d" % i]).max() < 1e-5, i
+
+
 def test_pose_optimize_from_identity_and_after_ransac(ctx):
     pr = problems([(1000, 50, 0.3, 0.5), (1000, 51, 0.0, 0.0)])
     for q in pr:
