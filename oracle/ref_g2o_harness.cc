@@ -6,9 +6,18 @@
 #include <frame.h>
 #include <mappoint.h>
 #include <Optimizer.h>
+#include <Tracking.h>
+#include <view.h>
+#include "Thirdparty/MB/MSA.h"
 
 #include <cstring>
+#include <fstream>
 #include <vector>
+
+// The viewer (src/view.cc: Pangolin / OpenGL drawing) is out of scope and not compiled; Tracking::SaveTrajectoryAndDraw
+// calls it once per frame.
+void View::DrawGraph(frame &, frame *) {}
+void View::DrawMappoints(set<mappoint *> &, int) {}
 
 extern "C" {
 
@@ -42,6 +51,42 @@ int ref_pose_optimize(const float *Tcw16, int n, const float *xy, const float *X
     const int r = Optimizer::PoseOptimization(f);                     // src/Optimizer.cc:15-86
     std::memcpy(Tcw_out16, f->Tcw.data, 64);
     return r;
+}
+
+// ---- Tracking::Track itself (src/Tracking.cc:180-252, compiled unmodified) -------------------------------------------
+// settings: a YAML file with Camera.fx / fy / cx / cy / bf (Tracking::Tracking reads it, src/Tracking.cc:22-39).
+void *ref_tracking_new(const char *settings)
+{
+    Tracking::frame_num = 0;                 // process-wide statics of the reference (src/Tracking.cc:18-19)
+    Tracking::LocalMapPoints.clear();
+    return new Tracking(std::string(settings));
+}
+void ref_tracking_free(void *t) { delete (Tracking *)t; }
+// One call of Tracking::Track.  disp: the dense disparity image frame::MB's solver returns for this pair (the MSA solver
+// itself is out of scope, ref_stubs/Thirdparty/MB/MSA.h); images 8-bit, ch channels.
+void ref_tracking_track(void *t, const unsigned char *L, const unsigned char *R, int w, int h, int ch, const float *disp,
+                        const float *K9, float bf, double ts, const int *boxes, int nboxes)
+{
+    cv::Mat l(h, w, CV_MAKETYPE(CV_8U, ch)), r(h, w, CV_MAKETYPE(CV_8U, ch)), none, K(3, 3, CV_32F), d(h, w, CV_32F);
+    std::memcpy(l.data, L, (size_t)w * h * ch); std::memcpy(r.data, R, (size_t)w * h * ch);
+    std::memcpy(d.data, disp, sizeof(float) * (size_t)w * h);
+    for (int i = 0; i < 9; ++i) K.at<float>(i / 3, i % 3) = K9[i];
+    cv::Mat det = l.clone();
+    minicv_next_disparity() = d;
+    std::vector<std::vector<int> > bx;
+    for (int k = 0; k < nboxes; ++k) bx.push_back(std::vector<int>(boxes + 4 * k, boxes + 4 * k + 4));
+    std::ofstream f("/dev/null"), f2("/dev/null");
+    pangolin::OpenGlMatrix M;
+    ((Tracking *)t)->Track(l, r, none, det, ts, K, bf, f, f2, M, bx);
+}
+void *ref_tracking_current(void *t) { return ((Tracking *)t)->currentframe; }
+void *ref_tracking_last(void *t) { return &((Tracking *)t)->lastframe; }
+void *ref_tracking_localmap() { return &Tracking::LocalMapPoints; }
+int ref_tracking_frame_num() { return Tracking::frame_num; }
+void ref_tracking_velocity(void *t, float *V16)
+{
+    const cv::Mat &V = ((Tracking *)t)->Velocity;
+    if (!V.empty()) for (int i = 0; i < 16; ++i) V16[i] = V.at<float>(i / 4, i % 4);
 }
 
 }

@@ -26,11 +26,20 @@ cv::Mat K_from(const float *K9)
 }
 // a map point is named by (id of the frame that created it, keypoint index there): AddObservation(this, i) is the
 // first observation it gets (src/frame.cc:229-231)
+// When Tracking::Track itself runs (oracle/ref_g2o_harness.cc), createmappoint is called on Tracking::lastframe, ONE object
+// that is re-assigned every frame: the creating observation of such a point is keyed by that object's address, whose id
+// moves on (and AddObservation ignores every later observation from the same address, src/mappoint.cc:19-20).  The
+// harness is told the address and reads the creating index from that entry.
+frame *g_alias_frame = nullptr;
 void name_of(mappoint *mp, int *create_id, int *idx)
 {
     *create_id = mp->create_id; *idx = -1;
     for (auto &ob : mp->observations)
-        if (ob.first->id == mp->create_id) { *idx = ob.second; break; }
+        if (ob.first->id == mp->create_id) { *idx = ob.second; return; }
+    if (g_alias_frame) {
+        auto it = mp->observations.find(g_alias_frame);
+        if (it != mp->observations.end()) *idx = it->second;
+    }
 }
 }  // namespace
 
@@ -41,6 +50,8 @@ void ref_set_hooks(cv::minicv_orb_fn orb, cv::minicv_fund_fn fund, cv::minicv_pn
     cv::MiniCvHooks &h = cv::minicv_hooks();
     h.orb = orb; h.fund = fund; h.pnp = pnp; h.rodrigues = rod;
 }
+
+void ref_set_alias_frame(void *f) { g_alias_frame = (frame *)f; }
 
 int ref_descriptor_distance(const uint8_t *a, const uint8_t *b)
 {

@@ -16,7 +16,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <iostream>
+#include <map>
 #include <memory>
 #include <sstream>
 #include <string>
@@ -408,6 +410,39 @@ public:
     void setDisp12MaxDiff(int) {} void setMode(int) {}
     void compute(const Mat &, const Mat &, Mat &) {}
 };
+// cv::FileStorage(path, READ)["Camera.fx"] as src/Tracking.cc:24-38 uses it: "key: number" lines of an OpenCV YAML file
+class FileNode {
+    double v_;
+public:
+    explicit FileNode(double v = 0) : v_(v) {}
+    operator float() const { return (float)v_; }
+    operator double() const { return v_; }
+    operator int() const { return (int)v_; }
+};
+class FileStorage {
+    std::map<std::string, double> kv_;
+    bool ok_;
+public:
+    enum { READ = 0, WRITE = 1 };
+    FileStorage(const std::string &path, int) : ok_(false)
+    {
+        std::ifstream f(path.c_str());
+        std::string line;
+        while (std::getline(f, line)) {
+            const size_t c = line.find(':');
+            if (c == std::string::npos || line[0] == '%' || line[0] == '#') continue;
+            char *end = nullptr;
+            const std::string val = line.substr(c + 1);
+            const double d = std::strtod(val.c_str(), &end);
+            if (end != val.c_str()) { kv_[line.substr(0, c)] = d; ok_ = true; }
+        }
+    }
+    bool isOpened() const { return ok_; }
+    FileNode operator[](const std::string &k) const { auto it = kv_.find(k); return FileNode(it == kv_.end() ? 0.0 : it->second); }
+    FileNode operator[](const char *k) const { return (*this)[std::string(k)]; }
+    void release() {}
+};
+
 }  // namespace cv
 
 // legacy C struct used by include/YOLOv3SE.h (not on the path)
