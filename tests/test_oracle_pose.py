@@ -1,7 +1,8 @@
 """CPU checks of the pose-stage oracle (oracle/svo_pose_oracle.c).
 
 * svo_o_pose_optimize restates Optimizer::PoseOptimization (src/Optimizer.cc:15-86) from the vendored g2o
-  sources; g2o cannot be built here (no Eigen), so the restatement is checked through properties:
+  sources.  It is pinned bit for bit to the reference's own build of that function in tests/test_ref_pin_pose.py
+  (and against recorded vectors in tests/test_oracle_golden_pose.py); here it is checked through properties:
   exact data gives the exact pose, the robust cost never increases and ends at a stationary point of the
   Huber cost (gradient computed independently in numpy), zero edges leave the pose alone.
 * svo_o_pnp_ransac DEFINES the data-parallel stand-in for cv::solvePnPRansac (src/pnpmatch.cc:227); it is
