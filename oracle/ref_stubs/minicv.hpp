@@ -10,6 +10,7 @@
 // and no-op drawing / GUI calls (cv::circle, cv::line, imshow, waitKey — SURVEY.md Appendix D).
 #pragma once
 #include <algorithm>
+#include <cassert>
 #include <climits>
 #include <cmath>
 #include <cstdint>
@@ -57,6 +58,13 @@ template <typename T> struct Point3_ {
     Point3_(T x_, T y_, T z_) : x(x_), y(y_), z(z_) {}
 };
 typedef Point3_<float> Point3f;
+struct Vec3b {                      // Thirdparty/MB/MSA.cpp paints a debug image through at<Vec3b>
+    unsigned char val[3];
+    Vec3b() { val[0] = val[1] = val[2] = 0; }
+    Vec3b(int a, int b, int c) { val[0] = (unsigned char)a; val[1] = (unsigned char)b; val[2] = (unsigned char)c; }
+    unsigned char &operator[](int i) { return val[i]; }
+    const unsigned char &operator[](int i) const { return val[i]; }
+};
 template <typename T> struct Size_ {
     T width, height;
     Size_() : width(0), height(0) {}
@@ -399,6 +407,7 @@ inline void line(const Mat &, Point2f, Point2f, const Scalar &, int = 1) {}
 inline void imshow(const std::string &, const Mat &) {}
 inline int waitKey(int = 0) { return -1; }
 inline Mat imread(const std::string &, int = 1) { return Mat(); }
+inline bool imwrite(const std::string &, const Mat &) { return true; }
 
 // frame::ElasMatch (never called, src/Tracking.cc:226 uses MB) still has to compile
 class StereoSGBM {
