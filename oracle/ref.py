@@ -26,6 +26,10 @@ PNP_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_in
 ROD_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double))
 
 LOG = {"fundamental": [], "pnp": []}     # what the hooks saw / returned, for the tests
+# Tests that need hand-made feature sets (adversarial descriptor chains, ties, thresholds) set this to a callable
+# (img, what) -> (n x 7 float32 keypoints, n x 32 uint8 descriptors) that answers the reference's cv::ORB calls instead
+# of cv2; what = 0 detectAndCompute, 1 detect, 2 compute (the keypoints handed in are the ones it returned for 1).
+ORB_OVERRIDE = None
 
 
 def available():
@@ -47,6 +51,16 @@ def _image(ptr, rows, cols, step, ch):
 def _orb_hook(ptr, rows, cols, step, ch, what, kps, desc, cap, n_in):
     import cv2
     img = _image(ptr, rows, cols, step, ch)
+    if ORB_OVERRIDE is not None:
+        k7, d = ORB_OVERRIDE(img, what)
+        n = len(k7)
+        assert n <= cap and (what != 2 or n == n_in)
+        flat = np.ascontiguousarray(k7, np.float32).reshape(-1)
+        for i in range(7 * n):
+            kps[i] = flat[i]
+        if what != 1 and n:
+            C.memmove(desc, np.ascontiguousarray(d, np.uint8).ctypes.data, n * 32)
+        return n
     orb = cv2.ORB_create()                       # cv::ORB::create(): src/frame.cc:77, src/pnpmatch.cc:261-262
     if what == 0:
         k, d = orb.detectAndCompute(img, None)

@@ -44,8 +44,10 @@ def test_descriptor_distance_is_the_oracles():
     assert R.descriptor_distance(np.zeros(32, np.uint8), np.full(32, 255, np.uint8)) == 256
 
 
-def replay_with_oracle(run, boxes):
-    """The oracle's pass 1 (+ veto) and pass 2 on the inputs the reference saw; pass 2 in the set's own order."""
+def replay_with_oracle(run, boxes, matcher=None):
+    """The oracle's pass 1 (+ veto) and pass 2 on the inputs the reference saw; pass 2 in the set's own order.
+    matcher: another implementation with O.match_greedy's signature (the GPU tests pass svo.Context.match_greedy)."""
+    match_greedy = matcher or O.match_greedy
     last0, map0 = run["before"]["last"], run["before"]["map"]
     cur, last = run["cur"], run["last"]
     M = last0["N"]
@@ -55,21 +57,21 @@ def replay_with_oracle(run, boxes):
     # find_feature_matches overwrote both frames' keypoints_l with a second ORB pass (src/pnpmatch.cc:306): the veto
     # reads those (they are the same keypoints: detect+compute == detectAndCompute)
     veto = dict(boxes=boxes, F=run["F"]["F"], row_xy=last["kps"][:M, :2], cur_xy=cur["kps"][:, :2]) if len(boxes) else None
-    p1 = O.match_greedy(rows, cur["desc"], 0, row_live=live, veto=veto)
+    p1 = match_greedy(rows, cur["desc"], 0, row_live=live, veto=veto)
     order = [(int(c), int(i)) for c, i in zip(map0["create_id"], map0["idx"])]
     assert all(c == 0 for c, _ in order)
     idx2 = np.array([i for _, i in order], np.int64)
     live2 = np.ones(len(idx2), np.uint8)
     live2[p1["row_bad"][idx2] == 1] = 0               # mp->bad (src/pnpmatch.cc:163)
     live2[p1["row_claimed"][idx2] == 1] = 0           # observations.count(CurrentFrame) (:165)
-    p2 = O.match_greedy(map0["desc"], cur["desc"], 1, claimed=p1["claimed"], claim_row=p1["claim_row"], row_live=live2,
-                        row_base=10 ** 6)
+    p2 = match_greedy(map0["desc"], cur["desc"], 1, claimed=p1["claimed"], claim_row=p1["claim_row"], row_live=live2,
+                      row_base=10 ** 6)
     return live, p1, idx2, p2
 
 
-def check_run(run, boxes):
+def check_run(run, boxes, matcher=None):
     cur, last = run["cur"], run["last"]
-    live, p1, idx2, p2 = replay_with_oracle(run, boxes)
+    live, p1, idx2, p2 = replay_with_oracle(run, boxes, matcher)
     M = len(live)
     # pass 1: match_score (src/pnpmatch.cc:99), bad flags (:141), claims (:151)
     lv = live.astype(bool)
