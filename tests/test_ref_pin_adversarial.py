@@ -79,3 +79,38 @@ def test_gpu_matchers_follow_the_recorded_reference_decisions(seed):
         check_case(seed, A.CASES[seed], A.unpack_run(np.load(GOLDEN), "c%d." % seed), matcher=ctx.match_greedy)
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("seed", sorted(A.CASES))
+def test_bf_matcher_on_adversarial_sets_is_cv2s(seed):
+    """cv::BFMatcher(NORM_HAMMING)::match as src/pnpmatch.cc:278 calls it, on the hand-made sets: a query with twenty
+    identical train rows at distance 0 takes the first; the filter threshold is max(2 * 0, 30) = 30 (:291-299)."""
+    import cv2
+    from oracle import oracle as O
+    (_, d_last), (_, d_cur) = A.feature_sets(seed)
+    m = cv2.BFMatcher(cv2.NORM_HAMMING).match(d_cur, d_last)
+    idx, dist, keep = O.match_bf(d_cur, d_last)
+    assert [x.queryIdx for x in m] == list(range(len(d_cur)))
+    assert (np.array([x.trainIdx for x in m]) == idx).all() and (np.array([x.distance for x in m]) == dist).all()
+    assert dist.min() == 0 and (keep == (dist <= 30)).all() and 0 < keep.sum() < len(keep)
+    assert (idx[(d_cur == d_last[0]).all(1)] == 0).all()           # the chain's columns all name the FIRST identical row
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref cannot be built here (/root/reference absent)")
+@pytest.mark.parametrize("seed", [0, 3])
+def test_F_inputs_on_adversarial_sets(seed):
+    """poseEstimation2D_2D (src/pnpmatch.cc:302-337) on the hand-made sets: the point pairs the reference hands to
+    findFundamentalMat are the oracle's filtered BF matches minus current keypoints inside a box grown by 10 px."""
+    from oracle import oracle as O
+    boxes = A.CASES[seed]
+    run = A.run_reference(seed, boxes, K, BF)
+    cur, last = run["cur"], run["last"]
+    idx, dist, keep = O.match_bf(cur["desc"], last["desc"])
+    q = np.nonzero(keep)[0]
+    x, y = cur["kps"][q, 0], cur["kps"][q, 1]
+    inside = np.zeros(len(q), bool)
+    for b in boxes:
+        inside |= (x > b[0] - 10) & (x < b[1] + 10) & (y > b[2] - 10) & (y < b[3] + 10)
+    q = q[~inside]
+    assert np.array_equal(cur["kps"][q, :2], run["F"]["p1"]) and np.array_equal(last["kps"][idx[q], :2], run["F"]["p2"])
+    assert len(q) >= 8 and (not boxes or inside.any())
