@@ -127,3 +127,61 @@ def unpack_run(g, prefix):
         else:
             run[path] = node
     return run
+
+
+def sequence_sets(seed, n):
+    """n frames of 500 hand-made features for the tracker pins: every frame re-observes most of the previous frame's
+    descriptors (0-3 bits flipped, shuffled positions in the descriptor matrix), brings back descriptors of two and three
+    frames ago with ~20 bits flipped (pass-2 material: best < 30, ratio > 2 against everything else), carries a block of
+    identical descriptors (a claim chain in both passes), and fills up with fresh random rows."""
+    rng = np.random.default_rng(1000 + seed)
+    N = 500
+    sets = []
+    for t in range(n):
+        d = rng.integers(0, 256, (N, 32), dtype=np.uint8)
+        slots = iter(rng.permutation(N))
+        if t > 0:
+            prev = sets[t - 1][1]
+            for r in rng.choice(N, 280, replace=False):
+                d[next(slots)] = at_distance(rng, prev[r], int(rng.integers(0, 4)))
+            for back in (2, 3):
+                if t >= back:
+                    old = sets[t - back][1]
+                    for r in rng.choice(N, 40, replace=False):
+                        d[next(slots)] = at_distance(rng, old[r], int(rng.integers(16, 29)))
+        chain = (sets[0][1][7] if t else d[7]).copy()          # the same block value in every frame
+        for _ in range(10):
+            d[next(slots)] = chain
+        k = keypoints(rng, N)
+        k[:, 0] += rng.uniform(-2, 2, N).astype(np.float32) - 2.0 * t
+        k[:, 1] += rng.uniform(-1.5, 1.5, N).astype(np.float32)
+        sets.append((k, d))
+    return sets
+
+
+def run_reference_sequence(seed, n, boxes_of, K, bf, runner=None, **kw):
+    """The hand-made sequence through the reference's frame loop (oracle/ref.py:run_sequence by default; pass
+    oracle.ref_g2o.run_tracking + tmpdir for Tracking::Track itself)."""
+    from oracle import ref as R
+    sets = sequence_sets(seed, n)
+    imgs = []
+    for t in range(n):
+        im = np.full(SHAPE, 128, np.uint8); im[0, 0] = 10 + t
+        imgs.append(im)
+
+    def orb(img, what):
+        return sets[int(img.reshape(img.shape[0], -1)[0, 0]) - 10]
+
+    disp = np.full(SHAPE, 10, np.float32)
+    mods = [R]
+    if runner is not None:
+        from oracle import ref_g2o as RG
+        mods.append(RG._ref_module())                          # the module instance bound to libsvo_ref_g2o.so
+    for m in mods:
+        m.ORB_OVERRIDE = orb
+    try:
+        run = runner or R.run_sequence
+        return run([(im, im) for im in imgs], [disp] * n, K, bf, [boxes_of(t) for t in range(n)], **kw)
+    finally:
+        for m in mods:
+            m.ORB_OVERRIDE = None

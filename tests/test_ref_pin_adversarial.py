@@ -114,3 +114,37 @@ def test_F_inputs_on_adversarial_sets(seed):
     q = q[~inside]
     assert np.array_equal(cur["kps"][q, :2], run["F"]["p1"]) and np.array_equal(last["kps"][idx[q], :2], run["F"]["p2"])
     assert len(q) >= 8 and (not boxes or inside.any())
+
+
+# ---- the tracker oracle (oracle/track.py) over hand-made SEQUENCES through the reference's frame loop -----------------
+
+def _track_check(recs, boxes_of):
+    from test_oracle_track import check, replay
+    return check(recs, replay(recs, boxes_of))
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref cannot be built here (/root/reference absent)")
+@pytest.mark.parametrize("seed,with_boxes", [(0, False), (1, True)])
+def test_tracker_oracle_on_hand_made_sequences(seed, with_boxes):
+    """Seven frames of hand-made features (tests/adversarial_sets.py:sequence_sets) through the reference's frame loop:
+    re-observed points, points coming back after two and three frames (pass 2), a block of identical descriptors in every
+    frame (claim chains in both passes), the 4-frame window — every frame's MapPoints, match_score, bad flags, created
+    points and local map equal the tracker oracle's."""
+    boxes_of = (lambda t: [[200, 700, 60, 250]] if t % 2 else [[900, 1100, 0, 200]]) if with_boxes else (lambda t: [])
+    recs = A.run_reference_sequence(seed, 7, boxes_of, K, BF)
+    n_bad, n_p1, n_p2 = _track_check(recs, boxes_of)
+    assert n_p1 > 600 and n_p2 > 60, (n_p1, n_p2)
+    assert (n_bad > 0) == with_boxes
+    assert sum(r["erased"] for r in recs) > 100
+
+
+def test_tracker_oracle_on_a_hand_made_sequence_through_tracking_track(tmp_path):
+    """The same through Tracking::Track itself (src/Tracking.cc compiled unmodified, oracle/_ref/libsvo_ref_g2o.so):
+    Tracking::init, poseEstimationPnP, Optimizer::PoseOptimization, createmappoint and the window as main.cpp drives them."""
+    from oracle import ref_g2o as RG
+    if not RG.available():
+        pytest.skip("/root/reference (or a prebuilt oracle/_ref/libsvo_ref_g2o.so) is not present")
+    boxes_of = lambda t: [[200, 700, 60, 250]] if t % 2 else []
+    recs = A.run_reference_sequence(2, 6, boxes_of, K, BF, runner=RG.run_tracking, tmpdir=tmp_path)
+    n_bad, n_p1, n_p2 = _track_check(recs, boxes_of)
+    assert n_p1 > 500 and n_p2 > 40 and n_bad > 0, (n_bad, n_p1, n_p2)
