@@ -134,6 +134,7 @@ def lib():
         hooks = (ORB_FN(_orb_hook), FUND_FN(_fund_hook), PNP_FN(_pnp_hook), ROD_FN(_rod_hook))
         _KEEP.extend(hooks)
         L.ref_set_hooks(*hooks)
+        L._svo_hooks = hooks
         L.ref_frame_new.restype = C.c_void_p
         L.ref_frame_new.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p,
                                     C.c_int, C.c_double, C.c_long]
@@ -161,6 +162,15 @@ def lib():
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def activate():
+    """(Re-)install THIS module instance's hooks.  oracle/ref_g2o.py binds a second instance of this module to another
+    library; if the two libraries ever shared their hook table (a GNU_UNIQUE symbol — the recipe builds with
+    -fno-gnu-unique so that they do not) the instance loaded last would answer both, and its LOG would get the records."""
+    L = lib()
+    L.ref_set_hooks(*L._svo_hooks)
+    return L
 
 
 def descriptor_distance(a, b):
@@ -263,6 +273,7 @@ def run_two_frames(frames, disps, K, bf, boxes, pose0=None):
     (src/Tracking.cc:184, :225-238, :114).  frames = ((L0, R0), (L1, R1)); disps = the dense disparity images standing
     in for frame::MB's output.  Returns everything the pin tests and the golden fixtures compare."""
     (L0, R0), (L1, R1) = frames
+    activate()
     LOG["fundamental"].clear(); LOG["pnp"].clear()
     f0 = Frame(L0, R0, K, bf, boxes, 0.0, 0)
     if pose0 is not None:
@@ -289,6 +300,7 @@ def run_sequence(frames, disps, K, bf, boxes_per_frame):
     here) only refines the pose and is left out: nothing on the matching path reads it.
     Returns one record per frame: the current frame's state after the matching, the fundamental matrix it used, the last
     frame's state and the local map (in the set's own order) after createmappoint + ageing."""
+    activate()
     lm = LocalMap()
     last = None
     out = []

@@ -89,7 +89,7 @@ def run_tracking(frames, disps, K, bf, boxes_per_frame, tmpdir):
     Optimizer::PoseOptimization), GetVelocity, lastframe = frame(currentframe), createmappoint, the 4-frame window.
     Returns records shaped like oracle/ref.py:run_sequence's (which restates that loop in its harness)."""
     RR = _ref_module()
-    L = RR.lib()
+    L = RR.activate()
     Kf = np.ascontiguousarray(K, np.float32).reshape(3, 3)
     path = os.path.join(str(tmpdir), "settings.yaml")
     with open(path, "w") as f:
