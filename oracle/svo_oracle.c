@@ -58,8 +58,13 @@ void svo_o_geometry(int W, int H, int nlevels, float scale_factor_f, int nfeatur
     for (int l = 0; l < nlevels; ++l) {
         float s = (float)pow(scale_factor, (double)l);
         lscale[l] = s;
-        lw[l] = cv_round_f((float)W / s);
-        lh[l] = cv_round_f((float)H / s);
+        /* cvRound(image.cols / scale): the OpenCV build this oracle is pinned to (cv2 4.13.0) evaluates the quotient as a
+         * float multiplication by the reciprocal of the scale, which differs from the true quotient only when cols / scale
+         * falls within a float ulp of k + 0.5 — at 1.2 every level of 140 of the dimensions below 4096 (249 -> 208, not
+         * 207); found by tools/fuzz_orb_cv2.py, rule fitted on 34 probed sizes, none of KITTI's is among them. */
+        volatile float inv = 1.0f / s;
+        lw[l] = cv_round_f((float)W * inv);
+        lh[l] = cv_round_f((float)H * inv);
     }
     float factor = (float)(1.0 / scale_factor);
     float ndes = (float)nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));

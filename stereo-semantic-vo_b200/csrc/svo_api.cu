@@ -175,15 +175,19 @@ int halloc(svo_ctx *ctx, T **p, size_t n)
 inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 // cv::ORB geometry: float scale = (float)pow((double)scaleFactor, l), sizes by
-// cvRound(cols/scale), quotas by the geometric series in float.
+// cvRound(cols * (1 / scale)), quotas by the geometric series in float.
 void orb_geometry(int W, int H, int nlevels, float scale_factor_f, int nfeatures, int *lw, int *lh, float *ls, int *quota)
 {
     const double sf = (double)scale_factor_f;
     for (int l = 0; l < nlevels; ++l) {
         const float s = (float)pow(sf, (double)l);
         ls[l] = s;
-        lw[l] = (int)lrintf((float)W / s);
-        lh[l] = (int)lrintf((float)H / s);
+        // cvRound(cols / scale) as the OpenCV build the parity oracle is pinned to (4.13.0) evaluates it: a float
+        // multiplication by the reciprocal.  Differs from the quotient only where cols / scale is within an ulp of k + 0.5
+        // (at 1.2: 140 of the dimensions below 4096, e.g. 249 -> 208; none of KITTI's)
+        volatile float inv = 1.0f / s;
+        lw[l] = (int)lrintf((float)W * inv);
+        lh[l] = (int)lrintf((float)H * inv);
     }
     const float factor = (float)(1.0 / sf);
     float ndes = (float)nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));

@@ -2,6 +2,8 @@
 single-call and the batch API, the batch pipeline at BASELINE configs[2] (1241x376 / 4000 features) and configs[3]
 (2560x720 / 8000 features) — where the free-column list no longer fits k_shortlist's tile, k_pairs runs more column
 tiles and the resolver stages 9088 columns —, KITTI's other image shapes, and the limits the API states."""
+import os
+
 import numpy as np
 import pytest
 
@@ -539,3 +541,26 @@ def test_other_level_counts_and_scale_factors(svo, nl, sf, nf, shape):
             assert (kp[f].view(np.uint32) == okp[f].view(np.uint32)).all(), f
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("shape,nf", [((181, 249), 200), ((297, 465), 600)])
+def test_extract_at_sizes_whose_level_rounding_sits_on_a_half(svo, shape, nf):
+    """249 / 1.2 = 207.5 - 8e-6: cv2 4.13 makes level 1 208 wide (cvRound of a float multiplication by the reciprocal of
+    the scale), the quotient rounds to 207 (tests/test_oracle_vs_cv2.py).  svo_extract against cv2's recorded output
+    (tests/golden/half_sizes.npz, make_golden_half_sizes.py) and the oracle; level geometry against the oracle's."""
+    h, w = shape
+    img = synth.texture(shape, 77)
+    c = svo.Context(w, h, nfeatures=nf, max_rows=1000)
+    try:
+        lw, lh, ls, q = c.geometry()
+        olw, olh, ols, oq = O.geometry(w, h, 8, 1.2, nf)
+        assert (lw == olw).all() and (lh == olh).all() and (q == oq).all()
+        assert lw[1] == {249: 208, 465: 388}[w] and lh[1] == {181: 151, 297: 248}[h]
+        kp, desc = c.extract(img)
+    finally:
+        c.close()
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "half_sizes.npz"))
+    for rkp, rdesc in ((g["kp_%dx%d" % (w, h)], g["desc_%dx%d" % (w, h)]), O.orb(img, nf)[:2]):
+        assert len(kp) == len(rkp) > 0 and (desc == rdesc).all() and (kp["octave"] == rkp["octave"]).all()
+        for f in ("x", "y", "size", "angle", "response"):
+            assert (kp[f].view(np.uint32) == rkp[f].view(np.uint32)).all(), f

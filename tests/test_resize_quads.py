@@ -31,7 +31,8 @@ def _level_sizes(w, h, nlevels, sf):
     out = []
     for l in range(nlevels):
         s = np.float32(np.float64(np.float32(sf)) ** l)
-        out.append((int(np.rint(np.float32(w) / s)), int(np.rint(np.float32(h) / s))))
+        inv = np.float32(1) / s                          # cvRound(cols * (1 / scale)), as orb_geometry (csrc/svo_api.cu)
+        out.append((int(np.rint(np.float32(w) * inv)), int(np.rint(np.float32(h) * inv))))
     return out
 
 
