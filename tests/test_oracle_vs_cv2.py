@@ -116,8 +116,8 @@ def test_orb_equals_cv2_at_sizes_on_a_half(shape, nf, nl):
 
 
 def test_a_slice_of_the_extraction_fuzz():
-    """tools/fuzz_orb_cv2.py (random sizes, feature counts, level counts, scale factors, image kinds): 600 seeds were run
-    when this was written — 8 diverged, all through the level-size rounding above, none since; 16 of them here, the eight
+    """tools/fuzz_orb_cv2.py (random sizes, feature counts, level counts, scale factors, image kinds): 2000 seeds were run
+    when this was written — 8 of the first 600 diverged, all through the level-size rounding above, none since; 16 of them here, the eight
     among them."""
     import os
     import sys

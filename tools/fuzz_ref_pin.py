@@ -4,6 +4,8 @@ positions — through the reference's own poseEstimationPnP, each run compared w
 tests/test_ref_pin.py.  Prints the seeds that diverge (none so far).
 
     python tools/fuzz_ref_pin.py [first_seed] [count]
+    python tools/fuzz_ref_pin.py --sequences [first_seed] [count]     # hand-made 8-frame sequences with random boxes through
+                                                                      # the reference's frame loop against oracle/track.py
 """
 import contextlib
 import os
@@ -85,7 +87,35 @@ def run(seed):
     return int(p1["row_claimed"].sum()), int(p1["row_bad"].sum()), int(p2["row_claimed"].sum())
 
 
+def run_sequence(seed, n=8):
+    """tests/adversarial_sets.py:sequence_sets with random boxes per frame; returns (vetoes, pass-1 claims, pass-2 claims)."""
+    from test_oracle_track import check, replay
+    rng = np.random.default_rng(seed)
+    bx = []
+    for _ in range(n):
+        b = []
+        for _ in range(int(rng.integers(0, 3))):
+            x0, y0 = int(rng.integers(0, 1000)), int(rng.integers(0, 250))
+            b.append([x0, x0 + int(rng.integers(50, 500)), y0, y0 + int(rng.integers(40, 250))])
+        bx.append(b)
+    boxes_of = lambda t: bx[t]
+    with quiet():
+        recs = A.run_reference_sequence(seed, n, boxes_of, K, BF)
+    return check(recs, replay(recs, boxes_of))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "--sequences":
+        first = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+        count = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+        bad, tot = [], np.zeros(3, np.int64)
+        for s in range(first, first + count):
+            try:
+                tot += run_sequence(s)
+            except AssertionError as e:
+                bad.append(s); print("seed", s, "DIVERGES:", str(e)[:300], file=sys.stderr)
+        print("sequences %d..%d: %d divergent %s; vetoed %d, pass-1 claims %d, pass-2 claims %d" % (first, first + count - 1, len(bad), bad, *tot))
+        sys.exit(0)
     first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     count = int(sys.argv[2]) if len(sys.argv) > 2 else 50
     bad = []
