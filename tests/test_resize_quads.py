@@ -49,7 +49,8 @@ def _run(model, src_img, dw, dh, rs):
 
 @pytest.mark.parametrize("w,h,nlevels,sf", [(1241, 376, 8, 1.2), (2560, 720, 8, 1.2), (1242, 375, 8, 1.2), (1226, 370, 8, 1.2),
                                             (400, 240, 8, 1.2), (317, 203, 6, 1.2), (640, 480, 5, 1.5), (640, 480, 4, 1.1),
-                                            (800, 600, 3, 1.9), (4095, 64, 3, 1.2)])
+                                            (800, 600, 3, 1.9), (4095, 64, 3, 1.2),
+                                            (249, 181, 6, 1.2), (465, 297, 8, 1.2), (558, 341, 8, 1.2)])   # level sizes on a half
 def test_quad_table_equals_cv2(model, w, h, nlevels, sf):
     rng = np.random.default_rng(w * 31 + h)
     sizes = _level_sizes(w, h, nlevels, sf)
