@@ -82,7 +82,12 @@ void svo_o_geometry(int W, int H, int nlevels, float scale_factor_f, int nfeatur
 /* ------------------------------------------------------------------ */
 void svo_o_resize_coeffs(int src, int dst, int *ofs, int *w1)
 {
-    double scale = (double)src / (double)dst;
+    /* OpenCV (resize.cpp, interpolationLinear) forms inv_scale = dst / src first and divides one by it: two roundings, not
+     * src / dst.  It matters only where a coefficient is an exact tie ((fv - iv) * 256 = k + 0.5 in exact arithmetic:
+     * v2(dst) - v2(src) = 8), e.g. 3993 -> 3328, the one transition among the pyramid chains of every image dimension up
+     * to 4095 at 1.2 where the two scales give different taps (found by sweeping tests/host_models' resize model). */
+    volatile double inv_scale = (double)dst / (double)src;
+    double scale = 1.0 / inv_scale;
     for (int d = 0; d < dst; ++d) {
         double fv = scale * ((double)d + 0.5) - 0.5;
         int iv = (int)floor(fv);

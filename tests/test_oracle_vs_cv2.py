@@ -129,3 +129,14 @@ def test_a_slice_of_the_extraction_fuzz():
         assert msg is None, msg
         total += n
     assert total > 5000
+
+
+@pytest.mark.parametrize("sw,dw", [(3993, 3328), (1971, 1792), (1037, 768), (1535, 768), (1151, 768), (961, 768)])
+def test_resize_coefficient_ties_follow_cv2(sw, dw):
+    """INTER_LINEAR_EXACT coefficients that are exact ties ((fv - iv) * 256 = k + 0.5: v2(dst) - v2(src) = 8) depend on how
+    the scale is formed; OpenCV divides one by dst / src.  3993 -> 3328 is the only such transition in the 1.2 pyramids of
+    image dimensions up to 4095; the others are the ones of scale factors 1.1, 1.35, 2.0, 1.5 and 1.25."""
+    rng = np.random.default_rng(sw)
+    img = rng.integers(0, 256, (40, sw), dtype=np.uint8)
+    assert (cv2.resize(img, (dw, 40), interpolation=cv2.INTER_LINEAR_EXACT) == O.resize(img, dw, 40)).all()
+    assert (cv2.resize(img.T.copy(), (40, dw), interpolation=cv2.INTER_LINEAR_EXACT) == O.resize(img.T.copy(), 40, dw)).all()
